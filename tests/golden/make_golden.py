@@ -1,0 +1,210 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference has no tests or golden vectors of its own,
+so these fixtures are outputs of the reference module itself
+(/root/reference/hwgat/models/HWGATE.py, model_params.py,
+losses/SmoothCrossEntropy.py), imported with a 3-line shim for the missing
+``timm`` package (only ``trunc_normal_`` at init, irrelevant because weights
+are loaded by state_dict).  Inputs and weights are not stored: they are
+regenerated from numpy PCG64 seeds by ``oracle.hwgate_oracle.make_state_dict``
+/ ``synthetic_keypoints``.  Large outputs are stored as a strided sample plus
+sums.  Everything is computed by the reference in float64 (``.double()``), so
+that the discontinuous threshold / ``== 0`` tests are reproducible.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/hwgat"
+
+
+def import_reference():
+    timm = types.ModuleType("timm")
+    timm_models = types.ModuleType("timm.models")
+    timm_layers = types.ModuleType("timm.models.layers")
+    timm_layers.trunc_normal_ = torch.nn.init.trunc_normal_
+    sys.modules.update({"timm": timm, "timm.models": timm_models, "timm.models.layers": timm_layers})
+    sys.path.insert(0, REF)
+    import importlib
+    hw = importlib.import_module("models.HWGATE")
+    mp = importlib.import_module("models.model_params")
+    sys.path.insert(0, os.path.join(REF, "losses"))
+    sce = importlib.import_module("SmoothCrossEntropy")
+    return hw, mp, sce
+
+
+class patched_rand:
+    """Make the reference's ``torch.rand(1).item()`` (HWGATE.py:96) return the
+    injected thresholds, in call order."""
+
+    def __init__(self, values):
+        self.values = list(values)
+        self.calls = 0
+
+    def __enter__(self):
+        self._orig = torch.rand
+
+        def fake(*a, **k):
+            v = self.values[self.calls]
+            self.calls += 1
+            return torch.tensor([v], dtype=torch.float64)
+
+        torch.rand = fake
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand = self._orig
+
+
+def sample(t, stride=7):
+    a = t.detach().double().reshape(-1).numpy()
+    return a[::stride].copy(), np.array([a.sum(), np.abs(a).sum(), float(a.size)])
+
+
+def build_ref_model(hw, mp, cfg, sd, drop=0.0):
+    from oracle import hwgate_oracle as O
+    params = mp.HWGATEParams({"num_class": cfg.num_classes, "src_len": cfg.temporal_dim}, cfg.kp_dim, "cpu")
+    params.drop_rate = drop
+    params.depths, params.num_heads = list(cfg.depths), list(cfg.num_heads)
+    params.embed_dim = cfg.embed_dim
+    model = hw.Model(*params.get_model_params())
+    missing = model.load_state_dict(sd, strict=True)
+    model = model.double()
+    for layer in model.layers:                       # adj_mat is a plain attribute (HWGATE.py:231)
+        layer.adj_mat = layer.adj_mat.double()
+        for blk in layer.blocks:
+            blk.attn.adj_mat = blk.attn.adj_mat.double()
+    return model, params
+
+
+def main():
+    from oracle import hwgate_oracle as O
+    hw, mp, sce = import_reference()
+    torch.manual_seed(0)
+    out = {}
+
+    # ---- 1. masks: reference float masks of every default block config, packed
+    params = mp.HWGATEParams({"num_class": 10, "src_len": 64}, 2, "cpu")
+    adj_ref = params.adj_mat.numpy()                                    # (4,32,32) float
+    out_m = {"adj": adj_ref.astype(np.uint8)}
+    for F in (64, 32, 16, 8, 4):
+        for shift in (0, 1):
+            blk = hw.PartAttentionBlock(dim=128, num_kps=64, num_heads=2, window_size=16,
+                                        temporal_patch_size=2, temporal_dim=F, shift_size=shift,
+                                        adj_mat=None)
+            full = torch.concatenate([params.adj_mat for _ in range(F // 2)])   # HWGATE.py:309
+            if blk.attn_mask is not None:
+                full = full * blk.attn_mask
+            bits = O.pack_mask_bits(full.numpy() != 0)
+            out_m[f"bits_F{F}_s{shift}"] = bits
+    np.savez_compressed(os.path.join(HERE, "masks.npz"), **out_m)
+
+    # ---- 2. index maps on an arange tensor
+    x = torch.arange(2 * 8 * 64 * 3, dtype=torch.float64).reshape(2, 8, 64, 3)
+    part = hw.window_partition(x, 16, 2)
+    rev = hw.window_reverse(part, 16, 2, 8, 64)
+    mer = hw.TemporalMerging(3, 2)(x)
+    np.savez_compressed(os.path.join(HERE, "index_maps.npz"), partition=part.numpy().astype(np.int32),
+                        reverse=rev.numpy().astype(np.int32), merge=mer.numpy().astype(np.int32))
+
+    # ---- 3. attention core (block minus norm/proj/ffn), every level, shift, mode
+    core = {}
+    for (d, h) in ((128, 2), (256, 4), (512, 8)):
+        for shift in (0, 1):
+            for thr in (None, 0.02, 0.04, 0.2):
+                for std in (0.02, 0.2):
+                    if thr in (0.02, 0.2) and std == 0.02:
+                        continue
+                    B, F = 1, 4
+                    rng = np.random.default_rng(1000 + d + 10 * shift + int(std * 100))
+                    xn = torch.from_numpy(rng.standard_normal((B, F, 64, d)))
+                    w = torch.from_numpy(rng.standard_normal((3 * d, d)) * std)
+                    b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1)
+                    g = torch.from_numpy(rng.standard_normal((B, F, 64, d)))
+                    blk = hw.PartAttentionBlock(dim=d, num_kps=64, num_heads=h, window_size=16,
+                                                temporal_patch_size=2, temporal_dim=F, shift_size=shift,
+                                                adj_mat=torch.concatenate([params.adj_mat] * (F // 2)).double(),
+                                                drop=0.0).double()
+                    msa = blk.attn
+                    with torch.no_grad():
+                        msa.qkv.weight.copy_(w); msa.qkv.bias.copy_(b)
+                        msa.proj.weight.copy_(torch.eye(d, dtype=torch.float64)); msa.proj.bias.zero_()
+                    msa.train(thr is not None)
+                    xn_ = xn.clone().requires_grad_(True)
+                    # the same sequence as PartAttentionBlock.forward, HWGATE.py:197-215, without norm1
+                    xs = torch.roll(xn_, shifts=-shift, dims=1) if shift else xn_
+                    xw = hw.window_partition(xs, 16, 2)
+                    with patched_rand([thr] if thr is not None else []):
+                        yw = msa(xw, B, F // 2, 4, mask=blk.attn_mask)
+                    y = hw.window_reverse(yw, 16, 2, F, 64)
+                    y = torch.roll(y, shifts=shift, dims=1) if shift else y
+                    (y * g).sum().backward()
+                    key = f"d{d}_s{shift}_thr{thr}_std{std}"
+                    core[key + "_y"], core[key + "_ysum"] = sample(y, 127)
+                    core[key + "_dx"], core[key + "_dxsum"] = sample(xn_.grad, 127)
+                    core[key + "_dw"], core[key + "_dwsum"] = sample(msa.qkv.weight.grad, 509)
+                    core[key + "_db"] = msa.qkv.bias.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "attention_core.npz"), **core)
+
+    # ---- 4. full model, default hierarchy
+    full = {}
+    for name, T, classes, B, thr in (
+            ("include_eval", 64, 262, 2, None),
+            ("include_train", 64, 262, 2, [0.03, 0.05, 0.031, 0.2, 0.033, 0.04, 0.0312, 0.1]),
+            ("fdmse_eval", 192, 2002, 1, None)):
+        cfg = O.HWGATEConfig(temporal_dim=T, num_classes=classes)
+        sd = O.make_state_dict(cfg, seed=1001, weight_std=0.05)
+        model, _ = build_ref_model(hw, mp, cfg, sd)
+        x = O.synthetic_keypoints(B, T, 2, seed=1001).double()
+        y = O.synthetic_labels(B, classes, seed=1001)
+        model.train(thr is not None)
+        with patched_rand(thr or []) as pr:
+            logits = model(x)
+        full[name + "_logits"] = logits.detach().numpy()
+        if thr is not None:
+            assert pr.calls == 8
+            loss = sce.SmoothedCrossEntropyLoss()(logits, y)
+            loss.backward()
+            full[name + "_loss"] = np.array(loss.item())
+            full[name + "_thr"] = np.array(thr)
+            names, norms, heads = [], [], []
+            for n, p in model.named_parameters():
+                if p.grad is None:
+                    continue
+                names.append(n)
+                norms.append(p.grad.norm().item())
+                heads.append(p.grad.reshape(-1)[:4].numpy().copy())
+            full[name + "_gnames"] = np.array(names)
+            full[name + "_gnorms"] = np.array(norms)
+            full[name + "_gheads"] = np.stack(heads)
+    # fp32 reference forward (what a user of the reference actually gets)
+    cfg = O.HWGATEConfig(temporal_dim=64, num_classes=262)
+    sd = O.make_state_dict(cfg, seed=1001, weight_std=0.05)
+    params32 = mp.HWGATEParams({"num_class": 262, "src_len": 64}, 2, "cpu")
+    params32.drop_rate = 0.0
+    m32 = hw.Model(*params32.get_model_params())
+    m32.load_state_dict(sd, strict=True)
+    m32.eval()
+    with torch.no_grad():
+        full["include_eval_logits_fp32"] = m32(O.synthetic_keypoints(2, 64, 2, seed=1001)).numpy()
+    full["state_dict_names"] = np.array(list(m32.state_dict().keys()))
+    full["state_dict_shapes"] = np.array([str(tuple(v.shape)) for v in m32.state_dict().values()])
+    np.savez_compressed(os.path.join(HERE, "full_model.npz"), **full)
+
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

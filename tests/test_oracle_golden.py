@@ -1,0 +1,175 @@
+"""Pins oracle/hwgate_oracle.py to the reference's own outputs
+(tests/golden/*.npz, produced by tests/golden/make_golden.py from the
+unmodified reference).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hwgate_oracle as O
+
+# packed rows of one window as listed in SURVEY.md section 8 row a1 [probe]
+SURVEY_ROWS_0_15 = [0x1000f, 0x20003, 0x40005, 0x80019, 0x100038, 0x200070, 0x4055e0, 0x80aac0,
+                    0x1000740, 0x2000b80, 0x4001d40, 0x8002e80, 0x10007440, 0x2000b880,
+                    0x4000d040, 0x8000e080]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_adjacency_matches_reference(golden_dir):
+    g = _load(golden_dir, "masks.npz")
+    cfg = O.HWGATEConfig()
+    adj = O.window_adjacency(cfg.edges, 16, 2)
+    assert adj.shape == (4, 32, 32)
+    assert np.array_equal(adj, g["adj"].astype(bool))
+    assert int(adj[0].sum()) == 164
+    bits = O.pack_mask_bits(adj)[0, :, 0]
+    assert [int(b) for b in bits[:16]] == SURVEY_ROWS_0_15
+    # rows 16-31: same pattern with the halves swapped
+    swapped = [((r >> 16) | (r << 16)) & 0xFFFFFFFF for r in SURVEY_ROWS_0_15]
+    assert [int(b) for b in bits[16:]] == swapped
+
+
+@pytest.mark.parametrize("F", [64, 32, 16, 8, 4])
+@pytest.mark.parametrize("shift", [0, 1])
+def test_combined_mask_bit_exact(golden_dir, F, shift):
+    g = _load(golden_dir, "masks.npz")
+    cfg = O.HWGATEConfig()
+    adj = O.window_adjacency(cfg.edges, 16, 2)
+    m = O.combined_mask(adj, F, 16, 2, shift)
+    assert np.array_equal(O.pack_mask_bits(m), g[f"bits_F{F}_s{shift}"])
+
+
+def test_index_maps(golden_dir):
+    g = _load(golden_dir, "index_maps.npz")
+    x = torch.arange(2 * 8 * 64 * 3, dtype=torch.float64).reshape(2, 8, 64, 3)
+    part = O.window_partition(x, 16, 2)
+    assert np.array_equal(part.numpy().astype(np.int32), g["partition"])
+    assert torch.equal(O.window_reverse(part, 16, 2, 8, 64), x)
+    mer = O.temporal_merge(x, 2)
+    assert np.array_equal(mer.numpy().astype(np.int32), g["merge"])
+    assert torch.equal(O.temporal_merge_backward(mer, 2), x)
+
+
+def _core_cases():
+    for (d, h) in ((128, 2), (256, 4), (512, 8)):
+        for shift in (0, 1):
+            for thr in (None, 0.02, 0.04, 0.2):
+                for std in (0.02, 0.2):
+                    if thr in (0.02, 0.2) and std == 0.02:
+                        continue
+                    yield d, h, shift, thr, std
+
+
+def core_inputs(d, shift, std, B=1, F=4):
+    rng = np.random.default_rng(1000 + d + 10 * shift + int(std * 100))
+    xn = torch.from_numpy(rng.standard_normal((B, F, 64, d)))
+    w = torch.from_numpy(rng.standard_normal((3 * d, d)) * std)
+    b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1)
+    g = torch.from_numpy(rng.standard_normal((B, F, 64, d)))
+    return xn, w, b, g
+
+
+@pytest.mark.parametrize("d,h,shift,thr,std", list(_core_cases()))
+def test_attention_core_matches_reference(golden_dir, d, h, shift, thr, std):
+    G = _load(golden_dir, "attention_core.npz")
+    key = f"d{d}_s{shift}_thr{thr}_std{std}"
+    xn, w, b, g = core_inputs(d, shift, std)
+    adj = O.window_adjacency(O.HWGATEConfig().edges, 16, 2)
+    mask = O.combined_mask(adj, 4, 16, 2, shift)
+    xn_ = xn.clone().requires_grad_(True)
+    w_ = w.clone().requires_grad_(True)
+    b_ = b.clone().requires_grad_(True)
+    y = O.attention_core(xn_, w_, b_, h, mask, 16, 2, shift, thr)
+    (y * g).sum().backward()
+
+    def chk(t, name, stride):
+        a = t.detach().reshape(-1).numpy()
+        np.testing.assert_allclose(a[::stride], G[key + "_" + name], rtol=1e-9, atol=1e-11)
+        s = G[key + "_" + name + "sum"]
+        np.testing.assert_allclose([a.sum(), np.abs(a).sum(), a.size], s, rtol=1e-9, atol=1e-9)
+
+    chk(y, "y", 127)
+    chk(xn_.grad, "dx", 127)
+    chk(w_.grad, "dw", 509)
+    np.testing.assert_allclose(b_.grad.numpy(), G[key + "_db"], rtol=1e-9, atol=1e-10)
+
+    # closed-form backward == autograd (this is the formula K3 implements)
+    dx, dw, db = O.attention_core_backward(xn, w, b, h, mask, 16, 2, shift, thr, g)
+    np.testing.assert_allclose(dx.numpy(), xn_.grad.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(dw.numpy(), w_.grad.numpy(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(db.numpy(), b_.grad.numpy(), rtol=1e-9, atol=1e-9)
+
+
+def test_fully_masked_rows_are_uniform():
+    """threshold below 1/32 drops every logit: softmax over 32 fills of -10000
+    is uniform over all 32 keys, neighbours or not."""
+    d, h = 128, 2
+    xn, w, b, g = core_inputs(d, 0, 0.02)
+    adj = O.window_adjacency(O.HWGATEConfig().edges, 16, 2)
+    mask = O.combined_mask(adj, 4, 16, 2, 0)
+    y = O.attention_core(xn, w, b, h, mask, 16, 2, 0, threshold=0.001)
+    xw = O.window_partition(xn, 16, 2)
+    v = (xw @ w.t() + b)[..., 2 * d:]
+    expect = O.window_reverse(v.mean(dim=1, keepdim=True).expand(-1, 32, -1), 16, 2, 4, 64)
+    np.testing.assert_allclose(y.numpy(), expect.numpy(), rtol=1e-10, atol=1e-12)
+
+
+def test_full_model_eval_matches_reference(golden_dir):
+    G = _load(golden_dir, "full_model.npz")
+    cfg = O.HWGATEConfig(temporal_dim=64, num_classes=262)
+    sd = O.make_state_dict(cfg, seed=1001, weight_std=0.05)
+    assert list(G["state_dict_names"]) == list(sd.keys())
+    assert [str(tuple(v.shape)) for v in sd.values()] == list(G["state_dict_shapes"])
+    x = O.synthetic_keypoints(2, 64, 2, seed=1001)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    logits = O.model_forward(x.double(), sd64, cfg)
+    np.testing.assert_allclose(logits.numpy(), G["include_eval_logits"], rtol=1e-9, atol=1e-10)
+    # fp32 oracle against the fp32 reference: the north_star's fp32 tolerance
+    l32 = O.model_forward(x, sd, cfg).numpy()
+    ref32 = G["include_eval_logits_fp32"]
+    assert np.abs(l32 - ref32).max() / np.abs(ref32).max() < 1e-5
+
+
+def test_full_model_train_matches_reference(golden_dir):
+    G = _load(golden_dir, "full_model.npz")
+    cfg = O.HWGATEConfig(temporal_dim=64, num_classes=262)
+    sd = {k: v.double().requires_grad_(v.dtype.is_floating_point and k not in ("B", "pos_encoder.pe")
+                                        and not k.endswith("attn_mask"))
+          for k, v in O.make_state_dict(cfg, seed=1001, weight_std=0.05).items()}
+    x = O.synthetic_keypoints(2, 64, 2, seed=1001).double()
+    y = O.synthetic_labels(2, 262, seed=1001)
+    thr = [float(t) for t in G["include_train_thr"]]
+    logits = O.model_forward(x, sd, cfg, thresholds=thr)
+    np.testing.assert_allclose(logits.detach().numpy(), G["include_train_logits"], rtol=1e-9, atol=1e-10)
+    loss = O.smoothed_cross_entropy(logits, y)
+    np.testing.assert_allclose(loss.item(), float(G["include_train_loss"]), rtol=1e-10)
+    loss.backward()
+    for name, norm, head in zip(G["include_train_gnames"], G["include_train_gnorms"], G["include_train_gheads"]):
+        g = sd[str(name)].grad
+        np.testing.assert_allclose(g.norm().item(), norm, rtol=1e-8, err_msg=str(name))
+        np.testing.assert_allclose(g.reshape(-1)[:4].numpy(), head, rtol=1e-7, atol=1e-12, err_msg=str(name))
+
+
+def test_full_model_long_sequence_eval(golden_dir):
+    G = _load(golden_dir, "full_model.npz")
+    cfg = O.HWGATEConfig(temporal_dim=192, num_classes=2002)
+    sd = {k: v.double() for k, v in O.make_state_dict(cfg, seed=1001, weight_std=0.05).items()}
+    x = O.synthetic_keypoints(1, 192, 2, seed=1001).double()
+    logits = O.model_forward(x, sd, cfg)
+    np.testing.assert_allclose(logits.numpy(), G["fdmse_eval_logits"], rtol=1e-9, atol=1e-10)
+
+
+def test_bf16_rounding_model_is_close_to_fp32():
+    """The rounding points used by the bf16 kernels stay inside the
+    north_star's 2e-2 relative tolerance against the unrounded oracle."""
+    d, h = 256, 4
+    xn, w, b, g = core_inputs(d, 1, 0.2)
+    adj = O.window_adjacency(O.HWGATEConfig().edges, 16, 2)
+    mask = O.combined_mask(adj, 4, 16, 2, 1)
+    y = O.attention_core(xn.float(), w.float(), b.float(), h, mask, 16, 2, 1)
+    yb = O.attention_core(xn.float(), w.float(), b.float(), h, mask, 16, 2, 1, bf16_points=True)
+    assert (y - yb).norm() / y.norm() < 2e-2
