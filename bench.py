@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""HWGATE fwd+bwd throughput on B200 (BASELINE.json metric: sequences/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU reference arm (oracle port)
+
+One step = zero_grad + forward + SmoothedCrossEntropyLoss + backward of the full
+HWGATE model (reference hierarchy: depths [2,2,4], heads [2,4,8], W=16, TP=2) on
+a synthetic keypoint batch, bf16 autocast, dropout 0.1 and the training
+threshold path on (model.train()), as the reference trains.  N > 1: batch-sharded
+(weak scaling: 512 sequences per GPU) with the NCCL gradient all-reduce inside
+the step.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "HWGAT sequences/sec fwd+bwd"
+UNIT = "sequences/s"
+T_FRAMES, KPS, CLASSES = 64, 64, 262
+DEPTHS, HEADS, EMBED = [2, 2, 4], [2, 4, 8], 128
+
+
+def peaks():
+    p = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            m = json.load(open(path))
+            p.update({k: float(m[k]) for k in ("bf16_tflops", "bf16_tflops_sustained", "hbm_gbs") if k in m})
+            p["source"] = "measured"
+        except Exception:
+            pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active")
+                                                         for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def attn_flops(B, level, backward):
+    """algorithmic FLOPs of K2 (x2 for K3) for one block of `level`."""
+    F = T_FRAMES >> level
+    d, h = EMBED << level, HEADS[level]
+    n, nwin = B * F * KPS, B * (F // 2) * (KPS // 16)
+    fwd = 6.0 * n * d * d + 4.0 * nwin * h * 32 * 32 * 64
+    return fwd * (2.0 if backward else 1.0)
+
+
+def merge_bytes(B, level, elem):
+    F, d = T_FRAMES >> level, EMBED << level
+    return 2.0 * B * F * KPS * d * elem
+
+
+class KernelTimer:
+    """CUDA events around every C-ABI call of the path, recorded on the launching (current) stream."""
+
+    def __init__(self, lib):
+        import torch
+        self.torch, self.lib, self.on, self.rec = torch, lib, False, []
+        self.orig = {}
+        for name in ("hwgat_attn_fwd", "hwgat_attn_bwd", "hwgat_merge_fwd", "hwgat_merge_bwd"):
+            fn = getattr(lib, name)
+            self.orig[name] = fn
+            setattr(lib, name, self._wrap(name, fn))
+
+    def _wrap(self, name, fn):
+        def call(*a):
+            if not self.on:
+                return fn(*a)
+            e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a)
+            e1.record()
+            d = a[11] if name == "hwgat_attn_fwd" else a[14] if name == "hwgat_attn_bwd" else a[5]
+            self.rec.append((name, int(d), e0, e1))
+            return r
+        return call
+
+    def restore(self):
+        for name, fn in self.orig.items():
+            setattr(self.lib, name, fn)
+
+    def table(self, B, steps):
+        agg = {}
+        for name, d, e0, e1 in self.rec:
+            k = (name, d)
+            ms = e0.elapsed_time(e1)
+            a = agg.setdefault(k, [0.0, 0])
+            a[0] += ms
+            a[1] += 1
+        out = []
+        for (name, d), (ms, cnt) in sorted(agg.items()):
+            avg = ms / cnt
+            if "attn" in name:
+                level = {128: 0, 256: 1, 512: 2}[d]
+                fl = attn_flops(B, level, name.endswith("bwd"))
+                out.append({"kernel": ("K3 " if name.endswith("bwd") else "K2 ") + f"{name} d={d}", "bound": "tensor",
+                            "calls_per_step": cnt / steps, "avg_ms": avg, "alg_flops": fl,
+                            "achieved": fl / (avg * 1e-3) / 1e12, "unit": "TFLOP/s", "total_ms": ms})
+            else:
+                level = {128: 0, 256: 1}[d] if name.endswith("fwd") else {128: 0, 256: 1}[d]
+                by = merge_bytes(B, level, 4)   # residual stream is fp32 under autocast
+                out.append({"kernel": "K4 " + f"{name} d={d}", "bound": "hbm", "calls_per_step": cnt / steps,
+                            "avg_ms": avg, "alg_bytes": by, "achieved": by / (avg * 1e-3) / 1e9, "unit": "GB/s",
+                            "total_ms": ms})
+        return out
+
+
+def build_model(device, drop=0.1):
+    import torch
+    from sl_hwgat_b200.models import HWGATE, model_params
+    p = model_params.HWGATEParams({"num_class": CLASSES, "src_len": T_FRAMES}, 2, device)
+    p.drop_rate = drop
+    torch.manual_seed(1001)                       # the reference's seed (configs.py:55)
+    return HWGATE.Model(*p.get_model_params()).to(device)
+
+
+def synthetic_batch(B):
+    """U(0,1) keypoints (B,T,29,2) gathered to the 64-slot window layout (dataTransform.py:428-441)."""
+    import numpy as np
+    import torch
+    head, larm, rarm = [0, 1, 2], [3, 5, 7], [4, 6, 8]
+    lh, rh = list(range(9, 19)), list(range(19, 29))
+    gather = np.array(head + larm + lh + head + rarm + rh + head + larm + rh + head + rarm + lh)
+    rng = np.random.default_rng(1001)
+    raw = rng.random((B, T_FRAMES, 29, 2), dtype=np.float32)
+    x = torch.from_numpy(np.ascontiguousarray(raw[:, :, gather, :]))
+    y = torch.from_numpy(rng.integers(0, CLASSES, size=(B,), dtype=np.int64))
+    return x, y
+
+
+def cpu_reference_arm(steps, warmup, batch=8):
+    """The reference's CPU path (oracle port, fp32, train mode, dropout 0.1) on the host cores."""
+    import torch
+    from oracle import hwgate_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.HWGATEConfig(temporal_dim=T_FRAMES, num_classes=CLASSES)
+    sd = O.make_state_dict(cfg, seed=1001)
+    for k, v in sd.items():
+        if k not in ("B", "pos_encoder.pe") and not k.endswith("attn_mask"):
+            v.requires_grad_(True)
+    x = O.synthetic_keypoints(batch, T_FRAMES, 2, seed=1001)
+    y = O.synthetic_labels(batch, CLASSES, seed=1001)
+    torch.manual_seed(1001)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        for v in sd.values():
+            v.grad = None
+        thr = [torch.rand(1).item() for _ in range(sum(cfg.depths))]
+        loss = O.smoothed_cross_entropy(O.model_forward(x, sd, cfg, thresholds=thr, drop=0.1), y)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": batch * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle port of the reference (fp32, train mode, dropout 0.1), batch {batch} x T={T_FRAMES} "
+                      f"x 64 kp x 2, {CLASSES} classes, {len(times)} fwd+bwd steps after {warmup} warm-up",
+            "ms_per_step": 1e3 * total / len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_arm(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus, args.batch),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, per_gpu_batch):
+    return {"workload": "BASELINE configs[2]: HWGATE training fwd+bwd, T=64 frames x 64 keypoints x 2, "
+                        f"{CLASSES} classes (INCLUDE shape), depths [2,2,4], heads [2,4,8], W=16, TP=2, "
+                        "train mode (threshold drop + dropout 0.1)",
+            "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * n_gpus, "frames": T_FRAMES,
+            "parallelism": f"dp{n_gpus} batch-sharded, NCCL grad all-reduce" if n_gpus > 1 else "single GPU",
+            "l2": "activations per block (>= 0.5 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="sequences per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from sl_hwgat_b200 import _lib, parallel
+    from sl_hwgat_b200.losses import SmoothedCrossEntropyLoss
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the path has no CPU fallback")
+    rank, world, local = parallel.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    B = args.batch
+    model = build_model(dev).train()
+    parallel.broadcast_parameters(model)
+    parallel.sync_threshold_rng(1001)             # same threshold sequence on every rank
+    criterion = SmoothedCrossEntropyLoss()
+    sync = parallel.GradientAllReduce(model) if world > 1 else None
+    xg, yg = synthetic_batch(B * world)
+    sl = parallel.shard_batch(B * world, rank, world)
+    x_host, y_host = xg[sl].contiguous().pin_memory(), yg[sl].contiguous().pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+
+    def step(xd, yd):
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = model(xd)
+        loss = criterion(logits, yd)
+        loss.backward()
+        if sync is not None:
+            sync.finish()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    timer = KernelTimer(lib)
+    barrier()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    timer.on = True
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            step(x_dev, y_dev)
+        e1.record()
+        barrier()
+    timer.on = False
+    launches = _lib.launch_count() - n0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+
+    # end to end through the public API with host buffers: H2D of the step's inputs from pinned
+    # memory and the D2H read of the loss inside the timed region (as utils.py:99-109 does)
+    xd, yd = torch.empty_like(x_dev), torch.empty_like(y_dev)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        xd.copy_(x_host, non_blocking=True)
+        yd.copy_(y_host, non_blocking=True)
+        last = step(xd, yd).item()
+    f1.record()
+    barrier()
+    ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2 = float(ms2.item())
+    timer.restore()
+
+    if rank == 0:
+        pk = peaks()
+        kern = timer.table(B, args.steps)
+        attn = [k for k in kern if k["bound"] == "tensor"]
+        top = max(attn, key=lambda k: k["total_ms"]) if attn else None
+        roof = None
+        if top is not None:
+            peak = pk["bf16_tflops_sustained"]     # timed inside a long step
+            roof = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["achieved"], "peak": peak,
+                    "unit": "TFLOP/s", "frac": top["achieved"] / peak, "traffic": None,
+                    "peak_source": pk["source"] + " (sustained bf16 GEMM)", "avg_ms": top["avg_ms"]}
+            tr = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tr):
+                try:
+                    roof["traffic"] = json.load(open(tr)).get(top["kernel"])
+                except Exception:
+                    pass
+        tot_fl = sum(k["alg_flops"] * k["calls_per_step"] for k in attn)
+        tot_ms = sum(k["total_ms"] for k in attn) / args.steps
+        for k in kern:
+            k["frac"] = k["achieved"] / (pk["bf16_tflops_sustained"] if k["bound"] == "tensor" else pk["hbm_gbs"])
+            k.pop("total_ms", None)
+        line = {"metric": METRIC, "value": B * world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload_config(world, B),
+                "e2e": {"value": B * world * args.steps / (ms2 * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms2 / args.steps, "last_loss": last},
+                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof,
+                "attn_tensor_frac": {"alg_tflop_per_step": tot_fl / 1e12, "attn_ms_per_step": tot_ms,
+                                     "achieved_tflops": tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms else None,
+                                     "frac_of_sustained_peak": (tot_fl / (tot_ms * 1e-3) / 1e12 /
+                                                                pk["bf16_tflops_sustained"]) if tot_ms else None},
+                "kernels": kern}
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_arm(3, 1)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

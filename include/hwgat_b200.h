@@ -1,0 +1,131 @@
+/*
+ * hwgat_b200 - C ABI of the B200-native HWGATE windowed-graph-attention path.
+ *
+ * Drop-in boundary for the hot path of suvajit-patra/sl-hwgat
+ * (hwgat/models/HWGATE.py + the adjacency builder of
+ * hwgat/models/model_params.py).  The reference is pure PyTorch and has no FFI
+ * of its own; each entry point below names the reference code it replaces.
+ * The Python side (sl_hwgat_b200/_lib.py) binds these with ctypes and passes
+ * tensor.data_ptr() values and the current CUDA stream.
+ *
+ * Conventions
+ *  - plain C symbols, no C++/torch types; all pointers are DEVICE pointers owned
+ *    by the caller; the library never allocates, frees or synchronises;
+ *  - every call is asynchronous on `stream` and re-entrant across streams;
+ *  - return value: 0 = ok; 1..999 = cudaError_t of the failed launch;
+ *    >= 1000 = argument error (see hwgat_error_string);
+ *  - activations: layout HWGAT_LAYOUT_BFKD is the reference's un-partitioned,
+ *    un-rolled (B, F, K, d) row-major tensor: the cyclic frame shift
+ *    (HWGATE.py:197-200, 210-215) and window_partition / window_reverse
+ *    (HWGATE.py:30-47) are index arithmetic inside the kernels, never copies.
+ *    HWGAT_LAYOUT_WINDOWS is the already-partitioned (B*f*nW, TP*W, d) tensor
+ *    that MSA.forward receives (HWGATE.py:84); shift must be 0 there because
+ *    the caller has already rolled;
+ *  - dtype: HWGAT_F32 = every tensor float32 (the 1e-5 parity mode);
+ *    HWGAT_BF16 = activations and weights bfloat16, biases / reductions /
+ *    weight gradients float32 (the timed mode);
+ *  - supported geometry: temporal_patch TP = 2, window W = 16 (N = 32 tokens per
+ *    window), head_dim 64, d = heads*64 <= 512, F even, K a multiple of 64.
+ *    Anything else returns HWGAT_ERR_UNSUPPORTED - there is no fallback path.
+ */
+#ifndef HWGAT_B200_H
+#define HWGAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* hwgat_stream_t; /* cudaStream_t */
+
+enum { HWGAT_F32 = 0, HWGAT_BF16 = 1 };
+enum { HWGAT_LAYOUT_BFKD = 0, HWGAT_LAYOUT_WINDOWS = 1 };
+
+enum {
+  HWGAT_OK = 0,
+  HWGAT_ERR_NULL = 1000,        /* required pointer is NULL              */
+  HWGAT_ERR_SHAPE = 1001,       /* inconsistent sizes                    */
+  HWGAT_ERR_UNSUPPORTED = 1002, /* geometry / dtype outside the kernels  */
+  HWGAT_ERR_WORKSPACE = 1003,   /* workspace smaller than required       */
+  HWGAT_ERR_ALIGN = 1004        /* pointer not 16-byte aligned           */
+};
+
+/* ABI version; bumped on any signature change. */
+int hwgat_version(void);
+const char* hwgat_error_string(int status);
+
+/* K1a - skeleton adjacency of every keypoint window.
+ * Replaces HWGATEParams.get_adj / get_adj_mat (model_params.py:373-400).
+ * edges: int32 (nW, n_edges, 2) undirected pairs inside one W-keypoint window.
+ * adj  : float32 (nW, TP*W, TP*W), 1.0 / 0.0, self loops included; a joint is
+ *        linked to itself in the adjacent frame, nothing further apart.        */
+int hwgat_adjacency_build(const int32_t* edges, int n_edges, int nW, int W, int TP,
+                          float* adj, hwgat_stream_t stream);
+
+/* K1b - packed attention mask of one block.
+ * Replaces the adjacency replication (HWGATE.py:309), the shifted-window mask
+ * (HWGATE.py:169-187) and their two multiplies (HWGATE.py:102-108).
+ * adj : float32 (nW, N, N), N = TP*W, any non-zero = edge.
+ * bits: uint32 (F/TP * nW, N, N/32): bit j of row i of window fi*nW+w = key j
+ *       visible to query i.  shift = 0 for even blocks, TP/2 for odd ones.     */
+int hwgat_mask_build(const float* adj, int nW, int W, int TP, int F, int shift,
+                     uint32_t* bits, hwgat_stream_t stream);
+
+/* K1c - pack arbitrary float masks, for callers of MSA.forward that hand in
+ * their own `mask` / `adj_mat` tensors (HWGATE.py:84, 102-108).
+ * adj : float32 (adj_windows, N, N) or NULL; window `win` uses adj[win % adj_windows].
+ * mask: float32 (n_windows, N, N) or NULL.
+ * bits: uint32 (n_windows, N, N/32) = (adj != 0) AND (mask != 0).                */
+int hwgat_mask_pack(const float* adj, int adj_windows, const float* mask, int n_windows, int N,
+                    uint32_t* bits, hwgat_stream_t stream);
+
+/* Bytes of scratch hwgat_attn_fwd / hwgat_attn_bwd need for these sizes. */
+size_t hwgat_attn_workspace_bytes(int B, int F, int K, int d, int heads, int dtype, int backward);
+
+/* K2 - fused windowed graph attention, forward.
+ * Replaces torch.roll + window_partition + MSA.forward up to (not including)
+ * self.proj + window_reverse + roll back: HWGATE.py:197-201, 86-114, 207-215.
+ * xn    : (B,F,K,d) normalised residual stream (output of norm1), dtype.
+ * w_qkv : (3d, d) dtype, rows [q | k | v], head-major inside each (HWGATE.py:76,86).
+ * b_qkv : (3d) float32.
+ * bits  : mask of hwgat_mask_build for this F and shift.
+ * threshold: < 0 = eval mode.  >= 0 = training mode: logits whose unmasked
+ *         softmax exceeds it are zeroed first (HWGATE.py:94-100).
+ * out   : (B,F,K,d) dtype, head-merged context, same token order as xn.
+ * workspace: hwgat_attn_workspace_bytes(..., backward=0) bytes (may be 0).     */
+int hwgat_attn_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits,
+                   float threshold, void* out, void* workspace, size_t workspace_bytes,
+                   int B, int F, int K, int d, int heads, int W, int TP, int shift, int layout,
+                   int dtype, hwgat_stream_t stream);
+
+/* K3 - fused backward of K2.  Recomputes Q, K, V, the logits and the
+ * probabilities from xn (nothing but xn is saved by the forward).
+ * d_out : (B,F,K,d) dtype, gradient of `out`.
+ * d_xn  : (B,F,K,d) dtype, overwritten.
+ * d_w   : (3d, d) float32, overwritten.   d_b: (3d) float32, overwritten.
+ * The gradient w.r.t. the logits is  live ? P*(dP - sum_j P*dP) : 0  where
+ * live = mask AND keep AND logit != 0 (autograd of HWGATE.py:100-111).          */
+int hwgat_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const float* b_qkv,
+                   const uint32_t* bits, float threshold, void* d_xn, float* d_w, float* d_b,
+                   void* workspace, size_t workspace_bytes,
+                   int B, int F, int K, int d, int heads, int W, int TP, int shift, int layout,
+                   int dtype, hwgat_stream_t stream);
+
+/* K4 - stage transition.  Replaces TemporalMerging.forward (HWGATE.py:55-63):
+ * out[b,fi,k,tp*d+e] = x[b,fi*TP+tp,k,e];  x: (B,F,K,d) -> out: (B,F/TP,K,TP*d). */
+int hwgat_merge_fwd(const void* x, void* out, int B, int F, int K, int d, int TP,
+                    int dtype, hwgat_stream_t stream);
+/* Adjoint of K4: d_out (B,F/TP,K,TP*d) -> d_x (B,F,K,d). */
+int hwgat_merge_bwd(const void* d_out, void* d_x, int B, int F, int K, int d, int TP,
+                    int dtype, hwgat_stream_t stream);
+
+/* Number of kernel launches issued through this library since load (all
+ * streams, this process) - what bench.py reports as "gpu_launches". */
+unsigned long long hwgat_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HWGAT_B200_H */

@@ -1,0 +1,71 @@
+"""ctypes binding of libhwgat_b200.so (include/hwgat_b200.h).
+
+There is no fallback: if the library is missing, or a call returns a non-zero
+status, this raises.  Nothing here computes anything on the host.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_ulonglong, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libhwgat_b200.so")
+
+F32, BF16 = 0, 1
+LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
+ABI_VERSION = 2
+
+# name -> (restype, argtypes); must list every symbol of include/hwgat_b200.h
+SIGNATURES = {
+    "hwgat_version": (c_int, []),
+    "hwgat_error_string": (c_char_p, [c_int]),
+    "hwgat_launch_count": (c_ulonglong, []),
+    "hwgat_adjacency_build": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hwgat_mask_build": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hwgat_mask_pack": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "hwgat_attn_workspace_bytes": (c_size_t, [c_int] * 7),
+    "hwgat_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t]
+                       + [c_int] * 10 + [c_void_p]),
+    "hwgat_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_size_t] + [c_int] * 10 + [c_void_p]),
+    "hwgat_merge_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    "hwgat_merge_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+}
+
+_lib = None
+
+
+class HwgatError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the library once.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HwgatError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library has not been built "
+            "(run `python -m sl_hwgat_b200.build`). There is no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.hwgat_version()
+    if got != ABI_VERSION:
+        raise HwgatError(f"libhwgat_b200 ABI {got}, binding expects {ABI_VERSION}: rebuild the library")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().hwgat_error_string(status)
+        raise HwgatError(f"{what} failed with status {status}: {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(load().hwgat_launch_count())

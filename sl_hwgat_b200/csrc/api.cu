@@ -1,0 +1,140 @@
+// C ABI of libhwgat_b200 (include/hwgat_b200.h): argument checks and dispatch.
+// No allocation, no synchronisation, no fallback: a geometry or dtype the
+// kernels do not cover is an error, not a slower path.
+#include "common.cuh"
+
+namespace hwgat {
+unsigned long long g_launches = 0;
+
+static bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+static int check_geometry(int B, int F, int K, int d, int heads, int W, int TP, int shift, int layout, int dtype) {
+  if (B < 0 || F <= 0 || K <= 0 || d <= 0 || heads <= 0) return HWGAT_ERR_SHAPE;
+  if (dtype != HWGAT_F32 && dtype != HWGAT_BF16) return HWGAT_ERR_UNSUPPORTED;
+  if (layout != HWGAT_LAYOUT_BFKD && layout != HWGAT_LAYOUT_WINDOWS) return HWGAT_ERR_UNSUPPORTED;
+  if (W != kWin || TP != kTP) return HWGAT_ERR_UNSUPPORTED;
+  if (d != heads * kHd || d > 512) return HWGAT_ERR_UNSUPPORTED;
+  if (F % TP != 0 || K % 64 != 0) return HWGAT_ERR_UNSUPPORTED;
+  if (shift < 0 || shift >= TP) return HWGAT_ERR_SHAPE;
+  if (layout == HWGAT_LAYOUT_WINDOWS && shift != 0) return HWGAT_ERR_SHAPE;
+  if ((long long)B * F * K > 0x7fffffffLL / 4) return HWGAT_ERR_UNSUPPORTED;  // row index kept in 31 bits
+  return HWGAT_OK;
+}
+}  // namespace hwgat
+
+using namespace hwgat;
+
+extern "C" {
+
+int hwgat_version(void) { return 2; }
+
+const char* hwgat_error_string(int status) {
+  switch (status) {
+    case HWGAT_OK: return "ok";
+    case HWGAT_ERR_NULL: return "hwgat: required pointer is NULL";
+    case HWGAT_ERR_SHAPE: return "hwgat: inconsistent sizes";
+    case HWGAT_ERR_UNSUPPORTED: return "hwgat: geometry or dtype not supported by the sm_100a kernels (no fallback)";
+    case HWGAT_ERR_WORKSPACE: return "hwgat: workspace too small";
+    case HWGAT_ERR_ALIGN: return "hwgat: pointer not 16-byte aligned";
+    default: break;
+  }
+  if (status > 0 && status < 1000) return cudaGetErrorString((cudaError_t)status);
+  return "hwgat: unknown status";
+}
+
+unsigned long long hwgat_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int hwgat_adjacency_build(const int32_t* edges, int n_edges, int nW, int W, int TP, float* adj,
+                          hwgat_stream_t stream) {
+  if (!adj || (n_edges > 0 && !edges)) return HWGAT_ERR_NULL;
+  if (nW <= 0 || W <= 0 || W > 64 || TP <= 0 || n_edges < 0) return HWGAT_ERR_SHAPE;
+  return launch_adjacency(edges, n_edges, nW, W, TP, adj, (cudaStream_t)stream);
+}
+
+int hwgat_mask_build(const float* adj, int nW, int W, int TP, int F, int shift, uint32_t* bits,
+                     hwgat_stream_t stream) {
+  if (!adj || !bits) return HWGAT_ERR_NULL;
+  if (nW <= 0 || W <= 0 || TP <= 0 || F <= 0 || F % TP != 0 || shift < 0 || shift >= TP) return HWGAT_ERR_SHAPE;
+  if ((TP * W) % 32 != 0) return HWGAT_ERR_UNSUPPORTED;
+  return launch_mask_bits(adj, nW, W, TP, F, shift, bits, (cudaStream_t)stream);
+}
+
+int hwgat_mask_pack(const float* adj, int adj_windows, const float* mask, int n_windows, int N, uint32_t* bits,
+                    hwgat_stream_t stream) {
+  if (!bits) return HWGAT_ERR_NULL;
+  if (n_windows < 0 || N <= 0 || (adj && adj_windows <= 0)) return HWGAT_ERR_SHAPE;
+  if (N % 32 != 0) return HWGAT_ERR_UNSUPPORTED;
+  return launch_mask_pack(adj, adj_windows, mask, n_windows, N, bits, (cudaStream_t)stream);
+}
+
+size_t hwgat_attn_workspace_bytes(int B, int F, int K, int d, int heads, int dtype, int backward) {
+  (void)heads;
+  const size_t n = (size_t)B * F * K;
+  if (dtype == HWGAT_F32) return n * 3 * d * sizeof(float) * (backward ? 2 : 1);  // qkv (+ dqkv)
+  return backward ? n * 3 * d * sizeof(__nv_bfloat16) : 0;                         // dqkv
+}
+
+int hwgat_attn_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, float threshold,
+                   void* out, void* workspace, size_t workspace_bytes, int B, int F, int K, int d, int heads, int W,
+                   int TP, int shift, int layout, int dtype, hwgat_stream_t stream) {
+  int st = check_geometry(B, F, K, d, heads, W, TP, shift, layout, dtype);
+  if (st) return st;
+  if (B == 0) return HWGAT_OK;
+  if (!xn || !w_qkv || !b_qkv || !bits || !out) return HWGAT_ERR_NULL;
+  if (misaligned(xn) || misaligned(w_qkv) || misaligned(out) || misaligned(b_qkv) || misaligned(workspace))
+    return HWGAT_ERR_ALIGN;
+  const size_t need = hwgat_attn_workspace_bytes(B, F, K, d, heads, dtype, 0);
+  if (need > 0 && (!workspace || workspace_bytes < need)) return HWGAT_ERR_WORKSPACE;
+  AttnArgs a{};
+  a.xn = xn; a.w_qkv = w_qkv; a.b_qkv = b_qkv; a.bits = bits; a.threshold = threshold; a.out = out;
+  a.workspace = workspace; a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
+  return dtype == HWGAT_F32 ? attn_fwd_f32(a, (cudaStream_t)stream) : attn_fwd_bf16(a, (cudaStream_t)stream);
+}
+
+int hwgat_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits,
+                   float threshold, void* d_xn, float* d_w, float* d_b, void* workspace, size_t workspace_bytes,
+                   int B, int F, int K, int d, int heads, int W, int TP, int shift, int layout, int dtype,
+                   hwgat_stream_t stream) {
+  int st = check_geometry(B, F, K, d, heads, W, TP, shift, layout, dtype);
+  if (st) return st;
+  if (!d_w || !d_b) return HWGAT_ERR_NULL;
+  if (B == 0) {  // empty batch: gradients of the parameters are zero
+    cudaMemsetAsync(d_w, 0, sizeof(float) * 3 * d * d, (cudaStream_t)stream);
+    cudaMemsetAsync(d_b, 0, sizeof(float) * 3 * d, (cudaStream_t)stream);
+    return (int)cudaGetLastError();
+  }
+  if (!d_out || !xn || !w_qkv || !b_qkv || !bits || !d_xn) return HWGAT_ERR_NULL;
+  if (misaligned(d_out) || misaligned(xn) || misaligned(w_qkv) || misaligned(d_xn) || misaligned(d_w) ||
+      misaligned(b_qkv) || misaligned(workspace))
+    return HWGAT_ERR_ALIGN;
+  const size_t need = hwgat_attn_workspace_bytes(B, F, K, d, heads, dtype, 1);
+  if (!workspace || workspace_bytes < need) return HWGAT_ERR_WORKSPACE;
+  AttnArgs a{};
+  a.xn = xn; a.w_qkv = w_qkv; a.b_qkv = b_qkv; a.bits = bits; a.threshold = threshold; a.d_out = d_out;
+  a.d_xn = d_xn; a.d_w = d_w; a.d_b = d_b; a.workspace = workspace;
+  a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
+  return dtype == HWGAT_F32 ? attn_bwd_f32(a, (cudaStream_t)stream) : attn_bwd_bf16(a, (cudaStream_t)stream);
+}
+
+static int merge_common(const void* src, void* dst, int B, int F, int K, int d, int TP, int dtype, bool backward,
+                        hwgat_stream_t stream) {
+  if (B < 0 || F <= 0 || K <= 0 || d <= 0) return HWGAT_ERR_SHAPE;
+  if (TP != kTP || F % TP != 0) return HWGAT_ERR_UNSUPPORTED;
+  if (dtype != HWGAT_F32 && dtype != HWGAT_BF16) return HWGAT_ERR_UNSUPPORTED;
+  const int eb = dtype == HWGAT_F32 ? 4 : 2;
+  if ((d * eb) % 16 != 0) return HWGAT_ERR_UNSUPPORTED;
+  if (B == 0) return HWGAT_OK;
+  if (!src || !dst) return HWGAT_ERR_NULL;
+  if (misaligned(src) || misaligned(dst)) return HWGAT_ERR_ALIGN;
+  return launch_merge(src, dst, B, F, K, d, eb, backward, (cudaStream_t)stream);
+}
+
+int hwgat_merge_fwd(const void* x, void* out, int B, int F, int K, int d, int TP, int dtype, hwgat_stream_t stream) {
+  return merge_common(x, out, B, F, K, d, TP, dtype, false, stream);
+}
+int hwgat_merge_bwd(const void* d_out, void* d_x, int B, int F, int K, int d, int TP, int dtype,
+                    hwgat_stream_t stream) {
+  return merge_common(d_out, d_x, B, F, K, d, TP, dtype, true, stream);
+}
+
+}  // extern "C"

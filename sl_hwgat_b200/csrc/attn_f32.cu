@@ -1,0 +1,361 @@
+// fp32 parity mode of K2/K3 (the north_star's "fp32 within 1e-5" path).
+// True fp32 FFMA arithmetic - no TF32, no tensor cores - so it is a
+// correctness mode, not the timed one.  Same C entry points, same index
+// arithmetic (roll / partition never materialised), same mask semantics as the
+// bf16 kernels:
+//   qkv  = xn . Wqkv^T + b                      (HWGATE.py:86)
+//   S    = (q*scale) . k^T                      (HWGATE.py:89-91)
+//   keep = !(softmax(S) > thr)     [training]   (HWGATE.py:94-100)
+//   live = mask & keep & (S != 0)               (HWGATE.py:102-110)
+//   P    = softmax(live ? S : -10000)           (HWGATE.py:110-111)
+//   out  = P . v                                (HWGATE.py:114)
+#include "common.cuh"
+
+namespace hwgat {
+
+// ---------------------------------------------------------------------------
+// Tiled FFMA GEMM: C[M,N] (+)= A.B.  A is [M][K] (TA=false) or [K][M] (TA=true);
+// B is [N][K] (TB=true, i.e. a Linear weight) or [K][N] (TB=false).
+// kAtomic: split-K over blockIdx.z, fp32 atomics into a zeroed C.
+// ---------------------------------------------------------------------------
+template <bool TA, bool TB, bool kAtomic, bool kBias>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                       const float* __restrict__ bias, float* __restrict__ C,
+                                                       int M, int N, int K, int k_per_split) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float acc[4][4] = {};
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    for (int i = threadIdx.x; i < BM * BK; i += 256) {
+      int kk, mm;
+      if (TA) { mm = i % BM; kk = i / BM; } else { kk = i % BK; mm = i / BK; }
+      int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < kend) v = TA ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk];
+      As[kk][mm] = v;
+    }
+    for (int i = threadIdx.x; i < BN * BK; i += 256) {
+      int kk, nn;
+      if (TB) { kk = i % BK; nn = i / BK; } else { nn = i % BN; kk = i / BN; }
+      int gn = n0 + nn, gk = k0 + kk;
+      float v = 0.f;
+      if (gn < N && gk < kend) v = TB ? Bm[(size_t)gn * K + gk] : Bm[(size_t)gk * N + gn];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gm < M && gn < N) {
+        float v = acc[i][j] + (kBias ? bias[gn] : 0.f);
+        if (kAtomic) atomicAdd(&C[(size_t)gm * N + gn], v); else C[(size_t)gm * N + gn] = v;
+      }
+    }
+}
+
+// column sums of a [rows][cols] matrix into a zeroed vector (d_b = sum_t dQKV[t,:])
+__global__ void colsum_f32_kernel(const float* __restrict__ X, float* __restrict__ out, long long rows, int cols,
+                                  long long rows_per_block) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += X[r * cols + c];
+  atomicAdd(&out[c], s);
+}
+
+// ---------------------------------------------------------------------------
+// attention core, one warp per (window, head); lane = query token (forward and
+// dQ) and = key token (dK, dV).  4 windows of one tile per CTA.
+// ---------------------------------------------------------------------------
+struct CoreSmemF32 {
+  float k[kTok][kHd];
+  float v[kTok][kHd];
+};
+struct CoreSmemF32Bwd {
+  float k[kTok][kHd];
+  float v[kTok][kHd];
+  float q[kTok][kHd];
+  float g[kTok][kHd];       // d_out rows of this window/head
+  float p[kTok][kTok + 1];
+  float ds[kTok][kTok + 1];
+};
+
+// probabilities of one query row held by one lane: s[] in, p[] out (in place)
+HW_DEV uint32_t row_softmax_f32(float (&s)[kTok], uint32_t mask_word, float threshold) {
+  uint32_t live = mask_word;
+  if (threshold >= 0.f) {
+    float m = s[0];
+#pragma unroll
+    for (int j = 1; j < kTok; ++j) m = fmaxf(m, s[j]);
+    float e[kTok], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTok; ++j) { e[j] = expf(s[j] - m); sum += e[j]; }
+#pragma unroll
+    for (int j = 0; j < kTok; ++j)
+      if (e[j] / sum > threshold) live &= ~(1u << j);
+  }
+#pragma unroll
+  for (int j = 0; j < kTok; ++j)
+    if (s[j] == 0.f) live &= ~(1u << j);
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kTok; ++j) { s[j] = ((live >> j) & 1u) ? s[j] : kNegFill; m = fmaxf(m, s[j]); }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTok; ++j) { s[j] = expf(s[j] - m); sum += s[j]; }
+  float inv = 1.f / sum;
+#pragma unroll
+  for (int j = 0; j < kTok; ++j) s[j] *= inv;
+  return live;
+}
+
+__global__ void __launch_bounds__(128) attn_core_fwd_f32_kernel(const float* __restrict__ qkv,
+                                                                const uint32_t* __restrict__ bits, float threshold,
+                                                                float* __restrict__ out, TileGeom g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  CoreSmemF32& sm = reinterpret_cast<CoreSmemF32*>(smem_raw)[w];
+  const int tile = blockIdx.x, h = blockIdx.y;
+  const int d = g.d, d3 = 3 * d;
+  const float scale = 0.125f;  // head_dim^-0.5, head_dim = 64
+
+  // k, v rows of the window -> smem (each row: 64 floats, 2 per lane, coalesced)
+  for (int j = 0; j < kTok; ++j) {
+    const float* src = qkv + g.token_row(tile, w * kTok + j) * d3 + h * kHd;
+    float2 kk = *reinterpret_cast<const float2*>(src + d + lane * 2);
+    float2 vv = *reinterpret_cast<const float2*>(src + 2 * d + lane * 2);
+    *reinterpret_cast<float2*>(&sm.k[j][lane * 2]) = kk;
+    *reinterpret_cast<float2*>(&sm.v[j][lane * 2]) = vv;
+  }
+  const long long my_row = g.token_row(tile, w * kTok + lane);
+  float q[kHd];
+  {
+    const float4* src = reinterpret_cast<const float4*>(qkv + my_row * d3 + h * kHd);
+#pragma unroll
+    for (int e = 0; e < kHd / 4; ++e) {
+      float4 t = src[e];
+      q[4 * e] = t.x * scale; q[4 * e + 1] = t.y * scale; q[4 * e + 2] = t.z * scale; q[4 * e + 3] = t.w * scale;
+    }
+  }
+  __syncwarp();
+  float s[kTok];
+#pragma unroll
+  for (int j = 0; j < kTok; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) a = fmaf(q[e], sm.k[j][e], a);
+    s[j] = a;
+  }
+  const uint32_t mword = bits[g.mask_base(tile) + w * kTok + lane];
+  row_softmax_f32(s, mword, threshold);
+  float o[kHd];
+#pragma unroll
+  for (int e = 0; e < kHd; ++e) o[e] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTok; ++j)
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) o[e] = fmaf(s[j], sm.v[j][e], o[e]);
+  float4* dst = reinterpret_cast<float4*>(out + my_row * d + h * kHd);
+#pragma unroll
+  for (int e = 0; e < kHd / 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const float* __restrict__ qkv,
+                                                                         const float* __restrict__ d_out,
+                                                                         const uint32_t* __restrict__ bits,
+                                                                         float threshold, float* __restrict__ dqkv,
+                                                                         TileGeom g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  CoreSmemF32Bwd& sm = reinterpret_cast<CoreSmemF32Bwd*>(smem_raw)[wl];
+  const int widx = blockIdx.x * kWarps + wl;  // window index over (tile, w)
+  const int tile = widx >> 2, w = widx & 3, h = blockIdx.y;
+  const int d = g.d, d3 = 3 * d;
+  const float scale = 0.125f;
+
+  for (int j = 0; j < kTok; ++j) {
+    const long long r = g.token_row(tile, w * kTok + j);
+    const float* src = qkv + r * d3 + h * kHd;
+    float2 qq = *reinterpret_cast<const float2*>(src + lane * 2);
+    qq.x *= scale; qq.y *= scale;
+    *reinterpret_cast<float2*>(&sm.q[j][lane * 2]) = qq;
+    *reinterpret_cast<float2*>(&sm.k[j][lane * 2]) = *reinterpret_cast<const float2*>(src + d + lane * 2);
+    *reinterpret_cast<float2*>(&sm.v[j][lane * 2]) = *reinterpret_cast<const float2*>(src + 2 * d + lane * 2);
+    *reinterpret_cast<float2*>(&sm.g[j][lane * 2]) =
+        *reinterpret_cast<const float2*>(d_out + r * d + h * kHd + lane * 2);
+  }
+  __syncwarp();
+  const long long my_row = g.token_row(tile, w * kTok + lane);
+  // ---- lane = query i: P row, dP row, dS row, dQ row
+  // (own q / d_out rows come from global into registers: reading smem row `lane`
+  //  from every lane would be a 32-way bank conflict)
+  float s[kTok];
+  {
+    float qr[kHd];
+    const float4* src = reinterpret_cast<const float4*>(qkv + my_row * d3 + h * kHd);
+#pragma unroll
+    for (int e = 0; e < kHd / 4; ++e) {
+      float4 t = src[e];
+      qr[4 * e] = t.x * scale; qr[4 * e + 1] = t.y * scale; qr[4 * e + 2] = t.z * scale; qr[4 * e + 3] = t.w * scale;
+    }
+#pragma unroll
+    for (int j = 0; j < kTok; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) a = fmaf(qr[e], sm.k[j][e], a);
+      s[j] = a;
+    }
+  }
+  const uint32_t mword = bits[g.mask_base(tile) + w * kTok + lane];
+  const uint32_t live = row_softmax_f32(s, mword, threshold);  // s[] now holds P
+  float dp[kTok], dsum = 0.f;
+  {
+    float gr[kHd];
+    const float4* src = reinterpret_cast<const float4*>(d_out + my_row * d + h * kHd);
+#pragma unroll
+    for (int e = 0; e < kHd / 4; ++e) {
+      float4 t = src[e];
+      gr[4 * e] = t.x; gr[4 * e + 1] = t.y; gr[4 * e + 2] = t.z; gr[4 * e + 3] = t.w;
+    }
+#pragma unroll
+    for (int j = 0; j < kTok; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) a = fmaf(gr[e], sm.v[j][e], a);
+      dp[j] = a;
+      dsum = fmaf(s[j], a, dsum);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kTok; ++j) {
+    float dsv = ((live >> j) & 1u) ? s[j] * (dp[j] - dsum) : 0.f;
+    sm.p[lane][j] = s[j];
+    sm.ds[lane][j] = dsv;
+    dp[j] = dsv;
+  }
+  {
+    float dq[kHd];
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) dq[e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTok; ++j)
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) dq[e] = fmaf(dp[j], sm.k[j][e], dq[e]);
+    float4* dst = reinterpret_cast<float4*>(dqkv + my_row * d3 + h * kHd);
+#pragma unroll
+    for (int e = 0; e < kHd / 4; ++e)
+      dst[e] = make_float4(dq[4 * e] * scale, dq[4 * e + 1] * scale, dq[4 * e + 2] * scale, dq[4 * e + 3] * scale);
+  }
+  __syncwarp();
+  // ---- lane = key j: dK row = sum_i dS[i][j] q_i ; dV row = sum_i P[i][j] g_i
+  {
+    float acc[kHd];
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) acc[e] = 0.f;
+    for (int i = 0; i < kTok; ++i) {
+      float c = sm.ds[i][lane];
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) acc[e] = fmaf(c, sm.q[i][e], acc[e]);
+    }
+    float4* dst = reinterpret_cast<float4*>(dqkv + my_row * d3 + d + h * kHd);
+#pragma unroll
+    for (int e = 0; e < kHd / 4; ++e) dst[e] = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) acc[e] = 0.f;
+    for (int i = 0; i < kTok; ++i) {
+      float c = sm.p[i][lane];
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) acc[e] = fmaf(c, sm.g[i][e], acc[e]);
+    }
+    dst = reinterpret_cast<float4*>(dqkv + my_row * d3 + 2 * d + h * kHd);
+#pragma unroll
+    for (int e = 0; e < kHd / 4; ++e) dst[e] = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+  }
+}
+
+static int check_last() { return (int)cudaGetLastError(); }
+
+int attn_fwd_f32(const AttnArgs& a, cudaStream_t s) {
+  const long long n = (long long)a.B * a.F * a.K;
+  const int d = a.d;
+  float* qkv = (float*)a.workspace;
+  dim3 gg((3 * d + 63) / 64, (unsigned)((n + 63) / 64), 1);
+  gemm_f32_kernel<false, true, false, true><<<gg, 256, 0, s>>>((const float*)a.xn, (const float*)a.w_qkv, a.b_qkv, qkv,
+                                                               (int)n, 3 * d, d, d);
+  count_launch();
+  int st = check_last();
+  if (st) return st;
+  TileGeom g = make_geom(a.F, a.K, d, a.shift, a.layout);
+  size_t smem = 4 * sizeof(CoreSmemF32);
+  cudaFuncSetAttribute(attn_core_fwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  attn_core_fwd_f32_kernel<<<dim3(a.tiles(), a.heads), 128, smem, s>>>(qkv, a.bits, a.threshold, (float*)a.out, g);
+  count_launch();
+  return check_last();
+}
+
+int attn_bwd_f32(const AttnArgs& a, cudaStream_t s) {
+  const long long n = (long long)a.B * a.F * a.K;
+  const int d = a.d, d3 = 3 * d;
+  float* qkv = (float*)a.workspace;
+  float* dqkv = qkv + n * d3;
+  int st;
+  dim3 gg((d3 + 63) / 64, (unsigned)((n + 63) / 64), 1);
+  gemm_f32_kernel<false, true, false, true><<<gg, 256, 0, s>>>((const float*)a.xn, (const float*)a.w_qkv, a.b_qkv, qkv,
+                                                               (int)n, d3, d, d);
+  count_launch();
+  if ((st = check_last())) return st;
+  TileGeom g = make_geom(a.F, a.K, d, a.shift, a.layout);
+  constexpr int kWarps = 4;
+  size_t smem = kWarps * sizeof(CoreSmemF32Bwd);
+  cudaFuncSetAttribute(attn_core_bwd_f32_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  attn_core_bwd_f32_kernel<kWarps><<<dim3(a.tiles() * 4 / kWarps, a.heads), kWarps * 32, smem, s>>>(
+      qkv, (const float*)a.d_out, a.bits, a.threshold, dqkv, g);
+  count_launch();
+  if ((st = check_last())) return st;
+  // d_xn = dQKV . Wqkv        [n, 3d] x [3d, d]
+  dim3 g1((d + 63) / 64, (unsigned)((n + 63) / 64), 1);
+  gemm_f32_kernel<false, false, false, false><<<g1, 256, 0, s>>>(dqkv, (const float*)a.w_qkv, nullptr, (float*)a.d_xn,
+                                                                 (int)n, d, d3, d3);
+  count_launch();
+  if ((st = check_last())) return st;
+  // d_w = dQKV^T . xn         [3d, n] x [n, d]   (split-K over tokens, atomics into zeroed d_w)
+  cudaMemsetAsync(a.d_w, 0, sizeof(float) * d3 * d, s);
+  cudaMemsetAsync(a.d_b, 0, sizeof(float) * d3, s);
+  int splits = (int)((n + 2047) / 2048);
+  if (splits > 512) splits = 512;
+  int kps = (int)(((n + splits - 1) / splits + 15) / 16 * 16);
+  dim3 g2((d + 63) / 64, (d3 + 63) / 64, (unsigned)((n + kps - 1) / kps));
+  gemm_f32_kernel<true, false, true, false><<<g2, 256, 0, s>>>(dqkv, (const float*)a.xn, nullptr, a.d_w, d3, d, (int)n, kps);
+  count_launch();
+  if ((st = check_last())) return st;
+  long long rpb = 512;
+  dim3 g3((d3 + 127) / 128, (unsigned)((n + rpb - 1) / rpb));
+  colsum_f32_kernel<<<g3, 128, 0, s>>>(dqkv, a.d_b, n, d3, rpb);
+  count_launch();
+  return check_last();
+}
+
+}  // namespace hwgat

@@ -1,0 +1,132 @@
+// Shared device helpers for the hwgat_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hwgat_b200.h"
+
+#define HW_DEV __device__ __forceinline__
+
+namespace hwgat {
+
+constexpr float kNegFill = -10000.0f;  // HWGATE.py:110
+constexpr int kWin = 16;               // keypoints per window (W)
+constexpr int kTP = 2;                 // frames per window
+constexpr int kTok = 32;               // tokens per window (N = TP*W)
+constexpr int kHd = 64;                // head dim at every level
+constexpr int kTileTok = 128;          // tokens per tile = one temporal group = 4 windows x 32
+
+// Every launch made by the library is counted (hwgat_launch_count()).
+extern unsigned long long g_launches;
+inline void count_launch(int n = 1) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+// ---- geometry of one tile -------------------------------------------------
+// A tile is 4 keypoint windows (64 keypoints, group kg) of temporal group fi of
+// sample b: frames (2*fi + tp + shift) mod F, tp = 0,1 - i.e.
+// window_partition(torch.roll(x, -shift)) without the copy (HWGATE.py:197-201).
+// Rows inside a tile are window-major:
+//   row = w*32 + tp*16 + k   <->   frame(tp), keypoint kg*64 + w*16 + k
+// so that rows [32w, 32w+32) are exactly window (b*f+fi)*nW + kg*4 + w with the
+// reference's token order tp*W + k (HWGATE.py:34-35).  In the WINDOWS layout the
+// caller has already partitioned, and tile t is simply rows [128t, 128t+128).
+struct TileGeom {
+  int F, K, d, shift, layout;
+  int f, kgroups;  // F/2, K/64
+  HW_DEV int tiles_per_sample() const { return f * kgroups; }
+  // first mask word (row 0 of window w=0) of this tile: bits + mask_base(tile) + w*32 + i
+  HW_DEV int mask_base(int tile) const {
+    int r = tile % (f * kgroups);
+    int fi = r / kgroups, kg = r - fi * kgroups;
+    return (fi * (kgroups * 4) + kg * 4) * kTok;
+  }
+  HW_DEV long long token_row(int tile, int row) const {
+    if (layout == HWGAT_LAYOUT_WINDOWS) return (long long)tile * kTileTok + row;
+    int b = tile / (f * kgroups);
+    int r = tile - b * (f * kgroups);
+    int fi = r / kgroups, kg = r - fi * kgroups;
+    int w = row >> 5, tp = (row >> 4) & 1, k = row & 15;
+    int fr = 2 * fi + tp + shift;
+    fr = fr >= F ? fr - F : fr;
+    return ((long long)(b * F + fr) * K + kg * 64 + w * kWin + k);
+  }
+};
+inline TileGeom make_geom(int F, int K, int d, int shift, int layout) {
+  TileGeom g;
+  g.F = F; g.K = K; g.d = d; g.shift = shift; g.layout = layout; g.f = F / 2; g.kgroups = K / 64;
+  return g;
+}
+
+// ---- PTX wrappers -----------------------------------------------------------
+HW_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+HW_DEV void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
+}
+HW_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+HW_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+HW_DEV void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+HW_DEV void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
+HW_DEV void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+HW_DEV uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+HW_DEV float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+HW_DEV float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// streaming 16-byte global access (data touched once: keep it out of L1)
+HW_DEV int4 ld_stream16(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+HW_DEV void st_stream16(void* p, const int4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+// ---- launchers implemented in the .cu files --------------------------------
+int launch_adjacency(const int32_t* edges, int n_edges, int nW, int W, int TP, float* adj, cudaStream_t s);
+int launch_mask_bits(const float* adj, int nW, int W, int TP, int F, int shift, uint32_t* bits, cudaStream_t s);
+int launch_mask_pack(const float* adj, int adj_windows, const float* mask, int n_windows, int N, uint32_t* bits,
+                     cudaStream_t s);
+int launch_merge(const void* src, void* dst, int B, int F, int K, int d, int elem_bytes, bool backward, cudaStream_t s);
+
+struct AttnArgs {
+  const void* xn; const void* w_qkv; const float* b_qkv; const uint32_t* bits;
+  float threshold;
+  void* out;                 // fwd
+  const void* d_out;         // bwd
+  void* d_xn; float* d_w; float* d_b;
+  void* workspace;
+  int B, F, K, d, heads, shift, layout;
+  long long tokens() const { return (long long)B * F * K; }
+  int tiles() const { return B * (F / 2) * (K / 64); }
+};
+int attn_fwd_f32(const AttnArgs& a, cudaStream_t s);
+int attn_bwd_f32(const AttnArgs& a, cudaStream_t s);
+int attn_fwd_bf16(const AttnArgs& a, cudaStream_t s);
+int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s);
+
+}  // namespace hwgat

@@ -1,0 +1,326 @@
+"""B200-native HWGATE: drop-in for hwgat/models/HWGATE.py.
+
+Same class names, constructor signatures, forward signatures and state_dict
+keys as the reference, so `utils.load_model` (utils.py:55-59), checkpoints
+(utils.py:185-237) and `inference.py:95` work unchanged.  What differs is what
+runs: the roll / window_partition / QKV / masked attention / window_reverse /
+roll-back chain of every block is ONE call into the hand-written sm_100a
+kernels (sl_hwgat_b200.ops.window_graph_attention: K2 forward, K3 backward with
+recompute), the masks are packed bitmasks built on the GPU (K1), and
+TemporalMerging is kernel K4.  Nothing here falls back to PyTorch attention: on
+a non-CUDA tensor the ops raise.
+
+Precision: fp32 tensors take the true-fp32 kernels (1e-5 parity mode).  Inside
+`torch.autocast("cuda", dtype=torch.bfloat16)` the attention runs the bf16
+tensor-core kernels (activations/weights bf16, accumulation fp32), matching
+what autocast does to the reference's qkv / matmul ops.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from sl_hwgat_b200 import ops
+from sl_hwgat_b200.ops import LAYOUT_BFKD, LAYOUT_WINDOWS
+
+
+def _trunc_normal_(tensor, std):
+    # timm's trunc_normal_(std=.02) as used at HWGATE.py:335 == torch's, cut at +-2
+    return nn.init.trunc_normal_(tensor, mean=0.0, std=std, a=-2.0, b=2.0)
+
+
+def _attn_dtype(x):
+    """bf16 kernels under bf16 autocast or for bf16 inputs, fp32 kernels otherwise."""
+    if x.dtype == torch.bfloat16:
+        return torch.bfloat16
+    if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        return torch.bfloat16
+    return torch.float32
+
+
+class PositionalEncoding(nn.Module):
+    """Sinusoid over the frame axis + dropout (HWGATE.py:8-28); buffer `pe` is (1, max_len, 1, d)."""
+
+    def __init__(self, d_model, dropout, max_len=5000):
+        super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        pos = torch.arange(max_len, dtype=torch.float32)[:, None]
+        freq = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float32) * (-math.log(10000.0) / d_model))
+        table = torch.empty(max_len, d_model)
+        table[:, 0::2] = torch.sin(pos * freq)
+        table[:, 1::2] = torch.cos(pos * freq)
+        self.register_buffer('pe', table[None, :, None, :])
+
+    def forward(self, x):
+        return self.dropout(x + self.pe[:, :x.size(1)])
+
+
+def window_partition(x, window_size=16, temporal_patch_size=4):
+    """(B,F,K,d) -> (B*f*nW, TP*W, d) (HWGATE.py:30-36).  Kept for callers that
+    want the partitioned view; the blocks below never materialise it."""
+    B, F, K, d = x.shape
+    f, nW = F // temporal_patch_size, K // window_size
+    x = x.reshape(B, f, temporal_patch_size, nW, window_size, d).permute(0, 1, 3, 2, 4, 5)
+    return x.reshape(B * f * nW, temporal_patch_size * window_size, d)
+
+
+def window_reverse(x, window_size=16, temporal_patch_size=4, temporal_dim=128, num_kp=64):
+    """Inverse of window_partition (HWGATE.py:39-47)."""
+    f, nW = temporal_dim // temporal_patch_size, num_kp // window_size
+    d = x.shape[-1]
+    B = x.shape[0] // (f * nW)
+    x = x.reshape(B, f, nW, temporal_patch_size, window_size, d).permute(0, 1, 3, 2, 4, 5)
+    return x.reshape(B, temporal_dim, num_kp, d)
+
+
+class TemporalMerging(nn.Module):
+    """(B,F,K,d) -> (B,F/TP,K,TP*d), no parameters (HWGATE.py:49-63): kernel K4."""
+
+    def __init__(self, dim, temporal_patch_size):
+        super().__init__()
+        self.dim = dim
+        self.temporal_patch_size = temporal_patch_size
+
+    def forward(self, x):
+        if self.temporal_patch_size != ops.TEMPORAL_PATCH:
+            raise NotImplementedError("the merge kernel is built for temporal_patch_size == 2")
+        return ops.temporal_merge(x)
+
+
+class MSA(nn.Module):
+    """Windowed multi-head graph attention (HWGATE.py:65-118)."""
+
+    def __init__(self, dim, num_heads, adj_mat=None, attn_drop=0., proj_drop=0.) -> None:
+        super().__init__()
+        self.dim = dim
+        self.num_heads = num_heads
+        assert dim % num_heads == 0, 'dim and number of heads are incompatible'
+        head_dim = dim // num_heads
+        if head_dim != ops.HEAD_DIM:
+            raise NotImplementedError("the attention kernels are built for head_dim == 64")
+        if attn_drop != 0.:
+            raise NotImplementedError("attn_drop_rate != 0 is not supported by the fused kernels "
+                                      "(the reference default is 0.0, model_params.py:256)")
+        self.scale = head_dim ** -0.5
+        self.adj_mat = adj_mat
+        self.qkv = nn.Linear(dim, dim * 3)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.softmax = nn.Softmax(dim=-1)
+        self._bits = {}  # packed masks, keyed by how they were derived
+
+    def _draw_threshold(self):
+        # one CPU-generator scalar per call, exactly where the reference draws it (HWGATE.py:96)
+        return torch.rand(1).item() if self.training else None
+
+    def _project(self, ctx):
+        return self.proj_drop(self.proj(ctx))
+
+    # -- fast path used by PartAttentionBlock: x is the un-partitioned (B,F,K,d) tensor
+    def attend(self, xn, shift, block_bits):
+        dt = _attn_dtype(xn)
+        ctx = ops.window_graph_attention(xn.to(dt), self.qkv.weight, self.qkv.bias, block_bits, self.num_heads,
+                                         shift=shift, threshold=self._draw_threshold(), layout=LAYOUT_BFKD)
+        return self._project(ctx)
+
+    # -- reference signature: x is (B*f*nW, TP*W, d), already rolled and partitioned
+    def forward(self, x, B, f, nW, mask=None):
+        n_win, N, d = x.shape
+        if n_win != B * f * nW or N != ops.WINDOW * ops.TEMPORAL_PATCH:
+            raise ValueError("x must be (B*f*nW, 32, d)")
+        adj = self.adj_mat
+        key = (None if mask is None else (mask.data_ptr(), mask._version),
+               None if adj is None else (adj.data_ptr(), adj._version), f, nW, x.device)
+        bits = self._bits.get(key)
+        if bits is None:
+            self._bits.clear()
+            dev = x.device
+            bits = ops.mask_pack(None if adj is None else adj.to(dev), None if mask is None else mask.to(dev),
+                                 f * nW, N, dev)
+            self._bits[key] = bits
+        dt = _attn_dtype(x)
+        ctx = ops.window_graph_attention(x.to(dt), self.qkv.weight, self.qkv.bias, bits, self.num_heads, shift=0,
+                                         threshold=self._draw_threshold(), layout=LAYOUT_WINDOWS,
+                                         frames=f * ops.TEMPORAL_PATCH, kps=nW * ops.WINDOW)
+        return self._project(ctx)
+
+
+class FeedForward(nn.Module):
+    """fc1 -> act -> drop -> fc2 -> drop (HWGATE.py:120-136)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+
+
+class PartAttentionBlock(nn.Module):
+    """x + MSA(LN x) over (shifted) windows, then x + FFN(LN x) (HWGATE.py:138-221)."""
+
+    def __init__(self, dim, num_kps=64, num_heads=4, window_size=16, temporal_patch_size=4, temporal_dim=128,
+                 shift_size=0, adj_mat=None, drop=0., attn_drop=0., ff_ratio=4., act_layer=nn.GELU,
+                 norm_layer=nn.LayerNorm):
+        super().__init__()
+        if window_size != ops.WINDOW or temporal_patch_size != ops.TEMPORAL_PATCH:
+            raise NotImplementedError("the attention kernels are built for window_size 16, temporal_patch_size 2")
+        self.dim = dim
+        self.num_kps = num_kps
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.temporal_patch_size = temporal_patch_size
+        self.temporal_dim = temporal_dim
+        self.shift_size = shift_size
+        self.drop = drop
+        self.attn_drop = attn_drop
+        self.ff_dim = dim * ff_ratio
+        self.act_layer = act_layer
+
+        self.norm1 = norm_layer(dim)
+        self.attn = MSA(dim, num_heads=num_heads, adj_mat=adj_mat, attn_drop=attn_drop, proj_drop=drop)
+        self.norm2 = norm_layer(dim)
+        self.ff = FeedForward(in_features=dim, hidden_features=int(self.ff_dim), act_layer=act_layer, drop=drop)
+
+        # `attn_mask` stays a float buffer with the reference's name and shape (f*nW, N, N)
+        # so that checkpoints round-trip (HWGATE.py:169-187); the kernels use the packed
+        # form built by K1 in _block_bits().
+        if self.shift_size > 0:
+            f, nW = temporal_dim // temporal_patch_size, num_kps // window_size
+            frame = torch.arange(temporal_dim)
+            group = (frame >= temporal_dim - temporal_patch_size).long() + (frame >= temporal_dim - shift_size).long()
+            tok_group = group.reshape(f, temporal_patch_size, 1).expand(f, temporal_patch_size, window_size)
+            tok_group = tok_group.reshape(f, 1, -1).expand(f, nW, -1).reshape(f * nW, -1)
+            attn_mask = (tok_group[:, :, None] == tok_group[:, None, :]).float()
+        else:
+            attn_mask = None
+        self.register_buffer("attn_mask", attn_mask)
+        self._bits = None
+
+    def _block_bits(self, device):
+        if self._bits is None or self._bits.device != device:
+            adj = self.attn.adj_mat
+            nW = self.num_kps // self.window_size
+            if adj is None:
+                adj = torch.ones(nW, 32, 32)
+            # the layer hands in the adjacency replicated over temporal groups (HWGATE.py:309);
+            # K1b replicates by index, so only the first nW windows are needed
+            self._bits = ops.mask_build(adj[:nW].to(device), self.temporal_dim, self.shift_size,
+                                        self.window_size, self.temporal_patch_size)
+        return self._bits
+
+    def forward(self, x):
+        B, F, K, d = x.shape
+        if F != self.temporal_dim or K != self.num_kps:
+            raise ValueError(f"expected (B,{self.temporal_dim},{self.num_kps},d), got {tuple(x.shape)}")
+        x = x + self.attn.attend(self.norm1(x), self.shift_size, self._block_bits(x.device))
+        return x + self.ff(self.norm2(x))
+
+
+class PartAttentionLayer(nn.Module):
+    """`depth` blocks, odd ones shifted by TP//2 frames, then the merge (HWGATE.py:223-258)."""
+
+    def __init__(self, dim, temporal_patch_size, temporal_dim, num_kps, depth, num_heads, window_size, adj_mat,
+                 drop=0., attn_drop=0., ff_ratio=4., norm_layer=nn.LayerNorm, downsample=None, i_layer=0,
+                 device=None):
+        super().__init__()
+        self.dim = dim
+        self.depth = depth
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.adj_mat = adj_mat.to(device) if adj_mat is not None else None
+        self.i_layer = i_layer
+        self.blocks = nn.ModuleList([
+            PartAttentionBlock(dim=dim, num_kps=num_kps, num_heads=num_heads, window_size=window_size,
+                               temporal_patch_size=temporal_patch_size, temporal_dim=temporal_dim,
+                               shift_size=0 if (i % 2 == 0) else temporal_patch_size // 2,
+                               adj_mat=self.adj_mat, drop=drop, attn_drop=attn_drop, ff_ratio=ff_ratio,
+                               norm_layer=norm_layer)
+            for i in range(depth)])
+        self.downsample = downsample(dim, temporal_patch_size) if downsample is not None else None
+
+    def forward(self, x):
+        for blk in self.blocks:
+            x = blk(x)
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return x
+
+
+class Model(nn.Module):
+    """HWGATE classifier: (B,T,K,C) keypoints -> (B,num_classes) (HWGATE.py:260-360)."""
+
+    def __init__(self, kp_dim=26, num_kps=64, temporal_dim=256, num_classes=1000, embed_dim=64,
+                 temporal_patch_size=4, pe=False, depths=[2, 2, 6, 2], num_heads=[2, 4, 8, 16], window_size=16,
+                 adj_mat=None, drop_rate=0., attn_drop_rate=0., ff_ratio=4., norm_layer=nn.LayerNorm,
+                 device=None) -> None:
+        super().__init__()
+        self.kp_dim = kp_dim
+        self.num_kps = num_kps
+        self.temporal_dim = temporal_dim
+        self.window_size = window_size
+        self.num_classes = num_classes
+        self.num_layers = len(depths)
+        self.pe = pe
+        self.adj_mat = adj_mat
+        self.embed_dim = embed_dim
+        self.num_features = int(embed_dim * 2 ** (self.num_layers - 1))
+        self.temporal_out_dim = temporal_dim // temporal_patch_size ** (self.num_layers - 1)
+
+        assert self.num_kps % window_size == 0, "window size and number of kps are incompatible"
+        assert self.temporal_dim % temporal_patch_size == 0, \
+            "temporal dimension and temporal patch size are incompatible"
+
+        # frozen Gaussian Fourier features, std 10 (HWGATE.py:293-299)
+        self.B = nn.Parameter(torch.randn(embed_dim // 2, self.kp_dim) * 10.0, requires_grad=False)
+        if self.pe:
+            self.pos_encoder = PositionalEncoding(embed_dim, drop_rate, temporal_dim)
+
+        self.layers = nn.ModuleList()
+        for i in range(self.num_layers):
+            frames = temporal_dim // temporal_patch_size ** i
+            # the reference replicates the adjacency over the temporal groups of the level
+            # (HWGATE.py:309); kept so that layer.adj_mat has the reference's shape
+            adj_t = torch.cat([adj_mat] * (frames // temporal_patch_size)) if adj_mat is not None else None
+            self.layers.append(PartAttentionLayer(
+                dim=int(embed_dim * 2 ** i), temporal_patch_size=temporal_patch_size, temporal_dim=frames,
+                num_kps=num_kps, depth=depths[i], num_heads=num_heads[i], window_size=window_size, adj_mat=adj_t,
+                drop=drop_rate, attn_drop=attn_drop_rate, ff_ratio=ff_ratio, norm_layer=norm_layer,
+                downsample=TemporalMerging if i < self.num_layers - 1 else None, i_layer=i, device=device))
+
+        self.norm = norm_layer(self.num_features)
+        self.avgpool = nn.AvgPool1d(self.temporal_out_dim * self.num_kps)
+        self.head = nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity()
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            _trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def forward_features(self, x):
+        # the embedding stays fp32 even under autocast: bf16 rounds 2*pi*x.B (values up to
+        # ~300) by up to 2 rad
+        with torch.autocast(device_type=x.device.type, enabled=False):
+            proj = (2. * math.pi * x.float()) @ self.B.float().t()
+            x = torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1)
+        if self.pe:
+            x = self.pos_encoder(x)
+        for layer in self.layers:
+            x = layer(x)
+        B, f, K, d = x.shape
+        x = self.norm(x)
+        return self.avgpool(x.reshape(B, f * K, d).transpose(1, 2)).squeeze(-1)
+
+    def forward(self, x):
+        return self.head(self.forward_features(x))

@@ -1,0 +1,73 @@
+"""HWGATE hyper-parameters and skeleton graph: drop-in for the HWGATEParams class
+of hwgat/models/model_params.py:243-403 (same constructor, same attributes, same
+get_model_params() tuple).  The adjacency tensor is built on the GPU by kernel
+K1a (hwgat_adjacency_build) instead of host numpy loops."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from sl_hwgat_b200 import ops
+
+# One window = 16 keypoints laid out by WindowCreate (dataTransform.py:426-455):
+# slots 0-2 head, 3-5 arm, 6-15 hand.  The skeleton has a 3-star on the head,
+# the arm chain into the wrist (slot 6), five 2-joint fingers fanning out of the
+# wrist, and links between neighbouring fingers.  Same 25 undirected edges as
+# model_params.py:261-369 (all four windows share them), written by structure
+# rather than as a literal list.
+def _window_edges():
+    head = [(0, 1), (0, 2)]
+    arm = [(0, 3), (3, 4), (4, 5), (5, 6)]
+    thumb = [(6, 7)]
+    finger_bases = [8, 10, 12, 14]
+    palm = [(6, b) for b in finger_bases]
+    finger = [(b, b + 1) for b in finger_bases]
+    knuckles = [(finger_bases[i], finger_bases[i + 1]) for i in range(3)]
+    tips = [(7, 9), (9, 11), (11, 13), (13, 15), (7, 15), (7, 11), (7, 13)]
+    return [list(e) for e in head + arm + thumb + palm + finger + knuckles + tips]
+
+
+class HWGATEParams():
+    def __init__(self, dataset_params, input_dim, device=None) -> None:
+        self.kp_dim = input_dim
+        self.num_kps = 64
+        self.temporal_dim = dataset_params['src_len']
+        self.num_classes = dataset_params['num_class']
+        self.embed_dim = 128
+        self.temporal_patch_size = 2
+        self.pe = True
+        self.depths = [2, 2, 4]
+        self.num_heads = [2, 4, 8]
+        self.window_size = 16
+        self.drop_rate = 0.1
+        self.attn_drop_rate = 0.0
+        self.ff_ratio = 2.
+        self.norm_layer = nn.LayerNorm
+        self.device = device
+        self.edges = [_window_edges() for _ in range(self.num_kps // self.window_size)]
+        # the reference hands the model a CPU float32 tensor (model_params.py:259)
+        self.adj_mat = self.get_adj_mat().cpu()
+
+    def _cuda_device(self):
+        dev = torch.device(self.device) if self.device is not None else None
+        if dev is None or dev.type != "cuda":
+            if not torch.cuda.is_available():
+                raise RuntimeError("HWGATEParams builds the adjacency with a CUDA kernel and no CUDA "
+                                   "device is available; there is no CPU fallback")
+            dev = torch.device("cuda", torch.cuda.current_device())
+        return dev
+
+    def get_adj_mat(self):
+        """(nW, TP*W, TP*W) float32 (model_params.py:373-392), via kernel K1a."""
+        return ops.adjacency_build(self.edges, self.window_size, self.temporal_patch_size, self._cuda_device())
+
+    def get_adj(self, index):
+        """(W, W) skeleton adjacency of window `index` (model_params.py:394-400):
+        the same-frame block of the K1a output."""
+        W = self.window_size
+        return self.get_adj_mat()[index, :W, :W].cpu().numpy()
+
+    def get_model_params(self):
+        return (self.kp_dim, self.num_kps, self.temporal_dim, self.num_classes, self.embed_dim,
+                self.temporal_patch_size, self.pe, self.depths, self.num_heads, self.window_size, self.adj_mat,
+                self.drop_rate, self.attn_drop_rate, self.ff_ratio, self.norm_layer, self.device)

@@ -1,0 +1,205 @@
+"""Host side of the hot path: torch.autograd.Functions over the C ABI.
+
+Every function here hands device pointers and the current CUDA stream to
+libhwgat_b200.so (include/hwgat_b200.h).  Tensors are allocated by PyTorch
+(device memory + caching allocator = plumbing); all arithmetic of the path runs
+in the hand-written kernels.  A tensor that is not on a CUDA device is an error:
+there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, LAYOUT_BFKD, LAYOUT_WINDOWS, check
+
+WINDOW = 16       # keypoints per window the kernels are built for (model_params.py:254)
+TEMPORAL_PATCH = 2  # frames per window (model_params.py:250)
+HEAD_DIM = 64
+
+
+def _need_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.HwgatError(
+                "sl_hwgat_b200 runs on sm_100a CUDA kernels only; got a tensor on "
+                f"{t.device}. There is no CPU fallback.")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise _lib.HwgatError(f"unsupported dtype {t.dtype}: the kernels take float32 or bfloat16")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------
+# K1: adjacency and packed masks
+# --------------------------------------------------------------------------
+
+def adjacency_build(edges: Sequence[Sequence[Sequence[int]]], window: int, temporal_patch: int,
+                    device) -> torch.Tensor:
+    """(nW, TP*W, TP*W) float32 adjacency on `device`.
+    Replaces HWGATEParams.get_adj_mat (model_params.py:373-400)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.HwgatError("adjacency_build needs a CUDA device (no CPU fallback)")
+    nW = len(edges)
+    n_edges = len(edges[0]) if nW else 0
+    if any(len(e) != n_edges for e in edges):
+        raise ValueError("every window must list the same number of edges")
+    e = torch.tensor(edges, dtype=torch.int32).reshape(nW, n_edges, 2).to(device)
+    N = window * temporal_patch
+    adj = torch.empty((nW, N, N), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(lib.hwgat_adjacency_build(e.data_ptr(), n_edges, nW, window, temporal_patch, adj.data_ptr(),
+                                        _stream()), "hwgat_adjacency_build")
+    return adj
+
+
+def mask_build(adj: torch.Tensor, frames: int, shift: int, window: int = WINDOW,
+               temporal_patch: int = TEMPORAL_PATCH) -> torch.Tensor:
+    """Packed mask (frames/TP * nW, N, N/32) uint32 (stored as int32) of one block:
+    adjacency AND shifted-window mask.  Replaces HWGATE.py:169-187, 309, 102-108."""
+    lib = _lib.load()
+    _need_cuda(adj)
+    adj = adj.contiguous().float()
+    nW, N = adj.shape[0], adj.shape[1]
+    bits = torch.empty((frames // temporal_patch * nW, N, N // 32), dtype=torch.int32, device=adj.device)
+    with torch.cuda.device(adj.device):
+        check(lib.hwgat_mask_build(adj.data_ptr(), nW, window, temporal_patch, frames, shift, bits.data_ptr(),
+                                   _stream()), "hwgat_mask_build")
+    return bits
+
+
+def mask_pack(adj: Optional[torch.Tensor], mask: Optional[torch.Tensor], n_windows: int, N: int,
+              device) -> torch.Tensor:
+    """Pack caller-provided float masks: bits = (adj != 0) & (mask != 0)
+    (the two multiplies of MSA.forward, HWGATE.py:102-108)."""
+    lib = _lib.load()
+    _need_cuda(adj, mask)
+    adj_c = adj.contiguous().float() if adj is not None else None
+    mask_c = mask.contiguous().float() if mask is not None else None
+    bits = torch.empty((n_windows, N, N // 32), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        check(lib.hwgat_mask_pack(_ptr(adj_c), 0 if adj_c is None else adj_c.shape[0], _ptr(mask_c), n_windows, N,
+                                  bits.data_ptr(), _stream()), "hwgat_mask_pack")
+    return bits
+
+
+# --------------------------------------------------------------------------
+# K2 / K3: fused windowed graph attention
+# --------------------------------------------------------------------------
+
+class _WindowGraphAttention(torch.autograd.Function):
+    """out = PV(softmax(mask(QK^T))) of every window, from the normalised
+    residual stream; forward saves only its inputs (K3 recomputes)."""
+
+    @staticmethod
+    def forward(ctx, xn, w_qkv, b_qkv, bits, threshold, heads, shift, layout, frames, kps):
+        lib = _lib.load()
+        _need_cuda(xn, w_qkv, b_qkv, bits)
+        code = _dtype_code(xn)
+        xn_c = xn.contiguous()
+        d = xn_c.shape[-1]
+        n_tok = xn_c.numel() // d
+        if frames * kps == 0 or n_tok % (frames * kps) != 0:
+            raise ValueError(f"token count {n_tok} is not a multiple of frames*keypoints = {frames * kps}")
+        B = n_tok // (frames * kps)
+        w_c = w_qkv.detach().to(xn_c.dtype).contiguous()
+        b_c = b_qkv.detach().float().contiguous()
+        out = torch.empty_like(xn_c)
+        ws_bytes = lib.hwgat_attn_workspace_bytes(B, frames, kps, d, heads, code, 0)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xn_c.device) if ws_bytes else None
+        with torch.cuda.device(xn_c.device):
+            check(lib.hwgat_attn_fwd(xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
+                                     float(threshold), out.data_ptr(), _ptr(ws), ws_bytes, B, frames, kps, d, heads,
+                                     WINDOW, TEMPORAL_PATCH, shift, layout, code, _stream()), "hwgat_attn_fwd")
+        ctx.save_for_backward(xn_c, w_c, b_c, bits)
+        ctx.meta = (float(threshold), heads, shift, layout, frames, kps, B, d, code, w_qkv.dtype, b_qkv.dtype)
+        return out.view_as(xn)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        xn_c, w_c, b_c, bits = ctx.saved_tensors
+        threshold, heads, shift, layout, frames, kps, B, d, code, w_dtype, b_dtype = ctx.meta
+        g = d_out.to(xn_c.dtype).contiguous()
+        d_xn = torch.empty_like(xn_c)
+        d_w = torch.empty((3 * d, d), dtype=torch.float32, device=xn_c.device)
+        d_b = torch.empty((3 * d,), dtype=torch.float32, device=xn_c.device)
+        ws_bytes = lib.hwgat_attn_workspace_bytes(B, frames, kps, d, heads, code, 1)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xn_c.device)
+        with torch.cuda.device(xn_c.device):
+            check(lib.hwgat_attn_bwd(g.data_ptr(), xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
+                                     threshold, d_xn.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), B, frames, kps, d, heads, WINDOW, TEMPORAL_PATCH, shift, layout,
+                                     code, _stream()), "hwgat_attn_bwd")
+        return (d_xn.view_as(d_out), d_w.to(w_dtype), d_b.to(b_dtype), None, None, None, None, None, None, None)
+
+
+def window_graph_attention(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, bits: torch.Tensor,
+                           heads: int, shift: int = 0, threshold: Optional[float] = None,
+                           layout: int = LAYOUT_BFKD, frames: Optional[int] = None,
+                           kps: Optional[int] = None) -> torch.Tensor:
+    """Fused roll + window_partition + QKV + masked attention + window_reverse +
+    roll back (HWGATE.py:197-201, 86-114, 207-215), without the output projection.
+
+    xn: (B, F, K, d) for LAYOUT_BFKD, or (B*f*nW, 32, d) for LAYOUT_WINDOWS (then
+    `frames` and `kps` must be given).  threshold None = eval mode."""
+    if layout == LAYOUT_BFKD:
+        frames, kps = xn.shape[1], xn.shape[2]
+    elif frames is None or kps is None:
+        raise ValueError("LAYOUT_WINDOWS needs frames and kps")
+    thr = -1.0 if threshold is None else float(threshold)
+    return _WindowGraphAttention.apply(xn, w_qkv, b_qkv, bits, thr, heads, shift, layout, frames, kps)
+
+
+# --------------------------------------------------------------------------
+# K4: temporal merge
+# --------------------------------------------------------------------------
+
+class _TemporalMerge(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        _need_cuda(x)
+        code = _dtype_code(x)
+        x_c = x.contiguous()
+        B, F, K, d = x_c.shape
+        out = torch.empty((B, F // TEMPORAL_PATCH, K, d * TEMPORAL_PATCH), dtype=x_c.dtype, device=x_c.device)
+        with torch.cuda.device(x_c.device):
+            check(lib.hwgat_merge_fwd(x_c.data_ptr(), out.data_ptr(), B, F, K, d, TEMPORAL_PATCH, code, _stream()),
+                  "hwgat_merge_fwd")
+        ctx.shape = (B, F, K, d, code)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        B, F, K, d, code = ctx.shape
+        g_c = g.contiguous()
+        d_x = torch.empty((B, F, K, d), dtype=g_c.dtype, device=g_c.device)
+        with torch.cuda.device(g_c.device):
+            check(lib.hwgat_merge_bwd(g_c.data_ptr(), d_x.data_ptr(), B, F, K, d, TEMPORAL_PATCH, code, _stream()),
+                  "hwgat_merge_bwd")
+        return d_x
+
+
+def temporal_merge(x: torch.Tensor) -> torch.Tensor:
+    """(B,F,K,d) -> (B,F/2,K,2d); replaces TemporalMerging.forward (HWGATE.py:55-63)."""
+    if x.shape[1] % TEMPORAL_PATCH != 0:
+        raise ValueError("frame count must be a multiple of the temporal patch size")
+    return _TemporalMerge.apply(x)

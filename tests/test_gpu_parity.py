@@ -1,0 +1,245 @@
+"""GPU parity tests proper: every call goes through the C ABI
+(sl_hwgat_b200.ops -> ctypes -> libhwgat_b200.so) and is compared with
+ (a) the committed golden fixtures = outputs of the unmodified reference, and
+ (b) the fp64 CPU oracle on the same seeded inputs.
+Tolerances are the north_star's: fp32 1e-5 relative, bf16 2e-2 relative,
+masks and index maps bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hwgate_oracle as O
+from tests._util import ADJ, CFG, core_inputs, cuda_core, device_bits, oracle_core, rel_inf, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5     # north_star: "fp32 within 1e-5 relative"
+BF16_TOL = 2e-2     # north_star: "bf16 within 2e-2 relative"
+LEVELS = ((128, 2), (256, 4), (512, 8))
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ------------------------------------------------------------------ K1
+def test_adjacency_bit_exact(golden_dir):
+    from sl_hwgat_b200 import ops
+    adj = ops.adjacency_build(CFG.edges, 16, 2, "cuda").cpu().numpy()
+    g = _load(golden_dir, "masks.npz")
+    assert adj.dtype == np.float32 and adj.shape == (4, 32, 32)
+    assert np.array_equal(adj, g["adj"].astype(np.float32))          # reference get_adj_mat()
+    assert np.array_equal(adj != 0, ADJ)                              # oracle
+
+
+def test_adjacency_other_graphs():
+    """ragged / degenerate graphs: no edges, a chain, out-of-range edges ignored."""
+    from sl_hwgat_b200 import ops
+    chain = [[[i, i + 1] for i in range(15)]] * 2
+    a = ops.adjacency_build(chain, 16, 2, "cuda").cpu().numpy() != 0
+    assert np.array_equal(a, O.window_adjacency(chain, 16, 2))
+    none = [[], [], []]
+    a = ops.adjacency_build(none, 16, 2, "cuda").cpu().numpy() != 0
+    assert np.array_equal(a, O.window_adjacency(none, 16, 2))
+
+
+@pytest.mark.parametrize("F", [64, 32, 16, 8, 4])
+@pytest.mark.parametrize("shift", [0, 1])
+def test_mask_bits_bit_exact(golden_dir, F, shift):
+    g = _load(golden_dir, "masks.npz")
+    bits = device_bits(F, shift).cpu().numpy().view(np.uint32)
+    assert np.array_equal(bits, g[f"bits_F{F}_s{shift}"])            # reference adj * attn_mask, packed
+
+
+@pytest.mark.parametrize("F,shift", [(2, 0), (2, 1), (192, 1), (256, 1), (6, 1)])
+def test_mask_bits_other_lengths(F, shift):
+    bits = device_bits(F, shift).cpu().numpy().view(np.uint32)
+    want = O.pack_mask_bits(O.combined_mask(ADJ, F, 16, 2, shift))
+    assert np.array_equal(bits, want)
+
+
+def test_mask_pack_matches_mask_build():
+    """K1c on the float tensors MSA.forward receives == K1b's analytic mask."""
+    from sl_hwgat_b200 import ops
+    F = 16
+    adj = torch.from_numpy(ADJ.astype(np.float32)).cuda()
+    sm = torch.from_numpy(O.shift_window_mask(F, 4, 16, 2, 1).astype(np.float32)).cuda()
+    packed = ops.mask_pack(adj, sm, (F // 2) * 4, 32, "cuda")
+    assert torch.equal(packed, device_bits(F, 1))
+    assert torch.equal(ops.mask_pack(adj, None, (F // 2) * 4, 32, "cuda"), device_bits(F, 0))
+    ones = ops.mask_pack(None, None, 3, 32, "cuda").cpu().numpy().view(np.uint32)
+    assert (ones == 0xFFFFFFFF).all()
+
+
+# ------------------------------------------------------------------ K4
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 8, 64, 128), (1, 2, 64, 256), (3, 6, 64, 8), (5, 4, 128, 512)])
+def test_merge_bit_exact(dtype, shape):
+    from sl_hwgat_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(shape, generator=g).to(dtype)
+    xc = x.cuda().requires_grad_(True)
+    y = ops.temporal_merge(xc)
+    assert torch.equal(y.cpu(), O.temporal_merge(x, 2))
+    gy = torch.randn(y.shape, generator=g).to(dtype)
+    y.backward(gy.cuda())
+    assert torch.equal(xc.grad.cpu(), O.temporal_merge_backward(gy, 2))
+
+
+def test_merge_golden_index_map(golden_dir):
+    from sl_hwgat_b200 import ops
+    g = _load(golden_dir, "index_maps.npz")
+    x = torch.arange(2 * 8 * 64 * 4, dtype=torch.float32).reshape(2, 8, 64, 4)
+    y = ops.temporal_merge(x.cuda()).cpu()
+    # the fixture was made with d=3; compare on the first 3 channels through the same index map
+    ref = O.temporal_merge(x, 2)
+    assert torch.equal(y, ref)
+    x3 = torch.arange(2 * 8 * 64 * 3, dtype=torch.float64).reshape(2, 8, 64, 3)
+    assert np.array_equal(O.temporal_merge(x3, 2).numpy().astype(np.int32), g["merge"])
+
+
+def test_merge_empty_batch():
+    from sl_hwgat_b200 import ops
+    y = ops.temporal_merge(torch.empty(0, 4, 64, 128, device="cuda"))
+    assert y.shape == (0, 2, 64, 256)
+
+
+def test_merge_full_size_round_trip():
+    """BASELINE config 3 size (B=512, T=64, d=128, bf16): merge then its adjoint is the identity."""
+    from sl_hwgat_b200 import ops
+    x = torch.randn(512, 64, 64, 128, device="cuda", dtype=torch.bfloat16).requires_grad_(True)
+    y = ops.temporal_merge(x)
+    y.backward(y.detach())
+    assert torch.equal(x.grad, x.detach())
+    assert y.shape == (512, 32, 64, 256)
+    # checksum: a permutation keeps the multiset of values
+    assert torch.equal(y.detach().float().sum(dim=(1, 2, 3)), x.detach().float().sum(dim=(1, 2, 3))) or \
+        torch.allclose(y.detach().float().sum(), x.detach().float().sum(), rtol=1e-3)
+
+
+# ------------------------------------------------------------------ K2 / K3, fp32
+def _core_cases():
+    for (d, h) in LEVELS:
+        for shift in (0, 1):
+            for thr in (None, 0.02, 0.04, 0.2):
+                for std in (0.02, 0.2):
+                    if thr in (0.02, 0.2) and std == 0.02:
+                        continue
+                    yield d, h, shift, thr, std
+
+
+@pytest.mark.parametrize("d,h,shift,thr,std", list(_core_cases()))
+def test_attention_fp32_vs_reference_golden(golden_dir, d, h, shift, thr, std):
+    """CUDA fp32 K2/K3 against outputs of the unmodified reference (fp64) on the same inputs."""
+    G = _load(golden_dir, "attention_core.npz")
+    key = f"d{d}_s{shift}_thr{thr}_std{std}"
+    xn, w, b, g = core_inputs(d, shift, std)
+    y, dx, dw, db = cuda_core(xn, w, b, g, h, shift, thr, torch.float32)
+
+    def chk(t, name, stride, tol):
+        a = t.detach().double().cpu().reshape(-1).numpy()
+        ref = G[key + "_" + name]
+        err = np.abs(a[::stride] - ref).max() / np.abs(ref).max()
+        assert err < tol, f"{key} {name}: rel err {err:.3e}"
+        s = G[key + "_" + name + "sum"]
+        assert abs(a.sum() - s[0]) <= tol * s[1] and a.size == int(s[2])
+
+    chk(y, "y", 127, FP32_TOL)
+    chk(dx, "dx", 127, FP32_TOL)
+    chk(dw, "dw", 509, FP32_TOL)
+    ref_db = G[key + "_db"]
+    assert np.abs(db.double().cpu().numpy() - ref_db).max() / np.abs(ref_db).max() < FP32_TOL
+
+
+@pytest.mark.parametrize("B,F", [(1, 2), (3, 8), (2, 64)])
+@pytest.mark.parametrize("d,h", LEVELS)
+@pytest.mark.parametrize("shift", [0, 1])
+@pytest.mark.parametrize("thr", [None, 0.05])
+def test_attention_fp32_vs_oracle(B, F, d, h, shift, thr):
+    if F == 64 and d != 128:
+        pytest.skip("oracle time")
+    xn, w, b, g = core_inputs(d, shift, 0.05, B=B, F=F)
+    y, dx, dw, db = cuda_core(xn, w, b, g, h, shift, thr, torch.float32)
+    ry, rdx, rdw, rdb = oracle_core(xn.float(), w.float(), b.float(), g.float(), h, F, shift, thr)
+    assert rel_inf(y, ry) < FP32_TOL
+    assert rel_inf(dx, rdx) < FP32_TOL
+    assert rel_inf(dw, rdw) < FP32_TOL
+    assert rel_inf(db, rdb) < FP32_TOL
+
+
+def test_fully_masked_rows_uniform_fp32():
+    """threshold below 1/32 drops every logit: softmax of 32 fills is uniform over all keys."""
+    d, h = 128, 2
+    xn, w, b, g = core_inputs(d, 0, 0.02)
+    y, dx, dw, db = cuda_core(xn, w, b, g, h, 0, 0.001, torch.float32)
+    ry, rdx, rdw, rdb = oracle_core(xn.float(), w.float(), b.float(), g.float(), h, 4, 0, 0.001)
+    assert rel_inf(y, ry) < FP32_TOL and rel_inf(dx, rdx) < FP32_TOL and rel_inf(dw, rdw) < FP32_TOL
+
+
+# ------------------------------------------------------------------ K2 / K3, bf16
+@pytest.mark.parametrize("d,h", LEVELS)
+@pytest.mark.parametrize("shift", [0, 1])
+@pytest.mark.parametrize("thr", [None, 0.04, 0.2])
+@pytest.mark.parametrize("std", [0.02, 0.1])
+def test_attention_bf16_vs_oracle(d, h, shift, thr, std):
+    B, F = 2, 8
+    xn, w, b, g = core_inputs(d, shift, std, B=B, F=F)
+    xn, g = xn.to(torch.bfloat16).double(), g.to(torch.bfloat16).double()
+    w = w.to(torch.bfloat16).double()
+    y, dx, dw, db = cuda_core(xn, w, b, g, h, shift, thr, torch.bfloat16)
+    ry, rdx, rdw, rdb = oracle_core(xn, w, b.float().double(), g, h, F, shift, thr)
+    errs = dict(y=rel_l2(y, ry), dx=rel_l2(dx, rdx), dw=rel_l2(dw, rdw), db=rel_l2(db, rdb))
+    assert all(e < BF16_TOL for e in errs.values()), errs
+    if thr is None:
+        # tighter: against the oracle that rounds where the kernel rounds
+        by = O.attention_core(xn, w, b.float().double(), h, O.combined_mask(ADJ, F, 16, 2, shift), 16, 2, shift,
+                              None, bf16_points=True)
+        assert rel_l2(y, by) < 4e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_windows_layout_equals_bfkd(dtype):
+    """MSA.forward's pre-partitioned input (HWGAT_LAYOUT_WINDOWS) gives the same numbers as
+    the un-partitioned path once un-partitioned."""
+    from sl_hwgat_b200 import ops
+    d, h, B, F = 256, 4, 2, 8
+    xn, w, b, g = core_inputs(d, 0, 0.05, B=B, F=F)
+    bits = device_bits(F, 0)
+    x = xn.to("cuda", dtype)
+    y0 = ops.window_graph_attention(x, w.float().cuda(), b.float().cuda(), bits, h)
+    xw = O.window_partition(x, 16, 2).contiguous()
+    yw = ops.window_graph_attention(xw, w.float().cuda(), b.float().cuda(), bits, h, layout=1, frames=F, kps=64)
+    assert torch.equal(O.window_reverse(yw, 16, 2, F, 64), y0)
+
+
+def test_attention_full_size_replication_bf16():
+    """BASELINE config 3 size (B=512, T=64, level 0): every sample is the same sequence, so every
+    sample's output and the per-sample share of dW must equal the small, oracle-checked case."""
+    from sl_hwgat_b200 import ops
+    d, h, F = 128, 2, 64
+    xn, w, b, g = core_inputs(d, 1, 0.05, B=1, F=F)
+    bits = device_bits(F, 1)
+    ys, dxs, dws, dbs = cuda_core(xn, w, b, g, h, 1, 0.05, torch.bfloat16)
+    Bbig = 512
+    yb, dxb, dwb, dbb = cuda_core(xn.expand(Bbig, -1, -1, -1).contiguous(), w, b,
+                                  g.expand(Bbig, -1, -1, -1).contiguous(), h, 1, 0.05, torch.bfloat16)
+    assert torch.equal(yb, ys.expand(Bbig, -1, -1, -1))
+    assert torch.equal(dxb, dxs.expand(Bbig, -1, -1, -1))
+    assert rel_l2(dwb, dws * Bbig) < 1e-3 and rel_l2(dbb, dbs * Bbig) < 1e-3
+
+
+def test_empty_batch_and_errors():
+    from sl_hwgat_b200 import _lib, ops
+    bits = device_bits(4, 0)
+    w = torch.zeros(384, 128, device="cuda")
+    b = torch.zeros(384, device="cuda")
+    y = ops.window_graph_attention(torch.empty(0, 4, 64, 128, device="cuda"), w, b, bits, 2)
+    assert y.shape == (0, 4, 64, 128)
+    with pytest.raises(_lib.HwgatError):      # head_dim != 64: unsupported, no fallback
+        ops.window_graph_attention(torch.zeros(1, 4, 64, 128, device="cuda"), w, b, bits, 4)
+    with pytest.raises(_lib.HwgatError):      # CPU tensor: no fallback
+        ops.window_graph_attention(torch.zeros(1, 4, 64, 128), w.cpu(), b.cpu(), bits.cpu(), 2)
+    with pytest.raises(_lib.HwgatError):      # K not a multiple of 64
+        ops.window_graph_attention(torch.zeros(1, 4, 48, 128, device="cuda"), w, b, bits, 2)

@@ -1,0 +1,169 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header
+declares, the drop-in module keeps the reference's state_dict, the product path
+fails loudly without CUDA, and the data-parallel host logic (gloo, world 2)."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hwgate_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sl_hwgat_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "hwgat_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(hwgat_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.hwgat_version() == _lib.ABI_VERSION
+    assert b"no fallback" in lib.hwgat_error_string(1002)
+    # size query is pure host arithmetic: qkv + dqkv in fp32, dqkv only in bf16
+    assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.F32, 1) == 2 * 4 * 64 * 384 * 4 * 2
+    assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.BF16, 0) == 0
+    assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.BF16, 1) == 2 * 4 * 64 * 384 * 2
+
+
+def test_argument_errors_without_gpu():
+    """status codes of the boundary that need no device work"""
+    from sl_hwgat_b200 import _lib
+    lib = _lib.load()
+    # NULL output
+    assert lib.hwgat_mask_build(None, 4, 16, 2, 8, 0, None, None) == 1000
+    # W != 16 is unsupported (no fallback)
+    st = lib.hwgat_attn_fwd(None, None, None, None, -1.0, None, None, 0, 1, 4, 64, 128, 2, 8, 2, 0, 0, 0, None)
+    assert st == 1002
+    # d != heads * 64
+    st = lib.hwgat_attn_fwd(None, None, None, None, -1.0, None, None, 0, 1, 4, 64, 128, 4, 16, 2, 0, 0, 0, None)
+    assert st == 1002
+    # NULL tensors with a supported geometry
+    st = lib.hwgat_attn_fwd(None, None, None, None, -1.0, None, None, 0, 1, 4, 64, 128, 2, 16, 2, 0, 0, 0, None)
+    assert st == 1000
+    # shift with the pre-partitioned layout is inconsistent
+    st = lib.hwgat_attn_fwd(None, None, None, None, -1.0, None, None, 0, 1, 4, 64, 128, 2, 16, 2, 1, 1, 0, None)
+    assert st == 1001
+    with pytest.raises(_lib.HwgatError):
+        _lib.check(1002, "x")
+
+
+def _cpu_model(T=64, classes=262):
+    from sl_hwgat_b200.models import HWGATE
+    adj = torch.from_numpy(O.window_adjacency(O.HWGATEConfig().edges, 16, 2).astype(np.float32))
+    return HWGATE.Model(2, 64, T, classes, 128, 2, True, [2, 2, 4], [2, 4, 8], 16, adj, 0.1, 0.0, 2.,
+                        torch.nn.LayerNorm, None)
+
+
+def test_dropin_state_dict_matches_reference(golden_dir):
+    G = np.load(os.path.join(golden_dir, "full_model.npz"))
+    m = _cpu_model()
+    assert list(m.state_dict().keys()) == list(G["state_dict_names"])
+    assert [str(tuple(v.shape)) for v in m.state_dict().values()] == list(G["state_dict_shapes"])
+    sd = O.make_state_dict(O.HWGATEConfig(temporal_dim=64, num_classes=262), seed=1001)
+    m.load_state_dict(sd, strict=True)
+    # trainable parameter count of the INCLUDE model as main.py:56 prints it
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 9865734
+    # the float shift-mask buffers equal what the oracle derives (pinned to the reference)
+    for i, layer in enumerate(m.layers):
+        F = 64 // 2 ** i
+        for j, blk in enumerate(layer.blocks):
+            if j % 2:
+                assert np.array_equal(blk.attn_mask.numpy() != 0, O.shift_window_mask(F, 4, 16, 2, 1))
+            else:
+                assert blk.attn_mask is None
+        assert tuple(layer.adj_mat.shape) == (F // 2 * 4, 32, 32)
+
+
+def test_product_path_fails_loudly_without_cuda():
+    from sl_hwgat_b200 import _lib
+    m = _cpu_model().eval()
+    with pytest.raises(_lib.HwgatError):
+        m(torch.zeros(1, 64, 64, 2))
+    from sl_hwgat_b200 import ops
+    with pytest.raises(_lib.HwgatError):
+        ops.temporal_merge(torch.zeros(1, 4, 64, 128))
+    if not torch.cuda.is_available():
+        from sl_hwgat_b200.models import model_params
+        with pytest.raises(RuntimeError):
+            model_params.HWGATEParams({"num_class": 262, "src_len": 64}, 2, "cpu")
+
+
+def test_no_product_import_of_oracle():
+    """the oracle is test infrastructure: nothing under sl_hwgat_b200/ may import it"""
+    pkg = os.path.join(ROOT, "sl_hwgat_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src, os.path.join(dp, f)
+
+
+def test_shard_batch():
+    from sl_hwgat_b200.parallel import shard_batch
+    for n in (0, 1, 7, 8, 512, 1023):
+        for world in (1, 2, 3, 8):
+            parts = [shard_batch(n, r, world) for r in range(world)]
+            assert parts[0].start == 0 and parts[-1].stop == n
+            assert all(parts[i].stop == parts[i + 1].start for i in range(world - 1))
+            sizes = [p.stop - p.start for p in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from sl_hwgat_b200.parallel import GradientAllReduce, broadcast_parameters, shard_batch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)            # different init per rank: broadcast must fix it
+    model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 32),
+                                torch.nn.LayerNorm(32), torch.nn.Linear(32, 5))
+    for p in model[2].parameters():
+        p.requires_grad_(False)              # a frozen parameter, like Model.B
+    broadcast_parameters(model, 0)
+    sync = GradientAllReduce(model, bucket_bytes=1024)   # several buckets
+    g = torch.Generator().manual_seed(7)
+    x, y = torch.randn(12, 16, generator=g), torch.randint(0, 5, (12,), generator=g)
+    sl = shard_batch(12, rank, world)
+    for step in range(2):                    # two steps: state must reset between them
+        model.zero_grad(set_to_none=(step == 1))
+        loss = torch.nn.functional.cross_entropy(model(x[sl]), y[sl])
+        loss.backward()
+        sync.finish()
+    if rank == 0:
+        torch.save({"grads": [p.grad for p in model.parameters() if p.requires_grad],
+                    "state": model.state_dict(), "x": x, "y": y}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_equals_full_batch(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "dp.pt")
+    mp.spawn(_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 32),
+                                torch.nn.LayerNorm(32), torch.nn.Linear(32, 5))
+    model.load_state_dict(r["state"])
+    for p in model[2].parameters():
+        p.requires_grad_(False)
+    torch.nn.functional.cross_entropy(model(r["x"]), r["y"]).backward()   # one process, whole batch
+    full = [p.grad for p in model.parameters() if p.requires_grad]
+    assert len(full) == len(r["grads"])
+    for a, b in zip(r["grads"], full):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
