@@ -48,6 +48,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       Bs[kk][nn] = v;
     }
     __syncthreads();
+    // blocked summation: a 16-term partial per k tile, then one add into the running sum, so
+    // the rounding error grows with K/16 + 16 instead of K (the 1e-5 budget is tight at d=512)
+    float part[4][4] = {};
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[4], b[4];
@@ -58,8 +61,12 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     __syncthreads();
   }
 #pragma unroll
@@ -101,6 +108,19 @@ struct CoreSmemF32Bwd {
   float p[kTok][kTok + 1];
   float ds[kTok][kTok + 1];
 };
+
+// 64-term dot product as 4 interleaved partial sums (shorter rounding chains, more ILP)
+HW_DEV float dot64(const float (&a)[kHd], const float* __restrict__ b) {
+  float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+  for (int e = 0; e < kHd; e += 4) {
+    p0 = fmaf(a[e], b[e], p0);
+    p1 = fmaf(a[e + 1], b[e + 1], p1);
+    p2 = fmaf(a[e + 2], b[e + 2], p2);
+    p3 = fmaf(a[e + 3], b[e + 3], p3);
+  }
+  return (p0 + p1) + (p2 + p3);
+}
 
 // probabilities of one query row held by one lane: s[] in, p[] out (in place)
 HW_DEV uint32_t row_softmax_f32(float (&s)[kTok], uint32_t mask_word, float threshold) {
@@ -162,12 +182,7 @@ __global__ void __launch_bounds__(128) attn_core_fwd_f32_kernel(const float* __r
   __syncwarp();
   float s[kTok];
 #pragma unroll
-  for (int j = 0; j < kTok; ++j) {
-    float a = 0.f;
-#pragma unroll
-    for (int e = 0; e < kHd; ++e) a = fmaf(q[e], sm.k[j][e], a);
-    s[j] = a;
-  }
+  for (int j = 0; j < kTok; ++j) s[j] = dot64(q, sm.k[j]);
   const uint32_t mword = bits[g.mask_base(tile) + w * kTok + lane];
   row_softmax_f32(s, mword, threshold);
   float o[kHd];
@@ -222,12 +237,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
       qr[4 * e] = t.x * scale; qr[4 * e + 1] = t.y * scale; qr[4 * e + 2] = t.z * scale; qr[4 * e + 3] = t.w * scale;
     }
 #pragma unroll
-    for (int j = 0; j < kTok; ++j) {
-      float a = 0.f;
-#pragma unroll
-      for (int e = 0; e < kHd; ++e) a = fmaf(qr[e], sm.k[j][e], a);
-      s[j] = a;
-    }
+    for (int j = 0; j < kTok; ++j) s[j] = dot64(qr, sm.k[j]);
   }
   const uint32_t mword = bits[g.mask_base(tile) + w * kTok + lane];
   const uint32_t live = row_softmax_f32(s, mword, threshold);  // s[] now holds P
@@ -242,9 +252,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
     }
 #pragma unroll
     for (int j = 0; j < kTok; ++j) {
-      float a = 0.f;
-#pragma unroll
-      for (int e = 0; e < kHd; ++e) a = fmaf(gr[e], sm.v[j][e], a);
+      float a = dot64(gr, sm.v[j]);
       dp[j] = a;
       dsum = fmaf(s[j], a, dsum);
     }

@@ -179,24 +179,45 @@ def test_fully_masked_rows_uniform_fp32():
 
 
 # ------------------------------------------------------------------ K2 / K3, bf16
+def _oracle_bf16_points(xn, w, b, g, h, F, shift, thr):
+    """fp64 oracle that rounds to bf16 where the kernels round (xn, W, q, k, v, P, O); backward
+    by autograd (the rounding is a straight-through identity)."""
+    mask = O.combined_mask(ADJ, F, 16, 2, shift)
+    x_ = xn.clone().requires_grad_(True)
+    w_ = w.clone().requires_grad_(True)
+    b_ = b.clone().requires_grad_(True)
+    y = O.attention_core(x_, w_, b_, h, mask, 16, 2, shift, thr, bf16_points=True)
+    (y * g).sum().backward()
+    return y.detach(), x_.grad, w_.grad, b_.grad
+
+
 @pytest.mark.parametrize("d,h", LEVELS)
 @pytest.mark.parametrize("shift", [0, 1])
 @pytest.mark.parametrize("thr", [None, 0.04, 0.2])
 @pytest.mark.parametrize("std", [0.02, 0.1])
 def test_attention_bf16_vs_oracle(d, h, shift, thr, std):
+    """bf16 K2/K3 within 2e-2 relative (north_star).  Eval mode: against the UNROUNDED fp64
+    oracle.  Training mode: the threshold drop (HWGATE.py:94-100) is a discontinuous function of
+    the logits, so a logit that bf16 rounding moves across the threshold changes a whole row; the
+    reference has the same property under autocast.  There the comparison is against the oracle
+    evaluated at the kernels' rounding points, plus a loose bound against the unrounded one."""
     B, F = 2, 8
     xn, w, b, g = core_inputs(d, shift, std, B=B, F=F)
     xn, g = xn.to(torch.bfloat16).double(), g.to(torch.bfloat16).double()
     w = w.to(torch.bfloat16).double()
+    b = b.float().double()
     y, dx, dw, db = cuda_core(xn, w, b, g, h, shift, thr, torch.bfloat16)
-    ry, rdx, rdw, rdb = oracle_core(xn, w, b.float().double(), g, h, F, shift, thr)
+    ry, rdx, rdw, rdb = oracle_core(xn, w, b, g, h, F, shift, thr)
     errs = dict(y=rel_l2(y, ry), dx=rel_l2(dx, rdx), dw=rel_l2(dw, rdw), db=rel_l2(db, rdb))
-    assert all(e < BF16_TOL for e in errs.values()), errs
     if thr is None:
-        # tighter: against the oracle that rounds where the kernel rounds
-        by = O.attention_core(xn, w, b.float().double(), h, O.combined_mask(ADJ, F, 16, 2, shift), 16, 2, shift,
-                              None, bf16_points=True)
-        assert rel_l2(y, by) < 4e-3
+        assert all(e < BF16_TOL for e in errs.values()), errs
+    else:
+        assert all(e < 0.15 for e in errs.values()), errs
+    by, bdx, bdw, bdb = _oracle_bf16_points(xn, w, b, g, h, F, shift, thr)
+    berrs = dict(y=rel_l2(y, by), dx=rel_l2(dx, bdx), dw=rel_l2(dw, bdw), db=rel_l2(db, bdb))
+    assert all(e < BF16_TOL for e in berrs.values()), berrs
+    if thr is None:
+        assert berrs["y"] < 4e-3, berrs
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
