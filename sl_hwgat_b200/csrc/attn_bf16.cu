@@ -253,10 +253,11 @@ HW_DEV void fill_rows(int* rows, const TileGeom& g, int tile) {
 __global__ void __launch_bounds__(256, 2) attn_fwd_bf16_kernel(const bf16* __restrict__ xn, const bf16* __restrict__ w,
                                                                const float* __restrict__ bias,
                                                                const uint32_t* __restrict__ bits, float threshold,
-                                                               bf16* __restrict__ out, TileGeom geo) {
+                                                               bf16* __restrict__ out, TileGeom geo, int heads) {
   extern __shared__ __align__(128) unsigned char smem[];
   int* rows = reinterpret_cast<int*>(smem + kOffRowsFwd);
-  const int tile = blockIdx.x, h = blockIdx.y, d = geo.d;
+  // heads of one tile are adjacent CTAs: they run together and share the X tile in L2
+  const int tile = blockIdx.x / heads, h = blockIdx.x - tile * heads, d = geo.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   fill_rows(rows, geo, tile);
   __syncthreads();
@@ -291,10 +292,10 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_bf16_kernel(const bf16* __res
                                                                const float* __restrict__ bias,
                                                                const uint32_t* __restrict__ bits, float threshold,
                                                                const bf16* __restrict__ d_out,
-                                                               bf16* __restrict__ dqkv, TileGeom geo) {
+                                                               bf16* __restrict__ dqkv, TileGeom geo, int heads) {
   extern __shared__ __align__(128) unsigned char smem[];
   int* rows = reinterpret_cast<int*>(smem + kOffRowsBwd);
-  const int tile = blockIdx.x, h = blockIdx.y, d = geo.d;
+  const int tile = blockIdx.x / heads, h = blockIdx.x - tile * heads, d = geo.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   fill_rows(rows, geo, tile);
   __syncthreads();
@@ -401,8 +402,8 @@ int attn_fwd_bf16(const AttnArgs& a, cudaStream_t s) {
     attr_done = true;
   }
   TileGeom g = make_geom(a.F, a.K, a.d, a.shift, a.layout);
-  attn_fwd_bf16_kernel<<<dim3(a.tiles(), a.heads), 256, kSmemFwd, s>>>(
-      (const bf16*)a.xn, (const bf16*)a.w_qkv, a.b_qkv, a.bits, a.threshold, (bf16*)a.out, g);
+  attn_fwd_bf16_kernel<<<dim3(a.tiles() * a.heads), 256, kSmemFwd, s>>>(
+      (const bf16*)a.xn, (const bf16*)a.w_qkv, a.b_qkv, a.bits, a.threshold, (bf16*)a.out, g, a.heads);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -415,8 +416,8 @@ int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s) {
   }
   TileGeom g = make_geom(a.F, a.K, a.d, a.shift, a.layout);
   bf16* dqkv = (bf16*)a.workspace;
-  attn_bwd_bf16_kernel<<<dim3(a.tiles(), a.heads), 256, kSmemBwd, s>>>(
-      (const bf16*)a.xn, (const bf16*)a.w_qkv, a.b_qkv, a.bits, a.threshold, (const bf16*)a.d_out, dqkv, g);
+  attn_bwd_bf16_kernel<<<dim3(a.tiles() * a.heads), 256, kSmemBwd, s>>>(
+      (const bf16*)a.xn, (const bf16*)a.w_qkv, a.b_qkv, a.bits, a.threshold, (const bf16*)a.d_out, dqkv, g, a.heads);
   count_launch();
   int st = (int)cudaGetLastError();
   if (st) return st;
