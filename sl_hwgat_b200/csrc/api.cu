@@ -71,7 +71,8 @@ size_t hwgat_attn_workspace_bytes(int B, int F, int K, int d, int heads, int dty
   (void)heads;
   const size_t n = (size_t)B * F * K;
   if (dtype == HWGAT_F32) return n * 3 * d * sizeof(float) * (backward ? 2 : 1);  // qkv (+ dqkv)
-  return backward ? n * 3 * d * sizeof(__nv_bfloat16) : 0;                         // dqkv
+  // dqkv [n,3d] + Wqkv^T [d,3d]
+  return backward ? (n * 3 * d + (size_t)3 * d * d) * sizeof(__nv_bfloat16) : 0;
 }
 
 int hwgat_attn_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, float threshold,
@@ -114,6 +115,14 @@ int hwgat_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const f
   a.d_xn = d_xn; a.d_w = d_w; a.d_b = d_b; a.workspace = workspace;
   a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
   return dtype == HWGAT_F32 ? attn_bwd_f32(a, (cudaStream_t)stream) : attn_bwd_bf16(a, (cudaStream_t)stream);
+}
+
+int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream) {
+  if (!A || !Bt || !C) return HWGAT_ERR_NULL;
+  if (misaligned(A) || misaligned(Bt) || misaligned(C)) return HWGAT_ERR_ALIGN;
+  if (M <= 0 || N <= 0 || K <= 0) return HWGAT_ERR_SHAPE;
+  return gemm_tc_nt((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bt, (__nv_bfloat16*)C, M, N, K,
+                    (cudaStream_t)stream);
 }
 
 static int merge_common(const void* src, void* dst, int B, int F, int K, int d, int TP, int dtype, bool backward,

@@ -14,6 +14,8 @@
 //            dq = dS k * scale, dk = dS^T q, dv = P^T dO
 //            and writes dQKV (bf16, token order) for the two weight-side GEMMs
 //            in gemm_bf16.cu (d_xn = dQKV.W, d_w = dQKV^T.xn, d_b = colsum).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hwgat {
@@ -396,6 +398,8 @@ int gemm_bf16_tn_f32(const bf16* A, const bf16* Bm, float* C, float* colsum, int
                      cudaStream_t s);
 
 int attn_fwd_bf16(const AttnArgs& a, cudaStream_t s) {
+  static const bool hmma_fwd = getenv("HWGAT_HMMA_FWD") != nullptr;  // A/B switch while the tcgen05 path is new
+  if (!hmma_fwd) return attn_fwd_tc(a, s);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(attn_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd);
@@ -423,8 +427,15 @@ int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s) {
   if (st) return st;
   const long long n = a.tokens();
   const int d = a.d, d3 = 3 * d;
-  // d_xn[n, d] = dQKV[n, 3d] . Wqkv[3d, d]
-  if ((st = gemm_bf16_nn(dqkv, (const bf16*)a.w_qkv, (bf16*)a.d_xn, (int)n, d, d3, s))) return st;
+  // d_xn[n, d] = dQKV[n, 3d] . Wqkv[3d, d]  (tcgen05 GEMM against Wqkv^T, K-major on both sides)
+  static const bool hmma_gemm = getenv("HWGAT_HMMA_GEMM") != nullptr;  // A/B switch while the tcgen05 path is new
+  if (hmma_gemm) {
+    if ((st = gemm_bf16_nn(dqkv, (const bf16*)a.w_qkv, (bf16*)a.d_xn, (int)n, d, d3, s))) return st;
+  } else {
+    bf16* wt = dqkv + n * d3;
+    if ((st = transpose_bf16((const bf16*)a.w_qkv, wt, d3, d, s))) return st;
+    if ((st = gemm_tc_nt(dqkv, wt, (bf16*)a.d_xn, (int)n, d, d3, s))) return st;
+  }
   // d_w[3d, d] = dQKV^T . xn ; d_b = column sums of dQKV (rides in the same kernel)
   return gemm_bf16_tn_f32(dqkv, (const bf16*)a.xn, a.d_w, a.d_b, d3, d, n, s);
 }

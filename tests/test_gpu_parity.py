@@ -264,3 +264,23 @@ def test_empty_batch_and_errors():
         ops.window_graph_attention(torch.zeros(1, 4, 64, 128), w.cpu(), b.cpu(), bits.cpu(), 2)
     with pytest.raises(_lib.HwgatError):      # K not a multiple of 64
         ops.window_graph_attention(torch.zeros(1, 4, 48, 128, device="cuda"), w, b, bits, 2)
+
+
+# ------------------------------------------------------------------ tcgen05 GEMM used by K3
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (256, 128, 384), (1024, 256, 768),
+                                   (4096, 512, 1536), (148 * 128 * 3, 128, 384)])
+def test_tcgen05_gemm_nt(M, N, K):
+    """C = A . Bt^T (TMA + tcgen05.mma + TMEM epilogue) against an fp32 matmul of the same bf16 inputs."""
+    from sl_hwgat_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    Bt = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
+    C = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.hwgat_debug_gemm_nt(A.data_ptr(), Bt.data_ptr(), C.data_ptr(), M, N, K,
+                                       torch.cuda.current_stream().cuda_stream), "hwgat_debug_gemm_nt")
+    torch.cuda.synchronize()
+    ref = A.float() @ Bt.float().t()
+    err = (C.float() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-2, err          # bf16 output rounding only
+    assert rel_l2(C.float(), ref) < 3e-3

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     # size query is pure host arithmetic: qkv + dqkv in fp32, dqkv only in bf16
     assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.F32, 1) == 2 * 4 * 64 * 384 * 4 * 2
     assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.BF16, 0) == 0
-    assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.BF16, 1) == 2 * 4 * 64 * 384 * 2
+    assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.BF16, 1) == (2 * 4 * 64 * 384 + 384 * 128) * 2
 
 
 def test_argument_errors_without_gpu():
