@@ -124,6 +124,10 @@ int hwgat_merge_bwd(const void* d_out, void* d_x, int B, int F, int K, int d, in
 /* Diagnostic: the plain bf16 GEMM K3 uses for d_xn, C[M,N] = A[M,K] . Bt[N,K]^T (fp32 accumulate,
  * TMA + tcgen05).  M % 128 == 0, N % 128 == 0, K % 64 == 0; all row-major bf16 device pointers. */
 int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream);
+/* Diagnostic: the GEMM K3 uses for d_w and d_b: C[M,N] (fp32) = A[Kd,M]^T . B[Kd,N], colsum[M] = column
+ * sums of A.  M % 128 == 0, N % 128 == 0, Kd % 64 == 0; A, B bf16 row-major device pointers. */
+int hwgat_debug_gemm_tn(const void* A, const void* B, float* C, float* colsum, int M, int N, long long Kd,
+                        hwgat_stream_t stream);
 
 /* Number of kernel launches issued through this library since load (all
  * streams, this process) - what bench.py reports as "gpu_launches". */

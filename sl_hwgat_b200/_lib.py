@@ -30,6 +30,7 @@ SIGNATURES = {
     "hwgat_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_size_t] + [c_int] * 10 + [c_void_p]),
     "hwgat_debug_gemm_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "hwgat_debug_gemm_tn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
     "hwgat_merge_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     "hwgat_merge_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
 }

@@ -125,6 +125,14 @@ int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, in
                     (cudaStream_t)stream);
 }
 
+int hwgat_debug_gemm_tn(const void* A, const void* B, float* C, float* colsum, int M, int N, long long Kd,
+                        hwgat_stream_t stream) {
+  if (!A || !B || !C || !colsum) return HWGAT_ERR_NULL;
+  if (misaligned(A) || misaligned(B) || misaligned(C)) return HWGAT_ERR_ALIGN;
+  if (M <= 0 || N <= 0 || Kd <= 0) return HWGAT_ERR_SHAPE;
+  return gemm_tc_tn((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, C, colsum, M, N, Kd, (cudaStream_t)stream);
+}
+
 static int merge_common(const void* src, void* dst, int B, int F, int K, int d, int TP, int dtype, bool backward,
                         hwgat_stream_t stream) {
   if (B < 0 || F <= 0 || K <= 0 || d <= 0) return HWGAT_ERR_SHAPE;

@@ -437,7 +437,8 @@ int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s) {
     if ((st = gemm_tc_nt(dqkv, wt, (bf16*)a.d_xn, (int)n, d, d3, s))) return st;
   }
   // d_w[3d, d] = dQKV^T . xn ; d_b = column sums of dQKV (rides in the same kernel)
-  return gemm_bf16_tn_f32(dqkv, (const bf16*)a.xn, a.d_w, a.d_b, d3, d, n, s);
+  if (hmma_gemm) return gemm_bf16_tn_f32(dqkv, (const bf16*)a.xn, a.d_w, a.d_b, d3, d, n, s);
+  return gemm_tc_tn(dqkv, (const bf16*)a.xn, a.d_w, a.d_b, d3, d, n, s);
 }
 
 }  // namespace hwgat

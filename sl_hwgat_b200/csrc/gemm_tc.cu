@@ -220,4 +220,160 @@ int gemm_tc_nt(const bf16* A, const bf16* Bt, bf16* C, int M, int N, int K, cuda
   return launch_nt<128>(A, Bt, C, M, N, K, s);
 }
 
+
+// ---------------------------------------------------------------------------
+// gemm_tc_tn : C[M,N] (fp32) += A[Kd,M]^T . B[Kd,N],  colsum[M] += sum_k A[k,m]
+//   d_w = dQKV^T . xn  and  d_b = column sums of dQKV   (autograd of self.qkv, HWGATE.py:86)
+// A and B are row-major with the contraction index (tokens) as the row, i.e. both are
+// MN-major UMMA operands: a TMA box of [64 tokens x 64 columns] lands as 64 k-rows of 128
+// swizzled bytes = eight SWIZZLE_128B MN-major atoms (LBO = next 64 columns = 8 KB, SBO = next 8
+// tokens = 1 KB).  Split over tokens: each CTA accumulates its token range in TMEM and adds it
+// to the zeroed fp32 output with red.global.add.  d_b comes from one extra N=16 MMA per k step
+// against an all-ones B tile.
+// ---------------------------------------------------------------------------
+template <int BN>
+struct GemmTnCfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kABytes = 64 * 128 * 2;         // [64 k][128 m] : 2 boxes of 8 KB
+  static constexpr int kBBytes = 64 * BN * 2;          // [64 k][BN n]  : BN/64 boxes of 8 KB
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kOnesOff = kStages * kStage;    // 8 KB of bf16 1.0
+  static constexpr int kBarOff = kOnesOff + 8192;
+  static constexpr int kSmem = kBarOff + 256 + 1024;
+  static constexpr int kTmemCols = 512;                // accumulator BN columns + 16 for the column sums
+  static constexpr int kOnesCol = BN;                  // TMEM column of the ones product
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmB,
+                                                            float* __restrict__ C, float* __restrict__ colsum, int M,
+                                                            int N, int k_blocks_total, int k_blocks_per_cta) {
+  using Cfg = GemmTnCfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* acc_full = empty + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = N / BN;
+  const int mb = blockIdx.x / n_blocks, nb = blockIdx.x - mb * n_blocks;
+  const int kb0 = blockIdx.y * k_blocks_per_cta;
+  const int kb1 = kb0 + k_blocks_per_cta < k_blocks_total ? kb0 + k_blocks_per_cta : k_blocks_total;
+  const bool do_sum = nb == 0;
+
+  for (int i = threadIdx.x; i < 8192 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + Cfg::kOnesOff)[i] = 0x3f803f80u;
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        unsigned char* st = smem + s * Cfg::kStage;
+        mbar_expect_tx(&full[s], Cfg::kStage);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_load_2d(st + j * 8192, &tmA, &full[s], mb * 128 + j * 64, kb * 64);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_2d(st + Cfg::kABytes + j * 8192, &tmB, &full[s], nb * BN + j * 64, kb * 64);
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, true, true);
+      constexpr uint32_t idesc1 = umma_idesc_bf16(128, 16, true, true);
+      const uint32_t sones = smem_u32(smem + Cfg::kOnesOff);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {  // 16 tokens per step = two 8-row atoms = 2 KB
+          const uint64_t da = umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024);
+          umma_bf16(tmem, da, umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024), idesc, (kb > kb0) | (ks > 0));
+          if (do_sum)
+            umma_bf16(tmem + Cfg::kOnesCol, da, umma_desc_mn_sw128(sones, 8192, 1024), idesc1, (kb > kb0) | (ks > 0));
+        }
+        umma_commit(&empty[s]);
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int row = mb * 128 + q * 32 + lane;
+    float* crow = C + (size_t)row * N + (size_t)nb * BN;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(crow + c + i, __uint_as_float(r[i]));
+    }
+    if (do_sum) {
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + Cfg::kOnesCol, r);  // 16 valid columns, all equal
+      tmem_ld_wait();
+      atomicAdd(colsum + row, __uint_as_float(r[0]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, Cfg::kTmemCols);
+}
+
+template <int BN>
+static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd,
+                     cudaStream_t s) {
+  using Cfg = GemmTnCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_tc_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    attr_done = true;
+  }
+  CUtensorMap tmA, tmB;
+  int st;
+  if ((st = make_tmap_2d(&tmA, A, (uint64_t)Kd, (uint64_t)M, 64))) return st;
+  if ((st = make_tmap_2d(&tmB, Bm, (uint64_t)Kd, (uint64_t)N, 64))) return st;
+  cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s);
+  cudaMemsetAsync(colsum, 0, sizeof(float) * M, s);
+  const int tiles = (M / 128) * (N / BN);
+  const int kblocks = (int)(Kd / 64);
+  int splits = (148 + tiles - 1) / tiles;
+  if (splits > kblocks) splits = kblocks;
+  const int per = (kblocks + splits - 1) / splits;
+  splits = (kblocks + per - 1) / per;
+  gemm_tc_tn_kernel<BN><<<dim3(tiles, splits), 192, Cfg::kSmem, s>>>(tmA, tmB, C, colsum, M, N, kblocks, per);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// C[M,N] = A[Kd,M]^T . B[Kd,N] (fp32 out), colsum[M] = column sums of A; M % 128 == 0, N % 128 == 0, Kd % 64 == 0
+int gemm_tc_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd, cudaStream_t s) {
+  if (M % 128 || N % 128 || Kd % 64) return HWGAT_ERR_UNSUPPORTED;
+  if (N % 256 == 0) return launch_tn<256>(A, Bm, C, colsum, M, N, Kd, s);
+  return launch_tn<128>(A, Bm, C, colsum, M, N, Kd, s);
+}
+
 }  // namespace hwgat

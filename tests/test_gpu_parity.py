@@ -284,3 +284,23 @@ def test_tcgen05_gemm_nt(M, N, K):
     err = (C.float() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-2, err          # bf16 output rounding only
     assert rel_l2(C.float(), ref) < 3e-3
+
+
+@pytest.mark.parametrize("M,N,Kd", [(128, 128, 64), (384, 128, 256), (768, 256, 4096), (1536, 512, 8192),
+                                    (384, 128, 64 * 1001)])
+def test_tcgen05_gemm_tn(M, N, Kd):
+    """C = A^T . B (both MN-major UMMA operands, split over the contraction, fp32 red.add) and the
+    column sums of A from the ones-tile MMA."""
+    from sl_hwgat_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N + Kd)
+    A = torch.randn(Kd, M, generator=g).to(torch.bfloat16).cuda()
+    B = torch.randn(Kd, N, generator=g).to(torch.bfloat16).cuda()
+    C = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    cs = torch.full((M,), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(lib.hwgat_debug_gemm_tn(A.data_ptr(), B.data_ptr(), C.data_ptr(), cs.data_ptr(), M, N, Kd,
+                                       torch.cuda.current_stream().cuda_stream), "hwgat_debug_gemm_tn")
+    torch.cuda.synchronize()
+    ref = A.double().t() @ B.double()
+    assert rel_l2(C, ref) < 1e-5
+    assert rel_inf(cs, A.double().sum(0)) < 1e-4
