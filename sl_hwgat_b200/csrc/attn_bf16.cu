@@ -420,10 +420,16 @@ int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s) {
   }
   TileGeom g = make_geom(a.F, a.K, a.d, a.shift, a.layout);
   bf16* dqkv = (bf16*)a.workspace;
-  attn_bwd_bf16_kernel<<<dim3(a.tiles() * a.heads), 256, kSmemBwd, s>>>(
-      (const bf16*)a.xn, (const bf16*)a.w_qkv, a.b_qkv, a.bits, a.threshold, (const bf16*)a.d_out, dqkv, g, a.heads);
-  count_launch();
-  int st = (int)cudaGetLastError();
+  static const bool hmma_bwd = getenv("HWGAT_HMMA_BWD") != nullptr;  // A/B switch while the tcgen05 path is new
+  int st;
+  if (hmma_bwd) {
+    attn_bwd_bf16_kernel<<<dim3(a.tiles() * a.heads), 256, kSmemBwd, s>>>(
+        (const bf16*)a.xn, (const bf16*)a.w_qkv, a.b_qkv, a.bits, a.threshold, (const bf16*)a.d_out, dqkv, g, a.heads);
+    count_launch();
+    st = (int)cudaGetLastError();
+  } else {
+    st = attn_bwd_tc(a, dqkv, s);
+  }
   if (st) return st;
   const long long n = a.tokens();
   const int d = a.d, d3 = 3 * d;

@@ -56,7 +56,8 @@ HW_DEV uint32_t movmatrix_trans(uint32_t a) {
 }
 
 // in-register masked softmax of attn_bf16.cu (same code path for both kernels)
-HW_DEV void masked_softmax_tc(float (&s)[4][4], uint32_t mword0, uint32_t mword1, float threshold, int t) {
+HW_DEV void masked_softmax_tc(float (&s)[4][4], uint32_t mword0, uint32_t mword1, float threshold, int t,
+                                  uint32_t (&live)[2]) {
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const uint32_t mw = r == 0 ? mword0 : mword1;
@@ -95,6 +96,81 @@ HW_DEV void masked_softmax_tc(float (&s)[4][4], uint32_t mword0, uint32_t mword1
     const float inv = 1.f / sum;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) { s[nt][2 * r] = v[2 * nt] * inv; s[nt][2 * r + 1] = v[2 * nt + 1] * inv; }
+    live[r] = lv;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// warp 0 (one lane): TMA producer shared by K2 and K3
+// ---------------------------------------------------------------------------
+HW_DEV void tc_producer(const TileGeom& geo, int heads, int tiles, int S, TcBars* bars, unsigned char* sX,
+                        unsigned char* sW, const CUtensorMap* tmX, const CUtensorMap* tmW) {
+  const int d = geo.d, nk = d / 64;
+  int s = 0;
+  uint32_t wph = 0;
+  int tcount = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
+    const int tps = geo.f * geo.kgroups;
+    const int b = tile / tps, rr = tile - b * tps, fi = rr / geo.kgroups, kg = rr - fi * geo.kgroups;
+    for (int h = 0; h < heads; ++h) {
+      for (int c = 0; c < nk; ++c) {
+        if (h == 0) {
+          mbar_wait(&bars->x_empty[c], (tcount & 1) ^ 1);
+          mbar_expect_tx(&bars->x_full[c], kXChunk);
+          unsigned char* dst = sX + c * kXChunk;
+          if (geo.layout == HWGAT_LAYOUT_WINDOWS) {
+            tma_load_2d(dst, tmX, &bars->x_full[c], c * 64, tile * kTileTok);
+          } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+              for (int tp = 0; tp < 2; ++tp) {
+                int fr = 2 * fi + tp + geo.shift;
+                fr = fr >= geo.F ? fr - geo.F : fr;
+                tma_load_4d(dst + (w * 32 + tp * 16) * 128, tmX, &bars->x_full[c], c * 64, kg * 64 + w * 16, fr, b);
+              }
+          }
+        }
+        mbar_wait(&bars->w_empty[s], wph ^ 1);
+        mbar_expect_tx(&bars->w_full[s], kWStage);
+        unsigned char* dw = sW + s * kWStage;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) tma_load_2d(dw + q * 8192, tmW, &bars->w_full[s], c * 64, q * d + h * kHd);
+        if (++s == S) { s = 0; wph ^= 1; }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// warp 1 (one lane): tcgen05.mma issuer shared by K2 and K3
+// ---------------------------------------------------------------------------
+HW_DEV void tc_issuer(const TileGeom& geo, int heads, int tiles, int S, TcBars* bars, unsigned char* sX,
+                      unsigned char* sW, uint32_t tmem) {
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 192);
+  const int nk = geo.d / 64;
+  int s = 0, it = 0, tcount = 0;
+  uint32_t wph = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
+    for (int h = 0; h < heads; ++h, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&bars->acc_empty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int c = 0; c < nk; ++c) {
+        mbar_wait(&bars->w_full[s], wph);
+        if (h == 0) mbar_wait(&bars->x_full[c], tcount & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(sX + c * kXChunk), sb = smem_u32(sW + s * kWStage);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem + buf * kAccStride, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
+                    (c | ks) != 0);
+        umma_commit(&bars->w_empty[s]);
+        if (h == heads - 1) umma_commit(&bars->x_empty[c]);
+        if (++s == S) { s = 0; wph ^= 1; }
+      }
+      umma_commit(&bars->acc_full[buf]);
+    }
   }
 }
 
@@ -133,71 +209,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
   const uint32_t tmem = bars->tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t wph = 0;
-      int tcount = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
-        const int tps = p.geo.f * p.geo.kgroups;
-        const int b = tile / tps, rr = tile - b * tps, fi = rr / p.geo.kgroups, kg = rr - fi * p.geo.kgroups;
-        for (int h = 0; h < heads; ++h) {
-          for (int c = 0; c < nk; ++c) {
-            if (h == 0) {
-              mbar_wait(&bars->x_empty[c], (tcount & 1) ^ 1);
-              mbar_expect_tx(&bars->x_full[c], kXChunk);
-              unsigned char* dst = sX + c * kXChunk;
-              if (p.geo.layout == HWGAT_LAYOUT_WINDOWS) {
-                tma_load_2d(dst, &tmX, &bars->x_full[c], c * 64, tile * kTileTok);
-              } else {
-#pragma unroll
-                for (int w = 0; w < 4; ++w)
-#pragma unroll
-                  for (int tp = 0; tp < 2; ++tp) {
-                    int fr = 2 * fi + tp + p.geo.shift;
-                    fr = fr >= p.geo.F ? fr - p.geo.F : fr;
-                    tma_load_4d(dst + (w * 32 + tp * 16) * 128, &tmX, &bars->x_full[c], c * 64, kg * 64 + w * 16, fr, b);
-                  }
-              }
-            }
-            mbar_wait(&bars->w_empty[s], wph ^ 1);
-            mbar_expect_tx(&bars->w_full[s], kWStage);
-            unsigned char* dw = sW + s * kWStage;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) tma_load_2d(dw + q * 8192, &tmW, &bars->w_full[s], c * 64, q * d + h * kHd);
-            if (++s == S) { s = 0; wph ^= 1; }
-          }
-        }
-      }
-    }
+    if (lane == 0) tc_producer(p.geo, p.heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 192);
-      int s = 0, it = 0, tcount = 0;
-      uint32_t wph = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
-        for (int h = 0; h < heads; ++h, ++it) {
-          const int buf = it & 1;
-          mbar_wait(&bars->acc_empty[buf], ((it >> 1) & 1) ^ 1);
-          tc_fence_after();
-          for (int c = 0; c < nk; ++c) {
-            mbar_wait(&bars->w_full[s], wph);
-            if (h == 0) mbar_wait(&bars->x_full[c], tcount & 1);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(sX + c * kXChunk), sb = smem_u32(sW + s * kWStage);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(tmem + buf * kAccStride, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
-                        (c | ks) != 0);
-            umma_commit(&bars->w_empty[s]);
-            if (h == heads - 1) umma_commit(&bars->x_empty[c]);
-            if (++s == S) { s = 0; wph ^= 1; }
-          }
-          umma_commit(&bars->acc_full[buf]);
-        }
-      }
-    }
+    if (lane == 0) tc_issuer(p.geo, p.heads, p.tiles, S, bars, sX, sW, tmem);
   } else {
     // ------------------------------------------------------------ attention warps
     const int win = warp & 3;             // TMEM lane quarter of this warp == window of the tile
@@ -259,7 +273,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
             }
           }
         }
-        masked_softmax_tc(s, mw0, mw1, p.threshold, t);
+        uint32_t live[2];
+        masked_softmax_tc(s, mw0, mw1, p.threshold, t, live);
         uint32_t pa[2][4];
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
@@ -332,6 +347,325 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   p.geo = make_geom(a.F, a.K, d, a.shift, a.layout);
   const int grid = p.tiles < 148 ? p.tiles : 148;
   attn_fwd_tc_kernel<<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ===========================================================================
+// K3a on tcgen05: recompute QKV_h in TMEM exactly as K2 does, then the attention
+// backward of every window, writing dQKV (bf16, token order) for the two
+// weight-side GEMMs (gemm_tc.cu).
+//
+// The attention warps work as pairs (one pair per window, each warp 16 query
+// rows).  Pass 1, per query half: S, P (recomputed), dP = dO v^T,
+// dS = live ? P*(dP - rowsum(P*dP)) : 0, dq = dS k * scale.  Pass 2, per key half:
+// dv = P^T dO and dk = dS^T q need the partner's P / dS / dO rows; they are
+// exchanged through a 64-column "mailbox" in the unused TMEM columns of the
+// accumulator buffer (tcgen05.st by the owner, tcgen05.ld by the partner: both
+// warps sit in the same TMEM lane quarter), so nothing goes through shared
+// memory.  Transposed operands (P^T, dS^T, and the [k=token][n=e] B operands)
+// are movmatrix.trans of the 8x8 bf16 blocks already held in registers.
+// ===========================================================================
+HW_DEV void tmem_st_16x256b_x8(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x8.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,"
+      "%31,%32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+HW_DEV void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+HW_DEV void pair_barrier(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
+
+constexpr int kMailCol = 192;  // mailbox columns [192, 256) of each accumulator buffer
+
+// 16 rows x 64 columns of the accumulator -> (+bias) * mul -> bf16 A-fragment / 8x8-block registers:
+// f[ks][0] = rows g, cols 16ks+2t..   f[ks][1] = rows g+8, same cols   f[ks][2], f[ks][3]: cols +8
+HW_DEV void ld_rows_as_blocks(uint32_t taddr, const float* __restrict__ bias2t, float mul, uint32_t (&f)[4][4]) {
+  uint32_t r[32];
+  tmem_ld_16x256b_x8(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      const int nt = 2 * ks + x;
+      const float2 bb = *reinterpret_cast<const float2*>(bias2t + 8 * nt);
+      f[ks][2 * x] = pack_bf16((__uint_as_float(r[4 * nt]) + bb.x) * mul, (__uint_as_float(r[4 * nt + 1]) + bb.y) * mul);
+      f[ks][2 * x + 1] =
+          pack_bf16((__uint_as_float(r[4 * nt + 2]) + bb.x) * mul, (__uint_as_float(r[4 * nt + 3]) + bb.y) * mul);
+    }
+}
+
+// acc[16 x 32] += A[16 x 64] . M^T where M (32 rows x 64 cols) sits in TMEM lanes [lane32, lane32+32) at column col0:
+// M's C fragments are the B fragments as they come (the q.k^T / dO.v^T pattern).
+HW_DEV void mma_rows_x_tmem_T(float (&acc)[4][4], const uint32_t (&a)[4][4], uint32_t tb, int lane32, int col0,
+                              const float* __restrict__ bias2t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    uint32_t r[32];
+    tmem_ld_16x256b_x8(tb + ((uint32_t)(lane32 + 16 * mt) << 16) + col0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const float2 b0 = *reinterpret_cast<const float2*>(bias2t + 8 * (2 * ks));
+      const float2 b1 = *reinterpret_cast<const float2*>(bias2t + 8 * (2 * ks + 1));
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t f0 = pack_bf16(__uint_as_float(r[4 * (2 * ks) + 2 * hh]) + b0.x,
+                                      __uint_as_float(r[4 * (2 * ks) + 2 * hh + 1]) + b0.y);
+        const uint32_t f1 = pack_bf16(__uint_as_float(r[4 * (2 * ks + 1) + 2 * hh]) + b1.x,
+                                      __uint_as_float(r[4 * (2 * ks + 1) + 2 * hh + 1]) + b1.y);
+        mma16816(acc[2 * mt + hh], a[ks], f0, f1);
+      }
+    }
+  }
+}
+
+// acc[16 x 64] += A[16 x 16] . Bm[16 x 64], Bm given as the 8x8-block registers f[ks][..] of its 16 rows
+// (layout of ld_rows_as_blocks): B fragments are movmatrix.trans of the blocks.
+HW_DEV void mma_16x64_k16_blocks(float (&acc)[8][4], const uint32_t (&a)[4], const uint32_t (&f)[4][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const uint32_t b0 = movmatrix_trans(f[nt >> 1][(nt & 1) * 2]);
+    const uint32_t b1 = movmatrix_trans(f[nt >> 1][(nt & 1) * 2 + 1]);
+    mma16816(acc[nt], a, b0, b1);
+  }
+}
+
+HW_DEV void store_rows_16x64(const float (&c)[8][4], float mul, bf16* __restrict__ p0, bf16* __restrict__ p1) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<uint32_t*>(p0 + 8 * nt) = pack_bf16(c[nt][0] * mul, c[nt][1] * mul);
+    *reinterpret_cast<uint32_t*>(p1 + 8 * nt) = pack_bf16(c[nt][2] * mul, c[nt][3] * mul);
+  }
+}
+
+struct BwdTcArgs {
+  const float* bias;
+  const uint32_t* bits;
+  const bf16* d_out;
+  bf16* dqkv;
+  float threshold;
+  int heads, tiles, w_stages;
+  TileGeom geo;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                    const __grid_constant__ CUtensorMap tmW,
+                                                                    const BwdTcArgs p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int d = p.geo.d, nk = d / 64, heads = p.heads, S = p.w_stages;
+  unsigned char* sX = smem;
+  unsigned char* sW = smem + nk * kXChunk;
+  TcBars* bars = reinterpret_cast<TcBars*>(sW + S * kWStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxChunks; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], 1); }
+    for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], kEpiWarps); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
+  } else if (warp == 1) {
+    if (lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, tmem);
+  } else {
+    const int win = warp & 3;        // TMEM lane quarter == window
+    const int qh = (warp - 2) >> 2;  // my 16 query rows (pass 1) and my 16 key rows (pass 2)
+    const int g = lane >> 2, t = lane & 3;
+    const int my_lanes = 32 * win + 16 * qh, other_lanes = 32 * win + 16 * (1 - qh);
+    const size_t d3 = (size_t)3 * d;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      const int row0 = 32 * win + 16 * qh;
+      const size_t tr0 = (size_t)p.geo.token_row(tile, row0 + g), tr1 = (size_t)p.geo.token_row(tile, row0 + g + 8);
+      const uint32_t* mw = p.bits + p.geo.mask_base(tile) + row0;
+      const uint32_t mw0 = mw[g], mw1 = mw[g + 8];
+      for (int h = 0; h < heads; ++h, ++it) {
+        const int buf = it & 1;
+        // dO rows of this warp as A fragments, straight from global (independent of the MMA: issue first)
+        uint32_t ga[4][4];
+        {
+          const bf16* g0 = p.d_out + tr0 * d + h * kHd + 2 * t;
+          const bf16* g1 = p.d_out + tr1 * d + h * kHd + 2 * t;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            ga[ks][0] = *reinterpret_cast<const uint32_t*>(g0 + 16 * ks);
+            ga[ks][1] = *reinterpret_cast<const uint32_t*>(g1 + 16 * ks);
+            ga[ks][2] = *reinterpret_cast<const uint32_t*>(g0 + 16 * ks + 8);
+            ga[ks][3] = *reinterpret_cast<const uint32_t*>(g1 + 16 * ks + 8);
+          }
+        }
+        mbar_wait(&bars->acc_full[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tb = tmem + buf * kAccStride;
+        const float* bq = p.bias + h * kHd + 2 * t;
+        const float* bk = bq + d;
+        const float* bv = bk + d;
+        // ---------------- pass 1: my 16 query rows
+        uint32_t qa[4][4];
+        ld_rows_as_blocks(tb + ((uint32_t)my_lanes << 16), bq, 0.125f, qa);
+        float pr[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pr[i][j] = 0.f;
+        mma_rows_x_tmem_T(pr, qa, tb, 32 * win, 64, bk);      // S = q k^T
+        uint32_t live[2];
+        masked_softmax_tc(pr, mw0, mw1, p.threshold, t, live);  // P
+        float ds[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ds[i][j] = 0.f;
+        mma_rows_x_tmem_T(ds, ga, tb, 32 * win, 128, bv);     // dP = dO v^T
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          float delta = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) delta += pr[nt][2 * r] * ds[nt][2 * r] + pr[nt][2 * r + 1] * ds[nt][2 * r + 1];
+          delta = quad_sum(delta);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              const bool on = (live[r] >> (2 * nt + x)) & 1u;
+              ds[nt][2 * r + x] = on ? pr[nt][2 * r + x] * (ds[nt][2 * r + x] - delta) : 0.f;
+            }
+        }
+        // 8x8 bf16 blocks: pb[hi][nn] = P[rows 8hi+g][keys 8nn+2t..], db likewise for dS
+        uint32_t pb[2][4], db[2][4];
+#pragma unroll
+        for (int nn = 0; nn < 4; ++nn) {
+          pb[0][nn] = pack_bf16(pr[nn][0], pr[nn][1]);
+          pb[1][nn] = pack_bf16(pr[nn][2], pr[nn][3]);
+          db[0][nn] = pack_bf16(ds[nn][0], ds[nn][1]);
+          db[1][nn] = pack_bf16(ds[nn][2], ds[nn][3]);
+        }
+        // mailbox for the partner: my P / dS blocks of ITS key columns, and my dO fragments
+        {
+          uint32_t m[32];
+          const int on = 2 * (1 - qh);
+          m[0] = pb[0][on]; m[1] = pb[0][on + 1]; m[2] = pb[1][on]; m[3] = pb[1][on + 1];
+          m[4] = db[0][on]; m[5] = db[0][on + 1]; m[6] = db[1][on]; m[7] = db[1][on + 1];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m[8 + 4 * ks + i] = ga[ks][i];
+#pragma unroll
+          for (int i = 24; i < 32; ++i) m[i] = 0u;
+          tmem_st_16x256b_x8(tb + ((uint32_t)my_lanes << 16) + kMailCol, m);
+        }
+        // dq = dS k * scale : A = dS fragments, B = movmatrix.trans of the k blocks
+        {
+          float dq[8][4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {  // keys 16mt.. = k step mt
+            uint32_t kb[4][4];
+            ld_rows_as_blocks(tb + ((uint32_t)(32 * win + 16 * mt) << 16) + 64, bk, 1.f, kb);
+            const uint32_t a[4] = {db[0][2 * mt], db[1][2 * mt], db[0][2 * mt + 1], db[1][2 * mt + 1]};
+            mma_16x64_k16_blocks(dq, a, kb);
+          }
+          store_rows_16x64(dq, 0.125f, p.dqkv + tr0 * d3 + h * kHd + 2 * t, p.dqkv + tr1 * d3 + h * kHd + 2 * t);
+        }
+        // the partner's q rows (B operand of dk) : last read of the accumulator
+        uint32_t qo[4][4];
+        ld_rows_as_blocks(tb + ((uint32_t)other_lanes << 16), bq, 0.125f, qo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+        pair_barrier(1 + win);
+        tc_fence_after();
+        uint32_t m[32];
+        tmem_ld_16x256b_x8(tb + ((uint32_t)other_lanes << 16) + kMailCol, m);
+        tmem_ld_wait();
+        // ---------------- pass 2: my 16 key rows (same token rows as my query rows)
+        const int mn = 2 * qh;
+        {
+          float dv[8][4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dv[i][j] = 0.f;
+          // P^T fragments: own 16 queries, then the partner's 16 queries
+          const uint32_t a_own[4] = {movmatrix_trans(pb[0][mn]), movmatrix_trans(pb[0][mn + 1]),
+                                     movmatrix_trans(pb[1][mn]), movmatrix_trans(pb[1][mn + 1])};
+          mma_16x64_k16_blocks(dv, a_own, ga);
+          const uint32_t a_oth[4] = {movmatrix_trans(m[0]), movmatrix_trans(m[1]), movmatrix_trans(m[2]),
+                                     movmatrix_trans(m[3])};
+          uint32_t go[4][4];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) go[ks][i] = m[8 + 4 * ks + i];
+          mma_16x64_k16_blocks(dv, a_oth, go);
+          store_rows_16x64(dv, 1.f, p.dqkv + tr0 * d3 + 2 * d + h * kHd + 2 * t,
+                           p.dqkv + tr1 * d3 + 2 * d + h * kHd + 2 * t);
+        }
+        {
+          float dk[8][4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dk[i][j] = 0.f;
+          const uint32_t a_own[4] = {movmatrix_trans(db[0][mn]), movmatrix_trans(db[0][mn + 1]),
+                                     movmatrix_trans(db[1][mn]), movmatrix_trans(db[1][mn + 1])};
+          mma_16x64_k16_blocks(dk, a_own, qa);
+          const uint32_t a_oth[4] = {movmatrix_trans(m[4]), movmatrix_trans(m[5]), movmatrix_trans(m[6]),
+                                     movmatrix_trans(m[7])};
+          mma_16x64_k16_blocks(dk, a_oth, qo);
+          store_rows_16x64(dk, 1.f, p.dqkv + tr0 * d3 + d + h * kHd + 2 * t, p.dqkv + tr1 * d3 + d + h * kHd + 2 * t);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+int attn_bwd_tc(const AttnArgs& a, bf16* dqkv, cudaStream_t s) {
+  const int d = a.d, nk = d / 64;
+  const int stages = d == 512 ? 4 : 6;
+  const int smem_bytes = nk * kXChunk + stages * kWStage + (int)sizeof(TcBars) + 1024;
+  static int attr_smem = 0;
+  if (smem_bytes > attr_smem) {
+    cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    attr_smem = smem_bytes;
+  }
+  CUtensorMap tmX, tmW;
+  int st;
+  if (a.layout == HWGAT_LAYOUT_WINDOWS) {
+    if ((st = make_tmap_2d(&tmX, a.xn, (uint64_t)a.tokens(), (uint64_t)d, kTileTok))) return st;
+  } else {
+    if ((st = make_tmap_4d(&tmX, a.xn, (uint64_t)d, (uint64_t)a.K, (uint64_t)a.F, (uint64_t)a.B, 16))) return st;
+  }
+  if ((st = make_tmap_2d(&tmW, a.w_qkv, (uint64_t)3 * d, (uint64_t)d, 64))) return st;
+  BwdTcArgs p;
+  p.bias = a.b_qkv; p.bits = a.bits; p.d_out = (const bf16*)a.d_out; p.dqkv = dqkv; p.threshold = a.threshold;
+  p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages;
+  p.geo = make_geom(a.F, a.K, d, a.shift, a.layout);
+  const int grid = p.tiles < 148 ? p.tiles : 148;
+  attn_bwd_tc_kernel<<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
   count_launch();
   return (int)cudaGetLastError();
 }
