@@ -51,52 +51,103 @@ HW_DEV void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
 }
 HW_DEV uint32_t movmatrix_trans(uint32_t a) {
   uint32_t d;
-  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;\n" : "=r"(d) : "r"(a));
+  asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;\n" : "=r"(d) : "r"(a));
   return d;
 }
 
-// in-register masked softmax of attn_bf16.cu (same code path for both kernels)
-HW_DEV void masked_softmax_tc(float (&s)[4][4], uint32_t mword0, uint32_t mword1, float threshold, int t,
-                                  uint32_t (&live)[2]) {
+// ---------------------------------------------------------------------------
+// In-register masked softmax of the two rows (g, g+8) a thread shares with its quad
+// (HWGATE.py:94-111).  s: logits in, probabilities out.  mk[r][i] is 1.0 where the packed
+// graph/shift mask lets row r see the thread's i-th column (column 8*(i>>1) + 2t + (i&1)),
+// else 0.0; it is built once per tile.  dead[r] is set when the row has no live logit at all
+// (then P is uniform over all 32 keys and the gradient w.r.t. the logits is zero).
+//
+// Training (threshold >= 0): the exponentials of the unmasked softmax are reused for the masked
+// one:  P_i = live_i * e_i / sum_j live_j * e_j  with  e_i = exp(s_i - max s), which equals
+// softmax(live ? s : -10000) whenever some live e_i is representable; otherwise (every logit
+// dropped or masked, or all live ones underflow) an exact second pass runs.
+// ---------------------------------------------------------------------------
+constexpr float kLog2e = 1.4426950408889634f;
+
+HW_DEV void build_row_masks(uint32_t mword0, uint32_t mword1, int t, float (&mk)[2][8]) {
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const uint32_t mw = r == 0 ? mword0 : mword1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mk[r][i] = ((mw >> (8 * (i >> 1) + 2 * t + (i & 1))) & 1u) ? 1.f : 0.f;
+  }
+}
+
+// exact (two-pass) row: live flags given as 0/1 floats lv[i]
+HW_DEV void softmax_row_exact(float (&v)[8], const float (&lv)[8], bool& dead) {
+  float m1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = lv[i] != 0.f ? v[i] : kNegFill;
+    m1 = fmaxf(m1, v[i]);
+  }
+  m1 = quad_max(m1);
+  dead = m1 == kNegFill;
+  const float ml = m1 * kLog2e;
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { v[i] = exp2f(fmaf(v[i], kLog2e, -ml)); sum += v[i]; }
+  sum = quad_sum(sum);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] *= inv;
+}
+
+HW_DEV void masked_softmax_tc(float (&s)[4][4], const float (&mk)[2][8], float threshold, bool (&dead)[2]) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
     float v[8];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) { v[2 * nt] = s[nt][2 * r]; v[2 * nt + 1] = s[nt][2 * r + 1]; }
-    uint32_t lv = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) lv |= ((mw >> (8 * (i >> 1) + 2 * t + (i & 1))) & 1u) << i;
-    if (threshold >= 0.f) {  // HWGATE.py:94-100
+    if (threshold >= 0.f) {
       float m0 = v[0];
 #pragma unroll
       for (int i = 1; i < 8; ++i) m0 = fmaxf(m0, v[i]);
       m0 = quad_max(m0);
+      const float ml = m0 * kLog2e;
       float e[8], sum0 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { e[i] = __expf(v[i] - m0); sum0 += e[i]; }
+      for (int i = 0; i < 8; ++i) { e[i] = exp2f(fmaf(v[i], kLog2e, -ml)); sum0 += e[i]; }
       sum0 = quad_sum(sum0);
-      const float inv0 = 1.f / sum0;
+      const float t0 = threshold * sum0;  // softmax_i > thr  <=>  e_i > thr * sum
+      float lv[8], sl = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (e[i] * inv0 > threshold) lv &= ~(1u << i);
+      for (int i = 0; i < 8; ++i) {
+        lv[i] = (e[i] > t0 || v[i] == 0.f) ? 0.f : mk[r][i];  // HWGATE.py:100 drop, :110 exact zeros, masks :102-108
+        e[i] *= lv[i];
+        sl += e[i];
+      }
+      sl = quad_sum(sl);
+      const bool slow = !(sl > 1e-30f);
+      if (__any_sync(0xffffffffu, slow)) {  // warp-uniform branch; quads that do not need it keep their fast result
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = v[i];
+        bool dd;
+        softmax_row_exact(w, lv, dd);
+        const float inv = 1.f / sl;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = slow ? w[i] : e[i] * inv;
+        dead[r] = slow && dd;
+      } else {
+        const float inv = 1.f / sl;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = e[i] * inv;
+        dead[r] = false;
+      }
+    } else {
+      float lv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) lv[i] = v[i] == 0.f ? 0.f : mk[r][i];
+      softmax_row_exact(v, lv, dead[r]);
     }
-    float m1 = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (v[i] == 0.f) lv &= ~(1u << i);  // HWGATE.py:110
-      v[i] = ((lv >> i) & 1u) ? v[i] : kNegFill;
-      m1 = fmaxf(m1, v[i]);
-    }
-    m1 = quad_max(m1);
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i] = __expf(v[i] - m1); sum += v[i]; }
-    sum = quad_sum(sum);
-    const float inv = 1.f / sum;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) { s[nt][2 * r] = v[2 * nt] * inv; s[nt][2 * r + 1] = v[2 * nt + 1] * inv; }
-    live[r] = lv;
+    for (int nt = 0; nt < 4; ++nt) { s[nt][2 * r] = v[2 * nt]; s[nt][2 * r + 1] = v[2 * nt + 1]; }
   }
 }
 
@@ -224,7 +275,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
       const size_t orow0 = (size_t)p.geo.token_row(tile, row0 + g) * d;
       const size_t orow1 = (size_t)p.geo.token_row(tile, row0 + g + 8) * d;
       const uint32_t* mw = p.bits + p.geo.mask_base(tile) + row0;
-      const uint32_t mw0 = mw[g], mw1 = mw[g + 8];
+      float mk[2][8];
+      build_row_masks(mw[g], mw[g + 8], t, mk);
       for (int h = 0; h < heads; ++h, ++it) {
         const int buf = it & 1;
         mbar_wait(&bars->acc_full[buf], (it >> 1) & 1);
@@ -273,8 +325,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
             }
           }
         }
-        uint32_t live[2];
-        masked_softmax_tc(s, mw0, mw1, p.threshold, t, live);
+        bool dead[2];
+        masked_softmax_tc(s, mk, p.threshold, dead);
         uint32_t pa[2][4];
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
@@ -494,7 +546,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
       const int row0 = 32 * win + 16 * qh;
       const size_t tr0 = (size_t)p.geo.token_row(tile, row0 + g), tr1 = (size_t)p.geo.token_row(tile, row0 + g + 8);
       const uint32_t* mw = p.bits + p.geo.mask_base(tile) + row0;
-      const uint32_t mw0 = mw[g], mw1 = mw[g + 8];
+      float mk[2][8];
+      build_row_masks(mw[g], mw[g + 8], t, mk);
       for (int h = 0; h < heads; ++h, ++it) {
         const int buf = it & 1;
         // dO rows of this warp as A fragments, straight from global (independent of the MMA: issue first)
@@ -525,8 +578,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 4; ++j) pr[i][j] = 0.f;
         mma_rows_x_tmem_T(pr, qa, tb, 32 * win, 64, bk);      // S = q k^T
-        uint32_t live[2];
-        masked_softmax_tc(pr, mw0, mw1, p.threshold, t, live);  // P
+        bool dead[2];
+        masked_softmax_tc(pr, mk, p.threshold, dead);  // P (exactly 0 wherever the logit is not live)
         float ds[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -542,10 +595,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int x = 0; x < 2; ++x) {
-              const bool on = (live[r] >> (2 * nt + x)) & 1u;
-              ds[nt][2 * r + x] = on ? pr[nt][2 * r + x] * (ds[nt][2 * r + x] - delta) : 0.f;
-            }
+            for (int x = 0; x < 2; ++x)  // dS = live ? P (dP - delta) : 0, and P == 0 off the live set
+              ds[nt][2 * r + x] = dead[r] ? 0.f : pr[nt][2 * r + x] * (ds[nt][2 * r + x] - delta);
         }
         // 8x8 bf16 blocks: pb[hi][nn] = P[rows 8hi+g][keys 8nn+2t..], db likewise for dS
         uint32_t pb[2][4], db[2][4];
