@@ -121,6 +121,34 @@ int hwgat_merge_fwd(const void* x, void* out, int B, int F, int K, int d, int TP
 int hwgat_merge_bwd(const void* d_out, void* d_x, int B, int F, int K, int d, int TP,
                     int dtype, hwgat_stream_t stream);
 
+/* ---- rest of the block, bf16 / autocast path --------------------------
+ * Bandwidth-bound fusions of the PyTorch elementwise chains of PartAttentionBlock.forward
+ * (HWGATE.py:189-221) and their autograd.  Dropout masks are regenerated from a Philox4x32-10
+ * stream (seed, offset) in forward and backward; nothing is stored.  numel % 8 == 0.            */
+
+/* K5: y(bf16) = LayerNorm(x fp32; gamma, beta, eps) per row of d in {128,256,512}; mean/rstd (n) saved.
+ * Replaces self.norm1 / self.norm2 (HWGATE.py:203, 219) + the autocast cast of their output.   */
+int hwgat_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                 long long n, int d, float eps, hwgat_stream_t stream);
+/* K5': dx(fp32) = (dres ? dres : 0) + LayerNorm'(dy bf16); dgamma, dbeta (d) overwritten.
+ * dres is the gradient arriving on the residual path (HWGATE.py:217, 219), fused into the same pass. */
+int hwgat_ln_bwd(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                 const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d,
+                 hwgat_stream_t stream);
+/* K6: out(fp32) = res(fp32) + dropout_p(a bf16).  Replaces proj_drop + shortcut add (HWGATE.py:116, 217)
+ * and ff.drop + residual add (HWGATE.py:135, 219).  p = 0 -> plain add.                          */
+int hwgat_dropout_add_fwd(const float* res, const void* a, float* out, long long numel, float p,
+                          unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
+/* K6': da(bf16) = mask * dout(fp32) / (1-p)  (the gradient w.r.t. res is dout itself).          */
+int hwgat_dropout_add_bwd(const float* dout, void* da, long long numel, float p, unsigned long long seed,
+                          unsigned long long offset, hwgat_stream_t stream);
+/* K7: g(bf16) = dropout_p(gelu(u bf16)), exact erf GELU.  Replaces ff.act + ff.drop (HWGATE.py:132-133). */
+int hwgat_gelu_dropout_fwd(const void* u, void* g, long long numel, float p, unsigned long long seed,
+                           unsigned long long offset, hwgat_stream_t stream);
+/* K7': du(bf16) = dg * mask / (1-p) * gelu'(u).                                                   */
+int hwgat_gelu_dropout_bwd(const void* u, const void* dg, void* du, long long numel, float p,
+                           unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
+
 /* Diagnostic: the plain bf16 GEMM K3 uses for d_xn, C[M,N] = A[M,K] . Bt[N,K]^T (fp32 accumulate,
  * TMA + tcgen05).  M % 128 == 0, N % 128 == 0, K % 64 == 0; all row-major bf16 device pointers. */
 int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream);

@@ -26,7 +26,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 2; }
+int hwgat_version(void) { return 3; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -115,6 +115,78 @@ int hwgat_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const f
   a.d_xn = d_xn; a.d_w = d_w; a.d_b = d_b; a.workspace = workspace;
   a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
   return dtype == HWGAT_F32 ? attn_bwd_f32(a, (cudaStream_t)stream) : attn_bwd_bf16(a, (cudaStream_t)stream);
+}
+
+static int check_ew(long long numel, float p) {
+  if (numel < 0 || !(p >= 0.f) || p >= 1.f) return HWGAT_ERR_SHAPE;
+  if (numel % 8) return HWGAT_ERR_UNSUPPORTED;
+  return HWGAT_OK;
+}
+
+int hwgat_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                 long long n, int d, float eps, hwgat_stream_t stream) {
+  if (n < 0) return HWGAT_ERR_SHAPE;
+  if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
+  if (n == 0) return HWGAT_OK;
+  if (!x || !gamma || !beta || !y || !mean || !rstd) return HWGAT_ERR_NULL;
+  if (misaligned(x) || misaligned(gamma) || misaligned(beta) || misaligned(y)) return HWGAT_ERR_ALIGN;
+  return launch_ln_fwd(x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, n, d, eps, (cudaStream_t)stream);
+}
+
+int hwgat_ln_bwd(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                 const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d,
+                 hwgat_stream_t stream) {
+  if (n < 0) return HWGAT_ERR_SHAPE;
+  if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
+  if (!dgamma || !dbeta) return HWGAT_ERR_NULL;
+  if (n > 0 && (!dy || !x || !mean || !rstd || !gamma || !dx)) return HWGAT_ERR_NULL;
+  if (misaligned(dy) || misaligned(dres) || misaligned(x) || misaligned(gamma) || misaligned(dx)) return HWGAT_ERR_ALIGN;
+  return launch_ln_bwd((const __nv_bfloat16*)dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, d,
+                       (cudaStream_t)stream);
+}
+
+int hwgat_dropout_add_fwd(const float* res, const void* a, float* out, long long numel, float p,
+                          unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  int st = check_ew(numel, p);
+  if (st) return st;
+  if (numel == 0) return HWGAT_OK;
+  if (!res || !a || !out) return HWGAT_ERR_NULL;
+  if (misaligned(res) || misaligned(a) || misaligned(out)) return HWGAT_ERR_ALIGN;
+  return launch_dropout_add(res, (const __nv_bfloat16*)a, out, nullptr, numel, p, seed, offset, false,
+                            (cudaStream_t)stream);
+}
+
+int hwgat_dropout_add_bwd(const float* dout, void* da, long long numel, float p, unsigned long long seed,
+                          unsigned long long offset, hwgat_stream_t stream) {
+  int st = check_ew(numel, p);
+  if (st) return st;
+  if (numel == 0) return HWGAT_OK;
+  if (!dout || !da) return HWGAT_ERR_NULL;
+  if (misaligned(dout) || misaligned(da)) return HWGAT_ERR_ALIGN;
+  return launch_dropout_add(dout, nullptr, nullptr, (__nv_bfloat16*)da, numel, p, seed, offset, true,
+                            (cudaStream_t)stream);
+}
+
+int hwgat_gelu_dropout_fwd(const void* u, void* g, long long numel, float p, unsigned long long seed,
+                           unsigned long long offset, hwgat_stream_t stream) {
+  int st = check_ew(numel, p);
+  if (st) return st;
+  if (numel == 0) return HWGAT_OK;
+  if (!u || !g) return HWGAT_ERR_NULL;
+  if (misaligned(u) || misaligned(g)) return HWGAT_ERR_ALIGN;
+  return launch_gelu_dropout((const __nv_bfloat16*)u, nullptr, (__nv_bfloat16*)g, numel, p, seed, offset, false,
+                             (cudaStream_t)stream);
+}
+
+int hwgat_gelu_dropout_bwd(const void* u, const void* dg, void* du, long long numel, float p,
+                           unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  int st = check_ew(numel, p);
+  if (st) return st;
+  if (numel == 0) return HWGAT_OK;
+  if (!u || !dg || !du) return HWGAT_ERR_NULL;
+  if (misaligned(u) || misaligned(dg) || misaligned(du)) return HWGAT_ERR_ALIGN;
+  return launch_gelu_dropout((const __nv_bfloat16*)u, (const __nv_bfloat16*)dg, (__nv_bfloat16*)du, numel, p, seed,
+                             offset, true, (cudaStream_t)stream);
 }
 
 int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream) {

@@ -113,6 +113,15 @@ int launch_mask_pack(const float* adj, int adj_windows, const float* mask, int n
                      cudaStream_t s);
 int launch_merge(const void* src, void* dst, int B, int F, int K, int d, int elem_bytes, bool backward, cudaStream_t s);
 
+int launch_ln_fwd(const float* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* mean, float* rstd,
+                  long long n, int d, float eps, cudaStream_t s);
+int launch_ln_bwd(const __nv_bfloat16* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                  const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d, cudaStream_t s);
+int launch_dropout_add(const float* res_or_dout, const __nv_bfloat16* a, float* out, __nv_bfloat16* da, long long numel,
+                       float p, unsigned long long seed, unsigned long long offset, bool backward, cudaStream_t s);
+int launch_gelu_dropout(const __nv_bfloat16* u, const __nv_bfloat16* dg, __nv_bfloat16* out, long long numel, float p,
+                        unsigned long long seed, unsigned long long offset, bool backward, cudaStream_t s);
+
 struct AttnArgs {
   const void* xn; const void* w_qkv; const float* b_qkv; const uint32_t* bits;
   float threshold;

@@ -215,12 +215,29 @@ class PartAttentionBlock(nn.Module):
                                         self.window_size, self.temporal_patch_size)
         return self._bits
 
+    def _fusable(self, x):
+        """bf16 autocast on the fp32 residual stream with the stock sub-modules: the elementwise chains
+        around the GEMMs run as the fused kernels K5-K7 instead of PyTorch ops."""
+        return (x.dtype == torch.float32 and _attn_dtype(x) == torch.bfloat16 and self.dim in (128, 256, 512)
+                and type(self.norm1) is nn.LayerNorm and type(self.norm2) is nn.LayerNorm
+                and isinstance(self.ff.act, nn.GELU) and getattr(self.ff.act, "approximate", "none") == "none")
+
     def forward(self, x):
         B, F, K, d = x.shape
         if F != self.temporal_dim or K != self.num_kps:
             raise ValueError(f"expected (B,{self.temporal_dim},{self.num_kps},d), got {tuple(x.shape)}")
-        x = x + self.attn.attend(self.norm1(x), self.shift_size, self._block_bits(x.device))
-        return x + self.ff(self.norm2(x))
+        bits = self._block_bits(x.device)
+        if not self._fusable(x):
+            x = x + self.attn.attend(self.norm1(x), self.shift_size, bits)
+            return x + self.ff(self.norm2(x))
+        attn, ff, p = self.attn, self.ff, float(self.drop)
+        x, xn = ops.layer_norm_residual(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        ctx = ops.window_graph_attention(xn, attn.qkv.weight, attn.qkv.bias, bits, attn.num_heads,
+                                         shift=self.shift_size, threshold=attn._draw_threshold(), layout=LAYOUT_BFKD)
+        x = ops.dropout_add(x, attn.proj(ctx), attn.proj_drop.p, self.training)
+        x, h = ops.layer_norm_residual(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        u = ops.gelu_dropout(ff.fc1(h), ff.drop.p, self.training)
+        return ops.dropout_add(x, ff.fc2(u), ff.drop.p, self.training)
 
 
 class PartAttentionLayer(nn.Module):

@@ -203,3 +203,132 @@ def temporal_merge(x: torch.Tensor) -> torch.Tensor:
     if x.shape[1] % TEMPORAL_PATCH != 0:
         raise ValueError("frame count must be a multiple of the temporal patch size")
     return _TemporalMerge.apply(x)
+
+
+# --------------------------------------------------------------------------
+# K5-K7: bandwidth-bound fusions of the rest of the block (bf16 / autocast path)
+# --------------------------------------------------------------------------
+
+def _philox_stream(device) -> tuple:
+    """(seed, offset) for one dropout call, taken from (and advancing) PyTorch's CUDA generator, so
+    torch.manual_seed / torch.cuda.manual_seed make the masks reproducible.  The CPU generator - the
+    one the training threshold is drawn from (HWGATE.py:96) - is not touched."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed, off = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(off + 4)
+    return seed & 0xFFFFFFFFFFFFFFFF, off
+
+
+class _LayerNormResidual(torch.autograd.Function):
+    """(x) -> (x, LayerNorm(x) as bf16).  The first output is x itself: routing the residual branch
+    through it lets backward add the residual gradient inside the LayerNorm-backward pass (K5')."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        lib = _lib.load()
+        _need_cuda(x, gamma, beta)
+        if x.dtype != torch.float32:
+            raise _lib.HwgatError("layer_norm_residual takes the fp32 residual stream")
+        x_c = x.contiguous()
+        d = x_c.shape[-1]
+        n = x_c.numel() // d
+        g_c, b_c = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        y = torch.empty(x_c.shape, dtype=torch.bfloat16, device=x_c.device)
+        mean = torch.empty(n, dtype=torch.float32, device=x_c.device)
+        rstd = torch.empty(n, dtype=torch.float32, device=x_c.device)
+        with torch.cuda.device(x_c.device):
+            check(lib.hwgat_ln_fwd(x_c.data_ptr(), g_c.data_ptr(), b_c.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                   rstd.data_ptr(), n, d, float(eps), _stream()), "hwgat_ln_fwd")
+        ctx.save_for_backward(x_c, g_c, mean, rstd)
+        ctx.meta = (n, d, gamma.dtype, beta.dtype)
+        return x_c.detach(), y
+
+    @staticmethod
+    def backward(ctx, g_res, g_y):
+        lib = _lib.load()
+        x_c, g_c, mean, rstd = ctx.saved_tensors
+        n, d, gdt, bdt = ctx.meta
+        if g_y is None:
+            return g_res, None, None, None
+        dy = g_y.to(torch.bfloat16).contiguous()
+        dres = g_res.float().contiguous() if g_res is not None else None
+        dx = torch.empty_like(x_c)
+        dgamma = torch.empty(d, dtype=torch.float32, device=x_c.device)
+        dbeta = torch.empty(d, dtype=torch.float32, device=x_c.device)
+        with torch.cuda.device(x_c.device):
+            check(lib.hwgat_ln_bwd(dy.data_ptr(), _ptr(dres), x_c.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                   g_c.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), n, d,
+                                   _stream()), "hwgat_ln_bwd")
+        return dx, dgamma.to(gdt), dbeta.to(bdt), None
+
+
+def layer_norm_residual(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5):
+    """Returns (x, y): y = LayerNorm(x) in bf16 (norm1 / norm2 of the block + the autocast cast);
+    use the returned x for the residual add."""
+    return _LayerNormResidual.apply(x, gamma, beta, eps)
+
+
+class _DropoutAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, res, a, p):
+        lib = _lib.load()
+        _need_cuda(res, a)
+        res_c, a_c = res.contiguous(), a.to(torch.bfloat16).contiguous()
+        if res_c.dtype != torch.float32 or res_c.shape != a_c.shape:
+            raise _lib.HwgatError("dropout_add takes an fp32 residual and a same-shape branch")
+        seed, off = _philox_stream(res_c.device) if p > 0 else (0, 0)
+        out = torch.empty_like(res_c)
+        with torch.cuda.device(res_c.device):
+            check(lib.hwgat_dropout_add_fwd(res_c.data_ptr(), a_c.data_ptr(), out.data_ptr(), res_c.numel(), float(p),
+                                            seed, off, _stream()), "hwgat_dropout_add_fwd")
+        ctx.meta = (float(p), seed, off, a.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        p, seed, off, adt = ctx.meta
+        g_c = g.float().contiguous()
+        da = torch.empty(g_c.shape, dtype=torch.bfloat16, device=g_c.device)
+        with torch.cuda.device(g_c.device):
+            check(lib.hwgat_dropout_add_bwd(g_c.data_ptr(), da.data_ptr(), g_c.numel(), p, seed, off, _stream()),
+                  "hwgat_dropout_add_bwd")
+        return g_c, da.to(adt), None
+
+
+def dropout_add(res: torch.Tensor, a: torch.Tensor, p: float, training: bool) -> torch.Tensor:
+    """res + dropout(a): proj_drop + shortcut (HWGATE.py:116, 217) or ff.drop + residual (:135, :219)."""
+    return _DropoutAdd.apply(res, a, p if training else 0.0)
+
+
+class _GeluDropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, p):
+        lib = _lib.load()
+        _need_cuda(u)
+        u_c = u.to(torch.bfloat16).contiguous()
+        seed, off = _philox_stream(u_c.device) if p > 0 else (0, 0)
+        g = torch.empty_like(u_c)
+        with torch.cuda.device(u_c.device):
+            check(lib.hwgat_gelu_dropout_fwd(u_c.data_ptr(), g.data_ptr(), u_c.numel(), float(p), seed, off,
+                                             _stream()), "hwgat_gelu_dropout_fwd")
+        ctx.save_for_backward(u_c)
+        ctx.meta = (float(p), seed, off, u.dtype)
+        return g
+
+    @staticmethod
+    def backward(ctx, dg):
+        lib = _lib.load()
+        (u_c,) = ctx.saved_tensors
+        p, seed, off, udt = ctx.meta
+        dg_c = dg.to(torch.bfloat16).contiguous()
+        du = torch.empty_like(u_c)
+        with torch.cuda.device(u_c.device):
+            check(lib.hwgat_gelu_dropout_bwd(u_c.data_ptr(), dg_c.data_ptr(), du.data_ptr(), u_c.numel(), p, seed, off,
+                                             _stream()), "hwgat_gelu_dropout_bwd")
+        return du.to(udt), None
+
+
+def gelu_dropout(u: torch.Tensor, p: float, training: bool) -> torch.Tensor:
+    """dropout(gelu(u)), exact erf GELU: ff.act + ff.drop (HWGATE.py:132-133)."""
+    return _GeluDropout.apply(u, p if training else 0.0)

@@ -304,3 +304,85 @@ def test_tcgen05_gemm_tn(M, N, Kd):
     ref = A.double().t() @ B.double()
     assert rel_l2(C, ref) < 1e-5
     assert rel_inf(cs, A.double().sum(0)) < 1e-4
+
+
+# ------------------------------------------------------------------ K5-K7: fused block elementwise kernels
+@pytest.mark.parametrize("d", [128, 256, 512])
+@pytest.mark.parametrize("n", [1, 37, 4096])
+def test_layer_norm_residual(d, n):
+    from sl_hwgat_b200 import ops
+    g = torch.Generator().manual_seed(d + n)
+    x = (torch.randn(n, d, generator=g) * 2 + 0.5).cuda().requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(d, generator=g)).cuda().requires_grad_(True)
+    beta = (0.1 * torch.randn(d, generator=g)).cuda().requires_grad_(True)
+    gy = torch.randn(n, d, generator=g).to(torch.bfloat16).cuda()
+    gres = torch.randn(n, d, generator=g).cuda()
+    xa, y = ops.layer_norm_residual(x, gamma, beta, 1e-5)
+    assert torch.equal(xa, x.detach()) and y.dtype == torch.bfloat16
+    (xa * gres).sum().backward(retain_graph=True)
+    y.backward(gy)
+    # fp64 reference of LayerNorm + residual pass-through
+    x64 = x.detach().double().requires_grad_(True)
+    g64, b64 = gamma.detach().double().requires_grad_(True), beta.detach().double().requires_grad_(True)
+    y64 = torch.nn.functional.layer_norm(x64, (d,), g64, b64, 1e-5)
+    ((x64 * gres.double()).sum() + (y64 * gy.double()).sum()).backward()
+    assert rel_inf(y.float(), y64) < 1e-2          # bf16 output rounding
+    assert rel_l2(y.float(), y64) < 3e-3
+    assert rel_inf(x.grad, x64.grad) < 1e-5        # fp32 math on bf16 dy
+    assert rel_inf(gamma.grad, g64.grad) < 1e-4 and rel_inf(beta.grad, b64.grad) < 1e-4
+
+
+@pytest.mark.parametrize("p", [0.0, 0.1, 0.5])
+def test_dropout_add_and_gelu_dropout(p):
+    from sl_hwgat_b200 import ops
+    torch.manual_seed(5)
+    n = 1 << 20
+    res = torch.randn(n, device="cuda").requires_grad_(True)
+    a = torch.randn(n, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    out = ops.dropout_add(res, a, p, True)
+    branch = out.detach() - res.detach()
+    kept = branch != 0
+    if p == 0:
+        assert torch.allclose(branch, a.detach().float(), atol=1e-6)
+    else:
+        frac = 1 - kept.float().mean().item()
+        assert abs(frac - p) < 5e-3, frac                       # drop rate
+        assert torch.allclose(branch[kept], a.detach().float()[kept] / (1 - p), rtol=2e-3, atol=1e-6)   # 1/(1-p) scale
+    g = torch.randn(n, device="cuda")
+    out.backward(g)
+    assert torch.equal(res.grad, g)                              # residual path is the identity
+    want = torch.where(kept, g / (1 - p), torch.zeros_like(g)) if p > 0 else g
+    assert rel_l2(a.grad.float(), want) < 5e-3                   # same mask regenerated in backward
+    # eval mode ignores p
+    assert torch.allclose(ops.dropout_add(res.detach(), a.detach(), p, False), res.detach() + a.detach().float(), atol=1e-6)
+
+    u = (torch.randn(n, device="cuda") * 2).to(torch.bfloat16).requires_grad_(True)
+    y = ops.gelu_dropout(u, p, True)
+    ref = torch.nn.functional.gelu(u.detach().float())
+    big = ref.abs() >= 1e-3                                      # where "output is zero" means "dropped"
+    kept = (y.detach().float() != 0) | ~big
+    if p == 0:
+        assert rel_l2(y.float(), ref) < 3e-3
+    else:
+        frac = 1 - kept[big].float().mean().item()
+        assert abs(frac - p) < 5e-3, frac
+        assert rel_l2(y.detach().float()[kept], (ref / (1 - p))[kept]) < 4e-3
+    gy = torch.randn(n, device="cuda").to(torch.bfloat16)
+    y.backward(gy)
+    u64 = u.detach().double().requires_grad_(True)
+    torch.nn.functional.gelu(u64).backward(gy.double())
+    want = torch.where(kept, u64.grad / (1 - p), torch.zeros_like(u64.grad)) if p > 0 else u64.grad
+    assert rel_l2(u.grad.float()[big], want[big]) < 6e-3
+
+
+def test_dropout_streams_differ_between_calls_and_repeat_with_seed():
+    from sl_hwgat_b200 import ops
+    res = torch.zeros(1 << 16, device="cuda")
+    a = torch.ones(1 << 16, device="cuda").to(torch.bfloat16)
+    torch.manual_seed(11)
+    m1 = ops.dropout_add(res, a, 0.5, True) != 0
+    m2 = ops.dropout_add(res, a, 0.5, True) != 0
+    torch.manual_seed(11)
+    m3 = ops.dropout_add(res, a, 0.5, True) != 0
+    assert not torch.equal(m1, m2) and torch.equal(m1, m3)
+    assert abs((m1 & m2).float().mean().item() - 0.25) < 0.02    # independent masks
