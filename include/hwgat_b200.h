@@ -123,7 +123,7 @@ int hwgat_merge_bwd(const void* d_out, void* d_x, int B, int F, int K, int d, in
 
 /* ---- rest of the block, bf16 / autocast path --------------------------
  * Bandwidth-bound fusions of the PyTorch elementwise chains of PartAttentionBlock.forward
- * (HWGATE.py:189-221) and their autograd.  Dropout masks are regenerated from a Philox4x32-10
+ * (HWGATE.py:189-221) and their autograd.  Dropout masks are regenerated from a Philox4x32-7
  * stream (seed, offset) in forward and backward; nothing is stored.  numel % 8 == 0.            */
 
 /* K5: y(bf16) = LayerNorm(x fp32; gamma, beta, eps) per row of d in {128,256,512}; mean/rstd (n) saved.

@@ -337,7 +337,9 @@ class Model(nn.Module):
             x = layer(x)
         B, f, K, d = x.shape
         x = self.norm(x)
-        return self.avgpool(x.reshape(B, f * K, d).transpose(1, 2)).squeeze(-1)
+        # self.avgpool (AvgPool1d over all f*K tokens, HWGATE.py:354) is a mean over tokens; mean() has the
+        # same value and a broadcast backward instead of avg_pool2d_backward (3.5 ms per step at B=512)
+        return x.reshape(B, f * K, d).mean(dim=1)
 
     def forward(self, x):
         return self.head(self.forward_features(x))
