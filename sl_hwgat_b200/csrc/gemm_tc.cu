@@ -360,7 +360,8 @@ static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int
   cudaMemsetAsync(colsum, 0, sizeof(float) * M, s);
   const int tiles = (M / 128) * (N / BN);
   const int kblocks = (int)(Kd / 64);
-  int splits = (148 + tiles - 1) / tiles;
+  int splits = 148 / tiles;  // one wave: tiles * splits <= 148 SMs (a 149th CTA would double the time)
+  if (splits < 1) splits = 1;
   if (splits > kblocks) splits = kblocks;
   const int per = (kblocks + splits - 1) / splits;
   splits = (kblocks + per - 1) / per;
