@@ -124,7 +124,7 @@ int hwgat_merge_bwd(const void* d_out, void* d_x, int B, int F, int K, int d, in
 /* ---- rest of the block, bf16 / autocast path --------------------------
  * Bandwidth-bound fusions of the PyTorch elementwise chains of PartAttentionBlock.forward
  * (HWGATE.py:189-221) and their autograd.  Dropout masks are regenerated from a Philox4x32-7
- * stream (seed, offset) in forward and backward; nothing is stored.  numel % 8 == 0.            */
+ * stream (seed, offset) in forward and backward; nothing is stored.                             */
 
 /* K5: y(bf16) = LayerNorm(x fp32; gamma, beta, eps) per row of d in {128,256,512}; mean/rstd (n) saved.
  * Replaces self.norm1 / self.norm2 (HWGATE.py:203, 219) + the autocast cast of their output.   */
@@ -135,19 +135,28 @@ int hwgat_ln_fwd(const float* x, const float* gamma, const float* beta, void* y,
 int hwgat_ln_bwd(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
                  const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d,
                  hwgat_stream_t stream);
-/* K6: out(fp32) = res(fp32) + dropout_p(a bf16).  Replaces proj_drop + shortcut add (HWGATE.py:116, 217)
- * and ff.drop + residual add (HWGATE.py:135, 219).  p = 0 -> plain add.                          */
-int hwgat_dropout_add_fwd(const float* res, const void* a, float* out, long long numel, float p,
-                          unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
-/* K6': da(bf16) = mask * dout(fp32) / (1-p)  (the gradient w.r.t. res is dout itself).          */
-int hwgat_dropout_add_bwd(const float* dout, void* da, long long numel, float p, unsigned long long seed,
-                          unsigned long long offset, hwgat_stream_t stream);
-/* K7: g(bf16) = dropout_p(gelu(u bf16)), exact erf GELU.  Replaces ff.act + ff.drop (HWGATE.py:132-133). */
-int hwgat_gelu_dropout_fwd(const void* u, void* g, long long numel, float p, unsigned long long seed,
-                           unsigned long long offset, hwgat_stream_t stream);
-/* K7': du(bf16) = dg * mask / (1-p) * gelu'(u).                                                   */
-int hwgat_gelu_dropout_bwd(const void* u, const void* dg, void* du, long long numel, float p,
-                           unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
+/* K6: x1(fp32) = res(fp32) + dropout_p(a0(bf16) + bias) and, when gamma != NULL, the LayerNorm that consumes
+ * x1 next: y(bf16) = LayerNorm(x1; gamma, beta, eps), mean / rstd (n) saved.  a0 is a Linear output WITHOUT its
+ * bias (bias may be NULL).  Replaces proj bias + proj_drop + shortcut (HWGATE.py:115-116, 217) fused with norm2
+ * (:219), and fc2 bias + ff.drop + residual (:134-135, :219) fused with the next block's norm1 (:203).         */
+int hwgat_bda_ln_fwd(const float* res, const void* a0, const float* bias, const float* gamma, const float* beta,
+                     float* x1, void* y, float* mean, float* rstd, long long n, int d, float eps, float p,
+                     unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
+/* K6': gamma != NULL: d_res(fp32) = (g_x1 ? g_x1 : 0) + LayerNorm'(dy bf16), dgamma, dbeta overwritten;
+ *      gamma == NULL: the gradient w.r.t. res is g_x1 itself and d_res is not written.
+ *      d_a0(bf16) = mask * that / (1-p);  dbias (d, may be NULL) = column sums of d_a0.                          */
+int hwgat_bda_ln_bwd(const float* g_x1, const void* dy, const float* x1, const float* mean, const float* rstd,
+                     const float* gamma, float* d_res, void* d_a0, float* dbias, float* dgamma, float* dbeta,
+                     long long n, int d, float p, unsigned long long seed, unsigned long long offset,
+                     hwgat_stream_t stream);
+/* K7: g(bf16) = dropout_p(gelu(u0(bf16) + bias)), exact erf GELU, u0: (n, cols) a Linear output without bias.
+ * Replaces fc1 bias + ff.act + ff.drop (HWGATE.py:131-133).  cols in {256, 512, 1024}.                          */
+int hwgat_bias_gelu_dropout_fwd(const void* u0, const float* bias, void* g, long long n, int cols, float p,
+                                unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
+/* K7': du0(bf16) = dg * mask / (1-p) * gelu'(u0 + bias);  dbias (cols, may be NULL) = column sums of du0.        */
+int hwgat_bias_gelu_dropout_bwd(const void* u0, const float* bias, const void* dg, void* du0, float* dbias,
+                                long long n, int cols, float p, unsigned long long seed, unsigned long long offset,
+                                hwgat_stream_t stream);
 
 /* Diagnostic: the plain bf16 GEMM K3 uses for d_xn, C[M,N] = A[M,K] . Bt[N,K]^T (fp32 accumulate,
  * TMA + tcgen05).  M % 128 == 0, N % 128 == 0, K % 64 == 0; all row-major bf16 device pointers. */

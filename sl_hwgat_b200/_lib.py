@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libhwgat_b200.so")
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # name -> (restype, argtypes); must list every symbol of include/hwgat_b200.h
 SIGNATURES = {
@@ -31,10 +31,13 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_size_t] + [c_int] * 10 + [c_void_p]),
     "hwgat_ln_fwd": (c_int, [c_void_p] * 6 + [c_longlong, c_int, c_float, c_void_p]),
     "hwgat_ln_bwd": (c_int, [c_void_p] * 9 + [c_longlong, c_int, c_void_p]),
-    "hwgat_dropout_add_fwd": (c_int, [c_void_p] * 3 + [c_longlong, c_float, c_ulonglong, c_ulonglong, c_void_p]),
-    "hwgat_dropout_add_bwd": (c_int, [c_void_p] * 2 + [c_longlong, c_float, c_ulonglong, c_ulonglong, c_void_p]),
-    "hwgat_gelu_dropout_fwd": (c_int, [c_void_p] * 2 + [c_longlong, c_float, c_ulonglong, c_ulonglong, c_void_p]),
-    "hwgat_gelu_dropout_bwd": (c_int, [c_void_p] * 3 + [c_longlong, c_float, c_ulonglong, c_ulonglong, c_void_p]),
+    "hwgat_bda_ln_fwd": (c_int, [c_void_p] * 9 + [c_longlong, c_int, c_float, c_float, c_ulonglong, c_ulonglong,
+                                                  c_void_p]),
+    "hwgat_bda_ln_bwd": (c_int, [c_void_p] * 11 + [c_longlong, c_int, c_float, c_ulonglong, c_ulonglong, c_void_p]),
+    "hwgat_bias_gelu_dropout_fwd": (c_int, [c_void_p] * 3 + [c_longlong, c_int, c_float, c_ulonglong, c_ulonglong,
+                                                             c_void_p]),
+    "hwgat_bias_gelu_dropout_bwd": (c_int, [c_void_p] * 5 + [c_longlong, c_int, c_float, c_ulonglong, c_ulonglong,
+                                                             c_void_p]),
     "hwgat_debug_gemm_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hwgat_debug_gemm_tn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
     "hwgat_merge_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),

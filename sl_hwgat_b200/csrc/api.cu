@@ -26,7 +26,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 3; }
+int hwgat_version(void) { return 4; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -117,12 +117,6 @@ int hwgat_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const f
   return dtype == HWGAT_F32 ? attn_bwd_f32(a, (cudaStream_t)stream) : attn_bwd_bf16(a, (cudaStream_t)stream);
 }
 
-static int check_ew(long long numel, float p) {
-  if (numel < 0 || !(p >= 0.f) || p >= 1.f) return HWGAT_ERR_SHAPE;
-  if (numel % 8) return HWGAT_ERR_UNSUPPORTED;
-  return HWGAT_OK;
-}
-
 int hwgat_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                  long long n, int d, float eps, hwgat_stream_t stream) {
   if (n < 0) return HWGAT_ERR_SHAPE;
@@ -145,48 +139,71 @@ int hwgat_ln_bwd(const void* dy, const float* dres, const float* x, const float*
                        (cudaStream_t)stream);
 }
 
-int hwgat_dropout_add_fwd(const float* res, const void* a, float* out, long long numel, float p,
-                          unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
-  int st = check_ew(numel, p);
-  if (st) return st;
-  if (numel == 0) return HWGAT_OK;
-  if (!res || !a || !out) return HWGAT_ERR_NULL;
-  if (misaligned(res) || misaligned(a) || misaligned(out)) return HWGAT_ERR_ALIGN;
-  return launch_dropout_add(res, (const __nv_bfloat16*)a, out, nullptr, numel, p, seed, offset, false,
-                            (cudaStream_t)stream);
+static bool bad_p(float p) { return !(p >= 0.f) || p >= 1.f; }
+
+int hwgat_bda_ln_fwd(const float* res, const void* a0, const float* bias, const float* gamma, const float* beta,
+                     float* x1, void* y, float* mean, float* rstd, long long n, int d, float eps, float p,
+                     unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  if (n < 0 || bad_p(p)) return HWGAT_ERR_SHAPE;
+  if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
+  if (n == 0) return HWGAT_OK;
+  if (!res || !a0 || !x1) return HWGAT_ERR_NULL;
+  if (gamma && (!beta || !y || !mean || !rstd)) return HWGAT_ERR_NULL;
+  if (misaligned(res) || misaligned(a0) || misaligned(bias) || misaligned(gamma) || misaligned(beta) ||
+      misaligned(x1) || misaligned(y))
+    return HWGAT_ERR_ALIGN;
+  return launch_bda_ln_fwd(res, (const __nv_bfloat16*)a0, bias, gamma, beta, x1, (__nv_bfloat16*)y, mean, rstd, n, d,
+                           eps, p, seed, offset, (cudaStream_t)stream);
 }
 
-int hwgat_dropout_add_bwd(const float* dout, void* da, long long numel, float p, unsigned long long seed,
-                          unsigned long long offset, hwgat_stream_t stream) {
-  int st = check_ew(numel, p);
-  if (st) return st;
-  if (numel == 0) return HWGAT_OK;
-  if (!dout || !da) return HWGAT_ERR_NULL;
-  if (misaligned(dout) || misaligned(da)) return HWGAT_ERR_ALIGN;
-  return launch_dropout_add(dout, nullptr, nullptr, (__nv_bfloat16*)da, numel, p, seed, offset, true,
-                            (cudaStream_t)stream);
+int hwgat_bda_ln_bwd(const float* g_x1, const void* dy, const float* x1, const float* mean, const float* rstd,
+                     const float* gamma, float* d_res, void* d_a0, float* dbias, float* dgamma, float* dbeta,
+                     long long n, int d, float p, unsigned long long seed, unsigned long long offset,
+                     hwgat_stream_t stream) {
+  if (n < 0 || bad_p(p)) return HWGAT_ERR_SHAPE;
+  if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
+  if (gamma && (!dgamma || !dbeta)) return HWGAT_ERR_NULL;
+  if (n > 0) {
+    if (!d_a0) return HWGAT_ERR_NULL;
+    if (gamma ? (!dy || !x1 || !mean || !rstd || !d_res) : !g_x1) return HWGAT_ERR_NULL;
+  }
+  if (misaligned(g_x1) || misaligned(dy) || misaligned(x1) || misaligned(gamma) || misaligned(d_res) ||
+      misaligned(d_a0))
+    return HWGAT_ERR_ALIGN;
+  return launch_bda_ln_bwd(g_x1, (const __nv_bfloat16*)dy, x1, mean, rstd, gamma, d_res, (__nv_bfloat16*)d_a0, dbias,
+                           dgamma, dbeta, n, d, p, seed, offset, (cudaStream_t)stream);
 }
 
-int hwgat_gelu_dropout_fwd(const void* u, void* g, long long numel, float p, unsigned long long seed,
-                           unsigned long long offset, hwgat_stream_t stream) {
-  int st = check_ew(numel, p);
-  if (st) return st;
-  if (numel == 0) return HWGAT_OK;
-  if (!u || !g) return HWGAT_ERR_NULL;
-  if (misaligned(u) || misaligned(g)) return HWGAT_ERR_ALIGN;
-  return launch_gelu_dropout((const __nv_bfloat16*)u, nullptr, (__nv_bfloat16*)g, numel, p, seed, offset, false,
-                             (cudaStream_t)stream);
+static int check_gelu(long long n, int cols, float p) {
+  if (n < 0 || bad_p(p)) return HWGAT_ERR_SHAPE;
+  if (cols != 256 && cols != 512 && cols != 1024) return HWGAT_ERR_UNSUPPORTED;
+  return HWGAT_OK;
 }
 
-int hwgat_gelu_dropout_bwd(const void* u, const void* dg, void* du, long long numel, float p,
-                           unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
-  int st = check_ew(numel, p);
+int hwgat_bias_gelu_dropout_fwd(const void* u0, const float* bias, void* g, long long n, int cols, float p,
+                                unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  int st = check_gelu(n, cols, p);
   if (st) return st;
-  if (numel == 0) return HWGAT_OK;
-  if (!u || !dg || !du) return HWGAT_ERR_NULL;
-  if (misaligned(u) || misaligned(dg) || misaligned(du)) return HWGAT_ERR_ALIGN;
-  return launch_gelu_dropout((const __nv_bfloat16*)u, (const __nv_bfloat16*)dg, (__nv_bfloat16*)du, numel, p, seed,
-                             offset, true, (cudaStream_t)stream);
+  if (n == 0) return HWGAT_OK;
+  if (!u0 || !g) return HWGAT_ERR_NULL;
+  if (misaligned(u0) || misaligned(g)) return HWGAT_ERR_ALIGN;
+  return launch_bias_gelu_dropout((const __nv_bfloat16*)u0, bias, nullptr, (__nv_bfloat16*)g, nullptr, n, cols, p,
+                                  seed, offset, false, (cudaStream_t)stream);
+}
+
+int hwgat_bias_gelu_dropout_bwd(const void* u0, const float* bias, const void* dg, void* du0, float* dbias,
+                                long long n, int cols, float p, unsigned long long seed, unsigned long long offset,
+                                hwgat_stream_t stream) {
+  int st = check_gelu(n, cols, p);
+  if (st) return st;
+  if (n == 0) {
+    if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * cols, (cudaStream_t)stream);
+    return HWGAT_OK;
+  }
+  if (!u0 || !dg || !du0) return HWGAT_ERR_NULL;
+  if (misaligned(u0) || misaligned(dg) || misaligned(du0)) return HWGAT_ERR_ALIGN;
+  return launch_bias_gelu_dropout((const __nv_bfloat16*)u0, bias, (const __nv_bfloat16*)dg, (__nv_bfloat16*)du0, dbias,
+                                  n, cols, p, seed, offset, true, (cudaStream_t)stream);
 }
 
 int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream) {

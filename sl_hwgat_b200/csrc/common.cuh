@@ -117,10 +117,15 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, __nv_bf
                   long long n, int d, float eps, cudaStream_t s);
 int launch_ln_bwd(const __nv_bfloat16* dy, const float* dres, const float* x, const float* mean, const float* rstd,
                   const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d, cudaStream_t s);
-int launch_dropout_add(const float* res_or_dout, const __nv_bfloat16* a, float* out, __nv_bfloat16* da, long long numel,
-                       float p, unsigned long long seed, unsigned long long offset, bool backward, cudaStream_t s);
-int launch_gelu_dropout(const __nv_bfloat16* u, const __nv_bfloat16* dg, __nv_bfloat16* out, long long numel, float p,
-                        unsigned long long seed, unsigned long long offset, bool backward, cudaStream_t s);
+int launch_bda_ln_fwd(const float* res, const __nv_bfloat16* a0, const float* bias, const float* gamma,
+                      const float* beta, float* x1, __nv_bfloat16* y, float* mean, float* rstd, long long n, int d,
+                      float eps, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s);
+int launch_bda_ln_bwd(const float* g_x1, const __nv_bfloat16* dy, const float* x1, const float* mean, const float* rstd,
+                      const float* gamma, float* d_res, __nv_bfloat16* d_a0, float* dbias, float* dgamma, float* dbeta,
+                      long long n, int d, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s);
+int launch_bias_gelu_dropout(const __nv_bfloat16* u0, const float* bias, const __nv_bfloat16* dg, __nv_bfloat16* out,
+                             float* dbias, long long n, int cols, float p, unsigned long long seed,
+                             unsigned long long offset, bool backward, cudaStream_t s);
 
 struct AttnArgs {
   const void* xn; const void* w_qkv; const float* b_qkv; const uint32_t* bits;

@@ -222,22 +222,33 @@ class PartAttentionBlock(nn.Module):
                 and type(self.norm1) is nn.LayerNorm and type(self.norm2) is nn.LayerNorm
                 and isinstance(self.ff.act, nn.GELU) and getattr(self.ff.act, "approximate", "none") == "none")
 
-    def forward(self, x):
+    def _check_shape(self, x):
         B, F, K, d = x.shape
         if F != self.temporal_dim or K != self.num_kps:
             raise ValueError(f"expected (B,{self.temporal_dim},{self.num_kps},d), got {tuple(x.shape)}")
-        bits = self._block_bits(x.device)
+
+    def forward(self, x):
+        self._check_shape(x)
         if not self._fusable(x):
-            x = x + self.attn.attend(self.norm1(x), self.shift_size, bits)
+            x = x + self.attn.attend(self.norm1(x), self.shift_size, self._block_bits(x.device))
             return x + self.ff(self.norm2(x))
-        attn, ff, p = self.attn, self.ff, float(self.drop)
         x, xn = ops.layer_norm_residual(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        ctx = ops.window_graph_attention(xn, attn.qkv.weight, attn.qkv.bias, bits, attn.num_heads,
-                                         shift=self.shift_size, threshold=attn._draw_threshold(), layout=LAYOUT_BFKD)
-        x = ops.dropout_add(x, attn.proj(ctx), attn.proj_drop.p, self.training)
-        x, h = ops.layer_norm_residual(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        u = ops.gelu_dropout(ff.fc1(h), ff.drop.p, self.training)
-        return ops.dropout_add(x, ff.fc2(u), ff.drop.p, self.training)
+        return self.forward_chain(x, xn, None)[0]
+
+    def forward_chain(self, x, xn, next_norm):
+        """Fused bf16 path.  x: fp32 residual stream, xn = norm1(x) in bf16 (made by the previous kernel of the
+        chain).  Returns (x_out, next_norm(x_out) in bf16 or None): the LayerNorm that consumes the block's output
+        is computed by the same kernel that forms the output (K6)."""
+        attn, ff = self.attn, self.ff
+        ctx = ops.window_graph_attention(xn, attn.qkv.weight, attn.qkv.bias, self._block_bits(x.device),
+                                         attn.num_heads, shift=self.shift_size, threshold=attn._draw_threshold(),
+                                         layout=LAYOUT_BFKD)
+        a0 = nn.functional.linear(ctx, attn.proj.weight)           # bias, dropout, shortcut and norm2: K6
+        x, h = ops.bias_dropout_add_ln(x, a0, attn.proj.bias, self.norm2, attn.proj_drop.p, self.training)
+        u0 = nn.functional.linear(h, ff.fc1.weight)                # bias, GELU, dropout: K7
+        g = ops.bias_gelu_dropout(u0, ff.fc1.bias, ff.drop.p, self.training)
+        v0 = nn.functional.linear(g, ff.fc2.weight)                # bias, dropout, residual (and the next norm1): K6
+        return ops.bias_dropout_add_ln(x, v0, ff.fc2.bias, next_norm, ff.drop.p, self.training)
 
 
 class PartAttentionLayer(nn.Module):
@@ -263,8 +274,16 @@ class PartAttentionLayer(nn.Module):
         self.downsample = downsample(dim, temporal_patch_size) if downsample is not None else None
 
     def forward(self, x):
-        for blk in self.blocks:
-            x = blk(x)
+        blocks = list(self.blocks)
+        if blocks and all(b._fusable(x) for b in blocks):
+            first = blocks[0]
+            x, xn = ops.layer_norm_residual(x, first.norm1.weight, first.norm1.bias, first.norm1.eps)
+            for i, blk in enumerate(blocks):
+                nxt = blocks[i + 1].norm1 if i + 1 < len(blocks) else None
+                x, xn = blk.forward_chain(x, xn, nxt)
+        else:
+            for blk in blocks:
+                x = blk(x)
         if self.downsample is not None:
             x = self.downsample(x)
         return x

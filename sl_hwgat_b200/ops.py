@@ -268,67 +268,110 @@ def layer_norm_residual(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor
     return _LayerNormResidual.apply(x, gamma, beta, eps)
 
 
-class _DropoutAdd(torch.autograd.Function):
+class _BiasDropoutAddLN(torch.autograd.Function):
+    """x1 = res + dropout(a0 + bias); optionally y = LayerNorm(x1) as bf16 in the same pass (K6 / K6')."""
+
     @staticmethod
-    def forward(ctx, res, a, p):
+    def forward(ctx, res, a0, bias, gamma, beta, eps, p):
         lib = _lib.load()
-        _need_cuda(res, a)
-        res_c, a_c = res.contiguous(), a.to(torch.bfloat16).contiguous()
+        _need_cuda(res, a0, bias, gamma, beta)
+        res_c, a_c = res.contiguous(), a0.to(torch.bfloat16).contiguous()
         if res_c.dtype != torch.float32 or res_c.shape != a_c.shape:
-            raise _lib.HwgatError("dropout_add takes an fp32 residual and a same-shape branch")
-        seed, off = _philox_stream(res_c.device) if p > 0 else (0, 0)
-        out = torch.empty_like(res_c)
-        with torch.cuda.device(res_c.device):
-            check(lib.hwgat_dropout_add_fwd(res_c.data_ptr(), a_c.data_ptr(), out.data_ptr(), res_c.numel(), float(p),
-                                            seed, off, _stream()), "hwgat_dropout_add_fwd")
-        ctx.meta = (float(p), seed, off, a.dtype)
-        return out
+            raise _lib.HwgatError("bias_dropout_add_ln takes an fp32 residual and a same-shape branch")
+        d = res_c.shape[-1]
+        n = res_c.numel() // d
+        dev = res_c.device
+        has_ln = gamma is not None
+        b_c = bias.detach().float().contiguous() if bias is not None else None
+        g_c = gamma.detach().float().contiguous() if has_ln else None
+        bt_c = beta.detach().float().contiguous() if has_ln else None
+        seed, off = _philox_stream(dev) if p > 0 else (0, 0)
+        x1 = torch.empty_like(res_c)
+        y = torch.empty(res_c.shape, dtype=torch.bfloat16, device=dev) if has_ln else None
+        mean = torch.empty(n, dtype=torch.float32, device=dev) if has_ln else None
+        rstd = torch.empty(n, dtype=torch.float32, device=dev) if has_ln else None
+        with torch.cuda.device(dev):
+            check(lib.hwgat_bda_ln_fwd(res_c.data_ptr(), a_c.data_ptr(), _ptr(b_c), _ptr(g_c), _ptr(bt_c),
+                                       x1.data_ptr(), _ptr(y), _ptr(mean), _ptr(rstd), n, d, float(eps), float(p),
+                                       seed, off, _stream()), "hwgat_bda_ln_fwd")
+        if has_ln:
+            ctx.save_for_backward(x1, g_c, mean, rstd)
+        ctx.meta = (n, d, float(p), seed, off, has_ln, a0.dtype,
+                    None if bias is None else bias.dtype, None if gamma is None else gamma.dtype,
+                    None if beta is None else beta.dtype)
+        if has_ln:
+            return x1, y
+        return x1, None
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g_x1, g_y):
         lib = _lib.load()
-        p, seed, off, adt = ctx.meta
-        g_c = g.float().contiguous()
-        da = torch.empty(g_c.shape, dtype=torch.bfloat16, device=g_c.device)
-        with torch.cuda.device(g_c.device):
-            check(lib.hwgat_dropout_add_bwd(g_c.data_ptr(), da.data_ptr(), g_c.numel(), p, seed, off, _stream()),
-                  "hwgat_dropout_add_bwd")
-        return g_c, da.to(adt), None
+        n, d, p, seed, off, has_ln, adt, bdt, gdt, btdt = ctx.meta
+        dev = (g_x1 if g_x1 is not None else g_y).device
+        gx = g_x1.float().contiguous() if g_x1 is not None else None
+        d_a0 = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
+        dbias = torch.empty(d, dtype=torch.float32, device=dev) if bdt is not None else None
+        if has_ln:
+            x1, g_c, mean, rstd = ctx.saved_tensors
+            dy = (g_y if g_y is not None else torch.zeros_like(x1, dtype=torch.bfloat16)).to(torch.bfloat16).contiguous()
+            d_res = torch.empty_like(x1)
+            dgamma = torch.empty(d, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(d, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                check(lib.hwgat_bda_ln_bwd(_ptr(gx), dy.data_ptr(), x1.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                           g_c.data_ptr(), d_res.data_ptr(), d_a0.data_ptr(), _ptr(dbias),
+                                           dgamma.data_ptr(), dbeta.data_ptr(), n, d, p, seed, off, _stream()),
+                      "hwgat_bda_ln_bwd")
+            shape = x1.shape
+            return (d_res, d_a0.view(shape).to(adt), None if dbias is None else dbias.to(bdt), dgamma.to(gdt),
+                    dbeta.to(btdt), None, None)
+        with torch.cuda.device(dev):
+            check(lib.hwgat_bda_ln_bwd(gx.data_ptr(), 0, 0, 0, 0, 0, 0, d_a0.data_ptr(), _ptr(dbias), 0, 0, n, d, p,
+                                       seed, off, _stream()), "hwgat_bda_ln_bwd")
+        return gx, d_a0.view(gx.shape).to(adt), None if dbias is None else dbias.to(bdt), None, None, None, None
 
 
-def dropout_add(res: torch.Tensor, a: torch.Tensor, p: float, training: bool) -> torch.Tensor:
-    """res + dropout(a): proj_drop + shortcut (HWGATE.py:116, 217) or ff.drop + residual (:135, :219)."""
-    return _DropoutAdd.apply(res, a, p if training else 0.0)
+def bias_dropout_add_ln(res: torch.Tensor, a0: torch.Tensor, bias: Optional[torch.Tensor], norm, p: float,
+                        training: bool):
+    """x1 = res + dropout(a0 + bias) [Linear bias + proj_drop / ff.drop + shortcut, HWGATE.py:115-116, 134-135,
+    217, 219] and, if `norm` (an nn.LayerNorm) is given, y = norm(x1) as bf16 in the same pass.  Returns (x1, y)."""
+    if norm is None:
+        return _BiasDropoutAddLN.apply(res, a0, bias, None, None, 0.0, p if training else 0.0)
+    return _BiasDropoutAddLN.apply(res, a0, bias, norm.weight, norm.bias, norm.eps, p if training else 0.0)
 
 
-class _GeluDropout(torch.autograd.Function):
+class _BiasGeluDropout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, u, p):
+    def forward(ctx, u0, bias, p):
         lib = _lib.load()
-        _need_cuda(u)
-        u_c = u.to(torch.bfloat16).contiguous()
+        _need_cuda(u0, bias)
+        u_c = u0.to(torch.bfloat16).contiguous()
+        cols = u_c.shape[-1]
+        n = u_c.numel() // cols
+        b_c = bias.detach().float().contiguous() if bias is not None else None
         seed, off = _philox_stream(u_c.device) if p > 0 else (0, 0)
         g = torch.empty_like(u_c)
         with torch.cuda.device(u_c.device):
-            check(lib.hwgat_gelu_dropout_fwd(u_c.data_ptr(), g.data_ptr(), u_c.numel(), float(p), seed, off,
-                                             _stream()), "hwgat_gelu_dropout_fwd")
-        ctx.save_for_backward(u_c)
-        ctx.meta = (float(p), seed, off, u.dtype)
+            check(lib.hwgat_bias_gelu_dropout_fwd(u_c.data_ptr(), _ptr(b_c), g.data_ptr(), n, cols, float(p), seed, off,
+                                                  _stream()), "hwgat_bias_gelu_dropout_fwd")
+        ctx.save_for_backward(u_c, b_c)
+        ctx.meta = (n, cols, float(p), seed, off, u0.dtype, None if bias is None else bias.dtype)
         return g
 
     @staticmethod
     def backward(ctx, dg):
         lib = _lib.load()
-        (u_c,) = ctx.saved_tensors
-        p, seed, off, udt = ctx.meta
+        u_c, b_c = ctx.saved_tensors
+        n, cols, p, seed, off, udt, bdt = ctx.meta
         dg_c = dg.to(torch.bfloat16).contiguous()
         du = torch.empty_like(u_c)
+        dbias = torch.empty(cols, dtype=torch.float32, device=u_c.device) if bdt is not None else None
         with torch.cuda.device(u_c.device):
-            check(lib.hwgat_gelu_dropout_bwd(u_c.data_ptr(), dg_c.data_ptr(), du.data_ptr(), u_c.numel(), p, seed, off,
-                                             _stream()), "hwgat_gelu_dropout_bwd")
-        return du.to(udt), None
+            check(lib.hwgat_bias_gelu_dropout_bwd(u_c.data_ptr(), _ptr(b_c), dg_c.data_ptr(), du.data_ptr(), _ptr(dbias),
+                                                  n, cols, p, seed, off, _stream()), "hwgat_bias_gelu_dropout_bwd")
+        return du.to(udt), None if dbias is None else dbias.to(bdt), None
 
 
-def gelu_dropout(u: torch.Tensor, p: float, training: bool) -> torch.Tensor:
-    """dropout(gelu(u)), exact erf GELU: ff.act + ff.drop (HWGATE.py:132-133)."""
-    return _GeluDropout.apply(u, p if training else 0.0)
+def bias_gelu_dropout(u0: torch.Tensor, bias: Optional[torch.Tensor], p: float, training: bool) -> torch.Tensor:
+    """dropout(gelu(u0 + bias)), exact erf GELU: fc1 bias + ff.act + ff.drop (HWGATE.py:131-133)."""
+    return _BiasGeluDropout.apply(u0, bias, p if training else 0.0)

@@ -332,57 +332,105 @@ def test_layer_norm_residual(d, n):
     assert rel_inf(gamma.grad, g64.grad) < 1e-4 and rel_inf(beta.grad, b64.grad) < 1e-4
 
 
-@pytest.mark.parametrize("p", [0.0, 0.1, 0.5])
-def test_dropout_add_and_gelu_dropout(p):
+@pytest.mark.parametrize("d", [128, 256, 512])
+@pytest.mark.parametrize("with_ln", [False, True])
+def test_bias_dropout_add_ln_no_dropout(d, with_ln):
+    """p = 0: x1 = res + a0 + bias and y = LayerNorm(x1); gradients against an fp64 reference."""
+    from sl_hwgat_b200 import ops
+    g = torch.Generator().manual_seed(d)
+    n = 777
+    res = torch.randn(n, d, generator=g).cuda().requires_grad_(True)
+    a0 = torch.randn(n, d, generator=g).to(torch.bfloat16).cuda().requires_grad_(True)
+    bias = (0.3 * torch.randn(d, generator=g)).cuda().requires_grad_(True)
+    norm = torch.nn.LayerNorm(d).cuda() if with_ln else None
+    if with_ln:
+        with torch.no_grad():
+            norm.weight.copy_(1 + 0.1 * torch.randn(d, generator=g)); norm.bias.copy_(0.1 * torch.randn(d, generator=g))
+    x1, y = ops.bias_dropout_add_ln(res, a0, bias, norm, 0.3, False)      # eval: p ignored
+    gx = torch.randn(n, d, generator=g).cuda()
+    gy = torch.randn(n, d, generator=g).to(torch.bfloat16).cuda()
+    loss = (x1 * gx).sum() + ((y.float() * gy.float()).sum() if with_ln else 0)
+    loss.backward()
+    r64, a64, b64 = (t.detach().double().requires_grad_(True) for t in (res, a0, bias))
+    x64 = r64 + a64 + b64
+    l64 = (x64 * gx.double()).sum()
+    if with_ln:
+        w64, bb64 = norm.weight.detach().double().requires_grad_(True), norm.bias.detach().double().requires_grad_(True)
+        y64 = torch.nn.functional.layer_norm(x64, (d,), w64, bb64, norm.eps)
+        l64 = l64 + (y64 * gy.double()).sum()
+    l64.backward()
+    assert rel_inf(x1, x64) < 1e-6
+    assert rel_inf(res.grad, r64.grad) < 1e-5
+    assert rel_l2(a0.grad.float(), a64.grad) < 4e-3                       # bf16 gradient
+    assert rel_inf(bias.grad, b64.grad) < 1e-4                           # column sums in fp32
+    if with_ln:
+        assert y.dtype == torch.bfloat16 and rel_l2(y.float(), y64) < 3e-3
+        assert rel_inf(norm.weight.grad, w64.grad) < 1e-4 and rel_inf(norm.bias.grad, bb64.grad) < 1e-4
+    else:
+        assert y is None
+
+
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_bias_dropout_add_ln_masks(p):
+    """dropout: rate, 1/(1-p) scaling, and the SAME mask regenerated by the backward kernel."""
     from sl_hwgat_b200 import ops
     torch.manual_seed(5)
-    n = 1 << 20
-    res = torch.randn(n, device="cuda").requires_grad_(True)
-    a = torch.randn(n, device="cuda").to(torch.bfloat16).requires_grad_(True)
-    out = ops.dropout_add(res, a, p, True)
-    branch = out.detach() - res.detach()
-    kept = branch != 0
-    if p == 0:
-        assert torch.allclose(branch, a.detach().float(), atol=1e-6)
-    else:
-        frac = 1 - kept.float().mean().item()
-        assert abs(frac - p) < 5e-3, frac                       # drop rate
-        assert torch.allclose(branch[kept], a.detach().float()[kept] / (1 - p), rtol=2e-3, atol=1e-6)   # 1/(1-p) scale
-    g = torch.randn(n, device="cuda")
-    out.backward(g)
-    assert torch.equal(res.grad, g)                              # residual path is the identity
-    want = torch.where(kept, g / (1 - p), torch.zeros_like(g)) if p > 0 else g
-    assert rel_l2(a.grad.float(), want) < 5e-3                   # same mask regenerated in backward
-    # eval mode ignores p
-    assert torch.allclose(ops.dropout_add(res.detach(), a.detach(), p, False), res.detach() + a.detach().float(), atol=1e-6)
+    n, d = 4096, 256
+    res = torch.zeros(n, d, device="cuda").requires_grad_(True)
+    a0 = (torch.rand(n, d, device="cuda") + 0.5).to(torch.bfloat16).requires_grad_(True)   # never zero
+    norm = torch.nn.LayerNorm(d).cuda()
+    x1, y = ops.bias_dropout_add_ln(res, a0, None, norm, p, True)
+    kept = x1.detach() != 0
+    assert abs(1 - kept.float().mean().item() - p) < 5e-3
+    assert torch.allclose(x1.detach()[kept], a0.detach().float()[kept] / (1 - p), rtol=2e-3)
+    gx = torch.randn(n, d, device="cuda")
+    (x1 * gx).sum().backward()           # y unused: the LayerNorm branch contributes nothing
+    assert torch.allclose(res.grad, gx, atol=1e-6)
+    want = torch.where(kept, gx / (1 - p), torch.zeros_like(gx))
+    assert rel_l2(a0.grad.float(), want) < 5e-3
+    # eval ignores p
+    xe, _ = ops.bias_dropout_add_ln(res.detach(), a0.detach(), None, None, p, False)
+    assert torch.allclose(xe, a0.detach().float(), atol=1e-6)
 
-    u = (torch.randn(n, device="cuda") * 2).to(torch.bfloat16).requires_grad_(True)
-    y = ops.gelu_dropout(u, p, True)
-    ref = torch.nn.functional.gelu(u.detach().float())
+
+@pytest.mark.parametrize("p", [0.0, 0.1, 0.5])
+@pytest.mark.parametrize("cols", [256, 1024])
+def test_bias_gelu_dropout(p, cols):
+    from sl_hwgat_b200 import ops
+    torch.manual_seed(6)
+    n = 2048
+    u = (torch.randn(n, cols, device="cuda") * 2).to(torch.bfloat16).requires_grad_(True)
+    bias = (0.5 * torch.randn(cols, device="cuda")).requires_grad_(True)
+    y = ops.bias_gelu_dropout(u, bias, p, True)
+    pre = u.detach().float() + bias.detach()
+    ref = torch.nn.functional.gelu(pre)
     big = ref.abs() >= 1e-3                                      # where "output is zero" means "dropped"
     kept = (y.detach().float() != 0) | ~big
     if p == 0:
         assert rel_l2(y.float(), ref) < 3e-3
     else:
-        frac = 1 - kept[big].float().mean().item()
-        assert abs(frac - p) < 5e-3, frac
+        assert abs(1 - kept[big].float().mean().item() - p) < 6e-3
         assert rel_l2(y.detach().float()[kept], (ref / (1 - p))[kept]) < 4e-3
-    gy = torch.randn(n, device="cuda").to(torch.bfloat16)
+    gy = torch.randn(n, cols, device="cuda").to(torch.bfloat16)
     y.backward(gy)
-    u64 = u.detach().double().requires_grad_(True)
-    torch.nn.functional.gelu(u64).backward(gy.double())
-    want = torch.where(kept, u64.grad / (1 - p), torch.zeros_like(u64.grad)) if p > 0 else u64.grad
+    pre64 = pre.double().requires_grad_(True)
+    torch.nn.functional.gelu(pre64).backward(gy.double())
+    want = torch.where(kept, pre64.grad / (1 - p), torch.zeros_like(pre64.grad)) if p > 0 else pre64.grad
     assert rel_l2(u.grad.float()[big], want[big]) < 6e-3
+    # dbias = column sums of du0 (the mask of near-zero outputs cannot be inferred, so compare with the kernel's own du0)
+    assert rel_l2(bias.grad, u.grad.double().sum(0)) < 5e-3
+    if p == 0:
+        assert rel_l2(bias.grad, want.sum(0)) < 5e-3
 
 
 def test_dropout_streams_differ_between_calls_and_repeat_with_seed():
     from sl_hwgat_b200 import ops
-    res = torch.zeros(1 << 16, device="cuda")
-    a = torch.ones(1 << 16, device="cuda").to(torch.bfloat16)
+    res = torch.zeros(512, 128, device="cuda")
+    a = torch.ones(512, 128, device="cuda").to(torch.bfloat16)
     torch.manual_seed(11)
-    m1 = ops.dropout_add(res, a, 0.5, True) != 0
-    m2 = ops.dropout_add(res, a, 0.5, True) != 0
+    m1 = ops.bias_dropout_add_ln(res, a, None, None, 0.5, True)[0] != 0
+    m2 = ops.bias_dropout_add_ln(res, a, None, None, 0.5, True)[0] != 0
     torch.manual_seed(11)
-    m3 = ops.dropout_add(res, a, 0.5, True) != 0
+    m3 = ops.bias_dropout_add_ln(res, a, None, None, 0.5, True)[0] != 0
     assert not torch.equal(m1, m2) and torch.equal(m1, m3)
     assert abs((m1 & m2).float().mean().item() - 0.25) < 0.02    # independent masks
