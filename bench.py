@@ -106,10 +106,26 @@ class KernelTimer:
         import torch
         self.torch, self.lib, self.on, self.rec = torch, lib, False, []
         self.orig = {}
-        for name in ("hwgat_attn_fwd", "hwgat_attn_bwd", "hwgat_merge_fwd", "hwgat_merge_bwd"):
+        for name in ("hwgat_attn_fwd", "hwgat_attn_bwd", "hwgat_merge_fwd", "hwgat_merge_bwd", "hwgat_ln_fwd",
+                     "hwgat_ln_bwd", "hwgat_bda_ln_fwd", "hwgat_bda_ln_bwd", "hwgat_bias_gelu_dropout_fwd",
+                     "hwgat_bias_gelu_dropout_bwd"):
             fn = getattr(lib, name)
             self.orig[name] = fn
             setattr(lib, name, self._wrap(name, fn))
+
+    # (columns of the tensor, extra info) from the C-ABI argument list of each entry point
+    DIM_ARG = {
+        "hwgat_attn_fwd": lambda a: (int(a[11]), 0), "hwgat_attn_bwd": lambda a: (int(a[14]), 0),
+        "hwgat_merge_fwd": lambda a: (int(a[5]), 0), "hwgat_merge_bwd": lambda a: (int(a[5]), 0),
+        "hwgat_ln_fwd": lambda a: (int(a[7]), int(a[6])), "hwgat_ln_bwd": lambda a: (int(a[10]), int(a[9])),
+        "hwgat_bda_ln_fwd": lambda a: (int(a[10]), int(a[9]), bool(a[3])),
+        "hwgat_bda_ln_bwd": lambda a: (int(a[12]), int(a[11]), bool(a[5])),
+        "hwgat_bias_gelu_dropout_fwd": lambda a: (int(a[4]), int(a[3])),
+        "hwgat_bias_gelu_dropout_bwd": lambda a: (int(a[6]), int(a[5])),
+    }
+    # algorithmic HBM bytes per element of the bandwidth-bound kernels
+    BYTES_PER_ELEM = {"hwgat_ln_fwd": 6, "hwgat_ln_bwd": 14, "hwgat_bias_gelu_dropout_fwd": 4,
+                      "hwgat_bias_gelu_dropout_bwd": 6}
 
     def _wrap(self, name, fn):
         def call(*a):
@@ -119,8 +135,8 @@ class KernelTimer:
             e0.record()
             r = fn(*a)
             e1.record()
-            d = a[11] if name == "hwgat_attn_fwd" else a[14] if name == "hwgat_attn_bwd" else a[5]
-            self.rec.append((name, int(d), e0, e1))
+            d = self.DIM_ARG[name](a)
+            self.rec.append((name, d, e0, e1))
             return r
         return call
 
@@ -137,7 +153,8 @@ class KernelTimer:
             a[0] += ms
             a[1] += 1
         out = []
-        for (name, d), (ms, cnt) in sorted(agg.items()):
+        for (name, key), (ms, cnt) in sorted(agg.items()):
+            d = key[0]
             avg = ms / cnt
             if "attn" in name:
                 level = {128: 0, 256: 1, 512: 2}[d]
@@ -145,12 +162,19 @@ class KernelTimer:
                 out.append({"kernel": ("K3 " if name.endswith("bwd") else "K2 ") + f"{name} d={d}", "bound": "tensor",
                             "calls_per_step": cnt / steps, "avg_ms": avg, "alg_flops": fl,
                             "achieved": fl / (avg * 1e-3) / 1e12, "unit": "TFLOP/s", "total_ms": ms})
+                continue
+            if "merge" in name:
+                label, by = "K4 " + f"{name} d={d}", merge_bytes(B, {128: 0, 256: 1}[d], 4)  # fp32 residual stream
+            elif "bda_ln" in name:
+                n_rows, with_ln = key[1], key[2]
+                per = (12 if with_ln else 10) if name.endswith("fwd") else (16 if with_ln else 6)
+                label, by = f"K6 {name} d={d} ln={int(with_ln)}", float(per) * n_rows * d
             else:
-                level = {128: 0, 256: 1}[d] if name.endswith("fwd") else {128: 0, 256: 1}[d]
-                by = merge_bytes(B, level, 4)   # residual stream is fp32 under autocast
-                out.append({"kernel": "K4 " + f"{name} d={d}", "bound": "hbm", "calls_per_step": cnt / steps,
-                            "avg_ms": avg, "alg_bytes": by, "achieved": by / (avg * 1e-3) / 1e9, "unit": "GB/s",
-                            "total_ms": ms})
+                n_rows = key[1]
+                label = ("K5 " if "ln" in name else "K7 ") + f"{name} cols={d}"
+                by = float(self.BYTES_PER_ELEM[name]) * n_rows * d
+            out.append({"kernel": label, "bound": "hbm", "calls_per_step": cnt / steps, "avg_ms": avg,
+                        "alg_bytes": by, "achieved": by / (avg * 1e-3) / 1e9, "unit": "GB/s", "total_ms": ms})
         return out
 
 
@@ -245,6 +269,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"       # the version banner goes to stdout and would precede the JSON line
     import torch
     import torch.distributed as dist
     from sl_hwgat_b200 import _lib, parallel

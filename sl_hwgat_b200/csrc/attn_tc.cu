@@ -23,7 +23,13 @@ namespace hwgat {
 typedef __nv_bfloat16 bf16;
 
 constexpr int kEpiWarps = 8;
-constexpr int kTcThreads = 32 * (2 + kEpiWarps);
+constexpr int kFirstEpiWarp = 4;  // warps 0-3: TMA producer, MMA issuer, two idle warps (one register-donor warpgroup)
+constexpr int kTcThreads = 32 * (kFirstEpiWarp + kEpiWarps);
+// Registers are allocated per SM sub-partition: with 3 warps on each, a thread gets at most 168.  The first warpgroup
+// needs ~40, so it hands its share to the attention warps (setmaxnreg): 4*32*40 + 8*32*232 = 64512 <= 65536.
+constexpr int kRegsDonor = 40, kRegsEpi = 232;
+HW_DEV void reg_dealloc_donor() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kRegsDonor)); }
+HW_DEV void reg_alloc_epi() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kRegsEpi)); }
 constexpr int kXChunk = kTileTok * 128;   // 16 KB: 128 rows x 64 bf16
 constexpr int kWStage = 192 * 128;        // 24 KB: q|k|v rows of one head x 64 bf16
 constexpr int kMaxChunks = 8;             // d <= 512
@@ -259,14 +265,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) tc_producer(p.geo, p.heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
-  } else if (warp == 1) {
-    if (lane == 0) tc_issuer(p.geo, p.heads, p.tiles, S, bars, sX, sW, tmem);
+  if (warp < kFirstEpiWarp) {
+    reg_dealloc_donor();
+    if (warp == 0 && lane == 0) tc_producer(p.geo, p.heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
+    if (warp == 1 && lane == 0) tc_issuer(p.geo, p.heads, p.tiles, S, bars, sX, sW, tmem);
   } else {
+    reg_alloc_epi();
     // ------------------------------------------------------------ attention warps
     const int win = warp & 3;             // TMEM lane quarter of this warp == window of the tile
-    const int qh = (warp - 2) >> 2;       // which 16 query rows of the window
+    const int qh = (warp - kFirstEpiWarp) >> 2;  // which 16 query rows of the window
     const int g = lane >> 2, t = lane & 3;
     const uint32_t lane_q = (uint32_t)(32 * win + 16 * qh) << 16;
     int it = 0;
@@ -531,13 +538,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
-  } else if (warp == 1) {
-    if (lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, tmem);
+  if (warp < kFirstEpiWarp) {
+    reg_dealloc_donor();
+    if (warp == 0 && lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
+    if (warp == 1 && lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, tmem);
   } else {
-    const int win = warp & 3;        // TMEM lane quarter == window
-    const int qh = (warp - 2) >> 2;  // my 16 query rows (pass 1) and my 16 key rows (pass 2)
+    reg_alloc_epi();
+    const int win = warp & 3;                    // TMEM lane quarter == window
+    const int qh = (warp - kFirstEpiWarp) >> 2;  // my 16 query rows (pass 1) and my 16 key rows (pass 2)
     const int g = lane >> 2, t = lane & 3;
     const int my_lanes = 32 * win + 16 * qh, other_lanes = 32 * win + 16 * (1 - qh);
     const size_t d3 = (size_t)3 * d;
@@ -552,6 +560,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
         const int buf = it & 1;
         // dO rows of this warp as A fragments, straight from global (independent of the MMA: issue first)
         uint32_t ga[4][4];
+        if (h + 1 < heads && lane < 16) {  // pull the next head's 16 x 128-byte dO rows into L2 ahead of time
+          const size_t r = (size_t)p.geo.token_row(tile, row0 + lane);
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.d_out + r * d + (h + 1) * kHd));
+        }
         {
           const bf16* g0 = p.d_out + tr0 * d + h * kHd + 2 * t;
           const bf16* g1 = p.d_out + tr1 * d + h * kHd + 2 * t;
@@ -610,9 +622,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
         // mailbox for the partner: my P / dS blocks of ITS key columns, and my dO fragments
         {
           uint32_t m[32];
-          const int on = 2 * (1 - qh);
-          m[0] = pb[0][on]; m[1] = pb[0][on + 1]; m[2] = pb[1][on]; m[3] = pb[1][on + 1];
-          m[4] = db[0][on]; m[5] = db[0][on + 1]; m[6] = db[1][on]; m[7] = db[1][on + 1];
+          // (selects, not pb[..][runtime index]: a dynamically indexed register array goes to local memory)
+          m[0] = qh ? pb[0][0] : pb[0][2]; m[1] = qh ? pb[0][1] : pb[0][3];
+          m[2] = qh ? pb[1][0] : pb[1][2]; m[3] = qh ? pb[1][1] : pb[1][3];
+          m[4] = qh ? db[0][0] : db[0][2]; m[5] = qh ? db[0][1] : db[0][3];
+          m[6] = qh ? db[1][0] : db[1][2]; m[7] = qh ? db[1][1] : db[1][3];
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
@@ -650,7 +664,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
         tmem_ld_16x256b_x8(tb + ((uint32_t)other_lanes << 16) + kMailCol, m);
         tmem_ld_wait();
         // ---------------- pass 2: my 16 key rows (same token rows as my query rows)
-        const int mn = 2 * qh;
+        // my P / dS blocks of MY key columns (key n tiles 2qh, 2qh+1), again by select
+        const uint32_t pm[4] = {qh ? pb[0][2] : pb[0][0], qh ? pb[0][3] : pb[0][1], qh ? pb[1][2] : pb[1][0],
+                                qh ? pb[1][3] : pb[1][1]};
+        const uint32_t dm[4] = {qh ? db[0][2] : db[0][0], qh ? db[0][3] : db[0][1], qh ? db[1][2] : db[1][0],
+                                qh ? db[1][3] : db[1][1]};
         {
           float dv[8][4];
 #pragma unroll
@@ -658,8 +676,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < 4; ++j) dv[i][j] = 0.f;
           // P^T fragments: own 16 queries, then the partner's 16 queries
-          const uint32_t a_own[4] = {movmatrix_trans(pb[0][mn]), movmatrix_trans(pb[0][mn + 1]),
-                                     movmatrix_trans(pb[1][mn]), movmatrix_trans(pb[1][mn + 1])};
+          const uint32_t a_own[4] = {movmatrix_trans(pm[0]), movmatrix_trans(pm[1]), movmatrix_trans(pm[2]),
+                                     movmatrix_trans(pm[3])};
           mma_16x64_k16_blocks(dv, a_own, ga);
           const uint32_t a_oth[4] = {movmatrix_trans(m[0]), movmatrix_trans(m[1]), movmatrix_trans(m[2]),
                                      movmatrix_trans(m[3])};
@@ -678,8 +696,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
           for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) dk[i][j] = 0.f;
-          const uint32_t a_own[4] = {movmatrix_trans(db[0][mn]), movmatrix_trans(db[0][mn + 1]),
-                                     movmatrix_trans(db[1][mn]), movmatrix_trans(db[1][mn + 1])};
+          const uint32_t a_own[4] = {movmatrix_trans(dm[0]), movmatrix_trans(dm[1]), movmatrix_trans(dm[2]),
+                                     movmatrix_trans(dm[3])};
           mma_16x64_k16_blocks(dk, a_own, qa);
           const uint32_t a_oth[4] = {movmatrix_trans(m[4]), movmatrix_trans(m[5]), movmatrix_trans(m[6]),
                                      movmatrix_trans(m[7])};
