@@ -55,6 +55,17 @@ HW_DEV void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// tcgen05.wait::ld with the destination registers of the outstanding load(s) as in/out operands: every use of
+// them is ordered after the wait, so loads can be issued early and waited for late.
+HW_DEV void tmem_wait_regs(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 HW_DEV uint32_t movmatrix_trans(uint32_t a) {
   uint32_t d;
   asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;\n" : "=r"(d) : "r"(a));
@@ -231,6 +242,12 @@ HW_DEV void tc_issuer(const TileGeom& geo, int heads, int tiles, int S, TcBars* 
   }
 }
 
+// (defined with the K3a helpers further down)
+HW_DEV void rows_to_blocks(const uint32_t (&r)[32], const float* __restrict__ bias2t, float mul, uint32_t (&f)[4][4]);
+HW_DEV void mma_rows_x_blocks_T(float (&acc)[4][4], const uint32_t (&a)[4][4], const uint32_t (&m0)[4][4],
+                                const uint32_t (&m1)[4][4]);
+HW_DEV void mma_16x64_k16_blocks(float (&acc)[8][4], const uint32_t (&a)[4], const uint32_t (&f)[4][4]);
+
 struct FwdTcArgs {
   const float* bias;
   const uint32_t* bits;
@@ -292,46 +309,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
         const float* bq = p.bias + h * kHd + 2 * t;
         const float* bk = bq + d;
         const float* bv = bk + d;
-        uint32_t r[32];
-        // ---- q: 16 rows x 64 -> A fragments (x head_dim^-0.5)
-        uint32_t qa[4][4];
-        tmem_ld_16x256b_x8(tb + lane_q, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            const int nt = 2 * ks + x;
-            const float2 bb = *reinterpret_cast<const float2*>(bq + 8 * nt);
-            qa[ks][2 * x] = pack_bf16((__uint_as_float(r[4 * nt]) + bb.x) * 0.125f,
-                                      (__uint_as_float(r[4 * nt + 1]) + bb.y) * 0.125f);
-            qa[ks][2 * x + 1] = pack_bf16((__uint_as_float(r[4 * nt + 2]) + bb.x) * 0.125f,
-                                          (__uint_as_float(r[4 * nt + 3]) + bb.y) * 0.125f);
-          }
-        // ---- S = q . k^T: k C-fragments are B fragments as they come
+        // TMEM reads in two groups, waited for late: {q, k} now, {v} under the softmax
+        uint32_t qa[4][4], kb0[4][4], kb1[4][4];
+        {
+          uint32_t r0[32], r1[32], r2[32];
+          tmem_ld_16x256b_x8(tb + lane_q, r0);
+          tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win) << 16) + 64, r1);
+          tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win + 16) << 16) + 64, r2);
+          tmem_wait_regs(r0); tmem_wait_regs(r1); tmem_wait_regs(r2);
+          rows_to_blocks(r0, bq, 0.125f, qa);   // q: A fragments (x head_dim^-0.5)
+          rows_to_blocks(r1, bk, 1.f, kb0);     // k: its C fragments are the B fragments of q.k^T as they come
+          rows_to_blocks(r2, bk, 1.f, kb1);
+        }
+        uint32_t v0[32], v1[32];
+        tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win) << 16) + 128, v0);
+        tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win + 16) << 16) + 128, v1);
         float s[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {  // keys 16*mt .. 16*mt+15
-          tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win + 16 * mt) << 16) + 64, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const float2 b0 = *reinterpret_cast<const float2*>(bk + 8 * (2 * ks));
-            const float2 b1 = *reinterpret_cast<const float2*>(bk + 8 * (2 * ks + 1));
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {  // keys 8*hh + g of this 16-group -> n tile 2*mt + hh
-              const uint32_t f0 = pack_bf16(__uint_as_float(r[4 * (2 * ks) + 2 * hh]) + b0.x,
-                                            __uint_as_float(r[4 * (2 * ks) + 2 * hh + 1]) + b0.y);
-              const uint32_t f1 = pack_bf16(__uint_as_float(r[4 * (2 * ks + 1) + 2 * hh]) + b1.x,
-                                            __uint_as_float(r[4 * (2 * ks + 1) + 2 * hh + 1]) + b1.y);
-              mma16816(s[2 * mt + hh], qa[ks], f0, f1);
-            }
-          }
-        }
+        mma_rows_x_blocks_T(s, qa, kb0, kb1);
         bool dead[2];
         masked_softmax_tc(s, mk, p.threshold, dead);
         uint32_t pa[2][4];
@@ -342,30 +340,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
           pa[kk][2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
           pa[kk][3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
         }
-        // ---- O = P . v: v C-fragments -> bf16 8x8 blocks -> movmatrix.trans -> B fragments
+        tmem_wait_regs(v0); tmem_wait_regs(v1);
+        // last TMEM read of this head: hand the accumulator back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+        // ---- O = P . v: v blocks -> movmatrix.trans -> B fragments
         float o[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {  // keys 16*mt .. : k step mt of P.v
-          tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win + 16 * mt) << 16) + 128, r);
-          tmem_ld_wait();
-          if (mt == 1) {  // last TMEM read of this head: hand the accumulator back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
-          }
-#pragma unroll
-          for (int nt = 0; nt < 8; ++nt) {
-            const float2 bb = *reinterpret_cast<const float2*>(bv + 8 * nt);
-            const uint32_t v0 = movmatrix_trans(pack_bf16(__uint_as_float(r[4 * nt]) + bb.x,
-                                                          __uint_as_float(r[4 * nt + 1]) + bb.y));
-            const uint32_t v1 = movmatrix_trans(pack_bf16(__uint_as_float(r[4 * nt + 2]) + bb.x,
-                                                          __uint_as_float(r[4 * nt + 3]) + bb.y));
-            mma16816(o[nt], pa[mt], v0, v1);
-          }
+        {
+          uint32_t vb[4][4];
+          rows_to_blocks(v0, bv, 1.f, vb);
+          mma_16x64_k16_blocks(o, pa[0], vb);
+          rows_to_blocks(v1, bv, 1.f, vb);
+          mma_16x64_k16_blocks(o, pa[1], vb);
         }
         // ---- store: (row g, row g+8) x 64 columns of this head
         bf16* o0 = p.out + orow0 + h * kHd + 2 * t;
@@ -456,6 +447,32 @@ HW_DEV void ld_rows_as_blocks(uint32_t taddr, const float* __restrict__ bias2t, 
       f[ks][2 * x] = pack_bf16((__uint_as_float(r[4 * nt]) + bb.x) * mul, (__uint_as_float(r[4 * nt + 1]) + bb.y) * mul);
       f[ks][2 * x + 1] =
           pack_bf16((__uint_as_float(r[4 * nt + 2]) + bb.x) * mul, (__uint_as_float(r[4 * nt + 3]) + bb.y) * mul);
+    }
+}
+
+// raw 16 x 64 accumulator rows (tcgen05.ld.16x256b.x8 registers) -> (+bias) * mul -> 8x8-block registers
+HW_DEV void rows_to_blocks(const uint32_t (&r)[32], const float* __restrict__ bias2t, float mul, uint32_t (&f)[4][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      const int nt = 2 * ks + x;
+      const float2 bb = *reinterpret_cast<const float2*>(bias2t + 8 * nt);
+      f[ks][2 * x] = pack_bf16((__uint_as_float(r[4 * nt]) + bb.x) * mul, (__uint_as_float(r[4 * nt + 1]) + bb.y) * mul);
+      f[ks][2 * x + 1] =
+          pack_bf16((__uint_as_float(r[4 * nt + 2]) + bb.x) * mul, (__uint_as_float(r[4 * nt + 3]) + bb.y) * mul);
+    }
+}
+// acc[16 x 32] += A[16 x 64] . M^T, M (32 rows x 64) given as the block registers of its two 16-row groups:
+// the blocks are the B fragments as they are (the q.k^T / dO.v^T pattern)
+HW_DEV void mma_rows_x_blocks_T(float (&acc)[4][4], const uint32_t (&a)[4][4], const uint32_t (&m0)[4][4],
+                                const uint32_t (&m1)[4][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      mma16816(acc[hh], a[ks], m0[ks][hh], m0[ks][2 + hh]);
+      mma16816(acc[2 + hh], a[ks], m1[ks][hh], m1[ks][2 + hh]);
     }
 }
 
@@ -582,22 +599,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
         const float* bk = bq + d;
         const float* bv = bk + d;
         // ---------------- pass 1: my 16 query rows
-        uint32_t qa[4][4];
-        ld_rows_as_blocks(tb + ((uint32_t)my_lanes << 16), bq, 0.125f, qa);
+        // TMEM reads are issued in two groups and waited for late: {q, k} now, {v, partner q} under the softmax
+        uint32_t qa[4][4], kb0[4][4], kb1[4][4];
+        {
+          uint32_t r0[32], r1[32], r2[32];
+          tmem_ld_16x256b_x8(tb + ((uint32_t)my_lanes << 16), r0);
+          tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win) << 16) + 64, r1);
+          tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win + 16) << 16) + 64, r2);
+          tmem_wait_regs(r0); tmem_wait_regs(r1); tmem_wait_regs(r2);
+          rows_to_blocks(r0, bq, 0.125f, qa);
+          rows_to_blocks(r1, bk, 1.f, kb0);
+          rows_to_blocks(r2, bk, 1.f, kb1);
+        }
+        uint32_t v0[32], v1[32], q2[32];
+        tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win) << 16) + 128, v0);
+        tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win + 16) << 16) + 128, v1);
+        tmem_ld_16x256b_x8(tb + ((uint32_t)other_lanes << 16), q2);
         float pr[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) pr[i][j] = 0.f;
-        mma_rows_x_tmem_T(pr, qa, tb, 32 * win, 64, bk);      // S = q k^T
+        mma_rows_x_blocks_T(pr, qa, kb0, kb1);                  // S = q k^T
         bool dead[2];
         masked_softmax_tc(pr, mk, p.threshold, dead);  // P (exactly 0 wherever the logit is not live)
+        tmem_wait_regs(v0); tmem_wait_regs(v1); tmem_wait_regs(q2);
+        // last read of the accumulator: hand it back to the MMA warp (the mailbox columns are not part of it)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
         float ds[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) ds[i][j] = 0.f;
-        mma_rows_x_tmem_T(ds, ga, tb, 32 * win, 128, bv);     // dP = dO v^T
+        {
+          uint32_t vb0[4][4], vb1[4][4];
+          rows_to_blocks(v0, bv, 1.f, vb0);
+          rows_to_blocks(v1, bv, 1.f, vb1);
+          mma_rows_x_blocks_T(ds, ga, vb0, vb1);                // dP = dO v^T
+        }
+        uint32_t qo[4][4];
+        rows_to_blocks(q2, bq, 0.125f, qo);                     // the partner's q rows (B operand of dk)
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           float delta = 0.f;
@@ -635,29 +678,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
           for (int i = 24; i < 32; ++i) m[i] = 0u;
           tmem_st_16x256b_x8(tb + ((uint32_t)my_lanes << 16) + kMailCol, m);
         }
-        // dq = dS k * scale : A = dS fragments, B = movmatrix.trans of the k blocks
+        // dq = dS k * scale : A = dS fragments, B = movmatrix.trans of the k blocks kept from the logits
         {
           float dq[8][4];
 #pragma unroll
           for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {  // keys 16mt.. = k step mt
-            uint32_t kb[4][4];
-            ld_rows_as_blocks(tb + ((uint32_t)(32 * win + 16 * mt) << 16) + 64, bk, 1.f, kb);
-            const uint32_t a[4] = {db[0][2 * mt], db[1][2 * mt], db[0][2 * mt + 1], db[1][2 * mt + 1]};
-            mma_16x64_k16_blocks(dq, a, kb);
-          }
+          const uint32_t a0[4] = {db[0][0], db[1][0], db[0][1], db[1][1]};
+          mma_16x64_k16_blocks(dq, a0, kb0);
+          const uint32_t a1[4] = {db[0][2], db[1][2], db[0][3], db[1][3]};
+          mma_16x64_k16_blocks(dq, a1, kb1);
           store_rows_16x64(dq, 0.125f, p.dqkv + tr0 * d3 + h * kHd + 2 * t, p.dqkv + tr1 * d3 + h * kHd + 2 * t);
         }
-        // the partner's q rows (B operand of dk) : last read of the accumulator
-        uint32_t qo[4][4];
-        ld_rows_as_blocks(tb + ((uint32_t)other_lanes << 16), bq, 0.125f, qo);
         tmem_st_wait();
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
         pair_barrier(1 + win);
         tc_fence_after();
         uint32_t m[32];
