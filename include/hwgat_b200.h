@@ -158,6 +158,22 @@ int hwgat_bias_gelu_dropout_bwd(const void* u0, const float* bias, const void* d
                                 long long n, int cols, float p, unsigned long long seed, unsigned long long offset,
                                 hwgat_stream_t stream);
 
+/* ---- model head and tail ----------------------------------------------- */
+
+/* K8: out(fp32, (n, E)) = dropout_p([sin(2 pi x.Bm^T), cos(2 pi x.Bm^T)] + pe[frame]); x: (n, C) fp32 keypoints,
+ * Bm: (E/2, C) the frozen Fourier matrix `B`, pe: (T, E) the sinusoid table, frame of token i = (i / K) % T.
+ * Replaces Model.forward_features' embedding and PositionalEncoding.forward (HWGATE.py:343-347, 25-28).
+ * Forward only (nothing upstream is trainable).  E % 8 == 0.                                              */
+int hwgat_embed_fwd(const float* x, const float* Bm, const float* pe, float* out, long long n, int C, int E, int K,
+                    int T, float p, unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
+/* K9: pooled(fp32, (B, d)) = mean over the `tokens` rows of each sample of LayerNorm(x; gamma, beta, eps);
+ * mean / rstd (B*tokens) saved.  Replaces self.norm + self.avgpool (HWGATE.py:353-354).  d in {128,256,512}. */
+int hwgat_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean,
+                      float* rstd, int B, int tokens, int d, float eps, hwgat_stream_t stream);
+/* K9': dx(fp32) of the above for g = d pooled (B, d); dgamma (d) overwritten (dbeta = column sums of g: caller). */
+int hwgat_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      float* dx, float* dgamma, int B, int tokens, int d, hwgat_stream_t stream);
+
 /* Diagnostic: the plain bf16 GEMM K3 uses for d_xn, C[M,N] = A[M,K] . Bt[N,K]^T (fp32 accumulate,
  * TMA + tcgen05).  M % 128 == 0, N % 128 == 0, K % 64 == 0; all row-major bf16 device pointers. */
 int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream);

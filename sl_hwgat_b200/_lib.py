@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libhwgat_b200.so")
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # name -> (restype, argtypes); must list every symbol of include/hwgat_b200.h
 SIGNATURES = {
@@ -38,6 +38,10 @@ SIGNATURES = {
                                                              c_void_p]),
     "hwgat_bias_gelu_dropout_bwd": (c_int, [c_void_p] * 5 + [c_longlong, c_int, c_float, c_ulonglong, c_ulonglong,
                                                              c_void_p]),
+    "hwgat_embed_fwd": (c_int, [c_void_p] * 4 + [c_longlong, c_int, c_int, c_int, c_int, c_float, c_ulonglong,
+                                                 c_ulonglong, c_void_p]),
+    "hwgat_ln_pool_fwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_float, c_void_p]),
+    "hwgat_ln_pool_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p]),
     "hwgat_debug_gemm_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hwgat_debug_gemm_tn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
     "hwgat_merge_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),

@@ -26,7 +26,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 4; }
+int hwgat_version(void) { return 5; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -204,6 +204,36 @@ int hwgat_bias_gelu_dropout_bwd(const void* u0, const float* bias, const void* d
   if (misaligned(u0) || misaligned(dg) || misaligned(du0)) return HWGAT_ERR_ALIGN;
   return launch_bias_gelu_dropout((const __nv_bfloat16*)u0, bias, (const __nv_bfloat16*)dg, (__nv_bfloat16*)du0, dbias,
                                   n, cols, p, seed, offset, true, (cudaStream_t)stream);
+}
+
+int hwgat_embed_fwd(const float* x, const float* Bm, const float* pe, float* out, long long n, int C, int E, int K,
+                    int T, float p, unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  if (n < 0 || C <= 0 || E <= 0 || K <= 0 || T <= 0 || bad_p(p)) return HWGAT_ERR_SHAPE;
+  if (E % 8) return HWGAT_ERR_UNSUPPORTED;
+  if (n == 0) return HWGAT_OK;
+  if (!x || !Bm || !pe || !out) return HWGAT_ERR_NULL;
+  if (misaligned(pe) || misaligned(out)) return HWGAT_ERR_ALIGN;
+  return launch_embed_fwd(x, Bm, pe, out, n, C, E, K, T, p, seed, offset, (cudaStream_t)stream);
+}
+
+int hwgat_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean,
+                      float* rstd, int B, int tokens, int d, float eps, hwgat_stream_t stream) {
+  if (B < 0 || tokens <= 0) return HWGAT_ERR_SHAPE;
+  if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
+  if (B == 0) return HWGAT_OK;
+  if (!x || !gamma || !beta || !pooled || !mean || !rstd) return HWGAT_ERR_NULL;
+  if (misaligned(x) || misaligned(gamma)) return HWGAT_ERR_ALIGN;
+  return launch_ln_pool_fwd(x, gamma, beta, pooled, mean, rstd, B, tokens, d, eps, (cudaStream_t)stream);
+}
+
+int hwgat_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      float* dx, float* dgamma, int B, int tokens, int d, hwgat_stream_t stream) {
+  if (B < 0 || tokens <= 0) return HWGAT_ERR_SHAPE;
+  if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
+  if (!dgamma) return HWGAT_ERR_NULL;
+  if (B > 0 && (!g || !x || !mean || !rstd || !gamma || !dx)) return HWGAT_ERR_NULL;
+  if (misaligned(g) || misaligned(x) || misaligned(gamma) || misaligned(dx)) return HWGAT_ERR_ALIGN;
+  return launch_ln_pool_bwd(g, x, mean, rstd, gamma, dx, dgamma, B, tokens, d, (cudaStream_t)stream);
 }
 
 int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream) {

@@ -557,3 +557,204 @@ int launch_bias_gelu_dropout(const bf16* u0, const float* bias, const bf16* dg, 
 }
 
 }  // namespace hwgat
+
+// ===========================================================================
+// Model head and tail, bf16 / autocast path
+// ===========================================================================
+namespace hwgat {
+
+// K8: h(fp32) = dropout([sin(2 pi x.B^T), cos(2 pi x.B^T)] + pe[frame])   (HWGATE.py:343-347, 25-28)
+// x: (n, C) keypoint coordinates, Bm: (E/2, C) frozen Fourier matrix, pe: (T, E), token i belongs to frame
+// (i / K) % T.  Forward only: nothing upstream of the embedding is trainable.  One thread = 4 Fourier
+// features of one token (sincosf shares the range reduction; the argument reaches ~300 rad, so the
+// accurate sincosf, not the MUFU approximation).
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Bm,
+                                                        const float* __restrict__ pe, float* __restrict__ out,
+                                                        long long n, int C, int E, int K, int T, float scale,
+                                                        uint32_t thresh, unsigned long long seed,
+                                                        unsigned long long offset) {
+  const int half = E / 2, groups = half / 4;
+  const long long total = n * groups, stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const long long tok = idx / groups;
+    const int j0 = (int)(idx - tok * groups) * 4;
+    const int frame = (int)((tok / K) % T);
+    float arg[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+      const float xc = 6.283185307179586f * x[tok * C + c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) arg[i] = fmaf(xc, Bm[(j0 + i) * C + c], arg[i]);
+    }
+    float sn[4], cs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sincosf(arg[i], &sn[i], &cs[i]);
+    const float4 p0 = *reinterpret_cast<const float4*>(pe + (long long)frame * E + j0);
+    const float4 p1 = *reinterpret_cast<const float4*>(pe + (long long)frame * E + half + j0);
+    const long long e0 = tok * E + j0, e1 = e0 + half;
+    const uint32_t k0 = thresh ? keep4((unsigned long long)e0 >> 2, offset, seed, thresh) : 0xFu;
+    const uint32_t k1 = thresh ? keep4((unsigned long long)e1 >> 2, offset, seed, thresh) : 0xFu;
+    float4 o0 = make_float4(sn[0] + p0.x, sn[1] + p0.y, sn[2] + p0.z, sn[3] + p0.w);
+    float4 o1 = make_float4(cs[0] + p1.x, cs[1] + p1.y, cs[2] + p1.z, cs[3] + p1.w);
+    o0.x = (k0 & 1u) ? o0.x * scale : 0.f; o0.y = (k0 & 2u) ? o0.y * scale : 0.f;
+    o0.z = (k0 & 4u) ? o0.z * scale : 0.f; o0.w = (k0 & 8u) ? o0.w * scale : 0.f;
+    o1.x = (k1 & 1u) ? o1.x * scale : 0.f; o1.y = (k1 & 2u) ? o1.y * scale : 0.f;
+    o1.z = (k1 & 4u) ? o1.z * scale : 0.f; o1.w = (k1 & 8u) ? o1.w * scale : 0.f;
+    *reinterpret_cast<float4*>(out + e0) = o0;
+    *reinterpret_cast<float4*>(out + e1) = o1;
+  }
+}
+
+int launch_embed_fwd(const float* x, const float* Bm, const float* pe, float* out, long long n, int C, int E, int K,
+                     int T, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s) {
+  const uint32_t thresh = drop_threshold16(p);
+  const float scale = thresh ? 65536.f / (65536.f - (float)thresh) : 1.f;
+  const int grid = ew_grid(n * (E / 8));
+  embed_fwd_kernel<<<grid, 256, 0, s>>>(x, Bm, pe, out, n, C, E, K, T, scale, thresh, seed, offset);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// K9: pooled[b, :] = mean over the tokens of sample b of LayerNorm(x[b, token, :])      (HWGATE.py:353-354)
+// One CTA per (sample, token slice); warp per row as K5; per-lane partial sums -> smem -> atomics into the
+// zeroed (B, d) output.  mean / rstd are saved for the backward.
+template <int kV>
+__global__ void __launch_bounds__(256) ln_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ pooled,
+                                                          float* __restrict__ mean, float* __restrict__ rstd,
+                                                          int tokens, int slices, float eps) {
+  constexpr int d = kV * 128;
+  __shared__ float red[8][d];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int b = blockIdx.x / slices, sl = blockIdx.x - b * slices;
+  float4 gm[kV], acc[kV];
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    gm[i] = *reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4);
+    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int tk = sl * 8 + wib; tk < tokens; tk += slices * 8) {
+    const long long row = (long long)b * tokens + tk;
+    float4 v[kV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      v[i] = *reinterpret_cast<const float4*>(x + row * d + i * 128 + lane * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mu = warp_sum(s) * (1.f / d);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      v[i].x -= mu; v[i].y -= mu; v[i].z -= mu; v[i].w -= mu;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rs = rsqrtf(warp_sum(q) * (1.f / d) + eps);
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {  // sum of xhat; gamma / beta / 1/tokens are applied once at the end
+      acc[i].x += v[i].x * rs; acc[i].y += v[i].y * rs; acc[i].z += v[i].z * rs; acc[i].w += v[i].w * rs;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kV; ++i) *reinterpret_cast<float4*>(&red[wib][i * 128 + lane * 4]) = acc[i];
+  __syncthreads();
+  const float inv = 1.f / tokens;
+  for (int c = threadIdx.x; c < d; c += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[w][c];
+    float val = a * inv * gamma[c];
+    if (sl == 0) val += beta[c];
+    atomicAdd(pooled + (long long)b * d + c, val);
+  }
+}
+
+// K9': dx[b, t, :] = LayerNorm'(g[b, :] / tokens) per row;  dgamma += sum_rows (g/tokens) * xhat ; dbeta = sum_b g
+template <int kV>
+__global__ void __launch_bounds__(256) ln_pool_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          const float* __restrict__ gamma, float* __restrict__ dx,
+                                                          float* __restrict__ dgamma, int tokens, int slices) {
+  constexpr int d = kV * 128;
+  __shared__ float red[8][d];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int b = blockIdx.x / slices, sl = blockIdx.x - b * slices;
+  const float inv = 1.f / tokens;
+  float4 gy[kV], gg[kV], dg[kV];
+  float s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    const float4 gv = *reinterpret_cast<const float4*>(g + (long long)b * d + i * 128 + lane * 4);
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4);
+    gy[i] = make_float4(gv.x * inv, gv.y * inv, gv.z * inv, gv.w * inv);
+    gg[i] = make_float4(gy[i].x * gm.x, gy[i].y * gm.y, gy[i].z * gm.z, gy[i].w * gm.w);
+    s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float m1 = warp_sum(s1) * (1.f / d);  // the same for every token of the sample
+  for (int tk = sl * 8 + wib; tk < tokens; tk += slices * 8) {
+    const long long row = (long long)b * tokens + tk;
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[kV];
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + row * d + i * 128 + lane * 4);
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      s2 += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
+      dg[i].x += gy[i].x * xh[i].x; dg[i].y += gy[i].y * xh[i].y; dg[i].z += gy[i].z * xh[i].z; dg[i].w += gy[i].w * xh[i].w;
+    }
+    const float m2 = warp_sum(s2) * (1.f / d);
+#pragma unroll
+    for (int i = 0; i < kV; ++i)
+      *reinterpret_cast<float4*>(dx + row * d + i * 128 + lane * 4) =
+          make_float4(rs * (gg[i].x - m1 - xh[i].x * m2), rs * (gg[i].y - m1 - xh[i].y * m2),
+                      rs * (gg[i].z - m1 - xh[i].z * m2), rs * (gg[i].w - m1 - xh[i].w * m2));
+  }
+#pragma unroll
+  for (int i = 0; i < kV; ++i) *reinterpret_cast<float4*>(&red[wib][i * 128 + lane * 4]) = dg[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[w][c];
+    atomicAdd(dgamma + c, a);
+  }
+}
+
+static int pool_slices(int B, int tokens) {
+  int s = (148 * 4 + B - 1) / B;
+  const int maxs = (tokens + 7) / 8;
+  if (s > maxs) s = maxs;
+  return s < 1 ? 1 : s;
+}
+
+int launch_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean, float* rstd,
+                       int B, int tokens, int d, float eps, cudaStream_t s) {
+  cudaMemsetAsync(pooled, 0, sizeof(float) * (size_t)B * d, s);
+  const int slices = pool_slices(B, tokens);
+  switch (d) {
+    case 128: ln_pool_fwd_kernel<1><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, tokens, slices, eps); break;
+    case 256: ln_pool_fwd_kernel<2><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, tokens, slices, eps); break;
+    case 512: ln_pool_fwd_kernel<4><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, tokens, slices, eps); break;
+    default: return HWGAT_ERR_UNSUPPORTED;
+  }
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int launch_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s) {
+  cudaMemsetAsync(dgamma, 0, sizeof(float) * d, s);
+  const int slices = pool_slices(B, tokens);
+  switch (d) {
+    case 128: ln_pool_bwd_kernel<1><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices); break;
+    case 256: ln_pool_bwd_kernel<2><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices); break;
+    case 512: ln_pool_bwd_kernel<4><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices); break;
+    default: return HWGAT_ERR_UNSUPPORTED;
+  }
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace hwgat

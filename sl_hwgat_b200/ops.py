@@ -375,3 +375,71 @@ class _BiasGeluDropout(torch.autograd.Function):
 def bias_gelu_dropout(u0: torch.Tensor, bias: Optional[torch.Tensor], p: float, training: bool) -> torch.Tensor:
     """dropout(gelu(u0 + bias)), exact erf GELU: fc1 bias + ff.act + ff.drop (HWGATE.py:131-133)."""
     return _BiasGeluDropout.apply(u0, bias, p if training else 0.0)
+
+
+# --------------------------------------------------------------------------
+# K8 / K9: model head and tail
+# --------------------------------------------------------------------------
+
+def fourier_embed(x: torch.Tensor, fourier_b: torch.Tensor, pe: torch.Tensor, p: float, training: bool) -> torch.Tensor:
+    """dropout([sin(2 pi x.B^T), cos(2 pi x.B^T)] + pe[frame]) as fp32 (B, T, K, E): the Fourier keypoint embedding
+    and PositionalEncoding.forward (HWGATE.py:343-347, 25-28) in one pass.  Forward only: `B` is frozen and `pe` is
+    a buffer, so no gradient flows upstream."""
+    lib = _lib.load()
+    _need_cuda(x, fourier_b, pe)
+    if fourier_b.requires_grad or x.requires_grad:
+        raise _lib.HwgatError("fourier_embed is forward-only; the reference's B matrix is frozen (HWGATE.py:299)")
+    Bsz, T, K, C = x.shape
+    E = 2 * fourier_b.shape[0]
+    x_c = x.detach().float().contiguous()
+    b_c = fourier_b.detach().float().contiguous()
+    pe_c = pe.detach().float().reshape(-1, E)[:T].contiguous()
+    out = torch.empty((Bsz, T, K, E), dtype=torch.float32, device=x.device)
+    pp = float(p) if training else 0.0
+    seed, off = _philox_stream(x.device) if pp > 0 else (0, 0)
+    with torch.cuda.device(x.device):
+        check(lib.hwgat_embed_fwd(x_c.data_ptr(), b_c.data_ptr(), pe_c.data_ptr(), out.data_ptr(), Bsz * T * K, C, E, K,
+                                  T, pp, seed, off, _stream()), "hwgat_embed_fwd")
+    return out
+
+
+class _LayerNormPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        lib = _lib.load()
+        _need_cuda(x, gamma, beta)
+        if x.dtype != torch.float32:
+            raise _lib.HwgatError("layer_norm_mean_pool takes the fp32 residual stream")
+        x_c = x.contiguous()
+        Bsz, d = x_c.shape[0], x_c.shape[-1]
+        tokens = x_c.numel() // (Bsz * d) if Bsz else 1
+        g_c, b_c = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        pooled = torch.empty((Bsz, d), dtype=torch.float32, device=x_c.device)
+        mean = torch.empty(Bsz * tokens, dtype=torch.float32, device=x_c.device)
+        rstd = torch.empty(Bsz * tokens, dtype=torch.float32, device=x_c.device)
+        with torch.cuda.device(x_c.device):
+            check(lib.hwgat_ln_pool_fwd(x_c.data_ptr(), g_c.data_ptr(), b_c.data_ptr(), pooled.data_ptr(),
+                                        mean.data_ptr(), rstd.data_ptr(), Bsz, tokens, d, float(eps), _stream()),
+                  "hwgat_ln_pool_fwd")
+        ctx.save_for_backward(x_c, g_c, mean, rstd)
+        ctx.meta = (Bsz, tokens, d, gamma.dtype, beta.dtype)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x_c, g_c, mean, rstd = ctx.saved_tensors
+        Bsz, tokens, d, gdt, bdt = ctx.meta
+        gg = g.float().contiguous()
+        dx = torch.empty_like(x_c)
+        dgamma = torch.empty(d, dtype=torch.float32, device=x_c.device)
+        with torch.cuda.device(x_c.device):
+            check(lib.hwgat_ln_pool_bwd(gg.data_ptr(), x_c.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g_c.data_ptr(),
+                                        dx.data_ptr(), dgamma.data_ptr(), Bsz, tokens, d, _stream()),
+                  "hwgat_ln_pool_bwd")
+        return dx, dgamma.to(gdt), gg.sum(0).to(bdt), None
+
+
+def layer_norm_mean_pool(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """(B, ..., d) -> (B, d): mean over all tokens of LayerNorm(x): self.norm + self.avgpool (HWGATE.py:353-354)."""
+    return _LayerNormPool.apply(x, gamma, beta, eps)

@@ -434,3 +434,43 @@ def test_dropout_streams_differ_between_calls_and_repeat_with_seed():
     m3 = ops.bias_dropout_add_ln(res, a, None, None, 0.5, True)[0] != 0
     assert not torch.equal(m1, m2) and torch.equal(m1, m3)
     assert abs((m1 & m2).float().mean().item() - 0.25) < 0.02    # independent masks
+
+
+# ------------------------------------------------------------------ K8 / K9: head and tail
+@pytest.mark.parametrize("C", [2, 3])
+def test_fourier_embed(C):
+    from sl_hwgat_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    B, T, K, E = 3, 8, 64, 128
+    x = torch.rand(B, T, K, C, generator=g).cuda()
+    Bm = (torch.randn(E // 2, C, generator=g) * 10).cuda()
+    pe = O.sinusoid_table(T, E).cuda()
+    out = ops.fourier_embed(x, Bm, pe, 0.1, False)
+    proj = (2 * np.pi * x.double()) @ Bm.double().t()
+    ref = torch.cat([torch.sin(proj), torch.cos(proj)], -1) + pe.double()
+    # the argument reaches ~300 rad: fp32 rounding of it alone is ~2e-5 absolute
+    assert (out.double() - ref).abs().max().item() < 2e-4
+    # dropout: rate and scale, positional table added before the mask
+    torch.manual_seed(1)
+    outd = ops.fourier_embed(x, Bm, pe, 0.25, True)
+    kept = outd != 0
+    assert abs(1 - kept.float().mean().item() - 0.25) < 2e-2
+    assert torch.allclose(outd[kept], out[kept] / 0.75, rtol=2e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("d,tokens,B", [(512, 1024, 3), (128, 64, 5), (256, 7, 2)])
+def test_layer_norm_mean_pool(d, tokens, B):
+    from sl_hwgat_b200 import ops
+    g = torch.Generator().manual_seed(d + tokens)
+    x = (torch.randn(B, tokens // 1, d, generator=g) * 2 + 0.3).cuda().requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(d, generator=g)).cuda().requires_grad_(True)
+    beta = (0.1 * torch.randn(d, generator=g)).cuda().requires_grad_(True)
+    y = ops.layer_norm_mean_pool(x, gamma, beta, 1e-5)
+    gy = torch.randn(B, d, generator=g).cuda()
+    y.backward(gy)
+    x64, g64, b64 = (t.detach().double().requires_grad_(True) for t in (x, gamma, beta))
+    y64 = torch.nn.functional.layer_norm(x64, (d,), g64, b64, 1e-5).mean(1)
+    y64.backward(gy.double())
+    assert rel_inf(y, y64) < 1e-5
+    assert rel_inf(x.grad, x64.grad) < 1e-5
+    assert rel_inf(gamma.grad, g64.grad) < 1e-4 and rel_inf(beta.grad, b64.grad) < 1e-5
