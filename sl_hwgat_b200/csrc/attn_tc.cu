@@ -16,6 +16,8 @@
 //               in registers: Q, K, V, S and P never touch shared memory.
 //               S = q k^T, threshold drop, packed graph/shift mask, -10000 fill,
 //               softmax, O = P v  (HWGATE.py:89-114), O written in token order.
+#include <cstdlib>
+
 #include "tc.cuh"
 
 namespace hwgat {
@@ -374,6 +376,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+__global__ void attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                                    const FwdTcArgs p);
+
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   const int d = a.d, nk = d / 64;
   const int stages = d == 512 ? 4 : (d == 256 ? 6 : 6);
@@ -396,7 +401,17 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages;
   p.geo = make_geom(a.F, a.K, d, a.shift, a.layout);
   const int grid = p.tiles < 148 ? p.tiles : 148;
-  attn_fwd_tc_kernel<<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
+  static const bool pair_warps = getenv("HWGAT_PAIR_WARPS") != nullptr;  // A/B switch: first-generation attention warps
+  if (pair_warps || (a.heads & 1)) {
+    attn_fwd_tc_kernel<<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
+  } else {
+    static int attr2 = 0;
+    if (smem_bytes > attr2) {
+      cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+      attr2 = smem_bytes;
+    }
+    attn_fwd_tc2_kernel<<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
+  }
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -739,6 +754,148 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
           mma_16x64_k16_blocks(dk, a_oth, qo);
           store_rows_16x64(dk, 1.f, p.dqkv + tr0 * d3 + d + h * kHd + 2 * t, p.dqkv + tr1 * d3 + d + h * kHd + 2 * t);
         }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ===========================================================================
+// Second-generation attention warps: ONE warp per window (all 32 query rows), the two warp sets
+// (warps 4-7, 8-11) work on alternate heads, one TMEM accumulator each.  Compared with the pair
+// design above this converts every q / k / v row from TMEM exactly once per window (instead of
+// k and v once per warp of the pair), re-uses each transposed B fragment for both 16-row m tiles,
+// and needs no exchange between warps.
+// ===========================================================================
+// acc[m][16 x 64] += A[m][16 x 16] . Bm[16 x 64] for both m tiles, Bm as block registers (transposed once)
+HW_DEV void mma_2x16x64_k16_blocks(float (&acc0)[8][4], float (&acc1)[8][4], const uint32_t (&a0)[4],
+                                   const uint32_t (&a1)[4], const uint32_t (&f)[4][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const uint32_t b0 = movmatrix_trans(f[nt >> 1][(nt & 1) * 2]);
+    const uint32_t b1 = movmatrix_trans(f[nt >> 1][(nt & 1) * 2 + 1]);
+    mma16816(acc0[nt], a0, b0, b1);
+    mma16816(acc1[nt], a1, b0, b1);
+  }
+}
+HW_DEV void zero8x4(float (&c)[8][4]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+}
+HW_DEV void zero4x4(float (&c)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+}
+HW_DEV void probs_to_afrag(uint32_t (&pa)[2][4], const float (&s)[4][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    pa[kk][0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+    pa[kk][1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+    pa[kk][2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[kk][3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                     const __grid_constant__ CUtensorMap tmW,
+                                                                     const FwdTcArgs p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int d = p.geo.d, nk = d / 64, heads = p.heads, S = p.w_stages;
+  unsigned char* sX = smem;
+  unsigned char* sW = smem + nk * kXChunk;
+  TcBars* bars = reinterpret_cast<TcBars*>(sW + S * kWStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxChunks; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], 1); }
+    for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp < kFirstEpiWarp) {
+    reg_dealloc_donor();
+    if (warp == 0 && lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
+    if (warp == 1 && lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, tmem);
+  } else {
+    reg_alloc_epi();
+    const int win = warp & 3;                      // TMEM lane quarter == window of the tile
+    const int set = (warp - kFirstEpiWarp) >> 2;   // this warp takes the heads whose accumulator is buffer `set`
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t tb = tmem + set * kAccStride + ((uint32_t)(32 * win) << 16);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      size_t orow[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) orow[r] = (size_t)p.geo.token_row(tile, 32 * win + 8 * r + g) * d;
+      const uint32_t* mw = p.bits + p.geo.mask_base(tile) + 32 * win;
+      float mk0[2][8], mk1[2][8];
+      build_row_masks(mw[g], mw[g + 8], t, mk0);
+      build_row_masks(mw[g + 16], mw[g + 24], t, mk1);
+      for (int h = 0; h < heads; ++h, ++it) {
+        if ((it & 1) != set) continue;
+        mbar_wait(&bars->acc_full[set], (it >> 1) & 1);
+        tc_fence_after();
+        const float* bq = p.bias + h * kHd + 2 * t;
+        const float* bk = bq + d;
+        const float* bv = bk + d;
+        uint32_t qa0[4][4], qa1[4][4], kb0[4][4], kb1[4][4];
+        {
+          uint32_t r0[32], r1[32], r2[32], r3[32];
+          tmem_ld_16x256b_x8(tb, r0);
+          tmem_ld_16x256b_x8(tb + (16u << 16), r1);
+          tmem_ld_16x256b_x8(tb + 64, r2);
+          tmem_ld_16x256b_x8(tb + (16u << 16) + 64, r3);
+          tmem_wait_regs(r0); tmem_wait_regs(r1); tmem_wait_regs(r2); tmem_wait_regs(r3);
+          rows_to_blocks(r0, bq, 0.125f, qa0);
+          rows_to_blocks(r1, bq, 0.125f, qa1);
+          rows_to_blocks(r2, bk, 1.f, kb0);
+          rows_to_blocks(r3, bk, 1.f, kb1);
+        }
+        uint32_t v0[32], v1[32];
+        tmem_ld_16x256b_x8(tb + 128, v0);
+        tmem_ld_16x256b_x8(tb + (16u << 16) + 128, v1);
+        float s0[4][4], s1[4][4];
+        zero4x4(s0);
+        zero4x4(s1);
+        mma_rows_x_blocks_T(s0, qa0, kb0, kb1);
+        mma_rows_x_blocks_T(s1, qa1, kb0, kb1);
+        bool dead[2];
+        masked_softmax_tc(s0, mk0, p.threshold, dead);
+        masked_softmax_tc(s1, mk1, p.threshold, dead);
+        uint32_t pa0[2][4], pa1[2][4];
+        probs_to_afrag(pa0, s0);
+        probs_to_afrag(pa1, s1);
+        tmem_wait_regs(v0); tmem_wait_regs(v1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[set]);  // last TMEM read of this head
+        float o0[8][4], o1[8][4];
+        zero8x4(o0);
+        zero8x4(o1);
+        {
+          uint32_t vb[4][4];
+          rows_to_blocks(v0, bv, 1.f, vb);
+          mma_2x16x64_k16_blocks(o0, o1, pa0[0], pa1[0], vb);
+          rows_to_blocks(v1, bv, 1.f, vb);
+          mma_2x16x64_k16_blocks(o0, o1, pa0[1], pa1[1], vb);
+        }
+        store_rows_16x64(o0, 1.f, p.out + orow[0] + h * kHd + 2 * t, p.out + orow[1] + h * kHd + 2 * t);
+        store_rows_16x64(o1, 1.f, p.out + orow[2] + h * kHd + 2 * t, p.out + orow[3] + h * kHd + 2 * t);
       }
     }
   }
