@@ -25,7 +25,7 @@
  *    HWGAT_BF16 = activations and weights bfloat16, biases / reductions /
  *    weight gradients float32 (the timed mode);
  *  - supported geometry: temporal_patch TP = 2, window W = 16 (N = 32 tokens per
- *    window), head_dim 64, d = heads*64 <= 512, F even, K a multiple of 64.
+ *    window), head_dim 64, d = heads*64 <= 512 (bf16: d a multiple of 128), F even, K a multiple of 64.
  *    Anything else returns HWGAT_ERR_UNSUPPORTED - there is no fallback path.
  */
 #ifndef HWGAT_B200_H

@@ -14,6 +14,7 @@ static int check_geometry(int B, int F, int K, int d, int heads, int W, int TP, 
   if (layout != HWGAT_LAYOUT_BFKD && layout != HWGAT_LAYOUT_WINDOWS) return HWGAT_ERR_UNSUPPORTED;
   if (W != kWin || TP != kTP) return HWGAT_ERR_UNSUPPORTED;
   if (d != heads * kHd || d > 512) return HWGAT_ERR_UNSUPPORTED;
+  if (dtype == HWGAT_BF16 && d % 128 != 0) return HWGAT_ERR_UNSUPPORTED;  // tcgen05 GEMM tiles are 128 wide
   if (F % TP != 0 || K % 64 != 0) return HWGAT_ERR_UNSUPPORTED;
   if (shift < 0 || shift >= TP) return HWGAT_ERR_SHAPE;
   if (layout == HWGAT_LAYOUT_WINDOWS && shift != 0) return HWGAT_ERR_SHAPE;

@@ -259,129 +259,19 @@ struct FwdTcArgs {
   TileGeom geo;
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                                    const __grid_constant__ CUtensorMap tmW,
-                                                                    const FwdTcArgs p) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int d = p.geo.d, nk = d / 64, heads = p.heads, S = p.w_stages;
-  unsigned char* sX = smem;
-  unsigned char* sW = smem + nk * kXChunk;
-  TcBars* bars = reinterpret_cast<TcBars*>(sW + S * kWStage);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxChunks; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], 1); }
-    for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], kEpiWarps); }
-    mbar_fence_init();
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmW);
-  }
-  if (warp == 1) tmem_alloc(&bars->tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = bars->tmem_slot;
-
-  if (warp < kFirstEpiWarp) {
-    reg_dealloc_donor();
-    if (warp == 0 && lane == 0) tc_producer(p.geo, p.heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
-    if (warp == 1 && lane == 0) tc_issuer(p.geo, p.heads, p.tiles, S, bars, sX, sW, tmem);
-  } else {
-    reg_alloc_epi();
-    // ------------------------------------------------------------ attention warps
-    const int win = warp & 3;             // TMEM lane quarter of this warp == window of the tile
-    const int qh = (warp - kFirstEpiWarp) >> 2;  // which 16 query rows of the window
-    const int g = lane >> 2, t = lane & 3;
-    const uint32_t lane_q = (uint32_t)(32 * win + 16 * qh) << 16;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-      const int row0 = 32 * win + 16 * qh;
-      const size_t orow0 = (size_t)p.geo.token_row(tile, row0 + g) * d;
-      const size_t orow1 = (size_t)p.geo.token_row(tile, row0 + g + 8) * d;
-      const uint32_t* mw = p.bits + p.geo.mask_base(tile) + row0;
-      float mk[2][8];
-      build_row_masks(mw[g], mw[g + 8], t, mk);
-      for (int h = 0; h < heads; ++h, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&bars->acc_full[buf], (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t tb = tmem + buf * kAccStride;
-        const float* bq = p.bias + h * kHd + 2 * t;
-        const float* bk = bq + d;
-        const float* bv = bk + d;
-        // TMEM reads in two groups, waited for late: {q, k} now, {v} under the softmax
-        uint32_t qa[4][4], kb0[4][4], kb1[4][4];
-        {
-          uint32_t r0[32], r1[32], r2[32];
-          tmem_ld_16x256b_x8(tb + lane_q, r0);
-          tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win) << 16) + 64, r1);
-          tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win + 16) << 16) + 64, r2);
-          tmem_wait_regs(r0); tmem_wait_regs(r1); tmem_wait_regs(r2);
-          rows_to_blocks(r0, bq, 0.125f, qa);   // q: A fragments (x head_dim^-0.5)
-          rows_to_blocks(r1, bk, 1.f, kb0);     // k: its C fragments are the B fragments of q.k^T as they come
-          rows_to_blocks(r2, bk, 1.f, kb1);
-        }
-        uint32_t v0[32], v1[32];
-        tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win) << 16) + 128, v0);
-        tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win + 16) << 16) + 128, v1);
-        float s[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
-        mma_rows_x_blocks_T(s, qa, kb0, kb1);
-        bool dead[2];
-        masked_softmax_tc(s, mk, p.threshold, dead);
-        uint32_t pa[2][4];
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          pa[kk][0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-          pa[kk][1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-          pa[kk][2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-          pa[kk][3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-        }
-        tmem_wait_regs(v0); tmem_wait_regs(v1);
-        // last TMEM read of this head: hand the accumulator back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
-        // ---- O = P . v: v blocks -> movmatrix.trans -> B fragments
-        float o[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-        {
-          uint32_t vb[4][4];
-          rows_to_blocks(v0, bv, 1.f, vb);
-          mma_16x64_k16_blocks(o, pa[0], vb);
-          rows_to_blocks(v1, bv, 1.f, vb);
-          mma_16x64_k16_blocks(o, pa[1], vb);
-        }
-        // ---- store: (row g, row g+8) x 64 columns of this head
-        bf16* o0 = p.out + orow0 + h * kHd + 2 * t;
-        bf16* o1 = p.out + orow1 + h * kHd + 2 * t;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          *reinterpret_cast<uint32_t*>(o0 + 8 * nt) = pack_bf16(o[nt][0], o[nt][1]);
-          *reinterpret_cast<uint32_t*>(o1 + 8 * nt) = pack_bf16(o[nt][2], o[nt][3]);
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
-}
-
-__global__ void attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+__global__ void attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                     const FwdTcArgs p);
+
+// weight-ring depth: what is left of the 227 KB after the resident X tile, at most 6 stages
+static int w_stages_for(int d) {
+  const int left = 232448 - 1024 - (int)sizeof(TcBars) - (d / 64) * kXChunk;
+  const int st = left / kWStage;
+  return st > 6 ? 6 : st;
+}
 
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   const int d = a.d, nk = d / 64;
-  const int stages = d == 512 ? 4 : (d == 256 ? 6 : 6);
+  const int stages = w_stages_for(d);
   const int smem_bytes = nk * kXChunk + stages * kWStage + (int)sizeof(TcBars) + 1024;
   static int attr_smem = 0;
   if (smem_bytes > attr_smem) {
@@ -401,68 +291,9 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages;
   p.geo = make_geom(a.F, a.K, d, a.shift, a.layout);
   const int grid = p.tiles < 148 ? p.tiles : 148;
-  static const bool pair_warps = getenv("HWGAT_PAIR_WARPS") != nullptr;  // A/B switch: first-generation attention warps
-  if (pair_warps || (a.heads & 1)) {
-    attn_fwd_tc_kernel<<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
-  } else {
-    static int attr2 = 0;
-    if (smem_bytes > attr2) {
-      cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-      attr2 = smem_bytes;
-    }
-    attn_fwd_tc2_kernel<<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
-  }
+  attn_fwd_tc_kernel<<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
   count_launch();
   return (int)cudaGetLastError();
-}
-
-// ===========================================================================
-// K3a on tcgen05: recompute QKV_h in TMEM exactly as K2 does, then the attention
-// backward of every window, writing dQKV (bf16, token order) for the two
-// weight-side GEMMs (gemm_tc.cu).
-//
-// The attention warps work as pairs (one pair per window, each warp 16 query
-// rows).  Pass 1, per query half: S, P (recomputed), dP = dO v^T,
-// dS = live ? P*(dP - rowsum(P*dP)) : 0, dq = dS k * scale.  Pass 2, per key half:
-// dv = P^T dO and dk = dS^T q need the partner's P / dS / dO rows; they are
-// exchanged through a 64-column "mailbox" in the unused TMEM columns of the
-// accumulator buffer (tcgen05.st by the owner, tcgen05.ld by the partner: both
-// warps sit in the same TMEM lane quarter), so nothing goes through shared
-// memory.  Transposed operands (P^T, dS^T, and the [k=token][n=e] B operands)
-// are movmatrix.trans of the 8x8 bf16 blocks already held in registers.
-// ===========================================================================
-HW_DEV void tmem_st_16x256b_x8(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.16x256b.x8.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,"
-      "%31,%32};\n" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-HW_DEV void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-HW_DEV void pair_barrier(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
-
-constexpr int kMailCol = 192;  // mailbox columns [192, 256) of each accumulator buffer
-
-// 16 rows x 64 columns of the accumulator -> (+bias) * mul -> bf16 A-fragment / 8x8-block registers:
-// f[ks][0] = rows g, cols 16ks+2t..   f[ks][1] = rows g+8, same cols   f[ks][2], f[ks][3]: cols +8
-HW_DEV void ld_rows_as_blocks(uint32_t taddr, const float* __restrict__ bias2t, float mul, uint32_t (&f)[4][4]) {
-  uint32_t r[32];
-  tmem_ld_16x256b_x8(taddr, r);
-  tmem_ld_wait();
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-    for (int x = 0; x < 2; ++x) {
-      const int nt = 2 * ks + x;
-      const float2 bb = *reinterpret_cast<const float2*>(bias2t + 8 * nt);
-      f[ks][2 * x] = pack_bf16((__uint_as_float(r[4 * nt]) + bb.x) * mul, (__uint_as_float(r[4 * nt + 1]) + bb.y) * mul);
-      f[ks][2 * x + 1] =
-          pack_bf16((__uint_as_float(r[4 * nt + 2]) + bb.x) * mul, (__uint_as_float(r[4 * nt + 3]) + bb.y) * mul);
-    }
 }
 
 // raw 16 x 64 accumulator rows (tcgen05.ld.16x256b.x8 registers) -> (+bias) * mul -> 8x8-block registers
@@ -491,31 +322,6 @@ HW_DEV void mma_rows_x_blocks_T(float (&acc)[4][4], const uint32_t (&a)[4][4], c
     }
 }
 
-// acc[16 x 32] += A[16 x 64] . M^T where M (32 rows x 64 cols) sits in TMEM lanes [lane32, lane32+32) at column col0:
-// M's C fragments are the B fragments as they come (the q.k^T / dO.v^T pattern).
-HW_DEV void mma_rows_x_tmem_T(float (&acc)[4][4], const uint32_t (&a)[4][4], uint32_t tb, int lane32, int col0,
-                              const float* __restrict__ bias2t) {
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    uint32_t r[32];
-    tmem_ld_16x256b_x8(tb + ((uint32_t)(lane32 + 16 * mt) << 16) + col0, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const float2 b0 = *reinterpret_cast<const float2*>(bias2t + 8 * (2 * ks));
-      const float2 b1 = *reinterpret_cast<const float2*>(bias2t + 8 * (2 * ks + 1));
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const uint32_t f0 = pack_bf16(__uint_as_float(r[4 * (2 * ks) + 2 * hh]) + b0.x,
-                                      __uint_as_float(r[4 * (2 * ks) + 2 * hh + 1]) + b0.y);
-        const uint32_t f1 = pack_bf16(__uint_as_float(r[4 * (2 * ks + 1) + 2 * hh]) + b1.x,
-                                      __uint_as_float(r[4 * (2 * ks + 1) + 2 * hh + 1]) + b1.y);
-        mma16816(acc[2 * mt + hh], a[ks], f0, f1);
-      }
-    }
-  }
-}
-
 // acc[16 x 64] += A[16 x 16] . Bm[16 x 64], Bm given as the 8x8-block registers f[ks][..] of its 16 rows
 // (layout of ld_rows_as_blocks): B fragments are movmatrix.trans of the blocks.
 HW_DEV void mma_16x64_k16_blocks(float (&acc)[8][4], const uint32_t (&a)[4], const uint32_t (&f)[4][4]) {
@@ -527,247 +333,47 @@ HW_DEV void mma_16x64_k16_blocks(float (&acc)[8][4], const uint32_t (&a)[4], con
   }
 }
 
-HW_DEV void store_rows_16x64(const float (&c)[8][4], float mul, bf16* __restrict__ p0, bf16* __restrict__ p1) {
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    *reinterpret_cast<uint32_t*>(p0 + 8 * nt) = pack_bf16(c[nt][0] * mul, c[nt][1] * mul);
-    *reinterpret_cast<uint32_t*>(p1 + 8 * nt) = pack_bf16(c[nt][2] * mul, c[nt][3] * mul);
+// 4x4 transpose of 32-bit words across the 4 lanes of a quad: r[j] on lane t  <-  r[t] of lane j
+HW_DEV void quad_transpose4(uint32_t (&r)[4], int t) {
+  {
+    const bool odd = t & 1;
+    uint32_t a = odd ? r[0] : r[1], b = odd ? r[2] : r[3];
+    a = __shfl_xor_sync(0xffffffffu, a, 1);
+    b = __shfl_xor_sync(0xffffffffu, b, 1);
+    if (odd) { r[0] = a; r[2] = b; } else { r[1] = a; r[3] = b; }
+  }
+  {
+    const bool hi = t & 2;
+    uint32_t a = hi ? r[0] : r[2], b = hi ? r[1] : r[3];
+    a = __shfl_xor_sync(0xffffffffu, a, 2);
+    b = __shfl_xor_sync(0xffffffffu, b, 2);
+    if (hi) { r[0] = a; r[1] = b; } else { r[2] = a; r[3] = b; }
   }
 }
-
-struct BwdTcArgs {
-  const float* bias;
-  const uint32_t* bits;
-  const bf16* d_out;
-  bf16* dqkv;
-  float threshold;
-  int heads, tiles, w_stages;
-  TileGeom geo;
-};
-
-__global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                                    const __grid_constant__ CUtensorMap tmW,
-                                                                    const BwdTcArgs p) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int d = p.geo.d, nk = d / 64, heads = p.heads, S = p.w_stages;
-  unsigned char* sX = smem;
-  unsigned char* sW = smem + nk * kXChunk;
-  TcBars* bars = reinterpret_cast<TcBars*>(sW + S * kWStage);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxChunks; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], 1); }
-    for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], kEpiWarps); }
-    mbar_fence_init();
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmW);
-  }
-  if (warp == 1) tmem_alloc(&bars->tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = bars->tmem_slot;
-
-  if (warp < kFirstEpiWarp) {
-    reg_dealloc_donor();
-    if (warp == 0 && lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
-    if (warp == 1 && lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, tmem);
-  } else {
-    reg_alloc_epi();
-    const int win = warp & 3;                    // TMEM lane quarter == window
-    const int qh = (warp - kFirstEpiWarp) >> 2;  // my 16 query rows (pass 1) and my 16 key rows (pass 2)
-    const int g = lane >> 2, t = lane & 3;
-    const int my_lanes = 32 * win + 16 * qh, other_lanes = 32 * win + 16 * (1 - qh);
-    const size_t d3 = (size_t)3 * d;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-      const int row0 = 32 * win + 16 * qh;
-      const size_t tr0 = (size_t)p.geo.token_row(tile, row0 + g), tr1 = (size_t)p.geo.token_row(tile, row0 + g + 8);
-      const uint32_t* mw = p.bits + p.geo.mask_base(tile) + row0;
-      float mk[2][8];
-      build_row_masks(mw[g], mw[g + 8], t, mk);
-      for (int h = 0; h < heads; ++h, ++it) {
-        const int buf = it & 1;
-        // dO rows of this warp as A fragments, straight from global (independent of the MMA: issue first)
-        uint32_t ga[4][4];
-        if (h + 1 < heads && lane < 16) {  // pull the next head's 16 x 128-byte dO rows into L2 ahead of time
-          const size_t r = (size_t)p.geo.token_row(tile, row0 + lane);
-          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.d_out + r * d + (h + 1) * kHd));
-        }
-        {
-          const bf16* g0 = p.d_out + tr0 * d + h * kHd + 2 * t;
-          const bf16* g1 = p.d_out + tr1 * d + h * kHd + 2 * t;
+// C fragments [16 x 64] -> bf16 -> global rows p0 (row g) and p1 (row g+8), 64 columns each.  A thread's
+// fragment holds 2 columns of every 8-column group; the quad transposes so that lane t owns the whole group t
+// (and 4+t) and stores 16 bytes: 4-byte scattered stores were 23 % of the forward attention warps' time.
+HW_DEV void store_rows_16x64(const float (&c)[8][4], float mul, bf16* __restrict__ p0, bf16* __restrict__ p1, int t) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            ga[ks][0] = *reinterpret_cast<const uint32_t*>(g0 + 16 * ks);
-            ga[ks][1] = *reinterpret_cast<const uint32_t*>(g1 + 16 * ks);
-            ga[ks][2] = *reinterpret_cast<const uint32_t*>(g0 + 16 * ks + 8);
-            ga[ks][3] = *reinterpret_cast<const uint32_t*>(g1 + 16 * ks + 8);
-          }
-        }
-        mbar_wait(&bars->acc_full[buf], (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t tb = tmem + buf * kAccStride;
-        const float* bq = p.bias + h * kHd + 2 * t;
-        const float* bk = bq + d;
-        const float* bv = bk + d;
-        // ---------------- pass 1: my 16 query rows
-        // TMEM reads are issued in two groups and waited for late: {q, k} now, {v, partner q} under the softmax
-        uint32_t qa[4][4], kb0[4][4], kb1[4][4];
-        {
-          uint32_t r0[32], r1[32], r2[32];
-          tmem_ld_16x256b_x8(tb + ((uint32_t)my_lanes << 16), r0);
-          tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win) << 16) + 64, r1);
-          tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win + 16) << 16) + 64, r2);
-          tmem_wait_regs(r0); tmem_wait_regs(r1); tmem_wait_regs(r2);
-          rows_to_blocks(r0, bq, 0.125f, qa);
-          rows_to_blocks(r1, bk, 1.f, kb0);
-          rows_to_blocks(r2, bk, 1.f, kb1);
-        }
-        uint32_t v0[32], v1[32], q2[32];
-        tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win) << 16) + 128, v0);
-        tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * win + 16) << 16) + 128, v1);
-        tmem_ld_16x256b_x8(tb + ((uint32_t)other_lanes << 16), q2);
-        float pr[4][4];
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r0[4], r1[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pr[i][j] = 0.f;
-        mma_rows_x_blocks_T(pr, qa, kb0, kb1);                  // S = q k^T
-        bool dead[2];
-        masked_softmax_tc(pr, mk, p.threshold, dead);  // P (exactly 0 wherever the logit is not live)
-        tmem_wait_regs(v0); tmem_wait_regs(v1); tmem_wait_regs(q2);
-        // last read of the accumulator: hand it back to the MMA warp (the mailbox columns are not part of it)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
-        float ds[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ds[i][j] = 0.f;
-        {
-          uint32_t vb0[4][4], vb1[4][4];
-          rows_to_blocks(v0, bv, 1.f, vb0);
-          rows_to_blocks(v1, bv, 1.f, vb1);
-          mma_rows_x_blocks_T(ds, ga, vb0, vb1);                // dP = dO v^T
-        }
-        uint32_t qo[4][4];
-        rows_to_blocks(q2, bq, 0.125f, qo);                     // the partner's q rows (B operand of dk)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          float delta = 0.f;
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) delta += pr[nt][2 * r] * ds[nt][2 * r] + pr[nt][2 * r + 1] * ds[nt][2 * r + 1];
-          delta = quad_sum(delta);
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-            for (int x = 0; x < 2; ++x)  // dS = live ? P (dP - delta) : 0, and P == 0 off the live set
-              ds[nt][2 * r + x] = dead[r] ? 0.f : pr[nt][2 * r + x] * (ds[nt][2 * r + x] - delta);
-        }
-        // 8x8 bf16 blocks: pb[hi][nn] = P[rows 8hi+g][keys 8nn+2t..], db likewise for dS
-        uint32_t pb[2][4], db[2][4];
-#pragma unroll
-        for (int nn = 0; nn < 4; ++nn) {
-          pb[0][nn] = pack_bf16(pr[nn][0], pr[nn][1]);
-          pb[1][nn] = pack_bf16(pr[nn][2], pr[nn][3]);
-          db[0][nn] = pack_bf16(ds[nn][0], ds[nn][1]);
-          db[1][nn] = pack_bf16(ds[nn][2], ds[nn][3]);
-        }
-        // mailbox for the partner: my P / dS blocks of ITS key columns, and my dO fragments
-        {
-          uint32_t m[32];
-          // (selects, not pb[..][runtime index]: a dynamically indexed register array goes to local memory)
-          m[0] = qh ? pb[0][0] : pb[0][2]; m[1] = qh ? pb[0][1] : pb[0][3];
-          m[2] = qh ? pb[1][0] : pb[1][2]; m[3] = qh ? pb[1][1] : pb[1][3];
-          m[4] = qh ? db[0][0] : db[0][2]; m[5] = qh ? db[0][1] : db[0][3];
-          m[6] = qh ? db[1][0] : db[1][2]; m[7] = qh ? db[1][1] : db[1][3];
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) m[8 + 4 * ks + i] = ga[ks][i];
-#pragma unroll
-          for (int i = 24; i < 32; ++i) m[i] = 0u;
-          tmem_st_16x256b_x8(tb + ((uint32_t)my_lanes << 16) + kMailCol, m);
-        }
-        // dq = dS k * scale : A = dS fragments, B = movmatrix.trans of the k blocks kept from the logits
-        {
-          float dq[8][4];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
-          const uint32_t a0[4] = {db[0][0], db[1][0], db[0][1], db[1][1]};
-          mma_16x64_k16_blocks(dq, a0, kb0);
-          const uint32_t a1[4] = {db[0][2], db[1][2], db[0][3], db[1][3]};
-          mma_16x64_k16_blocks(dq, a1, kb1);
-          store_rows_16x64(dq, 0.125f, p.dqkv + tr0 * d3 + h * kHd + 2 * t, p.dqkv + tr1 * d3 + h * kHd + 2 * t);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        pair_barrier(1 + win);
-        tc_fence_after();
-        uint32_t m[32];
-        tmem_ld_16x256b_x8(tb + ((uint32_t)other_lanes << 16) + kMailCol, m);
-        tmem_ld_wait();
-        // ---------------- pass 2: my 16 key rows (same token rows as my query rows)
-        // my P / dS blocks of MY key columns (key n tiles 2qh, 2qh+1), again by select
-        const uint32_t pm[4] = {qh ? pb[0][2] : pb[0][0], qh ? pb[0][3] : pb[0][1], qh ? pb[1][2] : pb[1][0],
-                                qh ? pb[1][3] : pb[1][1]};
-        const uint32_t dm[4] = {qh ? db[0][2] : db[0][0], qh ? db[0][3] : db[0][1], qh ? db[1][2] : db[1][0],
-                                qh ? db[1][3] : db[1][1]};
-        {
-          float dv[8][4];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dv[i][j] = 0.f;
-          // P^T fragments: own 16 queries, then the partner's 16 queries
-          const uint32_t a_own[4] = {movmatrix_trans(pm[0]), movmatrix_trans(pm[1]), movmatrix_trans(pm[2]),
-                                     movmatrix_trans(pm[3])};
-          mma_16x64_k16_blocks(dv, a_own, ga);
-          const uint32_t a_oth[4] = {movmatrix_trans(m[0]), movmatrix_trans(m[1]), movmatrix_trans(m[2]),
-                                     movmatrix_trans(m[3])};
-          uint32_t go[4][4];
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) go[ks][i] = m[8 + 4 * ks + i];
-          mma_16x64_k16_blocks(dv, a_oth, go);
-          store_rows_16x64(dv, 1.f, p.dqkv + tr0 * d3 + 2 * d + h * kHd + 2 * t,
-                           p.dqkv + tr1 * d3 + 2 * d + h * kHd + 2 * t);
-        }
-        {
-          float dk[8][4];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dk[i][j] = 0.f;
-          const uint32_t a_own[4] = {movmatrix_trans(dm[0]), movmatrix_trans(dm[1]), movmatrix_trans(dm[2]),
-                                     movmatrix_trans(dm[3])};
-          mma_16x64_k16_blocks(dk, a_own, qa);
-          const uint32_t a_oth[4] = {movmatrix_trans(m[4]), movmatrix_trans(m[5]), movmatrix_trans(m[6]),
-                                     movmatrix_trans(m[7])};
-          mma_16x64_k16_blocks(dk, a_oth, qo);
-          store_rows_16x64(dk, 1.f, p.dqkv + tr0 * d3 + d + h * kHd + 2 * t, p.dqkv + tr1 * d3 + d + h * kHd + 2 * t);
-        }
-      }
+    for (int j = 0; j < 4; ++j) {
+      r0[j] = pack_bf16(c[4 * half + j][0] * mul, c[4 * half + j][1] * mul);
+      r1[j] = pack_bf16(c[4 * half + j][2] * mul, c[4 * half + j][3] * mul);
     }
+    quad_transpose4(r0, t);
+    quad_transpose4(r1, t);
+    *reinterpret_cast<int4*>(p0 + 32 * half + 8 * t) = make_int4((int)r0[0], (int)r0[1], (int)r0[2], (int)r0[3]);
+    *reinterpret_cast<int4*>(p1 + 32 * half + 8 * t) = make_int4((int)r1[0], (int)r1[1], (int)r1[2], (int)r1[3]);
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 // ===========================================================================
-// Second-generation attention warps: ONE warp per window (all 32 query rows), the two warp sets
-// (warps 4-7, 8-11) work on alternate heads, one TMEM accumulator each.  Compared with the pair
-// design above this converts every q / k / v row from TMEM exactly once per window (instead of
-// k and v once per warp of the pair), re-uses each transposed B fragment for both 16-row m tiles,
-// and needs no exchange between warps.
+// K2 kernel.  Attention warps: ONE warp per window (all 32 query rows); the two warp sets (warps 4-7,
+// 8-11) work on alternate heads, one TMEM accumulator each.  Every q / k / v row is converted from
+// TMEM exactly once, each transposed B fragment serves both 16-row m tiles, and nothing is exchanged
+// between warps.
 // ===========================================================================
 // acc[m][16 x 64] += A[m][16 x 16] . Bm[16 x 64] for both m tiles, Bm as block registers (transposed once)
 HW_DEV void mma_2x16x64_k16_blocks(float (&acc0)[8][4], float (&acc1)[8][4], const uint32_t (&a0)[4],
@@ -802,7 +408,7 @@ HW_DEV void probs_to_afrag(uint32_t (&pa)[2][4], const float (&s)[4][4]) {
   }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmX,
+__global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                      const __grid_constant__ CUtensorMap tmW,
                                                                      const FwdTcArgs p) {
   extern __shared__ unsigned char smem_raw[];
@@ -894,8 +500,252 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc2_kernel(const __gri
           rows_to_blocks(v1, bv, 1.f, vb);
           mma_2x16x64_k16_blocks(o0, o1, pa0[1], pa1[1], vb);
         }
-        store_rows_16x64(o0, 1.f, p.out + orow[0] + h * kHd + 2 * t, p.out + orow[1] + h * kHd + 2 * t);
-        store_rows_16x64(o1, 1.f, p.out + orow[2] + h * kHd + 2 * t, p.out + orow[3] + h * kHd + 2 * t);
+        store_rows_16x64(o0, 1.f, p.out + orow[0] + h * kHd, p.out + orow[1] + h * kHd, t);
+        store_rows_16x64(o1, 1.f, p.out + orow[2] + h * kHd, p.out + orow[3] + h * kHd, t);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+struct BwdTcArgs {
+  const float* bias;
+  const uint32_t* bits;
+  const bf16* d_out;
+  bf16* dqkv;
+  float threshold;
+  int heads, tiles, w_stages;
+  TileGeom geo;
+};
+
+// compact per-row masks (bit i = the thread's i-th column allowed) -> the float form masked_softmax_tc takes;
+// the backward keeps the compact form between heads to save 28 registers
+HW_DEV void expand_row_masks(uint32_t c0, uint32_t c1, float (&mk)[2][8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mk[0][i] = (c0 >> i) & 1u ? 1.f : 0.f;
+    mk[1][i] = (c1 >> i) & 1u ? 1.f : 0.f;
+  }
+}
+HW_DEV uint32_t compact_row_mask(uint32_t mword, int t) {
+  uint32_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c |= ((mword >> (8 * (i >> 1) + 2 * t + (i & 1))) & 1u) << i;
+  return c;
+}
+// dS = dead ? 0 : P (dP - rowsum(P dP)) in place of dP; returns nothing (P is exactly 0 off the live set)
+HW_DEV void softmax_backward_rows(float (&ds)[4][4], const float (&pr)[4][4], const bool (&dead)[2]) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float delta = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) delta += pr[nt][2 * r] * ds[nt][2 * r] + pr[nt][2 * r + 1] * ds[nt][2 * r + 1];
+    delta = quad_sum(delta);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int x = 0; x < 2; ++x) ds[nt][2 * r + x] = dead[r] ? 0.f : pr[nt][2 * r + x] * (ds[nt][2 * r + x] - delta);
+  }
+}
+// [16 x 32] fp32 accumulator tiles -> 8x8 bf16 blocks b[hi][nn] (rows 8hi+g, columns 8nn+2t..)
+HW_DEV void tiles_to_blocks(uint32_t (&b)[2][4], const float (&s)[4][4]) {
+#pragma unroll
+  for (int nn = 0; nn < 4; ++nn) {
+    b[0][nn] = pack_bf16(s[nn][0], s[nn][1]);
+    b[1][nn] = pack_bf16(s[nn][2], s[nn][3]);
+  }
+}
+// dO rows (16 x 64 of one head) as A-fragment / block registers, 4-byte loads straight into the fragment layout
+// (16-byte loads + quad transposes measured 4 % slower: the shuffles cost more than the narrow loads, which hit L2)
+HW_DEV void load_rows_as_blocks_global(const bf16* __restrict__ g0, const bf16* __restrict__ g1, int t,
+                                       uint32_t (&ga)[4][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    ga[ks][0] = *reinterpret_cast<const uint32_t*>(g0 + 16 * ks + 2 * t);
+    ga[ks][1] = *reinterpret_cast<const uint32_t*>(g1 + 16 * ks + 2 * t);
+    ga[ks][2] = *reinterpret_cast<const uint32_t*>(g0 + 16 * ks + 8 + 2 * t);
+    ga[ks][3] = *reinterpret_cast<const uint32_t*>(g1 + 16 * ks + 8 + 2 * t);
+  }
+}
+
+// K3a, second generation: one warp per window, alternate heads per warp set (see attn_fwd_tc_kernel).
+// Everything of a window's backward stays inside one warp: no mailbox, no pair barrier.
+__global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                     const __grid_constant__ CUtensorMap tmW,
+                                                                     const BwdTcArgs p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int d = p.geo.d, nk = d / 64, heads = p.heads, S = p.w_stages;
+  unsigned char* sX = smem;
+  unsigned char* sW = smem + nk * kXChunk;
+  TcBars* bars = reinterpret_cast<TcBars*>(sW + S * kWStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxChunks; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], 1); }
+    for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp < kFirstEpiWarp) {
+    reg_dealloc_donor();
+    if (warp == 0 && lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
+    if (warp == 1 && lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, tmem);
+  } else {
+    reg_alloc_epi();
+    const int win = warp & 3;
+    const int set = (warp - kFirstEpiWarp) >> 2;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t tb = tmem + set * kAccStride + ((uint32_t)(32 * win) << 16);
+    const size_t d3 = (size_t)3 * d;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      size_t tr[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) tr[r] = (size_t)p.geo.token_row(tile, 32 * win + 8 * r + g);
+      const uint32_t* mw = p.bits + p.geo.mask_base(tile) + 32 * win;
+      uint32_t cm[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) cm[r] = compact_row_mask(mw[8 * r + g], t);
+      for (int h = 0; h < heads; ++h, ++it) {
+        if ((it & 1) != set) continue;
+        if (h + 2 < heads) {  // pull this warp's next head's dO rows (32 x 128 bytes) into L2 ahead of time
+          const size_t r = (size_t)p.geo.token_row(tile, 32 * win + lane);
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.d_out + r * d + (h + 2) * kHd));
+        }
+        mbar_wait(&bars->acc_full[set], (it >> 1) & 1);
+        tc_fence_after();
+        const float* bq = p.bias + h * kHd + 2 * t;
+        const float* bk = bq + d;
+        const float* bv = bk + d;
+        uint32_t qa0[4][4], qa1[4][4], kb0[4][4], kb1[4][4];
+        {
+          uint32_t r0[32], r1[32], r2[32], r3[32];
+          tmem_ld_16x256b_x8(tb, r0);
+          tmem_ld_16x256b_x8(tb + (16u << 16), r1);
+          tmem_ld_16x256b_x8(tb + 64, r2);
+          tmem_ld_16x256b_x8(tb + (16u << 16) + 64, r3);
+          tmem_wait_regs(r0); tmem_wait_regs(r1); tmem_wait_regs(r2); tmem_wait_regs(r3);
+          rows_to_blocks(r0, bq, 0.125f, qa0);
+          rows_to_blocks(r1, bq, 0.125f, qa1);
+          rows_to_blocks(r2, bk, 1.f, kb0);
+          rows_to_blocks(r3, bk, 1.f, kb1);
+        }
+        uint32_t v0[32], v1[32];
+        tmem_ld_16x256b_x8(tb + 128, v0);
+        tmem_ld_16x256b_x8(tb + (16u << 16) + 128, v1);
+        // dO rows (L2-resident thanks to the prefetch): loaded here, after the 128 raw q/k registers are dead
+        uint32_t ga0[4][4], ga1[4][4];
+        load_rows_as_blocks_global(p.d_out + tr[0] * d + h * kHd, p.d_out + tr[1] * d + h * kHd, t, ga0);
+        load_rows_as_blocks_global(p.d_out + tr[2] * d + h * kHd, p.d_out + tr[3] * d + h * kHd, t, ga1);
+        // ---- P (recomputed)
+        float p0[4][4], p1[4][4];
+        zero4x4(p0);
+        zero4x4(p1);
+        mma_rows_x_blocks_T(p0, qa0, kb0, kb1);
+        mma_rows_x_blocks_T(p1, qa1, kb0, kb1);
+        bool dead0[2], dead1[2];
+        {
+          float mk[2][8];
+          expand_row_masks(cm[0], cm[1], mk);
+          masked_softmax_tc(p0, mk, p.threshold, dead0);
+          expand_row_masks(cm[2], cm[3], mk);
+          masked_softmax_tc(p1, mk, p.threshold, dead1);
+        }
+        tmem_wait_regs(v0); tmem_wait_regs(v1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[set]);  // last TMEM read of this head
+        // ---- dP = dO v^T, dS
+        float s0[4][4], s1[4][4];
+        zero4x4(s0);
+        zero4x4(s1);
+        {
+          uint32_t vb0[4][4], vb1[4][4];
+          rows_to_blocks(v0, bv, 1.f, vb0);
+          rows_to_blocks(v1, bv, 1.f, vb1);
+          mma_rows_x_blocks_T(s0, ga0, vb0, vb1);
+          mma_rows_x_blocks_T(s1, ga1, vb0, vb1);
+        }
+        softmax_backward_rows(s0, p0, dead0);
+        softmax_backward_rows(s1, p1, dead1);
+        uint32_t pb0[2][4], pb1[2][4], db0[2][4], db1[2][4];
+        tiles_to_blocks(pb0, p0);
+        tiles_to_blocks(pb1, p1);
+        tiles_to_blocks(db0, s0);
+        tiles_to_blocks(db1, s1);
+        // ---- dq = dS k * scale (both query m tiles share the transposed k blocks)
+        {
+          float dq0[8][4], dq1[8][4];
+          zero8x4(dq0);
+          zero8x4(dq1);
+          {
+            const uint32_t a0[4] = {db0[0][0], db0[1][0], db0[0][1], db0[1][1]};
+            const uint32_t a1[4] = {db1[0][0], db1[1][0], db1[0][1], db1[1][1]};
+            mma_2x16x64_k16_blocks(dq0, dq1, a0, a1, kb0);
+          }
+          {
+            const uint32_t a0[4] = {db0[0][2], db0[1][2], db0[0][3], db0[1][3]};
+            const uint32_t a1[4] = {db1[0][2], db1[1][2], db1[0][3], db1[1][3]};
+            mma_2x16x64_k16_blocks(dq0, dq1, a0, a1, kb1);
+          }
+          store_rows_16x64(dq0, 0.125f, p.dqkv + tr[0] * d3 + h * kHd, p.dqkv + tr[1] * d3 + h * kHd, t);
+          store_rows_16x64(dq1, 0.125f, p.dqkv + tr[2] * d3 + h * kHd, p.dqkv + tr[3] * d3 + h * kHd, t);
+        }
+        // ---- dv = P^T dO : key m tiles jt = 0,1; k steps = the two query groups
+        {
+          float dv0[8][4], dv1[8][4];
+          zero8x4(dv0);
+          zero8x4(dv1);
+          {
+            const uint32_t a0[4] = {movmatrix_trans(pb0[0][0]), movmatrix_trans(pb0[0][1]), movmatrix_trans(pb0[1][0]),
+                                    movmatrix_trans(pb0[1][1])};
+            const uint32_t a1[4] = {movmatrix_trans(pb0[0][2]), movmatrix_trans(pb0[0][3]), movmatrix_trans(pb0[1][2]),
+                                    movmatrix_trans(pb0[1][3])};
+            mma_2x16x64_k16_blocks(dv0, dv1, a0, a1, ga0);
+          }
+          {
+            const uint32_t a0[4] = {movmatrix_trans(pb1[0][0]), movmatrix_trans(pb1[0][1]), movmatrix_trans(pb1[1][0]),
+                                    movmatrix_trans(pb1[1][1])};
+            const uint32_t a1[4] = {movmatrix_trans(pb1[0][2]), movmatrix_trans(pb1[0][3]), movmatrix_trans(pb1[1][2]),
+                                    movmatrix_trans(pb1[1][3])};
+            mma_2x16x64_k16_blocks(dv0, dv1, a0, a1, ga1);
+          }
+          store_rows_16x64(dv0, 1.f, p.dqkv + tr[0] * d3 + 2 * d + h * kHd, p.dqkv + tr[1] * d3 + 2 * d + h * kHd, t);
+          store_rows_16x64(dv1, 1.f, p.dqkv + tr[2] * d3 + 2 * d + h * kHd, p.dqkv + tr[3] * d3 + 2 * d + h * kHd, t);
+        }
+        // ---- dk = dS^T q (q carries the scale)
+        {
+          float dk0[8][4], dk1[8][4];
+          zero8x4(dk0);
+          zero8x4(dk1);
+          {
+            const uint32_t a0[4] = {movmatrix_trans(db0[0][0]), movmatrix_trans(db0[0][1]), movmatrix_trans(db0[1][0]),
+                                    movmatrix_trans(db0[1][1])};
+            const uint32_t a1[4] = {movmatrix_trans(db0[0][2]), movmatrix_trans(db0[0][3]), movmatrix_trans(db0[1][2]),
+                                    movmatrix_trans(db0[1][3])};
+            mma_2x16x64_k16_blocks(dk0, dk1, a0, a1, qa0);
+          }
+          {
+            const uint32_t a0[4] = {movmatrix_trans(db1[0][0]), movmatrix_trans(db1[0][1]), movmatrix_trans(db1[1][0]),
+                                    movmatrix_trans(db1[1][1])};
+            const uint32_t a1[4] = {movmatrix_trans(db1[0][2]), movmatrix_trans(db1[0][3]), movmatrix_trans(db1[1][2]),
+                                    movmatrix_trans(db1[1][3])};
+            mma_2x16x64_k16_blocks(dk0, dk1, a0, a1, qa1);
+          }
+          store_rows_16x64(dk0, 1.f, p.dqkv + tr[0] * d3 + d + h * kHd, p.dqkv + tr[1] * d3 + d + h * kHd, t);
+          store_rows_16x64(dk1, 1.f, p.dqkv + tr[2] * d3 + d + h * kHd, p.dqkv + tr[3] * d3 + d + h * kHd, t);
+        }
       }
     }
   }
@@ -906,7 +756,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc2_kernel(const __gri
 
 int attn_bwd_tc(const AttnArgs& a, bf16* dqkv, cudaStream_t s) {
   const int d = a.d, nk = d / 64;
-  const int stages = d == 512 ? 4 : 6;
+  const int stages = w_stages_for(d);
   const int smem_bytes = nk * kXChunk + stages * kWStage + (int)sizeof(TcBars) + 1024;
   static int attr_smem = 0;
   if (smem_bytes > attr_smem) {
@@ -929,6 +779,25 @@ int attn_bwd_tc(const AttnArgs& a, bf16* dqkv, cudaStream_t s) {
   attn_bwd_tc_kernel<<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
   count_launch();
   return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// bf16 entry points of the C ABI (api.cu): K2 = one kernel; K3 = K3a + the two weight-side GEMMs
+// ---------------------------------------------------------------------------
+int attn_fwd_bf16(const AttnArgs& a, cudaStream_t s) { return attn_fwd_tc(a, s); }
+
+int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s) {
+  bf16* dqkv = (bf16*)a.workspace;
+  int st = attn_bwd_tc(a, dqkv, s);
+  if (st) return st;
+  const long long n = a.tokens();
+  const int d = a.d, d3 = 3 * d;
+  // d_xn[n, d] = dQKV[n, 3d] . Wqkv[3d, d]  (against Wqkv^T so that both operands are K-major)
+  bf16* wt = dqkv + n * d3;
+  if ((st = transpose_bf16((const bf16*)a.w_qkv, wt, d3, d, s))) return st;
+  if ((st = gemm_tc_nt(dqkv, wt, (bf16*)a.d_xn, (int)n, d, d3, s))) return st;
+  // d_w[3d, d] = dQKV^T . xn ; d_b = column sums of dQKV (same kernel)
+  return gemm_tc_tn(dqkv, (const bf16*)a.xn, a.d_w, a.d_b, d3, d, n, s);
 }
 
 }  // namespace hwgat

@@ -474,3 +474,58 @@ def test_layer_norm_mean_pool(d, tokens, B):
     assert rel_inf(y, y64) < 1e-5
     assert rel_inf(x.grad, x64.grad) < 1e-5
     assert rel_inf(gamma.grad, g64.grad) < 1e-4 and rel_inf(beta.grad, b64.grad) < 1e-5
+
+
+# ------------------------------------------------------------------ other geometries of the tcgen05 kernels
+def test_attention_bf16_six_heads():
+    """d = 384 (6 heads, 6 k chunks, 5 weight stages): a width between the reference's levels."""
+    d, h, B, F = 384, 6, 3, 6
+    xn, w, b, g = core_inputs(d, 1, 0.1, B=B, F=F)
+    xn, g = xn.to(torch.bfloat16).double(), g.to(torch.bfloat16).double()
+    w = w.to(torch.bfloat16).double()
+    b = b.float().double()
+    y, dx, dw, db = cuda_core(xn, w, b, g, h, 1, None, torch.bfloat16)
+    ry, rdx, rdw, rdb = oracle_core(xn, w, b, g, h, F, 1, None)
+    errs = dict(y=rel_l2(y, ry), dx=rel_l2(dx, rdx), dw=rel_l2(dw, rdw), db=rel_l2(db, rdb))
+    assert all(e < BF16_TOL for e in errs.values()), errs
+
+
+@pytest.mark.parametrize("d,h", [(64, 1), (192, 3)])
+def test_widths_outside_the_bf16_kernels(d, h):
+    """bf16 needs d % 128 == 0 (tcgen05 GEMM tiles): other widths are an error, not a fallback; fp32 takes them."""
+    from sl_hwgat_b200 import _lib, ops
+    xn, w, b, g = core_inputs(d, 0, 0.1, B=1, F=4)
+    with pytest.raises(_lib.HwgatError):
+        cuda_core(xn, w, b, g, h, 0, None, torch.bfloat16)
+    y, dx, dw, db = cuda_core(xn, w, b, g, h, 0, None, torch.float32)
+    ry, rdx, rdw, rdb = oracle_core(xn.float(), w.float(), b.float(), g.float(), h, 4, 0, None)
+    assert rel_inf(y, ry) < FP32_TOL and rel_inf(dx, rdx) < FP32_TOL and rel_inf(dw, rdw) < FP32_TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_128_keypoints(dtype):
+    """K = 128 keypoints = 8 windows per frame group (two tiles per temporal group)."""
+    from sl_hwgat_b200 import ops
+    d, h, B, F, K = 128, 2, 2, 4, 128
+    rng = np.random.default_rng(3)
+    edges = [[[int(a), int(b)] for a, b in rng.integers(0, 16, size=(20, 2))] for _ in range(8)]
+    adj = O.window_adjacency(edges, 16, 2)                                  # (8, 32, 32)
+    mask = O.combined_mask(adj, F, 16, 2, 1)
+    xn = torch.from_numpy(rng.standard_normal((B, F, K, d)))
+    w = torch.from_numpy(rng.standard_normal((3 * d, d)) * 0.05)
+    b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1)
+    g = torch.from_numpy(rng.standard_normal((B, F, K, d)))
+    if dtype == torch.bfloat16:
+        xn, g, w = (t.to(torch.bfloat16).double() for t in (xn, g, w))
+    bits = ops.mask_build(torch.from_numpy(adj.astype(np.float32)).cuda(), F, 1)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), O.pack_mask_bits(mask))
+    x_ = xn.to("cuda", dtype).requires_grad_(True)
+    w_ = w.float().cuda().requires_grad_(True)
+    b_ = b.float().cuda().requires_grad_(True)
+    y = ops.window_graph_attention(x_, w_, b_, bits, h, shift=1)
+    y.backward(g.to("cuda", dtype))
+    ry = O.attention_core(xn.double(), w.double(), b.float().double(), h, mask, 16, 2, 1, None)
+    rdx, rdw, rdb = O.attention_core_backward(xn.double(), w.double(), b.float().double(), h, mask, 16, 2, 1, None,
+                                              g.double())
+    tol, f = (FP32_TOL, rel_inf) if dtype == torch.float32 else (BF16_TOL, rel_l2)
+    assert f(y, ry) < tol and f(x_.grad, rdx) < tol and f(w_.grad, rdw) < tol and f(b_.grad, rdb) < tol
