@@ -94,7 +94,7 @@ size_t hwgat_attn_workspace_bytes(int B, int F, int K, int d, int heads, int dty
  * threshold: < 0 = eval mode.  >= 0 = training mode: logits whose unmasked
  *         softmax exceeds it are zeroed first (HWGATE.py:94-100).
  * out   : (B,F,K,d) dtype, head-merged context, same token order as xn.
- * workspace: hwgat_attn_workspace_bytes(..., backward=0) bytes (may be 0).     */
+ * workspace: hwgat_attn_workspace_bytes(..., backward=0) bytes.                */
 int hwgat_attn_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits,
                    float threshold, void* out, void* workspace, size_t workspace_bytes,
                    int B, int F, int K, int d, int heads, int W, int TP, int shift, int layout,

@@ -69,11 +69,12 @@ int hwgat_mask_pack(const float* adj, int adj_windows, const float* mask, int n_
 }
 
 size_t hwgat_attn_workspace_bytes(int B, int F, int K, int d, int heads, int dtype, int backward) {
-  (void)heads;
   const size_t n = (size_t)B * F * K;
   if (dtype == HWGAT_F32) return n * 3 * d * sizeof(float) * (backward ? 2 : 1);  // qkv (+ dqkv)
-  // dqkv [n,3d] + Wqkv^T [d,3d]
-  return backward ? (n * 3 * d + (size_t)3 * d * d) * sizeof(__nv_bfloat16) : 0;
+  // forward: scaled weight copy [3d,d] + per-head bias tiles [heads][192 x 16];
+  // backward: dqkv [n,3d] + Wqkv^T [d,3d] + the same two
+  const size_t prep = (size_t)3 * d * d + (size_t)heads * 192 * 16;
+  return ((backward ? n * 3 * d + (size_t)3 * d * d : 0) + prep) * sizeof(__nv_bfloat16);
 }
 
 int hwgat_attn_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, float threshold,

@@ -37,11 +37,19 @@ constexpr int kWStage = 192 * 128;        // 24 KB: q|k|v rows of one head x 64 
 constexpr int kMaxChunks = 8;             // d <= 512
 constexpr int kMaxWStages = 8;
 constexpr int kAccStride = 256;           // TMEM columns between the two accumulators
+// Bias (and the q scale) ride in the GEMM: one extra K=16 MMA step per head, A = a constant [128 x 16] tile whose
+// first two columns are 1, B = a per-head [192 x 16] tile whose first two columns are bf16 hi / lo of the bias
+// (q rows pre-multiplied by 64^-1/2, as are the q rows of the weight copy).  Both tiles use the swizzle-free
+// K-major core-matrix layout.  The attention warps then only pack fp32 -> bf16.
+constexpr int kOnesBytes = kTileTok * 16 * 2;   // 4 KB
+constexpr int kBiasTile = 192 * 16 * 2;         // 6 KB per head
+constexpr int kBiasElems = 192 * 16;
 
 struct TcBars {
   uint64_t x_full[kMaxChunks], x_empty[kMaxChunks];
   uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t bias_full[2], bias_empty[2];
   uint32_t tmem_slot;
 };
 
@@ -174,15 +182,22 @@ HW_DEV void masked_softmax_tc(float (&s)[4][4], const float (&mk)[2][8], float t
 // warp 0 (one lane): TMA producer shared by K2 and K3
 // ---------------------------------------------------------------------------
 HW_DEV void tc_producer(const TileGeom& geo, int heads, int tiles, int S, TcBars* bars, unsigned char* sX,
-                        unsigned char* sW, const CUtensorMap* tmX, const CUtensorMap* tmW) {
+                        unsigned char* sW, unsigned char* sBias, const bf16* __restrict__ bias_tiles,
+                        const CUtensorMap* tmX, const CUtensorMap* tmW) {
   const int d = geo.d, nk = d / 64;
-  int s = 0;
+  int s = 0, it = 0;
   uint32_t wph = 0;
   int tcount = 0;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
     const int tps = geo.f * geo.kgroups;
     const int b = tile / tps, rr = tile - b * tps, fi = rr / geo.kgroups, kg = rr - fi * geo.kgroups;
-    for (int h = 0; h < heads; ++h) {
+    for (int h = 0; h < heads; ++h, ++it) {
+      {  // bias tile of this head into slot it & 1
+        const int slot = it & 1;
+        mbar_wait(&bars->bias_empty[slot], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&bars->bias_full[slot], kBiasTile);
+        bulk_load_1d(sBias + slot * kBiasTile, bias_tiles + (size_t)h * kBiasElems, kBiasTile, &bars->bias_full[slot]);
+      }
       for (int c = 0; c < nk; ++c) {
         if (h == 0) {
           mbar_wait(&bars->x_empty[c], (tcount & 1) ^ 1);
@@ -216,7 +231,7 @@ HW_DEV void tc_producer(const TileGeom& geo, int heads, int tiles, int S, TcBars
 // warp 1 (one lane): tcgen05.mma issuer shared by K2 and K3
 // ---------------------------------------------------------------------------
 HW_DEV void tc_issuer(const TileGeom& geo, int heads, int tiles, int S, TcBars* bars, unsigned char* sX,
-                      unsigned char* sW, uint32_t tmem) {
+                      unsigned char* sW, unsigned char* sOnes, unsigned char* sBias, uint32_t tmem) {
   constexpr uint32_t idesc = umma_idesc_bf16(128, 192);
   const int nk = geo.d / 64;
   int s = 0, it = 0, tcount = 0;
@@ -225,7 +240,12 @@ HW_DEV void tc_issuer(const TileGeom& geo, int heads, int tiles, int S, TcBars* 
     for (int h = 0; h < heads; ++h, ++it) {
       const int buf = it & 1;
       mbar_wait(&bars->acc_empty[buf], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&bars->bias_full[buf], (it >> 1) & 1);
       tc_fence_after();
+      // accumulator = 1 . bias^T  (K = 16 step against the ones tile), then += X . Wh^T
+      umma_bf16(tmem + buf * kAccStride, umma_desc_k_none(smem_u32(sOnes), kTileTok * 16, 128),
+                umma_desc_k_none(smem_u32(sBias + buf * kBiasTile), 192 * 16, 128), idesc, 0);
+      umma_commit(&bars->bias_empty[buf]);
       for (int c = 0; c < nk; ++c) {
         mbar_wait(&bars->w_full[s], wph);
         if (h == 0) mbar_wait(&bars->x_full[c], tcount & 1);
@@ -233,8 +253,7 @@ HW_DEV void tc_issuer(const TileGeom& geo, int heads, int tiles, int S, TcBars* 
         const uint32_t sa = smem_u32(sX + c * kXChunk), sb = smem_u32(sW + s * kWStage);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tmem + buf * kAccStride, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
-                    (c | ks) != 0);
+          umma_bf16(tmem + buf * kAccStride, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc, 1);
         umma_commit(&bars->w_empty[s]);
         if (h == heads - 1) umma_commit(&bars->x_empty[c]);
         if (++s == S) { s = 0; wph ^= 1; }
@@ -245,13 +264,13 @@ HW_DEV void tc_issuer(const TileGeom& geo, int heads, int tiles, int S, TcBars* 
 }
 
 // (defined with the K3a helpers further down)
-HW_DEV void rows_to_blocks(const uint32_t (&r)[32], const float* __restrict__ bias2t, float mul, uint32_t (&f)[4][4]);
+HW_DEV void rows_to_blocks(const uint32_t (&r)[32], uint32_t (&f)[4][4]);
 HW_DEV void mma_rows_x_blocks_T(float (&acc)[4][4], const uint32_t (&a)[4][4], const uint32_t (&m0)[4][4],
                                 const uint32_t (&m1)[4][4]);
 HW_DEV void mma_16x64_k16_blocks(float (&acc)[8][4], const uint32_t (&a)[4], const uint32_t (&f)[4][4]);
 
 struct FwdTcArgs {
-  const float* bias;
+  const bf16* bias_tiles;  // (heads, 192 x 16) core-matrix tiles made by prep_qkv_kernel
   const uint32_t* bits;
   bf16* out;
   float threshold;
@@ -262,9 +281,39 @@ struct FwdTcArgs {
 __global__ void attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                     const FwdTcArgs p);
 
+// Weight copy with the q rows pre-scaled by 64^-1/2 (exact in bf16) and the per-head bias tiles.
+__global__ void prep_qkv_kernel(const bf16* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ wp,
+                                bf16* __restrict__ bias_tiles, int d, int heads) {
+  const long long nw = (long long)3 * d * d, nb = (long long)heads * kBiasElems;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw + nb; i += stride) {
+    if (i < nw) {
+      const float v = __bfloat162float(w[i]);
+      wp[i] = __float2bfloat16(i < (long long)d * d ? v * 0.125f : v);
+    } else {
+      const int j = (int)(i - nw), h = j / kBiasElems, e = j - h * kBiasElems;
+      // e enumerates the tile in memory order: (k>>3)*1536 + (n>>3)*64 + (n&7)*8 + (k&7)
+      const int kc = e / 1536, r = e - kc * 1536, n = (r >> 6) * 8 + ((r >> 3) & 7), k = kc * 8 + (r & 7);
+      float val = 0.f;
+      if (k < 2) {
+        const float full = b[(n >> 6) * d + h * kHd + (n & 63)] * (n < 64 ? 0.125f : 1.f);
+        const float hi = __bfloat162float(__float2bfloat16(full));
+        val = k == 0 ? hi : full - hi;
+      }
+      bias_tiles[j] = __float2bfloat16(val);
+    }
+  }
+}
+
+static int prep_qkv(const AttnArgs& a, bf16* wp, bf16* bias_tiles, cudaStream_t s) {
+  prep_qkv_kernel<<<148, 256, 0, s>>>((const bf16*)a.w_qkv, a.b_qkv, wp, bias_tiles, a.d, a.heads);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 // weight-ring depth: what is left of the 227 KB after the resident X tile, at most 6 stages
 static int w_stages_for(int d) {
-  const int left = 232448 - 1024 - (int)sizeof(TcBars) - (d / 64) * kXChunk;
+  const int left = 232448 - 1024 - (int)sizeof(TcBars) - kOnesBytes - 2 * kBiasTile - (d / 64) * kXChunk;
   const int st = left / kWStage;
   return st > 6 ? 6 : st;
 }
@@ -272,7 +321,7 @@ static int w_stages_for(int d) {
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   const int d = a.d, nk = d / 64;
   const int stages = w_stages_for(d);
-  const int smem_bytes = nk * kXChunk + stages * kWStage + (int)sizeof(TcBars) + 1024;
+  const int smem_bytes = nk * kXChunk + stages * kWStage + kOnesBytes + 2 * kBiasTile + (int)sizeof(TcBars) + 1024;
   static int attr_smem = 0;
   if (smem_bytes > attr_smem) {
     cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -285,9 +334,12 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   } else {
     if ((st = make_tmap_4d(&tmX, a.xn, (uint64_t)d, (uint64_t)a.K, (uint64_t)a.F, (uint64_t)a.B, 16))) return st;
   }
-  if ((st = make_tmap_2d(&tmW, a.w_qkv, (uint64_t)3 * d, (uint64_t)d, 64))) return st;
+  bf16* wp = (bf16*)a.workspace;                 // [3d, d] weight copy, q rows x 64^-1/2
+  bf16* bias_tiles = wp + (size_t)3 * d * d;      // [heads][192 x 16]
+  if ((st = prep_qkv(a, wp, bias_tiles, s))) return st;
+  if ((st = make_tmap_2d(&tmW, wp, (uint64_t)3 * d, (uint64_t)d, 64))) return st;
   FwdTcArgs p;
-  p.bias = a.b_qkv; p.bits = a.bits; p.out = (bf16*)a.out; p.threshold = a.threshold;
+  p.bias_tiles = bias_tiles; p.bits = a.bits; p.out = (bf16*)a.out; p.threshold = a.threshold;
   p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages;
   p.geo = make_geom(a.F, a.K, d, a.shift, a.layout);
   const int grid = p.tiles < 148 ? p.tiles : 148;
@@ -296,17 +348,16 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-// raw 16 x 64 accumulator rows (tcgen05.ld.16x256b.x8 registers) -> (+bias) * mul -> 8x8-block registers
-HW_DEV void rows_to_blocks(const uint32_t (&r)[32], const float* __restrict__ bias2t, float mul, uint32_t (&f)[4][4]) {
+// raw 16 x 64 accumulator rows (tcgen05.ld.16x256b.x8 registers; bias and scale already in the accumulator)
+// -> bf16 8x8-block registers: f[ks][0] = rows g, cols 16ks+2t..  f[ks][1] = rows g+8  f[ks][2], f[ks][3]: cols +8
+HW_DEV void rows_to_blocks(const uint32_t (&r)[32], uint32_t (&f)[4][4]) {
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
       const int nt = 2 * ks + x;
-      const float2 bb = *reinterpret_cast<const float2*>(bias2t + 8 * nt);
-      f[ks][2 * x] = pack_bf16((__uint_as_float(r[4 * nt]) + bb.x) * mul, (__uint_as_float(r[4 * nt + 1]) + bb.y) * mul);
-      f[ks][2 * x + 1] =
-          pack_bf16((__uint_as_float(r[4 * nt + 2]) + bb.x) * mul, (__uint_as_float(r[4 * nt + 3]) + bb.y) * mul);
+      f[ks][2 * x] = pack_bf16(__uint_as_float(r[4 * nt]), __uint_as_float(r[4 * nt + 1]));
+      f[ks][2 * x + 1] = pack_bf16(__uint_as_float(r[4 * nt + 2]), __uint_as_float(r[4 * nt + 3]));
     }
 }
 // acc[16 x 32] += A[16 x 64] . M^T, M (32 rows x 64) given as the block registers of its two 16-row groups:
@@ -416,13 +467,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
   const int d = p.geo.d, nk = d / 64, heads = p.heads, S = p.w_stages;
   unsigned char* sX = smem;
   unsigned char* sW = smem + nk * kXChunk;
-  TcBars* bars = reinterpret_cast<TcBars*>(sW + S * kWStage);
+  unsigned char* sOnes = sW + S * kWStage;
+  unsigned char* sBias = sOnes + kOnesBytes;
+  TcBars* bars = reinterpret_cast<TcBars*>(sBias + 2 * kBiasTile);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ones tile [128 x 16], swizzle-free K-major core matrices: element (row r, col k) at
+  // (k>>3)*2048 + (r>>3)*128 + (r&7)*16 + (k&7)*2 bytes; columns 0 and 1 are 1.0 (bias hi + lo)
+  for (int i = threadIdx.x; i < kOnesBytes / 2; i += blockDim.x) {
+    const int k = ((i >> 10) << 3) | (i & 7);
+    reinterpret_cast<uint16_t*>(sOnes)[i] = k < 2 ? (uint16_t)0x3f80 : (uint16_t)0;
+  }
+  fence_proxy_async();
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxChunks; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], 1); }
     for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->bias_full[i], 1); mbar_init(&bars->bias_empty[i], 1); }
     mbar_fence_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
@@ -435,8 +496,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
 
   if (warp < kFirstEpiWarp) {
     reg_dealloc_donor();
-    if (warp == 0 && lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
-    if (warp == 1 && lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, tmem);
+    if (warp == 0 && lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, sBias, p.bias_tiles, &tmX, &tmW);
+    if (warp == 1 && lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, sOnes, sBias, tmem);
   } else {
     reg_alloc_epi();
     const int win = warp & 3;                      // TMEM lane quarter == window of the tile
@@ -456,9 +517,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
         if ((it & 1) != set) continue;
         mbar_wait(&bars->acc_full[set], (it >> 1) & 1);
         tc_fence_after();
-        const float* bq = p.bias + h * kHd + 2 * t;
-        const float* bk = bq + d;
-        const float* bv = bk + d;
         uint32_t qa0[4][4], qa1[4][4], kb0[4][4], kb1[4][4];
         {
           uint32_t r0[32], r1[32], r2[32], r3[32];
@@ -467,10 +525,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
           tmem_ld_16x256b_x8(tb + 64, r2);
           tmem_ld_16x256b_x8(tb + (16u << 16) + 64, r3);
           tmem_wait_regs(r0); tmem_wait_regs(r1); tmem_wait_regs(r2); tmem_wait_regs(r3);
-          rows_to_blocks(r0, bq, 0.125f, qa0);
-          rows_to_blocks(r1, bq, 0.125f, qa1);
-          rows_to_blocks(r2, bk, 1.f, kb0);
-          rows_to_blocks(r3, bk, 1.f, kb1);
+          rows_to_blocks(r0, qa0);
+          rows_to_blocks(r1, qa1);
+          rows_to_blocks(r2, kb0);
+          rows_to_blocks(r3, kb1);
         }
         uint32_t v0[32], v1[32];
         tmem_ld_16x256b_x8(tb + 128, v0);
@@ -495,9 +553,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
         zero8x4(o1);
         {
           uint32_t vb[4][4];
-          rows_to_blocks(v0, bv, 1.f, vb);
+          rows_to_blocks(v0, vb);
           mma_2x16x64_k16_blocks(o0, o1, pa0[0], pa1[0], vb);
-          rows_to_blocks(v1, bv, 1.f, vb);
+          rows_to_blocks(v1, vb);
           mma_2x16x64_k16_blocks(o0, o1, pa0[1], pa1[1], vb);
         }
         store_rows_16x64(o0, 1.f, p.out + orow[0] + h * kHd, p.out + orow[1] + h * kHd, t);
@@ -511,7 +569,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
 }
 
 struct BwdTcArgs {
-  const float* bias;
+  const bf16* bias_tiles;
   const uint32_t* bits;
   const bf16* d_out;
   bf16* dqkv;
@@ -580,13 +638,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
   const int d = p.geo.d, nk = d / 64, heads = p.heads, S = p.w_stages;
   unsigned char* sX = smem;
   unsigned char* sW = smem + nk * kXChunk;
-  TcBars* bars = reinterpret_cast<TcBars*>(sW + S * kWStage);
+  unsigned char* sOnes = sW + S * kWStage;
+  unsigned char* sBias = sOnes + kOnesBytes;
+  TcBars* bars = reinterpret_cast<TcBars*>(sBias + 2 * kBiasTile);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ones tile [128 x 16], swizzle-free K-major core matrices: element (row r, col k) at
+  // (k>>3)*2048 + (r>>3)*128 + (r&7)*16 + (k&7)*2 bytes; columns 0 and 1 are 1.0 (bias hi + lo)
+  for (int i = threadIdx.x; i < kOnesBytes / 2; i += blockDim.x) {
+    const int k = ((i >> 10) << 3) | (i & 7);
+    reinterpret_cast<uint16_t*>(sOnes)[i] = k < 2 ? (uint16_t)0x3f80 : (uint16_t)0;
+  }
+  fence_proxy_async();
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxChunks; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], 1); }
     for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->bias_full[i], 1); mbar_init(&bars->bias_empty[i], 1); }
     mbar_fence_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
@@ -599,8 +667,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
 
   if (warp < kFirstEpiWarp) {
     reg_dealloc_donor();
-    if (warp == 0 && lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, &tmX, &tmW);
-    if (warp == 1 && lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, tmem);
+    if (warp == 0 && lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, sBias, p.bias_tiles, &tmX, &tmW);
+    if (warp == 1 && lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, sOnes, sBias, tmem);
   } else {
     reg_alloc_epi();
     const int win = warp & 3;
@@ -625,9 +693,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
         }
         mbar_wait(&bars->acc_full[set], (it >> 1) & 1);
         tc_fence_after();
-        const float* bq = p.bias + h * kHd + 2 * t;
-        const float* bk = bq + d;
-        const float* bv = bk + d;
         uint32_t qa0[4][4], qa1[4][4], kb0[4][4], kb1[4][4];
         {
           uint32_t r0[32], r1[32], r2[32], r3[32];
@@ -636,10 +701,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
           tmem_ld_16x256b_x8(tb + 64, r2);
           tmem_ld_16x256b_x8(tb + (16u << 16) + 64, r3);
           tmem_wait_regs(r0); tmem_wait_regs(r1); tmem_wait_regs(r2); tmem_wait_regs(r3);
-          rows_to_blocks(r0, bq, 0.125f, qa0);
-          rows_to_blocks(r1, bq, 0.125f, qa1);
-          rows_to_blocks(r2, bk, 1.f, kb0);
-          rows_to_blocks(r3, bk, 1.f, kb1);
+          rows_to_blocks(r0, qa0);
+          rows_to_blocks(r1, qa1);
+          rows_to_blocks(r2, kb0);
+          rows_to_blocks(r3, kb1);
         }
         uint32_t v0[32], v1[32];
         tmem_ld_16x256b_x8(tb + 128, v0);
@@ -672,8 +737,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
         zero4x4(s1);
         {
           uint32_t vb0[4][4], vb1[4][4];
-          rows_to_blocks(v0, bv, 1.f, vb0);
-          rows_to_blocks(v1, bv, 1.f, vb1);
+          rows_to_blocks(v0, vb0);
+          rows_to_blocks(v1, vb1);
           mma_rows_x_blocks_T(s0, ga0, vb0, vb1);
           mma_rows_x_blocks_T(s1, ga1, vb0, vb1);
         }
@@ -757,7 +822,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
 int attn_bwd_tc(const AttnArgs& a, bf16* dqkv, cudaStream_t s) {
   const int d = a.d, nk = d / 64;
   const int stages = w_stages_for(d);
-  const int smem_bytes = nk * kXChunk + stages * kWStage + (int)sizeof(TcBars) + 1024;
+  const int smem_bytes = nk * kXChunk + stages * kWStage + kOnesBytes + 2 * kBiasTile + (int)sizeof(TcBars) + 1024;
   static int attr_smem = 0;
   if (smem_bytes > attr_smem) {
     cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -770,9 +835,12 @@ int attn_bwd_tc(const AttnArgs& a, bf16* dqkv, cudaStream_t s) {
   } else {
     if ((st = make_tmap_4d(&tmX, a.xn, (uint64_t)d, (uint64_t)a.K, (uint64_t)a.F, (uint64_t)a.B, 16))) return st;
   }
-  if ((st = make_tmap_2d(&tmW, a.w_qkv, (uint64_t)3 * d, (uint64_t)d, 64))) return st;
+  bf16* wp = dqkv + (size_t)a.tokens() * 3 * d + (size_t)3 * d * d;   // behind dQKV and Wqkv^T
+  bf16* bias_tiles = wp + (size_t)3 * d * d;
+  if ((st = prep_qkv(a, wp, bias_tiles, s))) return st;
+  if ((st = make_tmap_2d(&tmW, wp, (uint64_t)3 * d, (uint64_t)d, 64))) return st;
   BwdTcArgs p;
-  p.bias = a.b_qkv; p.bits = a.bits; p.d_out = (const bf16*)a.d_out; p.dqkv = dqkv; p.threshold = a.threshold;
+  p.bias_tiles = bias_tiles; p.bits = a.bits; p.d_out = (const bf16*)a.d_out; p.dqkv = dqkv; p.threshold = a.threshold;
   p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages;
   p.geo = make_geom(a.F, a.K, d, a.shift, a.layout);
   const int grid = p.tiles < 148 ? p.tiles : 148;

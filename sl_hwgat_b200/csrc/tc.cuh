@@ -82,6 +82,18 @@ HW_DEV uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// K-major operand without swizzle ("interleaved" canonical layout): 8-row x 16-byte core matrices (128 contiguous
+// bytes each); `lbo` = byte distance between the two core matrices of one K=16 step, `sbo` = between 8-row groups.
+HW_DEV uint64_t umma_desc_k_none(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes % 16 == 0, both addresses 16-byte aligned)
+HW_DEV void bulk_load_1d(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                   "r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32 (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_major = false, bool b_mn_major = false) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |

@@ -29,8 +29,8 @@ def test_library_exports_every_declared_symbol():
     assert b"no fallback" in lib.hwgat_error_string(1002)
     # size query is pure host arithmetic: qkv + dqkv in fp32, dqkv only in bf16
     assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.F32, 1) == 2 * 4 * 64 * 384 * 4 * 2
-    assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.BF16, 0) == 0
-    assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.BF16, 1) == (2 * 4 * 64 * 384 + 384 * 128) * 2
+    assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.BF16, 0) == (384 * 128 + 2 * 192 * 16) * 2
+    assert lib.hwgat_attn_workspace_bytes(2, 4, 64, 128, 2, _lib.BF16, 1) == (2 * 4 * 64 * 384 + 2 * 384 * 128 + 2 * 192 * 16) * 2
 
 
 def test_argument_errors_without_gpu():
