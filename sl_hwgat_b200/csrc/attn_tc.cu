@@ -125,13 +125,14 @@ HW_DEV void softmax_row_exact(float (&v)[8], const float (&lv)[8], bool& dead) {
   for (int i = 0; i < 8; ++i) v[i] *= inv;
 }
 
+template <bool kTrain>
 HW_DEV void masked_softmax_tc(float (&s)[4][4], const float (&mk)[2][8], float threshold, bool (&dead)[2]) {
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     float v[8];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) { v[2 * nt] = s[nt][2 * r]; v[2 * nt + 1] = s[nt][2 * r + 1]; }
-    if (threshold >= 0.f) {
+    if (kTrain) {
       float m0 = v[0];
 #pragma unroll
       for (int i = 1; i < 8; ++i) m0 = fmaxf(m0, v[i]);
@@ -278,8 +279,9 @@ struct FwdTcArgs {
   TileGeom geo;
 };
 
+template <bool kTrain>
 __global__ void attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                                    const FwdTcArgs p);
+                                   const FwdTcArgs p);
 
 // Weight copy with the q rows pre-scaled by 64^-1/2 (exact in bf16) and the per-head bias tiles.
 __global__ void prep_qkv_kernel(const bf16* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ wp,
@@ -324,7 +326,8 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   const int smem_bytes = nk * kXChunk + stages * kWStage + kOnesBytes + 2 * kBiasTile + (int)sizeof(TcBars) + 1024;
   static int attr_smem = 0;
   if (smem_bytes > attr_smem) {
-    cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     attr_smem = smem_bytes;
   }
   CUtensorMap tmX, tmW;
@@ -343,7 +346,10 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages;
   p.geo = make_geom(a.F, a.K, d, a.shift, a.layout);
   const int grid = p.tiles < 148 ? p.tiles : 148;
-  attn_fwd_tc_kernel<<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
+  if (a.threshold >= 0.f)   // training: threshold drop (HWGATE.py:94-100) compiled in
+    attn_fwd_tc_kernel<true><<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
+  else
+    attn_fwd_tc_kernel<false><<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -459,6 +465,7 @@ HW_DEV void probs_to_afrag(uint32_t (&pa)[2][4], const float (&s)[4][4]) {
   }
 }
 
+template <bool kTrain>
 __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                      const __grid_constant__ CUtensorMap tmW,
                                                                      const FwdTcArgs p) {
@@ -539,8 +546,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
         mma_rows_x_blocks_T(s0, qa0, kb0, kb1);
         mma_rows_x_blocks_T(s1, qa1, kb0, kb1);
         bool dead[2];
-        masked_softmax_tc(s0, mk0, p.threshold, dead);
-        masked_softmax_tc(s1, mk1, p.threshold, dead);
+        masked_softmax_tc<kTrain>(s0, mk0, p.threshold, dead);
+        masked_softmax_tc<kTrain>(s1, mk1, p.threshold, dead);
         uint32_t pa0[2][4], pa1[2][4];
         probs_to_afrag(pa0, s0);
         probs_to_afrag(pa1, s1);
@@ -630,6 +637,7 @@ HW_DEV void load_rows_as_blocks_global(const bf16* __restrict__ g0, const bf16* 
 
 // K3a, second generation: one warp per window, alternate heads per warp set (see attn_fwd_tc_kernel).
 // Everything of a window's backward stays inside one warp: no mailbox, no pair barrier.
+template <bool kTrain>
 __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                      const __grid_constant__ CUtensorMap tmW,
                                                                      const BwdTcArgs p) {
@@ -695,20 +703,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
         tc_fence_after();
         uint32_t qa0[4][4], qa1[4][4], kb0[4][4], kb1[4][4];
         {
-          uint32_t r0[32], r1[32], r2[32], r3[32];
+          uint32_t r0[32], r1[32];
           tmem_ld_16x256b_x8(tb, r0);
           tmem_ld_16x256b_x8(tb + (16u << 16), r1);
-          tmem_ld_16x256b_x8(tb + 64, r2);
-          tmem_ld_16x256b_x8(tb + (16u << 16) + 64, r3);
-          tmem_wait_regs(r0); tmem_wait_regs(r1); tmem_wait_regs(r2); tmem_wait_regs(r3);
+          tmem_wait_regs(r0); tmem_wait_regs(r1);
           rows_to_blocks(r0, qa0);
           rows_to_blocks(r1, qa1);
-          rows_to_blocks(r2, kb0);
-          rows_to_blocks(r3, kb1);
+          tmem_ld_16x256b_x8(tb + 64, r0);
+          tmem_ld_16x256b_x8(tb + (16u << 16) + 64, r1);
+          tmem_wait_regs(r0); tmem_wait_regs(r1);
+          rows_to_blocks(r0, kb0);
+          rows_to_blocks(r1, kb1);
         }
-        uint32_t v0[32], v1[32];
-        tmem_ld_16x256b_x8(tb + 128, v0);
-        tmem_ld_16x256b_x8(tb + (16u << 16) + 128, v1);
         // dO rows (L2-resident thanks to the prefetch): loaded here, after the 128 raw q/k registers are dead
         uint32_t ga0[4][4], ga1[4][4];
         load_rows_as_blocks_global(p.d_out + tr[0] * d + h * kHd, p.d_out + tr[1] * d + h * kHd, t, ga0);
@@ -723,10 +729,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
         {
           float mk[2][8];
           expand_row_masks(cm[0], cm[1], mk);
-          masked_softmax_tc(p0, mk, p.threshold, dead0);
+          masked_softmax_tc<kTrain>(p0, mk, p.threshold, dead0);
           expand_row_masks(cm[2], cm[3], mk);
-          masked_softmax_tc(p1, mk, p.threshold, dead1);
+          masked_softmax_tc<kTrain>(p1, mk, p.threshold, dead1);
         }
+        uint32_t v0[32], v1[32];   // (issued after the softmax: 64 more live registers under it made the kernel spill)
+        tmem_ld_16x256b_x8(tb + 128, v0);
+        tmem_ld_16x256b_x8(tb + (16u << 16) + 128, v1);
         tmem_wait_regs(v0); tmem_wait_regs(v1);
         tc_fence_before();
         __syncwarp();
@@ -749,23 +758,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
         tiles_to_blocks(pb1, p1);
         tiles_to_blocks(db0, s0);
         tiles_to_blocks(db1, s1);
-        // ---- dq = dS k * scale (both query m tiles share the transposed k blocks)
+        // ---- dq = dS k * scale.  This is the point of highest register pressure (q, k, dO, P and dS blocks are all
+        // live), so the two query m tiles go one after the other (32 accumulator registers instead of 64).
         {
-          float dq0[8][4], dq1[8][4];
-          zero8x4(dq0);
-          zero8x4(dq1);
+          float dq[8][4];
+          zero8x4(dq);
           {
             const uint32_t a0[4] = {db0[0][0], db0[1][0], db0[0][1], db0[1][1]};
-            const uint32_t a1[4] = {db1[0][0], db1[1][0], db1[0][1], db1[1][1]};
-            mma_2x16x64_k16_blocks(dq0, dq1, a0, a1, kb0);
+            mma_16x64_k16_blocks(dq, a0, kb0);
+            const uint32_t a1[4] = {db0[0][2], db0[1][2], db0[0][3], db0[1][3]};
+            mma_16x64_k16_blocks(dq, a1, kb1);
           }
+          store_rows_16x64(dq, 0.125f, p.dqkv + tr[0] * d3 + h * kHd, p.dqkv + tr[1] * d3 + h * kHd, t);
+          zero8x4(dq);
           {
-            const uint32_t a0[4] = {db0[0][2], db0[1][2], db0[0][3], db0[1][3]};
+            const uint32_t a0[4] = {db1[0][0], db1[1][0], db1[0][1], db1[1][1]};
+            mma_16x64_k16_blocks(dq, a0, kb0);
             const uint32_t a1[4] = {db1[0][2], db1[1][2], db1[0][3], db1[1][3]};
-            mma_2x16x64_k16_blocks(dq0, dq1, a0, a1, kb1);
+            mma_16x64_k16_blocks(dq, a1, kb1);
           }
-          store_rows_16x64(dq0, 0.125f, p.dqkv + tr[0] * d3 + h * kHd, p.dqkv + tr[1] * d3 + h * kHd, t);
-          store_rows_16x64(dq1, 0.125f, p.dqkv + tr[2] * d3 + h * kHd, p.dqkv + tr[3] * d3 + h * kHd, t);
+          store_rows_16x64(dq, 0.125f, p.dqkv + tr[2] * d3 + h * kHd, p.dqkv + tr[3] * d3 + h * kHd, t);
         }
         // ---- dv = P^T dO : key m tiles jt = 0,1; k steps = the two query groups
         {
@@ -825,7 +837,8 @@ int attn_bwd_tc(const AttnArgs& a, bf16* dqkv, cudaStream_t s) {
   const int smem_bytes = nk * kXChunk + stages * kWStage + kOnesBytes + 2 * kBiasTile + (int)sizeof(TcBars) + 1024;
   static int attr_smem = 0;
   if (smem_bytes > attr_smem) {
-    cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     attr_smem = smem_bytes;
   }
   CUtensorMap tmX, tmW;
@@ -844,7 +857,10 @@ int attn_bwd_tc(const AttnArgs& a, bf16* dqkv, cudaStream_t s) {
   p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages;
   p.geo = make_geom(a.F, a.K, d, a.shift, a.layout);
   const int grid = p.tiles < 148 ? p.tiles : 148;
-  attn_bwd_tc_kernel<<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
+  if (a.threshold >= 0.f)
+    attn_bwd_tc_kernel<true><<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
+  else
+    attn_bwd_tc_kernel<false><<<grid, kTcThreads, smem_bytes, s>>>(tmX, tmW, p);
   count_launch();
   return (int)cudaGetLastError();
 }
