@@ -537,9 +537,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
           rows_to_blocks(r2, kb0);
           rows_to_blocks(r3, kb1);
         }
-        uint32_t v0[32], v1[32];
-        tmem_ld_16x256b_x8(tb + 128, v0);
-        tmem_ld_16x256b_x8(tb + (16u << 16) + 128, v1);
+        // v is read right away as well and kept as bf16 blocks (32 registers) under the softmax: the accumulator goes
+        // back to the MMA warp BEFORE the attention math.  (Releasing it after the softmax held it for ~60 % of the
+        // attention phase; at d=512 the MMA of head h+2 then waited ~2300 cycles per head: tensor pipe 54 % busy.)
+        uint32_t vb0[4][4], vb1[4][4];
+        {
+          uint32_t v0[32], v1[32];
+          tmem_ld_16x256b_x8(tb + 128, v0);
+          tmem_ld_16x256b_x8(tb + (16u << 16) + 128, v1);
+          tmem_wait_regs(v0); tmem_wait_regs(v1);
+          rows_to_blocks(v0, vb0);
+          rows_to_blocks(v1, vb1);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[set]);  // last TMEM read of this head
         float s0[4][4], s1[4][4];
         zero4x4(s0);
         zero4x4(s1);
@@ -551,20 +563,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
         uint32_t pa0[2][4], pa1[2][4];
         probs_to_afrag(pa0, s0);
         probs_to_afrag(pa1, s1);
-        tmem_wait_regs(v0); tmem_wait_regs(v1);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->acc_empty[set]);  // last TMEM read of this head
         float o0[8][4], o1[8][4];
         zero8x4(o0);
         zero8x4(o1);
-        {
-          uint32_t vb[4][4];
-          rows_to_blocks(v0, vb);
-          mma_2x16x64_k16_blocks(o0, o1, pa0[0], pa1[0], vb);
-          rows_to_blocks(v1, vb);
-          mma_2x16x64_k16_blocks(o0, o1, pa0[1], pa1[1], vb);
-        }
+        mma_2x16x64_k16_blocks(o0, o1, pa0[0], pa1[0], vb0);
+        mma_2x16x64_k16_blocks(o0, o1, pa0[1], pa1[1], vb1);
         store_rows_16x64(o0, 1.f, p.out + orow[0] + h * kHd, p.out + orow[1] + h * kHd, t);
         store_rows_16x64(o1, 1.f, p.out + orow[2] + h * kHd, p.out + orow[3] + h * kHd, t);
       }
