@@ -108,7 +108,7 @@ class KernelTimer:
         self.orig = {}
         for name in ("hwgat_attn_fwd", "hwgat_attn_bwd", "hwgat_merge_fwd", "hwgat_merge_bwd", "hwgat_ln_fwd",
                      "hwgat_ln_bwd", "hwgat_bda_ln_fwd", "hwgat_bda_ln_bwd", "hwgat_bias_gelu_dropout_fwd",
-                     "hwgat_bias_gelu_dropout_bwd"):
+                     "hwgat_bias_gelu_dropout_bwd", "hwgat_ffn_fwd", "hwgat_ffn_bwd"):
             fn = getattr(lib, name)
             self.orig[name] = fn
             setattr(lib, name, self._wrap(name, fn))
@@ -122,6 +122,8 @@ class KernelTimer:
         "hwgat_bda_ln_bwd": lambda a: (int(a[12]), int(a[11]), bool(a[5])),
         "hwgat_bias_gelu_dropout_fwd": lambda a: (int(a[4]), int(a[3])),
         "hwgat_bias_gelu_dropout_bwd": lambda a: (int(a[6]), int(a[5])),
+        "hwgat_ffn_fwd": lambda a: (int(a[8]), int(a[7]), int(a[9])),
+        "hwgat_ffn_bwd": lambda a: (int(a[13]), int(a[12]), int(a[14])),
     }
     # algorithmic HBM bytes per element of the bandwidth-bound kernels
     BYTES_PER_ELEM = {"hwgat_ln_fwd": 6, "hwgat_ln_bwd": 14, "hwgat_bias_gelu_dropout_fwd": 4,
@@ -162,6 +164,14 @@ class KernelTimer:
                 out.append({"kernel": ("K3 " if name.endswith("bwd") else "K2 ") + f"{name} d={d}", "bound": "tensor",
                             "calls_per_step": cnt / steps, "avg_ms": avg, "alg_flops": fl,
                             "achieved": fl / (avg * 1e-3) / 1e12, "unit": "TFLOP/s", "total_ms": ms})
+                continue
+            if "ffn" in name:
+                # FeedForward GEMMs: fc1 + fc2 forward = 4 n d hidden FLOP, backward twice that
+                n_rows, hidden = key[1], key[2]
+                fl = 4.0 * n_rows * d * hidden * (2 if name.endswith("bwd") else 1)
+                out.append({"kernel": f"K10 {name} d={d}", "bound": "tensor", "calls_per_step": cnt / steps,
+                            "avg_ms": avg, "alg_flops": fl, "achieved": fl / (avg * 1e-3) / 1e12, "unit": "TFLOP/s",
+                            "total_ms": ms, "attention": False})
                 continue
             if "merge" in name:
                 label, by = "K4 " + f"{name} d={d}", merge_bytes(B, {128: 0, 256: 1}[d], 4)  # fp32 residual stream
@@ -350,7 +360,7 @@ def main():
     if rank == 0:
         pk = peaks()
         kern = timer.table(B, args.steps)
-        attn = [k for k in kern if k["bound"] == "tensor"]
+        attn = [k for k in kern if k["bound"] == "tensor" and k.pop("attention", True)]
         top = max(attn, key=lambda k: k["total_ms"]) if attn else None
         roof = None
         if top is not None:

@@ -158,6 +158,23 @@ int hwgat_bias_gelu_dropout_bwd(const void* u0, const float* bias, const void* d
                                 long long n, int cols, float p, unsigned long long seed, unsigned long long offset,
                                 hwgat_stream_t stream);
 
+/* K10: the FeedForward of a block without its last bias / dropout (those belong to K6), on tcgen05:
+ *   act(bf16, (n, hidden)) = dropout_p(gelu(h . W1^T + b1))   bias + exact erf GELU + dropout in the GEMM epilogue
+ *   gp (bf16, (n, hidden)) = d act / d (h . W1^T + b1)         dropout mask and 1/(1-p) folded in; NULL = do not save
+ *   v0 (bf16, (n, d))      = act . W2^T
+ * Replaces ff.fc1 + ff.act + ff.drop + ff.fc2's matmul (HWGATE.py:130-134).  h: (n, d) bf16, W1: (hidden, d) bf16,
+ * b1: (hidden) fp32 or NULL, W2: (d, hidden) bf16.  n % 128 == 0, d % 128 == 0, hidden % 128 == 0.               */
+int hwgat_ffn_fwd(const void* h, const void* w1, const float* b1, const void* w2, void* act, void* gp, void* v0,
+                  long long n, int d, int hidden, float p, unsigned long long seed, unsigned long long offset,
+                  hwgat_stream_t stream);
+/* K10': autograd of the above for dv0 (bf16, (n, d)): dh (bf16, (n, d)), dw1 (fp32, (hidden, d)), db1 (fp32,
+ * (hidden)), dw2 (fp32, (d, hidden)), all overwritten.  du0 = (dv0 . W2) o gp is formed in the epilogue of its GEMM.
+ * workspace: hwgat_ffn_bwd_workspace_bytes(n, d, hidden) bytes.                                                */
+size_t hwgat_ffn_bwd_workspace_bytes(long long n, int d, int hidden);
+int hwgat_ffn_bwd(const void* dv0, const void* h, const void* act, const void* gp, const void* w1, const void* w2,
+                  void* dh, float* dw1, float* db1, float* dw2, void* workspace, size_t workspace_bytes, long long n,
+                  int d, int hidden, hwgat_stream_t stream);
+
 /* ---- model head and tail ----------------------------------------------- */
 
 /* K8: out(fp32, (n, E)) = dropout_p([sin(2 pi x.Bm^T), cos(2 pi x.Bm^T)] + pe[frame]); x: (n, C) fp32 keypoints,
@@ -177,6 +194,8 @@ int hwgat_ln_pool_bwd(const float* g, const float* x, const float* mean, const f
 /* Diagnostic: the plain bf16 GEMM K3 uses for d_xn, C[M,N] = A[M,K] . Bt[N,K]^T (fp32 accumulate,
  * TMA + tcgen05).  M % 128 == 0, N % 128 == 0, K % 64 == 0; all row-major bf16 device pointers. */
 int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream);
+/* Diagnostic: the same product through K10's GEMM (eight epilogue warps, plain bf16 epilogue). */
+int hwgat_debug_gemm_nt_epi(const void* A, const void* Bt, void* C, long long M, int N, int K, hwgat_stream_t stream);
 /* Diagnostic: the GEMM K3 uses for d_w and d_b: C[M,N] (fp32) = A[Kd,M]^T . B[Kd,N], colsum[M] = column
  * sums of A.  M % 128 == 0, N % 128 == 0, Kd % 64 == 0; A, B bf16 row-major device pointers. */
 int hwgat_debug_gemm_tn(const void* A, const void* B, float* C, float* colsum, int M, int N, long long Kd,

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libhwgat_b200.so")
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # name -> (restype, argtypes); must list every symbol of include/hwgat_b200.h
 SIGNATURES = {
@@ -42,7 +42,12 @@ SIGNATURES = {
                                                  c_ulonglong, c_void_p]),
     "hwgat_ln_pool_fwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_float, c_void_p]),
     "hwgat_ln_pool_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p]),
+    "hwgat_ffn_fwd": (c_int, [c_void_p] * 7 + [c_longlong, c_int, c_int, c_float, c_ulonglong, c_ulonglong,
+                               c_void_p]),
+    "hwgat_ffn_bwd_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int]),
+    "hwgat_ffn_bwd": (c_int, [c_void_p] * 11 + [c_size_t, c_longlong, c_int, c_int, c_void_p]),
     "hwgat_debug_gemm_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "hwgat_debug_gemm_nt_epi": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
     "hwgat_debug_gemm_tn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
     "hwgat_merge_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     "hwgat_merge_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),

@@ -27,7 +27,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 5; }
+int hwgat_version(void) { return 6; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -208,6 +208,54 @@ int hwgat_bias_gelu_dropout_bwd(const void* u0, const float* bias, const void* d
                                   n, cols, p, seed, offset, true, (cudaStream_t)stream);
 }
 
+static int check_ffn(long long n, int d, int hidden) {
+  if (n < 0 || d <= 0 || hidden <= 0) return HWGAT_ERR_SHAPE;
+  if (n % 128 || d % 128 || hidden % 128 || n > 0x7fffffffLL) return HWGAT_ERR_UNSUPPORTED;
+  return HWGAT_OK;
+}
+
+int hwgat_ffn_fwd(const void* h, const void* w1, const float* b1, const void* w2, void* act, void* gp, void* v0,
+                  long long n, int d, int hidden, float p, unsigned long long seed, unsigned long long offset,
+                  hwgat_stream_t stream) {
+  int st = check_ffn(n, d, hidden);
+  if (st) return st;
+  if (bad_p(p)) return HWGAT_ERR_SHAPE;
+  if (n == 0) return HWGAT_OK;
+  if (!h || !w1 || !w2 || !act || !v0) return HWGAT_ERR_NULL;
+  if (misaligned(h) || misaligned(w1) || misaligned(b1) || misaligned(w2) || misaligned(act) || misaligned(gp) ||
+      misaligned(v0))
+    return HWGAT_ERR_ALIGN;
+  return ffn_fwd((const __nv_bfloat16*)h, (const __nv_bfloat16*)w1, b1, (const __nv_bfloat16*)w2, (__nv_bfloat16*)act,
+                 (__nv_bfloat16*)gp, (__nv_bfloat16*)v0, n, d, hidden, p, seed, offset, (cudaStream_t)stream);
+}
+
+size_t hwgat_ffn_bwd_workspace_bytes(long long n, int d, int hidden) {
+  if (check_ffn(n, d, hidden)) return 0;
+  return ffn_bwd_workspace_bytes(n, d, hidden);
+}
+
+int hwgat_ffn_bwd(const void* dv0, const void* h, const void* act, const void* gp, const void* w1, const void* w2,
+                  void* dh, float* dw1, float* db1, float* dw2, void* workspace, size_t workspace_bytes, long long n,
+                  int d, int hidden, hwgat_stream_t stream) {
+  int st = check_ffn(n, d, hidden);
+  if (st) return st;
+  if (!dw1 || !db1 || !dw2) return HWGAT_ERR_NULL;
+  if (n == 0) {  // empty batch: parameter gradients are zero
+    cudaMemsetAsync(dw1, 0, sizeof(float) * (size_t)hidden * d, (cudaStream_t)stream);
+    cudaMemsetAsync(dw2, 0, sizeof(float) * (size_t)hidden * d, (cudaStream_t)stream);
+    cudaMemsetAsync(db1, 0, sizeof(float) * hidden, (cudaStream_t)stream);
+    return (int)cudaGetLastError();
+  }
+  if (!dv0 || !h || !act || !gp || !w1 || !w2 || !dh) return HWGAT_ERR_NULL;
+  if (misaligned(dv0) || misaligned(h) || misaligned(act) || misaligned(gp) || misaligned(w1) || misaligned(w2) ||
+      misaligned(dh) || misaligned(dw1) || misaligned(dw2) || misaligned(workspace))
+    return HWGAT_ERR_ALIGN;
+  if (!workspace || workspace_bytes < ffn_bwd_workspace_bytes(n, d, hidden)) return HWGAT_ERR_WORKSPACE;
+  return ffn_bwd((const __nv_bfloat16*)dv0, (const __nv_bfloat16*)h, (const __nv_bfloat16*)act,
+                 (const __nv_bfloat16*)gp, (const __nv_bfloat16*)w1, (const __nv_bfloat16*)w2, (__nv_bfloat16*)dh, dw1,
+                 db1, dw2, workspace, n, d, hidden, (cudaStream_t)stream);
+}
+
 int hwgat_embed_fwd(const float* x, const float* Bm, const float* pe, float* out, long long n, int C, int E, int K,
                     int T, float p, unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
   if (n < 0 || C <= 0 || E <= 0 || K <= 0 || T <= 0 || bad_p(p)) return HWGAT_ERR_SHAPE;
@@ -244,6 +292,14 @@ int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, in
   if (M <= 0 || N <= 0 || K <= 0) return HWGAT_ERR_SHAPE;
   return gemm_tc_nt((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bt, (__nv_bfloat16*)C, M, N, K,
                     (cudaStream_t)stream);
+}
+
+int hwgat_debug_gemm_nt_epi(const void* A, const void* Bt, void* C, long long M, int N, int K, hwgat_stream_t stream) {
+  if (!A || !Bt || !C) return HWGAT_ERR_NULL;
+  if (misaligned(A) || misaligned(Bt) || misaligned(C)) return HWGAT_ERR_ALIGN;
+  if (M <= 0 || N <= 0 || K <= 0) return HWGAT_ERR_SHAPE;
+  return gemm_tc_nt_epi_none((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bt, (__nv_bfloat16*)C, M, N, K,
+                             (cudaStream_t)stream);
 }
 
 int hwgat_debug_gemm_tn(const void* A, const void* B, float* C, float* colsum, int M, int N, long long Kd,

@@ -882,7 +882,7 @@ int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s) {
   // d_xn[n, d] = dQKV[n, 3d] . Wqkv[3d, d]  (against Wqkv^T so that both operands are K-major)
   bf16* wt = dqkv + n * d3;
   if ((st = transpose_bf16((const bf16*)a.w_qkv, wt, d3, d, s))) return st;
-  if ((st = gemm_tc_nt(dqkv, wt, (bf16*)a.d_xn, (int)n, d, d3, s))) return st;
+  if ((st = gemm_tc_nt_epi_none(dqkv, wt, (bf16*)a.d_xn, n, d, d3, s))) return st;   // K10's GEMM (32-byte stores)
   // d_w[3d, d] = dQKV^T . xn ; d_b = column sums of dQKV (same kernel)
   return gemm_tc_tn(dqkv, (const bf16*)a.xn, a.d_w, a.d_b, d3, d, n, s);
 }

@@ -91,6 +91,19 @@ HW_DEV void st_stream16(void* p, const int4& v) {
   asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 
+// 32-byte (one full sector) global access, sm_100+: a thread that owns a whole row segment writes full sectors
+// (16-byte stores of row-per-thread epilogues hit every sector twice and halve the L2 write rate)
+HW_DEV void st_global32(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+HW_DEV void ld_global32(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
 // ---- launchers implemented in the .cu files --------------------------------
 int launch_adjacency(const int32_t* edges, int n_edges, int nW, int W, int TP, float* adj, cudaStream_t s);
 int launch_mask_bits(const float* adj, int nW, int W, int TP, int F, int shift, uint32_t* bits, cudaStream_t s);
@@ -140,5 +153,14 @@ int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* Bt, __nv_bfloat16* C
 int gemm_tc_tn(const __nv_bfloat16* A, const __nv_bfloat16* Bm, float* C, float* colsum, int M, int N, long long Kd,
                cudaStream_t s);
 int transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int R, int Cc, cudaStream_t s);
+int gemm_tc_nt_epi_none(const __nv_bfloat16* A, const __nv_bfloat16* Bt, __nv_bfloat16* C, long long M, int N, int K,
+                        cudaStream_t s);
+int ffn_fwd(const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1, const __nv_bfloat16* w2,
+            __nv_bfloat16* act, __nv_bfloat16* gp, __nv_bfloat16* v0, long long n, int d, int hidden, float p,
+            unsigned long long seed, unsigned long long offset, cudaStream_t s);
+size_t ffn_bwd_workspace_bytes(long long n, int d, int hidden);
+int ffn_bwd(const __nv_bfloat16* dv0, const __nv_bfloat16* h, const __nv_bfloat16* act, const __nv_bfloat16* gp,
+            const __nv_bfloat16* w1, const __nv_bfloat16* w2, __nv_bfloat16* dh, float* dw1, float* db1, float* dw2,
+            void* workspace, long long n, int d, int hidden, cudaStream_t s);
 
 }  // namespace hwgat

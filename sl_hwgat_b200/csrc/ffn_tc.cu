@@ -1,0 +1,290 @@
+// K10: the FeedForward of a block (HWGATE.py:120-136) on tcgen05, bf16 / autocast path.
+//
+//   forward   act = dropout(gelu(h . W1^T + b1))      one GEMM, bias + exact GELU + dropout in its epilogue; the
+//             gp  = d act / d (h . W1^T + b1)          epilogue also writes the local derivative (dropout mask and
+//             v0  = act . W2^T                         1/(1-p) folded in), so the backward needs no erf / Philox
+//   backward  du0 = (dv0 . W2) o gp                    one GEMM with the multiply in its epilogue
+//             dW2 = dv0^T . act,   dW1 = du0^T . h,  db1 = colsum(du0)       gemm_tc_tn (gemm_tc.cu)
+//             dh  = du0 . W1
+//
+// fc2's bias, the second dropout and the residual add stay with K6 (block_fused.cu), which fuses them with the
+// LayerNorm that follows.  This replaces cuBLAS GEMM + K7 (bias_gelu_dropout) pairs: the (n, 2d) hidden
+// activation is written once by the GEMM that produces it instead of written, re-read and written again.
+//
+// gemm_nt_epi_kernel: C[M,N] = epilogue(A[M,K] . Bt[N,K]^T), persistent, warp-specialised:
+//   warp 0 TMA producer, warp 1 tcgen05.mma issuer (+ TMEM owner), warps 2.. epilogue (two or four warps per TMEM
+//   lane quarter, one column slice each), two TMEM accumulators so the epilogue of tile i overlaps the MMAs of
+//   tile i+1.  Row-per-thread epilogues store 32 bytes (one full sector) per instruction.  The GELU epilogue is
+//   ALU work (Philox + erfc, ~40 instructions per element) and gets 16 warps.
+#include "ew.cuh"
+#include "tc.cuh"
+
+namespace hwgat {
+
+typedef __nv_bfloat16 bf16;
+
+enum { kEpiNone = 0, kEpiGelu = 1, kEpiMul = 2 };
+
+struct EpiArgs {
+  bf16* C;            // [M, N] output
+  bf16* C2;           // kEpiGelu: local derivative (may be null: inference)
+  const bf16* G;      // kEpiMul: elementwise factor [M, N]
+  const float* bias;  // kEpiGelu: [N] or null
+  float scale;        // dropout 1/(1-p)
+  uint32_t thresh;    // dropout 16-bit threshold, 0 = no dropout
+  unsigned long long seed, offset;
+};
+
+constexpr int kFM = 128, kFK = 64;
+// epilogue warps: 8 for the memory-bound epilogues, 16 for the ALU-bound GELU one (4 per SM sub-partition:
+// with 2 the issue slots were ~2/3 used and the fc1 GEMM ran at the speed of the standalone K7 kernel)
+template <int EPI>
+struct EpiWarps { static constexpr int kWarps = EPI == 1 ? 16 : 8; static constexpr int kThreads = 32 * (2 + kWarps); };
+
+template <int BN>
+struct FfnCfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kABytes = kFM * kFK * 2;
+  static constexpr int kBBytes = BN * kFK * 2;
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kBarOff = kStages * kStage;
+  static constexpr int kSmem = kBarOff + 256 + 1024;
+  static constexpr int kTmemCols = 2 * BN;
+};
+
+template <int EPI>
+HW_DEV void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& e, size_t elem, int col) {
+  // r: 32 consecutive columns of one row (fp32 accumulator); elem = row * N + col.  Every store is 32 bytes
+  // = one full sector of the thread's own row.
+  if (EPI == kEpiNone) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint32_t p[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        p[i] = pack_bf16(__uint_as_float(r[16 * g + 2 * i]), __uint_as_float(r[16 * g + 2 * i + 1]));
+      st_global32(e.C + elem + 16 * g, p);
+    }
+  } else if (EPI == kEpiMul) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint32_t w[8], o[8];
+      ld_global32(e.G + elem + 16 * g, w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        o[i] = pack_bf16(__uint_as_float(r[16 * g + 2 * i]) * bf16_lo(w[i]),
+                         __uint_as_float(r[16 * g + 2 * i + 1]) * bf16_hi(w[i]));
+      st_global32(e.C + elem + 16 * g, o);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint32_t oa[8], od[8];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int c8 = 16 * g + 8 * hh;
+        float b[8];
+        if (e.bias) {
+          const float4 b0 = *reinterpret_cast<const float4*>(e.bias + col + c8);
+          const float4 b1 = *reinterpret_cast<const float4*>(e.bias + col + c8 + 4);
+          b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) b[i] = 0.f;
+        }
+        // same granule index as K7 (bias_gelu_dropout): vector (row * N + col) / 8 of the flattened tensor
+        const uint32_t keep =
+            e.thresh ? keep8((unsigned long long)((elem + c8) >> 3), e.offset, e.seed, e.thresh) : 0xFFu;
+        float a[8], dv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = __uint_as_float(r[c8 + i]) + b[i];
+          float cdf, pdf;
+          gelu_cdf_pdf(x, cdf, pdf);
+          const float m = ((keep >> i) & 1u) ? e.scale : 0.f;
+          a[i] = x * cdf * m;
+          dv[i] = fmaf(x, pdf, cdf) * m;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          oa[4 * hh + i] = pack_bf16(a[2 * i], a[2 * i + 1]);
+          od[4 * hh + i] = pack_bf16(dv[2 * i], dv[2 * i + 1]);
+        }
+      }
+      st_global32(e.C + elem + 16 * g, oa);
+      if (e.C2) st_global32(e.C2 + elem + 16 * g, od);
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   const EpiArgs e, int M, int N, int K) {
+  using Cfg = FfnCfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* acc_full = empty + Cfg::kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = N / BN, m_blocks = M / kFM, tiles = n_blocks * m_blocks, nk = K / kFK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EpiWarps<EPI>::kWarps); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          unsigned char* st = smem + s * Cfg::kStage;
+          mbar_expect_tx(&full[s], Cfg::kStage);
+          tma_load_2d(st, &tmA, &full[s], kb * kFK, mb * kFM);
+          tma_load_2d(st + Cfg::kABytes, &tmB, &full[s], kb * kFK, nb * BN);
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kFM, BN);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int ks = 0; ks < kFK / 16; ++ks)
+            umma_bf16(tmem + buf * BN, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
+                      (kb | ks) != 0);
+          umma_commit(&empty[s]);
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // column slice of the tile
+    constexpr int kHalf = BN / (EpiWarps<EPI>::kWarps / 4);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
+      const int buf = it & 1;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const size_t row = (size_t)mb * kFM + q * 32 + lane;
+      const int col0 = nb * BN + half * kHalf;
+      const size_t elem0 = row * N + col0;
+#pragma unroll 1
+      for (int c = 0; c < kHalf; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + half * kHalf + c, r);
+        tmem_ld_wait();
+        epilogue_chunk<EPI>(r, e, elem0 + c, col0 + c);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, Cfg::kTmemCols);
+}
+
+template <int BN, int EPI>
+static int launch_epi(const bf16* A, const bf16* Bt, const EpiArgs& e, int M, int N, int K, cudaStream_t s) {
+  using Cfg = FfnCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_nt_epi_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    attr_done = true;
+  }
+  CUtensorMap tmA, tmB;
+  int st;
+  if ((st = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, kFM))) return st;
+  if ((st = make_tmap_2d(&tmB, Bt, (uint64_t)N, (uint64_t)K, BN))) return st;
+  const int tiles = (M / kFM) * (N / BN);
+  const int grid = tiles < 148 ? tiles : 148;
+  gemm_nt_epi_kernel<BN, EPI><<<grid, EpiWarps<EPI>::kThreads, Cfg::kSmem, s>>>(tmA, tmB, e, M, N, K);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// C[M,N] = epilogue(A[M,K] . Bt[N,K]^T); M % 128 == 0, N % 128 == 0, K % 64 == 0
+template <int EPI>
+static int gemm_nt_epi(const bf16* A, const bf16* Bt, const EpiArgs& e, long long M, int N, int K, cudaStream_t s) {
+  if (M % kFM || K % kFK || N % 128 || M > 0x7fffffffLL) return HWGAT_ERR_UNSUPPORTED;
+  if (N % 256 == 0) return launch_epi<256, EPI>(A, Bt, e, (int)M, N, K, s);
+  return launch_epi<128, EPI>(A, Bt, e, (int)M, N, K, s);
+}
+
+int gemm_tc_nt_epi_none(const bf16* A, const bf16* Bt, bf16* C, long long M, int N, int K, cudaStream_t s) {
+  EpiArgs e{};
+  e.C = C;
+  return gemm_nt_epi<kEpiNone>(A, Bt, e, M, N, K, s);
+}
+
+// ---------------------------------------------------------------------------
+// K10 entry points
+// ---------------------------------------------------------------------------
+int ffn_fwd(const bf16* h, const bf16* w1, const float* b1, const bf16* w2, bf16* act, bf16* gp, bf16* v0, long long n,
+            int d, int hidden, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s) {
+  EpiArgs e{};
+  e.C = act; e.C2 = gp; e.bias = b1; e.thresh = drop_threshold16(p); e.scale = drop_scale16(e.thresh);
+  e.seed = seed; e.offset = offset;
+  int st = gemm_nt_epi<kEpiGelu>(h, w1, e, n, hidden, d, s);          // act, gp  [n, hidden]
+  if (st) return st;
+  EpiArgs e2{};
+  e2.C = v0;
+  return gemm_nt_epi<kEpiNone>(act, w2, e2, n, d, hidden, s);         // v0 [n, d]
+}
+
+size_t ffn_bwd_workspace_bytes(long long n, int d, int hidden) {
+  // du0 [n, hidden] + W2^T [hidden, d] + W1^T [d, hidden] (bf16) + db2 scratch [d] (fp32)
+  return ((size_t)n * hidden + (size_t)2 * d * hidden) * sizeof(bf16) + (size_t)d * sizeof(float);
+}
+
+int ffn_bwd(const bf16* dv0, const bf16* h, const bf16* act, const bf16* gp, const bf16* w1, const bf16* w2, bf16* dh,
+            float* dw1, float* db1, float* dw2, void* workspace, long long n, int d, int hidden, cudaStream_t s) {
+  bf16* du0 = (bf16*)workspace;
+  bf16* w2t = du0 + (size_t)n * hidden;       // [hidden, d]
+  bf16* w1t = w2t + (size_t)d * hidden;       // [d, hidden]
+  float* db2 = (float*)(w1t + (size_t)d * hidden);
+  int st;
+  if ((st = transpose_bf16(w2, w2t, d, hidden, s))) return st;          // W2 is [d, hidden]
+  EpiArgs e{};
+  e.C = du0; e.G = gp;
+  if ((st = gemm_nt_epi<kEpiMul>(dv0, w2t, e, n, hidden, d, s))) return st;    // du0 = (dv0 . W2) o gp
+  if ((st = gemm_tc_tn(dv0, act, dw2, db2, d, hidden, n, s))) return st;       // dW2 [d, hidden] = dv0^T . act
+  if ((st = gemm_tc_tn(du0, h, dw1, db1, hidden, d, n, s))) return st;         // dW1 [hidden, d], db1 = colsum(du0)
+  if ((st = transpose_bf16(w1, w1t, hidden, d, s))) return st;          // W1 is [hidden, d]
+  EpiArgs e2{};
+  e2.C = dh;
+  return gemm_nt_epi<kEpiNone>(du0, w1t, e2, n, d, hidden, s);                 // dh = du0 . W1
+}
+
+}  // namespace hwgat

@@ -245,9 +245,15 @@ class PartAttentionBlock(nn.Module):
                                          layout=LAYOUT_BFKD)
         a0 = nn.functional.linear(ctx, attn.proj.weight)           # bias, dropout, shortcut and norm2: K6
         x, h = ops.bias_dropout_add_ln(x, a0, attn.proj.bias, self.norm2, attn.proj_drop.p, self.training)
-        u0 = nn.functional.linear(h, ff.fc1.weight)                # bias, GELU, dropout: K7
-        g = ops.bias_gelu_dropout(u0, ff.fc1.bias, ff.drop.p, self.training)
-        v0 = nn.functional.linear(g, ff.fc2.weight)                # bias, dropout, residual (and the next norm1): K6
+        hidden = ff.fc1.weight.shape[0]
+        if ops.ffn_supported(h.numel() // self.dim, self.dim, hidden):
+            # K10: fc1 + bias + GELU + dropout + fc2's matmul on the tcgen05 GEMMs with fused epilogues
+            v0 = ops.feed_forward_core(h, ff.fc1.weight, ff.fc1.bias, ff.fc2.weight, ff.drop.p, self.training)
+        else:
+            u0 = nn.functional.linear(h, ff.fc1.weight)            # bias, GELU, dropout: K7
+            g = ops.bias_gelu_dropout(u0, ff.fc1.bias, ff.drop.p, self.training)
+            v0 = nn.functional.linear(g, ff.fc2.weight)
+        # fc2's bias, dropout, residual (and the next norm1): K6
         return ops.bias_dropout_add_ln(x, v0, ff.fc2.bias, next_norm, ff.drop.p, self.training)
 
 

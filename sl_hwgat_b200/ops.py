@@ -377,6 +377,69 @@ def bias_gelu_dropout(u0: torch.Tensor, bias: Optional[torch.Tensor], p: float, 
     return _BiasGeluDropout.apply(u0, bias, p if training else 0.0)
 
 
+class _FeedForwardCore(torch.autograd.Function):
+    """v0 = dropout(gelu(h W1^T + b1)) W2^T on the tcgen05 GEMMs of K10 (bias, GELU and dropout in the first GEMM's
+    epilogue).  Saves h, the hidden activation and its local derivative (mask folded in); nothing is recomputed."""
+
+    @staticmethod
+    def forward(ctx, h, w1, b1, w2, p):
+        lib = _lib.load()
+        _need_cuda(h, w1, b1, w2)
+        h_c = h.to(torch.bfloat16).contiguous()
+        d = h_c.shape[-1]
+        n = h_c.numel() // d
+        hidden = w1.shape[0]
+        if tuple(w1.shape) != (hidden, d) or tuple(w2.shape) != (d, hidden):
+            raise ValueError(f"fc1 / fc2 weights {tuple(w1.shape)} / {tuple(w2.shape)} do not match (n, {d}) input")
+        w1_c = w1.detach().to(torch.bfloat16).contiguous()
+        w2_c = w2.detach().to(torch.bfloat16).contiguous()
+        b1_c = b1.detach().float().contiguous() if b1 is not None else None
+        need_grad = any(ctx.needs_input_grad[:4])
+        seed, off = _philox_stream(h_c.device) if p > 0 else (0, 0)
+        act = torch.empty((n, hidden), dtype=torch.bfloat16, device=h_c.device)
+        gp = torch.empty_like(act) if need_grad else None
+        v0 = torch.empty(h_c.shape, dtype=torch.bfloat16, device=h_c.device)
+        with torch.cuda.device(h_c.device):
+            check(lib.hwgat_ffn_fwd(h_c.data_ptr(), w1_c.data_ptr(), _ptr(b1_c), w2_c.data_ptr(), act.data_ptr(),
+                                    _ptr(gp), v0.data_ptr(), n, d, hidden, float(p), seed, off, _stream()),
+                  "hwgat_ffn_fwd")
+        if need_grad:
+            ctx.save_for_backward(h_c, act, gp, w1_c, w2_c)
+        ctx.meta = (n, d, hidden, h.dtype, w1.dtype, None if b1 is None else b1.dtype, w2.dtype)
+        return v0
+
+    @staticmethod
+    def backward(ctx, dv0):
+        lib = _lib.load()
+        h_c, act, gp, w1_c, w2_c = ctx.saved_tensors
+        n, d, hidden, hdt, w1dt, b1dt, w2dt = ctx.meta
+        dv = dv0.to(torch.bfloat16).contiguous()
+        dev = h_c.device
+        dh = torch.empty_like(h_c)
+        dw1 = torch.empty((hidden, d), dtype=torch.float32, device=dev)
+        db1 = torch.empty((hidden,), dtype=torch.float32, device=dev)
+        dw2 = torch.empty((d, hidden), dtype=torch.float32, device=dev)
+        ws_bytes = lib.hwgat_ffn_bwd_workspace_bytes(n, d, hidden)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.hwgat_ffn_bwd(dv.data_ptr(), h_c.data_ptr(), act.data_ptr(), gp.data_ptr(), w1_c.data_ptr(),
+                                    w2_c.data_ptr(), dh.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), n, d, hidden, _stream()), "hwgat_ffn_bwd")
+        return (dh.to(hdt), dw1.to(w1dt), None if b1dt is None else db1.to(b1dt), dw2.to(w2dt), None)
+
+
+def feed_forward_core(h: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor, p: float,
+                      training: bool) -> torch.Tensor:
+    """dropout(gelu(h @ w1.T + b1)) @ w2.T as bf16: ff.fc1, ff.act, ff.drop and ff.fc2's matmul (HWGATE.py:130-134);
+    fc2's bias, the second dropout and the residual add are K6's (bias_dropout_add_ln).
+    h: (..., d) with prod(...) % 128 == 0, d % 128 == 0, hidden % 128 == 0."""
+    return _FeedForwardCore.apply(h, w1, b1, w2, p if training else 0.0)
+
+
+def ffn_supported(n_tokens: int, d: int, hidden: int) -> bool:
+    return n_tokens % 128 == 0 and d % 128 == 0 and hidden % 128 == 0
+
+
 # --------------------------------------------------------------------------
 # K8 / K9: model head and tail
 # --------------------------------------------------------------------------

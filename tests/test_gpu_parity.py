@@ -423,6 +423,76 @@ def test_bias_gelu_dropout(p, cols):
         assert rel_l2(bias.grad, want.sum(0)) < 5e-3
 
 
+@pytest.mark.parametrize("d,hidden,n", [(128, 256, 1024), (256, 512, 640), (512, 1024, 384), (128, 128, 128),
+                                        (256, 384, 256)])
+def test_feed_forward_core_no_dropout(d, hidden, n):
+    """K10, p = 0: gelu(h W1^T + b1) W2^T and every gradient against an fp64 reference evaluated at the kernel's
+    bf16 rounding points (operands bf16, hidden activation bf16)."""
+    from sl_hwgat_b200 import ops
+    g = torch.Generator().manual_seed(d + hidden + n)
+    h = torch.randn(n, d, generator=g).to(torch.bfloat16).cuda().requires_grad_(True)
+    w1 = (torch.randn(hidden, d, generator=g) / d ** 0.5).to(torch.bfloat16).float().cuda().requires_grad_(True)
+    b1 = (0.3 * torch.randn(hidden, generator=g)).cuda().requires_grad_(True)
+    w2 = (torch.randn(d, hidden, generator=g) / hidden ** 0.5).to(torch.bfloat16).float().cuda().requires_grad_(True)
+    v0 = ops.feed_forward_core(h, w1, b1, w2, 0.3, False)                 # eval: p ignored
+    assert v0.dtype == torch.bfloat16 and v0.shape == h.shape
+    gv = torch.randn(n, d, generator=g).to(torch.bfloat16).cuda()
+    v0.backward(gv)
+    h64, w164, b164, w264 = (t.detach().double().requires_grad_(True) for t in (h, w1, b1, w2))
+    act64 = torch.nn.functional.gelu(h64 @ w164.t() + b164)
+    v64 = act64 @ w264.t()
+    v64.backward(gv.double())
+    assert rel_l2(v0.float(), v64) < 6e-3
+    assert rel_l2(h.grad.float(), h64.grad) < 8e-3
+    assert rel_l2(w1.grad, w164.grad) < 8e-3 and rel_l2(w2.grad, w264.grad) < 8e-3
+    assert rel_l2(b1.grad, b164.grad) < 8e-3
+
+
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_feed_forward_core_dropout(p):
+    """K10 with dropout: with W2 = I the output is the hidden activation itself, so the mask, its rate, the
+    1/(1-p) scale and the mask the backward uses (stored inside the local derivative) can all be read off."""
+    from sl_hwgat_b200 import ops
+    torch.manual_seed(8)
+    n, d, hidden = 2048, 256, 256
+    h = torch.randn(n, d, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    w1 = (torch.randn(hidden, d, device="cuda") / d ** 0.5).to(torch.bfloat16).float().requires_grad_(True)
+    # pre-activations ~ N(3, 1.1): gelu is (almost) never near zero, so "output == 0" identifies the dropped ones
+    b1 = (3 + 0.5 * torch.randn(hidden, device="cuda")).requires_grad_(True)
+    w2 = torch.eye(d, device="cuda").requires_grad_(True)
+    torch.manual_seed(88)
+    y = ops.feed_forward_core(h, w1, b1, w2, p, True)
+    pre = (h.detach().double() @ w1.detach().double().t() + b1.detach().double())
+    ref = torch.nn.functional.gelu(pre)
+    big = ref.abs() >= 1e-3
+    kept = (y.detach().float() != 0) | ~big
+    assert abs(1 - kept[big].float().mean().item() - p) < 6e-3
+    assert rel_l2(y.detach().float()[kept & big], (ref / (1 - p))[kept & big]) < 6e-3
+    gy = torch.randn(n, d, device="cuda").to(torch.bfloat16)
+    y.backward(gy)
+    pre64 = pre.clone().requires_grad_(True)
+    torch.nn.functional.gelu(pre64).backward(gy.double())
+    du = torch.where(kept, pre64.grad / (1 - p), torch.zeros_like(pre64.grad))   # d loss / d pre-activation
+    assert rel_l2(b1.grad[None].double(), du.sum(0, keepdim=True)) < 2e-2
+    assert rel_l2(h.grad.double(), du @ w1.detach().double()) < 2e-2
+    assert rel_l2(w1.grad.double(), du.t() @ h.detach().double()) < 2e-2
+    # the same seed gives the same mask; the next call a different one
+    h2 = h.detach()
+    torch.manual_seed(88)
+    y2 = ops.feed_forward_core(h2, w1.detach(), b1.detach(), w2.detach(), p, True)
+    y3 = ops.feed_forward_core(h2, w1.detach(), b1.detach(), w2.detach(), p, True)
+    assert torch.equal(y2 != 0, y.detach() != 0) and not torch.equal(y3 != 0, y2 != 0)
+
+
+def test_feed_forward_core_rejects_unsupported_shapes():
+    from sl_hwgat_b200 import _lib, ops
+    h = torch.zeros(100, 128, device="cuda", dtype=torch.bfloat16)          # 100 rows: not a multiple of 128
+    w1 = torch.zeros(256, 128, device="cuda"); w2 = torch.zeros(128, 256, device="cuda")
+    with pytest.raises(_lib.HwgatError):
+        ops.feed_forward_core(h, w1, None, w2, 0.0, False)
+    assert not ops.ffn_supported(100, 128, 256) and ops.ffn_supported(128, 128, 256)
+
+
 def test_dropout_streams_differ_between_calls_and_repeat_with_seed():
     from sl_hwgat_b200 import ops
     res = torch.zeros(512, 128, device="cuda")
