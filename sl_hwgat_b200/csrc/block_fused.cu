@@ -25,47 +25,73 @@ HW_DEV float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------
-// K5: one warp per row; lane holds kV float4 (kV = d/128)
+// K5 / K6 thread mapping.  A row of d = 128 / 256 / 512 columns is owned by kL = d/16 = 8 / 16 / 32 lanes, each
+// holding FOUR float4 (columns i*4*kL + 4*lc .. +3, i = 0..3), and a warp works on 32/kL rows at once.  Every
+// width therefore has the same bytes in flight per lane and the same per-lane code, and the row reductions are
+// log2(kL) shuffle steps shared by all rows of the warp (one warp per row at d = 128 spent 10 shuffles per 128
+// columns and ran at 65-78 % of the HBM rate the d = 512 kernels reach).
 // ---------------------------------------------------------------------------
-template <int kV>
+template <int kL>
+HW_DEV float group_sum(float v) {
+#pragma unroll
+  for (int o = kL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// per-lane column partials -> sum over the warp's row groups (lanes with equal lane % kL own the same columns)
+template <int kL>
+HW_DEV void fold_groups(float4 (&a)[4]) {
+#pragma unroll
+  for (int o = kL; o < 32; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[i].x += __shfl_xor_sync(0xffffffffu, a[i].x, o);
+      a[i].y += __shfl_xor_sync(0xffffffffu, a[i].y, o);
+      a[i].z += __shfl_xor_sync(0xffffffffu, a[i].z, o);
+      a[i].w += __shfl_xor_sync(0xffffffffu, a[i].w, o);
+    }
+}
+
+template <int kL>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, bf16* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd,
                                                      long long n, float eps) {
-  constexpr int d = kV * 128;
-  const int lane = threadIdx.x & 31;
+  constexpr int d = kL * 16, kRows = 32 / kL;
+  const int lane = threadIdx.x & 31, sub = lane / kL, lc = lane % kL;
   const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * 8;
-  float4 gm[kV], bt[kV];
+  float4 gm[4], bt[4];
 #pragma unroll
-  for (int i = 0; i < kV; ++i) {
-    gm[i] = *reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4);
-    bt[i] = *reinterpret_cast<const float4*>(beta + i * 128 + lane * 4);
+  for (int i = 0; i < 4; ++i) {
+    gm[i] = *reinterpret_cast<const float4*>(gamma + i * 4 * kL + lc * 4);
+    bt[i] = *reinterpret_cast<const float4*>(beta + i * 4 * kL + lc * 4);
   }
-  for (long long row = warp; row < n; row += nwarps) {
-    const float* xr = x + row * d;
-    float4 v[kV];
+  for (long long base = warp * kRows; base < n; base += nwarps * kRows) {
+    const long long row = base + sub;
+    const bool ok = row < n;
+    float4 v[4];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kV; ++i) {
-      v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+    for (int i = 0; i < 4; ++i) {
+      v[i] = ok ? *reinterpret_cast<const float4*>(x + row * d + i * 4 * kL + lc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
-    const float mu = warp_sum(s) * (1.f / d);
+    const float mu = group_sum<kL>(s) * (1.f / d);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kV; ++i) {
+    for (int i = 0; i < 4; ++i) {
       v[i].x -= mu; v[i].y -= mu; v[i].z -= mu; v[i].w -= mu;
       q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
     }
-    const float rs = rsqrtf(warp_sum(q) * (1.f / d) + eps);
-    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    const float rs = rsqrtf(group_sum<kL>(q) * (1.f / d) + eps);
+    if (!ok) continue;
+    if (lc == 0) { mean[row] = mu; rstd[row] = rs; }
     bf16* yr = y + row * d;
 #pragma unroll
-    for (int i = 0; i < kV; ++i) {
+    for (int i = 0; i < 4; ++i) {
       uint2 o;
       o.x = pack_bf16(v[i].x * rs * gm[i].x + bt[i].x, v[i].y * rs * gm[i].y + bt[i].y);
       o.y = pack_bf16(v[i].z * rs * gm[i].z + bt[i].z, v[i].w * rs * gm[i].w + bt[i].w);
-      *reinterpret_cast<uint2*>(yr + i * 128 + lane * 4) = o;
+      *reinterpret_cast<uint2*>(yr + i * 4 * kL + lc * 4) = o;
     }
   }
 }
@@ -74,31 +100,34 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 // K5': dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 //      dgamma += sum_rows dy * xhat, dbeta += sum_rows dy   (per-lane partials, smem reduce, one atomic per column per CTA)
 // ---------------------------------------------------------------------------
-template <int kV>
+template <int kL>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dres,
                                                      const float* __restrict__ x, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                      float* __restrict__ dx, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, long long n) {
-  constexpr int d = kV * 128;
+  constexpr int d = kL * 16, kRows = 32 / kL;
   __shared__ float red[2][8][d];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane / kL, lc = lane % kL;
   const long long warp = (long long)blockIdx.x * 8 + wib, nwarps = (long long)gridDim.x * 8;
-  float4 gm[kV], dg[kV], db[kV];
+  float4 gm[4], dg[4], db[4];
 #pragma unroll
-  for (int i = 0; i < kV; ++i) {
-    gm[i] = *reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4);
+  for (int i = 0; i < 4; ++i) {
+    gm[i] = *reinterpret_cast<const float4*>(gamma + i * 4 * kL + lc * 4);
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (long long row = warp; row < n; row += nwarps) {
+  for (long long base = warp * kRows; base < n; base += nwarps * kRows) {
+    const bool ok = base + sub < n;
+    const long long row = ok ? base + sub : 0;
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[kV], g[kV];
+    float4 xh[4], g[4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kV; ++i) {
-      const float4 xv = *reinterpret_cast<const float4*>(x + row * d + i * 128 + lane * 4);
-      const uint2 dv = *reinterpret_cast<const uint2*>(dy + row * d + i * 128 + lane * 4);
+    for (int i = 0; i < 4; ++i) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + row * d + i * 4 * kL + lc * 4);
+      uint2 dv = *reinterpret_cast<const uint2*>(dy + row * d + i * 4 * kL + lc * 4);
+      if (!ok) dv = make_uint2(0u, 0u);
       const float4 dyv = make_float4(bf16_lo(dv.x), bf16_hi(dv.x), bf16_lo(dv.y), bf16_hi(dv.y));
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       g[i] = make_float4(dyv.x * gm[i].x, dyv.y * gm[i].y, dyv.z * gm[i].z, dyv.w * gm[i].w);
@@ -107,22 +136,27 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
       dg[i].x += dyv.x * xh[i].x; dg[i].y += dyv.y * xh[i].y; dg[i].z += dyv.z * xh[i].z; dg[i].w += dyv.w * xh[i].w;
       db[i].x += dyv.x; db[i].y += dyv.y; db[i].z += dyv.z; db[i].w += dyv.w;
     }
-    const float m1 = warp_sum(s1) * (1.f / d), m2 = warp_sum(s2) * (1.f / d);
+    const float m1 = group_sum<kL>(s1) * (1.f / d), m2 = group_sum<kL>(s2) * (1.f / d);
+    if (!ok) continue;
 #pragma unroll
-    for (int i = 0; i < kV; ++i) {
+    for (int i = 0; i < 4; ++i) {
       float4 o = make_float4(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2),
                              rs * (g[i].z - m1 - xh[i].z * m2), rs * (g[i].w - m1 - xh[i].w * m2));
       if (dres) {
-        const float4 r = *reinterpret_cast<const float4*>(dres + row * d + i * 128 + lane * 4);
+        const float4 r = *reinterpret_cast<const float4*>(dres + row * d + i * 4 * kL + lc * 4);
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
-      *reinterpret_cast<float4*>(dx + row * d + i * 128 + lane * 4) = o;
+      *reinterpret_cast<float4*>(dx + row * d + i * 4 * kL + lc * 4) = o;
     }
   }
+  fold_groups<kL>(dg);
+  fold_groups<kL>(db);
+  if (sub == 0) {
 #pragma unroll
-  for (int i = 0; i < kV; ++i) {
-    *reinterpret_cast<float4*>(&red[0][wib][i * 128 + lane * 4]) = dg[i];
-    *reinterpret_cast<float4*>(&red[1][wib][i * 128 + lane * 4]) = db[i];
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<float4*>(&red[0][wib][i * 4 * kL + lc * 4]) = dg[i];
+      *reinterpret_cast<float4*>(&red[1][wib][i * 4 * kL + lc * 4]) = db[i];
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < d; c += 256) {
@@ -136,10 +170,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
 
 // ---------------------------------------------------------------------------
 // K6: x1 = res + dropout(a0 + bias)  and, fused, the LayerNorm that follows it: y = LN(x1) as bf16.
-// One warp per row, lane owns columns i*128 + 4*lane .. +3.  Dropout flags of a 4-element granule come
-// from one Philox call keyed by the granule index (row*d + col)/4, identically in forward and backward.
+// Thread mapping as K5.  Dropout flags of a 4-element granule come from one Philox call keyed by the granule
+// index (row*d + col)/4, identically in forward and backward.
 // ---------------------------------------------------------------------------
-template <int kV, bool kLN>
+template <int kL, bool kLN>
 __global__ void __launch_bounds__(256) bda_ln_fwd_kernel(const float* __restrict__ res, const bf16* __restrict__ a0,
                                                          const float* __restrict__ bias, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ x1,
@@ -147,57 +181,69 @@ __global__ void __launch_bounds__(256) bda_ln_fwd_kernel(const float* __restrict
                                                          float* __restrict__ rstd, long long n, float eps, float scale,
                                                          uint32_t thresh, unsigned long long seed,
                                                          unsigned long long offset) {
-  constexpr int d = kV * 128;
-  const int lane = threadIdx.x & 31;
+  constexpr int d = kL * 16, kRows = 32 / kL;
+  const int lane = threadIdx.x & 31, sub = lane / kL, lc = lane % kL;
   const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * 8;
-  float4 bs[kV], gm[kV], bt[kV];
+  float4 bs[4], gm[4], bt[4];
 #pragma unroll
-  for (int i = 0; i < kV; ++i) {
-    bs[i] = bias ? *reinterpret_cast<const float4*>(bias + i * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < 4; ++i) {
+    bs[i] = bias ? *reinterpret_cast<const float4*>(bias + i * 4 * kL + lc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (kLN) {
-      gm[i] = *reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4);
-      bt[i] = *reinterpret_cast<const float4*>(beta + i * 128 + lane * 4);
+      gm[i] = *reinterpret_cast<const float4*>(gamma + i * 4 * kL + lc * 4);
+      bt[i] = *reinterpret_cast<const float4*>(beta + i * 4 * kL + lc * 4);
     }
   }
-  for (long long row = warp; row < n; row += nwarps) {
-    float4 v[kV];
+  for (long long base = warp * kRows; base < n; base += nwarps * kRows) {
+    const bool ok = base + sub < n;
+    const long long row = ok ? base + sub : 0;   // rows past the end read row 0 and store nothing
+    // all loads first (a non-uniform `if (ok)` around load + store made four dependent load -> store rounds)
+    float4 v[4];
+    uint2 av[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long e = row * d + i * 4 * kL + lc * 4;
+      v[i] = *reinterpret_cast<const float4*>(res + e);
+      av[i] = *reinterpret_cast<const uint2*>(a0 + e);
+    }
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kV; ++i) {
-      const long long e = row * d + i * 128 + lane * 4;
-      const float4 r = *reinterpret_cast<const float4*>(res + e);
-      const uint2 av = *reinterpret_cast<const uint2*>(a0 + e);
+    for (int i = 0; i < 4; ++i) {
+      const long long e = row * d + i * 4 * kL + lc * 4;
       const uint32_t keep = thresh ? keep4((unsigned long long)e >> 2, offset, seed, thresh) : 0xFu;
-      v[i].x = r.x + ((keep & 1u) ? (bf16_lo(av.x) + bs[i].x) * scale : 0.f);
-      v[i].y = r.y + ((keep & 2u) ? (bf16_hi(av.x) + bs[i].y) * scale : 0.f);
-      v[i].z = r.z + ((keep & 4u) ? (bf16_lo(av.y) + bs[i].z) * scale : 0.f);
-      v[i].w = r.w + ((keep & 8u) ? (bf16_hi(av.y) + bs[i].w) * scale : 0.f);
-      *reinterpret_cast<float4*>(x1 + e) = v[i];
+      v[i].x += (keep & 1u) ? (bf16_lo(av[i].x) + bs[i].x) * scale : 0.f;
+      v[i].y += (keep & 2u) ? (bf16_hi(av[i].x) + bs[i].y) * scale : 0.f;
+      v[i].z += (keep & 4u) ? (bf16_lo(av[i].y) + bs[i].z) * scale : 0.f;
+      v[i].w += (keep & 8u) ? (bf16_hi(av[i].y) + bs[i].w) * scale : 0.f;
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(x1 + row * d + i * 4 * kL + lc * 4) = v[i];
+    }
     if (!kLN) continue;
-    const float mu = warp_sum(s) * (1.f / d);
+    const float mu = group_sum<kL>(s) * (1.f / d);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kV; ++i) {
+    for (int i = 0; i < 4; ++i) {
       v[i].x -= mu; v[i].y -= mu; v[i].z -= mu; v[i].w -= mu;
       q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
     }
-    const float rs = rsqrtf(warp_sum(q) * (1.f / d) + eps);
-    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    const float rs = rsqrtf(group_sum<kL>(q) * (1.f / d) + eps);
+    if (!ok) continue;
+    if (lc == 0) { mean[row] = mu; rstd[row] = rs; }
 #pragma unroll
-    for (int i = 0; i < kV; ++i) {
+    for (int i = 0; i < 4; ++i) {
       uint2 o;
       o.x = pack_bf16(v[i].x * rs * gm[i].x + bt[i].x, v[i].y * rs * gm[i].y + bt[i].y);
       o.y = pack_bf16(v[i].z * rs * gm[i].z + bt[i].z, v[i].w * rs * gm[i].w + bt[i].w);
-      *reinterpret_cast<uint2*>(y + row * d + i * 128 + lane * 4) = o;
+      *reinterpret_cast<uint2*>(y + row * d + i * 4 * kL + lc * 4) = o;
     }
   }
 }
 
 // K6': dx = g_x1 + LN'(dy)  [kLN]  or  dx = g_x1  [!kLN];   d_res = dx (written only if kLN),
 //      d_a0 = mask * scale * dx (bf16),  dbias += colsum(mask * scale * dx),  dgamma / dbeta as K5'.
-template <int kV, bool kLN>
+template <int kL, bool kLN>
 __global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict__ g_x1, const bf16* __restrict__ dy,
                                                          const float* __restrict__ x1, const float* __restrict__ mean,
                                                          const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -206,27 +252,30 @@ __global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict
                                                          float* __restrict__ dbeta, long long n, float scale,
                                                          uint32_t thresh, unsigned long long seed,
                                                          unsigned long long offset) {
-  constexpr int d = kV * 128;
+  constexpr int d = kL * 16, kRows = 32 / kL;
   __shared__ float red[kLN ? 3 : 1][8][d];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane / kL, lc = lane % kL;
   const long long warp = (long long)blockIdx.x * 8 + wib, nwarps = (long long)gridDim.x * 8;
-  float4 gm[kV], dg[kV], db[kV], dbs[kV];
+  float4 gm[4], dg[4], db[4], dbs[4];
 #pragma unroll
-  for (int i = 0; i < kV; ++i) {
-    if (kLN) gm[i] = *reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4);
+  for (int i = 0; i < 4; ++i) {
+    if (kLN) gm[i] = *reinterpret_cast<const float4*>(gamma + i * 4 * kL + lc * 4);
     dg[i] = db[i] = dbs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (long long row = warp; row < n; row += nwarps) {
-    float4 o[kV];
+  for (long long base = warp * kRows; base < n; base += nwarps * kRows) {
+    const bool ok = base + sub < n;
+    const long long row = ok ? base + sub : 0;
+    float4 o[4];
     if (kLN) {
       const float mu = mean[row], rs = rstd[row];
-      float4 xh[kV], g[kV];
+      float4 xh[4], g[4];
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < kV; ++i) {
-        const long long e = row * d + i * 128 + lane * 4;
+      for (int i = 0; i < 4; ++i) {
+        const long long e = row * d + i * 4 * kL + lc * 4;
         const float4 xv = *reinterpret_cast<const float4*>(x1 + e);
-        const uint2 dv = *reinterpret_cast<const uint2*>(dy + e);
+        uint2 dv = *reinterpret_cast<const uint2*>(dy + e);
+        if (!ok) dv = make_uint2(0u, 0u);
         const float4 dyv = make_float4(bf16_lo(dv.x), bf16_hi(dv.x), bf16_lo(dv.y), bf16_hi(dv.y));
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
         g[i] = make_float4(dyv.x * gm[i].x, dyv.y * gm[i].y, dyv.z * gm[i].z, dyv.w * gm[i].w);
@@ -235,24 +284,26 @@ __global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict
         dg[i].x += dyv.x * xh[i].x; dg[i].y += dyv.y * xh[i].y; dg[i].z += dyv.z * xh[i].z; dg[i].w += dyv.w * xh[i].w;
         db[i].x += dyv.x; db[i].y += dyv.y; db[i].z += dyv.z; db[i].w += dyv.w;
       }
-      const float m1 = warp_sum(s1) * (1.f / d), m2 = warp_sum(s2) * (1.f / d);
+      const float m1 = group_sum<kL>(s1) * (1.f / d), m2 = group_sum<kL>(s2) * (1.f / d);
+      if (!ok) continue;
 #pragma unroll
-      for (int i = 0; i < kV; ++i) {
+      for (int i = 0; i < 4; ++i) {
         o[i] = make_float4(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2),
                            rs * (g[i].z - m1 - xh[i].z * m2), rs * (g[i].w - m1 - xh[i].w * m2));
         if (g_x1) {
-          const float4 r = *reinterpret_cast<const float4*>(g_x1 + row * d + i * 128 + lane * 4);
+          const float4 r = *reinterpret_cast<const float4*>(g_x1 + row * d + i * 4 * kL + lc * 4);
           o[i].x += r.x; o[i].y += r.y; o[i].z += r.z; o[i].w += r.w;
         }
-        *reinterpret_cast<float4*>(d_res + row * d + i * 128 + lane * 4) = o[i];
+        *reinterpret_cast<float4*>(d_res + row * d + i * 4 * kL + lc * 4) = o[i];
       }
     } else {
+      if (!ok) continue;
 #pragma unroll
-      for (int i = 0; i < kV; ++i) o[i] = *reinterpret_cast<const float4*>(g_x1 + row * d + i * 128 + lane * 4);
+      for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const float4*>(g_x1 + row * d + i * 4 * kL + lc * 4);
     }
 #pragma unroll
-    for (int i = 0; i < kV; ++i) {
-      const long long e = row * d + i * 128 + lane * 4;
+    for (int i = 0; i < 4; ++i) {
+      const long long e = row * d + i * 4 * kL + lc * 4;
       const uint32_t keep = thresh ? keep4((unsigned long long)e >> 2, offset, seed, thresh) : 0xFu;
       const float4 da = make_float4((keep & 1u) ? o[i].x * scale : 0.f, (keep & 2u) ? o[i].y * scale : 0.f,
                                     (keep & 4u) ? o[i].z * scale : 0.f, (keep & 8u) ? o[i].w * scale : 0.f);
@@ -263,12 +314,16 @@ __global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict
       dbs[i].x += da.x; dbs[i].y += da.y; dbs[i].z += da.z; dbs[i].w += da.w;
     }
   }
+  fold_groups<kL>(dbs);
+  if (kLN) { fold_groups<kL>(dg); fold_groups<kL>(db); }
+  if (sub == 0) {
 #pragma unroll
-  for (int i = 0; i < kV; ++i) {
-    *reinterpret_cast<float4*>(&red[0][wib][i * 128 + lane * 4]) = dbs[i];
-    if (kLN) {
-      *reinterpret_cast<float4*>(&red[1][wib][i * 128 + lane * 4]) = dg[i];
-      *reinterpret_cast<float4*>(&red[2][wib][i * 128 + lane * 4]) = db[i];
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<float4*>(&red[0][wib][i * 4 * kL + lc * 4]) = dbs[i];
+      if (kLN) {
+        *reinterpret_cast<float4*>(&red[1][wib][i * 4 * kL + lc * 4]) = dg[i];
+        *reinterpret_cast<float4*>(&red[2][wib][i * 4 * kL + lc * 4]) = db[i];
+      }
     }
   }
   __syncthreads();
@@ -373,9 +428,9 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, bf16* y
                   long long n, int d, float eps, cudaStream_t s) {
   const int grid = ew_grid(n * 32);
   switch (d) {
-    case 128: ln_fwd_kernel<1><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
-    case 256: ln_fwd_kernel<2><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
-    case 512: ln_fwd_kernel<4><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
+    case 128: ln_fwd_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
+    case 256: ln_fwd_kernel<16><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
+    case 512: ln_fwd_kernel<32><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();
@@ -389,9 +444,9 @@ int launch_ln_bwd(const bf16* dy, const float* dres, const float* x, const float
   long long want = (n + 7) / 8;
   const int grid = (int)(want < 148LL * 4 ? (want < 1 ? 1 : want) : 148LL * 4);
   switch (d) {
-    case 128: ln_bwd_kernel<1><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n); break;
-    case 256: ln_bwd_kernel<2><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n); break;
-    case 512: ln_bwd_kernel<4><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n); break;
+    case 128: ln_bwd_kernel<8><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n); break;
+    case 256: ln_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n); break;
+    case 512: ln_bwd_kernel<32><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();
@@ -404,9 +459,9 @@ static int bda_fwd_dispatch(int grid, cudaStream_t s, const float* res, const bf
                             long long n, int d, float eps, float scale, uint32_t thresh, unsigned long long seed,
                             unsigned long long offset) {
   switch (d) {
-    case 128: bda_ln_fwd_kernel<1, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset); break;
-    case 256: bda_ln_fwd_kernel<2, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset); break;
-    case 512: bda_ln_fwd_kernel<4, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset); break;
+    case 128: bda_ln_fwd_kernel<8, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset); break;
+    case 256: bda_ln_fwd_kernel<16, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset); break;
+    case 512: bda_ln_fwd_kernel<32, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   return 0;
@@ -431,9 +486,9 @@ static int bda_bwd_dispatch(int grid, cudaStream_t s, const float* g_x1, const b
                             float* dbias, float* dgamma, float* dbeta, long long n, int d, float scale, uint32_t thresh,
                             unsigned long long seed, unsigned long long offset) {
   switch (d) {
-    case 128: bda_ln_bwd_kernel<1, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset); break;
-    case 256: bda_ln_bwd_kernel<2, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset); break;
-    case 512: bda_ln_bwd_kernel<4, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset); break;
+    case 128: bda_ln_bwd_kernel<8, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset); break;
+    case 256: bda_ln_bwd_kernel<16, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset); break;
+    case 512: bda_ln_bwd_kernel<32, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   return 0;

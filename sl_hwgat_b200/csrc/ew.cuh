@@ -66,15 +66,17 @@ HW_DEV float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(x));
   return r;
 }
+// Constants are pre-folded to shave multiplies (these epilogues are ALU-bound): zp = |x| sqrt(log2(e)/2), so
+// exp(-x^2/2) = 2^(-zp^2) and p z = 0.27273747 zp; the polynomial coefficients carry the 1/2 of erfc/2.
 HW_DEV void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));     // 1 ulp; the polynomial's own error is 1.5e-7
-  const float e = ex2_approx(-z * z * 1.4426950408889634f);  // exp(-x^2/2)
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float half_erfc = 0.5f * t * poly * e;
+  const float zp = fabsf(x) * 0.84932178f;
+  const float t = rcp_approx(fmaf(0.27273747f, zp, 1.f));   // 1 ulp; the polynomial's own error is 1.5e-7
+  const float e = ex2_approx(-zp * zp);                      // exp(-x^2/2)
+  float poly = fmaf(t, 0.5307027145f, -0.7265760135f);
+  poly = fmaf(t, poly, 0.7107068705f);
+  poly = fmaf(t, poly, -0.142248368f);
+  poly = fmaf(t, poly, 0.127414796f);
+  const float half_erfc = (t * e) * poly;
   cdf = x >= 0.f ? 1.f - half_erfc : half_erfc;
   pdf = 0.3989422804014327f * e;
 }
