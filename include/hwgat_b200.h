@@ -191,6 +191,18 @@ int hwgat_ln_pool_fwd(const float* x, const float* gamma, const float* beta, flo
 int hwgat_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
                       float* dx, float* dgamma, int B, int tokens, int d, hwgat_stream_t stream);
 
+/* ---- training loop ------------------------------------------------------ */
+
+/* K11: one AdamW step over n_tensors fp32 parameter tensors in ONE launch per 160 tensors (multi-tensor apply).
+ * Replaces optimizer.step() of torch.optim.AdamW(model.parameters(), lr) (utils.py:73-75, stepped at utils.py:107):
+ *   p *= 1 - lr*weight_decay;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *   p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps),   g = grad_scale * grads[t]
+ * params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors DEVICE pointers (fp32), sizes: HOST array of
+ * element counts.  step >= 1 is the step number after the increment (torch's state['step']).                 */
+int hwgat_adamw_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                     float* const* exp_avg_sq, const long long* sizes, double lr, double beta1, double beta2, double eps,
+                     double weight_decay, long long step, float grad_scale, hwgat_stream_t stream);
+
 /* Diagnostic: the plain bf16 GEMM K3 uses for d_xn, C[M,N] = A[M,K] . Bt[N,K]^T (fp32 accumulate,
  * TMA + tcgen05).  M % 128 == 0, N % 128 == 0, K % 64 == 0; all row-major bf16 device pointers. */
 int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream);

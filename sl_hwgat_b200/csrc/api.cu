@@ -27,7 +27,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 6; }
+int hwgat_version(void) { return 7; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -284,6 +284,23 @@ int hwgat_ln_pool_bwd(const float* g, const float* x, const float* mean, const f
   if (B > 0 && (!g || !x || !mean || !rstd || !gamma || !dx)) return HWGAT_ERR_NULL;
   if (misaligned(g) || misaligned(x) || misaligned(gamma) || misaligned(dx)) return HWGAT_ERR_ALIGN;
   return launch_ln_pool_bwd(g, x, mean, rstd, gamma, dx, dgamma, B, tokens, d, (cudaStream_t)stream);
+}
+
+int hwgat_adamw_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                     float* const* exp_avg_sq, const long long* sizes, double lr, double beta1, double beta2, double eps,
+                     double weight_decay, long long step, float grad_scale, hwgat_stream_t stream) {
+  if (n_tensors < 0 || step < 1) return HWGAT_ERR_SHAPE;
+  if (!(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0) || !(lr >= 0.0) ||
+      !(weight_decay >= 0.0))
+    return HWGAT_ERR_SHAPE;
+  if (n_tensors == 0) return HWGAT_OK;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !sizes) return HWGAT_ERR_NULL;
+  for (int t = 0; t < n_tensors; ++t) {
+    if (sizes[t] < 0) return HWGAT_ERR_SHAPE;
+    if (sizes[t] > 0 && (!params[t] || !grads[t] || !exp_avg[t] || !exp_avg_sq[t])) return HWGAT_ERR_NULL;
+  }
+  return adamw_step(n_tensors, params, grads, exp_avg, exp_avg_sq, sizes, lr, beta1, beta2, eps, weight_decay, step,
+                    grad_scale, (cudaStream_t)stream);
 }
 
 int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream) {

@@ -158,6 +158,9 @@ int gemm_tc_nt_epi_none(const __nv_bfloat16* A, const __nv_bfloat16* Bt, __nv_bf
 int ffn_fwd(const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1, const __nv_bfloat16* w2,
             __nv_bfloat16* act, __nv_bfloat16* gp, __nv_bfloat16* v0, long long n, int d, int hidden, float p,
             unsigned long long seed, unsigned long long offset, cudaStream_t s);
+int adamw_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+               float* const* exp_avg_sq, const long long* sizes, double lr, double beta1, double beta2, double eps,
+               double weight_decay, long long step, float grad_scale, cudaStream_t s);
 size_t ffn_bwd_workspace_bytes(long long n, int d, int hidden);
 int ffn_bwd(const __nv_bfloat16* dv0, const __nv_bfloat16* h, const __nv_bfloat16* act, const __nv_bfloat16* gp,
             const __nv_bfloat16* w1, const __nv_bfloat16* w2, __nv_bfloat16* dh, float* dw1, float* db1, float* dw2,

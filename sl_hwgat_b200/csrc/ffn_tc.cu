@@ -92,16 +92,21 @@ HW_DEV void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& e, size_t ele
 #pragma unroll
           for (int i = 0; i < 8; ++i) b[i] = 0.f;
         }
-        // same granule index as K7 (bias_gelu_dropout): vector (row * N + col) / 8 of the flattened tensor
-        const uint32_t keep =
-            e.thresh ? keep8((unsigned long long)((elem + c8) >> 3), e.offset, e.seed, e.thresh) : 0xFFu;
+        // same stream and granule index as K7 (bias_gelu_dropout): vector (row * N + col) / 8 of the flattened
+        // tensor, element 2j <- low half of word j, element 2j+1 <- high half (keep8).  The 16-bit compares are
+        // done in place: (w << 16) >= (t << 16) and w >= (t << 16), no mask word is assembled.
+        uint4 rnd = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (e.thresh) rnd = philox4x32((unsigned long long)((elem + c8) >> 3), e.offset, e.seed);
+        const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+        const uint32_t t16 = e.thresh << 16;
         float a[8], dv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float x = __uint_as_float(r[c8 + i]) + b[i];
           float cdf, pdf;
           gelu_cdf_pdf(x, cdf, pdf);
-          const float m = ((keep >> i) & 1u) ? e.scale : 0.f;
+          const bool keep = ((i & 1) ? rw[i >> 1] : (rw[i >> 1] << 16)) >= t16;
+          const float m = keep ? e.scale : 0.f;
           a[i] = x * cdf * m;
           dv[i] = fmaf(x, pdf, cdf) * m;
         }
@@ -193,17 +198,43 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_kernel
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
       const int buf = it & 1;
-      mbar_wait(&acc_full[buf], (it >> 1) & 1);
-      tc_fence_after();
       const size_t row = (size_t)mb * kFM + q * 32 + lane;
       const int col0 = nb * BN + half * kHalf;
       const size_t elem0 = row * N + col0;
+      if constexpr (EPI == kEpiMul) {
+        // The factor rows are fetched BEFORE the accumulator is waited for: a row-per-thread load touches 32 lines
+        // per instruction, and issued inside the chunk loop its latency was exposed once per chunk (tensor pipe
+        // 39 % busy on a GEMM whose HBM time and MMA time are both ~half of what it took).
+        uint32_t gq[kHalf / 16][8];
+#pragma unroll
+        for (int j = 0; j < kHalf / 16; ++j) ld_global32(e.G + elem0 + 16 * j, gq[j]);
+        mbar_wait(&acc_full[buf], (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < kHalf; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + half * kHalf + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              o[i] = pack_bf16(__uint_as_float(r[16 * g + 2 * i]) * bf16_lo(gq[c / 16 + g][i]),
+                               __uint_as_float(r[16 * g + 2 * i + 1]) * bf16_hi(gq[c / 16 + g][i]));
+            st_global32(e.C + elem0 + c + 16 * g, o);
+          }
+        }
+      } else {
+        mbar_wait(&acc_full[buf], (it >> 1) & 1);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < kHalf; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + half * kHalf + c, r);
-        tmem_ld_wait();
-        epilogue_chunk<EPI>(r, e, elem0 + c, col0 + c);
+        for (int c = 0; c < kHalf; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + half * kHalf + c, r);
+          tmem_ld_wait();
+          epilogue_chunk<EPI>(r, e, elem0 + c, col0 + c);
+        }
       }
       tc_fence_before();
       __syncwarp();

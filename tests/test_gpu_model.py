@@ -177,3 +177,53 @@ def test_threshold_draw_order_matches_reference():
     torch.set_rng_state(st)
     m(x)
     assert torch.rand(1).item() == expect_after
+
+
+# ------------------------------------------------------------------ K11: fused AdamW
+@pytest.mark.parametrize("wd", [0.01, 0.0])
+def test_fused_adamw_matches_torch(wd):
+    """K11 against torch.optim.AdamW (the reference's optimizer, utils.py:73-75) on ragged tensor sizes, five steps,
+    with a learning-rate change in between (CosineAnnealingLR drives param_groups[0]['lr'], utils.py:86-88)."""
+    from sl_hwgat_b200.optim import AdamW
+    g = torch.Generator().manual_seed(3)
+    shapes = [(1,), (7,), (1000,), (4099,), (64, 128), (3, 5, 17), (4096 * 5 + 3,)]
+    ours = [torch.randn(s, generator=g).cuda().requires_grad_(True) for s in shapes]
+    ref = [p.detach().clone().requires_grad_(True) for p in ours]
+    o1, o2 = AdamW(ours, lr=5e-4, weight_decay=wd), torch.optim.AdamW(ref, lr=5e-4, weight_decay=wd)
+    for it in range(5):
+        for p, q in zip(ours, ref):
+            gr = torch.randn(p.shape, generator=g).cuda() * (10.0 ** (it - 2))
+            p.grad, q.grad = gr.clone(), gr.clone()
+        if it == 3:
+            o1.param_groups[0]["lr"] = o2.param_groups[0]["lr"] = 1e-4
+        o1.step(); o2.step()
+    for p, q in zip(ours, ref):
+        assert (p - q).abs().max().item() <= 2e-6 * max(1.0, q.abs().max().item())
+    s1, s2 = o1.state_dict(), o2.state_dict()
+    assert s1["param_groups"][0].keys() >= {"lr", "betas", "eps", "weight_decay"}
+    for k in s2["state"]:
+        assert set(s1["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
+        assert float(s1["state"][k]["step"]) == float(s2["state"][k]["step"]) == 5
+        assert torch.allclose(s1["state"][k]["exp_avg"], s2["state"][k]["exp_avg"], rtol=1e-5, atol=1e-8)
+        assert torch.allclose(s1["state"][k]["exp_avg_sq"], s2["state"][k]["exp_avg_sq"], rtol=1e-5, atol=1e-10)
+    # checkpoints interoperate: torch's state loads into ours and the next step still agrees
+    o1.load_state_dict(s2)
+    for p, q in zip(ours, ref):
+        p.data.copy_(q.data)
+        gr = torch.randn(p.shape, generator=g).cuda()
+        p.grad, q.grad = gr.clone(), gr.clone()
+    o1.step(); o2.step()
+    for p, q in zip(ours, ref):
+        assert (p - q).abs().max().item() <= 2e-6 * max(1.0, q.abs().max().item())
+
+
+def test_fused_adamw_grad_scale_and_skipped_params():
+    from sl_hwgat_b200.optim import AdamW
+    a = torch.ones(10, device="cuda", requires_grad=True)
+    b = torch.ones(10, device="cuda", requires_grad=True)      # never gets a gradient
+    r = torch.ones(10, device="cuda", requires_grad=True)
+    o1, o2 = AdamW([a, b], lr=1e-2), torch.optim.AdamW([r], lr=1e-2)
+    a.grad = torch.full((10,), 8.0, device="cuda"); r.grad = torch.full((10,), 2.0, device="cuda")
+    o1.step(grad_scale=0.25); o2.step()
+    assert torch.allclose(a, r, rtol=1e-6) and torch.equal(b, torch.ones_like(b))
+    assert len(o1.state[b]) == 0

@@ -167,3 +167,18 @@ def test_gradient_allreduce_world2_equals_full_batch(tmp_path):
     assert len(full) == len(r["grads"])
     for a, b in zip(r["grads"], full):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+
+
+def test_fused_adamw_has_no_cpu_path():
+    """The optimizer mirrors torch.optim.AdamW's interface but only updates CUDA tensors."""
+    import torch
+    from sl_hwgat_b200 import _lib
+    from sl_hwgat_b200.optim import AdamW
+    p = torch.ones(4, requires_grad=True)
+    opt = AdamW([p], lr=1e-3)
+    assert opt.defaults["betas"] == (0.9, 0.999) and opt.defaults["weight_decay"] == 1e-2   # torch's defaults
+    p.grad = torch.ones(4)
+    with pytest.raises(_lib.HwgatError):
+        opt.step()
+    with pytest.raises(NotImplementedError):
+        AdamW([p], amsgrad=True)
