@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libhwgat_b200.so")
+LIB_PATH = os.environ.get("HWGAT_B200_LIB") or os.path.join(HERE, "lib", "libhwgat_b200.so")   # override: A/B builds
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
