@@ -209,7 +209,8 @@ def test_fused_adamw_matches_torch(wd):
             a, b = s1["state"][k][key], s2["state"][k][key]
             assert (a - b).abs().max().item() <= 1e-5 * b.abs().max().item()
     # checkpoints interoperate: torch's state loads into ours and the next step still agrees
-    o1.load_state_dict(s2)
+    import copy
+    o1.load_state_dict(copy.deepcopy(s2))       # (a checkpoint round trip copies; load_state_dict itself aliases)
     for p, q in zip(ours, ref):
         p.data.copy_(q.data)
         gr = torch.randn(p.shape, generator=g).cuda()
@@ -229,3 +230,26 @@ def test_fused_adamw_grad_scale_and_skipped_params():
     o1.step(grad_scale=0.25); o2.step()
     assert torch.allclose(a, r, rtol=1e-6) and torch.equal(b, torch.ones_like(b))
     assert len(o1.state[b]) == 0
+
+
+# ------------------------------------------------------------------ CUDA-graph inference (inference.py:95 path)
+def test_graphed_inference_matches_eager_and_is_batch1_safe():
+    from sl_hwgat_b200 import _lib
+    from sl_hwgat_b200.runtime import GraphedInference
+    T, classes = 16, 11
+    model, _, _ = build(T, classes)
+    model.train()
+    with pytest.raises(RuntimeError):
+        GraphedInference(model)                     # train mode: refused
+    model.eval()
+    fast = GraphedInference(model)
+    for B in (1, 3, 1):                             # batch 1 is what inference.py:95 feeds; shapes are cached
+        x = torch.rand(B, T, 64, 2, device="cuda")
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            want = model(x)
+        got = fast(x)
+        assert got.shape == (B, classes) and torch.equal(got, want)
+    assert len(fast._graphs) == 2
+    n0 = _lib.launch_count()
+    fast(torch.rand(1, T, 64, 2, device="cuda"))
+    assert _lib.launch_count() == n0                # replay: no host-side launches through the library
