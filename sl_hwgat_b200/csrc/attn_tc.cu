@@ -426,6 +426,22 @@ HW_DEV void store_rows_16x64(const float (&c)[8][4], float mul, bf16* __restrict
   }
 }
 
+// C fragments [16 x 64] -> bf16 -> global rows p0 (row g) and p1 (row g+8) in the PERMUTED column order of the dQKV
+// workspace: inside each head's 64-column block, logical column 8 nt + 2 t + b is stored at column 16 t + 2 nt + b,
+// i.e. the eight words a fragment thread holds for one row are contiguous: one 32-byte store per row, no shuffles.
+// The two consumers of dQKV undo it for free: the d_xn GEMM contracts over these columns (its transposed weight copy
+// is permuted the same way) and the d_w / d_b GEMM maps its output rows back (gemm_tc_tn, perm64).
+HW_DEV void store_rows_16x64_perm(const float (&c)[8][4], float mul, bf16* __restrict__ p0, bf16* __restrict__ p1, int t) {
+  uint32_t r0[8], r1[8];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    r0[nt] = pack_bf16(c[nt][0] * mul, c[nt][1] * mul);
+    r1[nt] = pack_bf16(c[nt][2] * mul, c[nt][3] * mul);
+  }
+  st_global32(p0 + 16 * t, r0);
+  st_global32(p1 + 16 * t, r1);
+}
+
 // ===========================================================================
 // K2 kernel.  Attention warps: ONE warp per window (all 32 query rows); the two warp sets (warps 4-7,
 // 8-11) work on alternate heads, one TMEM accumulator each.  Every q / k / v row is converted from
@@ -772,7 +788,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
             const uint32_t a1[4] = {db0[0][2], db0[1][2], db0[0][3], db0[1][3]};
             mma_16x64_k16_blocks(dq, a1, kb1);
           }
-          store_rows_16x64(dq, 0.125f, p.dqkv + tr[0] * d3 + h * kHd, p.dqkv + tr[1] * d3 + h * kHd, t);
+          store_rows_16x64_perm(dq, 0.125f, p.dqkv + tr[0] * d3 + h * kHd, p.dqkv + tr[1] * d3 + h * kHd, t);
           zero8x4(dq);
           {
             const uint32_t a0[4] = {db1[0][0], db1[1][0], db1[0][1], db1[1][1]};
@@ -780,7 +796,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
             const uint32_t a1[4] = {db1[0][2], db1[1][2], db1[0][3], db1[1][3]};
             mma_16x64_k16_blocks(dq, a1, kb1);
           }
-          store_rows_16x64(dq, 0.125f, p.dqkv + tr[2] * d3 + h * kHd, p.dqkv + tr[3] * d3 + h * kHd, t);
+          store_rows_16x64_perm(dq, 0.125f, p.dqkv + tr[2] * d3 + h * kHd, p.dqkv + tr[3] * d3 + h * kHd, t);
         }
         // ---- dv = P^T dO : key m tiles jt = 0,1; k steps = the two query groups
         {
@@ -801,8 +817,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
                                     movmatrix_trans(pb1[1][3])};
             mma_2x16x64_k16_blocks(dv0, dv1, a0, a1, ga1);
           }
-          store_rows_16x64(dv0, 1.f, p.dqkv + tr[0] * d3 + 2 * d + h * kHd, p.dqkv + tr[1] * d3 + 2 * d + h * kHd, t);
-          store_rows_16x64(dv1, 1.f, p.dqkv + tr[2] * d3 + 2 * d + h * kHd, p.dqkv + tr[3] * d3 + 2 * d + h * kHd, t);
+          store_rows_16x64_perm(dv0, 1.f, p.dqkv + tr[0] * d3 + 2 * d + h * kHd, p.dqkv + tr[1] * d3 + 2 * d + h * kHd, t);
+          store_rows_16x64_perm(dv1, 1.f, p.dqkv + tr[2] * d3 + 2 * d + h * kHd, p.dqkv + tr[3] * d3 + 2 * d + h * kHd, t);
         }
         // ---- dk = dS^T q (q carries the scale)
         {
@@ -823,8 +839,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
                                     movmatrix_trans(db1[1][3])};
             mma_2x16x64_k16_blocks(dk0, dk1, a0, a1, qa1);
           }
-          store_rows_16x64(dk0, 1.f, p.dqkv + tr[0] * d3 + d + h * kHd, p.dqkv + tr[1] * d3 + d + h * kHd, t);
-          store_rows_16x64(dk1, 1.f, p.dqkv + tr[2] * d3 + d + h * kHd, p.dqkv + tr[3] * d3 + d + h * kHd, t);
+          store_rows_16x64_perm(dk0, 1.f, p.dqkv + tr[0] * d3 + d + h * kHd, p.dqkv + tr[1] * d3 + d + h * kHd, t);
+          store_rows_16x64_perm(dk1, 1.f, p.dqkv + tr[2] * d3 + d + h * kHd, p.dqkv + tr[3] * d3 + d + h * kHd, t);
         }
       }
     }
@@ -881,10 +897,11 @@ int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s) {
   const int d = a.d, d3 = 3 * d;
   // d_xn[n, d] = dQKV[n, 3d] . Wqkv[3d, d]  (against Wqkv^T so that both operands are K-major)
   bf16* wt = dqkv + n * d3;
-  if ((st = transpose_bf16((const bf16*)a.w_qkv, wt, d3, d, s))) return st;
+  // (dQKV's columns are permuted inside each head block, see store_rows_16x64_perm: the copy is permuted alike)
+  if ((st = transpose_bf16((const bf16*)a.w_qkv, wt, d3, d, s, true))) return st;
   if ((st = gemm_tc_nt_epi_none(dqkv, wt, (bf16*)a.d_xn, n, d, d3, s))) return st;   // K10's GEMM (32-byte stores)
   // d_w[3d, d] = dQKV^T . xn ; d_b = column sums of dQKV (same kernel)
-  return gemm_tc_tn(dqkv, (const bf16*)a.xn, a.d_w, a.d_b, d3, d, n, s);
+  return gemm_tc_tn(dqkv, (const bf16*)a.xn, a.d_w, a.d_b, d3, d, n, s, true);
 }
 
 }  // namespace hwgat

@@ -177,7 +177,17 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_nt_kernel(const __grid_constan
 }
 
 // bf16 transpose [R][Cc] -> [Cc][R] (Wqkv -> Wqkv^T, 3d x d: tiny)
-__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R, int Cc) {
+// perm64: the input-row index r (= output column) is mapped through the dQKV column permutation of K3
+// (attn_tc.cu, store_rows_16x64_perm): inside each block of 64, 8 nt + 2 t + b -> 16 t + 2 nt + b.
+HW_DEV int perm64_fwd(int r) {
+  const int p = r & 63, nt = p >> 3, t = (p >> 1) & 3, b = p & 1;
+  return (r & ~63) + 16 * t + 2 * nt + b;
+}
+HW_DEV int perm64_inv(int r) {
+  const int p = r & 63, t = p >> 4, nt = (p >> 1) & 7, b = p & 1;
+  return (r & ~63) + 8 * nt + 2 * t + b;
+}
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R, int Cc, bool perm64) {
   __shared__ bf16 t[32][33];
   int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8)
@@ -185,11 +195,12 @@ __global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restr
   __syncthreads();
   int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += 8)
-    if (c0 + i < Cc && r < R) out[(size_t)(c0 + i) * R + r] = t[threadIdx.x][i];
+    if (c0 + i < Cc && r < R) out[(size_t)(c0 + i) * R + (perm64 ? perm64_fwd(r) : r)] = t[threadIdx.x][i];
 }
 
-int transpose_bf16(const bf16* in, bf16* out, int R, int Cc, cudaStream_t s) {
-  transpose_bf16_kernel<<<dim3((Cc + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, s>>>(in, out, R, Cc);
+int transpose_bf16(const bf16* in, bf16* out, int R, int Cc, cudaStream_t s, bool perm64) {
+  if (perm64 && R % 64) return HWGAT_ERR_UNSUPPORTED;
+  transpose_bf16_kernel<<<dim3((Cc + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, s>>>(in, out, R, Cc, perm64);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -248,7 +259,8 @@ template <int BN>
 __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB,
                                                             float* __restrict__ C, float* __restrict__ colsum, int M,
-                                                            int N, int k_blocks_total, int k_blocks_per_cta) {
+                                                            int N, int k_blocks_total, int k_blocks_per_cta,
+                                                            bool perm64) {
   using Cfg = GemmTnCfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -321,7 +333,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
     const int q = warp & 3;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int row = mb * 128 + q * 32 + lane;
+    const int arow = mb * 128 + q * 32 + lane;              // row of A^T = column of A
+    const int row = perm64 ? perm64_inv(arow) : arow;       // A's columns are K3's permuted dQKV columns: undo
     float* crow = C + (size_t)row * N + (size_t)nb * BN;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
 
 template <int BN>
 static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd,
-                     cudaStream_t s) {
+                     cudaStream_t s, bool perm64) {
   using Cfg = GemmTnCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -365,16 +378,18 @@ static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int
   if (splits > kblocks) splits = kblocks;
   const int per = (kblocks + splits - 1) / splits;
   splits = (kblocks + per - 1) / per;
-  gemm_tc_tn_kernel<BN><<<dim3(tiles, splits), 192, Cfg::kSmem, s>>>(tmA, tmB, C, colsum, M, N, kblocks, per);
+  gemm_tc_tn_kernel<BN><<<dim3(tiles, splits), 192, Cfg::kSmem, s>>>(tmA, tmB, C, colsum, M, N, kblocks, per, perm64);
   count_launch();
   return (int)cudaGetLastError();
 }
 
 // C[M,N] = A[Kd,M]^T . B[Kd,N] (fp32 out), colsum[M] = column sums of A; M % 128 == 0, N % 128 == 0, Kd % 64 == 0
-int gemm_tc_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd, cudaStream_t s) {
+// perm64: rows of C / entries of colsum are written through the inverse of K3's dQKV column permutation
+int gemm_tc_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd, cudaStream_t s,
+               bool perm64) {
   if (M % 128 || N % 128 || Kd % 64) return HWGAT_ERR_UNSUPPORTED;
-  if (N % 256 == 0) return launch_tn<256>(A, Bm, C, colsum, M, N, Kd, s);
-  return launch_tn<128>(A, Bm, C, colsum, M, N, Kd, s);
+  if (N % 256 == 0) return launch_tn<256>(A, Bm, C, colsum, M, N, Kd, s, perm64);
+  return launch_tn<128>(A, Bm, C, colsum, M, N, Kd, s, perm64);
 }
 
 }  // namespace hwgat
