@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
 
 // ---------------------------------------------------------------------------
 // K6: x1 = res + dropout(a0 + bias)  and, fused, the LayerNorm that follows it: y = LN(x1) as bf16.
-// Thread mapping as K5.  Dropout flags of a 4-element granule come from one Philox call keyed by the granule
-// index (row*d + col)/4, identically in forward and backward.
+// Thread mapping as K5.  Dropout flags of an 8-element granule (two of the lane's float4) come from one Philox call
+// keyed by (row, pair, lane column), identically in forward and backward.
 // ---------------------------------------------------------------------------
 template <int kL, bool kLN>
 __global__ void __launch_bounds__(256) bda_ln_fwd_kernel(const float* __restrict__ res, const bf16* __restrict__ a0,
@@ -206,10 +206,14 @@ __global__ void __launch_bounds__(256) bda_ln_fwd_kernel(const float* __restrict
       av[i] = *reinterpret_cast<const uint2*>(a0 + e);
     }
     float s = 0.f;
+    // one Philox call covers 8 elements: the lane's float4 pair (i, i+1); granule id = (row, pair, lane column)
+    uint32_t keep2[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      keep2[j] = thresh ? keep8(((unsigned long long)row * 2 + j) * kL + lc, offset, seed, thresh) : 0xFFu;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const long long e = row * d + i * 4 * kL + lc * 4;
-      const uint32_t keep = thresh ? keep4((unsigned long long)e >> 2, offset, seed, thresh) : 0xFu;
+      const uint32_t keep = keep2[i >> 1] >> (4 * (i & 1));
       v[i].x += (keep & 1u) ? (bf16_lo(av[i].x) + bs[i].x) * scale : 0.f;
       v[i].y += (keep & 2u) ? (bf16_hi(av[i].x) + bs[i].y) * scale : 0.f;
       v[i].z += (keep & 4u) ? (bf16_lo(av[i].y) + bs[i].z) * scale : 0.f;
@@ -301,10 +305,14 @@ __global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const float4*>(g_x1 + row * d + i * 4 * kL + lc * 4);
     }
+    uint32_t keep2[2];   // same granules as the forward kernel
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      keep2[j] = thresh ? keep8(((unsigned long long)row * 2 + j) * kL + lc, offset, seed, thresh) : 0xFFu;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long long e = row * d + i * 4 * kL + lc * 4;
-      const uint32_t keep = thresh ? keep4((unsigned long long)e >> 2, offset, seed, thresh) : 0xFu;
+      const uint32_t keep = keep2[i >> 1] >> (4 * (i & 1));
       const float4 da = make_float4((keep & 1u) ? o[i].x * scale : 0.f, (keep & 2u) ? o[i].y * scale : 0.f,
                                     (keep & 4u) ? o[i].z * scale : 0.f, (keep & 8u) ? o[i].w * scale : 0.f);
       uint2 pk;
