@@ -210,7 +210,7 @@ int hwgat_bias_gelu_dropout_bwd(const void* u0, const float* bias, const void* d
 
 static int check_ffn(long long n, int d, int hidden) {
   if (n < 0 || d <= 0 || hidden <= 0) return HWGAT_ERR_SHAPE;
-  if (n % 128 || d % 128 || hidden % 128 || n > 0x7fffffffLL) return HWGAT_ERR_UNSUPPORTED;
+  if (n % 128 || d % 128 || hidden % 128 || hidden > 2048 || n > 0x7fffffffLL) return HWGAT_ERR_UNSUPPORTED;
   return HWGAT_OK;
 }
 

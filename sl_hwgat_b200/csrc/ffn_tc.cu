@@ -41,6 +41,8 @@ constexpr int kFM = 128, kFK = 64;
 template <int EPI>
 struct EpiWarps { static constexpr int kWarps = EPI == 1 ? 16 : 8; static constexpr int kThreads = 32 * (2 + kWarps); };
 
+constexpr int kMaxBiasN = 2048;  // widest bias the GELU epilogue stages in shared memory (hidden <= 2048)
+
 template <int BN>
 struct FfnCfg {
   static constexpr int kStages = BN == 256 ? 4 : 6;
@@ -48,12 +50,13 @@ struct FfnCfg {
   static constexpr int kBBytes = BN * kFK * 2;
   static constexpr int kStage = kABytes + kBBytes;
   static constexpr int kBarOff = kStages * kStage;
-  static constexpr int kSmem = kBarOff + 256 + 1024;
+  static constexpr int kBiasOff = kBarOff + 256;        // fp32 bias of all N columns (GELU epilogue)
+  static constexpr int kSmem = kBiasOff + kMaxBiasN * 4 + 1024;
   static constexpr int kTmemCols = 2 * BN;
 };
 
 template <int EPI>
-HW_DEV void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& e, size_t elem, int col) {
+HW_DEV void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& e, size_t elem, int col, const float* sbias) {
   // r: 32 consecutive columns of one row (fp32 accumulator); elem = row * N + col.  Every store is 32 bytes
   // = one full sector of the thread's own row.
   if (EPI == kEpiNone) {
@@ -83,15 +86,11 @@ HW_DEV void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& e, size_t ele
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int c8 = 16 * g + 8 * hh;
-        float b[8];
-        if (e.bias) {
-          const float4 b0 = *reinterpret_cast<const float4*>(e.bias + col + c8);
-          const float4 b1 = *reinterpret_cast<const float4*>(e.bias + col + c8 + 4);
-          b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) b[i] = 0.f;
-        }
+        // bias from shared memory (broadcast reads): read from global here, the loads sat on the long scoreboard
+        // in front of every chunk (30 % of the kernel's stall samples)
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + col + c8);
+        const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + c8 + 4);
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         // same stream and granule index as K7 (bias_gelu_dropout): vector (row * N + col) / 8 of the flattened
         // tensor, element 2j <- low half of word j, element 2j+1 <- high half (keep8).  The 16-bit compares are
         // done in place: (w << 16) >= (t << 16) and w >= (t << 16), no mask word is assembled.
@@ -134,9 +133,12 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_kernel
   uint64_t* acc_full = empty + Cfg::kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::kBiasOff);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blocks = N / BN, m_blocks = M / kFM, tiles = n_blocks * m_blocks, nk = K / kFK;
+  if (EPI == kEpiGelu)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sbias[i] = e.bias ? e.bias[i] : 0.f;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_kernel
           uint32_t r[32];
           tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + half * kHalf + c, r);
           tmem_ld_wait();
-          epilogue_chunk<EPI>(r, e, elem0 + c, col0 + c);
+          epilogue_chunk<EPI>(r, e, elem0 + c, col0 + c, sbias);
         }
       }
       tc_fence_before();
@@ -287,6 +289,7 @@ int ffn_fwd(const bf16* h, const bf16* w1, const float* b1, const bf16* w2, bf16
   EpiArgs e{};
   e.C = act; e.C2 = gp; e.bias = b1; e.thresh = drop_threshold16(p); e.scale = drop_scale16(e.thresh);
   e.seed = seed; e.offset = offset;
+  if (hidden > kMaxBiasN) return HWGAT_ERR_UNSUPPORTED;
   int st = gemm_nt_epi<kEpiGelu>(h, w1, e, n, hidden, d, s);          // act, gp  [n, hidden]
   if (st) return st;
   EpiArgs e2{};

@@ -432,12 +432,12 @@ def feed_forward_core(h: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tens
                       training: bool) -> torch.Tensor:
     """dropout(gelu(h @ w1.T + b1)) @ w2.T as bf16: ff.fc1, ff.act, ff.drop and ff.fc2's matmul (HWGATE.py:130-134);
     fc2's bias, the second dropout and the residual add are K6's (bias_dropout_add_ln).
-    h: (..., d) with prod(...) % 128 == 0, d % 128 == 0, hidden % 128 == 0."""
+    h: (..., d) with prod(...) % 128 == 0, d % 128 == 0, hidden % 128 == 0, hidden <= 2048."""
     return _FeedForwardCore.apply(h, w1, b1, w2, p if training else 0.0)
 
 
 def ffn_supported(n_tokens: int, d: int, hidden: int) -> bool:
-    return n_tokens % 128 == 0 and d % 128 == 0 and hidden % 128 == 0
+    return n_tokens % 128 == 0 and d % 128 == 0 and hidden % 128 == 0 and hidden <= 2048
 
 
 # --------------------------------------------------------------------------
