@@ -203,12 +203,11 @@ int hwgat_adamw_step(int n_tensors, float* const* params, const float* const* gr
                      float* const* exp_avg_sq, const long long* sizes, double lr, double beta1, double beta2, double eps,
                      double weight_decay, long long step, float grad_scale, hwgat_stream_t stream);
 
-/* Diagnostic: the plain bf16 GEMM K3 uses for d_xn, C[M,N] = A[M,K] . Bt[N,K]^T (fp32 accumulate,
- * TMA + tcgen05).  M % 128 == 0, N % 128 == 0, K % 64 == 0; all row-major bf16 device pointers. */
-int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream);
-/* Diagnostic: the same product through K10's GEMM (eight epilogue warps, plain bf16 epilogue). */
-int hwgat_debug_gemm_nt_epi(const void* A, const void* Bt, void* C, long long M, int N, int K, hwgat_stream_t stream);
-/* Diagnostic: the GEMM K3 uses for d_w and d_b: C[M,N] (fp32) = A[Kd,M]^T . B[Kd,N], colsum[M] = column
+/* Diagnostic: the plain-epilogue form of K10's GEMM, which K3 also uses for d_xn: C[M,N] = A[M,K] . Bt[N,K]^T
+ * (bf16 operands, fp32 accumulate, TMA + tcgen05, 32-byte row stores).  M % 128 == 0, N % 128 == 0, K % 64 == 0;
+ * all row-major bf16 device pointers. */
+int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, long long M, int N, int K, hwgat_stream_t stream);
+/* Diagnostic: the GEMM K3 and K10 use for weight and bias gradients: C[M,N] (fp32) = A[Kd,M]^T . B[Kd,N], colsum[M] = column
  * sums of A.  M % 128 == 0, N % 128 == 0, Kd % 64 == 0; A, B bf16 row-major device pointers. */
 int hwgat_debug_gemm_tn(const void* A, const void* B, float* C, float* colsum, int M, int N, long long Kd,
                         hwgat_stream_t stream);

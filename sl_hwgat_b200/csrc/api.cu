@@ -27,7 +27,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 7; }
+int hwgat_version(void) { return 8; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -303,15 +303,7 @@ int hwgat_adamw_step(int n_tensors, float* const* params, const float* const* gr
                     grad_scale, (cudaStream_t)stream);
 }
 
-int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, int M, int N, int K, hwgat_stream_t stream) {
-  if (!A || !Bt || !C) return HWGAT_ERR_NULL;
-  if (misaligned(A) || misaligned(Bt) || misaligned(C)) return HWGAT_ERR_ALIGN;
-  if (M <= 0 || N <= 0 || K <= 0) return HWGAT_ERR_SHAPE;
-  return gemm_tc_nt((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bt, (__nv_bfloat16*)C, M, N, K,
-                    (cudaStream_t)stream);
-}
-
-int hwgat_debug_gemm_nt_epi(const void* A, const void* Bt, void* C, long long M, int N, int K, hwgat_stream_t stream) {
+int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, long long M, int N, int K, hwgat_stream_t stream) {
   if (!A || !Bt || !C) return HWGAT_ERR_NULL;
   if (misaligned(A) || misaligned(Bt) || misaligned(C)) return HWGAT_ERR_ALIGN;
   if (M <= 0 || N <= 0 || K <= 0) return HWGAT_ERR_SHAPE;

@@ -149,7 +149,6 @@ int attn_fwd_bf16(const AttnArgs& a, cudaStream_t s);
 int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s);
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t s);
 int attn_bwd_tc(const AttnArgs& a, __nv_bfloat16* dqkv, cudaStream_t s);
-int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* Bt, __nv_bfloat16* C, int M, int N, int K, cudaStream_t s);
 int gemm_tc_tn(const __nv_bfloat16* A, const __nv_bfloat16* Bm, float* C, float* colsum, int M, int N, long long Kd,
                cudaStream_t s, bool perm64 = false);
 int transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int R, int Cc, cudaStream_t s, bool perm64 = false);

@@ -484,6 +484,35 @@ def test_feed_forward_core_dropout(p):
     assert torch.equal(y2 != 0, y.detach() != 0) and not torch.equal(y3 != 0, y2 != 0)
 
 
+@pytest.mark.parametrize("d", [128, 512])
+def test_feed_forward_core_full_size_replication(d):
+    """K10 at the BASELINE config-3 size (512 x 64 x 64 x 128 activation elements per level): the token rows are
+    1024 copies of a small, fp64-checked block, so every copy's output and input gradient must be bit-identical to
+    the small case and the weight gradients must be 1024 x the small case's (a sum over tokens)."""
+    from sl_hwgat_b200 import ops
+    g = torch.Generator().manual_seed(d)
+    hidden = 2 * d
+    n_small = 512 * 64 * 64 * 128 // d // 1024            # 2048 rows (d=128) / 512 rows (d=512)
+    h0 = torch.randn(n_small, d, generator=g).to(torch.bfloat16).cuda()
+    gv0 = torch.randn(n_small, d, generator=g).to(torch.bfloat16).cuda()
+    w1 = (torch.randn(hidden, d, generator=g) / d ** 0.5).cuda().requires_grad_(True)
+    b1 = (0.3 * torch.randn(hidden, generator=g)).cuda().requires_grad_(True)
+    w2 = (torch.randn(d, hidden, generator=g) / hidden ** 0.5).cuda().requires_grad_(True)
+
+    def run(h, gv):
+        for t in (w1, b1, w2):
+            t.grad = None
+        h = h.clone().requires_grad_(True)
+        v = ops.feed_forward_core(h, w1, b1, w2, 0.0, True)
+        v.backward(gv)
+        return v.detach(), h.grad, w1.grad.clone(), b1.grad.clone(), w2.grad.clone()
+
+    vs, dhs, dw1s, db1s, dw2s = run(h0, gv0)
+    vb, dhb, dw1b, db1b, dw2b = run(h0.repeat(1024, 1), gv0.repeat(1024, 1))
+    assert torch.equal(vb, vs.repeat(1024, 1)) and torch.equal(dhb, dhs.repeat(1024, 1))
+    assert rel_l2(dw1b, dw1s * 1024) < 1e-3 and rel_l2(dw2b, dw2s * 1024) < 1e-3 and rel_l2(db1b, db1s * 1024) < 1e-3
+
+
 def test_feed_forward_core_rejects_unsupported_shapes():
     from sl_hwgat_b200 import _lib, ops
     h = torch.zeros(100, 128, device="cuda", dtype=torch.bfloat16)          # 100 rows: not a multiple of 128
