@@ -208,9 +208,14 @@ int hwgat_adamw_step(int n_tensors, float* const* params, const float* const* gr
  * all row-major bf16 device pointers. */
 int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, long long M, int N, int K, hwgat_stream_t stream);
 /* Diagnostic: the GEMM K3 and K10 use for weight and bias gradients: C[M,N] (fp32) = A[Kd,M]^T . B[Kd,N], colsum[M] = column
- * sums of A.  M % 128 == 0, N % 128 == 0, Kd % 64 == 0; A, B bf16 row-major device pointers. */
+ * sums of A (colsum may be NULL: not computed).  M % 128 == 0, N % 128 == 0, Kd % 64 == 0; A, B bf16 row-major device
+ * pointers.  N % 256 == 0 and M >= 256 run on CTA pairs (cta_group::2) unless hwgat_debug_set_gemm_pair(0). */
 int hwgat_debug_gemm_tn(const void* A, const void* B, float* C, float* colsum, int M, int N, long long Kd,
                         hwgat_stream_t stream);
+
+/* Diagnostic (A/B measurements): wide GEMMs (N % 256 == 0, M >= 256) run on CTA pairs (cta_group::2, 256 x 256
+ * tiles) when on != 0 (the default), on the single-CTA 128 x 256 kernel otherwise.  Returns the previous setting. */
+int hwgat_debug_set_gemm_pair(int on);
 
 /* Number of kernel launches issued through this library since load (all
  * streams, this process) - what bench.py reports as "gpu_launches". */

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("HWGAT_B200_LIB") or os.path.join(HERE, "lib", "libhwg
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # name -> (restype, argtypes); must list every symbol of include/hwgat_b200.h
 SIGNATURES = {
@@ -50,6 +50,7 @@ SIGNATURES = {
                                   c_double, c_double, c_longlong, c_float, c_void_p]),
     "hwgat_debug_gemm_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
     "hwgat_debug_gemm_tn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p]),
+    "hwgat_debug_set_gemm_pair": (c_int, [c_int]),
     "hwgat_merge_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     "hwgat_merge_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
 }

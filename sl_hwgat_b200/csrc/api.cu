@@ -27,7 +27,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 8; }
+int hwgat_version(void) { return 9; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -313,11 +313,13 @@ int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, long long M, int
 
 int hwgat_debug_gemm_tn(const void* A, const void* B, float* C, float* colsum, int M, int N, long long Kd,
                         hwgat_stream_t stream) {
-  if (!A || !B || !C || !colsum) return HWGAT_ERR_NULL;
+  if (!A || !B || !C) return HWGAT_ERR_NULL;   /* colsum may be NULL: no column sums */
   if (misaligned(A) || misaligned(B) || misaligned(C)) return HWGAT_ERR_ALIGN;
   if (M <= 0 || N <= 0 || Kd <= 0) return HWGAT_ERR_SHAPE;
   return gemm_tc_tn((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, C, colsum, M, N, Kd, (cudaStream_t)stream);
 }
+
+int hwgat_debug_set_gemm_pair(int on) { return set_gemm_pair(on != 0) ? 1 : 0; }
 
 static int merge_common(const void* src, void* dst, int B, int F, int K, int d, int TP, int dtype, bool backward,
                         hwgat_stream_t stream) {

@@ -152,6 +152,8 @@ int attn_bwd_tc(const AttnArgs& a, __nv_bfloat16* dqkv, cudaStream_t s);
 int gemm_tc_tn(const __nv_bfloat16* A, const __nv_bfloat16* Bm, float* C, float* colsum, int M, int N, long long Kd,
                cudaStream_t s, bool perm64 = false);
 int transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int R, int Cc, cudaStream_t s, bool perm64 = false);
+bool gemm_pair_enabled();
+bool set_gemm_pair(bool on);
 int gemm_tc_nt_epi_none(const __nv_bfloat16* A, const __nv_bfloat16* Bt, __nv_bfloat16* C, long long M, int N, int K,
                         cudaStream_t s);
 int ffn_fwd(const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1, const __nv_bfloat16* w2,

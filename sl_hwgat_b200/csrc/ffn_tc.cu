@@ -121,6 +121,48 @@ HW_DEV void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& e, size_t ele
   }
 }
 
+// One epilogue warp's share of a tile: wait for the accumulator, read kHalf columns of this thread's row from TMEM
+// (32 at a time), apply the epilogue, store.  taddr = TMEM address of the warp's lane quarter and first column.
+template <int EPI, int kHalf>
+HW_DEV void epilogue_tile(const EpiArgs& e, uint64_t* acc_full_bar, uint32_t parity, uint32_t taddr, size_t elem0, int col0,
+                          const float* sbias) {
+  if constexpr (EPI == kEpiMul) {
+    // The factor rows are fetched BEFORE the accumulator is waited for: a row-per-thread load touches 32 lines
+    // per instruction, and issued inside the chunk loop its latency was exposed once per chunk (tensor pipe
+    // 39 % busy on a GEMM whose HBM time and MMA time are both ~half of what it took).
+    uint32_t gq[kHalf / 16][8];
+#pragma unroll
+    for (int j = 0; j < kHalf / 16; ++j) ld_global32(e.G + elem0 + 16 * j, gq[j]);
+    mbar_wait(acc_full_bar, parity);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < kHalf; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = pack_bf16(__uint_as_float(r[16 * g + 2 * i]) * bf16_lo(gq[c / 16 + g][i]),
+                           __uint_as_float(r[16 * g + 2 * i + 1]) * bf16_hi(gq[c / 16 + g][i]));
+        st_global32(e.C + elem0 + c + 16 * g, o);
+      }
+    }
+  } else {
+    mbar_wait(acc_full_bar, parity);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < kHalf; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c, r);
+      tmem_ld_wait();
+      epilogue_chunk<EPI>(r, e, elem0 + c, col0 + c, sbias);
+    }
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
@@ -203,41 +245,7 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_kernel
       const size_t row = (size_t)mb * kFM + q * 32 + lane;
       const int col0 = nb * BN + half * kHalf;
       const size_t elem0 = row * N + col0;
-      if constexpr (EPI == kEpiMul) {
-        // The factor rows are fetched BEFORE the accumulator is waited for: a row-per-thread load touches 32 lines
-        // per instruction, and issued inside the chunk loop its latency was exposed once per chunk (tensor pipe
-        // 39 % busy on a GEMM whose HBM time and MMA time are both ~half of what it took).
-        uint32_t gq[kHalf / 16][8];
-#pragma unroll
-        for (int j = 0; j < kHalf / 16; ++j) ld_global32(e.G + elem0 + 16 * j, gq[j]);
-        mbar_wait(&acc_full[buf], (it >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < kHalf; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + half * kHalf + c, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint32_t o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              o[i] = pack_bf16(__uint_as_float(r[16 * g + 2 * i]) * bf16_lo(gq[c / 16 + g][i]),
-                               __uint_as_float(r[16 * g + 2 * i + 1]) * bf16_hi(gq[c / 16 + g][i]));
-            st_global32(e.C + elem0 + c + 16 * g, o);
-          }
-        }
-      } else {
-        mbar_wait(&acc_full[buf], (it >> 1) & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < kHalf; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + half * kHalf + c, r);
-          tmem_ld_wait();
-          epilogue_chunk<EPI>(r, e, elem0 + c, col0 + c, sbias);
-        }
-      }
+      epilogue_tile<EPI, kHalf>(e, acc_full + buf, (it >> 1) & 1, tmem + ((uint32_t)(q * 32) << 16) + buf * BN + half * kHalf, elem0, col0, sbias);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -267,11 +275,191 @@ static int launch_epi(const bf16* A, const bf16* Bt, const EpiArgs& e, int M, in
   return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one cluster of two CTAs (the two SMs of a TPC) computes a 256 x 256 tile.
+// A single-CTA M=128, N=256 SS MMA reads 12 KB of operands from shared memory per 128 clocks while TMA writes
+// 48 KB per 512: 190 B/clk against the 128 B/clk/SM shared-memory port, which is why the single-CTA kernel's
+// tensor pipe stops at ~73 %.  In a pair each CTA stages its own 128 rows of A and only HALF of B's 256 rows
+// (32 KB per k block instead of 48) and its tensor core reads the other half from the peer: 128 B/clk.
+//   leader (cluster rank 0): `full[s]` counts the TMA bytes of BOTH CTAs; its warp 1 issues the MMAs and commits
+//   with a multicast arrive to `empty[s]` / `acc_full[b]` of both CTAs; `acc_empty[b]` (leader) collects the
+//   arrivals of both CTAs' epilogue warps.  The peer's warp 1 only owns its TMEM allocation.
+// ---------------------------------------------------------------------------
+struct PairCfg {
+  static constexpr int kBN = 256;
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = kFM * kFK * 2;          // this CTA's 128 rows of A
+  static constexpr int kBBytes = (kBN / 2) * kFK * 2;    // this CTA's 128 of B's 256 rows
+  static constexpr int kStage = kABytes + kBBytes;       // 32 KB
+  static constexpr int kBarOff = kStages * kStage;
+  static constexpr int kBiasOff = kBarOff + 256;
+  static constexpr int kSmem = kBiasOff + kMaxBiasN * 4 + 1024;
+  static constexpr int kTmemCols = 2 * kBN;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_pair_kernel(
+    const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiArgs e, int M, int N, int K) {
+  using Cfg = PairCfg;
+  constexpr int BN = Cfg::kBN;
+  extern __shared__ unsigned char smem_raw[];
+  // the dynamic shared-memory window starts at the same offset in both CTAs, so the aligned offsets agree
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* acc_full = empty + Cfg::kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::kBiasOff);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int n_blocks = N / BN, m_blocks = (M + 2 * kFM - 1) / (2 * kFM), tiles = n_blocks * m_blocks, nk = K / kFK;
+  if (EPI == kEpiGelu)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sbias[i] = e.bias ? e.bias[i] : 0.f;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * EpiWarps<EPI>::kWarps); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before either touches the other's
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = pair; tile < tiles; tile += npairs) {
+        const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait_cluster(&empty[s], ph ^ 1);
+          unsigned char* st = smem + s * Cfg::kStage;
+          const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::kStage);
+          tma_load_2d_pair(st, &tmA, lead_full, kb * kFK, (2 * mb + (int)rank) * kFM);     // rows past M: zero fill
+          tma_load_2d_pair(st + Cfg::kABytes, &tmB, lead_full, kb * kFK, nb * BN + (int)rank * (BN / 2));
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kFM, BN);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int tile = pair; tile < tiles; tile += npairs, ++it) {
+        const int buf = it & 1;
+        mbar_wait_cluster(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait_cluster(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int ks = 0; ks < kFK / 16; ++ks)
+            umma_bf16_pair(tmem + buf * BN, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
+                           (kb | ks) != 0);
+          umma_commit_pair(&empty[s]);
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit_pair(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int kHalf = BN / (EpiWarps<EPI>::kWarps / 4);
+    int it = 0;
+    for (int tile = pair; tile < tiles; tile += npairs, ++it) {
+      const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
+      const int buf = it & 1;
+      const size_t row = (size_t)(2 * mb + (int)rank) * kFM + q * 32 + lane;
+      const int col0 = nb * BN + half * kHalf;
+      if (row < (size_t)M) {
+        epilogue_tile<EPI, kHalf>(e, acc_full + buf, (it >> 1) & 1,
+                                  tmem + ((uint32_t)(q * 32) << 16) + buf * BN + half * kHalf, row * N + col0, col0, sbias);
+      } else {   // odd number of 128-row blocks: the peer's half of the last tile is padding (warp-uniform)
+        mbar_wait(acc_full + buf, (it >> 1) & 1);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the leader's MMAs read the peer's shared memory: neither CTA may exit early
+  if (warp == 1) tmem_dealloc_pair(tmem, Cfg::kTmemCols);
+}
+
+static int g_gemm_pair = -1;
+bool gemm_pair_enabled() {
+  if (g_gemm_pair < 0) {
+    const char* s = getenv("HWGAT_GEMM_PAIR");   // A/B measurements only; default on
+    g_gemm_pair = (s && s[0] == '0') ? 0 : 1;
+  }
+  return g_gemm_pair != 0;
+}
+bool set_gemm_pair(bool on) {
+  const bool prev = gemm_pair_enabled();
+  g_gemm_pair = on ? 1 : 0;
+  return prev;
+}
+
+template <int EPI>
+static int launch_epi_pair(const bf16* A, const bf16* Bt, const EpiArgs& e, int M, int N, int K, cudaStream_t s) {
+  using Cfg = PairCfg;
+  static bool attr_done = false;
+  static int max_clusters = 0;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(EpiWarps<EPI>::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmem;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_nt_epi_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    cfg.gridDim = dim3(148);
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, gemm_nt_epi_pair_kernel<EPI>, &cfg) != cudaSuccess || max_clusters < 1) {
+      cudaGetLastError();
+      max_clusters = 74;
+    }
+    if (max_clusters > 74) max_clusters = 74;
+    attr_done = true;
+  }
+  CUtensorMap tmA, tmB;
+  int st;
+  if ((st = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, kFM))) return st;
+  if ((st = make_tmap_2d(&tmB, Bt, (uint64_t)N, (uint64_t)K, Cfg::kBN / 2))) return st;
+  const int tiles = ((M + 2 * kFM - 1) / (2 * kFM)) * (N / Cfg::kBN);
+  const int pairs = tiles < max_clusters ? tiles : max_clusters;
+  cfg.gridDim = dim3(2 * pairs);
+  cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_nt_epi_pair_kernel<EPI>, tmA, tmB, e, M, N, K);
+  count_launch();
+  return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
+}
+
 // C[M,N] = epilogue(A[M,K] . Bt[N,K]^T); M % 128 == 0, N % 128 == 0, K % 64 == 0
 template <int EPI>
 static int gemm_nt_epi(const bf16* A, const bf16* Bt, const EpiArgs& e, long long M, int N, int K, cudaStream_t s) {
   if (M % kFM || K % kFK || N % 128 || M > 0x7fffffffLL) return HWGAT_ERR_UNSUPPORTED;
-  if (N % 256 == 0) return launch_epi<256, EPI>(A, Bt, e, (int)M, N, K, s);
+  if (N % 256 == 0) {
+    // CTA pairs (256 x 256 tiles) pay off once the k loop is long enough to be tensor-bound (measured: +5-8 % at
+    // K >= 768, -5 % at K <= 512 where the GEMM is bound by its HBM writes and the pair only adds hand-shakes)
+    if (gemm_pair_enabled() && M >= 2 * kFM && K >= 768) return launch_epi_pair<EPI>(A, Bt, e, (int)M, N, K, s);
+    return launch_epi<256, EPI>(A, Bt, e, (int)M, N, K, s);
+  }
   return launch_epi<128, EPI>(A, Bt, e, (int)M, N, K, s);
 }
 
@@ -307,13 +495,12 @@ int ffn_bwd(const bf16* dv0, const bf16* h, const bf16* act, const bf16* gp, con
   bf16* du0 = (bf16*)workspace;
   bf16* w2t = du0 + (size_t)n * hidden;       // [hidden, d]
   bf16* w1t = w2t + (size_t)d * hidden;       // [d, hidden]
-  float* db2 = (float*)(w1t + (size_t)d * hidden);
   int st;
   if ((st = transpose_bf16(w2, w2t, d, hidden, s))) return st;          // W2 is [d, hidden]
   EpiArgs e{};
   e.C = du0; e.G = gp;
   if ((st = gemm_nt_epi<kEpiMul>(dv0, w2t, e, n, hidden, d, s))) return st;    // du0 = (dv0 . W2) o gp
-  if ((st = gemm_tc_tn(dv0, act, dw2, db2, d, hidden, n, s))) return st;       // dW2 [d, hidden] = dv0^T . act
+  if ((st = gemm_tc_tn(dv0, act, dw2, nullptr, d, hidden, n, s))) return st;   // dW2 [d, hidden] = dv0^T . act (db2 comes from K6')
   if ((st = gemm_tc_tn(du0, h, dw1, db1, hidden, d, n, s))) return st;         // dW1 [hidden, d], db1 = colsum(du0)
   if ((st = transpose_bf16(w1, w1t, hidden, d, s))) return st;          // W1 is [hidden, d]
   EpiArgs e2{};

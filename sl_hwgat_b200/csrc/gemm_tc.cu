@@ -107,6 +107,32 @@ struct GemmTnCfg {
   static constexpr int kOnesCol = BN;                  // TMEM column of the ones product
 };
 
+// MMA issue loop over k blocks [kb, kend).  SUM: also the column-sum MMA (N = 16 against the all-ones tile), which
+// re-reads the whole A slice and costs ~1/4 of the main MMA.  The loop exists in both forms because a predicated-off
+// UTCHMMA is not free (measured: a no-sum GEMM with `@!p UTCHMMA` in its loop ran 15 % slower than with a branch).
+// main_first / sum_first: k block whose first MMA overwrites the accumulator instead of adding to it.
+template <int BN, bool SUM>
+HW_DEV void tn_issue(unsigned char* smem, uint64_t* full, uint64_t* empty, uint32_t tmem, int kb, int kend, int main_first,
+                     int sum_first, int& s, uint32_t& ph) {
+  using Cfg = GemmTnCfg<BN>;
+  constexpr uint32_t idesc = umma_idesc_bf16(128, BN, true, true);
+  constexpr uint32_t idesc1 = umma_idesc_bf16(128, 16, true, true);
+  const uint32_t sones = smem_u32(smem + Cfg::kOnesOff);
+  for (; kb < kend; ++kb) {
+    mbar_wait(&full[s], ph);
+    tc_fence_after();
+    const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {  // 16 tokens per step = two 8-row atoms = 2 KB
+      const uint64_t da = umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024);
+      umma_bf16(tmem, da, umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024), idesc, (kb > main_first) | (ks > 0));
+      if (SUM) umma_bf16(tmem + Cfg::kOnesCol, da, umma_desc_mn_sw128(sones, 8192, 1024), idesc1, (kb > sum_first) | (ks > 0));
+    }
+    umma_commit(&empty[s]);
+    if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB,
@@ -125,7 +151,12 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
   const int mb = blockIdx.x / n_blocks, nb = blockIdx.x - mb * n_blocks;
   const int kb0 = blockIdx.y * k_blocks_per_cta;
   const int kb1 = kb0 + k_blocks_per_cta < k_blocks_total ? kb0 + k_blocks_per_cta : k_blocks_total;
-  const bool do_sum = nb == 0;
+  // Column sums: the n_blocks CTAs that share an A tile each sum a contiguous 1/n_blocks of their k range (all of them
+  // add into colsum), so the extra MMAs are spread evenly instead of doubling up on the nb == 0 CTAs.
+  const int klen = kb1 - kb0;
+  const int sum0 = colsum ? kb0 + (int)((long long)klen * nb / n_blocks) : kb1;
+  const int sum1 = colsum ? kb0 + (int)((long long)klen * (nb + 1) / n_blocks) : kb1;
+  const bool do_sum = sum1 > sum0;
 
   for (int i = threadIdx.x; i < 8192 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + Cfg::kOnesOff)[i] = 0x3f803f80u;
   fence_proxy_async();
@@ -160,25 +191,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, true, true);
-      constexpr uint32_t idesc1 = umma_idesc_bf16(128, 16, true, true);
-      const uint32_t sones = smem_u32(smem + Cfg::kOnesOff);
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {  // 16 tokens per step = two 8-row atoms = 2 KB
-          const uint64_t da = umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024);
-          umma_bf16(tmem, da, umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024), idesc, (kb > kb0) | (ks > 0));
-          if (do_sum)
-            umma_bf16(tmem + Cfg::kOnesCol, da, umma_desc_mn_sw128(sones, 8192, 1024), idesc1, (kb > kb0) | (ks > 0));
-        }
-        umma_commit(&empty[s]);
-        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
-      }
+      tn_issue<BN, false>(smem, full, empty, tmem, kb0, sum0, kb0, sum0, s, ph);
+      tn_issue<BN, true>(smem, full, empty, tmem, sum0, sum1, kb0, sum0, s, ph);
+      tn_issue<BN, false>(smem, full, empty, tmem, sum1, kb1, kb0, sum0, s, ph);
       umma_commit(acc_full);
     }
   } else {
@@ -222,7 +239,7 @@ static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int
   if ((st = make_tmap_2d(&tmA, A, (uint64_t)Kd, (uint64_t)M, 64))) return st;
   if ((st = make_tmap_2d(&tmB, Bm, (uint64_t)Kd, (uint64_t)N, 64))) return st;
   cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s);
-  cudaMemsetAsync(colsum, 0, sizeof(float) * M, s);
+  if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * M, s);
   const int tiles = (M / 128) * (N / BN);
   const int kblocks = (int)(Kd / 64);
   int splits = 148 / tiles;  // one wave: tiles * splits <= 148 SMs (a 149th CTA would double the time)
@@ -235,12 +252,190 @@ static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int
   return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2, see ffn_tc.cu): a cluster of two CTAs accumulates one 256 x 256 tile of C over its
+// token range; each CTA stages 128 of A's columns and 128 of B's columns per 64-token k block (32 KB instead of the
+// 48 KB of the single-CTA 128 x 256 tile, and half of B comes out of the peer's shared memory).
+// ---------------------------------------------------------------------------
+struct GemmTnPairCfg {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = 64 * 128 * 2;         // [64 k][128 m] of this CTA
+  static constexpr int kBBytes = 64 * 128 * 2;         // [64 k][128 n] of this CTA
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kOnesOff = kStages * kStage;
+  static constexpr int kBarOff = kOnesOff + 8192;
+  static constexpr int kSmem = kBarOff + 256 + 1024;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kOnesCol = 256;
+};
+
+template <bool SUM>
+HW_DEV void tn_pair_issue(unsigned char* smem, uint64_t* full, uint64_t* empty, uint32_t tmem, int kb, int kend,
+                          int main_first, int sum_first, int& s, uint32_t& ph) {
+  using Cfg = GemmTnPairCfg;
+  constexpr uint32_t idesc = umma_idesc_bf16(256, 256, true, true);
+  constexpr uint32_t idesc1 = umma_idesc_bf16(256, 16, true, true);
+  const uint32_t sones = smem_u32(smem + Cfg::kOnesOff);
+  for (; kb < kend; ++kb) {
+    mbar_wait_cluster(&full[s], ph);
+    tc_fence_after();
+    const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t da = umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024);
+      umma_bf16_pair(tmem, da, umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024), idesc, (kb > main_first) | (ks > 0));
+      if (SUM)
+        umma_bf16_pair(tmem + Cfg::kOnesCol, da, umma_desc_mn_sw128(sones, 8192, 1024), idesc1, (kb > sum_first) | (ks > 0));
+    }
+    umma_commit_pair(&empty[s]);
+    if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+  }
+}
+
+__global__ void __launch_bounds__(192, 1) gemm_tc_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 float* __restrict__ C, float* __restrict__ colsum, int M,
+                                                                 int N, int k_blocks_total, int k_blocks_per_cta,
+                                                                 bool perm64) {
+  using Cfg = GemmTnPairCfg;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* acc_full = empty + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_blocks = N / 256;
+  const int tile = blockIdx.x >> 1;
+  const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
+  const int kb0 = blockIdx.y * k_blocks_per_cta;
+  const int kb1 = kb0 + k_blocks_per_cta < k_blocks_total ? kb0 + k_blocks_per_cta : k_blocks_total;
+  const int klen = kb1 - kb0;   // column sums: see gemm_tc_tn_kernel
+  const int sum0 = colsum ? kb0 + (int)((long long)klen * nb / n_blocks) : kb1;
+  const int sum1 = colsum ? kb0 + (int)((long long)klen * (nb + 1) / n_blocks) : kb1;
+  const bool do_sum = sum1 > sum0;
+
+  for (int i = threadIdx.x; i < 8192 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + Cfg::kOnesOff)[i] = 0x3f803f80u;
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int acol = (2 * mb + (int)rank) * 128, bcol = nb * 256 + (int)rank * 128;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait_cluster(&empty[s], ph ^ 1);
+        unsigned char* st = smem + s * Cfg::kStage;
+        const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
+        if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::kStage);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_load_2d_pair(st + j * 8192, &tmA, lead_full, acol + j * 64, kb * 64);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_load_2d_pair(st + Cfg::kABytes + j * 8192, &tmB, lead_full, bcol + j * 64, kb * 64);
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      tn_pair_issue<false>(smem, full, empty, tmem, kb0, sum0, kb0, sum0, s, ph);
+      tn_pair_issue<true>(smem, full, empty, tmem, sum0, sum1, kb0, sum0, s, ph);
+      tn_pair_issue<false>(smem, full, empty, tmem, sum1, kb1, kb0, sum0, s, ph);
+      umma_commit_pair(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int arow = (2 * mb + (int)rank) * 128 + q * 32 + lane;
+    if (arow < M) {   // warp-uniform: M % 128 == 0
+      const int row = perm64 ? perm64_inv(arow) : arow;
+      float* crow = C + (size_t)row * N + (size_t)nb * 256;
+#pragma unroll 1
+      for (int c = 0; c < 256; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(crow + c + i, __uint_as_float(r[i]));
+      }
+      if (do_sum) {
+        uint32_t r[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + Cfg::kOnesCol, r);
+        tmem_ld_wait();
+        atomicAdd(colsum + row, __uint_as_float(r[0]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem, Cfg::kTmemCols);
+}
+
+static int launch_tn_pair(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd,
+                          cudaStream_t s, bool perm64) {
+  using Cfg = GemmTnPairCfg;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_tc_tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    attr_done = true;
+  }
+  CUtensorMap tmA, tmB;
+  int st;
+  if ((st = make_tmap_2d(&tmA, A, (uint64_t)Kd, (uint64_t)M, 64))) return st;
+  if ((st = make_tmap_2d(&tmB, Bm, (uint64_t)Kd, (uint64_t)N, 64))) return st;
+  cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s);
+  if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * M, s);
+  const int tiles = ((M + 255) / 256) * (N / 256);
+  const int kblocks = (int)(Kd / 64);
+  int splits = 74 / tiles;  // one wave of CTA pairs
+  if (splits < 1) splits = 1;
+  if (splits > kblocks) splits = kblocks;
+  const int per = (kblocks + splits - 1) / splits;
+  splits = (kblocks + per - 1) / per;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(2 * tiles, splits);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg::kSmem;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_tn_pair_kernel, tmA, tmB, C, colsum, M, N, kblocks, per, perm64);
+  count_launch();
+  return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
+}
+
 // C[M,N] = A[Kd,M]^T . B[Kd,N] (fp32 out), colsum[M] = column sums of A; M % 128 == 0, N % 128 == 0, Kd % 64 == 0
 // perm64: rows of C / entries of colsum are written through the inverse of K3's dQKV column permutation
 int gemm_tc_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd, cudaStream_t s,
                bool perm64) {
   if (M % 128 || N % 128 || Kd % 64) return HWGAT_ERR_UNSUPPORTED;
-  if (N % 256 == 0) return launch_tn<256>(A, Bm, C, colsum, M, N, Kd, s, perm64);
+  if (N % 256 == 0) {
+    // CTA pairs (256 x 256 tiles): +10-15 % once there are enough tiles to split the token range over 74 pairs evenly
+    // (measured at M x N = 1536 x 512, 1024 x 512, 512 x 1024, 768 x 256; slower at two tiles)
+    if (gemm_pair_enabled() && M >= 256 && ((M + 255) / 256) * (N / 256) >= 3)
+      return launch_tn_pair(A, Bm, C, colsum, M, N, Kd, s, perm64);
+    return launch_tn<256>(A, Bm, C, colsum, M, N, Kd, s, perm64);
+  }
   return launch_tn<128>(A, Bm, C, colsum, M, N, Kd, s, perm64);
 }
 

@@ -266,44 +266,66 @@ def test_empty_batch_and_errors():
         ops.window_graph_attention(torch.zeros(1, 4, 48, 128, device="cuda"), w, b, bits, 2)
 
 
-# ------------------------------------------------------------------ tcgen05 GEMM used by K3
+# ------------------------------------------------------------------ tcgen05 GEMMs used by K3 and K10
+@pytest.fixture(params=[1, 0], ids=["pair", "single"])
+def gemm_pair(request):
+    """Both forms of the wide GEMMs: CTA pairs (cta_group::2, 256 x 256 tiles; the default where the shape rules of
+    ffn_tc.cu / gemm_tc.cu select it) and the single-CTA 128 x 256 kernels."""
+    from sl_hwgat_b200 import _lib
+    lib = _lib.load()
+    prev = lib.hwgat_debug_set_gemm_pair(request.param)
+    yield request.param
+    lib.hwgat_debug_set_gemm_pair(prev)
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (256, 128, 384), (1024, 256, 768),
-                                   (4096, 512, 1536), (148 * 128 * 3, 128, 384)])
-def test_tcgen05_gemm_nt(M, N, K):
-    """C = A . Bt^T (TMA + tcgen05.mma + TMEM epilogue) against an fp32 matmul of the same bf16 inputs."""
+                                   (4096, 512, 1536), (148 * 128 * 3, 128, 384),
+                                   (256, 256, 768), (384, 256, 832), (128 * 301, 512, 1024)])
+def test_tcgen05_gemm_nt(M, N, K, gemm_pair):
+    """C = A . Bt^T (TMA + tcgen05.mma + TMEM epilogue) against an fp32 matmul of the same bf16 inputs.  K >= 768
+    with N % 256 == 0 runs on CTA pairs; M = 384 and 128 * 301 leave the second CTA of the last pair without rows."""
     from sl_hwgat_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
     Bt = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
-    C = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    C = torch.full((M + 128, N), float("nan"), dtype=torch.bfloat16, device="cuda")   # guard rows after the output
     _lib.check(lib.hwgat_debug_gemm_nt(A.data_ptr(), Bt.data_ptr(), C.data_ptr(), M, N, K,
                                        torch.cuda.current_stream().cuda_stream), "hwgat_debug_gemm_nt")
     torch.cuda.synchronize()
+    assert torch.isnan(C[M:]).all()      # nothing written past row M
     ref = A.float() @ Bt.float().t()
-    err = (C.float() - ref).abs().max().item() / ref.abs().max().item()
+    err = (C[:M].float() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-2, err          # bf16 output rounding only
-    assert rel_l2(C.float(), ref) < 3e-3
+    assert rel_l2(C[:M].float(), ref) < 3e-3
 
 
+@pytest.mark.parametrize("with_colsum", [True, False])
 @pytest.mark.parametrize("M,N,Kd", [(128, 128, 64), (384, 128, 256), (768, 256, 4096), (1536, 512, 8192),
-                                    (384, 128, 64 * 1001)])
-def test_tcgen05_gemm_tn(M, N, Kd):
+                                    (384, 128, 64 * 1001), (256, 256, 64), (384, 512, 64 * 77), (512, 1024, 64 * 333),
+                                    (1024, 512, 64 * 3)])
+def test_tcgen05_gemm_tn(M, N, Kd, with_colsum, gemm_pair):
     """C = A^T . B (both MN-major UMMA operands, split over the contraction, fp32 red.add) and the
-    column sums of A from the ones-tile MMA."""
+    column sums of A from the ones-tile MMA (spread over the CTAs that share an A tile; skipped for a NULL colsum).
+    Three or more 256 x 256 tiles run on CTA pairs; M = 384 leaves half of the last pair empty; Kd = 64 * 3 gives
+    fewer k blocks than tile columns (some CTAs sum nothing)."""
     from sl_hwgat_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(M + N + Kd)
     A = torch.randn(Kd, M, generator=g).to(torch.bfloat16).cuda()
     B = torch.randn(Kd, N, generator=g).to(torch.bfloat16).cuda()
-    C = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
-    cs = torch.full((M,), float("nan"), dtype=torch.float32, device="cuda")
-    _lib.check(lib.hwgat_debug_gemm_tn(A.data_ptr(), B.data_ptr(), C.data_ptr(), cs.data_ptr(), M, N, Kd,
-                                       torch.cuda.current_stream().cuda_stream), "hwgat_debug_gemm_tn")
+    C = torch.full((M + 1, N), float("nan"), dtype=torch.float32, device="cuda")
+    cs = torch.full((M + 1,), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(lib.hwgat_debug_gemm_tn(A.data_ptr(), B.data_ptr(), C.data_ptr(), cs.data_ptr() if with_colsum else None,
+                                       M, N, Kd, torch.cuda.current_stream().cuda_stream), "hwgat_debug_gemm_tn")
     torch.cuda.synchronize()
+    assert torch.isnan(C[M:]).all() and torch.isnan(cs[M:]).all()
     ref = A.double().t() @ B.double()
-    assert rel_l2(C, ref) < 1e-5
-    assert rel_inf(cs, A.double().sum(0)) < 1e-4
+    assert rel_l2(C[:M], ref) < 1e-5
+    if with_colsum:
+        assert rel_inf(cs[:M], A.double().sum(0)) < 1e-4
+    else:
+        assert torch.isnan(cs).all()     # untouched
 
 
 # ------------------------------------------------------------------ K5-K7: fused block elementwise kernels
