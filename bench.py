@@ -108,7 +108,8 @@ class KernelTimer:
         self.orig = {}
         for name in ("hwgat_attn_fwd", "hwgat_attn_bwd", "hwgat_merge_fwd", "hwgat_merge_bwd", "hwgat_ln_fwd",
                      "hwgat_ln_bwd", "hwgat_bda_ln_fwd", "hwgat_bda_ln_bwd", "hwgat_bias_gelu_dropout_fwd",
-                     "hwgat_bias_gelu_dropout_bwd", "hwgat_ffn_fwd", "hwgat_ffn_bwd"):
+                     "hwgat_bias_gelu_dropout_bwd", "hwgat_ffn_fwd", "hwgat_ffn_bwd", "hwgat_proj_fwd",
+                     "hwgat_proj_bwd"):
             fn = getattr(lib, name)
             self.orig[name] = fn
             setattr(lib, name, self._wrap(name, fn))
@@ -124,6 +125,8 @@ class KernelTimer:
         "hwgat_bias_gelu_dropout_bwd": lambda a: (int(a[6]), int(a[5])),
         "hwgat_ffn_fwd": lambda a: (int(a[8]), int(a[7]), int(a[9])),
         "hwgat_ffn_bwd": lambda a: (int(a[13]), int(a[12]), int(a[14])),
+        "hwgat_proj_fwd": lambda a: (int(a[4]), int(a[3]), int(a[5])),
+        "hwgat_proj_bwd": lambda a: (int(a[8]), int(a[7]), int(a[9])),
     }
     # algorithmic HBM bytes per element of the bandwidth-bound kernels
     BYTES_PER_ELEM = {"hwgat_ln_fwd": 6, "hwgat_ln_bwd": 14, "hwgat_bias_gelu_dropout_fwd": 4,
@@ -170,6 +173,14 @@ class KernelTimer:
                 n_rows, hidden = key[1], key[2]
                 fl = 4.0 * n_rows * d * hidden * (2 if name.endswith("bwd") else 1)
                 out.append({"kernel": f"K10 {name} d={d}", "bound": "tensor", "calls_per_step": cnt / steps,
+                            "avg_ms": avg, "alg_flops": fl, "achieved": fl / (avg * 1e-3) / 1e12, "unit": "TFLOP/s",
+                            "total_ms": ms, "attention": False})
+                continue
+            if "proj" in name:
+                # output projection: 2 n d_in d_out FLOP forward, twice that backward
+                n_rows, d_out = key[1], key[2]
+                fl = 2.0 * n_rows * d * d_out * (2 if name.endswith("bwd") else 1)
+                out.append({"kernel": f"K12 {name} d={d}", "bound": "tensor", "calls_per_step": cnt / steps,
                             "avg_ms": avg, "alg_flops": fl, "achieved": fl / (avg * 1e-3) / 1e12, "unit": "TFLOP/s",
                             "total_ms": ms, "attention": False})
                 continue

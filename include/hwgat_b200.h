@@ -193,6 +193,17 @@ int hwgat_ln_pool_bwd(const float* g, const float* x, const float* mean, const f
 
 /* ---- training loop ------------------------------------------------------ */
 
+/* K12: the output projection of MSA without its bias (the bias, proj_drop and the shortcut add belong to K6):
+ *   y (bf16, (n, d_out)) = ctx (bf16, (n, d_in)) . W^T,   W: (d_out, d_in) bf16
+ * Replaces self.proj's matmul (HWGATE.py:115) with the library's own TMA + tcgen05 GEMM, so the whole of MSA.forward
+ * runs on this library.  n % 128 == 0, d_out % 128 == 0, d_in % 64 == 0.                                          */
+int hwgat_proj_fwd(const void* ctx, const void* w, void* y, long long n, int d_in, int d_out, hwgat_stream_t stream);
+/* K12': d_ctx (bf16, (n, d_in)) = dy . W,  dw (fp32, (d_out, d_in)) = dy^T . ctx, both overwritten (the bias gradient
+ * is K6's).  Needs d_in % 128 == 0 as well.  workspace: hwgat_proj_bwd_workspace_bytes(d_in, d_out) bytes (W^T).  */
+size_t hwgat_proj_bwd_workspace_bytes(int d_in, int d_out);
+int hwgat_proj_bwd(const void* dy, const void* ctx, const void* w, void* d_ctx, float* dw, void* workspace,
+                   size_t workspace_bytes, long long n, int d_in, int d_out, hwgat_stream_t stream);
+
 /* K11: one AdamW step over n_tensors fp32 parameter tensors in ONE launch per 160 tensors (multi-tensor apply).
  * Replaces optimizer.step() of torch.optim.AdamW(model.parameters(), lr) (utils.py:73-75, stepped at utils.py:107):
  *   p *= 1 - lr*weight_decay;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("HWGAT_B200_LIB") or os.path.join(HERE, "lib", "libhwg
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # name -> (restype, argtypes); must list every symbol of include/hwgat_b200.h
 SIGNATURES = {
@@ -46,6 +46,9 @@ SIGNATURES = {
                                c_void_p]),
     "hwgat_ffn_bwd_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int]),
     "hwgat_ffn_bwd": (c_int, [c_void_p] * 11 + [c_size_t, c_longlong, c_int, c_int, c_void_p]),
+    "hwgat_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
+    "hwgat_proj_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "hwgat_proj_bwd": (c_int, [c_void_p] * 6 + [c_size_t, c_longlong, c_int, c_int, c_void_p]),
     "hwgat_adamw_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double,
                                   c_double, c_double, c_longlong, c_float, c_void_p]),
     "hwgat_debug_gemm_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),

@@ -27,7 +27,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 9; }
+int hwgat_version(void) { return 10; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -301,6 +301,47 @@ int hwgat_adamw_step(int n_tensors, float* const* params, const float* const* gr
   }
   return adamw_step(n_tensors, params, grads, exp_avg, exp_avg_sq, sizes, lr, beta1, beta2, eps, weight_decay, step,
                     grad_scale, (cudaStream_t)stream);
+}
+
+static int check_proj(long long n, int d_in, int d_out, bool backward) {
+  if (n < 0 || d_in <= 0 || d_out <= 0) return HWGAT_ERR_SHAPE;
+  if (n % 128 || d_out % 128 || d_in % 64 || (backward && d_in % 128)) return HWGAT_ERR_UNSUPPORTED;
+  return HWGAT_OK;
+}
+
+int hwgat_proj_fwd(const void* ctx, const void* w, void* y, long long n, int d_in, int d_out, hwgat_stream_t stream) {
+  int st = check_proj(n, d_in, d_out, false);
+  if (st) return st;
+  if (n == 0) return HWGAT_OK;
+  if (!ctx || !w || !y) return HWGAT_ERR_NULL;
+  if (misaligned(ctx) || misaligned(w) || misaligned(y)) return HWGAT_ERR_ALIGN;
+  return gemm_tc_nt_epi_none((const __nv_bfloat16*)ctx, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, n, d_out, d_in,
+                             (cudaStream_t)stream);
+}
+
+size_t hwgat_proj_bwd_workspace_bytes(int d_in, int d_out) {
+  if (d_in <= 0 || d_out <= 0) return 0;
+  return (size_t)d_in * d_out * sizeof(__nv_bfloat16);
+}
+
+int hwgat_proj_bwd(const void* dy, const void* ctx, const void* w, void* d_ctx, float* dw, void* workspace,
+                   size_t workspace_bytes, long long n, int d_in, int d_out, hwgat_stream_t stream) {
+  int st = check_proj(n, d_in, d_out, true);
+  if (st) return st;
+  if (!dw) return HWGAT_ERR_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) {
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d_in * d_out, s);
+    return (int)cudaGetLastError();
+  }
+  if (!dy || !ctx || !w || !d_ctx) return HWGAT_ERR_NULL;
+  if (misaligned(dy) || misaligned(ctx) || misaligned(w) || misaligned(d_ctx) || misaligned(dw) || misaligned(workspace))
+    return HWGAT_ERR_ALIGN;
+  if (!workspace || workspace_bytes < hwgat_proj_bwd_workspace_bytes(d_in, d_out)) return HWGAT_ERR_WORKSPACE;
+  __nv_bfloat16* wt = (__nv_bfloat16*)workspace;   // W^T [d_in, d_out]: both operands of d_ctx = dy . W K-major
+  if ((st = transpose_bf16((const __nv_bfloat16*)w, wt, d_out, d_in, s))) return st;
+  if ((st = gemm_tc_nt_epi_none((const __nv_bfloat16*)dy, wt, (__nv_bfloat16*)d_ctx, n, d_in, d_out, s))) return st;
+  return gemm_tc_tn((const __nv_bfloat16*)dy, (const __nv_bfloat16*)ctx, dw, nullptr, d_out, d_in, n, s);
 }
 
 int hwgat_debug_gemm_nt(const void* A, const void* Bt, void* C, long long M, int N, int K, hwgat_stream_t stream) {

@@ -243,7 +243,10 @@ class PartAttentionBlock(nn.Module):
         ctx = ops.window_graph_attention(xn, attn.qkv.weight, attn.qkv.bias, self._block_bits(x.device),
                                          attn.num_heads, shift=self.shift_size, threshold=attn._draw_threshold(),
                                          layout=LAYOUT_BFKD)
-        a0 = nn.functional.linear(ctx, attn.proj.weight)           # bias, dropout, shortcut and norm2: K6
+        if ops.proj_supported(ctx.numel() // self.dim, self.dim, self.dim):
+            a0 = ops.output_projection(ctx, attn.proj.weight)      # K12; bias, dropout, shortcut and norm2: K6
+        else:
+            a0 = nn.functional.linear(ctx, attn.proj.weight)
         x, h = ops.bias_dropout_add_ln(x, a0, attn.proj.bias, self.norm2, attn.proj_drop.p, self.training)
         hidden = ff.fc1.weight.shape[0]
         if ops.ffn_supported(h.numel() // self.dim, self.dim, hidden):

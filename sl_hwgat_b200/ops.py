@@ -440,6 +440,55 @@ def ffn_supported(n_tokens: int, d: int, hidden: int) -> bool:
     return n_tokens % 128 == 0 and d % 128 == 0 and hidden % 128 == 0 and hidden <= 2048
 
 
+class _OutputProjection(torch.autograd.Function):
+    """y = ctx W^T (bf16) on the library's tcgen05 GEMMs (K12): self.proj's matmul, HWGATE.py:115."""
+
+    @staticmethod
+    def forward(ctx_, x, w):
+        lib = _lib.load()
+        _need_cuda(x, w)
+        x_c = x.to(torch.bfloat16).contiguous()
+        d_in = x_c.shape[-1]
+        n = x_c.numel() // d_in
+        d_out = w.shape[0]
+        if tuple(w.shape) != (d_out, d_in):
+            raise ValueError(f"proj weight {tuple(w.shape)} does not match (n, {d_in}) input")
+        w_c = w.detach().to(torch.bfloat16).contiguous()
+        y = torch.empty(x_c.shape[:-1] + (d_out,), dtype=torch.bfloat16, device=x_c.device)
+        with torch.cuda.device(x_c.device):
+            check(lib.hwgat_proj_fwd(x_c.data_ptr(), w_c.data_ptr(), y.data_ptr(), n, d_in, d_out, _stream()),
+                  "hwgat_proj_fwd")
+        if any(ctx_.needs_input_grad[:2]):
+            ctx_.save_for_backward(x_c, w_c)
+        ctx_.meta = (n, d_in, d_out, x.dtype, w.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx_, dy):
+        lib = _lib.load()
+        x_c, w_c = ctx_.saved_tensors
+        n, d_in, d_out, xdt, wdt = ctx_.meta
+        dy_c = dy.to(torch.bfloat16).contiguous()
+        dev = x_c.device
+        dx = torch.empty_like(x_c)
+        dw = torch.empty((d_out, d_in), dtype=torch.float32, device=dev)
+        ws = torch.empty(max(lib.hwgat_proj_bwd_workspace_bytes(d_in, d_out), 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.hwgat_proj_bwd(dy_c.data_ptr(), x_c.data_ptr(), w_c.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), n, d_in, d_out, _stream()), "hwgat_proj_bwd")
+        return dx.to(xdt), dw.to(wdt)
+
+
+def output_projection(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """x @ w.T as bf16 (no bias: the bias, proj_drop and the shortcut add are K6's): MSA's self.proj matmul
+    (HWGATE.py:115).  x: (..., d_in) with prod(...) % 128 == 0, d_in % 128 == 0, d_out % 128 == 0."""
+    return _OutputProjection.apply(x, w)
+
+
+def proj_supported(n_tokens: int, d_in: int, d_out: int) -> bool:
+    return n_tokens % 128 == 0 and d_in % 128 == 0 and d_out % 128 == 0
+
+
 # --------------------------------------------------------------------------
 # K8 / K9: model head and tail
 # --------------------------------------------------------------------------

@@ -328,6 +328,36 @@ def test_tcgen05_gemm_tn(M, N, Kd, with_colsum, gemm_pair):
         assert torch.isnan(cs).all()     # untouched
 
 
+# ------------------------------------------------------------------ K12: MSA output projection (self.proj matmul)
+@pytest.mark.parametrize("n,d", [(128, 128), (384, 256), (1024, 512), (128 * 37, 512)])
+def test_output_projection(n, d, gemm_pair):
+    """ctx @ W^T on the library's GEMMs (HWGATE.py:115, bias belongs to K6) and its autograd against fp64 matmuls of
+    the same bf16 operands; 2e-2 is north_star's bf16 tolerance, the observed error is bf16 output rounding."""
+    from sl_hwgat_b200 import ops
+    g = torch.Generator().manual_seed(n + d)
+    x = torch.randn(n, d, generator=g).to(torch.bfloat16).cuda().requires_grad_(True)
+    w = (torch.randn(d, d, generator=g) / d ** 0.5).cuda().requires_grad_(True)
+    gy = torch.randn(n, d, generator=g).to(torch.bfloat16).cuda()
+    assert ops.proj_supported(n, d, d)
+    y = ops.output_projection(x, w)
+    assert y.dtype == torch.bfloat16 and y.shape == (n, d)
+    y.backward(gy)
+    xb, wb = x.detach().double(), w.detach().to(torch.bfloat16).double()
+    assert rel_l2(y.float(), xb @ wb.t()) < 3e-3
+    assert rel_l2(x.grad.float(), gy.double() @ wb) < 3e-3
+    assert w.grad.dtype == torch.float32
+    assert rel_l2(w.grad, gy.double().t() @ xb) < 1e-5
+
+
+def test_output_projection_rejects_ragged():
+    from sl_hwgat_b200 import _lib, ops
+    assert not ops.proj_supported(100, 128, 128) and not ops.proj_supported(128, 96, 128)
+    x = torch.randn(100, 128, device="cuda").to(torch.bfloat16)
+    w = torch.randn(128, 128, device="cuda")
+    with pytest.raises(_lib.HwgatError):
+        ops.output_projection(x, w)
+
+
 # ------------------------------------------------------------------ K5-K7: fused block elementwise kernels
 @pytest.mark.parametrize("d", [128, 256, 512])
 @pytest.mark.parametrize("n", [1, 37, 4096])
