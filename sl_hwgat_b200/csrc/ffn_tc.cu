@@ -55,6 +55,14 @@ struct FfnCfg {
   static constexpr int kTmemCols = 2 * BN;
 };
 
+// explicit ld.shared: the 1024-byte-aligned smem pointer is built with integer arithmetic, so the compiler no longer
+// knows its address space and would emit generic LD.E loads
+HW_DEV float4 lds_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
 template <int EPI>
 HW_DEV void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& e, size_t elem, int col, const float* sbias) {
   // r: 32 consecutive columns of one row (fp32 accumulator); elem = row * N + col.  Every store is 32 bytes
@@ -88,8 +96,8 @@ HW_DEV void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& e, size_t ele
         const int c8 = 16 * g + 8 * hh;
         // bias from shared memory (broadcast reads): read from global here, the loads sat on the long scoreboard
         // in front of every chunk (30 % of the kernel's stall samples)
-        const float4 b0 = *reinterpret_cast<const float4*>(sbias + col + c8);
-        const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + c8 + 4);
+        const float4 b0 = lds_f4(sbias + col + c8);
+        const float4 b1 = lds_f4(sbias + col + c8 + 4);
         const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         // same stream and granule index as K7 (bias_gelu_dropout): vector (row * N + col) / 8 of the flattened
         // tensor, element 2j <- low half of word j, element 2j+1 <- high half (keep8).  The 16-bit compares are
