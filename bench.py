@@ -290,8 +290,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"       # the version banner goes to stdout and would precede the JSON line
+    # stdout carries exactly one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG >= VERSION, so a
+    # bare VERSION setting is dropped and anything NCCL does log goes to stderr
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        del os.environ["NCCL_DEBUG"]
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from sl_hwgat_b200 import _lib, parallel
