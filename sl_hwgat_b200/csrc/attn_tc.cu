@@ -180,11 +180,12 @@ HW_DEV void masked_softmax_tc(float (&s)[4][4], const float (&mk)[2][8], float t
 }
 
 // ---------------------------------------------------------------------------
-// warp 0 (one lane): TMA producer shared by K2 and K3
+// warp 0: TMA producer shared by K2 and K3
 // ---------------------------------------------------------------------------
 HW_DEV void tc_producer(const TileGeom& geo, int heads, int tiles, int S, TcBars* bars, unsigned char* sX,
                         unsigned char* sW, unsigned char* sBias, const bf16* __restrict__ bias_tiles,
                         const CUtensorMap* tmX, const CUtensorMap* tmW) {
+  // whole warp: the loops and waits are warp-uniform, the copies are issued by one elected lane
   const int d = geo.d, nk = d / 64;
   int s = 0, it = 0;
   uint32_t wph = 0;
@@ -196,32 +197,41 @@ HW_DEV void tc_producer(const TileGeom& geo, int heads, int tiles, int S, TcBars
       {  // bias tile of this head into slot it & 1
         const int slot = it & 1;
         mbar_wait(&bars->bias_empty[slot], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&bars->bias_full[slot], kBiasTile);
-        bulk_load_1d(sBias + slot * kBiasTile, bias_tiles + (size_t)h * kBiasElems, kBiasTile, &bars->bias_full[slot]);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&bars->bias_full[slot], kBiasTile);
+          bulk_load_1d(sBias + slot * kBiasTile, bias_tiles + (size_t)h * kBiasElems, kBiasTile, &bars->bias_full[slot]);
+        }
+        __syncwarp();
       }
       for (int c = 0; c < nk; ++c) {
         if (h == 0) {
           mbar_wait(&bars->x_empty[c], (tcount & 1) ^ 1);
-          mbar_expect_tx(&bars->x_full[c], kXChunk);
-          unsigned char* dst = sX + c * kXChunk;
-          if (geo.layout == HWGAT_LAYOUT_WINDOWS) {
-            tma_load_2d(dst, tmX, &bars->x_full[c], c * 64, tile * kTileTok);
-          } else {
+          if (elect_one_sync()) {
+            mbar_expect_tx(&bars->x_full[c], kXChunk);
+            unsigned char* dst = sX + c * kXChunk;
+            if (geo.layout == HWGAT_LAYOUT_WINDOWS) {
+              tma_load_2d(dst, tmX, &bars->x_full[c], c * 64, tile * kTileTok);
+            } else {
 #pragma unroll
-            for (int w = 0; w < 4; ++w)
+              for (int w = 0; w < 4; ++w)
 #pragma unroll
-              for (int tp = 0; tp < 2; ++tp) {
-                int fr = 2 * fi + tp + geo.shift;
-                fr = fr >= geo.F ? fr - geo.F : fr;
-                tma_load_4d(dst + (w * 32 + tp * 16) * 128, tmX, &bars->x_full[c], c * 64, kg * 64 + w * 16, fr, b);
-              }
+                for (int tp = 0; tp < 2; ++tp) {
+                  int fr = 2 * fi + tp + geo.shift;
+                  fr = fr >= geo.F ? fr - geo.F : fr;
+                  tma_load_4d(dst + (w * 32 + tp * 16) * 128, tmX, &bars->x_full[c], c * 64, kg * 64 + w * 16, fr, b);
+                }
+            }
           }
+          __syncwarp();
         }
         mbar_wait(&bars->w_empty[s], wph ^ 1);
-        mbar_expect_tx(&bars->w_full[s], kWStage);
-        unsigned char* dw = sW + s * kWStage;
+        if (elect_one_sync()) {
+          mbar_expect_tx(&bars->w_full[s], kWStage);
+          unsigned char* dw = sW + s * kWStage;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) tma_load_2d(dw + q * 8192, tmW, &bars->w_full[s], c * 64, q * d + h * kHd);
+          for (int q = 0; q < 3; ++q) tma_load_2d(dw + q * 8192, tmW, &bars->w_full[s], c * 64, q * d + h * kHd);
+        }
+        __syncwarp();
         if (++s == S) { s = 0; wph ^= 1; }
       }
     }
@@ -229,10 +239,11 @@ HW_DEV void tc_producer(const TileGeom& geo, int heads, int tiles, int S, TcBars
 }
 
 // ---------------------------------------------------------------------------
-// warp 1 (one lane): tcgen05.mma issuer shared by K2 and K3
+// warp 1: tcgen05.mma issuer shared by K2 and K3
 // ---------------------------------------------------------------------------
 HW_DEV void tc_issuer(const TileGeom& geo, int heads, int tiles, int S, TcBars* bars, unsigned char* sX,
                       unsigned char* sW, unsigned char* sOnes, unsigned char* sBias, uint32_t tmem) {
+  // whole warp (see elect_one_sync): waits are warp-uniform, MMAs and commits come from the elected lane
   constexpr uint32_t idesc = umma_idesc_bf16(128, 192);
   const int nk = geo.d / 64;
   int s = 0, it = 0, tcount = 0;
@@ -244,22 +255,28 @@ HW_DEV void tc_issuer(const TileGeom& geo, int heads, int tiles, int S, TcBars* 
       mbar_wait(&bars->bias_full[buf], (it >> 1) & 1);
       tc_fence_after();
       // accumulator = 1 . bias^T  (K = 16 step against the ones tile), then += X . Wh^T
-      umma_bf16(tmem + buf * kAccStride, umma_desc_k_none(smem_u32(sOnes), kTileTok * 16, 128),
-                umma_desc_k_none(smem_u32(sBias + buf * kBiasTile), 192 * 16, 128), idesc, 0);
-      umma_commit(&bars->bias_empty[buf]);
+      if (elect_one_sync()) {
+        umma_bf16(tmem + buf * kAccStride, umma_desc_k_none(smem_u32(sOnes), kTileTok * 16, 128),
+                  umma_desc_k_none(smem_u32(sBias + buf * kBiasTile), 192 * 16, 128), idesc, 0);
+        umma_commit(&bars->bias_empty[buf]);
+      }
+      __syncwarp();
       for (int c = 0; c < nk; ++c) {
         mbar_wait(&bars->w_full[s], wph);
         if (h == 0) mbar_wait(&bars->x_full[c], tcount & 1);
         tc_fence_after();
-        const uint32_t sa = smem_u32(sX + c * kXChunk), sb = smem_u32(sW + s * kWStage);
+        if (elect_one_sync()) {
+          const uint32_t sa = smem_u32(sX + c * kXChunk), sb = smem_u32(sW + s * kWStage);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tmem + buf * kAccStride, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc, 1);
-        umma_commit(&bars->w_empty[s]);
-        if (h == heads - 1) umma_commit(&bars->x_empty[c]);
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem + buf * kAccStride, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc, 1);
+          umma_commit(&bars->w_empty[s]);
+          if (h == heads - 1) umma_commit(&bars->x_empty[c]);
+          if (c == nk - 1) umma_commit(&bars->acc_full[buf]);
+        }
+        __syncwarp();
         if (++s == S) { s = 0; wph ^= 1; }
       }
-      umma_commit(&bars->acc_full[buf]);
     }
   }
 }
@@ -519,8 +536,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
 
   if (warp < kFirstEpiWarp) {
     reg_dealloc_donor();
-    if (warp == 0 && lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, sBias, p.bias_tiles, &tmX, &tmW);
-    if (warp == 1 && lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, sOnes, sBias, tmem);
+    if (warp == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, sBias, p.bias_tiles, &tmX, &tmW);
+    if (warp == 1) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, sOnes, sBias, tmem);
   } else {
     reg_alloc_epi();
     const int win = warp & 3;                      // TMEM lane quarter == window of the tile
@@ -694,8 +711,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
 
   if (warp < kFirstEpiWarp) {
     reg_dealloc_donor();
-    if (warp == 0 && lane == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, sBias, p.bias_tiles, &tmX, &tmW);
-    if (warp == 1 && lane == 0) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, sOnes, sBias, tmem);
+    if (warp == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, sBias, p.bias_tiles, &tmX, &tmW);
+    if (warp == 1) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, sOnes, sBias, tmem);
   } else {
     reg_alloc_epi();
     const int win = warp & 3;

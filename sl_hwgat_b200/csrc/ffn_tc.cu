@@ -203,43 +203,48 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_kernel
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // Producer and issuer run their loops with the whole warp and issue under elect_one_sync (tc.cuh): inside
+  // `if (lane == 0)` every UTMALDG / UTCHMMA was wrapped in ~20 instructions of uniform-register shuffling, and four
+  // MMAs per k block took longer to issue (~720 clocks) than to execute (512).
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
-        for (int kb = 0; kb < nk; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one_sync()) {
           unsigned char* st = smem + s * Cfg::kStage;
           mbar_expect_tx(&full[s], Cfg::kStage);
           tma_load_2d(st, &tmA, &full[s], kb * kFK, mb * kFM);
           tma_load_2d(st + Cfg::kABytes, &tmB, &full[s], kb * kFK, nb * BN);
-          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kFM, BN);
-      int s = 0, it = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+    constexpr uint32_t idesc = umma_idesc_bf16(kFM, BN);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        for (int kb = 0; kb < nk; ++kb) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
 #pragma unroll
           for (int ks = 0; ks < kFK / 16; ++ks)
             umma_bf16(tmem + buf * BN, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
                       (kb | ks) != 0);
           umma_commit(&empty[s]);
-          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+          if (kb == nk - 1) umma_commit(&acc_full[buf]);
         }
-        umma_commit(&acc_full[buf]);
+        __syncwarp();
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -341,25 +346,26 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_pair_k
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = pair; tile < tiles; tile += npairs) {
-        const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
-        for (int kb = 0; kb < nk; ++kb) {
-          mbar_wait_cluster(&empty[s], ph ^ 1);
+  if (warp == 0) {   // whole warp, issue under elect_one_sync (see gemm_nt_epi_kernel)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = pair; tile < tiles; tile += npairs) {
+      const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait_cluster(&empty[s], ph ^ 1);
+        if (elect_one_sync()) {
           unsigned char* st = smem + s * Cfg::kStage;
           const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
           if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::kStage);
           tma_load_2d_pair(st, &tmA, lead_full, kb * kFK, (2 * mb + (int)rank) * kFM);     // rows past M: zero fill
           tma_load_2d_pair(st + Cfg::kABytes, &tmB, lead_full, kb * kFK, nb * BN + (int)rank * (BN / 2));
-          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * kFM, BN);
       int s = 0, it = 0;
       uint32_t ph = 0;
@@ -370,15 +376,18 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_pair_k
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait_cluster(&full[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
 #pragma unroll
-          for (int ks = 0; ks < kFK / 16; ++ks)
-            umma_bf16_pair(tmem + buf * BN, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
-                           (kb | ks) != 0);
-          umma_commit_pair(&empty[s]);
+            for (int ks = 0; ks < kFK / 16; ++ks)
+              umma_bf16_pair(tmem + buf * BN, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
+                             (kb | ks) != 0);
+            umma_commit_pair(&empty[s]);
+            if (kb == nk - 1) umma_commit_pair(&acc_full[buf]);
+          }
+          __syncwarp();
           if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
         }
-        umma_commit_pair(&acc_full[buf]);
       }
     }
   } else {

@@ -118,17 +118,20 @@ HW_DEV void tn_issue(unsigned char* smem, uint64_t* full, uint64_t* empty, uint3
   constexpr uint32_t idesc = umma_idesc_bf16(128, BN, true, true);
   constexpr uint32_t idesc1 = umma_idesc_bf16(128, 16, true, true);
   const uint32_t sones = smem_u32(smem + Cfg::kOnesOff);
-  for (; kb < kend; ++kb) {
+  for (; kb < kend; ++kb) {   // whole warp; MMAs and commits from one elected lane
     mbar_wait(&full[s], ph);
     tc_fence_after();
-    const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
+    if (elect_one_sync()) {
+      const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {  // 16 tokens per step = two 8-row atoms = 2 KB
-      const uint64_t da = umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024);
-      umma_bf16(tmem, da, umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024), idesc, (kb > main_first) | (ks > 0));
-      if (SUM) umma_bf16(tmem + Cfg::kOnesCol, da, umma_desc_mn_sw128(sones, 8192, 1024), idesc1, (kb > sum_first) | (ks > 0));
+      for (int ks = 0; ks < 4; ++ks) {  // 16 tokens per step = two 8-row atoms = 2 KB
+        const uint64_t da = umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024);
+        umma_bf16(tmem, da, umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024), idesc, (kb > main_first) | (ks > 0));
+        if (SUM) umma_bf16(tmem + Cfg::kOnesCol, da, umma_desc_mn_sw128(sones, 8192, 1024), idesc1, (kb > sum_first) | (ks > 0));
+      }
+      umma_commit(&empty[s]);
     }
-    umma_commit(&empty[s]);
+    __syncwarp();
     if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
   }
 }
@@ -173,12 +176,12 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty[s], ph ^ 1);
+  if (warp == 0) {   // whole warp; the copies are issued by one elected lane (elect_one_sync, tc.cuh)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one_sync()) {
         unsigned char* st = smem + s * Cfg::kStage;
         mbar_expect_tx(&full[s], Cfg::kStage);
 #pragma unroll
@@ -186,17 +189,19 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
           tma_load_2d(st + Cfg::kABytes + j * 8192, &tmB, &full[s], nb * BN + j * 64, kb * 64);
-        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int s = 0;
       uint32_t ph = 0;
       tn_issue<BN, false>(smem, full, empty, tmem, kb0, sum0, kb0, sum0, s, ph);
       tn_issue<BN, true>(smem, full, empty, tmem, sum0, sum1, kb0, sum0, s, ph);
       tn_issue<BN, false>(smem, full, empty, tmem, sum1, kb1, kb0, sum0, s, ph);
-      umma_commit(acc_full);
+      if (elect_one_sync()) umma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
@@ -279,15 +284,18 @@ HW_DEV void tn_pair_issue(unsigned char* smem, uint64_t* full, uint64_t* empty, 
   for (; kb < kend; ++kb) {
     mbar_wait_cluster(&full[s], ph);
     tc_fence_after();
-    const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
+    if (elect_one_sync()) {
+      const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + Cfg::kABytes;
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const uint64_t da = umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024);
-      umma_bf16_pair(tmem, da, umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024), idesc, (kb > main_first) | (ks > 0));
-      if (SUM)
-        umma_bf16_pair(tmem + Cfg::kOnesCol, da, umma_desc_mn_sw128(sones, 8192, 1024), idesc1, (kb > sum_first) | (ks > 0));
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t da = umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024);
+        umma_bf16_pair(tmem, da, umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024), idesc, (kb > main_first) | (ks > 0));
+        if (SUM)
+          umma_bf16_pair(tmem + Cfg::kOnesCol, da, umma_desc_mn_sw128(sones, 8192, 1024), idesc1, (kb > sum_first) | (ks > 0));
+      }
+      umma_commit_pair(&empty[s]);
     }
-    umma_commit_pair(&empty[s]);
+    __syncwarp();
     if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
   }
 }
@@ -332,13 +340,13 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_pair_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      const int acol = (2 * mb + (int)rank) * 128, bcol = nb * 256 + (int)rank * 128;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait_cluster(&empty[s], ph ^ 1);
+  if (warp == 0) {   // whole warp, issue under elect_one_sync
+    int s = 0;
+    uint32_t ph = 0;
+    const int acol = (2 * mb + (int)rank) * 128, bcol = nb * 256 + (int)rank * 128;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait_cluster(&empty[s], ph ^ 1);
+      if (elect_one_sync()) {
         unsigned char* st = smem + s * Cfg::kStage;
         const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
         if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::kStage);
@@ -346,17 +354,19 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_pair_kernel(const __grid_co
         for (int j = 0; j < 2; ++j) tma_load_2d_pair(st + j * 8192, &tmA, lead_full, acol + j * 64, kb * 64);
 #pragma unroll
         for (int j = 0; j < 2; ++j) tma_load_2d_pair(st + Cfg::kABytes + j * 8192, &tmB, lead_full, bcol + j * 64, kb * 64);
-        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       int s = 0;
       uint32_t ph = 0;
       tn_pair_issue<false>(smem, full, empty, tmem, kb0, sum0, kb0, sum0, s, ph);
       tn_pair_issue<true>(smem, full, empty, tmem, sum0, sum1, kb0, sum0, s, ph);
       tn_pair_issue<false>(smem, full, empty, tmem, sum1, kb1, kb0, sum0, s, ph);
-      umma_commit_pair(acc_full);
+      if (elect_one_sync()) umma_commit_pair(acc_full);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

@@ -35,6 +35,19 @@ HW_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of the (converged) warp.  The TMA / MMA roles run their loops and waits with the WHOLE warp and issue the
+// asynchronous instructions under this predicate: inside `if (lane == 0)` the compiler is in divergent code and wraps
+// every UTMALDG / UTCHMMA (their operands are uniform registers) in an ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY loop,
+// ~20 dependent instructions per MMA, which took longer to issue (~180 clocks) than a 128 x 192 x 16 MMA takes to
+// execute (96): K2 at d=512 spent 37 % of its warp samples waiting for accumulators.  With the converged warp the four
+// MMAs of a k block are four consecutive UTCHMMAs.  (One polling lane + __syncwarp instead of 32 polling lanes was
+// measured too: slower.)
+HW_DEV bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 // generic-proxy smem writes (st.shared / cp.async) -> visible to the async proxy (UMMA, TMA)
 HW_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
