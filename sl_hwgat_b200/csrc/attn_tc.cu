@@ -242,7 +242,7 @@ HW_DEV void tc_producer(const TileGeom& geo, int heads, int tiles, int S, TcBars
 // warp 1: tcgen05.mma issuer shared by K2 and K3
 // ---------------------------------------------------------------------------
 HW_DEV void tc_issuer(const TileGeom& geo, int heads, int tiles, int S, TcBars* bars, unsigned char* sX,
-                      unsigned char* sW, unsigned char* sOnes, unsigned char* sBias, uint32_t tmem) {
+                      unsigned char* sW, unsigned char* sOnes, unsigned char* sBias, uint32_t tmem, int pace) {
   // whole warp (see elect_one_sync): waits are warp-uniform, MMAs and commits come from the elected lane
   constexpr uint32_t idesc = umma_idesc_bf16(128, 192);
   const int nk = geo.d / 64;
@@ -275,6 +275,12 @@ HW_DEV void tc_issuer(const TileGeom& geo, int heads, int tiles, int S, TcBars* 
           if (c == nk - 1) umma_commit(&bars->acc_full[buf]);
         }
         __syncwarp();
+        // Pacing: the attention warps' HMMAs share the tensor pipe with these MMAs and wait behind whatever is queued.
+        // Where the attention warps are the limiter (forward at d = 128, backward at d <= 256) the next chunk is issued
+        // only after this one has completed, so an HMMA waits for at most four MMAs (measured: forward -10 % at
+        // d = 128, backward -4 % at d = 128 / 256; where the MMA is the limiter it costs 5-12 %; waiting after every
+        // single MMA is slower everywhere).
+        if (pace) mbar_wait(&bars->w_empty[s], wph);
         if (++s == S) { s = 0; wph ^= 1; }
       }
     }
@@ -293,6 +299,7 @@ struct FwdTcArgs {
   bf16* out;
   float threshold;
   int heads, tiles, w_stages;
+  int pace;   // 1: one chunk of MMAs in flight at a time (tc_issuer)
   TileGeom geo;
 };
 
@@ -330,11 +337,15 @@ static int prep_qkv(const AttnArgs& a, bf16* wp, bf16* bias_tiles, cudaStream_t 
   return (int)cudaGetLastError();
 }
 
-// weight-ring depth: what is left of the 227 KB after the resident X tile, at most 6 stages
+// weight-ring depth: THREE stages of one 64-column chunk (24 KB) each.  A deeper ring (up to 6 fit next to the
+// resident X tile) lets the MMA warp run ahead in long bursts of back-to-back UTCHMMAs that hold the tensor pipe
+// against the attention warps' HMMAs: measured forward 8-10 % slower at every width with 4-6 stages than with 3
+// (0.60 / 0.63 / 0.94 ms against 0.53 / 0.58 / 0.86 ms at d = 128 / 256 / 512), backward equal; 2 stages starve the
+// backward at d = 512 (2.84 against 2.62 ms).
 static int w_stages_for(int d) {
   const int left = 232448 - 1024 - (int)sizeof(TcBars) - kOnesBytes - 2 * kBiasTile - (d / 64) * kXChunk;
   const int st = left / kWStage;
-  return st > 6 ? 6 : st;
+  return st > 3 ? 3 : st;
 }
 
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
@@ -360,7 +371,7 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   if ((st = make_tmap_2d(&tmW, wp, (uint64_t)3 * d, (uint64_t)d, 64))) return st;
   FwdTcArgs p;
   p.bias_tiles = bias_tiles; p.bits = a.bits; p.out = (bf16*)a.out; p.threshold = a.threshold;
-  p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages;
+  p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages; p.pace = d == 128;   // forward: see tc_issuer
   p.geo = make_geom(a.F, a.K, d, a.shift, a.layout);
   const int grid = p.tiles < 148 ? p.tiles : 148;
   if (a.threshold >= 0.f)   // training: threshold drop (HWGATE.py:94-100) compiled in
@@ -537,7 +548,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
   if (warp < kFirstEpiWarp) {
     reg_dealloc_donor();
     if (warp == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, sBias, p.bias_tiles, &tmX, &tmW);
-    if (warp == 1) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, sOnes, sBias, tmem);
+    if (warp == 1) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, sOnes, sBias, tmem, p.pace);
   } else {
     reg_alloc_epi();
     const int win = warp & 3;                      // TMEM lane quarter == window of the tile
@@ -618,6 +629,7 @@ struct BwdTcArgs {
   bf16* dqkv;
   float threshold;
   int heads, tiles, w_stages;
+  int pace;   // 1: one chunk of MMAs in flight at a time (tc_issuer)
   TileGeom geo;
 };
 
@@ -712,7 +724,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_bwd_tc_kernel(const __grid
   if (warp < kFirstEpiWarp) {
     reg_dealloc_donor();
     if (warp == 0) tc_producer(p.geo, heads, p.tiles, S, bars, sX, sW, sBias, p.bias_tiles, &tmX, &tmW);
-    if (warp == 1) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, sOnes, sBias, tmem);
+    if (warp == 1) tc_issuer(p.geo, heads, p.tiles, S, bars, sX, sW, sOnes, sBias, tmem, p.pace);
   } else {
     reg_alloc_epi();
     const int win = warp & 3;
@@ -890,7 +902,7 @@ int attn_bwd_tc(const AttnArgs& a, bf16* dqkv, cudaStream_t s) {
   if ((st = make_tmap_2d(&tmW, wp, (uint64_t)3 * d, (uint64_t)d, 64))) return st;
   BwdTcArgs p;
   p.bias_tiles = bias_tiles; p.bits = a.bits; p.d_out = (const bf16*)a.d_out; p.dqkv = dqkv; p.threshold = a.threshold;
-  p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages;
+  p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages; p.pace = d <= 256;   // backward: see tc_issuer
   p.geo = make_geom(a.F, a.K, d, a.shift, a.layout);
   const int grid = p.tiles < 148 ? p.tiles : 148;
   if (a.threshold >= 0.f)
