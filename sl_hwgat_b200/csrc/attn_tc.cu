@@ -1,21 +1,28 @@
-// K2 on tcgen05: fused QKV projection + windowed graph attention, bf16.
+// K2 / K3 on tcgen05: fused QKV projection + windowed graph attention (forward, and backward with
+// recompute), bf16.
 //
 // Persistent CTA (one per SM), one tile (128 tokens = 4 windows) at a time, all
 // heads of the tile inside the CTA:
 //
-//   warp 0      TMA producer: the X tile (resident in smem for all heads; the
-//               roll / window partition is the box coordinate of 16-token TMA
-//               boxes) and a ring of per-head weight chunks Wh[192 x 64].
-//   warp 1      tcgen05.mma issuer: QKV_h[128 x 192] = X[128 x d] . Wh^T, fp32
-//               accumulator in TMEM, two accumulators so head h+1 is multiplied
-//               while head h is in the attention phase.
-//   warps 2-9   attention: warp = (window, 16 query rows).  tcgen05.ld.16x256b
-//               returns the accumulator directly in the HMMA C-fragment layout,
-//               so q (A fragments), k (B fragments of q.k^T) and, after one
-//               movmatrix.trans per 8x8 block, v (B fragments of P.v) are built
-//               in registers: Q, K, V, S and P never touch shared memory.
-//               S = q k^T, threshold drop, packed graph/shift mask, -10000 fill,
-//               softmax, O = P v  (HWGATE.py:89-114), O written in token order.
+//   warp 0      TMA producer (whole warp, copies issued under elect.sync): the X tile
+//               (resident in smem for all heads; the roll / window partition is the box
+//               coordinate of 16-token TMA boxes) and a three-stage ring of per-head
+//               weight chunks Wh[192 x 64].
+//   warp 1      tcgen05.mma issuer (whole warp, MMAs under elect.sync):
+//               QKV_h[128 x 192] = X[128 x d] . Wh^T (+ bias through a ones-column K step),
+//               fp32 accumulator in TMEM, two accumulators so head h+1 is multiplied
+//               while head h is in the attention phase.  Where the attention warps are
+//               the limiter the chunks are paced (they share the tensor pipe with the
+//               attention warps' HMMAs).
+//   warps 2-3   idle; with warps 0-1 they donate registers (setmaxnreg) to
+//   warps 4-11  attention: ONE warp per window (all 32 query rows), the two warp sets
+//               (4-7, 8-11) take alternate heads.  tcgen05.ld.16x256b returns the
+//               accumulator directly in the HMMA C-fragment layout, so q (A fragments),
+//               k (B fragments of q.k^T) and, after one movmatrix.trans per 8x8 block,
+//               v (B fragments of P.v) are built in registers: Q, K, V, S and P never
+//               touch shared memory.  S = q k^T, threshold drop, packed graph/shift mask,
+//               -10000 fill, softmax, O = P v  (HWGATE.py:89-114), O written in token
+//               order; the backward kernel recomputes P and forms dq, dk, dv the same way.
 #include <cstdlib>
 
 #include "tc.cuh"
