@@ -1,15 +1,20 @@
 #!/usr/bin/env python
 """HWGATE fwd+bwd throughput on B200 (BASELINE.json metric: sequences/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
-    python bench.py --impl reference [--steps K] [--warmup W]      # CPU reference arm (oracle port)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config NAME]   # our arm
+    python bench.py --impl reference [--steps K] [--warmup W]             # CPU reference arm (oracle port)
 
-One step = zero_grad + forward + SmoothedCrossEntropyLoss + backward of the full
-HWGATE model (reference hierarchy: depths [2,2,4], heads [2,4,8], W=16, TP=2) on
-a synthetic keypoint batch, bf16 autocast, dropout 0.1 and the training
-threshold path on (model.train()), as the reference trains.  N > 1: batch-sharded
-(weak scaling: 512 sequences per GPU) with the NCCL gradient all-reduce inside
-the step.  Prints ONE JSON line (rank 0).
+--config train512 (default; BASELINE configs[2] / [3]): one step = zero_grad + forward +
+SmoothedCrossEntropyLoss + backward of the full HWGATE model (reference hierarchy: depths [2,2,4],
+heads [2,4,8], W=16, TP=2) on a synthetic keypoint batch, bf16 autocast, dropout 0.1 and the training
+threshold path on (model.train()), as the reference trains.  N > 1: batch-sharded (weak scaling: 512
+sequences per GPU) with the NCCL gradient all-reduce inside the step.
+--config infer256_t192 (configs[1]): eval forward, batch 256 per GPU, T=192, 2002 classes, bf16; N > 1
+shards the batch with no collective.
+--config train_t256 / train_t256_w32 / train_t256_w64 (configs[4]): T=256, 128 sequences per GPU
+(global 1024 on 8 GPUs), window_size 16 / 32 / 64 ("larger temporal windows": N = 32 / 64 / 128 tokens).
+--strong: fixed GLOBAL batch (--batch) split over the ranks.
+Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -28,6 +33,33 @@ METRIC = "HWGAT sequences/sec fwd+bwd"
 UNIT = "sequences/s"
 T_FRAMES, KPS, CLASSES = 64, 64, 262
 DEPTHS, HEADS, EMBED = [2, 2, 4], [2, 4, 8], 128
+WINDOW = 16
+
+CONFIGS = {
+    # name: (mode, frames, classes, per-GPU batch, window_size, what BASELINE.json calls it)
+    "train512": ("train", 64, 262, 512, 16,
+                 "BASELINE configs[2]: HWGATE training fwd+bwd, T=64 frames x 64 keypoints x 2, 262 classes "
+                 "(INCLUDE shape), depths [2,2,4], heads [2,4,8], W=16, TP=2, train mode (threshold drop + dropout 0.1)"),
+    "infer256_t192": ("infer", 192, 2002, 256, 16,
+                      "BASELINE configs[1]: HWGATE inference forward, batch 256 x T=192 frames x 64 keypoints x 2, "
+                      "2002 classes (FDMSE-ISL shape), bf16, eval mode"),
+    "train_t256": ("train", 256, 262, 128, 16,
+                   "BASELINE configs[4] at the reference window (W=16): training fwd+bwd, T=256 frames, 128 sequences "
+                   "per GPU (1024 on 8 GPUs), 262 classes, train mode"),
+    "train_t256_w32": ("train", 256, 262, 128, 32,
+                       "BASELINE configs[4], larger windows W=32 (N=64 tokens per window): training fwd+bwd, T=256, "
+                       "128 sequences per GPU, 262 classes, train mode"),
+    "train_t256_w64": ("train", 256, 262, 128, 64,
+                       "BASELINE configs[4], larger windows W=64 (N=128 tokens per window): training fwd+bwd, T=256, "
+                       "128 sequences per GPU, 262 classes, train mode"),
+}
+
+
+def set_config(name):
+    global T_FRAMES, CLASSES, WINDOW, METRIC
+    mode, T_FRAMES, CLASSES, batch, WINDOW, what = CONFIGS[name]
+    METRIC = "HWGAT sequences/sec fwd+bwd" if mode == "train" else "HWGAT sequences/sec inference forward"
+    return mode, batch, what
 
 
 def peaks():
@@ -89,8 +121,8 @@ def attn_flops(B, level, backward):
     """algorithmic FLOPs of K2 (x2 for K3) for one block of `level`."""
     F = T_FRAMES >> level
     d, h = EMBED << level, HEADS[level]
-    n, nwin = B * F * KPS, B * (F // 2) * (KPS // 16)
-    fwd = 6.0 * n * d * d + 4.0 * nwin * h * 32 * 32 * 64
+    n, nwin, N = B * F * KPS, B * (F // 2) * (KPS // WINDOW), 2 * WINDOW
+    fwd = 6.0 * n * d * d + 4.0 * nwin * h * N * N * 64
     return fwd * (2.0 if backward else 1.0)
 
 
@@ -204,6 +236,8 @@ def build_model(device, drop=0.1):
     from sl_hwgat_b200.models import HWGATE, model_params
     p = model_params.HWGATEParams({"num_class": CLASSES, "src_len": T_FRAMES}, 2, device)
     p.drop_rate = drop
+    if WINDOW != p.window_size:
+        p.set_window_size(WINDOW)
     torch.manual_seed(1001)                       # the reference's seed (configs.py:55)
     return HWGATE.Model(*p.get_model_params()).to(device)
 
@@ -222,16 +256,17 @@ def synthetic_batch(B):
     return x, y
 
 
-def cpu_reference_arm(steps, warmup, batch=8):
-    """The reference's CPU path (oracle port, fp32, train mode, dropout 0.1) on the host cores."""
+def cpu_reference_arm(steps, warmup, batch=8, mode="train"):
+    """The reference's CPU path (oracle port, fp32; train mode with dropout 0.1, or the eval forward) on the host cores."""
     import torch
     from oracle import hwgate_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.HWGATEConfig(temporal_dim=T_FRAMES, num_classes=CLASSES)
+    cfg = O.HWGATEConfig(temporal_dim=T_FRAMES, num_classes=CLASSES, window_size=WINDOW,
+                         edges=O.HWGATEConfig().edges[:KPS // WINDOW])
     sd = O.make_state_dict(cfg, seed=1001)
     for k, v in sd.items():
-        if k not in ("B", "pos_encoder.pe") and not k.endswith("attn_mask"):
+        if mode == "train" and k not in ("B", "pos_encoder.pe") and not k.endswith("attn_mask"):
             v.requires_grad_(True)
     x = O.synthetic_keypoints(batch, T_FRAMES, 2, seed=1001)
     y = O.synthetic_labels(batch, CLASSES, seed=1001)
@@ -239,42 +274,117 @@ def cpu_reference_arm(steps, warmup, batch=8):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        for v in sd.values():
-            v.grad = None
-        thr = [torch.rand(1).item() for _ in range(sum(cfg.depths))]
-        loss = O.smoothed_cross_entropy(O.model_forward(x, sd, cfg, thresholds=thr, drop=0.1), y)
-        loss.backward()
+        if mode == "train":
+            for v in sd.values():
+                v.grad = None
+            thr = [torch.rand(1).item() for _ in range(sum(cfg.depths))]
+            loss = O.smoothed_cross_entropy(O.model_forward(x, sd, cfg, thresholds=thr, drop=0.1), y)
+            loss.backward()
+        else:
+            with torch.no_grad():
+                O.model_forward(x, sd, cfg)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     total = sum(times)
     return {"value": batch * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle port of the reference (fp32, train mode, dropout 0.1), batch {batch} x T={T_FRAMES} "
-                      f"x 64 kp x 2, {CLASSES} classes, {len(times)} fwd+bwd steps after {warmup} warm-up",
-            "ms_per_step": 1e3 * total / len(times)}
+            "sample": f"oracle port of the reference (fp32, " +
+                      ("train mode, dropout 0.1" if mode == "train" else "eval forward") +
+                      f"), batch {batch} x T={T_FRAMES} x 64 kp x 2, {CLASSES} classes, window_size {WINDOW}, "
+                      f"{len(times)} " + ("fwd+bwd" if mode == "train" else "forward") + f" steps after {warmup} warm-up",
+            "ms_per_step": 1e3 * total / len(times), "batch": batch}
+
+
+def gpu_eager_baseline(dev, mode, batch):
+    """The incumbent BASELINE.md section 3 names: the reference's op sequence in eager PyTorch on this B200
+    (cuBLAS / ATen kernels, no kernel of ours).  /root/reference cannot travel to the box, so the op sequence is the
+    oracle's restatement of it (oracle.model_forward: roll, partition, Linear, softmax, ..., one ATen call per
+    reference op) run on CUDA tensors, in fp32 (what main.py runs, utils.py:102) and under autocast(bf16), same
+    seeds, dropout 0.1, threshold path on.  A reported baseline, timed with CUDA events after our own timed regions."""
+    import torch
+    from oracle import hwgate_oracle as O
+    cfg = O.HWGATEConfig(temporal_dim=T_FRAMES, num_classes=CLASSES, window_size=WINDOW,
+                         edges=O.HWGATEConfig().edges[:KPS // WINDOW])
+    sd = {k: v.to(dev) for k, v in O.make_state_dict(cfg, seed=1001).items()}
+    train = mode == "train"
+    for k, v in sd.items():
+        if train and k not in ("B", "pos_encoder.pe") and not k.endswith("attn_mask"):
+            v.requires_grad_(True)
+    out = {}
+    for name, autocast in (("fp32", False), ("bf16_autocast", True)):
+        B = batch
+        while B >= 8:
+            try:
+                x = O.synthetic_keypoints(B, T_FRAMES, 2, seed=1001).to(dev)
+                y = O.synthetic_labels(B, CLASSES, seed=1001).to(dev)
+                torch.manual_seed(1001)
+
+                def step():
+                    if not train:
+                        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                            return O.model_forward(x, sd, cfg)
+                    for v in sd.values():
+                        v.grad = None
+                    thr = [torch.rand(1).item() for _ in range(sum(cfg.depths))]
+                    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                        logits = O.model_forward(x, sd, cfg, thresholds=thr, drop=0.1)
+                    loss = O.smoothed_cross_entropy(logits.float(), y)
+                    loss.backward()
+                    return loss
+
+                for _ in range(2):
+                    step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = 3
+                e0.record()
+                for _ in range(n):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / n
+                out[name] = {"value": B / (ms * 1e-3), "unit": UNIT, "batch": B, "ms_per_step": ms,
+                             "max_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+                break
+            except torch.OutOfMemoryError:
+                B //= 2
+            finally:
+                for v in sd.values():
+                    v.grad = None
+                x = y = None
+                torch.cuda.empty_cache()
+    out["what"] = ("eager PyTorch (cuBLAS/ATen) restatement of the reference's op sequence on the same B200, "
+                   + ("train fwd+bwd, dropout 0.1, threshold path" if train else "eval forward"))
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_arm(args.steps, args.warmup)
+    mode, _, what = set_config(args.config)
+    r = cpu_reference_arm(args.steps, args.warmup, mode=mode)
+    cfg = workload_config(1, r["batch"], what, mode, False)
+    cfg["note"] = ("a bounded CPU sample of the same workload: batch %d per step on the host cores (the GPU arm runs "
+                   "its own per-GPU batch); sequences/s normalises it" % r["batch"])
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus, args.batch),
+            "config": cfg,
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, per_gpu_batch):
-    return {"workload": "BASELINE configs[2]: HWGATE training fwd+bwd, T=64 frames x 64 keypoints x 2, "
-                        f"{CLASSES} classes (INCLUDE shape), depths [2,2,4], heads [2,4,8], W=16, TP=2, "
-                        "train mode (threshold drop + dropout 0.1)",
-            "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * n_gpus, "frames": T_FRAMES,
-            "parallelism": f"dp{n_gpus} batch-sharded, NCCL grad all-reduce" if n_gpus > 1 else "single GPU",
+def workload_config(n_gpus, per_gpu_batch, what, mode, strong):
+    par = "single GPU"
+    if n_gpus > 1:
+        par = (f"dp{n_gpus} batch-sharded, NCCL grad all-reduce" if mode == "train"
+               else f"dp{n_gpus} batch-sharded inference, no collective")
+    return {"workload": what, "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * n_gpus,
+            "frames": T_FRAMES, "window_size": WINDOW, "tokens_per_window": 2 * WINDOW, "parallelism": par,
+            "scaling_mode": "strong (fixed global batch)" if strong else "weak (fixed per-GPU batch)",
             "l2": "activations per block (>= 0.5 GB) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -284,11 +394,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="sequences per GPU")
+    ap.add_argument("--config", default="train512", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="sequences per GPU (default: the config's); with --strong: global")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --batch is the GLOBAL batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--trace-allreduce", action="store_true", help="CUDA events around every gradient bucket")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    mode, cfg_batch, what = set_config(args.config)
+    train = mode == "train"
 
     # stdout carries exactly one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG >= VERSION, so a
     # bare VERSION setting is dropped and anything NCCL does log goes to stderr
@@ -306,19 +422,31 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.load()
-    B = args.batch
-    model = build_model(dev).train()
+    B = args.batch or cfg_batch
+    if args.strong:
+        if B % world:
+            raise SystemExit("--strong needs a global batch divisible by the number of GPUs")
+        B //= world
+    model = build_model(dev)
+    model = model.train() if train else model.eval()
     parallel.broadcast_parameters(model)
-    parallel.sync_threshold_rng(1001)             # same threshold sequence on every rank
+    parallel.sync_threshold_rng(1001, model)      # same threshold sequence on every rank
     criterion = SmoothedCrossEntropyLoss()
-    sync = parallel.GradientAllReduce(model) if world > 1 else None
+    sync = parallel.GradientAllReduce(model, trace=args.trace_allreduce) if (world > 1 and train) else None
     xg, yg = synthetic_batch(B * world)
     sl = parallel.shard_batch(B * world, rank, world)
     x_host, y_host = xg[sl].contiguous().pin_memory(), yg[sl].contiguous().pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    pred_host = torch.empty(B, dtype=torch.int64).pin_memory()
 
     def step(xd, yd):
-        model.zero_grad(set_to_none=True)
+        if not train:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                return model(xd)
+        if sync is not None:
+            sync.zero_grad()
+        else:
+            model.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = model(xd)
         loss = criterion(logits, yd)
@@ -352,8 +480,29 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
 
+    # gradient all-reduce trace of ONE extra step: when each bucket's collective ran relative to backward
+    ar_trace = None
+    if sync is not None and args.trace_allreduce:
+        barrier()
+        t0, t_bwd = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_end = torch.cuda.Event(enable_timing=True)
+        sync.zero_grad()
+        t0.record()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = model(x_dev)
+        loss = criterion(logits, y_dev)
+        loss.backward()
+        t_bwd.record()
+        sync.finish()
+        t_end.record()
+        torch.cuda.synchronize()
+        ar_trace = {"backward_done_ms": t0.elapsed_time(t_bwd), "step_done_ms": t0.elapsed_time(t_end),
+                    "buckets": [{"bucket": bi, "bytes": nb, "start_ms": a, "end_ms": b}
+                                for bi, nb, a, b in sync.trace_report(t0)]}
+
     # end to end through the public API with host buffers: H2D of the step's inputs from pinned
-    # memory and the D2H read of the loss inside the timed region (as utils.py:99-109 does)
+    # memory and the D2H read of the loss (training, as utils.py:99-109 does) or of the predictions (inference,
+    # utils.py:128-133) inside the timed region
     xd, yd = torch.empty_like(x_dev), torch.empty_like(y_dev)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -361,8 +510,12 @@ def main():
     last = 0.0
     for _ in range(args.steps):
         xd.copy_(x_host, non_blocking=True)
-        yd.copy_(y_host, non_blocking=True)
-        last = step(xd, yd).item()
+        if train:
+            yd.copy_(y_host, non_blocking=True)
+            last = step(xd, yd).item()
+        else:
+            pred_host.copy_(step(xd, yd).argmax(dim=1))      # blocking D2H of the predicted classes
+            last = float(pred_host[0])
     f1.record()
     barrier()
     ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
@@ -383,7 +536,7 @@ def main():
                     "unit": "TFLOP/s", "frac": top["achieved"] / peak, "traffic": None,
                     "peak_source": pk["source"] + " (sustained bf16 GEMM)", "avg_ms": top["avg_ms"]}
             tr = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.exists(tr):
+            if os.path.exists(tr) and args.config == "train512":
                 try:
                     roof["traffic"] = json.load(open(tr)).get(top["kernel"])
                 except Exception:
@@ -393,21 +546,34 @@ def main():
         for k in kern:
             k["frac"] = k["achieved"] / (pk["bf16_tflops_sustained"] if k["bound"] == "tensor" else pk["hbm_gbs"])
             k.pop("total_ms", None)
+        h2d = x_host.numel() * 4 + (y_host.numel() * 8 if train else 0)
         line = {"metric": METRIC, "value": B * world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic", "config": workload_config(world, B),
+                "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic", "config": workload_config(world, B, what, mode, args.strong),
                 "e2e": {"value": B * world * args.steps / (ms2 * 1e-3), "unit": UNIT,
-                        "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
-                        "ms_per_step": ms2 / args.steps, "last_loss": last},
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if train else B * 8,
+                        "ms_per_step": ms2 / args.steps, "last_loss" if train else "last_pred": last},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof,
                 "attn_tensor_frac": {"alg_tflop_per_step": tot_fl / 1e12, "attn_ms_per_step": tot_ms,
                                      "achieved_tflops": tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms else None,
                                      "frac_of_sustained_peak": (tot_fl / (tot_ms * 1e-3) / 1e12 /
                                                                 pk["bf16_tflops_sustained"]) if tot_ms else None},
                 "kernels": kern}
+        if ar_trace is not None:
+            line["allreduce_trace"] = ar_trace
+        if world == 1 and not args.no_eager_baseline:
+            del model
+            torch.cuda.empty_cache()
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(dev, mode, min(B, 128))
+                eb = line["gpu_eager_baseline"].get("bf16_autocast") or line["gpu_eager_baseline"].get("fp32")
+                if eb:
+                    line["speedup_vs_gpu_eager_bf16"] = line["value"] / eb["value"]
+            except Exception as exc:      # a reported baseline must not take the bench line down with it
+                line["gpu_eager_baseline"] = {"error": repr(exc)[:300]}
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference_arm(3, 1)
+            cb = cpu_reference_arm(3, 1, mode=mode)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:

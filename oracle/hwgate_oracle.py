@@ -231,7 +231,7 @@ def attention_core(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, h
     k = _rb(qkv[1], bf16_points)
     v = _rb(qkv[2], bf16_points)
     s = q @ k.transpose(-1, -2)                                         # (B_, h, N, N)
-    m = torch.from_numpy(mask).to(torch.bool)                           # (f*nW, N, N)
+    m = torch.from_numpy(mask).to(device=s.device, dtype=torch.bool)    # (f*nW, N, N)
     m = m.unsqueeze(0).unsqueeze(2).expand(B, f * nW, heads, N, N).reshape(B * f * nW, heads, N, N)
     if threshold is not None:
         p0 = torch.softmax(s.detach(), dim=-1)
@@ -261,7 +261,7 @@ def attention_core_backward(xn, w_qkv, b_qkv, heads, mask, W, TP, shift, thresho
     qkv = (xw @ w_qkv.t() + b_qkv).reshape(-1, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0] * scale, qkv[1], qkv[2]
     s = q @ k.transpose(-1, -2)
-    m = torch.from_numpy(mask).to(torch.bool)
+    m = torch.from_numpy(mask).to(device=s.device, dtype=torch.bool)
     m = m.unsqueeze(0).unsqueeze(2).expand(B, f * nW, heads, N, N).reshape(B * f * nW, heads, N, N)
     if threshold is not None:
         m = m & ~(torch.softmax(s, dim=-1) > threshold)

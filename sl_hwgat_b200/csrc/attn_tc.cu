@@ -43,6 +43,7 @@ constexpr int kXChunk = kTileTok * 128;   // 16 KB: 128 rows x 64 bf16
 constexpr int kWStage = 192 * 128;        // 24 KB: q|k|v rows of one head x 64 bf16
 constexpr int kMaxChunks = 8;             // d <= 512
 constexpr int kMaxWStages = 8;
+constexpr int kMaxDynSmem = 232448;       // 227 KB: the opt-in limit per CTA on sm_100
 constexpr int kAccStride = 256;           // TMEM columns between the two accumulators
 // Bias (and the q scale) ride in the GEMM: one extra K=16 MMA step per head, A = a constant [128 x 16] tile whose
 // first two columns are 1, B = a per-head [192 x 16] tile whose first two columns are bf16 hi / lo of the bias
@@ -359,12 +360,11 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   const int d = a.d, nk = d / 64;
   const int stages = w_stages_for(d);
   const int smem_bytes = nk * kXChunk + stages * kWStage + kOnesBytes + 2 * kBiasTile + (int)sizeof(TcBars) + 1024;
-  static int attr_smem = 0;
-  if (smem_bytes > attr_smem) {
-    cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    attr_smem = smem_bytes;
-  }
+  static PerDeviceOnce once;
+  once.run([] {
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  });
   CUtensorMap tmX, tmW;
   int st;
   if (a.layout == HWGAT_LAYOUT_WINDOWS) {
@@ -890,12 +890,11 @@ int attn_bwd_tc(const AttnArgs& a, bf16* dqkv, cudaStream_t s) {
   const int d = a.d, nk = d / 64;
   const int stages = w_stages_for(d);
   const int smem_bytes = nk * kXChunk + stages * kWStage + kOnesBytes + 2 * kBiasTile + (int)sizeof(TcBars) + 1024;
-  static int attr_smem = 0;
-  if (smem_bytes > attr_smem) {
-    cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    attr_smem = smem_bytes;
-  }
+  static PerDeviceOnce once;
+  once.run([] {
+    cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  });
   CUtensorMap tmX, tmW;
   int st;
   if (a.layout == HWGAT_LAYOUT_WINDOWS) {

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/hwgat_b200.h"
 
 #define HW_DEV __device__ __forceinline__
@@ -20,6 +22,22 @@ constexpr int kTileTok = 128;          // tokens per tile = one temporal group =
 // Every launch made by the library is counted (hwgat_launch_count()).
 extern unsigned long long g_launches;
 inline void count_launch(int n = 1) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute: every launcher opts its kernel in once
+// per device (a process may drive several GPUs, and autograd runs backward on its own threads; setting the attribute
+// twice from two racing threads is harmless).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  template <class Fn>
+  void run(Fn&& fn) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return;
+    fn();
+    done.fetch_or(bit, std::memory_order_release);
+  }
+};
 
 // ---- geometry of one tile -------------------------------------------------
 // A tile is 4 keypoint windows (64 keypoints, group kg) of temporal group fi of

@@ -272,11 +272,8 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_kernel
 template <int BN, int EPI>
 static int launch_epi(const bf16* A, const bf16* Bt, const EpiArgs& e, int M, int N, int K, cudaStream_t s) {
   using Cfg = FfnCfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(gemm_nt_epi_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    attr_done = true;
-  }
+  static PerDeviceOnce once;
+  once.run([] { cudaFuncSetAttribute(gemm_nt_epi_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem); });
   CUtensorMap tmA, tmB;
   int st;
   if ((st = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, kFM))) return st;
@@ -434,8 +431,8 @@ bool set_gemm_pair(bool on) {
 template <int EPI>
 static int launch_epi_pair(const bf16* A, const bf16* Bt, const EpiArgs& e, int M, int N, int K, cudaStream_t s) {
   using Cfg = PairCfg;
-  static bool attr_done = false;
-  static int max_clusters = 0;
+  static PerDeviceOnce once;
+  static std::atomic<int> max_clusters_s{0};
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -445,16 +442,17 @@ static int launch_epi_pair(const bf16* A, const bf16* Bt, const EpiArgs& e, int 
   cfg.stream = s;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (!attr_done) {
+  once.run([&] {
     cudaFuncSetAttribute(gemm_nt_epi_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     cfg.gridDim = dim3(148);
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, gemm_nt_epi_pair_kernel<EPI>, &cfg) != cudaSuccess || max_clusters < 1) {
+    int mc = 0;
+    if (cudaOccupancyMaxActiveClusters(&mc, gemm_nt_epi_pair_kernel<EPI>, &cfg) != cudaSuccess || mc < 1) {
       cudaGetLastError();
-      max_clusters = 74;
+      mc = 74;
     }
-    if (max_clusters > 74) max_clusters = 74;
-    attr_done = true;
-  }
+    max_clusters_s.store(mc > 74 ? 74 : mc);
+  });
+  const int max_clusters = max_clusters_s.load() > 0 ? max_clusters_s.load() : 74;
   CUtensorMap tmA, tmB;
   int st;
   if ((st = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, kFM))) return st;

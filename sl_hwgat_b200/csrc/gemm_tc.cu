@@ -234,11 +234,8 @@ template <int BN>
 static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd,
                      cudaStream_t s, bool perm64) {
   using Cfg = GemmTnCfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(gemm_tc_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    attr_done = true;
-  }
+  static PerDeviceOnce once;
+  once.run([] { cudaFuncSetAttribute(gemm_tc_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem); });
   CUtensorMap tmA, tmB;
   int st;
   if ((st = make_tmap_2d(&tmA, A, (uint64_t)Kd, (uint64_t)M, 64))) return st;
@@ -401,11 +398,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_pair_kernel(const __grid_co
 static int launch_tn_pair(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd,
                           cudaStream_t s, bool perm64) {
   using Cfg = GemmTnPairCfg;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(gemm_tc_tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    attr_done = true;
-  }
+  static PerDeviceOnce once;
+  once.run([] { cudaFuncSetAttribute(gemm_tc_tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem); });
   CUtensorMap tmA, tmB;
   int st;
   if ((st = make_tmap_2d(&tmA, A, (uint64_t)Kd, (uint64_t)M, 64))) return st;

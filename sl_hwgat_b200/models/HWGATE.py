@@ -109,10 +109,17 @@ class MSA(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         self.softmax = nn.Softmax(dim=-1)
         self._bits = {}  # packed masks, keyed by how they were derived
+        self._thr_gen = None  # see sl_hwgat_b200.parallel.sync_threshold_rng
 
     def _draw_threshold(self):
-        # one CPU-generator scalar per call, exactly where the reference draws it (HWGATE.py:96)
-        return torch.rand(1).item() if self.training else None
+        # one CPU-generator scalar per call, exactly where the reference draws it (HWGATE.py:96).  Data-parallel
+        # training installs a dedicated, identically seeded generator on every rank (parallel.sync_threshold_rng):
+        # the global CPU generator is also consumed by data loading at rank-dependent rates.
+        if not self.training:
+            return None
+        if self._thr_gen is not None:
+            return torch.rand(1, generator=self._thr_gen).item()
+        return torch.rand(1).item()
 
     def _project(self, ctx):
         return self.proj_drop(self.proj(ctx))
@@ -201,18 +208,34 @@ class PartAttentionBlock(nn.Module):
         else:
             attn_mask = None
         self.register_buffer("attn_mask", attn_mask)
-        self._bits = None
+        self._bits, self._bits_key = None, None
 
     def _block_bits(self, device):
-        if self._bits is None or self._bits.device != device:
-            adj = self.attn.adj_mat
+        """Packed graph + shift mask of this block (K1), rebuilt when `attn.adj_mat` is replaced or modified in
+        place (the reference multiplies by whatever tensor is there on every call, HWGATE.py:106-108)."""
+        adj = self.attn.adj_mat
+        key = (device, None if adj is None else (adj.data_ptr(), adj._version, tuple(adj.shape)))
+        if self._bits is None or self._bits_key != key:
             nW = self.num_kps // self.window_size
+            f = self.temporal_dim // self.temporal_patch_size
+            N = self.window_size * self.temporal_patch_size
             if adj is None:
-                adj = torch.ones(nW, 32, 32)
-            # the layer hands in the adjacency replicated over temporal groups (HWGATE.py:309);
-            # K1b replicates by index, so only the first nW windows are needed
-            self._bits = ops.mask_build(adj[:nW].to(device), self.temporal_dim, self.shift_size,
-                                        self.window_size, self.temporal_patch_size)
+                adj_d = torch.ones(nW, N, N, device=device)
+            else:
+                adj_d = adj.to(device)
+            if adj_d.shape[0] == nW or (adj_d.shape[0] == f * nW and
+                                        bool((adj_d.reshape(f, nW, N, N) == adj_d[:nW]).all().item())):
+                # the layer hands in the adjacency replicated over temporal groups (HWGATE.py:309);
+                # K1b replicates by index, so only the first nW windows are needed
+                self._bits = ops.mask_build(adj_d[:nW], self.temporal_dim, self.shift_size,
+                                            self.window_size, self.temporal_patch_size)
+            elif adj_d.shape[0] == f * nW:
+                # a per-temporal-group adjacency: pack the float tensors as MSA.forward would see them (K1c)
+                am = self.attn_mask.to(device) if self.attn_mask is not None else None
+                self._bits = ops.mask_pack(adj_d, am, f * nW, N, device)
+            else:
+                raise ValueError(f"adj_mat has {adj_d.shape[0]} windows; expected {nW} or {f * nW}")
+            self._bits_key = key
         return self._bits
 
     def _fusable(self, x):
@@ -220,7 +243,9 @@ class PartAttentionBlock(nn.Module):
         around the GEMMs run as the fused kernels K5-K7 instead of PyTorch ops."""
         return (x.dtype == torch.float32 and _attn_dtype(x) == torch.bfloat16 and self.dim in (128, 256, 512)
                 and type(self.norm1) is nn.LayerNorm and type(self.norm2) is nn.LayerNorm
-                and isinstance(self.ff.act, nn.GELU) and getattr(self.ff.act, "approximate", "none") == "none")
+                and isinstance(self.ff.act, nn.GELU) and getattr(self.ff.act, "approximate", "none") == "none"
+                and ops.proj_supported(x.numel() // self.dim, self.dim, self.dim)
+                and ops.ffn_supported(x.numel() // self.dim, self.dim, self.ff.fc1.weight.shape[0]))
 
     def _check_shape(self, x):
         B, F, K, d = x.shape
@@ -243,19 +268,10 @@ class PartAttentionBlock(nn.Module):
         ctx = ops.window_graph_attention(xn, attn.qkv.weight, attn.qkv.bias, self._block_bits(x.device),
                                          attn.num_heads, shift=self.shift_size, threshold=attn._draw_threshold(),
                                          layout=LAYOUT_BFKD)
-        if ops.proj_supported(ctx.numel() // self.dim, self.dim, self.dim):
-            a0 = ops.output_projection(ctx, attn.proj.weight)      # K12; bias, dropout, shortcut and norm2: K6
-        else:
-            a0 = nn.functional.linear(ctx, attn.proj.weight)
+        a0 = ops.output_projection(ctx, attn.proj.weight)          # K12; bias, dropout, shortcut and norm2: K6
         x, h = ops.bias_dropout_add_ln(x, a0, attn.proj.bias, self.norm2, attn.proj_drop.p, self.training)
-        hidden = ff.fc1.weight.shape[0]
-        if ops.ffn_supported(h.numel() // self.dim, self.dim, hidden):
-            # K10: fc1 + bias + GELU + dropout + fc2's matmul on the tcgen05 GEMMs with fused epilogues
-            v0 = ops.feed_forward_core(h, ff.fc1.weight, ff.fc1.bias, ff.fc2.weight, ff.drop.p, self.training)
-        else:
-            u0 = nn.functional.linear(h, ff.fc1.weight)            # bias, GELU, dropout: K7
-            g = ops.bias_gelu_dropout(u0, ff.fc1.bias, ff.drop.p, self.training)
-            v0 = nn.functional.linear(g, ff.fc2.weight)
+        # K10: fc1 + bias + GELU + dropout + fc2's matmul on the tcgen05 GEMMs with fused epilogues
+        v0 = ops.feed_forward_core(h, ff.fc1.weight, ff.fc1.bias, ff.fc2.weight, ff.drop.p, self.training)
         # fc2's bias, dropout, residual (and the next norm1): K6
         return ops.bias_dropout_add_ln(x, v0, ff.fc2.bias, next_norm, ff.drop.p, self.training)
 
@@ -355,7 +371,7 @@ class Model(nn.Module):
 
     def forward_features(self, x):
         fused = x.is_cuda and _attn_dtype(x) == torch.bfloat16 and x.dtype == torch.float32
-        if fused and self.pe and not self.B.requires_grad:
+        if fused and self.pe and not self.B.requires_grad and not x.requires_grad:
             # K8: Fourier embedding + positional encoding + its dropout in one pass, fp32 (see below why)
             x = ops.fourier_embed(x, self.B, self.pos_encoder.pe, self.pos_encoder.dropout.p, self.training)
         else:

@@ -44,6 +44,44 @@ def _ptr(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+def _require_binary(t: Optional[torch.Tensor], what: str) -> None:
+    """The kernels hold the two multiplicative masks of MSA.forward (HWGATE.py:102-108) as ONE bit per
+    (query, key).  That is exact for 0/1 masks - what the reference ships - and wrong for weighted ones, which
+    the reference would multiply into the logits: refuse those instead of silently binarising them.  Runs once
+    per mask (the packed bits are cached by the callers)."""
+    if t is not None and not bool(((t == 0) | (t == 1)).all().item()):
+        raise NotImplementedError(
+            f"{what} has entries other than 0 and 1: the packed-bitmask kernels only represent 0/1 "
+            "multiplicative masks (the reference's skeleton adjacency and shifted-window mask)")
+
+
+_CAST_CACHE: dict = {}
+
+
+def cast_cached(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Detached contiguous copy of a parameter in `dtype`, reused until the parameter is modified in place
+    (`_version`) or re-allocated (`data_ptr`): inference re-casts nothing, training casts once per step
+    instead of once per forward and once per backward."""
+    src = t.detach()
+    if src.dtype == dtype and src.is_contiguous():
+        return src
+    if src.is_cuda and torch.cuda.is_current_stream_capturing():
+        return src.to(dtype).contiguous()      # inside a CUDA graph the cast is part of the graph (replays see updates)
+    key = (id(t), dtype)
+    tag = (src.data_ptr(), t._version, src.device, tuple(src.shape))
+    hit = _CAST_CACHE.get(key)
+    if hit is not None and hit[0] == tag and hit[2]() is t:
+        return hit[1]
+    out = src.to(dtype).contiguous()
+    import weakref
+    try:
+        ref = weakref.ref(t, lambda _r, k=key: _CAST_CACHE.pop(k, None))
+    except TypeError:
+        return out
+    _CAST_CACHE[key] = (tag, out, ref)
+    return out
+
+
 # --------------------------------------------------------------------------
 # K1: adjacency and packed masks
 # --------------------------------------------------------------------------
@@ -76,6 +114,7 @@ def mask_build(adj: torch.Tensor, frames: int, shift: int, window: int = WINDOW,
     lib = _lib.load()
     _need_cuda(adj)
     adj = adj.contiguous().float()
+    _require_binary(adj, "adj_mat")
     nW, N = adj.shape[0], adj.shape[1]
     bits = torch.empty((frames // temporal_patch * nW, N, N // 32), dtype=torch.int32, device=adj.device)
     with torch.cuda.device(adj.device):
@@ -92,6 +131,8 @@ def mask_pack(adj: Optional[torch.Tensor], mask: Optional[torch.Tensor], n_windo
     _need_cuda(adj, mask)
     adj_c = adj.contiguous().float() if adj is not None else None
     mask_c = mask.contiguous().float() if mask is not None else None
+    _require_binary(adj_c, "adj_mat")
+    _require_binary(mask_c, "attn_mask")
     bits = torch.empty((n_windows, N, N // 32), dtype=torch.int32, device=device)
     with torch.cuda.device(device):
         check(lib.hwgat_mask_pack(_ptr(adj_c), 0 if adj_c is None else adj_c.shape[0], _ptr(mask_c), n_windows, N,
@@ -118,8 +159,8 @@ class _WindowGraphAttention(torch.autograd.Function):
         if frames * kps == 0 or n_tok % (frames * kps) != 0:
             raise ValueError(f"token count {n_tok} is not a multiple of frames*keypoints = {frames * kps}")
         B = n_tok // (frames * kps)
-        w_c = w_qkv.detach().to(xn_c.dtype).contiguous()
-        b_c = b_qkv.detach().float().contiguous()
+        w_c = cast_cached(w_qkv, xn_c.dtype)
+        b_c = cast_cached(b_qkv, torch.float32)
         out = torch.empty_like(xn_c)
         ws_bytes = lib.hwgat_attn_workspace_bytes(B, frames, kps, d, heads, code, 0)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xn_c.device) if ws_bytes else None
@@ -391,9 +432,9 @@ class _FeedForwardCore(torch.autograd.Function):
         hidden = w1.shape[0]
         if tuple(w1.shape) != (hidden, d) or tuple(w2.shape) != (d, hidden):
             raise ValueError(f"fc1 / fc2 weights {tuple(w1.shape)} / {tuple(w2.shape)} do not match (n, {d}) input")
-        w1_c = w1.detach().to(torch.bfloat16).contiguous()
-        w2_c = w2.detach().to(torch.bfloat16).contiguous()
-        b1_c = b1.detach().float().contiguous() if b1 is not None else None
+        w1_c = cast_cached(w1, torch.bfloat16)
+        w2_c = cast_cached(w2, torch.bfloat16)
+        b1_c = cast_cached(b1, torch.float32) if b1 is not None else None
         need_grad = any(ctx.needs_input_grad[:4])
         seed, off = _philox_stream(h_c.device) if p > 0 else (0, 0)
         act = torch.empty((n, hidden), dtype=torch.bfloat16, device=h_c.device)
@@ -453,7 +494,7 @@ class _OutputProjection(torch.autograd.Function):
         d_out = w.shape[0]
         if tuple(w.shape) != (d_out, d_in):
             raise ValueError(f"proj weight {tuple(w.shape)} does not match (n, {d_in}) input")
-        w_c = w.detach().to(torch.bfloat16).contiguous()
+        w_c = cast_cached(w, torch.bfloat16)
         y = torch.empty(x_c.shape[:-1] + (d_out,), dtype=torch.bfloat16, device=x_c.device)
         with torch.cuda.device(x_c.device):
             check(lib.hwgat_proj_fwd(x_c.data_ptr(), w_c.data_ptr(), y.data_ptr(), n, d_in, d_out, _stream()),

@@ -87,10 +87,62 @@ def build_ref_model(hw, mp, cfg, sd, drop=0.0):
     return model, params
 
 
+AUTOCAST_THR = [0.03, 0.05, 0.031, 0.2, 0.033, 0.04, 0.0312, 0.1]
+AUTOCAST_STRIDE = 31
+
+
+def autocast_train_golden(hw, mp, sce):
+    """Section 5: the UNMODIFIED reference (fp32 parameters) under torch.autocast("cpu", bfloat16) - the only
+    bf16 mode the reference can run in - in TRAIN mode with injected thresholds: logits, loss,
+    and for every parameter the gradient norm and a strided sample of the gradient.  This pins what "bf16 training"
+    means to the reference itself rather than to a rounding model of ours."""
+    from oracle import hwgate_oracle as O
+    cfg = O.HWGATEConfig(temporal_dim=64, num_classes=262)
+    sd = O.make_state_dict(cfg, seed=1001, weight_std=0.05)
+    params = mp.HWGATEParams({"num_class": 262, "src_len": 64}, 2, "cpu")
+    params.drop_rate = 0.0
+    model = hw.Model(*params.get_model_params())
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    x = O.synthetic_keypoints(2, 64, 2, seed=1001)
+    y = O.synthetic_labels(2, 262, seed=1001)
+    out = {}
+    with patched_rand(AUTOCAST_THR) as pr, torch.autocast("cpu", dtype=torch.bfloat16):
+        logits = model(x)
+        loss = sce.SmoothedCrossEntropyLoss()(logits.float(), y)
+    assert pr.calls == 8
+    loss.backward()
+    out["logits"] = logits.detach().float().numpy()
+    out["loss"] = np.array(loss.item())
+    out["thr"] = np.array(AUTOCAST_THR)
+    names, norms, samples, offsets = [], [], [], [0]
+    for n, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        g = p.grad.detach().float().reshape(-1).numpy()
+        names.append(n)
+        norms.append(float(np.linalg.norm(g.astype(np.float64))))
+        samples.append(g[::AUTOCAST_STRIDE].astype(np.float32))
+        offsets.append(offsets[-1] + samples[-1].size)
+    out["gnames"] = np.array(names)
+    out["gnorms"] = np.array(norms)
+    out["gsamples"] = np.concatenate(samples)
+    out["goffsets"] = np.array(offsets)
+    out["stride"] = np.array(AUTOCAST_STRIDE)
+    # the same model in eval mode under autocast (no threshold): the reference's own bf16 inference
+    model.eval()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        out["eval_logits"] = model(x).float().numpy()
+    np.savez_compressed(os.path.join(HERE, "autocast_train.npz"), **out)
+
+
 def main():
     from oracle import hwgate_oracle as O
     hw, mp, sce = import_reference()
     torch.manual_seed(0)
+    if "--only-autocast" in sys.argv:
+        autocast_train_golden(hw, mp, sce)
+        return
     out = {}
 
     # ---- 1. masks: reference float masks of every default block config, packed
@@ -200,6 +252,8 @@ def main():
     full["state_dict_names"] = np.array(list(m32.state_dict().keys()))
     full["state_dict_shapes"] = np.array([str(tuple(v.shape)) for v in m32.state_dict().values()])
     np.savez_compressed(os.path.join(HERE, "full_model.npz"), **full)
+
+    autocast_train_golden(hw, mp, sce)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

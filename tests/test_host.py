@@ -140,11 +140,17 @@ def _dp_worker(rank, world, port, out):
     g = torch.Generator().manual_seed(7)
     x, y = torch.randn(12, 16, generator=g), torch.randint(0, 5, (12,), generator=g)
     sl = shard_batch(12, rank, world)
-    for step in range(2):                    # two steps: state must reset between them
-        model.zero_grad(set_to_none=(step == 1))
+    views = [p.grad.data_ptr() for p in model.parameters() if p.requires_grad]
+    for step in range(3):                    # three steps: state must reset between them
+        if step == 2:
+            sync.zero_grad()                 # the intended call: one memset per bucket, .grad stays a bucket view
+        else:
+            model.zero_grad(set_to_none=(step == 1))   # also tolerated: in-place zero, and .grad replaced (copied in)
         loss = torch.nn.functional.cross_entropy(model(x[sl]), y[sl])
         loss.backward()
         sync.finish()
+        # every .grad is (again) the view into its flat bucket: no unpack copy happened
+        assert views == [p.grad.data_ptr() for p in model.parameters() if p.requires_grad]
     if rank == 0:
         torch.save({"grads": [p.grad for p in model.parameters() if p.requires_grad],
                     "state": model.state_dict(), "x": x, "y": y}, out)
