@@ -138,7 +138,8 @@ class KernelTimer:
         import torch
         self.torch, self.lib, self.on, self.rec = torch, lib, False, []
         self.orig = {}
-        for name in ("hwgat_attn_fwd", "hwgat_attn_bwd", "hwgat_merge_fwd", "hwgat_merge_bwd", "hwgat_ln_fwd",
+        for name in ("hwgat_attn_fwd", "hwgat_attn_bwd", "hwgat_attn2_fwd", "hwgat_attn2_bwd", "hwgat_bda_merge_fwd",
+                     "hwgat_ln_bwd_unmerge", "hwgat_merge_fwd", "hwgat_merge_bwd", "hwgat_ln_fwd",
                      "hwgat_ln_bwd", "hwgat_bda_ln_fwd", "hwgat_bda_ln_bwd", "hwgat_bias_gelu_dropout_fwd",
                      "hwgat_bias_gelu_dropout_bwd", "hwgat_ffn_fwd", "hwgat_ffn_bwd", "hwgat_proj_fwd",
                      "hwgat_proj_bwd"):
@@ -149,6 +150,9 @@ class KernelTimer:
     # (columns of the tensor, extra info) from the C-ABI argument list of each entry point
     DIM_ARG = {
         "hwgat_attn_fwd": lambda a: (int(a[11]), 0), "hwgat_attn_bwd": lambda a: (int(a[14]), 0),
+        "hwgat_attn2_fwd": lambda a: (int(a[12]), 0), "hwgat_attn2_bwd": lambda a: (int(a[15]), 0),
+        "hwgat_bda_merge_fwd": lambda a: (int(a[5]), int(a[4]), False),
+        "hwgat_ln_bwd_unmerge": lambda a: (int(a[10]), int(a[9])),
         "hwgat_merge_fwd": lambda a: (int(a[5]), 0), "hwgat_merge_bwd": lambda a: (int(a[5]), 0),
         "hwgat_ln_fwd": lambda a: (int(a[7]), int(a[6])), "hwgat_ln_bwd": lambda a: (int(a[10]), int(a[9])),
         "hwgat_bda_ln_fwd": lambda a: (int(a[10]), int(a[9]), bool(a[3])),
@@ -161,7 +165,7 @@ class KernelTimer:
         "hwgat_proj_bwd": lambda a: (int(a[8]), int(a[7]), int(a[9])),
     }
     # algorithmic HBM bytes per element of the bandwidth-bound kernels
-    BYTES_PER_ELEM = {"hwgat_ln_fwd": 6, "hwgat_ln_bwd": 14, "hwgat_bias_gelu_dropout_fwd": 4,
+    BYTES_PER_ELEM = {"hwgat_ln_fwd": 6, "hwgat_ln_bwd": 14, "hwgat_ln_bwd_unmerge": 14, "hwgat_bias_gelu_dropout_fwd": 4,
                       "hwgat_bias_gelu_dropout_bwd": 6}
 
     def _wrap(self, name, fn):
@@ -216,9 +220,9 @@ class KernelTimer:
                             "avg_ms": avg, "alg_flops": fl, "achieved": fl / (avg * 1e-3) / 1e12, "unit": "TFLOP/s",
                             "total_ms": ms, "attention": False})
                 continue
-            if "merge" in name:
+            if name in ("hwgat_merge_fwd", "hwgat_merge_bwd"):
                 label, by = "K4 " + f"{name} d={d}", merge_bytes(B, {128: 0, 256: 1}[d], 4)  # fp32 residual stream
-            elif "bda_ln" in name:
+            elif "bda_" in name:
                 n_rows, with_ln = key[1], key[2]
                 per = (12 if with_ln else 10) if name.endswith("fwd") else (16 if with_ln else 6)
                 label, by = f"K6 {name} d={d} ln={int(with_ln)}", float(per) * n_rows * d

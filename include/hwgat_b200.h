@@ -121,6 +121,22 @@ int hwgat_merge_fwd(const void* x, void* out, int B, int F, int K, int d, int TP
 int hwgat_merge_bwd(const void* d_out, void* d_x, int B, int F, int K, int d, int TP,
                     int dtype, hwgat_stream_t stream);
 
+/* ---- K2b / K3b: the same attention for ANY window of W in {16, 32, 64} keypoints x TP = 2 frames (N = 32, 64, 128
+ * tokens; the reference takes window_size at model_params.py:254 and runs W = 32 / 64 unchanged, HWGATE.py:30-36,
+ * 290-291), bf16 only.  The QKV projection is one tcgen05 GEMM with the bias in its epilogue; the attention core
+ * runs S = QK^T, O = PV (and dP, dV, dQ, dK in the backward) as block-diagonal M = 128 tcgen05 tiles with one thread
+ * per query row for the masked softmax.  `qkv` (n x 3d bf16, n = B*F*K) is written by the forward and may be handed
+ * back to the backward (NULL: the backward re-projects it into its workspace).  bits: hwgat_mask_build /
+ * hwgat_mask_pack for this W (N/32 words per row).                                                              */
+size_t hwgat_attn2_workspace_bytes(int B, int F, int K, int d, int heads, int backward, int have_qkv);
+int hwgat_attn2_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, float threshold,
+                    void* out, void* qkv, void* workspace, size_t workspace_bytes, int B, int F, int K, int d,
+                    int heads, int W, int TP, int shift, int layout, hwgat_stream_t stream);
+int hwgat_attn2_bwd(const void* d_out, const void* xn, const void* w_qkv, const float* b_qkv, const void* qkv,
+                    const uint32_t* bits, float threshold, void* d_xn, float* d_w, float* d_b, void* workspace,
+                    size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int TP, int shift,
+                    int layout, hwgat_stream_t stream);
+
 /* ---- rest of the block, bf16 / autocast path --------------------------
  * Bandwidth-bound fusions of the PyTorch elementwise chains of PartAttentionBlock.forward
  * (HWGATE.py:189-221) and their autograd.  Dropout masks are regenerated from a Philox4x32-7
@@ -149,6 +165,32 @@ int hwgat_bda_ln_bwd(const float* g_x1, const void* dy, const float* x1, const f
                      const float* gamma, float* d_res, void* d_a0, float* dbias, float* dgamma, float* dbeta,
                      long long n, int d, float p, unsigned long long seed, unsigned long long offset,
                      hwgat_stream_t stream);
+/* K6 with TemporalMerging.forward (HWGATE.py:55-63) folded in: the last K6 of a level (no LayerNorm follows inside the
+ * level) stores x1 = res + dropout_p(a0 + bias) directly in the merged layout (B, F/2, K, 2d); res and a0 are
+ * (B, F, K, d) = n rows of d in {128, 256}.  K4 is then not launched.                                              */
+int hwgat_bda_merge_fwd(const float* res, const void* a0, const float* bias, float* x_merged, long long n, int d, int F,
+                        int K, float p, unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
+/* K5' with the adjoint of TemporalMerging folded in: the LayerNorm-backward of the first norm1 of a level, run on the
+ * merged rows (n_merged rows of d_merged in {256, 512} columns; x, dy, dres in the merged layout (B, F_merged, K,
+ * d_merged)), stores dx UN-merged as (B, 2 F_merged, K, d_merged/2).  K4's adjoint is then not launched.            */
+int hwgat_ln_bwd_unmerge(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                         const float* gamma, float* dx, float* dgamma, float* dbeta, long long n_merged, int d_merged,
+                         int F_merged, int K, hwgat_stream_t stream);
+/* K13: y(fp32) = x(fp32) . w^T + bias: the classifier head self.head (HWGATE.py:359) on the fp32 FFMA GEMM
+ * (0.1 - 1 GFLOP; its output feeds a log-softmax, so it stays fp32 also under autocast).  bias may be NULL.       */
+int hwgat_linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, int n, int d_in, int d_out,
+                         hwgat_stream_t stream);
+/* K13': dx = dy . w, dw = dy^T . x, db = column sums of dy; each output may be NULL (skipped).                    */
+int hwgat_linear_f32_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int n,
+                         int d_in, int d_out, hwgat_stream_t stream);
+/* K14: label-smoothed cross entropy, SmoothedCrossEntropyLoss.forward (losses/SmoothCrossEntropy.py:35-39):
+ * loss = mean_b [(1-smooth) * (-logp[b, target_b]) + smooth * (-mean_c logp[b, c])]; logits (rows, classes) fp32,
+ * target int64; lse and row_loss (rows) are saved / scratch; the mean is a fixed-order sum (deterministic).        */
+int hwgat_smooth_ce_fwd(const float* logits, const long long* target, float* lse, float* row_loss, float* loss,
+                        int rows, int classes, float smooth, hwgat_stream_t stream);
+/* K14': dlogits = (*g / rows) * (softmax(logits) - (1-smooth) * onehot(target) - smooth / classes); g: device scalar. */
+int hwgat_smooth_ce_bwd(const float* logits, const long long* target, const float* lse, const float* g,
+                        float* dlogits, int rows, int classes, float smooth, hwgat_stream_t stream);
 /* K7: g(bf16) = dropout_p(gelu(u0(bf16) + bias)), exact erf GELU, u0: (n, cols) a Linear output without bias.
  * Replaces fc1 bias + ff.act + ff.drop (HWGATE.py:131-133).  cols in {256, 512, 1024}.                          */
 int hwgat_bias_gelu_dropout_fwd(const void* u0, const float* bias, void* g, long long n, int cols, float p,

@@ -19,6 +19,8 @@ static int check_geometry(int B, int F, int K, int d, int heads, int W, int TP, 
   if (shift < 0 || shift >= TP) return HWGAT_ERR_SHAPE;
   if (layout == HWGAT_LAYOUT_WINDOWS && shift != 0) return HWGAT_ERR_SHAPE;
   if ((long long)B * F * K > 0x7fffffffLL / 4) return HWGAT_ERR_UNSUPPORTED;  // row index kept in 31 bits
+  // the fp32 parity kernels put 64-token tiles on grid.y (limit 65535): larger calls are refused, not mis-launched
+  if (dtype == HWGAT_F32 && ((long long)B * F * K + 63) / 64 > 65535) return HWGAT_ERR_UNSUPPORTED;
   return HWGAT_OK;
 }
 }  // namespace hwgat
@@ -27,7 +29,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 10; }
+int hwgat_version(void) { return 11; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -119,6 +121,65 @@ int hwgat_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const f
   return dtype == HWGAT_F32 ? attn_bwd_f32(a, (cudaStream_t)stream) : attn_bwd_bf16(a, (cudaStream_t)stream);
 }
 
+static int check_geometry2(int B, int F, int K, int d, int heads, int W, int TP, int shift, int layout) {
+  if (B < 0 || F <= 0 || K <= 0 || d <= 0 || heads <= 0) return HWGAT_ERR_SHAPE;
+  if (layout != HWGAT_LAYOUT_BFKD && layout != HWGAT_LAYOUT_WINDOWS) return HWGAT_ERR_UNSUPPORTED;
+  if ((W != 16 && W != 32 && W != 64) || TP != kTP) return HWGAT_ERR_UNSUPPORTED;
+  if (d != heads * kHd || d > 512 || d % 128 != 0) return HWGAT_ERR_UNSUPPORTED;
+  if (F % TP != 0 || K % 64 != 0) return HWGAT_ERR_UNSUPPORTED;
+  if (shift < 0 || shift >= TP) return HWGAT_ERR_SHAPE;
+  if (layout == HWGAT_LAYOUT_WINDOWS && shift != 0) return HWGAT_ERR_SHAPE;
+  if ((long long)B * F * K > 0x7fffffffLL / 4) return HWGAT_ERR_UNSUPPORTED;
+  return HWGAT_OK;
+}
+
+size_t hwgat_attn2_workspace_bytes(int B, int F, int K, int d, int heads, int backward, int have_qkv) {
+  (void)heads;
+  return attn2_workspace_bytes((long long)B * F * K, d, backward, have_qkv);
+}
+
+int hwgat_attn2_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, float threshold,
+                    void* out, void* qkv, void* workspace, size_t workspace_bytes, int B, int F, int K, int d,
+                    int heads, int W, int TP, int shift, int layout, hwgat_stream_t stream) {
+  int st = check_geometry2(B, F, K, d, heads, W, TP, shift, layout);
+  if (st) return st;
+  if (B == 0) return HWGAT_OK;
+  if (!xn || !w_qkv || !b_qkv || !bits || !out || !qkv) return HWGAT_ERR_NULL;
+  if (misaligned(xn) || misaligned(w_qkv) || misaligned(out) || misaligned(b_qkv) || misaligned(workspace) ||
+      misaligned(qkv))
+    return HWGAT_ERR_ALIGN;
+  if (!workspace || workspace_bytes < hwgat_attn2_workspace_bytes(B, F, K, d, heads, 0, 1)) return HWGAT_ERR_WORKSPACE;
+  AttnArgs a{};
+  a.xn = xn; a.w_qkv = w_qkv; a.b_qkv = b_qkv; a.bits = bits; a.threshold = threshold; a.out = out;
+  a.workspace = workspace; a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
+  return attn2_fwd(a, W, (__nv_bfloat16*)qkv, (cudaStream_t)stream);
+}
+
+int hwgat_attn2_bwd(const void* d_out, const void* xn, const void* w_qkv, const float* b_qkv, const void* qkv,
+                    const uint32_t* bits, float threshold, void* d_xn, float* d_w, float* d_b, void* workspace,
+                    size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int TP, int shift,
+                    int layout, hwgat_stream_t stream) {
+  int st = check_geometry2(B, F, K, d, heads, W, TP, shift, layout);
+  if (st) return st;
+  if (!d_w || !d_b) return HWGAT_ERR_NULL;
+  if (B == 0) {
+    cudaMemsetAsync(d_w, 0, sizeof(float) * 3 * d * d, (cudaStream_t)stream);
+    cudaMemsetAsync(d_b, 0, sizeof(float) * 3 * d, (cudaStream_t)stream);
+    return (int)cudaGetLastError();
+  }
+  if (!d_out || !xn || !w_qkv || !b_qkv || !bits || !d_xn) return HWGAT_ERR_NULL;
+  if (misaligned(d_out) || misaligned(xn) || misaligned(w_qkv) || misaligned(d_xn) || misaligned(d_w) ||
+      misaligned(b_qkv) || misaligned(workspace) || misaligned(qkv))
+    return HWGAT_ERR_ALIGN;
+  if (!workspace || workspace_bytes < hwgat_attn2_workspace_bytes(B, F, K, d, heads, 1, qkv != nullptr))
+    return HWGAT_ERR_WORKSPACE;
+  AttnArgs a{};
+  a.xn = xn; a.w_qkv = w_qkv; a.b_qkv = b_qkv; a.bits = bits; a.threshold = threshold; a.d_out = d_out;
+  a.d_xn = d_xn; a.d_w = d_w; a.d_b = d_b; a.workspace = workspace;
+  a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
+  return attn2_bwd(a, W, (const __nv_bfloat16*)qkv, (cudaStream_t)stream);
+}
+
 int hwgat_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                  long long n, int d, float eps, hwgat_stream_t stream) {
   if (n < 0) return HWGAT_ERR_SHAPE;
@@ -142,6 +203,69 @@ int hwgat_ln_bwd(const void* dy, const float* dres, const float* x, const float*
 }
 
 static bool bad_p(float p) { return !(p >= 0.f) || p >= 1.f; }
+
+int hwgat_ln_bwd_unmerge(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                         const float* gamma, float* dx, float* dgamma, float* dbeta, long long n_merged, int d_merged,
+                         int F_merged, int K, hwgat_stream_t stream) {
+  if (n_merged < 0 || F_merged <= 0 || K <= 0) return HWGAT_ERR_SHAPE;
+  if (d_merged != 256 && d_merged != 512) return HWGAT_ERR_UNSUPPORTED;
+  if (n_merged % ((long long)F_merged * K) != 0) return HWGAT_ERR_SHAPE;
+  if (!dgamma || !dbeta) return HWGAT_ERR_NULL;
+  if (n_merged > 0 && (!dy || !x || !mean || !rstd || !gamma || !dx)) return HWGAT_ERR_NULL;
+  if (misaligned(dy) || misaligned(dres) || misaligned(x) || misaligned(gamma) || misaligned(dx)) return HWGAT_ERR_ALIGN;
+  return launch_ln_bwd((const __nv_bfloat16*)dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n_merged, d_merged,
+                       (cudaStream_t)stream, F_merged, K);
+}
+
+int hwgat_bda_merge_fwd(const float* res, const void* a0, const float* bias, float* x_merged, long long n, int d, int F,
+                        int K, float p, unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  if (n < 0 || bad_p(p) || F <= 0 || K <= 0) return HWGAT_ERR_SHAPE;
+  if (d != 128 && d != 256) return HWGAT_ERR_UNSUPPORTED;
+  if (F % 2 != 0) return HWGAT_ERR_UNSUPPORTED;
+  if (n % ((long long)F * K) != 0) return HWGAT_ERR_SHAPE;
+  if (n == 0) return HWGAT_OK;
+  if (!res || !a0 || !x_merged) return HWGAT_ERR_NULL;
+  if (misaligned(res) || misaligned(a0) || misaligned(bias) || misaligned(x_merged)) return HWGAT_ERR_ALIGN;
+  return launch_bda_ln_fwd(res, (const __nv_bfloat16*)a0, bias, nullptr, nullptr, x_merged, nullptr, nullptr, nullptr, n,
+                           d, 0.f, p, seed, offset, (cudaStream_t)stream, F, K);
+}
+
+int hwgat_linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, int n, int d_in, int d_out,
+                         hwgat_stream_t stream) {
+  if (n < 0 || d_in <= 0 || d_out <= 0) return HWGAT_ERR_SHAPE;
+  if (n == 0) return HWGAT_OK;
+  if (!x || !w || !y) return HWGAT_ERR_NULL;
+  if ((n + 63) / 64 > 65535) return HWGAT_ERR_UNSUPPORTED;
+  return linear_f32_fwd(x, w, bias, y, n, d_in, d_out, (cudaStream_t)stream);
+}
+
+int hwgat_linear_f32_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int n,
+                         int d_in, int d_out, hwgat_stream_t stream) {
+  if (n < 0 || d_in <= 0 || d_out <= 0) return HWGAT_ERR_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) {
+    if (dw) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d_in * d_out, s);
+    if (db) cudaMemsetAsync(db, 0, sizeof(float) * d_out, s);
+    return (int)cudaGetLastError();
+  }
+  if (!dy || (dx && !w) || (dw && !x)) return HWGAT_ERR_NULL;
+  if ((n + 63) / 64 > 65535) return HWGAT_ERR_UNSUPPORTED;
+  return linear_f32_bwd(dy, x, w, dx, dw, db, n, d_in, d_out, s);
+}
+
+int hwgat_smooth_ce_fwd(const float* logits, const long long* target, float* lse, float* row_loss, float* loss,
+                        int rows, int classes, float smooth, hwgat_stream_t stream) {
+  if (rows <= 0 || classes <= 0 || !(smooth >= 0.f) || smooth > 1.f) return HWGAT_ERR_SHAPE;
+  if (!logits || !target || !lse || !row_loss || !loss) return HWGAT_ERR_NULL;
+  return smooth_ce_fwd(logits, target, lse, row_loss, loss, rows, classes, smooth, (cudaStream_t)stream);
+}
+
+int hwgat_smooth_ce_bwd(const float* logits, const long long* target, const float* lse, const float* g,
+                        float* dlogits, int rows, int classes, float smooth, hwgat_stream_t stream) {
+  if (rows <= 0 || classes <= 0 || !(smooth >= 0.f) || smooth > 1.f) return HWGAT_ERR_SHAPE;
+  if (!logits || !target || !lse || !g || !dlogits) return HWGAT_ERR_NULL;
+  return smooth_ce_bwd(logits, target, lse, g, dlogits, rows, classes, smooth, (cudaStream_t)stream);
+}
 
 int hwgat_bda_ln_fwd(const float* res, const void* a0, const float* bias, const float* gamma, const float* beta,
                      float* x1, void* y, float* mean, float* rstd, long long n, int d, float eps, float p,

@@ -1,0 +1,703 @@
+// K2b / K3b: windowed graph attention with EVERY product on tcgen05, for any window of N = 32, 64 or 128 tokens
+// (window_size W = 16, 32, 64 keypoints x TP = 2 frames; HWGATE.py:30-36, 84-114, model_params.py:254).
+//
+// The QKV projection runs as one tcgen05 GEMM with the bias in its epilogue (ffn_tc.cu), q pre-scaled by 64^-1/2; this
+// file is the attention core on the projected rows.  One work item = (tile of 128 tokens, head).  A tile is one
+// temporal group (frame pair) x 64 keypoints = 128/N whole windows, so the per-window products are block-diagonal
+// M = 128 UMMA tiles (at N = 128 a window IS the tile; at N = 32 three quarters of the S / P columns are off the
+// diagonal - 4x of 4-14 % of the FLOPs - and the softmax threads never touch them):
+//
+//   warp 0     TMA producer: Q, K, V (and dO in the backward) tiles [128 x 64] straight from the projected rows in
+//              global memory as 16-token boxes of a 4-D tensor map (roll + window partition = box coordinates),
+//              landing in the SWIZZLE_128B K-major layout the MMAs read; 2-3 stage ring.
+//   warp 1     tcgen05.mma issuer:  S = Q K^T  (M128 N128 K64),  O = P V  (M128 N64 K128, P from shared memory as
+//              bf16, V as the MN-major B operand);  backward:  dP = dO V^T,  dV = P^T dO,  dQ = dS K,  dK = dS^T Q
+//              with the transposed operands taken through MN-major descriptors of the same shared-memory tiles.
+//              S of item i+1 is issued before the second-stage MMAs of item i, so the tensor pipe works under the
+//              softmax of item i.
+//   warps 4-11 softmax warps, ONE THREAD PER QUERY ROW (tcgen05.ld 32x32b): the row's N live logits in registers,
+//              threshold drop, packed graph / shift mask, -10000 fill and softmax without any shuffle
+//              (HWGATE.py:94-111); P (and dS) written as bf16 into the K-major tile; outputs read back from TMEM and
+//              stored as full 32-byte sectors of the thread's own row.  Two warp sets alternate items.
+//   warps 2-3  idle: they donate registers (setmaxnreg) so a softmax thread can hold a 128-column row.
+//
+// TMEM: two 256-column buffers; forward S [0,128) + O [128,192); backward S [0,128) + dP [128,256), then
+// dQ [0,64) + dK [64,128) + dV [128,192) over the consumed S / dP.
+#include <cstdlib>
+
+#include "tc.cuh"
+
+namespace hwgat {
+
+typedef __nv_bfloat16 bf16;
+
+namespace tc2 {
+
+constexpr int kThreads = 384;
+constexpr int kFirstSoftWarp = 4;
+constexpr int kRegsDonor = 40, kRegsSoft = 232;
+constexpr int kTile = 128 * 128;            // bytes of a [128 x 64] bf16 tile
+constexpr int kPBytes = 2 * kTile;          // [128 x 128] bf16 as two 64-column chunks
+constexpr int kMaxDynSmem2 = 232448;
+constexpr float kLog2e = 1.4426950408889634f;
+
+HW_DEV void reg_dealloc_donor() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kRegsDonor)); }
+HW_DEV void reg_alloc_soft() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kRegsSoft)); }
+
+struct Geo2 {
+  int F, K, shift, layout, f, kgroups, W, N, wpt, nWt;   // wpt = windows per tile (64 / W), nWt = windows per frame pair
+  HW_DEV void decode(int tile, int& b, int& fi, int& kg) const {
+    const int tps = f * kgroups;
+    b = tile / tps;
+    const int r = tile - b * tps;
+    fi = r / kgroups;
+    kg = r - fi * kgroups;
+  }
+  // global token row of tile row `row` (HWGATE.py:197-201 without the copies)
+  HW_DEV long long token_row(int tile, int row) const {
+    if (layout == HWGAT_LAYOUT_WINDOWS) return (long long)tile * 128 + row;
+    int b, fi, kg;
+    decode(tile, b, fi, kg);
+    const int w = row / N, rr = row - w * N, tp = rr / W, k = rr - tp * W;
+    int fr = 2 * fi + tp + shift;
+    fr = fr >= F ? fr - F : fr;
+    return (long long)(b * F + fr) * K + kg * 64 + w * W + k;
+  }
+  // first mask word of tile row `row`: bits is (f * nWt windows, N rows, N/32 words)
+  HW_DEV long long mask_word(int tile, int row) const {
+    int b, fi, kg;
+    decode(tile, b, fi, kg);
+    const int w = row / N, rr = row - w * N;
+    return ((long long)(fi * nWt + kg * wpt + w) * N + rr) * (N / 32);
+  }
+};
+
+// one [128 x 64] tile (columns col .. col+63 of the tile's 128 token rows) -> dst (16 KB, SWIZZLE_128B K-major)
+HW_DEV void load_tile(unsigned char* dst, const CUtensorMap* tm, uint64_t* bar, const Geo2& g, int tile, int col) {
+  if (g.layout == HWGAT_LAYOUT_WINDOWS) {
+    tma_load_2d(dst, tm, bar, col, tile * 128);
+    return;
+  }
+  int b, fi, kg;
+  g.decode(tile, b, fi, kg);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int r0 = 16 * j, w = r0 / g.N, rr = r0 - w * g.N, tp = rr / g.W, k0 = rr - tp * g.W;
+    int fr = 2 * fi + tp + g.shift;
+    fr = fr >= g.F ? fr - g.F : fr;
+    tma_load_4d(dst + j * 2048, tm, bar, col, kg * 64 + w * g.W + k0, fr, b);
+  }
+}
+
+HW_DEV void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// row `row` of a [128 x 128] bf16 K-major SWIZZLE_128B tile pair, columns col0 .. col0+N-1 (col0 % 8 == 0) <- v[0..N)
+template <int N>
+HW_DEV void store_row_bf16(uint32_t tile_saddr, int row, int col0, const float (&v)[N]) {
+#pragma unroll
+  for (int u = 0; u < N / 8; ++u) {
+    const int col = col0 + 8 * u;
+    const uint32_t a = tile_saddr + (uint32_t)((col >> 6) * kTile + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4));
+    sts128(a, pack_bf16(v[8 * u], v[8 * u + 1]), pack_bf16(v[8 * u + 2], v[8 * u + 3]),
+           pack_bf16(v[8 * u + 4], v[8 * u + 5]), pack_bf16(v[8 * u + 6], v[8 * u + 7]));
+  }
+}
+
+// N consecutive TMEM columns of this thread's lane -> v (as floats)
+template <int N>
+HW_DEV void tmem_row(uint32_t taddr, float (&v)[N]) {
+#pragma unroll
+  for (int c = 0; c < N / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + 32 * c, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[32 * c + i] = __uint_as_float(r[i]);
+  }
+}
+
+// exact two-pass softmax of one row with a live set (bit i of lv): v <- softmax(live ? v : -10000); dead = no live logit
+template <int N>
+HW_DEV void softmax_exact_row(float (&v)[N], const uint32_t (&lv)[N / 32], bool& dead) {
+  float m1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    v[i] = ((lv[i >> 5] >> (i & 31)) & 1u) ? v[i] : kNegFill;
+    m1 = fmaxf(m1, v[i]);
+  }
+  dead = m1 == kNegFill;
+  const float ml = m1 * kLog2e;
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) { v[i] = exp2f(fmaf(v[i], kLog2e, -ml)); sum += v[i]; }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] *= inv;
+}
+
+// Masked softmax of one query row held by one thread (HWGATE.py:94-111).  v: the row's N logits in, probabilities
+// out.  mw: packed graph / shift mask of the row.  Training (kTrain): the exponentials of the UNMASKED softmax over the
+// window's N keys decide the threshold drop and are reused for the masked softmax,
+//   P_i = live_i e_i / sum_j live_j e_j,  e_i = exp(s_i - max s),
+// which equals softmax(live ? s : -10000) whenever some live e_i is representable; otherwise (every logit dropped or
+// masked, or all live ones underflow) the logits are read again from TMEM (`taddr`) and the exact form runs.
+template <int N, bool kTrain>
+HW_DEV void masked_softmax_row(float (&v)[N], const uint32_t (&mw)[N / 32], float threshold, uint32_t taddr, bool& dead) {
+  uint32_t lv[N / 32];
+  if (kTrain) {
+    float m0 = v[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) m0 = fmaxf(m0, v[i]);
+    const float ml = m0 * kLog2e;
+    float sum0 = 0.f;
+#pragma unroll
+    for (int w = 0; w < N / 32; ++w) lv[w] = mw[w];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (v[i] == 0.f) lv[i >> 5] &= ~(1u << (i & 31));          // exact zeros are filled too (HWGATE.py:110)
+      v[i] = exp2f(fmaf(v[i], kLog2e, -ml));
+      sum0 += v[i];
+    }
+    const float t0 = threshold * sum0;                            // softmax_i > thr  <=>  e_i > thr * sum
+    float sl = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (v[i] > t0) lv[i >> 5] &= ~(1u << (i & 31));              // HWGATE.py:97-100
+      v[i] = ((lv[i >> 5] >> (i & 31)) & 1u) ? v[i] : 0.f;
+      sl += v[i];
+    }
+    if (sl > 1e-30f) {
+      const float inv = 1.f / sl;
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] *= inv;
+      dead = false;
+    } else {
+      tmem_row<N>(taddr, v);
+      softmax_exact_row<N>(v, lv, dead);
+    }
+  } else {
+#pragma unroll
+    for (int w = 0; w < N / 32; ++w) lv[w] = mw[w];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (v[i] == 0.f) lv[i >> 5] &= ~(1u << (i & 31));
+    softmax_exact_row<N>(v, lv, dead);
+  }
+}
+
+struct CoreArgs {
+  const uint32_t* bits;
+  bf16* out;            // forward: [n, d]
+  bf16* dqkv;           // backward: [n, 3d]
+  float threshold;
+  int d, heads, tiles, stages;
+  Geo2 geo;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------------
+struct FwdBars {
+  uint64_t in_full[3], in_empty[3];
+  uint64_t s_full[2], p_ready[2], o_full[2], t_empty[2];
+  uint32_t tmem_slot;
+};
+
+template <int N, bool kTrain>
+__global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                         const CoreArgs p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int S = p.stages;
+  unsigned char* sIn = smem;                          // S stages of [Q | K | V]
+  unsigned char* sP = smem + S * 3 * kTile;           // two P tiles
+  FwdBars* bars = reinterpret_cast<FwdBars*>(sP + 2 * kPBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = p.tiles * p.heads;
+
+  // P tiles start as zeros: a softmax thread only ever writes its own window's columns, so the off-diagonal blocks
+  // stay zero for the whole kernel
+  for (int i = threadIdx.x; i < 2 * kPBytes / 16; i += blockDim.x) reinterpret_cast<int4*>(sP)[i] = make_int4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->s_full[i], 1); mbar_init(&bars->p_ready[i], 4);
+      mbar_init(&bars->o_full[i], 1); mbar_init(&bars->t_empty[i], 4);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmQKV);
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp < kFirstSoftWarp) {
+    reg_dealloc_donor();
+    if (warp == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int g = blockIdx.x; g < items; g += gridDim.x) {
+        const int tile = g / p.heads, h = g - tile * p.heads;
+        mbar_wait(&bars->in_empty[s], ph ^ 1);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&bars->in_full[s], 3 * kTile);
+          unsigned char* st = sIn + s * 3 * kTile;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) load_tile(st + q * kTile, &tmQKV, &bars->in_full[s], p.geo, tile, q * p.d + h * kHd);
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idS = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idO = umma_idesc_bf16(128, 64, false, true);
+      int s = 0, ps = 0, j = 0;     // ps: stage of the previous item
+      uint32_t ph = 0;
+      auto issue_pv = [&](int i, int stage) {
+        const int b = i & 1;
+        mbar_wait(&bars->p_ready[b], (i >> 1) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sp = smem_u32(sP + b * kPBytes), sv = smem_u32(sIn + stage * 3 * kTile + 2 * kTile);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_bf16(tmem + b * 256 + 128, umma_desc_k_sw128(sp + (ks >> 2) * kTile + (ks & 3) * 32),
+                      umma_desc_mn_sw128(sv + ks * 2048, 8192, 1024), idO, ks != 0);
+          umma_commit(&bars->o_full[b]);
+          umma_commit(&bars->in_empty[stage]);
+        }
+        __syncwarp();
+      };
+      for (int g = blockIdx.x; g < items; g += gridDim.x, ++j) {
+        const int b = j & 1;
+        mbar_wait(&bars->in_full[s], ph);
+        mbar_wait(&bars->t_empty[b], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sq = smem_u32(sIn + s * 3 * kTile), sk = sq + kTile;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem + b * 256, umma_desc_k_sw128(sq + ks * 32), umma_desc_k_sw128(sk + ks * 32), idS, ks != 0);
+          umma_commit(&bars->s_full[b]);
+        }
+        __syncwarp();
+        if (j > 0) issue_pv(j - 1, ps);
+        ps = s;
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      if (j > 0) issue_pv(j - 1, ps);
+    }
+  } else {
+    reg_alloc_soft();
+    const int q = warp & 3;                              // TMEM lane quarter
+    const int set = (warp - kFirstSoftWarp) >> 2;        // items with (j & 1) == set
+    const int row = 32 * q + lane;
+    const int win = row / N, col0 = win * N;             // the row's window = its live columns (warp-uniform)
+    const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16) + set * 256;
+    int j = 0;
+    for (int g = blockIdx.x; g < items; g += gridDim.x, ++j) {
+      if ((j & 1) != set) continue;
+      const int tile = g / p.heads, h = g - tile * p.heads;
+      const uint32_t par = (j >> 1) & 1;
+      uint32_t mw[N / 32];
+      {
+        const uint32_t* mp = p.bits + p.geo.mask_word(tile, row);
+#pragma unroll
+        for (int w = 0; w < N / 32; ++w) mw[w] = mp[w];
+      }
+      bf16* orow = p.out + (size_t)p.geo.token_row(tile, row) * p.d + h * kHd;
+      mbar_wait(&bars->s_full[set], par);
+      tc_fence_after();
+      {
+        float v[N];
+        tmem_row<N>(tq + col0, v);
+        bool dead;
+        masked_softmax_row<N, kTrain>(v, mw, p.threshold, tq + col0, dead);
+        store_row_bf16<N>(smem_u32(sP + set * kPBytes), row, col0, v);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_ready[set]);
+      mbar_wait(&bars->o_full[set], par);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tq + 128 + 32 * c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int gq = 0; gq < 2; ++gq) {
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            o[i] = pack_bf16(__uint_as_float(r[16 * gq + 2 * i]), __uint_as_float(r[16 * gq + 2 * i + 1]));
+          st_global32(orow + 32 * c + 16 * gq, o);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->t_empty[set]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// backward (S and P recomputed from the saved / re-projected q, k, v)
+// ---------------------------------------------------------------------------------------------------------------------
+struct BwdBars {
+  uint64_t in_full[2], in_empty[2];
+  uint64_t sdp_full[2], dqkv_full[2], t_empty[2];
+  uint64_t pds_ready, pds_empty;
+  uint32_t tmem_slot;
+};
+
+template <int N, bool kTrain>
+__global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                         const __grid_constant__ CUtensorMap tmDO,
+                                                                         const CoreArgs p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int S = 2;
+  unsigned char* sIn = smem;                          // 2 stages of [Q | K | V | dO]
+  unsigned char* sP = smem + S * 4 * kTile;
+  unsigned char* sDS = sP + kPBytes;
+  BwdBars* bars = reinterpret_cast<BwdBars*>(sDS + kPBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = p.tiles * p.heads;
+
+  for (int i = threadIdx.x; i < 2 * kPBytes / 16; i += blockDim.x) reinterpret_cast<int4*>(sP)[i] = make_int4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 1);
+      mbar_init(&bars->sdp_full[i], 1); mbar_init(&bars->dqkv_full[i], 1); mbar_init(&bars->t_empty[i], 4);
+    }
+    mbar_init(&bars->pds_ready, 4);
+    mbar_init(&bars->pds_empty, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp < kFirstSoftWarp) {
+    reg_dealloc_donor();
+    if (warp == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int g = blockIdx.x; g < items; g += gridDim.x) {
+        const int tile = g / p.heads, h = g - tile * p.heads;
+        mbar_wait(&bars->in_empty[s], ph ^ 1);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&bars->in_full[s], 4 * kTile);
+          unsigned char* st = sIn + s * 4 * kTile;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) load_tile(st + q * kTile, &tmQKV, &bars->in_full[s], p.geo, tile, q * p.d + h * kHd);
+          load_tile(st + 3 * kTile, &tmDO, &bars->in_full[s], p.geo, tile, h * kHd);
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idS = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idKM = umma_idesc_bf16(128, 64, false, true);   // A K-major,  B MN-major   (dQ = dS K)
+      constexpr uint32_t idMM = umma_idesc_bf16(128, 64, true, true);    // A MN-major, B MN-major   (dV, dK)
+      int s = 0, ps = 0, j = 0;
+      uint32_t ph = 0;
+      auto issue_grads = [&](int i, int stage) {
+        const int b = i & 1;
+        mbar_wait(&bars->pds_ready, i & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sq = smem_u32(sIn + stage * 4 * kTile), sk = sq + kTile, sdo = sq + 3 * kTile;
+          const uint32_t sp = smem_u32(sP), sds = smem_u32(sDS);
+          const uint32_t t = tmem + b * 256;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {   // dV[key] = sum_q P[q, key] dO[q]
+            umma_bf16(t + 128, umma_desc_mn_sw128(sp + ks * 2048, kTile, 1024), umma_desc_mn_sw128(sdo + ks * 2048, 8192, 1024),
+                      idMM, ks != 0);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {   // dQ[q] = sum_key dS[q, key] K[key]
+            umma_bf16(t, umma_desc_k_sw128(sds + (ks >> 2) * kTile + (ks & 3) * 32), umma_desc_mn_sw128(sk + ks * 2048, 8192, 1024),
+                      idKM, ks != 0);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {   // dK[key] = sum_q dS[q, key] Q[q]
+            umma_bf16(t + 64, umma_desc_mn_sw128(sds + ks * 2048, kTile, 1024), umma_desc_mn_sw128(sq + ks * 2048, 8192, 1024),
+                      idMM, ks != 0);
+          }
+          umma_commit(&bars->dqkv_full[b]);
+          umma_commit(&bars->in_empty[stage]);
+          umma_commit(&bars->pds_empty);
+        }
+        __syncwarp();
+      };
+      for (int g = blockIdx.x; g < items; g += gridDim.x, ++j) {
+        const int b = j & 1;
+        mbar_wait(&bars->in_full[s], ph);
+        mbar_wait(&bars->t_empty[b], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sq = smem_u32(sIn + s * 4 * kTile), sk = sq + kTile, sv = sq + 2 * kTile, sdo = sq + 3 * kTile;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem + b * 256, umma_desc_k_sw128(sq + ks * 32), umma_desc_k_sw128(sk + ks * 32), idS, ks != 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem + b * 256 + 128, umma_desc_k_sw128(sdo + ks * 32), umma_desc_k_sw128(sv + ks * 32), idS, ks != 0);
+          umma_commit(&bars->sdp_full[b]);
+        }
+        __syncwarp();
+        if (j > 0) issue_grads(j - 1, ps);
+        ps = s;
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      if (j > 0) issue_grads(j - 1, ps);
+    }
+  } else {
+    reg_alloc_soft();
+    const int q = warp & 3;
+    const int set = (warp - kFirstSoftWarp) >> 2;
+    const int row = 32 * q + lane;
+    const int win = row / N, col0 = win * N;
+    const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16) + set * 256;
+    const size_t d3 = (size_t)3 * p.d;
+    int j = 0;
+    for (int g = blockIdx.x; g < items; g += gridDim.x, ++j) {
+      if ((j & 1) != set) continue;
+      const int tile = g / p.heads, h = g - tile * p.heads;
+      const uint32_t par = (j >> 1) & 1;
+      uint32_t mw[N / 32];
+      {
+        const uint32_t* mp = p.bits + p.geo.mask_word(tile, row);
+#pragma unroll
+        for (int w = 0; w < N / 32; ++w) mw[w] = mp[w];
+      }
+      bf16* grow = p.dqkv + (size_t)p.geo.token_row(tile, row) * d3 + h * kHd;
+      mbar_wait(&bars->sdp_full[set], par);
+      tc_fence_after();
+      {
+        float v[N];
+        tmem_row<N>(tq + col0, v);
+        bool dead;
+        masked_softmax_row<N, kTrain>(v, mw, p.threshold, tq + col0, dead);
+        // delta = sum_j P_j dP_j: dP streamed from TMEM in 32-column chunks (twice: once for delta, once for dS), so
+        // a 128-column row of P stays in registers next to one chunk
+        float delta = 0.f;
+#pragma unroll
+        for (int c = 0; c < N / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tq + 128 + col0 + 32 * c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) delta = fmaf(v[32 * c + i], __uint_as_float(r[i]), delta);
+        }
+        // the previous item's second-stage MMAs must have finished reading sP / sDS
+        mbar_wait(&bars->pds_empty, (j & 1) ^ 1);
+        store_row_bf16<N>(smem_u32(sP), row, col0, v);
+#pragma unroll
+        for (int c = 0; c < N / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tq + 128 + col0 + 32 * c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)      // dS = P (dP - delta); P is exactly 0 off the live set; dead rows: 0
+            v[32 * c + i] = dead ? 0.f : v[32 * c + i] * (__uint_as_float(r[i]) - delta);
+        }
+        store_row_bf16<N>(smem_u32(sDS), row, col0, v);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->pds_ready);
+      mbar_wait(&bars->dqkv_full[set], par);
+      tc_fence_after();
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {      // dQ (x 64^-1/2: q carries the scale), dK, dV
+        const float mul = part == 0 ? 0.125f : 1.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tq + 64 * part + 32 * c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int gq = 0; gq < 2; ++gq) {
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              o[i] = pack_bf16(__uint_as_float(r[16 * gq + 2 * i]) * mul, __uint_as_float(r[16 * gq + 2 * i + 1]) * mul);
+            st_global32(grow + (size_t)part * p.d + 32 * c + 16 * gq, o);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->t_empty[set]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// q rows of the weight copy and the q part of the bias pre-multiplied by 64^-1/2 (exact in bf16 / fp32)
+__global__ void prep_qkv2_kernel(const bf16* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ wp,
+                                 float* __restrict__ bs, int d) {
+  const long long nw = (long long)3 * d * d;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw + 3 * d; i += stride) {
+    if (i < nw) {
+      const float v = __bfloat162float(w[i]);
+      wp[i] = __float2bfloat16(i < (long long)d * d ? v * 0.125f : v);
+    } else {
+      const int c = (int)(i - nw);
+      bs[c] = c < d ? b[c] * 0.125f : b[c];
+    }
+  }
+}
+
+static Geo2 make_geo2(const AttnArgs& a, int W) {
+  Geo2 g;
+  g.F = a.F; g.K = a.K; g.shift = a.shift; g.layout = a.layout; g.f = a.F / 2; g.kgroups = a.K / 64;
+  g.W = W; g.N = 2 * W; g.wpt = 64 / W; g.nWt = a.K / W;
+  return g;
+}
+
+}  // namespace tc2
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+int gemm_tc_nt_epi_bias(const bf16* A, const bf16* Bt, const float* bias, bf16* C, long long M, int N, int K,
+                        cudaStream_t s);
+
+// workspace layout (bf16 units unless noted):
+//   forward : wp [3d, d] | bias_s [3d] fp32                                      (qkv goes to the caller's qkv buffer)
+//   backward: dqkv [n, 3d] | Wqkv^T [d, 3d] | (qkv [n, 3d] | wp [3d, d] | bias_s [3d] fp32   when qkv is re-projected)
+size_t attn2_workspace_bytes(long long n, int d, int backward, int have_qkv) {
+  const size_t prep = (size_t)3 * d * d * sizeof(bf16) + (size_t)3 * d * sizeof(float) + 256;
+  if (!backward) return prep;
+  size_t b = ((size_t)n * 3 * d + (size_t)3 * d * d) * sizeof(bf16) + 256;
+  if (!have_qkv) b += (size_t)n * 3 * d * sizeof(bf16) + prep;
+  return b;
+}
+
+static int project_qkv(const AttnArgs& a, bf16* qkv, unsigned char* prep_ws, cudaStream_t s) {
+  const int d = a.d;
+  bf16* wp = (bf16*)prep_ws;
+  float* bs = (float*)(prep_ws + (((size_t)3 * d * d * sizeof(bf16) + 255) & ~(size_t)255));
+  tc2::prep_qkv2_kernel<<<148, 256, 0, s>>>((const bf16*)a.w_qkv, a.b_qkv, wp, bs, d);
+  count_launch();
+  int st = (int)cudaGetLastError();
+  if (st) return st;
+  return gemm_tc_nt_epi_bias((const bf16*)a.xn, wp, bs, qkv, a.tokens(), 3 * d, d, s);
+}
+
+template <int N>
+static int launch_core_fwd(const CUtensorMap& tm, const tc2::CoreArgs& p, bool train, int grid, int smem, cudaStream_t s) {
+  static PerDeviceOnce once;
+  once.run([] {
+    cudaFuncSetAttribute(tc2::attn_core_fwd_tc2_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kMaxDynSmem2);
+    cudaFuncSetAttribute(tc2::attn_core_fwd_tc2_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kMaxDynSmem2);
+  });
+  if (train) tc2::attn_core_fwd_tc2_kernel<N, true><<<grid, tc2::kThreads, smem, s>>>(tm, p);
+  else tc2::attn_core_fwd_tc2_kernel<N, false><<<grid, tc2::kThreads, smem, s>>>(tm, p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <int N>
+static int launch_core_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const tc2::CoreArgs& p, bool train, int grid,
+                           int smem, cudaStream_t s) {
+  static PerDeviceOnce once;
+  once.run([] {
+    cudaFuncSetAttribute(tc2::attn_core_bwd_tc2_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kMaxDynSmem2);
+    cudaFuncSetAttribute(tc2::attn_core_bwd_tc2_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kMaxDynSmem2);
+  });
+  if (train) tc2::attn_core_bwd_tc2_kernel<N, true><<<grid, tc2::kThreads, smem, s>>>(tm, tmdo, p);
+  else tc2::attn_core_bwd_tc2_kernel<N, false><<<grid, tc2::kThreads, smem, s>>>(tm, tmdo, p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+static int make_row_map(CUtensorMap* tm, const void* base, const AttnArgs& a, int cols) {
+  if (a.layout == HWGAT_LAYOUT_WINDOWS) return make_tmap_2d(tm, base, (uint64_t)a.tokens(), (uint64_t)cols, 128);
+  return make_tmap_4d(tm, base, (uint64_t)cols, (uint64_t)a.K, (uint64_t)a.F, (uint64_t)a.B, 16);
+}
+
+// forward: qkv (caller's buffer, kept for the backward) = xn . Wp^T + b ; out = attention core
+int attn2_fwd(const AttnArgs& a, int W, bf16* qkv, cudaStream_t s) {
+  int st;
+  if ((st = project_qkv(a, qkv, (unsigned char*)a.workspace, s))) return st;
+  CUtensorMap tm;
+  if ((st = make_row_map(&tm, qkv, a, 3 * a.d))) return st;
+  tc2::CoreArgs p{};
+  p.bits = a.bits; p.out = (bf16*)a.out; p.threshold = a.threshold; p.d = a.d; p.heads = a.heads; p.tiles = a.tiles();
+  p.stages = 3;
+  p.geo = tc2::make_geo2(a, W);
+  const int items = p.tiles * p.heads;
+  const int grid = items < 148 ? items : 148;
+  const int smem = p.stages * 3 * tc2::kTile + 2 * tc2::kPBytes + (int)sizeof(tc2::FwdBars) + 1024;
+  const bool train = a.threshold >= 0.f;
+  switch (2 * W) {
+    case 32: return launch_core_fwd<32>(tm, p, train, grid, smem, s);
+    case 64: return launch_core_fwd<64>(tm, p, train, grid, smem, s);
+    case 128: return launch_core_fwd<128>(tm, p, train, grid, smem, s);
+  }
+  return HWGAT_ERR_UNSUPPORTED;
+}
+
+int attn2_bwd(const AttnArgs& a, int W, const bf16* qkv_saved, cudaStream_t s) {
+  const long long n = a.tokens();
+  const int d = a.d, d3 = 3 * d;
+  bf16* dqkv = (bf16*)a.workspace;
+  bf16* wt = dqkv + (size_t)n * d3;
+  int st;
+  const bf16* qkv = qkv_saved;
+  if (!qkv) {
+    unsigned char* after = (unsigned char*)(wt + (size_t)d3 * d);
+    after = (unsigned char*)(((uintptr_t)after + 255) & ~(uintptr_t)255);
+    bf16* q2 = (bf16*)after;
+    if ((st = project_qkv(a, q2, after + (size_t)n * d3 * sizeof(bf16), s))) return st;
+    qkv = q2;
+  }
+  CUtensorMap tm, tmdo;
+  if ((st = make_row_map(&tm, qkv, a, d3))) return st;
+  if ((st = make_row_map(&tmdo, a.d_out, a, d))) return st;
+  tc2::CoreArgs p{};
+  p.bits = a.bits; p.dqkv = dqkv; p.threshold = a.threshold; p.d = d; p.heads = a.heads; p.tiles = a.tiles();
+  p.stages = 2;
+  p.geo = tc2::make_geo2(a, W);
+  const int items = p.tiles * p.heads;
+  const int grid = items < 148 ? items : 148;
+  const int smem = 2 * 4 * tc2::kTile + 2 * tc2::kPBytes + (int)sizeof(tc2::BwdBars) + 1024;
+  const bool train = a.threshold >= 0.f;
+  switch (2 * W) {
+    case 32: st = launch_core_bwd<32>(tm, tmdo, p, train, grid, smem, s); break;
+    case 64: st = launch_core_bwd<64>(tm, tmdo, p, train, grid, smem, s); break;
+    case 128: st = launch_core_bwd<128>(tm, tmdo, p, train, grid, smem, s); break;
+    default: return HWGAT_ERR_UNSUPPORTED;
+  }
+  if (st) return st;
+  // d_xn[n, d] = dQKV[n, 3d] . Wqkv[3d, d]  (against Wqkv^T so that both operands are K-major)
+  if ((st = transpose_bf16((const bf16*)a.w_qkv, wt, d3, d, s, false))) return st;
+  if ((st = gemm_tc_nt_epi_none(dqkv, wt, (bf16*)a.d_xn, n, d, d3, s))) return st;
+  // d_w[3d, d] = dQKV^T . xn ; d_b = column sums of dQKV
+  return gemm_tc_tn(dqkv, (const bf16*)a.xn, a.d_w, a.d_b, d3, d, n, s, false);
+}
+
+}  // namespace hwgat

@@ -366,4 +366,52 @@ int attn_bwd_f32(const AttnArgs& a, cudaStream_t s) {
   return check_last();
 }
 
+// ---------------------------------------------------------------------------
+// K13: a plain fp32 Linear on the same FFMA GEMM (the classifier head, HWGATE.py:359)
+// ---------------------------------------------------------------------------
+int linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, int n, int d_in, int d_out,
+                   cudaStream_t s) {
+  dim3 g((d_out + 63) / 64, (unsigned)((n + 63) / 64), 1);
+  if (bias)
+    gemm_f32_kernel<false, true, false, true><<<g, 256, 0, s>>>(x, w, bias, y, n, d_out, d_in, d_in);
+  else
+    gemm_f32_kernel<false, true, false, false><<<g, 256, 0, s>>>(x, w, nullptr, y, n, d_out, d_in, d_in);
+  count_launch();
+  return check_last();
+}
+
+// dx[n, d_in] = dy . W ; dw[d_out, d_in] = dy^T . x ; db[d_out] = column sums of dy  (any of the three may be NULL)
+int linear_f32_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int n, int d_in,
+                   int d_out, cudaStream_t s) {
+  int st;
+  if (dx) {
+    dim3 g((d_in + 63) / 64, (unsigned)((n + 63) / 64), 1);
+    gemm_f32_kernel<false, false, false, false><<<g, 256, 0, s>>>(dy, w, nullptr, dx, n, d_in, d_out, d_out);
+    count_launch();
+    if ((st = check_last())) return st;
+  }
+  if (dw) {
+    // the contraction runs over the n rows: one split (deterministic plain stores) up to 4096 rows
+    dim3 g((d_in + 63) / 64, (d_out + 63) / 64, 1);
+    if (n <= 4096) {
+      gemm_f32_kernel<true, false, false, false><<<g, 256, 0, s>>>(dy, x, nullptr, dw, d_out, d_in, n, n);
+    } else {
+      cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d_out * d_in, s);
+      const int kps = 4096;
+      g.z = (unsigned)((n + kps - 1) / kps);
+      gemm_f32_kernel<true, false, true, false><<<g, 256, 0, s>>>(dy, x, nullptr, dw, d_out, d_in, n, kps);
+    }
+    count_launch();
+    if ((st = check_last())) return st;
+  }
+  if (db) {
+    cudaMemsetAsync(db, 0, sizeof(float) * d_out, s);
+    dim3 g((d_out + 127) / 128, 1);
+    colsum_f32_kernel<<<g, 128, 0, s>>>(dy, db, n, d_out, n);
+    count_launch();
+    if ((st = check_last())) return st;
+  }
+  return 0;
+}
+
 }  // namespace hwgat

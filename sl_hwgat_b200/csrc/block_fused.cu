@@ -51,6 +51,29 @@ HW_DEV void fold_groups(float4 (&a)[4]) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// TemporalMerging (HWGATE.py:55-63) folded into its neighbours.  The merged tensor (B, F/2, K, 2d) is, in units of
+// d-wide rows, (B, F/2, K, 2, d): merging is a ROW permutation of the (B, F, K, d) tensor,
+//   row (b*F + fr)*K + k   ->   ((b*(F/2) + fr/2)*K + k)*2 + (fr & 1).
+// The last K6 of a level stores its rows through this map (forward), and the first LayerNorm-backward of the next
+// level stores each half of its 2d-wide rows through the inverse (backward), so K4 and its adjoint are not launched.
+// ---------------------------------------------------------------------------
+HW_DEV long long merged_row(long long r, int F, int K) {
+  const long long bf = r / K;
+  const int k = (int)(r - bf * K);
+  const long long b = bf / F;
+  const int fr = (int)(bf - b * F);
+  return ((((b * (F >> 1)) + (fr >> 1)) * K + k) << 1) | (fr & 1);
+}
+// inverse, for row R of the MERGED tensor (F2 = F/2 frames) and half tp: the un-merged d-wide row
+HW_DEV long long unmerged_row(long long R, int tp, int F2, int K) {
+  const long long bf = R / K;
+  const int k = (int)(R - bf * K);
+  const long long b = bf / F2;
+  const int fi = (int)(bf - b * F2);
+  return ((b * (2 * F2) + 2 * fi + tp) * K + k);
+}
+
 template <int kL>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, bf16* __restrict__ y,
@@ -105,7 +128,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
                                                      const float* __restrict__ x, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                      float* __restrict__ dx, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, long long n) {
+                                                     float* __restrict__ dbeta, long long n, int uF2, int uK) {
   constexpr int d = kL * 16, kRows = 32 / kL;
   __shared__ float red[2][8][d];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane / kL, lc = lane % kL;
@@ -146,7 +169,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
         const float4 r = *reinterpret_cast<const float4*>(dres + row * d + i * 4 * kL + lc * 4);
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
-      *reinterpret_cast<float4*>(dx + row * d + i * 4 * kL + lc * 4) = o;
+      if (uF2) {   // un-merge: this row is a merged 2 x (d/2) row; columns < d/2 belong to frame 2 fi, the rest to 2 fi + 1
+        const int c = i * 4 * kL + lc * 4, tp = c >= d / 2;
+        *reinterpret_cast<float4*>(dx + unmerged_row(row, tp, uF2, uK) * (d / 2) + (c - tp * (d / 2))) = o;
+      } else {
+        *reinterpret_cast<float4*>(dx + row * d + i * 4 * kL + lc * 4) = o;
+      }
     }
   }
   fold_groups<kL>(dg);
@@ -180,7 +208,7 @@ __global__ void __launch_bounds__(256) bda_ln_fwd_kernel(const float* __restrict
                                                          bf16* __restrict__ y, float* __restrict__ mean,
                                                          float* __restrict__ rstd, long long n, float eps, float scale,
                                                          uint32_t thresh, unsigned long long seed,
-                                                         unsigned long long offset) {
+                                                         unsigned long long offset, int mF, int mK) {
   constexpr int d = kL * 16, kRows = 32 / kL;
   const int lane = threadIdx.x & 31, sub = lane / kL, lc = lane % kL;
   const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * 8;
@@ -221,8 +249,9 @@ __global__ void __launch_bounds__(256) bda_ln_fwd_kernel(const float* __restrict
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
     if (ok) {
+      const long long orow = mF ? merged_row(row, mF, mK) : row;   // (x1 stored in the merged layout: see merged_row)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(x1 + row * d + i * 4 * kL + lc * 4) = v[i];
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(x1 + orow * d + i * 4 * kL + lc * 4) = v[i];
     }
     if (!kLN) continue;
     const float mu = group_sum<kL>(s) * (1.f / d);
@@ -446,15 +475,17 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, bf16* y
 }
 
 int launch_ln_bwd(const bf16* dy, const float* dres, const float* x, const float* mean, const float* rstd,
-                  const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d, cudaStream_t s) {
+                  const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d, cudaStream_t s,
+                  int unmerge_F2, int unmerge_K) {
+  const int uF2 = unmerge_F2, uK = unmerge_K;
   cudaMemsetAsync(dgamma, 0, sizeof(float) * d, s);
   cudaMemsetAsync(dbeta, 0, sizeof(float) * d, s);
   long long want = (n + 7) / 8;
   const int grid = (int)(want < 148LL * 4 ? (want < 1 ? 1 : want) : 148LL * 4);
   switch (d) {
-    case 128: ln_bwd_kernel<8><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n); break;
-    case 256: ln_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n); break;
-    case 512: ln_bwd_kernel<32><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n); break;
+    case 128: ln_bwd_kernel<8><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK); break;
+    case 256: ln_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK); break;
+    case 512: ln_bwd_kernel<32><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();
@@ -465,11 +496,11 @@ template <bool kLN>
 static int bda_fwd_dispatch(int grid, cudaStream_t s, const float* res, const bf16* a0, const float* bias,
                             const float* gamma, const float* beta, float* x1, bf16* y, float* mean, float* rstd,
                             long long n, int d, float eps, float scale, uint32_t thresh, unsigned long long seed,
-                            unsigned long long offset) {
+                            unsigned long long offset, int mF, int mK) {
   switch (d) {
-    case 128: bda_ln_fwd_kernel<8, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset); break;
-    case 256: bda_ln_fwd_kernel<16, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset); break;
-    case 512: bda_ln_fwd_kernel<32, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset); break;
+    case 128: bda_ln_fwd_kernel<8, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset, mF, mK); break;
+    case 256: bda_ln_fwd_kernel<16, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset, mF, mK); break;
+    case 512: bda_ln_fwd_kernel<32, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset, mF, mK); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   return 0;
@@ -477,12 +508,13 @@ static int bda_fwd_dispatch(int grid, cudaStream_t s, const float* res, const bf
 
 int launch_bda_ln_fwd(const float* res, const bf16* a0, const float* bias, const float* gamma, const float* beta,
                       float* x1, bf16* y, float* mean, float* rstd, long long n, int d, float eps, float p,
-                      unsigned long long seed, unsigned long long offset, cudaStream_t s) {
+                      unsigned long long seed, unsigned long long offset, cudaStream_t s, int merge_F, int merge_K) {
+  const int mF = merge_F, mK = merge_K;
   const uint32_t thresh = drop_threshold16(p);
   const float scale = thresh ? 65536.f / (65536.f - (float)thresh) : 1.f;
   const int grid = ew_grid(n * 32);
-  int st = gamma ? bda_fwd_dispatch<true>(grid, s, res, a0, bias, gamma, beta, x1, y, mean, rstd, n, d, eps, scale, thresh, seed, offset)
-                 : bda_fwd_dispatch<false>(grid, s, res, a0, bias, gamma, beta, x1, y, mean, rstd, n, d, eps, scale, thresh, seed, offset);
+  int st = gamma ? bda_fwd_dispatch<true>(grid, s, res, a0, bias, gamma, beta, x1, y, mean, rstd, n, d, eps, scale, thresh, seed, offset, mF, mK)
+                 : bda_fwd_dispatch<false>(grid, s, res, a0, bias, gamma, beta, x1, y, mean, rstd, n, d, eps, scale, thresh, seed, offset, mF, mK);
   if (st) return st;
   count_launch();
   return (int)cudaGetLastError();

@@ -132,10 +132,12 @@ int launch_merge(const void* src, void* dst, int B, int F, int K, int d, int ele
 int launch_ln_fwd(const float* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* mean, float* rstd,
                   long long n, int d, float eps, cudaStream_t s);
 int launch_ln_bwd(const __nv_bfloat16* dy, const float* dres, const float* x, const float* mean, const float* rstd,
-                  const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d, cudaStream_t s);
+                  const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d, cudaStream_t s,
+                  int unmerge_F2 = 0, int unmerge_K = 0);
 int launch_bda_ln_fwd(const float* res, const __nv_bfloat16* a0, const float* bias, const float* gamma,
                       const float* beta, float* x1, __nv_bfloat16* y, float* mean, float* rstd, long long n, int d,
-                      float eps, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s);
+                      float eps, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s,
+                      int merge_F = 0, int merge_K = 0);
 int launch_bda_ln_bwd(const float* g_x1, const __nv_bfloat16* dy, const float* x1, const float* mean, const float* rstd,
                       const float* gamma, float* d_res, __nv_bfloat16* d_a0, float* dbias, float* dgamma, float* dbeta,
                       long long n, int d, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s);
@@ -149,6 +151,15 @@ int launch_ln_pool_fwd(const float* x, const float* gamma, const float* beta, fl
                        int B, int tokens, int d, float eps, cudaStream_t s);
 int launch_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
                        float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s);
+
+int linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, int n, int d_in, int d_out,
+                   cudaStream_t s);
+int linear_f32_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int n, int d_in,
+                   int d_out, cudaStream_t s);
+int smooth_ce_fwd(const float* logits, const long long* target, float* lse, float* row_loss, float* loss, int rows,
+                  int classes, float smooth, cudaStream_t s);
+int smooth_ce_bwd(const float* logits, const long long* target, const float* lse, const float* g, float* dlogits,
+                  int rows, int classes, float smooth, cudaStream_t s);
 
 struct AttnArgs {
   const void* xn; const void* w_qkv; const float* b_qkv; const uint32_t* bits;
@@ -165,6 +176,9 @@ int attn_fwd_f32(const AttnArgs& a, cudaStream_t s);
 int attn_bwd_f32(const AttnArgs& a, cudaStream_t s);
 int attn_fwd_bf16(const AttnArgs& a, cudaStream_t s);
 int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s);
+size_t attn2_workspace_bytes(long long n, int d, int backward, int have_qkv);
+int attn2_fwd(const AttnArgs& a, int W, __nv_bfloat16* qkv, cudaStream_t s);
+int attn2_bwd(const AttnArgs& a, int W, const __nv_bfloat16* qkv_saved, cudaStream_t s);
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t s);
 int attn_bwd_tc(const AttnArgs& a, __nv_bfloat16* dqkv, cudaStream_t s);
 int gemm_tc_tn(const __nv_bfloat16* A, const __nv_bfloat16* Bm, float* C, float* colsum, int M, int N, long long Kd,

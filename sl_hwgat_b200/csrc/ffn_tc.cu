@@ -23,7 +23,7 @@ namespace hwgat {
 
 typedef __nv_bfloat16 bf16;
 
-enum { kEpiNone = 0, kEpiGelu = 1, kEpiMul = 2 };
+enum { kEpiNone = 0, kEpiGelu = 1, kEpiMul = 2, kEpiBias = 3 };   // kEpiBias: C = acc + bias (fp32 add, then bf16)
 
 struct EpiArgs {
   bf16* C;            // [M, N] output
@@ -74,6 +74,18 @@ HW_DEV void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& e, size_t ele
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         p[i] = pack_bf16(__uint_as_float(r[16 * g + 2 * i]), __uint_as_float(r[16 * g + 2 * i + 1]));
+      st_global32(e.C + elem + 16 * g, p);
+    }
+  } else if (EPI == kEpiBias) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint32_t p[8];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 b = lds_f4(sbias + col + 16 * g + 4 * q4);
+        p[2 * q4] = pack_bf16(__uint_as_float(r[16 * g + 4 * q4]) + b.x, __uint_as_float(r[16 * g + 4 * q4 + 1]) + b.y);
+        p[2 * q4 + 1] = pack_bf16(__uint_as_float(r[16 * g + 4 * q4 + 2]) + b.z, __uint_as_float(r[16 * g + 4 * q4 + 3]) + b.w);
+      }
       st_global32(e.C + elem + 16 * g, p);
     }
   } else if (EPI == kEpiMul) {
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_kernel
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blocks = N / BN, m_blocks = M / kFM, tiles = n_blocks * m_blocks, nk = K / kFK;
-  if (EPI == kEpiGelu)
+  if (EPI == kEpiGelu || EPI == kEpiBias)
     for (int i = threadIdx.x; i < N; i += blockDim.x) sbias[i] = e.bias ? e.bias[i] : 0.f;
 
   if (threadIdx.x == 0) {
@@ -326,7 +338,7 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_pair_k
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int n_blocks = N / BN, m_blocks = (M + 2 * kFM - 1) / (2 * kFM), tiles = n_blocks * m_blocks, nk = K / kFK;
-  if (EPI == kEpiGelu)
+  if (EPI == kEpiGelu || EPI == kEpiBias)
     for (int i = threadIdx.x; i < N; i += blockDim.x) sbias[i] = e.bias ? e.bias[i] : 0.f;
 
   if (threadIdx.x == 0) {
@@ -482,6 +494,16 @@ int gemm_tc_nt_epi_none(const bf16* A, const bf16* Bt, bf16* C, long long M, int
   EpiArgs e{};
   e.C = C;
   return gemm_nt_epi<kEpiNone>(A, Bt, e, M, N, K, s);
+}
+
+// C = A . Bt^T + bias (fp32 bias add before the bf16 rounding): the QKV projection of the general-window attention
+// path (attn_core_tc2.cu).  N <= kMaxBiasN.
+int gemm_tc_nt_epi_bias(const bf16* A, const bf16* Bt, const float* bias, bf16* C, long long M, int N, int K,
+                        cudaStream_t s) {
+  if (N > kMaxBiasN) return HWGAT_ERR_UNSUPPORTED;
+  EpiArgs e{};
+  e.C = C; e.bias = bias;
+  return gemm_nt_epi<kEpiBias>(A, Bt, e, M, N, K, s);
 }
 
 // ---------------------------------------------------------------------------

@@ -92,6 +92,7 @@ class MSA(nn.Module):
 
     def __init__(self, dim, num_heads, adj_mat=None, attn_drop=0., proj_drop=0.) -> None:
         super().__init__()
+        self.window_size = ops.WINDOW      # set by PartAttentionBlock (the reference's MSA infers N from its input)
         self.dim = dim
         self.num_heads = num_heads
         assert dim % num_heads == 0, 'dim and number of heads are incompatible'
@@ -128,14 +129,16 @@ class MSA(nn.Module):
     def attend(self, xn, shift, block_bits):
         dt = _attn_dtype(xn)
         ctx = ops.window_graph_attention(xn.to(dt), self.qkv.weight, self.qkv.bias, block_bits, self.num_heads,
-                                         shift=shift, threshold=self._draw_threshold(), layout=LAYOUT_BFKD)
+                                         shift=shift, threshold=self._draw_threshold(), layout=LAYOUT_BFKD,
+                                         window=self.window_size)
         return self._project(ctx)
 
     # -- reference signature: x is (B*f*nW, TP*W, d), already rolled and partitioned
     def forward(self, x, B, f, nW, mask=None):
         n_win, N, d = x.shape
-        if n_win != B * f * nW or N != ops.WINDOW * ops.TEMPORAL_PATCH:
-            raise ValueError("x must be (B*f*nW, 32, d)")
+        window = N // ops.TEMPORAL_PATCH
+        if n_win != B * f * nW or N != window * ops.TEMPORAL_PATCH or window not in ops.WINDOWS:
+            raise ValueError("x must be (B*f*nW, 2*window_size, d) with window_size in (16, 32, 64)")
         adj = self.adj_mat
         key = (None if mask is None else (mask.data_ptr(), mask._version),
                None if adj is None else (adj.data_ptr(), adj._version), f, nW, x.device)
@@ -149,7 +152,7 @@ class MSA(nn.Module):
         dt = _attn_dtype(x)
         ctx = ops.window_graph_attention(x.to(dt), self.qkv.weight, self.qkv.bias, bits, self.num_heads, shift=0,
                                          threshold=self._draw_threshold(), layout=LAYOUT_WINDOWS,
-                                         frames=f * ops.TEMPORAL_PATCH, kps=nW * ops.WINDOW)
+                                         frames=f * ops.TEMPORAL_PATCH, kps=nW * window, window=window)
         return self._project(ctx)
 
 
@@ -176,8 +179,9 @@ class PartAttentionBlock(nn.Module):
                  shift_size=0, adj_mat=None, drop=0., attn_drop=0., ff_ratio=4., act_layer=nn.GELU,
                  norm_layer=nn.LayerNorm):
         super().__init__()
-        if window_size != ops.WINDOW or temporal_patch_size != ops.TEMPORAL_PATCH:
-            raise NotImplementedError("the attention kernels are built for window_size 16, temporal_patch_size 2")
+        if window_size not in ops.WINDOWS or temporal_patch_size != ops.TEMPORAL_PATCH:
+            raise NotImplementedError("the attention kernels are built for window_size 16 / 32 / 64 and "
+                                      "temporal_patch_size 2 (the multi-level reference only runs with TP = 2)")
         self.dim = dim
         self.num_kps = num_kps
         self.num_heads = num_heads
@@ -192,6 +196,7 @@ class PartAttentionBlock(nn.Module):
 
         self.norm1 = norm_layer(dim)
         self.attn = MSA(dim, num_heads=num_heads, adj_mat=adj_mat, attn_drop=attn_drop, proj_drop=drop)
+        self.attn.window_size = window_size
         self.norm2 = norm_layer(dim)
         self.ff = FeedForward(in_features=dim, hidden_features=int(self.ff_dim), act_layer=act_layer, drop=drop)
 
@@ -260,19 +265,23 @@ class PartAttentionBlock(nn.Module):
         x, xn = ops.layer_norm_residual(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         return self.forward_chain(x, xn, None)[0]
 
-    def forward_chain(self, x, xn, next_norm):
+    def forward_chain(self, x, xn, next_norm, merge=False):
         """Fused bf16 path.  x: fp32 residual stream, xn = norm1(x) in bf16 (made by the previous kernel of the
         chain).  Returns (x_out, next_norm(x_out) in bf16 or None): the LayerNorm that consumes the block's output
-        is computed by the same kernel that forms the output (K6)."""
+        is computed by the same kernel that forms the output (K6).  merge=True (last block of a level, next_norm =
+        the next level's first norm1): x_out is stored directly in TemporalMerging's layout (B, F/2, K, 2d) and
+        next_norm runs over the merged 2d-wide rows - K4 and its adjoint are folded into K6 / K5'."""
         attn, ff = self.attn, self.ff
         ctx = ops.window_graph_attention(xn, attn.qkv.weight, attn.qkv.bias, self._block_bits(x.device),
                                          attn.num_heads, shift=self.shift_size, threshold=attn._draw_threshold(),
-                                         layout=LAYOUT_BFKD)
+                                         layout=LAYOUT_BFKD, window=self.window_size)
         a0 = ops.output_projection(ctx, attn.proj.weight)          # K12; bias, dropout, shortcut and norm2: K6
         x, h = ops.bias_dropout_add_ln(x, a0, attn.proj.bias, self.norm2, attn.proj_drop.p, self.training)
         # K10: fc1 + bias + GELU + dropout + fc2's matmul on the tcgen05 GEMMs with fused epilogues
         v0 = ops.feed_forward_core(h, ff.fc1.weight, ff.fc1.bias, ff.fc2.weight, ff.drop.p, self.training)
         # fc2's bias, dropout, residual (and the next norm1): K6
+        if merge:
+            return ops.bias_dropout_add_merge_ln(x, v0, ff.fc2.bias, next_norm, ff.drop.p, self.training)
         return ops.bias_dropout_add_ln(x, v0, ff.fc2.bias, next_norm, ff.drop.p, self.training)
 
 
@@ -298,17 +307,36 @@ class PartAttentionLayer(nn.Module):
             for i in range(depth)])
         self.downsample = downsample(dim, temporal_patch_size) if downsample is not None else None
 
-    def forward(self, x):
+    def fusable(self, x):
         blocks = list(self.blocks)
-        if blocks and all(b._fusable(x) for b in blocks):
+        return bool(blocks) and all(b._fusable(x) for b in blocks)
+
+    def forward_fused(self, x, xn=None, next_level_norm=None):
+        """The level on the fused bf16 kernels.  xn: norm1 of the first block already applied to x (bf16), or None.
+        next_level_norm: the first norm1 of the NEXT level; when given (and this level ends in a TemporalMerging the
+        fold supports) the last K6 stores the merged layout and computes that LayerNorm, and (x_merged, xn_next) is
+        returned; otherwise (x_merged or x, None)."""
+        blocks = list(self.blocks)
+        if xn is None:
             first = blocks[0]
             x, xn = ops.layer_norm_residual(x, first.norm1.weight, first.norm1.bias, first.norm1.eps)
-            for i, blk in enumerate(blocks):
-                nxt = blocks[i + 1].norm1 if i + 1 < len(blocks) else None
-                x, xn = blk.forward_chain(x, xn, nxt)
-        else:
-            for blk in blocks:
-                x = blk(x)
+        fold = (next_level_norm is not None and type(self.downsample) is TemporalMerging
+                and self.downsample.temporal_patch_size == ops.TEMPORAL_PATCH and type(next_level_norm) is nn.LayerNorm
+                and ops.merge_fold_supported(self.dim, x.shape[1]))
+        for i, blk in enumerate(blocks):
+            last = i + 1 == len(blocks)
+            if last and fold:
+                return blk.forward_chain(x, xn, next_level_norm, merge=True)
+            x, xn = blk.forward_chain(x, xn, None if last else blocks[i + 1].norm1)
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return x, None
+
+    def forward(self, x):
+        if self.fusable(x):
+            return self.forward_fused(x)[0]
+        for blk in self.blocks:
+            x = blk(x)
         if self.downsample is not None:
             x = self.downsample(x)
         return x
@@ -382,8 +410,20 @@ class Model(nn.Module):
                 x = torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1)
             if self.pe:
                 x = self.pos_encoder(x)
-        for layer in self.layers:
-            x = layer(x)
+        layers = list(self.layers)
+        if fused and all(isinstance(l, PartAttentionLayer) and l.fusable(x) for l in layers[:1]):
+            # levels chained on the fused kernels: each level's last residual add stores TemporalMerging's layout and
+            # applies the next level's first LayerNorm in the same pass (K4 folded away)
+            xn = None
+            for i, layer in enumerate(layers):
+                if not layer.fusable(x):
+                    x, xn = layer(x), None
+                    continue
+                nxt = layers[i + 1].blocks[0].norm1 if i + 1 < len(layers) and len(layers[i + 1].blocks) else None
+                x, xn = layer.forward_fused(x, xn, nxt)
+        else:
+            for layer in layers:
+                x = layer(x)
         B, f, K, d = x.shape
         if fused and type(self.norm) is nn.LayerNorm and d in (128, 256, 512):
             # K9: final LayerNorm + mean over the f*K tokens (self.avgpool, HWGATE.py:354) in one pass
@@ -394,4 +434,9 @@ class Model(nn.Module):
         return x.reshape(B, f * K, d).mean(dim=1)
 
     def forward(self, x):
-        return self.head(self.forward_features(x))
+        feats = self.forward_features(x)
+        if feats.is_cuda and type(self.head) is nn.Linear:
+            # K13: the classifier head in fp32 on the library's FFMA GEMM (also under autocast: its output feeds
+            # the log-softmax of the loss)
+            return ops.linear_f32(feats, self.head.weight, self.head.bias)
+        return self.head(feats)

@@ -48,6 +48,16 @@ class HWGATEParams():
         # the reference hands the model a CPU float32 tensor (model_params.py:259)
         self.adj_mat = self.get_adj_mat().cpu()
 
+    def set_window_size(self, window_size):
+        """Larger keypoint windows (BASELINE configs[4]): the reference takes `window_size` at model_params.py:254
+        and builds np.eye(W) + the 25 skeleton edges for the first K/W edge lists (model_params.py:373-400); this
+        re-derives adj_mat the same way for W in {16, 32, 64}."""
+        if self.num_kps % window_size != 0:
+            raise ValueError("window size and number of kps are incompatible")
+        self.window_size = window_size
+        self.edges = [_window_edges() for _ in range(self.num_kps // window_size)]
+        self.adj_mat = self.get_adj_mat().cpu()
+
     def _cuda_device(self):
         dev = torch.device(self.device) if self.device is not None else None
         if dev is None or dev.type != "cuda":

@@ -15,9 +15,18 @@ import torch
 from . import _lib
 from ._lib import BF16, F32, LAYOUT_BFKD, LAYOUT_WINDOWS, check
 
-WINDOW = 16       # keypoints per window the kernels are built for (model_params.py:254)
+import os
+
+WINDOW = 16       # the reference's keypoints per window (model_params.py:254)
+WINDOWS = (16, 32, 64)   # window sizes the bf16 kernels cover: N = 2 W = 32, 64, 128 tokens per window
 TEMPORAL_PATCH = 2  # frames per window (model_params.py:250)
 HEAD_DIM = 64
+
+# Which bf16 attention kernels run for the reference window (W = 16):
+#   "fused" : K2 / K3 (attn_tc.cu) - QKV projection inside the attention kernel, 32 x 32 windows on mma.sync
+#   "tc2"   : K2b / K3b (attn_core_tc2.cu) - projection GEMM + attention core with every product on tcgen05
+# W = 32 / 64 always take "tc2" (the only kernels built for them).  HWGAT_ATTN_IMPL overrides for A/B runs.
+ATTN_IMPL = os.environ.get("HWGAT_ATTN_IMPL", "fused")
 
 
 def _need_cuda(*tensors: torch.Tensor) -> None:
@@ -191,20 +200,81 @@ class _WindowGraphAttention(torch.autograd.Function):
         return (d_xn.view_as(d_out), d_w.to(w_dtype), d_b.to(b_dtype), None, None, None, None, None, None, None)
 
 
+class _WindowGraphAttention2(torch.autograd.Function):
+    """The same op on K2b / K3b (any window of W in {16, 32, 64} keypoints): projection GEMM + tcgen05 attention
+    core.  The projected q, k, v rows are kept for the backward (3x the activation in bf16) unless `save_qkv` is
+    False, in which case the backward re-projects them."""
+
+    @staticmethod
+    def forward(ctx, xn, w_qkv, b_qkv, bits, threshold, heads, shift, layout, frames, kps, window, save_qkv):
+        lib = _lib.load()
+        _need_cuda(xn, w_qkv, b_qkv, bits)
+        if xn.dtype != torch.bfloat16:
+            raise _lib.HwgatError("the general-window attention kernels (K2b / K3b) are bf16 only; the fp32 parity "
+                                  "kernels are built for window_size 16")
+        xn_c = xn.contiguous()
+        d = xn_c.shape[-1]
+        n_tok = xn_c.numel() // d
+        if frames * kps == 0 or n_tok % (frames * kps) != 0:
+            raise ValueError(f"token count {n_tok} is not a multiple of frames*keypoints = {frames * kps}")
+        B = n_tok // (frames * kps)
+        w_c = cast_cached(w_qkv, torch.bfloat16)
+        b_c = cast_cached(b_qkv, torch.float32)
+        out = torch.empty_like(xn_c)
+        qkv = torch.empty((n_tok, 3 * d), dtype=torch.bfloat16, device=xn_c.device)
+        ws_bytes = lib.hwgat_attn2_workspace_bytes(B, frames, kps, d, heads, 0, 1)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xn_c.device)
+        with torch.cuda.device(xn_c.device):
+            check(lib.hwgat_attn2_fwd(xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
+                                      float(threshold), out.data_ptr(), qkv.data_ptr(), ws.data_ptr(), ws.numel(), B,
+                                      frames, kps, d, heads, window, TEMPORAL_PATCH, shift, layout, _stream()),
+                  "hwgat_attn2_fwd")
+        keep = save_qkv and any(ctx.needs_input_grad[:3])
+        ctx.save_for_backward(xn_c, w_c, b_c, bits, qkv if keep else None)
+        ctx.meta = (float(threshold), heads, shift, layout, frames, kps, B, d, window, w_qkv.dtype, b_qkv.dtype)
+        return out.view_as(xn)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        xn_c, w_c, b_c, bits, qkv = ctx.saved_tensors
+        threshold, heads, shift, layout, frames, kps, B, d, window, w_dtype, b_dtype = ctx.meta
+        g = d_out.to(torch.bfloat16).contiguous()
+        d_xn = torch.empty_like(xn_c)
+        d_w = torch.empty((3 * d, d), dtype=torch.float32, device=xn_c.device)
+        d_b = torch.empty((3 * d,), dtype=torch.float32, device=xn_c.device)
+        ws_bytes = lib.hwgat_attn2_workspace_bytes(B, frames, kps, d, heads, 1, 0 if qkv is None else 1)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xn_c.device)
+        with torch.cuda.device(xn_c.device):
+            check(lib.hwgat_attn2_bwd(g.data_ptr(), xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), _ptr(qkv),
+                                      bits.data_ptr(), threshold, d_xn.data_ptr(), d_w.data_ptr(), d_b.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), B, frames, kps, d, heads, window, TEMPORAL_PATCH,
+                                      shift, layout, _stream()), "hwgat_attn2_bwd")
+        return (d_xn.view_as(d_out), d_w.to(w_dtype), d_b.to(b_dtype)) + (None,) * 9
+
+
 def window_graph_attention(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, bits: torch.Tensor,
                            heads: int, shift: int = 0, threshold: Optional[float] = None,
                            layout: int = LAYOUT_BFKD, frames: Optional[int] = None,
-                           kps: Optional[int] = None) -> torch.Tensor:
+                           kps: Optional[int] = None, window: int = WINDOW, impl: Optional[str] = None,
+                           save_qkv: bool = True) -> torch.Tensor:
     """Fused roll + window_partition + QKV + masked attention + window_reverse +
     roll back (HWGATE.py:197-201, 86-114, 207-215), without the output projection.
 
-    xn: (B, F, K, d) for LAYOUT_BFKD, or (B*f*nW, 32, d) for LAYOUT_WINDOWS (then
-    `frames` and `kps` must be given).  threshold None = eval mode."""
+    xn: (B, F, K, d) for LAYOUT_BFKD, or (B*f*nW, 2*window, d) for LAYOUT_WINDOWS (then
+    `frames` and `kps` must be given).  threshold None = eval mode.  window: keypoints per window
+    (16 = the reference; 32 and 64 are bf16 only).  impl: "fused" | "tc2" | None (= ops.ATTN_IMPL), see above."""
     if layout == LAYOUT_BFKD:
         frames, kps = xn.shape[1], xn.shape[2]
     elif frames is None or kps is None:
         raise ValueError("LAYOUT_WINDOWS needs frames and kps")
     thr = -1.0 if threshold is None else float(threshold)
+    if window not in WINDOWS:
+        raise _lib.HwgatError(f"window_size {window} is not supported by the sm_100a kernels (16, 32, 64; no fallback)")
+    impl = impl or ATTN_IMPL
+    if window != WINDOW or (impl == "tc2" and xn.dtype == torch.bfloat16):
+        return _WindowGraphAttention2.apply(xn, w_qkv, b_qkv, bits, thr, heads, shift, layout, frames, kps, window,
+                                            save_qkv)
     return _WindowGraphAttention.apply(xn, w_qkv, b_qkv, bits, thr, heads, shift, layout, frames, kps)
 
 
@@ -379,6 +449,72 @@ def bias_dropout_add_ln(res: torch.Tensor, a0: torch.Tensor, bias: Optional[torc
     if norm is None:
         return _BiasDropoutAddLN.apply(res, a0, bias, None, None, 0.0, p if training else 0.0)
     return _BiasDropoutAddLN.apply(res, a0, bias, norm.weight, norm.bias, norm.eps, p if training else 0.0)
+
+
+class _BdaMergeLN(torch.autograd.Function):
+    """Level boundary in one Function: x1 = res + dropout(a0 + bias) stored directly in TemporalMerging's layout
+    (B, F/2, K, 2d) [K6 with the merge folded in], then y = LayerNorm_{2d}(x1) as bf16 [K5 of the next level's first
+    norm1].  Backward: K5' stores its result un-merged [the merge's adjoint folded in], then K6' (no-LN form).
+    Replaces K6 + K4 + K5 and K5' + K4' + K6' (HWGATE.py:134-135, 219, 55-63, 203)."""
+
+    @staticmethod
+    def forward(ctx, res, a0, bias, gamma, beta, eps, p):
+        lib = _lib.load()
+        _need_cuda(res, a0, bias, gamma, beta)
+        res_c, a_c = res.contiguous(), a0.to(torch.bfloat16).contiguous()
+        if res_c.dtype != torch.float32 or res_c.shape != a_c.shape or res_c.dim() != 4:
+            raise _lib.HwgatError("bias_dropout_add_merge_ln takes an fp32 (B,F,K,d) residual and a same-shape branch")
+        B, F, K, d = res_c.shape
+        n, dev = B * F * K, res_c.device
+        b_c = cast_cached(bias, torch.float32) if bias is not None else None
+        g_c, bt_c = cast_cached(gamma, torch.float32), cast_cached(beta, torch.float32)
+        seed, off = _philox_stream(dev) if p > 0 else (0, 0)
+        xm = torch.empty((B, F // 2, K, 2 * d), dtype=torch.float32, device=dev)
+        y = torch.empty((B, F // 2, K, 2 * d), dtype=torch.bfloat16, device=dev)
+        mean = torch.empty(n // 2, dtype=torch.float32, device=dev)
+        rstd = torch.empty(n // 2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.hwgat_bda_merge_fwd(res_c.data_ptr(), a_c.data_ptr(), _ptr(b_c), xm.data_ptr(), n, d, F, K,
+                                          float(p), seed, off, _stream()), "hwgat_bda_merge_fwd")
+            check(lib.hwgat_ln_fwd(xm.data_ptr(), g_c.data_ptr(), bt_c.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                   rstd.data_ptr(), n // 2, 2 * d, float(eps), _stream()), "hwgat_ln_fwd")
+        ctx.save_for_backward(xm, g_c, mean, rstd)
+        ctx.meta = (B, F, K, d, float(p), seed, off, a0.dtype, None if bias is None else bias.dtype, gamma.dtype,
+                    beta.dtype)
+        return xm, y
+
+    @staticmethod
+    def backward(ctx, g_xm, g_y):
+        lib = _lib.load()
+        xm, g_c, mean, rstd = ctx.saved_tensors
+        B, F, K, d, p, seed, off, adt, bdt, gdt, btdt = ctx.meta
+        n, dev = B * F * K, xm.device
+        dy = (g_y if g_y is not None else torch.zeros_like(xm, dtype=torch.bfloat16)).to(torch.bfloat16).contiguous()
+        gx = g_xm.float().contiguous() if g_xm is not None else None
+        d_x1 = torch.empty((B, F, K, d), dtype=torch.float32, device=dev)
+        dgamma = torch.empty(2 * d, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(2 * d, dtype=torch.float32, device=dev)
+        d_a0 = torch.empty((B, F, K, d), dtype=torch.bfloat16, device=dev)
+        dbias = torch.empty(d, dtype=torch.float32, device=dev) if bdt is not None else None
+        with torch.cuda.device(dev):
+            check(lib.hwgat_ln_bwd_unmerge(dy.data_ptr(), _ptr(gx), xm.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                           g_c.data_ptr(), d_x1.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                           n // 2, 2 * d, F // 2, K, _stream()), "hwgat_ln_bwd_unmerge")
+            check(lib.hwgat_bda_ln_bwd(d_x1.data_ptr(), 0, 0, 0, 0, 0, 0, d_a0.data_ptr(), _ptr(dbias), 0, 0, n, d, p,
+                                       seed, off, _stream()), "hwgat_bda_ln_bwd")
+        return (d_x1, d_a0.to(adt), None if dbias is None else dbias.to(bdt), dgamma.to(gdt), dbeta.to(btdt), None,
+                None)
+
+
+def bias_dropout_add_merge_ln(res: torch.Tensor, a0: torch.Tensor, bias: Optional[torch.Tensor], next_norm, p: float,
+                              training: bool):
+    """The last residual add of a level, TemporalMerging and the next level's first LayerNorm:
+    returns (x_merged fp32 (B,F/2,K,2d), next_norm(x_merged) as bf16)."""
+    return _BdaMergeLN.apply(res, a0, bias, next_norm.weight, next_norm.bias, next_norm.eps, p if training else 0.0)
+
+
+def merge_fold_supported(d: int, frames: int) -> bool:
+    return d in (128, 256) and frames % 2 == 0
 
 
 class _BiasGeluDropout(torch.autograd.Function):
@@ -596,3 +732,89 @@ class _LayerNormPool(torch.autograd.Function):
 def layer_norm_mean_pool(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     """(B, ..., d) -> (B, d): mean over all tokens of LayerNorm(x): self.norm + self.avgpool (HWGATE.py:353-354)."""
     return _LayerNormPool.apply(x, gamma, beta, eps)
+
+
+# --------------------------------------------------------------------------
+# K13 / K14: classifier head and label-smoothed cross entropy
+# --------------------------------------------------------------------------
+
+class _LinearF32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        lib = _lib.load()
+        _need_cuda(x, w, b)
+        x_c = x.float().contiguous()
+        w_c = cast_cached(w, torch.float32)
+        b_c = cast_cached(b, torch.float32) if b is not None else None
+        d_in, d_out = x_c.shape[-1], w_c.shape[0]
+        if tuple(w_c.shape) != (d_out, d_in):
+            raise ValueError(f"head weight {tuple(w.shape)} does not match (n, {d_in}) input")
+        n = x_c.numel() // d_in
+        y = torch.empty(x_c.shape[:-1] + (d_out,), dtype=torch.float32, device=x_c.device)
+        with torch.cuda.device(x_c.device):
+            check(lib.hwgat_linear_f32_fwd(x_c.data_ptr(), w_c.data_ptr(), _ptr(b_c), y.data_ptr(), n, d_in, d_out,
+                                           _stream()), "hwgat_linear_f32_fwd")
+        ctx.save_for_backward(x_c, w_c)
+        ctx.meta = (n, d_in, d_out, x.dtype, w.dtype, None if b is None else b.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x_c, w_c = ctx.saved_tensors
+        n, d_in, d_out, xdt, wdt, bdt = ctx.meta
+        dy_c = dy.float().contiguous()
+        dev = x_c.device
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], bdt is not None and ctx.needs_input_grad[2]
+        dx = torch.empty_like(x_c) if need_x else None
+        dw = torch.empty((d_out, d_in), dtype=torch.float32, device=dev) if need_w else None
+        db = torch.empty((d_out,), dtype=torch.float32, device=dev) if need_b else None
+        with torch.cuda.device(dev):
+            check(lib.hwgat_linear_f32_bwd(dy_c.data_ptr(), x_c.data_ptr(), w_c.data_ptr(), _ptr(dx), _ptr(dw), _ptr(db),
+                                           n, d_in, d_out, _stream()), "hwgat_linear_f32_bwd")
+        return (None if dx is None else dx.to(xdt), None if dw is None else dw.to(wdt),
+                None if db is None else db.to(bdt))
+
+
+def linear_f32(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    """x @ w.T + b in fp32 on the library's FFMA GEMM (K13): the classifier head self.head (HWGATE.py:359)."""
+    return _LinearF32.apply(x, w, b)
+
+
+class _SmoothCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, smooth):
+        lib = _lib.load()
+        _need_cuda(logits, target)
+        z = logits.float().contiguous()
+        if z.dim() != 2 or target.shape != z.shape[:1]:
+            raise ValueError("smooth_cross_entropy takes (rows, classes) logits and (rows,) class indices")
+        t = target.to(torch.int64).contiguous()
+        rows, classes = z.shape
+        dev = z.device
+        lse = torch.empty(rows, dtype=torch.float32, device=dev)
+        row_loss = torch.empty(rows, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.hwgat_smooth_ce_fwd(z.data_ptr(), t.data_ptr(), lse.data_ptr(), row_loss.data_ptr(), loss.data_ptr(),
+                                          rows, classes, float(smooth), _stream()), "hwgat_smooth_ce_fwd")
+        ctx.save_for_backward(z, t, lse)
+        ctx.meta = (rows, classes, float(smooth), logits.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        z, t, lse = ctx.saved_tensors
+        rows, classes, smooth, dt = ctx.meta
+        g_c = g.float().contiguous()
+        dz = torch.empty_like(z)
+        with torch.cuda.device(z.device):
+            check(lib.hwgat_smooth_ce_bwd(z.data_ptr(), t.data_ptr(), lse.data_ptr(), g_c.data_ptr(), dz.data_ptr(), rows,
+                                          classes, smooth, _stream()), "hwgat_smooth_ce_bwd")
+        return dz.to(dt), None, None
+
+
+def smooth_cross_entropy(logits: torch.Tensor, target: torch.Tensor, smooth: float = 0.01) -> torch.Tensor:
+    """Label-smoothed cross entropy, mean over the batch (losses/SmoothCrossEntropy.py:35-39), as K14."""
+    return _SmoothCE.apply(logits, target, smooth)

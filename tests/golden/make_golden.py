@@ -136,12 +136,95 @@ def autocast_train_golden(hw, mp, sce):
     np.savez_compressed(os.path.join(HERE, "autocast_train.npz"), **out)
 
 
+def ref_params_with_window(mp, W, classes=10, T=16):
+    """The reference's HWGATEParams with another window_size: the class hard-codes 16 in __init__ and derives adj_mat
+    there, so the attribute is set afterwards and adj_mat re-derived by the reference's own get_adj_mat()
+    (model_params.py:373-400), which reads self.window_size."""
+    params = mp.HWGATEParams({"num_class": classes, "src_len": T}, 2, "cpu")
+    params.window_size = W
+    params.adj_mat = torch.tensor(params.get_adj_mat(), dtype=torch.float32)
+    params.drop_rate = 0.0
+    return params
+
+
+def larger_windows_golden(hw, mp, sce):
+    """Section 6: window_size 32 and 64 (N = 64 / 128 tokens per window; BASELINE configs[4] "larger temporal
+    windows"), which the unmodified reference runs (HWGATE.py:30-36, 290-291): masks, attention core, full model."""
+    from oracle import hwgate_oracle as O
+    out = {}
+    for W in (32, 64):
+        params = ref_params_with_window(mp, W)
+        nW = 64 // W
+        out[f"adj_W{W}"] = params.adj_mat.numpy().astype(np.uint8)
+        for F in (8, 4):
+            for shift in (0, 1):
+                blk = hw.PartAttentionBlock(dim=128, num_kps=64, num_heads=2, window_size=W, temporal_patch_size=2,
+                                            temporal_dim=F, shift_size=shift, adj_mat=None)
+                full = torch.concatenate([params.adj_mat for _ in range(F // 2)])
+                if blk.attn_mask is not None:
+                    full = full * blk.attn_mask
+                out[f"bits_W{W}_F{F}_s{shift}"] = O.pack_mask_bits(full.numpy() != 0)
+        for (d, h) in ((128, 2), (256, 4)):
+            for shift in (0, 1):
+                for thr in (None, 0.04):
+                    B, F, std = 1, 4, 0.2
+                    rng = np.random.default_rng(3000 + d + 10 * shift + W)
+                    xn = torch.from_numpy(rng.standard_normal((B, F, 64, d)))
+                    w = torch.from_numpy(rng.standard_normal((3 * d, d)) * std)
+                    b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1)
+                    g = torch.from_numpy(rng.standard_normal((B, F, 64, d)))
+                    blk = hw.PartAttentionBlock(dim=d, num_kps=64, num_heads=h, window_size=W, temporal_patch_size=2,
+                                                temporal_dim=F, shift_size=shift,
+                                                adj_mat=torch.concatenate([params.adj_mat] * (F // 2)).double(),
+                                                drop=0.0).double()
+                    msa = blk.attn
+                    with torch.no_grad():
+                        msa.qkv.weight.copy_(w); msa.qkv.bias.copy_(b)
+                        msa.proj.weight.copy_(torch.eye(d, dtype=torch.float64)); msa.proj.bias.zero_()
+                    msa.train(thr is not None)
+                    xn_ = xn.clone().requires_grad_(True)
+                    xs = torch.roll(xn_, shifts=-shift, dims=1) if shift else xn_
+                    xw = hw.window_partition(xs, W, 2)
+                    with patched_rand([thr] if thr is not None else []):
+                        yw = msa(xw, B, F // 2, nW, mask=blk.attn_mask)
+                    y = hw.window_reverse(yw, W, 2, F, 64)
+                    y = torch.roll(y, shifts=shift, dims=1) if shift else y
+                    (y * g).sum().backward()
+                    key = f"W{W}_d{d}_s{shift}_thr{thr}"
+                    out[key + "_y"], out[key + "_ysum"] = sample(y, 61)
+                    out[key + "_dx"], out[key + "_dxsum"] = sample(xn_.grad, 61)
+                    out[key + "_dw"], out[key + "_dwsum"] = sample(msa.qkv.weight.grad, 251)
+                    out[key + "_db"] = msa.qkv.bias.grad.numpy().copy()
+        # full model, T = 16, 10 classes, eval and train (fp64)
+        cfg = O.HWGATEConfig(temporal_dim=16, num_classes=10, window_size=W, edges=O.HWGATEConfig().edges[:nW])
+        sd = O.make_state_dict(cfg, seed=1001, weight_std=0.05)
+        params = ref_params_with_window(mp, W)
+        model = hw.Model(*params.get_model_params())
+        model.load_state_dict(sd, strict=True)
+        model = model.double()
+        for layer in model.layers:
+            layer.adj_mat = layer.adj_mat.double()
+            for blk in layer.blocks:
+                blk.attn.adj_mat = blk.attn.adj_mat.double()
+        x = O.synthetic_keypoints(2, 16, 2, seed=1001).double()
+        model.eval()
+        with torch.no_grad():
+            out[f"model_W{W}_eval_logits"] = model(x).numpy()
+        model.train()
+        with patched_rand(AUTOCAST_THR):
+            out[f"model_W{W}_train_logits"] = model(x).detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "larger_windows.npz"), **out)
+
+
 def main():
     from oracle import hwgate_oracle as O
     hw, mp, sce = import_reference()
     torch.manual_seed(0)
     if "--only-autocast" in sys.argv:
         autocast_train_golden(hw, mp, sce)
+        return
+    if "--only-windows" in sys.argv:
+        larger_windows_golden(hw, mp, sce)
         return
     out = {}
 
@@ -254,6 +337,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "full_model.npz"), **full)
 
     autocast_train_golden(hw, mp, sce)
+    larger_windows_golden(hw, mp, sce)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -88,7 +88,13 @@ def test_attention_multi_tile_distinct_samples_vs_oracle(d, h, F):
         # per-sample errors: a single bad tile must not hide in the aggregate
         ey = ((y.double().cpu() - by).flatten(1).norm(dim=1) / by.flatten(1).norm(dim=1)).max().item()
         ex = ((dx.double().cpu() - bdx).flatten(1).norm(dim=1) / bdx.flatten(1).norm(dim=1)).max().item()
-        assert ey < BF16_TOL and ex < BF16_TOL, (thr, ey, ex)
+        # eval: continuous, every sample within the tolerance.  train: the threshold decisions of a few borderline
+        # logits differ between the kernel's fp32 accumulation order and the oracle's (HWGATE.py:94-100 is
+        # discontinuous), which moves whole rows of a sample: the aggregate stays within the tolerance, one sample
+        # may not, so its bound is looser - a tile that read a neighbour's data would be O(1) off.
+        per_sample = BF16_TOL if thr is None else 8e-2
+        assert ey < per_sample and ex < per_sample, (thr, ey, ex)
+        assert rel_l2(y, by) < BF16_TOL and rel_l2(dx, bdx) < BF16_TOL, (thr, rel_l2(y, by), rel_l2(dx, bdx))
         assert rel_l2(dw, bdw) < BF16_TOL and rel_l2(db, bdb) < BF16_TOL
 
 
@@ -392,3 +398,126 @@ def test_second_device_in_one_process():
         outs.append((y.detach().cpu(), x_.grad.cpu(), w_.grad.cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert rel_l2(outs[0][2], outs[1][2]) < 1e-5
+
+
+# ------------------------------------------------------------------ K4 folded into K6 / K5'
+@pytest.mark.parametrize("d,F,B", [(128, 8, 3), (256, 4, 2), (128, 64, 5)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_merge_fold_equals_k6_k4_k5(d, F, B, p):
+    """bias_dropout_add_merge_ln (K6 storing TemporalMerging's layout + K5 over the merged rows; backward K5' storing
+    un-merged + K6') against the three separate ops K6 -> K4 -> K5: same dropout stream, so forward is bit-identical
+    and the gradients agree to fp32 rounding of the atomically summed column reductions."""
+    from sl_hwgat_b200 import ops
+    g = torch.Generator().manual_seed(d + F)
+    res = torch.randn(B, F, 64, d, generator=g).cuda()
+    a0 = torch.randn(B, F, 64, d, generator=g).to(torch.bfloat16).cuda()
+    bias = torch.randn(d, generator=g).cuda()
+    norm = torch.nn.LayerNorm(2 * d).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.1 * torch.randn(2 * d, generator=g))
+        norm.bias.copy_(0.1 * torch.randn(2 * d, generator=g))
+    gx = torch.randn(B, F // 2, 64, 2 * d, generator=g).cuda()
+    gy = torch.randn(B, F // 2, 64, 2 * d, generator=g).to(torch.bfloat16).cuda()
+
+    def run(folded):
+        r, a, b_ = res.clone().requires_grad_(True), a0.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+        norm.zero_grad()
+        torch.manual_seed(11); torch.cuda.manual_seed(11)
+        if folded:
+            xm, y = ops.bias_dropout_add_merge_ln(r, a, b_, norm, p, True)
+        else:
+            x1, _ = ops.bias_dropout_add_ln(r, a, b_, None, p, True)
+            xm = ops.temporal_merge(x1)
+            xm, y = ops.layer_norm_residual(xm, norm.weight, norm.bias, norm.eps)
+        torch.autograd.backward([xm, y], [gx, gy])
+        return xm.detach(), y.detach(), r.grad, a.grad, b_.grad, norm.weight.grad.clone(), norm.bias.grad.clone()
+
+    f, u = run(True), run(False)
+    assert torch.equal(f[0], u[0]) and torch.equal(f[1], u[1])
+    assert torch.equal(f[2], u[2]) and torch.equal(f[3], u[3])          # d_res, d_a0: row-local, bit-identical
+    for i in (4, 5, 6):
+        assert rel_l2(f[i], u[i]) < 1e-5, i
+    # and against PyTorch in fp64 when there is no dropout
+    if p == 0.0:
+        x1 = res.double() + a0.double() + bias.double()
+        xm_ref = O.temporal_merge(x1.cpu(), 2)
+        assert rel_inf(f[0], xm_ref) < 1e-6
+        y_ref = torch.nn.functional.layer_norm(xm_ref, (2 * d,), norm.weight.double().cpu(), norm.bias.double().cpu(), 1e-5)
+        assert rel_l2(f[1], y_ref) < 4e-3
+
+
+def test_model_uses_merge_fold_and_matches_unfolded():
+    """The full model takes the folded path under autocast (no K4 launches) and gives the same logits / gradients as
+    the per-layer path that still launches K4."""
+    from sl_hwgat_b200 import _lib
+    m, cfg, sd = build(16, 10, drop=0.0)
+    m.train()
+    x = O.synthetic_keypoints(2, 16, 2, seed=3).cuda()
+    y = O.synthetic_labels(2, 10, seed=3).cuda()
+    thr = THR
+    calls = {"merge": 0}
+    lib = _lib.load()
+    real = lib.hwgat_merge_fwd
+
+    def counting(*a):
+        calls["merge"] += 1
+        return real(*a)
+    lib.hwgat_merge_fwd = counting
+    try:
+        logits, loss, grads = _run_model(m, x, y, thr, autocast=True)
+        assert calls["merge"] == 0
+        # per-layer path: call the layers one by one (each PartAttentionLayer.forward ends in its own K4)
+        m.zero_grad(set_to_none=True)
+        with patched_rand(thr), torch.autocast("cuda", dtype=torch.bfloat16):
+            from sl_hwgat_b200 import ops
+            h = ops.fourier_embed(x, m.B, m.pos_encoder.pe, 0.0, True)
+            for layer in m.layers:
+                h = layer(h)
+            feats = ops.layer_norm_mean_pool(h, m.norm.weight, m.norm.bias, m.norm.eps)
+            logits2 = ops.linear_f32(feats, m.head.weight, m.head.bias)
+            loss2 = O.smoothed_cross_entropy(logits2.float(), y)
+        loss2.backward()
+        assert calls["merge"] == 2
+    finally:
+        lib.hwgat_merge_fwd = real
+    assert torch.equal(logits, logits2.detach().float())
+    for n, p_ in m.named_parameters():
+        if p_.grad is not None:
+            assert rel_l2(p_.grad, grads[n]) < 1e-4, n
+
+
+# ------------------------------------------------------------------ K13 / K14: head and loss
+@pytest.mark.parametrize("n,d_in,d_out", [(2, 512, 262), (512, 512, 2002), (37, 128, 10), (5000, 64, 33)])
+def test_head_linear_f32(n, d_in, d_out):
+    from sl_hwgat_b200 import ops
+    g = torch.Generator().manual_seed(n + d_out)
+    x = torch.randn(n, d_in, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(d_out, d_in, generator=g) * 0.05).cuda().requires_grad_(True)
+    b = torch.randn(d_out, generator=g).cuda().requires_grad_(True)
+    gy = torch.randn(n, d_out, generator=g).cuda()
+    y = ops.linear_f32(x, w, b)
+    y.backward(gy)
+    xr, wr, br = (t.detach().double().cpu().requires_grad_(True) for t in (x, w, b))
+    yr = xr @ wr.t() + br
+    yr.backward(gy.double().cpu())
+    assert rel_inf(y, yr) < 1e-5
+    assert rel_inf(x.grad, xr.grad) < 1e-5 and rel_inf(w.grad, wr.grad) < 1e-5 and rel_inf(b.grad, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("rows,classes", [(2, 262), (512, 2002), (37, 10), (3, 5000)])
+@pytest.mark.parametrize("smooth", [0.01, 0.0, 0.2])
+def test_smooth_cross_entropy_kernel(rows, classes, smooth):
+    """K14 against the reference formula (SmoothCrossEntropy.py:35-39, restated in the oracle) in fp64."""
+    from sl_hwgat_b200.losses import SmoothedCrossEntropyLoss
+    g = torch.Generator().manual_seed(rows + classes)
+    z = (torch.randn(rows, classes, generator=g) * 3).cuda().requires_grad_(True)
+    t = torch.randint(0, classes, (rows,), generator=g).cuda()
+    loss = SmoothedCrossEntropyLoss(smooth)(z, t)
+    (loss * 1.7).backward()
+    zr = z.detach().double().cpu().requires_grad_(True)
+    ref = O.smoothed_cross_entropy(zr, t.cpu(), smooth)
+    (ref * 1.7).backward()
+    assert abs(loss.item() - ref.item()) < 1e-6 * max(1.0, abs(ref.item()))
+    assert rel_inf(z.grad, zr.grad) < 1e-5
+    # deterministic: two evaluations give the same bits
+    assert SmoothedCrossEntropyLoss(smooth)(z.detach(), t).item() == SmoothedCrossEntropyLoss(smooth)(z.detach(), t).item()

@@ -173,3 +173,87 @@ def test_bf16_rounding_model_is_close_to_fp32():
     y = O.attention_core(xn.float(), w.float(), b.float(), h, mask, 16, 2, 1)
     yb = O.attention_core(xn.float(), w.float(), b.float(), h, mask, 16, 2, 1, bf16_points=True)
     assert (y - yb).norm() / y.norm() < 2e-2
+
+
+# ------------------------------------------------------------------ larger windows (W = 32, 64; BASELINE configs[4])
+def _adj_w(W):
+    return O.window_adjacency(O.HWGATEConfig().edges[:64 // W], W, 2)
+
+
+def window_core_inputs(d, shift, W, B=1, F=4, std=0.2):
+    """Same seeded inputs as tests/golden/make_golden.py section 6."""
+    rng = np.random.default_rng(3000 + d + 10 * shift + W)
+    xn = torch.from_numpy(rng.standard_normal((B, F, 64, d)))
+    w = torch.from_numpy(rng.standard_normal((3 * d, d)) * std)
+    b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1)
+    g = torch.from_numpy(rng.standard_normal((B, F, 64, d)))
+    return xn, w, b, g
+
+
+@pytest.mark.parametrize("W", [32, 64])
+def test_larger_window_masks_bit_exact(golden_dir, W):
+    G = _load(golden_dir, "larger_windows.npz")
+    adj = _adj_w(W)
+    assert adj.shape == (64 // W, 2 * W, 2 * W)
+    assert np.array_equal(adj, G[f"adj_W{W}"].astype(bool))
+    for F in (8, 4):
+        for shift in (0, 1):
+            assert np.array_equal(O.pack_mask_bits(O.combined_mask(adj, F, W, 2, shift)), G[f"bits_W{W}_F{F}_s{shift}"])
+
+
+@pytest.mark.parametrize("W", [32, 64])
+@pytest.mark.parametrize("d,h", [(128, 2), (256, 4)])
+@pytest.mark.parametrize("shift", [0, 1])
+@pytest.mark.parametrize("thr", [None, 0.04])
+def test_larger_window_attention_core_matches_reference(golden_dir, W, d, h, shift, thr):
+    G = _load(golden_dir, "larger_windows.npz")
+    key = f"W{W}_d{d}_s{shift}_thr{thr}"
+    xn, w, b, g = window_core_inputs(d, shift, W)
+    mask = O.combined_mask(_adj_w(W), 4, W, 2, shift)
+    x_ = xn.clone().requires_grad_(True)
+    w_ = w.clone().requires_grad_(True)
+    b_ = b.clone().requires_grad_(True)
+    y = O.attention_core(x_, w_, b_, h, mask, W, 2, shift, thr)
+    (y * g).sum().backward()
+    cdx, cdw, cdb = O.attention_core_backward(xn, w, b, h, mask, W, 2, shift, thr, g)
+
+    def chk(t, name, stride):
+        a = t.detach().reshape(-1).numpy()
+        ref = G[key + "_" + name]
+        assert np.abs(a[::stride] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (key, name)
+        s = G[key + "_" + name + "sum"]
+        assert abs(a.sum() - s[0]) <= 1e-9 * s[1] and a.size == int(s[2])
+
+    chk(y, "y", 61)
+    chk(x_.grad, "dx", 61)
+    chk(w_.grad, "dw", 251)
+    assert np.abs(b_.grad.numpy() - G[key + "_db"]).max() <= 1e-9 * np.abs(G[key + "_db"]).max()
+    # closed-form backward == autograd
+    assert torch.allclose(cdx, x_.grad, rtol=1e-9, atol=1e-12) and torch.allclose(cdw, w_.grad, rtol=1e-9, atol=1e-11)
+    assert torch.allclose(cdb, b_.grad, rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("W", [32, 64])
+def test_larger_window_full_model_matches_reference(golden_dir, W):
+    G = _load(golden_dir, "larger_windows.npz")
+    cfg = O.HWGATEConfig(temporal_dim=16, num_classes=10, window_size=W, edges=O.HWGATEConfig().edges[:64 // W])
+    sd = {k: v.double() for k, v in O.make_state_dict(cfg, seed=1001, weight_std=0.05).items()}
+    x = O.synthetic_keypoints(2, 16, 2, seed=1001).double()
+    ev = O.model_forward(x, sd, cfg)
+    assert np.abs(ev.numpy() - G[f"model_W{W}_eval_logits"]).max() <= 1e-9 * np.abs(G[f"model_W{W}_eval_logits"]).max()
+    thr = [0.03, 0.05, 0.031, 0.2, 0.033, 0.04, 0.0312, 0.1]
+    tr = O.model_forward(x, sd, cfg, thresholds=thr)
+    assert np.abs(tr.numpy() - G[f"model_W{W}_train_logits"]).max() <= 1e-9 * np.abs(G[f"model_W{W}_train_logits"]).max()
+
+
+def test_autocast_golden_is_consistent_with_fp64_golden(golden_dir):
+    """tests/golden/autocast_train.npz (the reference under torch.autocast(bfloat16), train mode) sits within the
+    bf16 band of the fp64 goldens of the same case - the band the GPU bf16 tests are judged against."""
+    A, F = _load(golden_dir, "autocast_train.npz"), _load(golden_dir, "full_model.npz")
+    assert list(A["thr"]) == list(F["include_train_thr"])
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    assert rel(A["logits"], F["include_train_logits"]) < 2.5e-2
+    assert rel(A["eval_logits"], F["include_eval_logits"]) < 2e-2
+    assert list(A["gnames"]) == list(F["include_train_gnames"])
+    assert np.abs(A["gnorms"] - F["include_train_gnorms"]).max() / F["include_train_gnorms"].max() < 2e-2
+    assert int(A["goffsets"][-1]) == A["gsamples"].size
