@@ -226,9 +226,13 @@ int hwgat_ffn_bwd(const void* dv0, const void* h, const void* act, const void* g
 int hwgat_embed_fwd(const float* x, const float* Bm, const float* pe, float* out, long long n, int C, int E, int K,
                     int T, float p, unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
 /* K9: pooled(fp32, (B, d)) = mean over the `tokens` rows of each sample of LayerNorm(x; gamma, beta, eps);
- * mean / rstd (B*tokens) saved.  Replaces self.norm + self.avgpool (HWGATE.py:353-354).  d in {128,256,512}. */
+ * mean / rstd (B*tokens) saved.  Replaces self.norm + self.avgpool (HWGATE.py:353-354).  d in {128,256,512}.
+ * Small batches are split over several CTAs per sample; their partial sums go through `scratch`
+ * (hwgat_ln_pool_scratch_bytes, may be 0) and are added in a fixed order: the result is deterministic. */
+size_t hwgat_ln_pool_scratch_bytes(int B, int tokens, int d);
 int hwgat_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean,
-                      float* rstd, int B, int tokens, int d, float eps, hwgat_stream_t stream);
+                      float* rstd, void* scratch, size_t scratch_bytes, int B, int tokens, int d, float eps,
+                      hwgat_stream_t stream);
 /* K9': dx(fp32) of the above for g = d pooled (B, d); dgamma (d) overwritten (dbeta = column sums of g: caller). */
 int hwgat_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
                       float* dx, float* dgamma, int B, int tokens, int d, hwgat_stream_t stream);

@@ -390,14 +390,22 @@ int hwgat_embed_fwd(const float* x, const float* Bm, const float* pe, float* out
   return launch_embed_fwd(x, Bm, pe, out, n, C, E, K, T, p, seed, offset, (cudaStream_t)stream);
 }
 
+size_t hwgat_ln_pool_scratch_bytes(int B, int tokens, int d) {
+  if (B <= 0 || tokens <= 0 || (d != 128 && d != 256 && d != 512)) return 0;
+  return ln_pool_scratch_bytes(B, tokens, d);
+}
+
 int hwgat_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean,
-                      float* rstd, int B, int tokens, int d, float eps, hwgat_stream_t stream) {
+                      float* rstd, void* scratch, size_t scratch_bytes, int B, int tokens, int d, float eps,
+                      hwgat_stream_t stream) {
   if (B < 0 || tokens <= 0) return HWGAT_ERR_SHAPE;
   if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
   if (B == 0) return HWGAT_OK;
   if (!x || !gamma || !beta || !pooled || !mean || !rstd) return HWGAT_ERR_NULL;
   if (misaligned(x) || misaligned(gamma)) return HWGAT_ERR_ALIGN;
-  return launch_ln_pool_fwd(x, gamma, beta, pooled, mean, rstd, B, tokens, d, eps, (cudaStream_t)stream);
+  const size_t need = ln_pool_scratch_bytes(B, tokens, d);
+  if (need > 0 && (!scratch || scratch_bytes < need)) return HWGAT_ERR_WORKSPACE;
+  return launch_ln_pool_fwd(x, gamma, beta, pooled, mean, rstd, (float*)scratch, B, tokens, d, eps, (cudaStream_t)stream);
 }
 
 int hwgat_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,

@@ -72,20 +72,31 @@ struct Geo2 {
   }
 };
 
-// one [128 x 64] tile (columns col .. col+63 of the tile's 128 token rows) -> dst (16 KB, SWIZZLE_128B K-major)
-HW_DEV void load_tile(unsigned char* dst, const CUtensorMap* tm, uint64_t* bar, const Geo2& g, int tile, int col) {
+// one [128 x 64] tile (columns col .. col+63 of the tile's 128 token rows) -> dst (16 KB, SWIZZLE_128B K-major).
+// One TMA box per WINDOW: (64 columns, W keypoints, 2 frames) lands as the window's N rows in the reference's token
+// order tp * W + k (HWGATE.py:34-35) - 4 / 2 / 1 copies per tile instead of eight 16-token boxes (the producer lane
+// issued 24-32 copies per item and was the slowest role).  The shifted last temporal group wraps around (frames
+// F-1 and 0): it takes two one-frame boxes per window (tm1).
+template <int N>
+HW_DEV void load_tile(unsigned char* dst, const CUtensorMap* tm2, const CUtensorMap* tm1, uint64_t* bar, const Geo2& g,
+                      int tile, int col) {
   if (g.layout == HWGAT_LAYOUT_WINDOWS) {
-    tma_load_2d(dst, tm, bar, col, tile * 128);
+    tma_load_2d(dst, tm2, bar, col, tile * 128);
     return;
   }
+  constexpr int W = N / 2, wpt = 128 / N;
   int b, fi, kg;
   g.decode(tile, b, fi, kg);
+  const int fr0 = 2 * fi + g.shift;                 // <= F - 1
+  if (fr0 + 1 < g.F) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int r0 = 16 * j, w = r0 / g.N, rr = r0 - w * g.N, tp = rr / g.W, k0 = rr - tp * g.W;
-    int fr = 2 * fi + tp + g.shift;
-    fr = fr >= g.F ? fr - g.F : fr;
-    tma_load_4d(dst + j * 2048, tm, bar, col, kg * 64 + w * g.W + k0, fr, b);
+    for (int w = 0; w < wpt; ++w) tma_load_4d(dst + w * N * 128, tm2, bar, col, kg * 64 + w * W, fr0, b);
+  } else {
+#pragma unroll
+    for (int w = 0; w < wpt; ++w) {
+      tma_load_4d(dst + w * N * 128, tm1, bar, col, kg * 64 + w * W, fr0, b);
+      tma_load_4d(dst + (w * N + W) * 128, tm1, bar, col, kg * 64 + w * W, 0, b);
+    }
   }
 }
 
@@ -168,14 +179,16 @@ HW_DEV void masked_softmax_row(float (&v)[N], const uint32_t (&mw)[N / 32], floa
       v[i] = ((lv[i >> 5] >> (i & 31)) & 1u) ? v[i] : 0.f;
       sl += v[i];
     }
-    if (sl > 1e-30f) {
+    // tcgen05.ld is warp-collective (.sync.aligned): if ANY row of the warp needs the exact form, the whole warp reads
+    // its logits again and takes it (for the other rows it is the same softmax, rounded slightly differently)
+    if (__any_sync(0xffffffffu, !(sl > 1e-30f))) {
+      tmem_row<N>(taddr, v);
+      softmax_exact_row<N>(v, lv, dead);
+    } else {
       const float inv = 1.f / sl;
 #pragma unroll
       for (int i = 0; i < N; ++i) v[i] *= inv;
       dead = false;
-    } else {
-      tmem_row<N>(taddr, v);
-      softmax_exact_row<N>(v, lv, dead);
     }
   } else {
 #pragma unroll
@@ -199,14 +212,19 @@ struct CoreArgs {
 // ---------------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------------
+// TMEM of the forward: THREE S buffers (columns 0, 128, 256) and two O buffers (384, 448).  An S buffer is free again
+// as soon as its softmax has produced P, so S of item j+1 and j+2 are computed while item j is still being finished:
+// the S MMA and its latency never sit in front of a softmax warp.
 struct FwdBars {
   uint64_t in_full[3], in_empty[3];
-  uint64_t s_full[2], p_ready[2], o_full[2], t_empty[2];
+  uint64_t s_full[3], p_ready[2], o_full[2], o_empty[2];
   uint32_t tmem_slot;
 };
+constexpr int kOCol = 384;
 
 template <int N, bool kTrain>
 __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                         const __grid_constant__ CUtensorMap tmQKV1,
                                                                          const CoreArgs p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -222,13 +240,15 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
   for (int i = threadIdx.x; i < 2 * kPBytes / 16; i += blockDim.x) reinterpret_cast<int4*>(sP)[i] = make_int4(0, 0, 0, 0);
   fence_proxy_async();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 1); mbar_init(&bars->s_full[i], 1);
+    }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->s_full[i], 1); mbar_init(&bars->p_ready[i], 4);
-      mbar_init(&bars->o_full[i], 1); mbar_init(&bars->t_empty[i], 4);
+      mbar_init(&bars->p_ready[i], 4); mbar_init(&bars->o_full[i], 1); mbar_init(&bars->o_empty[i], 4);
     }
     mbar_fence_init();
     tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmQKV1);
   }
   if (warp == 1) tmem_alloc(&bars->tmem_slot, 512);
   tc_fence_before();
@@ -248,7 +268,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
           mbar_expect_tx(&bars->in_full[s], 3 * kTile);
           unsigned char* st = sIn + s * 3 * kTile;
 #pragma unroll
-          for (int q = 0; q < 3; ++q) load_tile(st + q * kTile, &tmQKV, &bars->in_full[s], p.geo, tile, q * p.d + h * kHd);
+          for (int q = 0; q < 3; ++q)
+            load_tile<N>(st + q * kTile, &tmQKV, &tmQKV1, &bars->in_full[s], p.geo, tile, q * p.d + h * kHd);
         }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1; }
@@ -261,34 +282,35 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
       auto issue_pv = [&](int i, int stage) {
         const int b = i & 1;
         mbar_wait(&bars->p_ready[b], (i >> 1) & 1);
+        mbar_wait(&bars->o_empty[b], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t sp = smem_u32(sP + b * kPBytes), sv = smem_u32(sIn + stage * 3 * kTile + 2 * kTile);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_bf16(tmem + b * 256 + 128, umma_desc_k_sw128(sp + (ks >> 2) * kTile + (ks & 3) * 32),
+            umma_bf16(tmem + kOCol + b * 64, umma_desc_k_sw128(sp + (ks >> 2) * kTile + (ks & 3) * 32),
                       umma_desc_mn_sw128(sv + ks * 2048, 8192, 1024), idO, ks != 0);
           umma_commit(&bars->o_full[b]);
           umma_commit(&bars->in_empty[stage]);
         }
         __syncwarp();
       };
+      int sb = 0;   // S buffer of item j = j % 3; it is free: P of item j-3 was waited for before PV(j-3) was issued
       for (int g = blockIdx.x; g < items; g += gridDim.x, ++j) {
-        const int b = j & 1;
         mbar_wait(&bars->in_full[s], ph);
-        mbar_wait(&bars->t_empty[b], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t sq = smem_u32(sIn + s * 3 * kTile), sk = sq + kTile;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(tmem + b * 256, umma_desc_k_sw128(sq + ks * 32), umma_desc_k_sw128(sk + ks * 32), idS, ks != 0);
-          umma_commit(&bars->s_full[b]);
+            umma_bf16(tmem + sb * 128, umma_desc_k_sw128(sq + ks * 32), umma_desc_k_sw128(sk + ks * 32), idS, ks != 0);
+          umma_commit(&bars->s_full[sb]);
         }
         __syncwarp();
         if (j > 0) issue_pv(j - 1, ps);
         ps = s;
         if (++s == S) { s = 0; ph ^= 1; }
+        if (++sb == 3) sb = 0;
       }
       if (j > 0) issue_pv(j - 1, ps);
     }
@@ -298,12 +320,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
     const int set = (warp - kFirstSoftWarp) >> 2;        // items with (j & 1) == set
     const int row = 32 * q + lane;
     const int win = row / N, col0 = win * N;             // the row's window = its live columns (warp-uniform)
-    const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16) + set * 256;
+    const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
     int j = 0;
     for (int g = blockIdx.x; g < items; g += gridDim.x, ++j) {
       if ((j & 1) != set) continue;
       const int tile = g / p.heads, h = g - tile * p.heads;
       const uint32_t par = (j >> 1) & 1;
+      const int sb = j % 3;
+      const uint32_t tq = tlane + sb * 128;
       uint32_t mw[N / 32];
       {
         const uint32_t* mp = p.bits + p.geo.mask_word(tile, row);
@@ -311,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
         for (int w = 0; w < N / 32; ++w) mw[w] = mp[w];
       }
       bf16* orow = p.out + (size_t)p.geo.token_row(tile, row) * p.d + h * kHd;
-      mbar_wait(&bars->s_full[set], par);
+      mbar_wait(&bars->s_full[sb], (j / 3) & 1);
       tc_fence_after();
       {
         float v[N];
@@ -329,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld32(tq + 128 + 32 * c, r);
+        tmem_ld32(tlane + kOCol + set * 64 + 32 * c, r);
         tmem_ld_wait();
 #pragma unroll
         for (int gq = 0; gq < 2; ++gq) {
@@ -342,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->t_empty[set]);
+      if (lane == 0) mbar_arrive(&bars->o_empty[set]);
     }
   }
   tc_fence_before();
@@ -362,7 +386,9 @@ struct BwdBars {
 
 template <int N, bool kTrain>
 __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                         const __grid_constant__ CUtensorMap tmQKV1,
                                                                          const __grid_constant__ CUtensorMap tmDO,
+                                                                         const __grid_constant__ CUtensorMap tmDO1,
                                                                          const CoreArgs p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -385,7 +411,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
     mbar_init(&bars->pds_empty, 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmQKV1);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDO1);
   }
   if (warp == 1) tmem_alloc(&bars->tmem_slot, 512);
   tc_fence_before();
@@ -405,8 +433,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
           mbar_expect_tx(&bars->in_full[s], 4 * kTile);
           unsigned char* st = sIn + s * 4 * kTile;
 #pragma unroll
-          for (int q = 0; q < 3; ++q) load_tile(st + q * kTile, &tmQKV, &bars->in_full[s], p.geo, tile, q * p.d + h * kHd);
-          load_tile(st + 3 * kTile, &tmDO, &bars->in_full[s], p.geo, tile, h * kHd);
+          for (int q = 0; q < 3; ++q)
+            load_tile<N>(st + q * kTile, &tmQKV, &tmQKV1, &bars->in_full[s], p.geo, tile, q * p.d + h * kHd);
+          load_tile<N>(st + 3 * kTile, &tmDO, &tmDO1, &bars->in_full[s], p.geo, tile, h * kHd);
         }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1; }
@@ -608,43 +637,46 @@ static int project_qkv(const AttnArgs& a, bf16* qkv, unsigned char* prep_ws, cud
 }
 
 template <int N>
-static int launch_core_fwd(const CUtensorMap& tm, const tc2::CoreArgs& p, bool train, int grid, int smem, cudaStream_t s) {
+static int launch_core_fwd(const CUtensorMap& tm, const CUtensorMap& tm1, const tc2::CoreArgs& p, bool train, int grid,
+                           int smem, cudaStream_t s) {
   static PerDeviceOnce once;
   once.run([] {
     cudaFuncSetAttribute(tc2::attn_core_fwd_tc2_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kMaxDynSmem2);
     cudaFuncSetAttribute(tc2::attn_core_fwd_tc2_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kMaxDynSmem2);
   });
-  if (train) tc2::attn_core_fwd_tc2_kernel<N, true><<<grid, tc2::kThreads, smem, s>>>(tm, p);
-  else tc2::attn_core_fwd_tc2_kernel<N, false><<<grid, tc2::kThreads, smem, s>>>(tm, p);
+  if (train) tc2::attn_core_fwd_tc2_kernel<N, true><<<grid, tc2::kThreads, smem, s>>>(tm, tm1, p);
+  else tc2::attn_core_fwd_tc2_kernel<N, false><<<grid, tc2::kThreads, smem, s>>>(tm, tm1, p);
   count_launch();
   return (int)cudaGetLastError();
 }
 
 template <int N>
-static int launch_core_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const tc2::CoreArgs& p, bool train, int grid,
-                           int smem, cudaStream_t s) {
+static int launch_core_bwd(const CUtensorMap& tm, const CUtensorMap& tm1, const CUtensorMap& tmdo, const CUtensorMap& tmdo1,
+                           const tc2::CoreArgs& p, bool train, int grid, int smem, cudaStream_t s) {
   static PerDeviceOnce once;
   once.run([] {
     cudaFuncSetAttribute(tc2::attn_core_bwd_tc2_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kMaxDynSmem2);
     cudaFuncSetAttribute(tc2::attn_core_bwd_tc2_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kMaxDynSmem2);
   });
-  if (train) tc2::attn_core_bwd_tc2_kernel<N, true><<<grid, tc2::kThreads, smem, s>>>(tm, tmdo, p);
-  else tc2::attn_core_bwd_tc2_kernel<N, false><<<grid, tc2::kThreads, smem, s>>>(tm, tmdo, p);
+  if (train) tc2::attn_core_bwd_tc2_kernel<N, true><<<grid, tc2::kThreads, smem, s>>>(tm, tm1, tmdo, tmdo1, p);
+  else tc2::attn_core_bwd_tc2_kernel<N, false><<<grid, tc2::kThreads, smem, s>>>(tm, tm1, tmdo, tmdo1, p);
   count_launch();
   return (int)cudaGetLastError();
 }
 
-static int make_row_map(CUtensorMap* tm, const void* base, const AttnArgs& a, int cols) {
+// tensor maps over the token rows of a (B, F, K, cols) tensor: boxes of (64 columns, W keypoints, `frames` frames)
+static int make_row_map(CUtensorMap* tm, const void* base, const AttnArgs& a, int cols, int W, int frames) {
   if (a.layout == HWGAT_LAYOUT_WINDOWS) return make_tmap_2d(tm, base, (uint64_t)a.tokens(), (uint64_t)cols, 128);
-  return make_tmap_4d(tm, base, (uint64_t)cols, (uint64_t)a.K, (uint64_t)a.F, (uint64_t)a.B, 16);
+  return make_tmap_4d(tm, base, (uint64_t)cols, (uint64_t)a.K, (uint64_t)a.F, (uint64_t)a.B, (uint32_t)W, (uint32_t)frames);
 }
 
 // forward: qkv (caller's buffer, kept for the backward) = xn . Wp^T + b ; out = attention core
 int attn2_fwd(const AttnArgs& a, int W, bf16* qkv, cudaStream_t s) {
   int st;
   if ((st = project_qkv(a, qkv, (unsigned char*)a.workspace, s))) return st;
-  CUtensorMap tm;
-  if ((st = make_row_map(&tm, qkv, a, 3 * a.d))) return st;
+  CUtensorMap tm, tm1;
+  if ((st = make_row_map(&tm, qkv, a, 3 * a.d, W, 2))) return st;
+  if ((st = make_row_map(&tm1, qkv, a, 3 * a.d, W, 1))) return st;
   tc2::CoreArgs p{};
   p.bits = a.bits; p.out = (bf16*)a.out; p.threshold = a.threshold; p.d = a.d; p.heads = a.heads; p.tiles = a.tiles();
   p.stages = 3;
@@ -654,9 +686,9 @@ int attn2_fwd(const AttnArgs& a, int W, bf16* qkv, cudaStream_t s) {
   const int smem = p.stages * 3 * tc2::kTile + 2 * tc2::kPBytes + (int)sizeof(tc2::FwdBars) + 1024;
   const bool train = a.threshold >= 0.f;
   switch (2 * W) {
-    case 32: return launch_core_fwd<32>(tm, p, train, grid, smem, s);
-    case 64: return launch_core_fwd<64>(tm, p, train, grid, smem, s);
-    case 128: return launch_core_fwd<128>(tm, p, train, grid, smem, s);
+    case 32: return launch_core_fwd<32>(tm, tm1, p, train, grid, smem, s);
+    case 64: return launch_core_fwd<64>(tm, tm1, p, train, grid, smem, s);
+    case 128: return launch_core_fwd<128>(tm, tm1, p, train, grid, smem, s);
   }
   return HWGAT_ERR_UNSUPPORTED;
 }
@@ -675,9 +707,11 @@ int attn2_bwd(const AttnArgs& a, int W, const bf16* qkv_saved, cudaStream_t s) {
     if ((st = project_qkv(a, q2, after + (size_t)n * d3 * sizeof(bf16), s))) return st;
     qkv = q2;
   }
-  CUtensorMap tm, tmdo;
-  if ((st = make_row_map(&tm, qkv, a, d3))) return st;
-  if ((st = make_row_map(&tmdo, a.d_out, a, d))) return st;
+  CUtensorMap tm, tm1, tmdo, tmdo1;
+  if ((st = make_row_map(&tm, qkv, a, d3, W, 2))) return st;
+  if ((st = make_row_map(&tm1, qkv, a, d3, W, 1))) return st;
+  if ((st = make_row_map(&tmdo, a.d_out, a, d, W, 2))) return st;
+  if ((st = make_row_map(&tmdo1, a.d_out, a, d, W, 1))) return st;
   tc2::CoreArgs p{};
   p.bits = a.bits; p.dqkv = dqkv; p.threshold = a.threshold; p.d = d; p.heads = a.heads; p.tiles = a.tiles();
   p.stages = 2;
@@ -687,9 +721,9 @@ int attn2_bwd(const AttnArgs& a, int W, const bf16* qkv_saved, cudaStream_t s) {
   const int smem = 2 * 4 * tc2::kTile + 2 * tc2::kPBytes + (int)sizeof(tc2::BwdBars) + 1024;
   const bool train = a.threshold >= 0.f;
   switch (2 * W) {
-    case 32: st = launch_core_bwd<32>(tm, tmdo, p, train, grid, smem, s); break;
-    case 64: st = launch_core_bwd<64>(tm, tmdo, p, train, grid, smem, s); break;
-    case 128: st = launch_core_bwd<128>(tm, tmdo, p, train, grid, smem, s); break;
+    case 32: st = launch_core_bwd<32>(tm, tm1, tmdo, tmdo1, p, train, grid, smem, s); break;
+    case 64: st = launch_core_bwd<64>(tm, tm1, tmdo, tmdo1, p, train, grid, smem, s); break;
+    case 128: st = launch_core_bwd<128>(tm, tm1, tmdo, tmdo1, p, train, grid, smem, s); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   if (st) return st;

@@ -58,20 +58,20 @@ HW_DEV void fold_groups(float4 (&a)[4]) {
 // The last K6 of a level stores its rows through this map (forward), and the first LayerNorm-backward of the next
 // level stores each half of its 2d-wide rows through the inverse (backward), so K4 and its adjoint are not launched.
 // ---------------------------------------------------------------------------
+// (row indices fit 31 bits: the C ABI refuses more than 2^29 tokens; 32-bit divisions)
 HW_DEV long long merged_row(long long r, int F, int K) {
-  const long long bf = r / K;
-  const int k = (int)(r - bf * K);
-  const long long b = bf / F;
-  const int fr = (int)(bf - b * F);
-  return ((((b * (F >> 1)) + (fr >> 1)) * K + k) << 1) | (fr & 1);
+  const uint32_t r32 = (uint32_t)r;
+  const uint32_t bf = r32 / (uint32_t)K, k = r32 - bf * (uint32_t)K;
+  const uint32_t b = bf / (uint32_t)F, fr = bf - b * (uint32_t)F;
+  return (long long)((((b * (uint32_t)(F >> 1)) + (fr >> 1)) * (uint32_t)K + k) << 1 | (fr & 1u));
 }
-// inverse, for row R of the MERGED tensor (F2 = F/2 frames) and half tp: the un-merged d-wide row
-HW_DEV long long unmerged_row(long long R, int tp, int F2, int K) {
-  const long long bf = R / K;
-  const int k = (int)(R - bf * K);
-  const long long b = bf / F2;
-  const int fi = (int)(bf - b * F2);
-  return ((b * (2 * F2) + 2 * fi + tp) * K + k);
+// inverse, for row R of the MERGED tensor (F2 = F/2 frames): the un-merged d-wide row of its FIRST half (frame 2 fi);
+// the second half (frame 2 fi + 1) is K rows further
+HW_DEV long long unmerged_row0(long long R, int F2, int K) {
+  const uint32_t r32 = (uint32_t)R;
+  const uint32_t bf = r32 / (uint32_t)K, k = r32 - bf * (uint32_t)K;
+  const uint32_t b = bf / (uint32_t)F2, fi = bf - b * (uint32_t)F2;
+  return (long long)((b * (uint32_t)(2 * F2) + 2u * fi) * (uint32_t)K + k);
 }
 
 template <int kL>
@@ -161,6 +161,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
     }
     const float m1 = group_sum<kL>(s1) * (1.f / d), m2 = group_sum<kL>(s2) * (1.f / d);
     if (!ok) continue;
+    // output row pointers of the two halves of the row (chunks i = 0, 1 are columns < d/2; i = 2, 3 the rest).
+    // Un-merge: the row is a merged 2 x (d/2) row; its halves go to frames 2 fi and 2 fi + 1 of the (B, F, K, d/2)
+    // tensor, K rows apart.  o1 is biased by -d/2 so that both halves index with the merged column.
+    float* o0 = dx + row * d;
+    float* o1 = o0;
+    if (uF2) {
+      o0 = dx + unmerged_row0(row, uF2, uK) * (d / 2);
+      o1 = o0 + (long long)uK * (d / 2) - d / 2;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float4 o = make_float4(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2),
@@ -169,12 +178,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
         const float4 r = *reinterpret_cast<const float4*>(dres + row * d + i * 4 * kL + lc * 4);
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
-      if (uF2) {   // un-merge: this row is a merged 2 x (d/2) row; columns < d/2 belong to frame 2 fi, the rest to 2 fi + 1
-        const int c = i * 4 * kL + lc * 4, tp = c >= d / 2;
-        *reinterpret_cast<float4*>(dx + unmerged_row(row, tp, uF2, uK) * (d / 2) + (c - tp * (d / 2))) = o;
-      } else {
-        *reinterpret_cast<float4*>(dx + row * d + i * 4 * kL + lc * 4) = o;
-      }
+      *reinterpret_cast<float4*>((i < 2 ? o0 : o1) + i * 4 * kL + lc * 4) = o;
     }
   }
   fold_groups<kL>(dg);
@@ -635,7 +639,8 @@ template <int kV>
 __global__ void __launch_bounds__(256) ln_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ pooled,
                                                           float* __restrict__ mean, float* __restrict__ rstd,
-                                                          int tokens, int slices, float eps) {
+                                                          float* __restrict__ scratch, int tokens, int slices,
+                                                          float eps) {
   constexpr int d = kV * 128;
   __shared__ float red[8][d];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -677,10 +682,21 @@ __global__ void __launch_bounds__(256) ln_pool_fwd_kernel(const float* __restric
     float a = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) a += red[w][c];
-    float val = a * inv * gamma[c];
-    if (sl == 0) val += beta[c];
-    atomicAdd(pooled + (long long)b * d + c, val);
+    if (slices == 1) pooled[(long long)b * d + c] = a * inv * gamma[c] + beta[c];
+    else scratch[((long long)b * slices + sl) * d + c] = a;       // summed in a fixed order by ln_pool_finish_kernel
   }
+}
+
+// pooled[b, c] = (sum over the slices, in slice order) / tokens * gamma[c] + beta[c]: deterministic (no atomics)
+__global__ void ln_pool_finish_kernel(const float* __restrict__ scratch, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float* __restrict__ pooled, int B, int d,
+                                      int slices, float inv) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * d) return;
+  const int b = idx / d, c = idx - b * d;
+  float a = 0.f;
+  for (int sl = 0; sl < slices; ++sl) a += scratch[((long long)b * slices + sl) * d + c];
+  pooled[idx] = a * inv * gamma[c] + beta[c];
 }
 
 // K9': dx[b, t, :] = LayerNorm'(g[b, :] / tokens) per row;  dgamma += sum_rows (g/tokens) * xhat ; dbeta = sum_b g
@@ -743,17 +759,25 @@ static int pool_slices(int B, int tokens) {
   return s < 1 ? 1 : s;
 }
 
+size_t ln_pool_scratch_bytes(int B, int tokens, int d) {
+  const int slices = pool_slices(B, tokens);
+  return slices > 1 ? sizeof(float) * (size_t)B * slices * d : 0;
+}
+
 int launch_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean, float* rstd,
-                       int B, int tokens, int d, float eps, cudaStream_t s) {
-  cudaMemsetAsync(pooled, 0, sizeof(float) * (size_t)B * d, s);
+                       float* scratch, int B, int tokens, int d, float eps, cudaStream_t s) {
   const int slices = pool_slices(B, tokens);
   switch (d) {
-    case 128: ln_pool_fwd_kernel<1><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, tokens, slices, eps); break;
-    case 256: ln_pool_fwd_kernel<2><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, tokens, slices, eps); break;
-    case 512: ln_pool_fwd_kernel<4><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, tokens, slices, eps); break;
+    case 128: ln_pool_fwd_kernel<1><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps); break;
+    case 256: ln_pool_fwd_kernel<2><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps); break;
+    case 512: ln_pool_fwd_kernel<4><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();
+  if (slices > 1) {
+    ln_pool_finish_kernel<<<(B * d + 255) / 256, 256, 0, s>>>(scratch, gamma, beta, pooled, B, d, slices, 1.f / tokens);
+    count_launch();
+  }
   return (int)cudaGetLastError();
 }
 

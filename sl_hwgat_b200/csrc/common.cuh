@@ -147,8 +147,9 @@ int launch_bias_gelu_dropout(const __nv_bfloat16* u0, const float* bias, const _
 
 int launch_embed_fwd(const float* x, const float* Bm, const float* pe, float* out, long long n, int C, int E, int K,
                      int T, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s);
+size_t ln_pool_scratch_bytes(int B, int tokens, int d);
 int launch_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean, float* rstd,
-                       int B, int tokens, int d, float eps, cudaStream_t s);
+                       float* scratch, int B, int tokens, int d, float eps, cudaStream_t s);
 int launch_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
                        float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s);
 

@@ -41,12 +41,12 @@ int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t col
 }
 
 int make_tmap_4d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
-                 uint32_t box1) {
+                 uint32_t box1, uint32_t box2) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   cuuint64_t gdim[4] = {d0, d1, d2, d3};
   cuuint64_t gstr[3] = {d0 * sizeof(bf16), d0 * d1 * sizeof(bf16), d0 * d1 * d2 * sizeof(bf16)};
-  cuuint32_t box[4] = {64, box1, 1, 1};
+  cuuint32_t box[4] = {64, box1, box2, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

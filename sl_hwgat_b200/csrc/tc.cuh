@@ -211,7 +211,8 @@ HW_DEV void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" :::
 // ---- host: tensor maps -----------------------------------------------------------
 // 2-D bf16 row-major matrix [rows][cols], box [box_rows][64 cols] landing as 128-byte swizzled rows.
 int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
-// 4-D bf16 tensor [d3][d2][d1][d0] (d0 contiguous), box [1][1][box1][64].
-int make_tmap_4d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t box1);
+// 4-D bf16 tensor [d3][d2][d1][d0] (d0 contiguous), box [1][box2][box1][64].
+int make_tmap_4d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t box1,
+                 uint32_t box2 = 1);
 
 }  // namespace hwgat

@@ -706,10 +706,12 @@ class _LayerNormPool(torch.autograd.Function):
         pooled = torch.empty((Bsz, d), dtype=torch.float32, device=x_c.device)
         mean = torch.empty(Bsz * tokens, dtype=torch.float32, device=x_c.device)
         rstd = torch.empty(Bsz * tokens, dtype=torch.float32, device=x_c.device)
+        sc_bytes = lib.hwgat_ln_pool_scratch_bytes(Bsz, tokens, d)
+        scratch = torch.empty(sc_bytes, dtype=torch.uint8, device=x_c.device) if sc_bytes else None
         with torch.cuda.device(x_c.device):
             check(lib.hwgat_ln_pool_fwd(x_c.data_ptr(), g_c.data_ptr(), b_c.data_ptr(), pooled.data_ptr(),
-                                        mean.data_ptr(), rstd.data_ptr(), Bsz, tokens, d, float(eps), _stream()),
-                  "hwgat_ln_pool_fwd")
+                                        mean.data_ptr(), rstd.data_ptr(), _ptr(scratch), sc_bytes, Bsz, tokens, d,
+                                        float(eps), _stream()), "hwgat_ln_pool_fwd")
         ctx.save_for_backward(x_c, g_c, mean, rstd)
         ctx.meta = (Bsz, tokens, d, gamma.dtype, beta.dtype)
         return pooled

@@ -167,7 +167,8 @@ def larger_windows_golden(hw, mp, sce):
         for (d, h) in ((128, 2), (256, 4)):
             for shift in (0, 1):
                 for thr in (None, 0.04):
-                    B, F, std = 1, 4, 0.2
+                    B, F = 1, 4
+                    std = 0.2 if d == 128 else 0.1     # logits of the same spread at both widths (std * sqrt(d))
                     rng = np.random.default_rng(3000 + d + 10 * shift + W)
                     xn = torch.from_numpy(rng.standard_normal((B, F, 64, d)))
                     w = torch.from_numpy(rng.standard_normal((3 * d, d)) * std)

@@ -199,17 +199,26 @@ def test_model_bf16_train_vs_reference_autocast_golden(golden_dir):
     assert gap_ours < max(BF16_TOL, 1.25 * gap_ref)
     assert gap_between < gap_ref + gap_ours + 5e-3
     assert abs(loss - float(G["loss"])) < 1e-2 * abs(float(G["loss"]))
-    # gradients: strided samples of every parameter's gradient as the reference's autocast run produced them
+    # gradients: strided samples of every parameter's gradient as the reference's autocast run produced them, next to
+    # the same samples of the fp64 oracle gradients.  The reference's OWN autocast run is up to 11.5 % (LayerNorm
+    # weights) and ~5 % (fc1 / proj / qkv weights of level 0) away from its fp64 gradients on these samples, so the
+    # statement checked per parameter is: this path is at least as close to the fp64 reference as the reference's
+    # autocast run is (x1.25 + 1e-2), and never further than 5e-2.
+    r_logits, r_loss, r_grads = _oracle_grads(sd, cfg, x, y, thr)
     stride, offs = int(G["stride"]), G["goffsets"]
-    bad = []
+    bad, worst_ref, worst_ours = [], 0.0, 0.0
     for i, name in enumerate(G["gnames"]):
         g = grads[str(name)].detach().float().reshape(-1).cpu().numpy()[::stride]
-        ref = G["gsamples"][offs[i]:offs[i + 1]]
-        assert g.shape == ref.shape, name
-        err = np.linalg.norm(g - ref) / max(np.linalg.norm(ref), 1e-30)
+        ac = G["gsamples"][offs[i]:offs[i + 1]]
+        r64 = r_grads[str(name)].detach().reshape(-1).cpu().numpy()[::stride]
+        assert g.shape == ac.shape == r64.shape, name
+        nrm = max(np.linalg.norm(r64), 1e-30)
+        gap_ref_i, gap_ours_i = np.linalg.norm(ac - r64) / nrm, np.linalg.norm(g - r64) / nrm
+        worst_ref, worst_ours = max(worst_ref, gap_ref_i), max(worst_ours, gap_ours_i)
         nerr = abs(np.linalg.norm(grads[str(name)].double().cpu().numpy()) - G["gnorms"][i]) / G["gnorms"][i]
-        if err > 8e-2 or nerr > 3e-2:
-            bad.append((str(name), float(err), float(nerr)))
+        if gap_ours_i > min(5e-2, 1.25 * gap_ref_i + 1e-2) or nerr > 3e-2:
+            bad.append((str(name), float(gap_ours_i), float(gap_ref_i), float(nerr)))
+    print(f"gradient samples vs fp64: worst reference-autocast {worst_ref:.3e}, worst ours {worst_ours:.3e}")
     assert not bad, bad
     # eval mode (no threshold): continuous, so the plain 2e-2 applies between the two bf16 runs
     m.eval()

@@ -180,8 +180,9 @@ def _adj_w(W):
     return O.window_adjacency(O.HWGATEConfig().edges[:64 // W], W, 2)
 
 
-def window_core_inputs(d, shift, W, B=1, F=4, std=0.2):
+def window_core_inputs(d, shift, W, B=1, F=4, std=None):
     """Same seeded inputs as tests/golden/make_golden.py section 6."""
+    std = (0.2 if d == 128 else 0.1) if std is None else std
     rng = np.random.default_rng(3000 + d + 10 * shift + W)
     xn = torch.from_numpy(rng.standard_normal((B, F, 64, d)))
     w = torch.from_numpy(rng.standard_normal((3 * d, d)) * std)
