@@ -228,14 +228,19 @@ int hwgat_embed_fwd(const float* x, const float* Bm, const float* pe, float* out
 /* K9: pooled(fp32, (B, d)) = mean over the `tokens` rows of each sample of LayerNorm(x; gamma, beta, eps);
  * mean / rstd (B*tokens) saved.  Replaces self.norm + self.avgpool (HWGATE.py:353-354).  d in {128,256,512}.
  * Small batches are split over several CTAs per sample; their partial sums go through `scratch`
- * (hwgat_ln_pool_scratch_bytes, may be 0) and are added in a fixed order: the result is deterministic. */
+ * (hwgat_ln_pool_scratch_bytes, may be 0) and are added in a fixed order: the result is deterministic.
+ * kp_real / kp_pad (0, 0 = none): a padded keypoint axis - the sibling model HGATE has 29 keypoints, stored as 32
+ * (HGATE.py:341): `tokens` counts the real tokens (frames * kp_real), the rows are stored frames * kp_pad per sample,
+ * mean / rstd have B * frames * kp_pad entries and only the real rows are pooled.                                */
 size_t hwgat_ln_pool_scratch_bytes(int B, int tokens, int d);
 int hwgat_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean,
                       float* rstd, void* scratch, size_t scratch_bytes, int B, int tokens, int d, float eps,
-                      hwgat_stream_t stream);
-/* K9': dx(fp32) of the above for g = d pooled (B, d); dgamma (d) overwritten (dbeta = column sums of g: caller). */
+                      int kp_real, int kp_pad, hwgat_stream_t stream);
+/* K9': dx(fp32) of the above for g = d pooled (B, d); dgamma (d) overwritten (dbeta = column sums of g: caller).
+ * With a padded keypoint axis the padded rows of dx are NOT written (the caller zero-fills dx).                  */
 int hwgat_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
-                      float* dx, float* dgamma, int B, int tokens, int d, hwgat_stream_t stream);
+                      float* dx, float* dgamma, int B, int tokens, int d, int kp_real, int kp_pad,
+                      hwgat_stream_t stream);
 
 /* ---- training loop ------------------------------------------------------ */
 

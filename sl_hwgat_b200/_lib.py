@@ -53,8 +53,8 @@ SIGNATURES = {
     "hwgat_embed_fwd": (c_int, [c_void_p] * 4 + [c_longlong, c_int, c_int, c_int, c_int, c_float, c_ulonglong,
                                                  c_ulonglong, c_void_p]),
     "hwgat_ln_pool_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "hwgat_ln_pool_fwd": (c_int, [c_void_p] * 7 + [c_size_t, c_int, c_int, c_int, c_float, c_void_p]),
-    "hwgat_ln_pool_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p]),
+    "hwgat_ln_pool_fwd": (c_int, [c_void_p] * 7 + [c_size_t, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
+    "hwgat_ln_pool_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hwgat_ffn_fwd": (c_int, [c_void_p] * 7 + [c_longlong, c_int, c_int, c_float, c_ulonglong, c_ulonglong,
                                c_void_p]),
     "hwgat_ffn_bwd_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int]),

@@ -126,7 +126,8 @@ static int check_geometry2(int B, int F, int K, int d, int heads, int W, int TP,
   if (layout != HWGAT_LAYOUT_BFKD && layout != HWGAT_LAYOUT_WINDOWS) return HWGAT_ERR_UNSUPPORTED;
   if ((W != 16 && W != 32 && W != 64) || TP != kTP) return HWGAT_ERR_UNSUPPORTED;
   if (d != heads * kHd || d > 512 || d % 128 != 0) return HWGAT_ERR_UNSUPPORTED;
-  if (F % TP != 0 || K % 64 != 0) return HWGAT_ERR_UNSUPPORTED;
+  // whole windows per keypoint axis and whole 128-token tiles per sample (a tile is 128 / (2 W) consecutive windows)
+  if (F % TP != 0 || K % W != 0 || ((F / TP) * (K / W)) % (64 / W) != 0) return HWGAT_ERR_UNSUPPORTED;
   if (shift < 0 || shift >= TP) return HWGAT_ERR_SHAPE;
   if (layout == HWGAT_LAYOUT_WINDOWS && shift != 0) return HWGAT_ERR_SHAPE;
   if ((long long)B * F * K > 0x7fffffffLL / 4) return HWGAT_ERR_UNSUPPORTED;
@@ -395,27 +396,34 @@ size_t hwgat_ln_pool_scratch_bytes(int B, int tokens, int d) {
   return ln_pool_scratch_bytes(B, tokens, d);
 }
 
+static bool bad_pad(int tokens, int kp_real, int kp_pad) {
+  if (kp_real == 0 && kp_pad == 0) return false;
+  return kp_real <= 0 || kp_pad < kp_real || tokens % kp_real != 0;
+}
+
 int hwgat_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean,
                       float* rstd, void* scratch, size_t scratch_bytes, int B, int tokens, int d, float eps,
-                      hwgat_stream_t stream) {
-  if (B < 0 || tokens <= 0) return HWGAT_ERR_SHAPE;
+                      int kp_real, int kp_pad, hwgat_stream_t stream) {
+  if (B < 0 || tokens <= 0 || bad_pad(tokens, kp_real, kp_pad)) return HWGAT_ERR_SHAPE;
   if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
   if (B == 0) return HWGAT_OK;
   if (!x || !gamma || !beta || !pooled || !mean || !rstd) return HWGAT_ERR_NULL;
   if (misaligned(x) || misaligned(gamma)) return HWGAT_ERR_ALIGN;
   const size_t need = ln_pool_scratch_bytes(B, tokens, d);
   if (need > 0 && (!scratch || scratch_bytes < need)) return HWGAT_ERR_WORKSPACE;
-  return launch_ln_pool_fwd(x, gamma, beta, pooled, mean, rstd, (float*)scratch, B, tokens, d, eps, (cudaStream_t)stream);
+  return launch_ln_pool_fwd(x, gamma, beta, pooled, mean, rstd, (float*)scratch, B, tokens, d, eps, (cudaStream_t)stream,
+                            kp_real, kp_pad);
 }
 
 int hwgat_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
-                      float* dx, float* dgamma, int B, int tokens, int d, hwgat_stream_t stream) {
-  if (B < 0 || tokens <= 0) return HWGAT_ERR_SHAPE;
+                      float* dx, float* dgamma, int B, int tokens, int d, int kp_real, int kp_pad,
+                      hwgat_stream_t stream) {
+  if (B < 0 || tokens <= 0 || bad_pad(tokens, kp_real, kp_pad)) return HWGAT_ERR_SHAPE;
   if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
   if (!dgamma) return HWGAT_ERR_NULL;
   if (B > 0 && (!g || !x || !mean || !rstd || !gamma || !dx)) return HWGAT_ERR_NULL;
   if (misaligned(g) || misaligned(x) || misaligned(gamma) || misaligned(dx)) return HWGAT_ERR_ALIGN;
-  return launch_ln_pool_bwd(g, x, mean, rstd, gamma, dx, dgamma, B, tokens, d, (cudaStream_t)stream);
+  return launch_ln_pool_bwd(g, x, mean, rstd, gamma, dx, dgamma, B, tokens, d, (cudaStream_t)stream, kp_real, kp_pad);
 }
 
 int hwgat_adamw_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,

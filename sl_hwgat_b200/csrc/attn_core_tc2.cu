@@ -39,36 +39,36 @@ constexpr int kRegsDonor = 40, kRegsSoft = 232;
 constexpr int kTile = 128 * 128;            // bytes of a [128 x 64] bf16 tile
 constexpr int kPBytes = 2 * kTile;          // [128 x 128] bf16 as two 64-column chunks
 constexpr int kMaxDynSmem2 = 232448;
+constexpr int kPrefetchAhead = 3;           // producer: L2 prefetch distance in items
 constexpr float kLog2e = 1.4426950408889634f;
 
 HW_DEV void reg_dealloc_donor() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kRegsDonor)); }
 HW_DEV void reg_alloc_soft() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kRegsSoft)); }
 
+// Geometry.  A sample's windows are ordered (temporal group fi, keypoint window kwin) = the reference's window order
+// (HWGATE.py:34-35: index (b f + fi) nW + w); a tile is 128 / N consecutive windows of one sample.  At the reference's
+// K = 64 that is one temporal group (W = 16: 4 windows, W = 32: 2, W = 64: 1); at K = 128 half of one; at K = 32 (HGATE's
+// 29 keypoints padded to 32, one window of N = 64 per temporal group) two temporal groups.
 struct Geo2 {
-  int F, K, shift, layout, f, kgroups, W, N, wpt, nWt;   // wpt = windows per tile (64 / W), nWt = windows per frame pair
-  HW_DEV void decode(int tile, int& b, int& fi, int& kg) const {
-    const int tps = f * kgroups;
-    b = tile / tps;
-    const int r = tile - b * tps;
-    fi = r / kgroups;
-    kg = r - fi * kgroups;
-  }
+  int F, K, shift, layout, f, nWt, tps;   // nWt = K / W windows per temporal group, tps = tiles per sample
   // global token row of tile row `row` (HWGATE.py:197-201 without the copies)
+  template <int N>
   HW_DEV long long token_row(int tile, int row) const {
     if (layout == HWGAT_LAYOUT_WINDOWS) return (long long)tile * 128 + row;
-    int b, fi, kg;
-    decode(tile, b, fi, kg);
-    const int w = row / N, rr = row - w * N, tp = rr / W, k = rr - tp * W;
+    constexpr int W = N / 2, wpt = 128 / N;
+    const int b = tile / tps, w = row / N, widx = (tile - b * tps) * wpt + w;
+    const int fi = widx / nWt, kwin = widx - fi * nWt;
+    const int rr = row - w * N, tp = rr / W, k = rr - tp * W;
     int fr = 2 * fi + tp + shift;
     fr = fr >= F ? fr - F : fr;
-    return (long long)(b * F + fr) * K + kg * 64 + w * W + k;
+    return (long long)(b * F + fr) * K + kwin * W + k;
   }
   // first mask word of tile row `row`: bits is (f * nWt windows, N rows, N/32 words)
+  template <int N>
   HW_DEV long long mask_word(int tile, int row) const {
-    int b, fi, kg;
-    decode(tile, b, fi, kg);
-    const int w = row / N, rr = row - w * N;
-    return ((long long)(fi * nWt + kg * wpt + w) * N + rr) * (N / 32);
+    constexpr int wpt = 128 / N;
+    const int w = row / N, widx = (tile % tps) * wpt + w;
+    return ((long long)widx * N + (row - w * N)) * (N / 32);
   }
 };
 
@@ -76,7 +76,7 @@ struct Geo2 {
 // One TMA box per WINDOW: (64 columns, W keypoints, 2 frames) lands as the window's N rows in the reference's token
 // order tp * W + k (HWGATE.py:34-35) - 4 / 2 / 1 copies per tile instead of eight 16-token boxes (the producer lane
 // issued 24-32 copies per item and was the slowest role).  The shifted last temporal group wraps around (frames
-// F-1 and 0): it takes two one-frame boxes per window (tm1).
+// F-1 and 0): it takes two one-frame boxes per window (tm1).  Keypoints past K (a padded keypoint axis) read as zeros.
 template <int N>
 HW_DEV void load_tile(unsigned char* dst, const CUtensorMap* tm2, const CUtensorMap* tm1, uint64_t* bar, const Geo2& g,
                       int tile, int col) {
@@ -85,17 +85,38 @@ HW_DEV void load_tile(unsigned char* dst, const CUtensorMap* tm2, const CUtensor
     return;
   }
   constexpr int W = N / 2, wpt = 128 / N;
-  int b, fi, kg;
-  g.decode(tile, b, fi, kg);
-  const int fr0 = 2 * fi + g.shift;                 // <= F - 1
-  if (fr0 + 1 < g.F) {
+  const int b = tile / g.tps, w0 = (tile - b * g.tps) * wpt;
 #pragma unroll
-    for (int w = 0; w < wpt; ++w) tma_load_4d(dst + w * N * 128, tm2, bar, col, kg * 64 + w * W, fr0, b);
-  } else {
+  for (int w = 0; w < wpt; ++w) {
+    const int widx = w0 + w, fi = widx / g.nWt, kwin = widx - fi * g.nWt;
+    const int fr0 = 2 * fi + g.shift;                 // <= F - 1
+    if (fr0 + 1 < g.F) {
+      tma_load_4d(dst + w * N * 128, tm2, bar, col, kwin * W, fr0, b);
+    } else {
+      tma_load_4d(dst + w * N * 128, tm1, bar, col, kwin * W, fr0, b);
+      tma_load_4d(dst + (w * N + W) * 128, tm1, bar, col, kwin * W, 0, b);
+    }
+  }
+}
+
+// the same boxes, prefetched into L2 only (issued by the producer a few items ahead of the copy)
+template <int N>
+HW_DEV void prefetch_tile(const CUtensorMap* tm2, const CUtensorMap* tm1, const Geo2& g, int tile, int col) {
+  if (g.layout == HWGAT_LAYOUT_WINDOWS) {
+    tma_prefetch_2d(tm2, col, tile * 128);
+    return;
+  }
+  constexpr int W = N / 2, wpt = 128 / N;
+  const int b = tile / g.tps, w0 = (tile - b * g.tps) * wpt;
 #pragma unroll
-    for (int w = 0; w < wpt; ++w) {
-      tma_load_4d(dst + w * N * 128, tm1, bar, col, kg * 64 + w * W, fr0, b);
-      tma_load_4d(dst + (w * N + W) * 128, tm1, bar, col, kg * 64 + w * W, 0, b);
+  for (int w = 0; w < wpt; ++w) {
+    const int widx = w0 + w, fi = widx / g.nWt, kwin = widx - fi * g.nWt;
+    const int fr0 = 2 * fi + g.shift;
+    if (fr0 + 1 < g.F) {
+      tma_prefetch_4d(tm2, col, kwin * W, fr0, b);
+    } else {
+      tma_prefetch_4d(tm1, col, kwin * W, fr0, b);
+      tma_prefetch_4d(tm1, col, kwin * W, 0, b);
     }
   }
 }
@@ -263,6 +284,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
       uint32_t ph = 0;
       for (int g = blockIdx.x; g < items; g += gridDim.x) {
         const int tile = g / p.heads, h = g - tile * p.heads;
+        const int gp = g + kPrefetchAhead * (int)gridDim.x;      // the item kPrefetchAhead iterations ahead: into L2 now
+        if (gp < items && elect_one_sync()) {
+          const int tp = gp / p.heads, hp = gp - tp * p.heads;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) prefetch_tile<N>(&tmQKV, &tmQKV1, p.geo, tp, q * p.d + hp * kHd);
+        }
+        __syncwarp();
         mbar_wait(&bars->in_empty[s], ph ^ 1);
         if (elect_one_sync()) {
           mbar_expect_tx(&bars->in_full[s], 3 * kTile);
@@ -330,11 +358,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
       const uint32_t tq = tlane + sb * 128;
       uint32_t mw[N / 32];
       {
-        const uint32_t* mp = p.bits + p.geo.mask_word(tile, row);
+        const uint32_t* mp = p.bits + p.geo.mask_word<N>(tile, row);
 #pragma unroll
         for (int w = 0; w < N / 32; ++w) mw[w] = mp[w];
       }
-      bf16* orow = p.out + (size_t)p.geo.token_row(tile, row) * p.d + h * kHd;
+      bf16* orow = p.out + (size_t)p.geo.token_row<N>(tile, row) * p.d + h * kHd;
       mbar_wait(&bars->s_full[sb], (j / 3) & 1);
       tc_fence_after();
       {
@@ -428,6 +456,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
       uint32_t ph = 0;
       for (int g = blockIdx.x; g < items; g += gridDim.x) {
         const int tile = g / p.heads, h = g - tile * p.heads;
+        // only two 64 KB stages fit next to the P / dS tiles, and a stage is held until the item's last MMA: the
+        // boxes of the item kPrefetchAhead iterations ahead are pulled into L2 now, so the copy that refills a
+        // stage is an L2 hit instead of an HBM round trip
+        const int gp = g + kPrefetchAhead * (int)gridDim.x;
+        if (gp < items && elect_one_sync()) {
+          const int tp = gp / p.heads, hp = gp - tp * p.heads;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) prefetch_tile<N>(&tmQKV, &tmQKV1, p.geo, tp, q * p.d + hp * kHd);
+          prefetch_tile<N>(&tmDO, &tmDO1, p.geo, tp, hp * kHd);
+        }
+        __syncwarp();
         mbar_wait(&bars->in_empty[s], ph ^ 1);
         if (elect_one_sync()) {
           mbar_expect_tx(&bars->in_full[s], 4 * kTile);
@@ -512,11 +551,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
       const uint32_t par = (j >> 1) & 1;
       uint32_t mw[N / 32];
       {
-        const uint32_t* mp = p.bits + p.geo.mask_word(tile, row);
+        const uint32_t* mp = p.bits + p.geo.mask_word<N>(tile, row);
 #pragma unroll
         for (int w = 0; w < N / 32; ++w) mw[w] = mp[w];
       }
-      bf16* grow = p.dqkv + (size_t)p.geo.token_row(tile, row) * d3 + h * kHd;
+      bf16* grow = p.dqkv + (size_t)p.geo.token_row<N>(tile, row) * d3 + h * kHd;
       mbar_wait(&bars->sdp_full[set], par);
       tc_fence_after();
       {
@@ -601,8 +640,8 @@ __global__ void prep_qkv2_kernel(const bf16* __restrict__ w, const float* __rest
 
 static Geo2 make_geo2(const AttnArgs& a, int W) {
   Geo2 g;
-  g.F = a.F; g.K = a.K; g.shift = a.shift; g.layout = a.layout; g.f = a.F / 2; g.kgroups = a.K / 64;
-  g.W = W; g.N = 2 * W; g.wpt = 64 / W; g.nWt = a.K / W;
+  g.F = a.F; g.K = a.K; g.shift = a.shift; g.layout = a.layout; g.f = a.F / 2;
+  g.nWt = a.K / W; g.tps = g.f * g.nWt / (64 / W);
   return g;
 }
 
@@ -678,7 +717,7 @@ int attn2_fwd(const AttnArgs& a, int W, bf16* qkv, cudaStream_t s) {
   if ((st = make_row_map(&tm, qkv, a, 3 * a.d, W, 2))) return st;
   if ((st = make_row_map(&tm1, qkv, a, 3 * a.d, W, 1))) return st;
   tc2::CoreArgs p{};
-  p.bits = a.bits; p.out = (bf16*)a.out; p.threshold = a.threshold; p.d = a.d; p.heads = a.heads; p.tiles = a.tiles();
+  p.bits = a.bits; p.out = (bf16*)a.out; p.threshold = a.threshold; p.d = a.d; p.heads = a.heads; p.tiles = (int)(a.tokens() / 128);
   p.stages = 3;
   p.geo = tc2::make_geo2(a, W);
   const int items = p.tiles * p.heads;
@@ -713,7 +752,7 @@ int attn2_bwd(const AttnArgs& a, int W, const bf16* qkv_saved, cudaStream_t s) {
   if ((st = make_row_map(&tmdo, a.d_out, a, d, W, 2))) return st;
   if ((st = make_row_map(&tmdo1, a.d_out, a, d, W, 1))) return st;
   tc2::CoreArgs p{};
-  p.bits = a.bits; p.dqkv = dqkv; p.threshold = a.threshold; p.d = d; p.heads = a.heads; p.tiles = a.tiles();
+  p.bits = a.bits; p.dqkv = dqkv; p.threshold = a.threshold; p.d = d; p.heads = a.heads; p.tiles = (int)(a.tokens() / 128);
   p.stages = 2;
   p.geo = tc2::make_geo2(a, W);
   const int items = p.tiles * p.heads;

@@ -640,11 +640,14 @@ __global__ void __launch_bounds__(256) ln_pool_fwd_kernel(const float* __restric
                                                           const float* __restrict__ beta, float* __restrict__ pooled,
                                                           float* __restrict__ mean, float* __restrict__ rstd,
                                                           float* __restrict__ scratch, int tokens, int slices,
-                                                          float eps) {
+                                                          float eps, int kp_real, int kp_pad) {
   constexpr int d = kV * 128;
   __shared__ float red[8][d];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int b = blockIdx.x / slices, sl = blockIdx.x - b * slices;
+  // a padded keypoint axis (HGATE: 29 keypoints stored as 32): `tokens` counts the REAL tokens of a sample; token tk
+  // sits at row (tk / kp_real) * kp_pad + tk % kp_real of the sample's tokens / kp_real * kp_pad stored rows
+  const int tokens_st = kp_pad ? tokens / kp_real * kp_pad : tokens;
   float4 gm[kV], acc[kV];
 #pragma unroll
   for (int i = 0; i < kV; ++i) {
@@ -652,7 +655,8 @@ __global__ void __launch_bounds__(256) ln_pool_fwd_kernel(const float* __restric
     acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int tk = sl * 8 + wib; tk < tokens; tk += slices * 8) {
-    const long long row = (long long)b * tokens + tk;
+    const int tks = kp_pad ? (tk / kp_real) * kp_pad + tk % kp_real : tk;
+    const long long row = (long long)b * tokens_st + tks;
     float4 v[kV];
     float s = 0.f;
 #pragma unroll
@@ -704,7 +708,8 @@ template <int kV>
 __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma, float* __restrict__ dx,
-                                                          float* __restrict__ dgamma, int tokens, int slices) {
+                                                          float* __restrict__ dgamma, int tokens, int slices,
+                                                          int kp_real, int kp_pad) {
   constexpr int d = kV * 128;
   __shared__ float red[8][d];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -722,8 +727,10 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(const float* __restric
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float m1 = warp_sum(s1) * (1.f / d);  // the same for every token of the sample
-  for (int tk = sl * 8 + wib; tk < tokens; tk += slices * 8) {
-    const long long row = (long long)b * tokens + tk;
+  const int tokens_st = kp_pad ? tokens / kp_real * kp_pad : tokens;   // (padded keypoint axis: see ln_pool_fwd_kernel;
+  for (int tk = sl * 8 + wib; tk < tokens; tk += slices * 8) {         //  the padded rows of dx are not written)
+    const int tks = kp_pad ? (tk / kp_real) * kp_pad + tk % kp_real : tk;
+    const long long row = (long long)b * tokens_st + tks;
     const float mu = mean[row], rs = rstd[row];
     float4 xh[kV];
     float s2 = 0.f;
@@ -765,12 +772,12 @@ size_t ln_pool_scratch_bytes(int B, int tokens, int d) {
 }
 
 int launch_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean, float* rstd,
-                       float* scratch, int B, int tokens, int d, float eps, cudaStream_t s) {
+                       float* scratch, int B, int tokens, int d, float eps, cudaStream_t s, int kp_real, int kp_pad) {
   const int slices = pool_slices(B, tokens);
   switch (d) {
-    case 128: ln_pool_fwd_kernel<1><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps); break;
-    case 256: ln_pool_fwd_kernel<2><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps); break;
-    case 512: ln_pool_fwd_kernel<4><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps); break;
+    case 128: ln_pool_fwd_kernel<1><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps, kp_real, kp_pad); break;
+    case 256: ln_pool_fwd_kernel<2><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps, kp_real, kp_pad); break;
+    case 512: ln_pool_fwd_kernel<4><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps, kp_real, kp_pad); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();
@@ -782,13 +789,13 @@ int launch_ln_pool_fwd(const float* x, const float* gamma, const float* beta, fl
 }
 
 int launch_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
-                       float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s) {
+                       float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s, int kp_real, int kp_pad) {
   cudaMemsetAsync(dgamma, 0, sizeof(float) * d, s);
   const int slices = pool_slices(B, tokens);
   switch (d) {
-    case 128: ln_pool_bwd_kernel<1><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices); break;
-    case 256: ln_pool_bwd_kernel<2><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices); break;
-    case 512: ln_pool_bwd_kernel<4><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices); break;
+    case 128: ln_pool_bwd_kernel<1><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad); break;
+    case 256: ln_pool_bwd_kernel<2><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad); break;
+    case 512: ln_pool_bwd_kernel<4><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();

@@ -149,9 +149,10 @@ int launch_embed_fwd(const float* x, const float* Bm, const float* pe, float* ou
                      int T, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s);
 size_t ln_pool_scratch_bytes(int B, int tokens, int d);
 int launch_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean, float* rstd,
-                       float* scratch, int B, int tokens, int d, float eps, cudaStream_t s);
+                       float* scratch, int B, int tokens, int d, float eps, cudaStream_t s, int kp_real = 0,
+                       int kp_pad = 0);
 int launch_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
-                       float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s);
+                       float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s, int kp_real = 0, int kp_pad = 0);
 
 int linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, int n, int d_in, int d_out,
                    cudaStream_t s);

@@ -69,6 +69,19 @@ HW_DEV void tma_load_4d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0,
       : "memory");
 }
 
+// L2 prefetch of a TMA box (no shared memory, no barrier): lets a producer whose stage ring is shallow pull the boxes
+// of a later work item into L2 early, so the real copy that follows is an L2 hit
+HW_DEV void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+HW_DEV void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];\n" ::
+                   "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // ---- tcgen05 --------------------------------------------------------------------
 HW_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 HW_DEV void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }

@@ -397,14 +397,20 @@ class Model(nn.Module):
             nn.init.constant_(m.bias, 0)
             nn.init.constant_(m.weight, 1.0)
 
+    # (overridden by the sibling model HGATE, which stores its 29 keypoints as 32)
+    _kp_real = 0
+
+    def _embed_fused(self, x):
+        """K8: Fourier embedding + positional encoding + its dropout in one pass, fp32 (bf16 would round the
+        argument 2*pi*x.B, values up to ~300, by up to 2 rad: SURVEY.md 7.2)."""
+        return ops.fourier_embed(x, self.B, self.pos_encoder.pe, self.pos_encoder.dropout.p, self.training)
+
     def forward_features(self, x):
         fused = x.is_cuda and _attn_dtype(x) == torch.bfloat16 and x.dtype == torch.float32
         if fused and self.pe and not self.B.requires_grad and not x.requires_grad:
-            # K8: Fourier embedding + positional encoding + its dropout in one pass, fp32 (see below why)
-            x = ops.fourier_embed(x, self.B, self.pos_encoder.pe, self.pos_encoder.dropout.p, self.training)
+            x = self._embed_fused(x)
         else:
-            # the embedding stays fp32 even under autocast: bf16 rounds 2*pi*x.B (values up to
-            # ~300) by up to 2 rad
+            # the embedding stays fp32 even under autocast (see _embed_fused)
             with torch.autocast(device_type=x.device.type, enabled=False):
                 proj = (2. * math.pi * x.float()) @ self.B.float().t()
                 x = torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1)
@@ -427,7 +433,7 @@ class Model(nn.Module):
         B, f, K, d = x.shape
         if fused and type(self.norm) is nn.LayerNorm and d in (128, 256, 512):
             # K9: final LayerNorm + mean over the f*K tokens (self.avgpool, HWGATE.py:354) in one pass
-            return ops.layer_norm_mean_pool(x, self.norm.weight, self.norm.bias, self.norm.eps)
+            return ops.layer_norm_mean_pool(x, self.norm.weight, self.norm.bias, self.norm.eps, kp_real=self._kp_real)
         x = self.norm(x)
         # self.avgpool (AvgPool1d over all f*K tokens, HWGATE.py:354) is a mean over tokens; mean() has the
         # same value and a broadcast backward instead of avg_pool2d_backward (3.5 ms per step at B=512)

@@ -81,3 +81,58 @@ class HWGATEParams():
         return (self.kp_dim, self.num_kps, self.temporal_dim, self.num_classes, self.embed_dim,
                 self.temporal_patch_size, self.pe, self.depths, self.num_heads, self.window_size, self.adj_mat,
                 self.drop_rate, self.attn_drop_rate, self.ff_ratio, self.norm_layer, self.device)
+
+
+def _hand_edges(wrist):
+    """12 edges of one 10-keypoint hand whose wrist is keypoint `wrist`: the thumb joint, four finger bases, a second
+    joint per finger, and links between neighbouring finger bases."""
+    bases = [wrist + 2 * i for i in range(1, 5)]
+    return ([[wrist, wrist + 1]] + [[wrist, b] for b in bases] + [[b, b + 1] for b in bases] +
+            [[bases[i], bases[i + 1]] for i in range(3)])
+
+
+def _body_edges():
+    """The 29-keypoint mediapipe skeleton of HGATE (same 34 undirected edges as model_params.py:422-457): 0-2 head,
+    3-8 shoulders / elbows / wrists, 9-18 left hand, 19-28 right hand."""
+    head = [[2, 0], [1, 0]]
+    arms = [[0, 3], [0, 4], [3, 5], [4, 6], [5, 7], [6, 8]]
+    return head + arms + [[7, 9]] + _hand_edges(9) + [[8, 19]] + _hand_edges(19)
+
+
+class HGATEParams():
+    """Drop-in for the HGATEParams class of hwgat/models/model_params.py:405-483 (same constructor, attributes and
+    get_model_params() tuple); the (58, 58) block adjacency is built on the GPU by kernel K1a."""
+
+    def __init__(self, dataset_params, input_dim, device=None) -> None:
+        self.kp_dim = input_dim
+        self.num_kps = 29
+        self.temporal_dim = dataset_params['src_len']
+        self.num_classes = dataset_params['num_class']
+        self.embed_dim = 128
+        self.temporal_patch_size = 2
+        self.pe = True
+        self.depths = [2, 2, 4]
+        self.num_heads = [2, 4, 8]
+        self.drop_rate = 0.1
+        self.attn_drop_rate = 0.0
+        self.ff_ratio = 2.
+        self.norm_layer = nn.LayerNorm
+        self.device = device
+        self.edges = [_body_edges()]
+        self.adj_mat = self.get_adj_mat().cpu()
+
+    _cuda_device = HWGATEParams._cuda_device
+
+    def get_adj_mat(self):
+        """(TP*K, TP*K) float32 (model_params.py:461-474): one "window" of all K keypoints, via kernel K1a."""
+        return ops.adjacency_build(self.edges, self.num_kps, self.temporal_patch_size, self._cuda_device())[0]
+
+    def get_adj(self):
+        """(K, K) skeleton adjacency (model_params.py:476-481)."""
+        K = self.num_kps
+        return self.get_adj_mat()[:K, :K].cpu().numpy()
+
+    def get_model_params(self):
+        return (self.kp_dim, self.num_kps, self.temporal_dim, self.num_classes, self.embed_dim,
+                self.temporal_patch_size, self.pe, self.depths, self.num_heads, self.adj_mat, self.drop_rate,
+                self.attn_drop_rate, self.ff_ratio, self.norm_layer, self.device)

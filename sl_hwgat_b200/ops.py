@@ -694,46 +694,58 @@ def fourier_embed(x: torch.Tensor, fourier_b: torch.Tensor, pe: torch.Tensor, p:
 
 class _LayerNormPool(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps):
+    def forward(ctx, x, gamma, beta, eps, kp_real):
         lib = _lib.load()
         _need_cuda(x, gamma, beta)
         if x.dtype != torch.float32:
             raise _lib.HwgatError("layer_norm_mean_pool takes the fp32 residual stream")
         x_c = x.contiguous()
         Bsz, d = x_c.shape[0], x_c.shape[-1]
-        tokens = x_c.numel() // (Bsz * d) if Bsz else 1
+        stored = x_c.numel() // (Bsz * d) if Bsz else 1
+        kp_pad = 0
+        tokens = stored
+        if kp_real:                      # padded keypoint axis (HGATE): x is (B, F, kp_pad, d), kp_real real keypoints
+            kp_pad = x_c.shape[-2]
+            if x_c.dim() != 4 or kp_pad < kp_real:
+                raise ValueError("a padded keypoint axis needs x as (B, F, kp_pad, d) with kp_pad >= kp_real")
+            tokens = stored // kp_pad * kp_real
+            if kp_pad == kp_real:
+                kp_real = kp_pad = 0
         g_c, b_c = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         pooled = torch.empty((Bsz, d), dtype=torch.float32, device=x_c.device)
-        mean = torch.empty(Bsz * tokens, dtype=torch.float32, device=x_c.device)
-        rstd = torch.empty(Bsz * tokens, dtype=torch.float32, device=x_c.device)
+        mean = torch.empty(Bsz * stored, dtype=torch.float32, device=x_c.device)
+        rstd = torch.empty(Bsz * stored, dtype=torch.float32, device=x_c.device)
         sc_bytes = lib.hwgat_ln_pool_scratch_bytes(Bsz, tokens, d)
         scratch = torch.empty(sc_bytes, dtype=torch.uint8, device=x_c.device) if sc_bytes else None
         with torch.cuda.device(x_c.device):
             check(lib.hwgat_ln_pool_fwd(x_c.data_ptr(), g_c.data_ptr(), b_c.data_ptr(), pooled.data_ptr(),
                                         mean.data_ptr(), rstd.data_ptr(), _ptr(scratch), sc_bytes, Bsz, tokens, d,
-                                        float(eps), _stream()), "hwgat_ln_pool_fwd")
+                                        float(eps), kp_real, kp_pad, _stream()), "hwgat_ln_pool_fwd")
         ctx.save_for_backward(x_c, g_c, mean, rstd)
-        ctx.meta = (Bsz, tokens, d, gamma.dtype, beta.dtype)
+        ctx.meta = (Bsz, tokens, d, gamma.dtype, beta.dtype, kp_real, kp_pad)
         return pooled
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
         x_c, g_c, mean, rstd = ctx.saved_tensors
-        Bsz, tokens, d, gdt, bdt = ctx.meta
+        Bsz, tokens, d, gdt, bdt, kp_real, kp_pad = ctx.meta
         gg = g.float().contiguous()
-        dx = torch.empty_like(x_c)
+        dx = torch.zeros_like(x_c) if kp_pad else torch.empty_like(x_c)     # padded rows get no gradient
         dgamma = torch.empty(d, dtype=torch.float32, device=x_c.device)
         with torch.cuda.device(x_c.device):
             check(lib.hwgat_ln_pool_bwd(gg.data_ptr(), x_c.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g_c.data_ptr(),
-                                        dx.data_ptr(), dgamma.data_ptr(), Bsz, tokens, d, _stream()),
+                                        dx.data_ptr(), dgamma.data_ptr(), Bsz, tokens, d, kp_real, kp_pad, _stream()),
                   "hwgat_ln_pool_bwd")
-        return dx, dgamma.to(gdt), gg.sum(0).to(bdt), None
+        return dx, dgamma.to(gdt), gg.sum(0).to(bdt), None, None
 
 
-def layer_norm_mean_pool(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
-    """(B, ..., d) -> (B, d): mean over all tokens of LayerNorm(x): self.norm + self.avgpool (HWGATE.py:353-354)."""
-    return _LayerNormPool.apply(x, gamma, beta, eps)
+def layer_norm_mean_pool(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+                         kp_real: int = 0) -> torch.Tensor:
+    """(B, ..., d) -> (B, d): mean over all tokens of LayerNorm(x): self.norm + self.avgpool (HWGATE.py:353-354).
+    kp_real > 0: x is (B, F, kp_pad, d) with only the first kp_real keypoints of every frame real (HGATE's 29
+    keypoints stored as 32); the padded rows are neither pooled nor given a gradient."""
+    return _LayerNormPool.apply(x, gamma, beta, eps, kp_real)
 
 
 # --------------------------------------------------------------------------

@@ -217,10 +217,82 @@ def larger_windows_golden(hw, mp, sce):
     np.savez_compressed(os.path.join(HERE, "larger_windows.npz"), **out)
 
 
+def hgate_golden(mp, sce):
+    """Section 7: the sibling model HGATE (hwgat/models/HGATE.py, HGATEParams): 29 keypoints, blocks of 2 x 29 tokens,
+    adjacency and shift mask both multiplicative, no threshold drop.  Unmodified reference, fp64."""
+    import importlib
+    from oracle import hgate_oracle as H
+    hg = importlib.import_module("models.HGATE")
+    out = {}
+    params = mp.HGATEParams({"num_class": 10, "src_len": 16}, 2, "cpu")
+    params.drop_rate = 0.0
+    out["adj"] = params.adj_mat.numpy().astype(np.uint8)                         # (58, 58)
+    for F in (8, 4):
+        blk = hg.GraphAttentionBlock(dim=128, num_kps=29, num_heads=2, temporal_patch_size=2, temporal_dim=F,
+                                     shift_size=1, adj_mat=None)
+        out[f"shift_mask_F{F}"] = (blk.attn_mask.numpy() != 0)
+    for (d, h) in ((128, 2), (256, 4)):
+        for shift in (0, 1):
+            B, F = 2, 4
+            std = 0.2 if d == 128 else 0.1
+            rng = np.random.default_rng(5000 + d + 10 * shift)
+            xn = torch.from_numpy(rng.standard_normal((B, F, 29, d)))
+            w = torch.from_numpy(rng.standard_normal((3 * d, d)) * std)
+            b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1)
+            g = torch.from_numpy(rng.standard_normal((B, F, 29, d)))
+            blk = hg.GraphAttentionBlock(dim=d, num_kps=29, num_heads=h, temporal_patch_size=2, temporal_dim=F,
+                                         shift_size=shift, adj_mat=params.adj_mat.double(), drop=0.0).double()
+            msa = blk.attn
+            with torch.no_grad():
+                msa.qkv.weight.copy_(w); msa.qkv.bias.copy_(b)
+                msa.proj.weight.copy_(torch.eye(d, dtype=torch.float64)); msa.proj.bias.zero_()
+            xn_ = xn.clone().requires_grad_(True)
+            xs = torch.roll(xn_, shifts=-shift, dims=1) if shift else xn_
+            xb = hg.block_partition(xs, 2)
+            yb = msa(xb, B, F // 2, attn_mask=blk.attn_mask)
+            y = hg.block_reverse(yb, 2, F, 29)
+            y = torch.roll(y, shifts=shift, dims=1) if shift else y
+            (y * g).sum().backward()
+            key = f"d{d}_s{shift}"
+            out[key + "_y"], out[key + "_ysum"] = sample(y, 53)
+            out[key + "_dx"], out[key + "_dxsum"] = sample(xn_.grad, 53)
+            out[key + "_dw"], out[key + "_dwsum"] = sample(msa.qkv.weight.grad, 251)
+            out[key + "_db"] = msa.qkv.bias.grad.numpy().copy()
+    cfg = H.HGATEConfig(temporal_dim=16, num_classes=10)
+    sd = H.make_state_dict(cfg, seed=1001, weight_std=0.05)
+    model = hg.Model(*params.get_model_params())
+    model.load_state_dict(sd, strict=True)
+    out["state_dict_names"] = np.array(list(model.state_dict().keys()))
+    out["state_dict_shapes"] = np.array([str(tuple(v.shape)) for v in model.state_dict().values()])
+    model = model.double()
+    for layer in model.layers:
+        layer.adj_mat = layer.adj_mat.double()
+        for blk in layer.blocks:
+            blk.attn.adj_mat = blk.attn.adj_mat.double()
+    x = H.synthetic_keypoints(2, 16, seed=1001).double()
+    y = torch.from_numpy(np.array([3, 7]))
+    model.train()                                   # drop_rate 0: train == eval for HGATE (no threshold path)
+    logits = model(x)
+    loss = sce.SmoothedCrossEntropyLoss()(logits, y)
+    loss.backward()
+    out["model_logits"] = logits.detach().numpy()
+    out["model_loss"] = np.array(loss.item())
+    names, norms, heads = [], [], []
+    for n, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        names.append(n); norms.append(p.grad.norm().item()); heads.append(p.grad.reshape(-1)[:4].numpy().copy())
+    out["gnames"], out["gnorms"], out["gheads"] = np.array(names), np.array(norms), np.stack(heads)
+    np.savez_compressed(os.path.join(HERE, "hgate.npz"), **out)
+
+
 def main():
     from oracle import hwgate_oracle as O
     hw, mp, sce = import_reference()
     torch.manual_seed(0)
+    if "--only-hgate" in sys.argv:
+        hgate_golden(mp, sce)
+        return
     if "--only-autocast" in sys.argv:
         autocast_train_golden(hw, mp, sce)
         return
@@ -339,6 +411,7 @@ def main():
 
     autocast_train_golden(hw, mp, sce)
     larger_windows_golden(hw, mp, sce)
+    hgate_golden(mp, sce)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -258,3 +258,71 @@ def test_autocast_golden_is_consistent_with_fp64_golden(golden_dir):
     assert list(A["gnames"]) == list(F["include_train_gnames"])
     assert np.abs(A["gnorms"] - F["include_train_gnorms"]).max() / F["include_train_gnorms"].max() < 2e-2
     assert int(A["goffsets"][-1]) == A["gsamples"].size
+
+
+# ------------------------------------------------------------------ sibling model HGATE
+def hgate_core_inputs(d, shift, B=2, F=4):
+    """Same seeded inputs as tests/golden/make_golden.py section 7."""
+    std = 0.2 if d == 128 else 0.1
+    rng = np.random.default_rng(5000 + d + 10 * shift)
+    xn = torch.from_numpy(rng.standard_normal((B, F, 29, d)))
+    w = torch.from_numpy(rng.standard_normal((3 * d, d)) * std)
+    b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1)
+    g = torch.from_numpy(rng.standard_normal((B, F, 29, d)))
+    return xn, w, b, g
+
+
+def test_hgate_masks_match_reference(golden_dir):
+    from oracle import hgate_oracle as H
+    G = _load(golden_dir, "hgate.npz")
+    adj = H.block_adjacency(H.HGATEConfig().edges, 29, 2)
+    assert adj.shape == (58, 58) and np.array_equal(adj, G["adj"].astype(bool))
+    assert len(H.HGATE_EDGES) == 34
+    for F in (8, 4):
+        assert np.array_equal(H.block_shift_mask(F, 29, 2, 1), G[f"shift_mask_F{F}"])
+
+
+@pytest.mark.parametrize("d,h", [(128, 2), (256, 4)])
+@pytest.mark.parametrize("shift", [0, 1])
+def test_hgate_attention_core_matches_reference(golden_dir, d, h, shift):
+    from oracle import hgate_oracle as H
+    G = _load(golden_dir, "hgate.npz")
+    key = f"d{d}_s{shift}"
+    xn, w, b, g = hgate_core_inputs(d, shift)
+    mask = H.block_mask(H.block_adjacency(H.HGATEConfig().edges, 29, 2), 4, 29, 2, shift)
+    x_, w_, b_ = (t.clone().requires_grad_(True) for t in (xn, w, b))
+    y = H.attention_core(x_, w_, b_, h, mask, 2, shift)
+    (y * g).sum().backward()
+
+    def chk(t, name, stride):
+        a = t.detach().reshape(-1).numpy()
+        ref = G[key + "_" + name]
+        assert np.abs(a[::stride] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (key, name)
+        s = G[key + "_" + name + "sum"]
+        assert abs(a.sum() - s[0]) <= 1e-9 * s[1] and a.size == int(s[2])
+    chk(y, "y", 53)
+    chk(x_.grad, "dx", 53)
+    chk(w_.grad, "dw", 251)
+    assert np.abs(b_.grad.numpy() - G[key + "_db"]).max() <= 1e-9 * np.abs(G[key + "_db"]).max()
+
+
+def test_hgate_full_model_matches_reference(golden_dir):
+    from oracle import hgate_oracle as H
+    G = _load(golden_dir, "hgate.npz")
+    cfg = H.HGATEConfig(temporal_dim=16, num_classes=10)
+    sd = H.make_state_dict(cfg, seed=1001, weight_std=0.05)
+    assert sorted(sd.keys()) == sorted(G["state_dict_names"])
+    shapes = dict(zip(G["state_dict_names"], G["state_dict_shapes"]))
+    assert all(str(tuple(v.shape)) == shapes[k] for k, v in sd.items())
+    sd64 = {k: v.double().requires_grad_(k not in ("B", "pos_encoder.pe") and not k.endswith("attn_mask"))
+            for k, v in sd.items()}
+    x = H.synthetic_keypoints(2, 16, seed=1001).double()
+    logits = H.model_forward(x, sd64, cfg)
+    assert np.abs(logits.detach().numpy() - G["model_logits"]).max() <= 1e-9 * np.abs(G["model_logits"]).max()
+    loss = O.smoothed_cross_entropy(logits, torch.tensor([3, 7]))
+    assert abs(loss.item() - float(G["model_loss"])) < 1e-9
+    loss.backward()
+    for name, norm, head in zip(G["gnames"], G["gnorms"], G["gheads"]):
+        gr = sd64[str(name)].grad
+        assert abs(gr.norm().item() - norm) <= 1e-8 * norm, name
+        assert np.abs(gr.reshape(-1)[:4].numpy() - head).max() <= 1e-8 * max(np.abs(head).max(), 1e-12), name
