@@ -39,7 +39,6 @@ constexpr int kRegsDonor = 40, kRegsSoft = 232;
 constexpr int kTile = 128 * 128;            // bytes of a [128 x 64] bf16 tile
 constexpr int kPBytes = 2 * kTile;          // [128 x 128] bf16 as two 64-column chunks
 constexpr int kMaxDynSmem2 = 232448;
-constexpr int kPrefetchAhead = 3;           // producer: L2 prefetch distance in items
 constexpr float kLog2e = 1.4426950408889634f;
 
 HW_DEV void reg_dealloc_donor() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kRegsDonor)); }
@@ -95,28 +94,6 @@ HW_DEV void load_tile(unsigned char* dst, const CUtensorMap* tm2, const CUtensor
     } else {
       tma_load_4d(dst + w * N * 128, tm1, bar, col, kwin * W, fr0, b);
       tma_load_4d(dst + (w * N + W) * 128, tm1, bar, col, kwin * W, 0, b);
-    }
-  }
-}
-
-// the same boxes, prefetched into L2 only (issued by the producer a few items ahead of the copy)
-template <int N>
-HW_DEV void prefetch_tile(const CUtensorMap* tm2, const CUtensorMap* tm1, const Geo2& g, int tile, int col) {
-  if (g.layout == HWGAT_LAYOUT_WINDOWS) {
-    tma_prefetch_2d(tm2, col, tile * 128);
-    return;
-  }
-  constexpr int W = N / 2, wpt = 128 / N;
-  const int b = tile / g.tps, w0 = (tile - b * g.tps) * wpt;
-#pragma unroll
-  for (int w = 0; w < wpt; ++w) {
-    const int widx = w0 + w, fi = widx / g.nWt, kwin = widx - fi * g.nWt;
-    const int fr0 = 2 * fi + g.shift;
-    if (fr0 + 1 < g.F) {
-      tma_prefetch_4d(tm2, col, kwin * W, fr0, b);
-    } else {
-      tma_prefetch_4d(tm1, col, kwin * W, fr0, b);
-      tma_prefetch_4d(tm1, col, kwin * W, 0, b);
     }
   }
 }
@@ -284,13 +261,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
       uint32_t ph = 0;
       for (int g = blockIdx.x; g < items; g += gridDim.x) {
         const int tile = g / p.heads, h = g - tile * p.heads;
-        const int gp = g + kPrefetchAhead * (int)gridDim.x;      // the item kPrefetchAhead iterations ahead: into L2 now
-        if (gp < items && elect_one_sync()) {
-          const int tp = gp / p.heads, hp = gp - tp * p.heads;
-#pragma unroll
-          for (int q = 0; q < 3; ++q) prefetch_tile<N>(&tmQKV, &tmQKV1, p.geo, tp, q * p.d + hp * kHd);
-        }
-        __syncwarp();
         mbar_wait(&bars->in_empty[s], ph ^ 1);
         if (elect_one_sync()) {
           mbar_expect_tx(&bars->in_full[s], 3 * kTile);
@@ -405,10 +375,16 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
 // ---------------------------------------------------------------------------------------------------------------------
 // backward (S and P recomputed from the saved / re-projected q, k, v)
 // ---------------------------------------------------------------------------------------------------------------------
+// Shared memory of the backward: THREE 64 KB stages of [Q | K | V | dO] and ONE [128 x 128] bf16 tile that holds P
+// first (for dV = P^T dO) and dS second (for dQ, dK) - with separate P and dS tiles only two stages fit, a stage is
+// held until the item's last MMA, and the copies could not run far enough ahead of the MMAs (ncu: 1.16 ms for
+// 3.7 GB at N = 32, long-scoreboard stalls 75 % of the samples).
+// TMEM, per 256-column buffer: S [0,128) + dP [128,256); then dV [0,64) over the consumed S, and dQ [64,128),
+// dK [128,192) once dS has been extracted from dP.
 struct BwdBars {
-  uint64_t in_full[2], in_empty[2];
+  uint64_t in_full[3], in_empty[3];
   uint64_t sdp_full[2], dqkv_full[2], t_empty[2];
-  uint64_t pds_ready, pds_empty;
+  uint64_t p_ready, pv_done, ds_ready, pd_empty;
   uint32_t tmem_slot;
 };
 
@@ -420,23 +396,25 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
                                                                          const CoreArgs p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int S = 2;
-  unsigned char* sIn = smem;                          // 2 stages of [Q | K | V | dO]
-  unsigned char* sP = smem + S * 4 * kTile;
-  unsigned char* sDS = sP + kPBytes;
-  BwdBars* bars = reinterpret_cast<BwdBars*>(sDS + kPBytes);
+  constexpr int S = 3;
+  unsigned char* sIn = smem;                          // 3 stages of [Q | K | V | dO]
+  unsigned char* sPD = smem + S * 4 * kTile;          // P, then dS
+  BwdBars* bars = reinterpret_cast<BwdBars*>(sPD + kPBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int items = p.tiles * p.heads;
 
-  for (int i = threadIdx.x; i < 2 * kPBytes / 16; i += blockDim.x) reinterpret_cast<int4*>(sP)[i] = make_int4(0, 0, 0, 0);
+  // zeros once: a softmax thread only ever writes its own window's columns (P and dS are block-diagonal)
+  for (int i = threadIdx.x; i < kPBytes / 16; i += blockDim.x) reinterpret_cast<int4*>(sPD)[i] = make_int4(0, 0, 0, 0);
   fence_proxy_async();
   if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 1);
       mbar_init(&bars->sdp_full[i], 1); mbar_init(&bars->dqkv_full[i], 1); mbar_init(&bars->t_empty[i], 4);
     }
-    mbar_init(&bars->pds_ready, 4);
-    mbar_init(&bars->pds_empty, 1);
+    mbar_init(&bars->p_ready, 4);
+    mbar_init(&bars->ds_ready, 4);
+    mbar_init(&bars->pv_done, 1);
+    mbar_init(&bars->pd_empty, 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmQKV1);
@@ -456,17 +434,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
       uint32_t ph = 0;
       for (int g = blockIdx.x; g < items; g += gridDim.x) {
         const int tile = g / p.heads, h = g - tile * p.heads;
-        // only two 64 KB stages fit next to the P / dS tiles, and a stage is held until the item's last MMA: the
-        // boxes of the item kPrefetchAhead iterations ahead are pulled into L2 now, so the copy that refills a
-        // stage is an L2 hit instead of an HBM round trip
-        const int gp = g + kPrefetchAhead * (int)gridDim.x;
-        if (gp < items && elect_one_sync()) {
-          const int tp = gp / p.heads, hp = gp - tp * p.heads;
-#pragma unroll
-          for (int q = 0; q < 3; ++q) prefetch_tile<N>(&tmQKV, &tmQKV1, p.geo, tp, q * p.d + hp * kHd);
-          prefetch_tile<N>(&tmDO, &tmDO1, p.geo, tp, hp * kHd);
-        }
-        __syncwarp();
         mbar_wait(&bars->in_empty[s], ph ^ 1);
         if (elect_one_sync()) {
           mbar_expect_tx(&bars->in_full[s], 4 * kTile);
@@ -487,30 +454,33 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
       uint32_t ph = 0;
       auto issue_grads = [&](int i, int stage) {
         const int b = i & 1;
-        mbar_wait(&bars->pds_ready, i & 1);
+        const uint32_t sq = smem_u32(sIn + stage * 4 * kTile), sk = sq + kTile, sdo = sq + 3 * kTile;
+        const uint32_t spd = smem_u32(sPD);
+        const uint32_t t = tmem + b * 256;
+        mbar_wait(&bars->p_ready, i & 1);
         tc_fence_after();
         if (elect_one_sync()) {
-          const uint32_t sq = smem_u32(sIn + stage * 4 * kTile), sk = sq + kTile, sdo = sq + 3 * kTile;
-          const uint32_t sp = smem_u32(sP), sds = smem_u32(sDS);
-          const uint32_t t = tmem + b * 256;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {   // dV[key] = sum_q P[q, key] dO[q]
-            umma_bf16(t + 128, umma_desc_mn_sw128(sp + ks * 2048, kTile, 1024), umma_desc_mn_sw128(sdo + ks * 2048, 8192, 1024),
+          for (int ks = 0; ks < 8; ++ks)     // dV[key] = sum_q P[q, key] dO[q]
+            umma_bf16(t, umma_desc_mn_sw128(spd + ks * 2048, kTile, 1024), umma_desc_mn_sw128(sdo + ks * 2048, 8192, 1024),
                       idMM, ks != 0);
-          }
+          umma_commit(&bars->pv_done);
+        }
+        __syncwarp();
+        mbar_wait(&bars->ds_ready, i & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {   // dQ[q] = sum_key dS[q, key] K[key]
-            umma_bf16(t, umma_desc_k_sw128(sds + (ks >> 2) * kTile + (ks & 3) * 32), umma_desc_mn_sw128(sk + ks * 2048, 8192, 1024),
-                      idKM, ks != 0);
-          }
+          for (int ks = 0; ks < 8; ++ks)     // dQ[q] = sum_key dS[q, key] K[key]
+            umma_bf16(t + 64, umma_desc_k_sw128(spd + (ks >> 2) * kTile + (ks & 3) * 32),
+                      umma_desc_mn_sw128(sk + ks * 2048, 8192, 1024), idKM, ks != 0);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {   // dK[key] = sum_q dS[q, key] Q[q]
-            umma_bf16(t + 64, umma_desc_mn_sw128(sds + ks * 2048, kTile, 1024), umma_desc_mn_sw128(sq + ks * 2048, 8192, 1024),
+          for (int ks = 0; ks < 8; ++ks)     // dK[key] = sum_q dS[q, key] Q[q]
+            umma_bf16(t + 128, umma_desc_mn_sw128(spd + ks * 2048, kTile, 1024), umma_desc_mn_sw128(sq + ks * 2048, 8192, 1024),
                       idMM, ks != 0);
-          }
           umma_commit(&bars->dqkv_full[b]);
           umma_commit(&bars->in_empty[stage]);
-          umma_commit(&bars->pds_empty);
+          umma_commit(&bars->pd_empty);
         }
         __syncwarp();
       };
@@ -574,33 +544,40 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
 #pragma unroll
           for (int i = 0; i < 32; ++i) delta = fmaf(v[32 * c + i], __uint_as_float(r[i]), delta);
         }
-        // the previous item's second-stage MMAs must have finished reading sP / sDS
-        mbar_wait(&bars->pds_empty, (j & 1) ^ 1);
-        store_row_bf16<N>(smem_u32(sP), row, col0, v);
+        // P: the previous item's dQ / dK MMAs must have finished reading the tile (it then held that item's dS)
+        mbar_wait(&bars->pd_empty, (j & 1) ^ 1);
+        store_row_bf16<N>(smem_u32(sPD), row, col0, v);
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_ready);
+        // dS = P (dP - delta), under the dV MMAs; P is exactly 0 off the live set; dead rows: 0
 #pragma unroll
         for (int c = 0; c < N / 32; ++c) {
           uint32_t r[32];
           tmem_ld32(tq + 128 + col0 + 32 * c, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)      // dS = P (dP - delta); P is exactly 0 off the live set; dead rows: 0
+          for (int i = 0; i < 32; ++i)
             v[32 * c + i] = dead ? 0.f : v[32 * c + i] * (__uint_as_float(r[i]) - delta);
         }
-        store_row_bf16<N>(smem_u32(sDS), row, col0, v);
+        mbar_wait(&bars->pv_done, j & 1);      // dV = P^T dO has read P: the tile may take dS
+        store_row_bf16<N>(smem_u32(sPD), row, col0, v);
       }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->pds_ready);
+      if (lane == 0) mbar_arrive(&bars->ds_ready);
       mbar_wait(&bars->dqkv_full[set], par);
       tc_fence_after();
 #pragma unroll
       for (int part = 0; part < 3; ++part) {      // dQ (x 64^-1/2: q carries the scale), dK, dV
         const float mul = part == 0 ? 0.125f : 1.f;
+        const int tcol = part == 0 ? 64 : (part == 1 ? 128 : 0);      // TMEM: dV [0,64), dQ [64,128), dK [128,192)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t r[32];
-          tmem_ld32(tq + 64 * part + 32 * c, r);
+          tmem_ld32(tq + tcol + 32 * c, r);
           tmem_ld_wait();
 #pragma unroll
           for (int gq = 0; gq < 2; ++gq) {
@@ -753,11 +730,11 @@ int attn2_bwd(const AttnArgs& a, int W, const bf16* qkv_saved, cudaStream_t s) {
   if ((st = make_row_map(&tmdo1, a.d_out, a, d, W, 1))) return st;
   tc2::CoreArgs p{};
   p.bits = a.bits; p.dqkv = dqkv; p.threshold = a.threshold; p.d = d; p.heads = a.heads; p.tiles = (int)(a.tokens() / 128);
-  p.stages = 2;
+  p.stages = 3;
   p.geo = tc2::make_geo2(a, W);
   const int items = p.tiles * p.heads;
   const int grid = items < 148 ? items : 148;
-  const int smem = 2 * 4 * tc2::kTile + 2 * tc2::kPBytes + (int)sizeof(tc2::BwdBars) + 1024;
+  const int smem = 3 * 4 * tc2::kTile + tc2::kPBytes + (int)sizeof(tc2::BwdBars) + 1024;
   const bool train = a.threshold >= 0.f;
   switch (2 * W) {
     case 32: st = launch_core_bwd<32>(tm, tm1, tmdo, tmdo1, p, train, grid, smem, s); break;
