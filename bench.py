@@ -52,12 +52,19 @@ CONFIGS = {
     "train_t256_w64": ("train", 256, 262, 128, 64,
                        "BASELINE configs[4], larger windows W=64 (N=128 tokens per window): training fwd+bwd, T=256, "
                        "128 sequences per GPU, 262 classes, train mode"),
+    # the sibling model HGATE: 29 keypoints stored as 32, one 64-token window per block
+    "hgate_train512": ("train", 64, 262, 512, 32,
+                       "sibling model HGATE (hwgat/models/HGATE.py): training fwd+bwd, T=64 frames x 29 keypoints x 2, "
+                       "262 classes, depths [2,2,4], heads [2,4,8], TP=2, dropout 0.1"),
 }
+MODEL = "HWGATE"
 
 
 def set_config(name):
-    global T_FRAMES, CLASSES, WINDOW, METRIC
+    global T_FRAMES, CLASSES, WINDOW, METRIC, MODEL, KPS
     mode, T_FRAMES, CLASSES, batch, WINDOW, what = CONFIGS[name]
+    MODEL = "HGATE" if name.startswith("hgate") else "HWGATE"
+    KPS = 32 if MODEL == "HGATE" else 64          # stored keypoints per frame
     METRIC = "HWGAT sequences/sec fwd+bwd" if mode == "train" else "HWGAT sequences/sec inference forward"
     return mode, batch, what
 
@@ -238,6 +245,12 @@ class KernelTimer:
 def build_model(device, drop=0.1):
     import torch
     from sl_hwgat_b200.models import HWGATE, model_params
+    if MODEL == "HGATE":
+        from sl_hwgat_b200.models import HGATE
+        p = model_params.HGATEParams({"num_class": CLASSES, "src_len": T_FRAMES}, 2, device)
+        p.drop_rate = drop
+        torch.manual_seed(1001)
+        return HGATE.Model(*p.get_model_params()).to(device)
     p = model_params.HWGATEParams({"num_class": CLASSES, "src_len": T_FRAMES}, 2, device)
     p.drop_rate = drop
     if WINDOW != p.window_size:
@@ -255,9 +268,32 @@ def synthetic_batch(B):
     gather = np.array(head + larm + lh + head + rarm + rh + head + larm + rh + head + rarm + lh)
     rng = np.random.default_rng(1001)
     raw = rng.random((B, T_FRAMES, 29, 2), dtype=np.float32)
-    x = torch.from_numpy(np.ascontiguousarray(raw[:, :, gather, :]))
+    x = torch.from_numpy(np.ascontiguousarray(raw if MODEL == "HGATE" else raw[:, :, gather, :]))
     y = torch.from_numpy(rng.integers(0, CLASSES, size=(B,), dtype=np.int64))
     return x, y
+
+
+def _oracle_setup(batch, device=None):
+    """(forward(x, sd, thresholds or None, drop), sd, x, y, n_thresholds) of the oracle for the configured model"""
+    import torch
+    from oracle import hwgate_oracle as O
+    if MODEL == "HGATE":
+        from oracle import hgate_oracle as H
+        cfg = H.HGATEConfig(temporal_dim=T_FRAMES, num_classes=CLASSES)
+        sd = H.make_state_dict(cfg, seed=1001)
+        x = H.synthetic_keypoints(batch, T_FRAMES, seed=1001)
+        fwd = lambda xx, s_, thr, drop: H.model_forward(xx, s_, cfg, drop=drop, training=thr is not None)
+    else:
+        cfg = O.HWGATEConfig(temporal_dim=T_FRAMES, num_classes=CLASSES, window_size=WINDOW,
+                             edges=O.HWGATEConfig().edges[:64 // WINDOW])
+        sd = O.make_state_dict(cfg, seed=1001)
+        x = O.synthetic_keypoints(batch, T_FRAMES, 2, seed=1001)
+        fwd = lambda xx, s_, thr, drop: O.model_forward(xx, s_, cfg, thresholds=thr, drop=drop)
+    y = O.synthetic_labels(batch, CLASSES, seed=1001)
+    if device is not None:
+        sd = {k: v.to(device) for k, v in sd.items()}
+        x, y = x.to(device), y.to(device)
+    return fwd, sd, x, y, sum(cfg.depths)
 
 
 def cpu_reference_arm(steps, warmup, batch=8, mode="train"):
@@ -266,14 +302,10 @@ def cpu_reference_arm(steps, warmup, batch=8, mode="train"):
     from oracle import hwgate_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.HWGATEConfig(temporal_dim=T_FRAMES, num_classes=CLASSES, window_size=WINDOW,
-                         edges=O.HWGATEConfig().edges[:KPS // WINDOW])
-    sd = O.make_state_dict(cfg, seed=1001)
+    fwd, sd, x, y, n_thr = _oracle_setup(batch)
     for k, v in sd.items():
         if mode == "train" and k not in ("B", "pos_encoder.pe") and not k.endswith("attn_mask"):
             v.requires_grad_(True)
-    x = O.synthetic_keypoints(batch, T_FRAMES, 2, seed=1001)
-    y = O.synthetic_labels(batch, CLASSES, seed=1001)
     torch.manual_seed(1001)
     times = []
     for i in range(warmup + steps):
@@ -281,20 +313,21 @@ def cpu_reference_arm(steps, warmup, batch=8, mode="train"):
         if mode == "train":
             for v in sd.values():
                 v.grad = None
-            thr = [torch.rand(1).item() for _ in range(sum(cfg.depths))]
-            loss = O.smoothed_cross_entropy(O.model_forward(x, sd, cfg, thresholds=thr, drop=0.1), y)
+            thr = [torch.rand(1).item() for _ in range(n_thr)]
+            loss = O.smoothed_cross_entropy(fwd(x, sd, thr, 0.1), y)
             loss.backward()
         else:
             with torch.no_grad():
-                O.model_forward(x, sd, cfg)
+                fwd(x, sd, None, 0.0)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     total = sum(times)
     return {"value": batch * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle port of the reference (fp32, " +
+            "sample": f"oracle port of the reference {MODEL} (fp32, " +
                       ("train mode, dropout 0.1" if mode == "train" else "eval forward") +
-                      f"), batch {batch} x T={T_FRAMES} x 64 kp x 2, {CLASSES} classes, window_size {WINDOW}, "
+                      f"), batch {batch} x T={T_FRAMES} x {29 if MODEL == 'HGATE' else 64} kp x 2, {CLASSES} classes, "
+                      f"window_size {WINDOW}, "
                       f"{len(times)} " + ("fwd+bwd" if mode == "train" else "forward") + f" steps after {warmup} warm-up",
             "ms_per_step": 1e3 * total / len(times), "batch": batch}
 
@@ -307,10 +340,8 @@ def gpu_eager_baseline(dev, mode, batch):
     seeds, dropout 0.1, threshold path on.  A reported baseline, timed with CUDA events after our own timed regions."""
     import torch
     from oracle import hwgate_oracle as O
-    cfg = O.HWGATEConfig(temporal_dim=T_FRAMES, num_classes=CLASSES, window_size=WINDOW,
-                         edges=O.HWGATEConfig().edges[:KPS // WINDOW])
-    sd = {k: v.to(dev) for k, v in O.make_state_dict(cfg, seed=1001).items()}
     train = mode == "train"
+    fwd, sd, _, _, n_thr = _oracle_setup(8, dev)
     for k, v in sd.items():
         if train and k not in ("B", "pos_encoder.pe") and not k.endswith("attn_mask"):
             v.requires_grad_(True)
@@ -319,19 +350,18 @@ def gpu_eager_baseline(dev, mode, batch):
         B = batch
         while B >= 8:
             try:
-                x = O.synthetic_keypoints(B, T_FRAMES, 2, seed=1001).to(dev)
-                y = O.synthetic_labels(B, CLASSES, seed=1001).to(dev)
+                _, _, x, y, _ = _oracle_setup(B, dev)
                 torch.manual_seed(1001)
 
                 def step():
                     if not train:
                         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-                            return O.model_forward(x, sd, cfg)
+                            return fwd(x, sd, None, 0.0)
                     for v in sd.values():
                         v.grad = None
-                    thr = [torch.rand(1).item() for _ in range(sum(cfg.depths))]
+                    thr = [torch.rand(1).item() for _ in range(n_thr)]
                     with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-                        logits = O.model_forward(x, sd, cfg, thresholds=thr, drop=0.1)
+                        logits = fwd(x, sd, thr, 0.1)
                     loss = O.smoothed_cross_entropy(logits.float(), y)
                     loss.backward()
                     return loss
