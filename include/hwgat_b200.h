@@ -127,15 +127,18 @@ int hwgat_merge_bwd(const void* d_out, void* d_x, int B, int F, int K, int d, in
  * runs S = QK^T, O = PV (and dP, dV, dQ, dK in the backward) as block-diagonal M = 128 tcgen05 tiles with one thread
  * per query row for the masked softmax.  `qkv` (n x 3d bf16, n = B*F*K) is written by the forward and may be handed
  * back to the backward (NULL: the backward re-projects it into its workspace).  bits: hwgat_mask_build /
- * hwgat_mask_pack for this W (N/32 words per row).                                                              */
+ * hwgat_mask_pack for this W (N/32 words per row).  attn_p > 0: attention dropout, self.attn_drop on the
+ * probabilities (HWGATE.py:112), from the Philox stream (seed, offset); the backward regenerates the same mask.  */
 size_t hwgat_attn2_workspace_bytes(int B, int F, int K, int d, int heads, int backward, int have_qkv);
 int hwgat_attn2_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, float threshold,
                     void* out, void* qkv, void* workspace, size_t workspace_bytes, int B, int F, int K, int d,
-                    int heads, int W, int TP, int shift, int layout, hwgat_stream_t stream);
+                    int heads, int W, int TP, int shift, int layout, float attn_p, unsigned long long seed,
+                    unsigned long long offset, hwgat_stream_t stream);
 int hwgat_attn2_bwd(const void* d_out, const void* xn, const void* w_qkv, const float* b_qkv, const void* qkv,
                     const uint32_t* bits, float threshold, void* d_xn, float* d_w, float* d_b, void* workspace,
                     size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int TP, int shift,
-                    int layout, hwgat_stream_t stream);
+                    int layout, float attn_p, unsigned long long seed, unsigned long long offset,
+                    hwgat_stream_t stream);
 
 /* ---- rest of the block, bf16 / autocast path --------------------------
  * Bandwidth-bound fusions of the PyTorch elementwise chains of PartAttentionBlock.forward

@@ -205,7 +205,8 @@ def _rb(t: torch.Tensor, on: bool) -> torch.Tensor:
 
 def attention_core(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, heads: int,
                    mask: np.ndarray, W: int, TP: int, shift: int,
-                   threshold: Optional[float] = None, bf16_points: bool = False) -> torch.Tensor:
+                   threshold: Optional[float] = None, bf16_points: bool = False,
+                   drop_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Windowed graph attention of one block, from the normalised residual
     stream ``xn`` (B,F,K,d) to the head-merged context (B,F,K,d) *before* the
     output projection, in the un-rolled, un-partitioned layout.
@@ -218,6 +219,8 @@ def attention_core(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, h
 
     bf16_points=True rounds at the points where the CUDA bf16 kernels round
     (xn, weights, q, k, v, P, O), so it can be compared tightly with them.
+    drop_mask: (B_, heads, N, N) keep / (1-p) factors of self.attn_drop
+    (HWGATE.py:112), applied to the probabilities; None = p 0 / eval.
     """
     B, F, K, d = xn.shape
     hd = d // heads
@@ -239,6 +242,8 @@ def attention_core(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, h
     live = m & (s != 0)
     s = torch.where(live, s, torch.full_like(s, NEG_FILL))
     p = torch.softmax(s, dim=-1)
+    if drop_mask is not None:
+        p = p * drop_mask.to(p.dtype)                                    # HWGATE.py:112
     o = _rb(p, bf16_points) @ v                                          # (B_, h, N, hd)
     o = _rb(o.transpose(1, 2).reshape(-1, N, d), bf16_points)
     o = window_reverse(o, W, TP, F, K)

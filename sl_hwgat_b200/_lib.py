@@ -31,9 +31,10 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_size_t] + [c_int] * 10 + [c_void_p]),
     "hwgat_attn2_workspace_bytes": (c_size_t, [c_int] * 7),
     "hwgat_attn2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t]
-                        + [c_int] * 9 + [c_void_p]),
+                        + [c_int] * 9 + [c_float, c_ulonglong, c_ulonglong, c_void_p]),
     "hwgat_attn2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_size_t] + [c_int] * 9 + [c_void_p]),
+                                c_void_p, c_void_p, c_size_t] + [c_int] * 9 + [c_float, c_ulonglong, c_ulonglong,
+                                                                               c_void_p]),
     "hwgat_ln_fwd": (c_int, [c_void_p] * 6 + [c_longlong, c_int, c_float, c_void_p]),
     "hwgat_ln_bwd": (c_int, [c_void_p] * 9 + [c_longlong, c_int, c_void_p]),
     "hwgat_bda_ln_fwd": (c_int, [c_void_p] * 9 + [c_longlong, c_int, c_float, c_float, c_ulonglong, c_ulonglong,

@@ -141,9 +141,11 @@ size_t hwgat_attn2_workspace_bytes(int B, int F, int K, int d, int heads, int ba
 
 int hwgat_attn2_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, float threshold,
                     void* out, void* qkv, void* workspace, size_t workspace_bytes, int B, int F, int K, int d,
-                    int heads, int W, int TP, int shift, int layout, hwgat_stream_t stream) {
+                    int heads, int W, int TP, int shift, int layout, float attn_p, unsigned long long seed,
+                    unsigned long long offset, hwgat_stream_t stream) {
   int st = check_geometry2(B, F, K, d, heads, W, TP, shift, layout);
   if (st) return st;
+  if (!(attn_p >= 0.f) || attn_p >= 1.f) return HWGAT_ERR_SHAPE;
   if (B == 0) return HWGAT_OK;
   if (!xn || !w_qkv || !b_qkv || !bits || !out || !qkv) return HWGAT_ERR_NULL;
   if (misaligned(xn) || misaligned(w_qkv) || misaligned(out) || misaligned(b_qkv) || misaligned(workspace) ||
@@ -153,15 +155,18 @@ int hwgat_attn2_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const
   AttnArgs a{};
   a.xn = xn; a.w_qkv = w_qkv; a.b_qkv = b_qkv; a.bits = bits; a.threshold = threshold; a.out = out;
   a.workspace = workspace; a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
+  a.attn_p = attn_p; a.seed = seed; a.offset = offset;
   return attn2_fwd(a, W, (__nv_bfloat16*)qkv, (cudaStream_t)stream);
 }
 
 int hwgat_attn2_bwd(const void* d_out, const void* xn, const void* w_qkv, const float* b_qkv, const void* qkv,
                     const uint32_t* bits, float threshold, void* d_xn, float* d_w, float* d_b, void* workspace,
                     size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int TP, int shift,
-                    int layout, hwgat_stream_t stream) {
+                    int layout, float attn_p, unsigned long long seed, unsigned long long offset,
+                    hwgat_stream_t stream) {
   int st = check_geometry2(B, F, K, d, heads, W, TP, shift, layout);
   if (st) return st;
+  if (!(attn_p >= 0.f) || attn_p >= 1.f) return HWGAT_ERR_SHAPE;
   if (!d_w || !d_b) return HWGAT_ERR_NULL;
   if (B == 0) {
     cudaMemsetAsync(d_w, 0, sizeof(float) * 3 * d * d, (cudaStream_t)stream);
@@ -178,6 +183,7 @@ int hwgat_attn2_bwd(const void* d_out, const void* xn, const void* w_qkv, const 
   a.xn = xn; a.w_qkv = w_qkv; a.b_qkv = b_qkv; a.bits = bits; a.threshold = threshold; a.d_out = d_out;
   a.d_xn = d_xn; a.d_w = d_w; a.d_b = d_b; a.workspace = workspace;
   a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
+  a.attn_p = attn_p; a.seed = seed; a.offset = offset;
   return attn2_bwd(a, W, (const __nv_bfloat16*)qkv, (cudaStream_t)stream);
 }
 

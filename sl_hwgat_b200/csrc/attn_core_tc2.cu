@@ -25,6 +25,7 @@
 // dQ [0,64) + dK [64,128) + dV [128,192) over the consumed S / dP.
 #include <cstdlib>
 
+#include "ew.cuh"
 #include "tc.cuh"
 
 namespace hwgat {
@@ -204,8 +205,37 @@ struct CoreArgs {
   bf16* dqkv;           // backward: [n, 3d]
   float threshold;
   int d, heads, tiles, stages;
+  // attention dropout (self.attn_drop on P, HWGATE.py:112): 16-bit threshold (0 = off), 1/(1-p), Philox stream
+  uint32_t drop_thresh;
+  float drop_scale;
+  unsigned long long seed, offset;
   Geo2 geo;
 };
+
+// keep flags of one query row's N probabilities (bit i = key i kept): one Philox call per 8 keys, counter =
+// ((global token row * heads + head) * N/8 + granule), identical in forward and backward
+template <int N>
+HW_DEV void attn_drop_flags(uint32_t (&kf)[N / 32], long long token_row, int head, const CoreArgs& p) {
+  const unsigned long long base = ((unsigned long long)token_row * p.heads + head) * (N / 8);
+#pragma unroll
+  for (int w = 0; w < N / 32; ++w) kf[w] = 0;
+#pragma unroll
+  for (int u = 0; u < N / 8; ++u) kf[u >> 2] |= keep8(base + u, p.offset, p.seed, p.drop_thresh) << (8 * (u & 3));
+}
+// row of P' = P o keep / (1-p) as bf16 (see store_row_bf16)
+template <int N>
+HW_DEV void store_row_bf16_dropped(uint32_t tile_saddr, int row, int col0, const float (&v)[N], const uint32_t (&kf)[N / 32],
+                                   float scale) {
+#pragma unroll
+  for (int u = 0; u < N / 8; ++u) {
+    const int col = col0 + 8 * u;
+    const uint32_t a = tile_saddr + (uint32_t)((col >> 6) * kTile + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4));
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = ((kf[u >> 2] >> (8 * (u & 3) + i)) & 1u) ? v[8 * u + i] * scale : 0.f;
+    sts128(a, pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // forward
@@ -332,7 +362,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
 #pragma unroll
         for (int w = 0; w < N / 32; ++w) mw[w] = mp[w];
       }
-      bf16* orow = p.out + (size_t)p.geo.token_row<N>(tile, row) * p.d + h * kHd;
+      const long long trow = p.geo.token_row<N>(tile, row);
+      bf16* orow = p.out + (size_t)trow * p.d + h * kHd;
       mbar_wait(&bars->s_full[sb], (j / 3) & 1);
       tc_fence_after();
       {
@@ -340,7 +371,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_fwd_tc2_kernel(const __
         tmem_row<N>(tq + col0, v);
         bool dead;
         masked_softmax_row<N, kTrain>(v, mw, p.threshold, tq + col0, dead);
-        store_row_bf16<N>(smem_u32(sP + set * kPBytes), row, col0, v);
+        if (p.drop_thresh) {
+          uint32_t kf[N / 32];
+          attn_drop_flags<N>(kf, trow, h, p);
+          store_row_bf16_dropped<N>(smem_u32(sP + set * kPBytes), row, col0, v, kf, p.drop_scale);
+        } else {
+          store_row_bf16<N>(smem_u32(sP + set * kPBytes), row, col0, v);
+        }
       }
       tc_fence_before();
       fence_proxy_async();
@@ -525,7 +562,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
 #pragma unroll
         for (int w = 0; w < N / 32; ++w) mw[w] = mp[w];
       }
-      bf16* grow = p.dqkv + (size_t)p.geo.token_row<N>(tile, row) * d3 + h * kHd;
+      const long long trow = p.geo.token_row<N>(tile, row);
+      bf16* grow = p.dqkv + (size_t)trow * d3 + h * kHd;
       mbar_wait(&bars->sdp_full[set], par);
       tc_fence_after();
       {
@@ -533,6 +571,15 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
         tmem_row<N>(tq + col0, v);
         bool dead;
         masked_softmax_row<N, kTrain>(v, mw, p.threshold, tq + col0, dead);
+        // attention dropout: O = (P o m) V with m = keep / (1-p), so dV uses P o m and dP enters as dP o m
+        uint32_t kf[N / 32];
+        const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
+        if (p.drop_thresh) {
+          attn_drop_flags<N>(kf, trow, h, p);
+        } else {
+#pragma unroll
+          for (int w = 0; w < N / 32; ++w) kf[w] = 0xFFFFFFFFu;
+        }
         // delta = sum_j P_j dP_j: dP streamed from TMEM in 32-column chunks (twice: once for delta, once for dS), so
         // a 128-column row of P stays in registers next to one chunk
         float delta = 0.f;
@@ -542,11 +589,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
           tmem_ld32(tq + 128 + col0 + 32 * c, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) delta = fmaf(v[32 * c + i], __uint_as_float(r[i]), delta);
+          for (int i = 0; i < 32; ++i)
+            delta = fmaf(v[32 * c + i], ((kf[c] >> i) & 1u) ? __uint_as_float(r[i]) * dscale : 0.f, delta);
         }
         // P: the previous item's dQ / dK MMAs must have finished reading the tile (it then held that item's dS)
         mbar_wait(&bars->pd_empty, (j & 1) ^ 1);
-        store_row_bf16<N>(smem_u32(sPD), row, col0, v);
+        if (p.drop_thresh) store_row_bf16_dropped<N>(smem_u32(sPD), row, col0, v, kf, dscale);
+        else store_row_bf16<N>(smem_u32(sPD), row, col0, v);
         tc_fence_before();
         fence_proxy_async();
         __syncwarp();
@@ -559,7 +608,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_core_bwd_tc2_kernel(const __
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            v[32 * c + i] = dead ? 0.f : v[32 * c + i] * (__uint_as_float(r[i]) - delta);
+            v[32 * c + i] = dead ? 0.f
+                                 : v[32 * c + i] * ((((kf[c] >> i) & 1u) ? __uint_as_float(r[i]) * dscale : 0.f) - delta);
         }
         mbar_wait(&bars->pv_done, j & 1);      // dV = P^T dO has read P: the tile may take dS
         store_row_bf16<N>(smem_u32(sPD), row, col0, v);
@@ -696,6 +746,7 @@ int attn2_fwd(const AttnArgs& a, int W, bf16* qkv, cudaStream_t s) {
   tc2::CoreArgs p{};
   p.bits = a.bits; p.out = (bf16*)a.out; p.threshold = a.threshold; p.d = a.d; p.heads = a.heads; p.tiles = (int)(a.tokens() / 128);
   p.stages = 3;
+  p.drop_thresh = drop_threshold16(a.attn_p); p.drop_scale = drop_scale16(p.drop_thresh); p.seed = a.seed; p.offset = a.offset;
   p.geo = tc2::make_geo2(a, W);
   const int items = p.tiles * p.heads;
   const int grid = items < 148 ? items : 148;
@@ -731,6 +782,7 @@ int attn2_bwd(const AttnArgs& a, int W, const bf16* qkv_saved, cudaStream_t s) {
   tc2::CoreArgs p{};
   p.bits = a.bits; p.dqkv = dqkv; p.threshold = a.threshold; p.d = d; p.heads = a.heads; p.tiles = (int)(a.tokens() / 128);
   p.stages = 3;
+  p.drop_thresh = drop_threshold16(a.attn_p); p.drop_scale = drop_scale16(p.drop_thresh); p.seed = a.seed; p.offset = a.offset;
   p.geo = tc2::make_geo2(a, W);
   const int items = p.tiles * p.heads;
   const int grid = items < 148 ? items : 148;

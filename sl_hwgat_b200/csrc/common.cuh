@@ -170,6 +170,8 @@ struct AttnArgs {
   const void* d_out;         // bwd
   void* d_xn; float* d_w; float* d_b;
   void* workspace;
+  float attn_p = 0.f;                       // attention dropout (K2b / K3b only)
+  unsigned long long seed = 0, offset = 0;
   int B, F, K, d, heads, shift, layout;
   long long tokens() const { return (long long)B * F * K; }
   int tiles() const { return B * (F / 2) * (K / 64); }

@@ -83,7 +83,7 @@ class MSA(_hw.MSA):
         xp = _pad_kp(x.reshape(B_f, TP, K, d), 2).reshape(B_f, TP * KP_PAD, d)
         ctx = ops.window_graph_attention(xp.to(torch.bfloat16), self.qkv.weight, self.qkv.bias, bits, self.num_heads,
                                          shift=0, threshold=None, layout=LAYOUT_WINDOWS, frames=f * TP, kps=KP_PAD,
-                                         window=KP_PAD)
+                                         window=KP_PAD, attn_drop=self._attn_p())
         ctx = ctx.reshape(B_f, TP, KP_PAD, d)[:, :, :K].reshape(B_f, TP_K, d)
         return self._project(ctx)
 

@@ -206,7 +206,7 @@ class _WindowGraphAttention2(torch.autograd.Function):
     False, in which case the backward re-projects them."""
 
     @staticmethod
-    def forward(ctx, xn, w_qkv, b_qkv, bits, threshold, heads, shift, layout, frames, kps, window, save_qkv):
+    def forward(ctx, xn, w_qkv, b_qkv, bits, threshold, heads, shift, layout, frames, kps, window, save_qkv, attn_p):
         lib = _lib.load()
         _need_cuda(xn, w_qkv, b_qkv, bits)
         if xn.dtype != torch.bfloat16:
@@ -224,21 +224,23 @@ class _WindowGraphAttention2(torch.autograd.Function):
         qkv = torch.empty((n_tok, 3 * d), dtype=torch.bfloat16, device=xn_c.device)
         ws_bytes = lib.hwgat_attn2_workspace_bytes(B, frames, kps, d, heads, 0, 1)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xn_c.device)
+        seed, off = _philox_stream(xn_c.device) if attn_p > 0 else (0, 0)
         with torch.cuda.device(xn_c.device):
             check(lib.hwgat_attn2_fwd(xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
                                       float(threshold), out.data_ptr(), qkv.data_ptr(), ws.data_ptr(), ws.numel(), B,
-                                      frames, kps, d, heads, window, TEMPORAL_PATCH, shift, layout, _stream()),
-                  "hwgat_attn2_fwd")
+                                      frames, kps, d, heads, window, TEMPORAL_PATCH, shift, layout, float(attn_p), seed,
+                                      off, _stream()), "hwgat_attn2_fwd")
         keep = save_qkv and any(ctx.needs_input_grad[:3])
         ctx.save_for_backward(xn_c, w_c, b_c, bits, qkv if keep else None)
-        ctx.meta = (float(threshold), heads, shift, layout, frames, kps, B, d, window, w_qkv.dtype, b_qkv.dtype)
+        ctx.meta = (float(threshold), heads, shift, layout, frames, kps, B, d, window, w_qkv.dtype, b_qkv.dtype,
+                    float(attn_p), seed, off)
         return out.view_as(xn)
 
     @staticmethod
     def backward(ctx, d_out):
         lib = _lib.load()
         xn_c, w_c, b_c, bits, qkv = ctx.saved_tensors
-        threshold, heads, shift, layout, frames, kps, B, d, window, w_dtype, b_dtype = ctx.meta
+        threshold, heads, shift, layout, frames, kps, B, d, window, w_dtype, b_dtype, attn_p, seed, off = ctx.meta
         g = d_out.to(torch.bfloat16).contiguous()
         d_xn = torch.empty_like(xn_c)
         d_w = torch.empty((3 * d, d), dtype=torch.float32, device=xn_c.device)
@@ -249,21 +251,23 @@ class _WindowGraphAttention2(torch.autograd.Function):
             check(lib.hwgat_attn2_bwd(g.data_ptr(), xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), _ptr(qkv),
                                       bits.data_ptr(), threshold, d_xn.data_ptr(), d_w.data_ptr(), d_b.data_ptr(),
                                       ws.data_ptr(), ws.numel(), B, frames, kps, d, heads, window, TEMPORAL_PATCH,
-                                      shift, layout, _stream()), "hwgat_attn2_bwd")
-        return (d_xn.view_as(d_out), d_w.to(w_dtype), d_b.to(b_dtype)) + (None,) * 9
+                                      shift, layout, attn_p, seed, off, _stream()), "hwgat_attn2_bwd")
+        return (d_xn.view_as(d_out), d_w.to(w_dtype), d_b.to(b_dtype)) + (None,) * 10
 
 
 def window_graph_attention(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, bits: torch.Tensor,
                            heads: int, shift: int = 0, threshold: Optional[float] = None,
                            layout: int = LAYOUT_BFKD, frames: Optional[int] = None,
                            kps: Optional[int] = None, window: int = WINDOW, impl: Optional[str] = None,
-                           save_qkv: bool = True) -> torch.Tensor:
+                           save_qkv: bool = True, attn_drop: float = 0.0) -> torch.Tensor:
     """Fused roll + window_partition + QKV + masked attention + window_reverse +
     roll back (HWGATE.py:197-201, 86-114, 207-215), without the output projection.
 
     xn: (B, F, K, d) for LAYOUT_BFKD, or (B*f*nW, 2*window, d) for LAYOUT_WINDOWS (then
     `frames` and `kps` must be given).  threshold None = eval mode.  window: keypoints per window
-    (16 = the reference; 32 and 64 are bf16 only).  impl: "fused" | "tc2" | None (= ops.ATTN_IMPL), see above."""
+    (16 = the reference; 32 and 64 are bf16 only).  impl: "fused" | "tc2" | None (= ops.ATTN_IMPL), see above.
+    attn_drop > 0: dropout on the attention probabilities (self.attn_drop, HWGATE.py:112; pass 0 in eval mode) - built
+    into K2b / K3b only, so it selects them (bf16)."""
     if layout == LAYOUT_BFKD:
         frames, kps = xn.shape[1], xn.shape[2]
     elif frames is None or kps is None:
@@ -272,9 +276,11 @@ def window_graph_attention(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.T
     if window not in WINDOWS:
         raise _lib.HwgatError(f"window_size {window} is not supported by the sm_100a kernels (16, 32, 64; no fallback)")
     impl = impl or ATTN_IMPL
-    if window != WINDOW or (impl == "tc2" and xn.dtype == torch.bfloat16):
+    if not 0.0 <= attn_drop < 1.0:
+        raise ValueError("attn_drop must be in [0, 1)")
+    if window != WINDOW or attn_drop > 0 or (impl == "tc2" and xn.dtype == torch.bfloat16):
         return _WindowGraphAttention2.apply(xn, w_qkv, b_qkv, bits, thr, heads, shift, layout, frames, kps, window,
-                                            save_qkv)
+                                            save_qkv, float(attn_drop))
     return _WindowGraphAttention.apply(xn, w_qkv, b_qkv, bits, thr, heads, shift, layout, frames, kps)
 
 

@@ -530,3 +530,23 @@ def test_smooth_cross_entropy_kernel(rows, classes, smooth):
     assert rel_inf(z.grad, zr.grad) < 1e-5
     # deterministic: two evaluations give the same bits
     assert SmoothedCrossEntropyLoss(smooth)(z.detach(), t).item() == SmoothedCrossEntropyLoss(smooth)(z.detach(), t).item()
+
+
+def test_env_autocast_switch_runs_the_bf16_kernels_without_a_source_change():
+    """HWGAT_AUTOCAST=bf16: Model.forward opens the autocast region itself, so the reference's unmodified loop
+    (model(x) without autocast, utils.py:102) takes the tcgen05 path; off by default."""
+    from sl_hwgat_b200.models import HWGATE
+    m, cfg, sd = build(16, 10)
+    m.eval()
+    x = O.synthetic_keypoints(2, 16, 2, seed=3).cuda()
+    with torch.no_grad():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            want = m(x)
+        fp32 = m(x)
+        HWGATE.AUTOCAST = "bf16"
+        try:
+            got = m(x)
+        finally:
+            HWGATE.AUTOCAST = ""
+    assert torch.equal(got, want) and not torch.equal(got, fp32)
+    assert rel_l2(got, fp32) < BF16_TOL

@@ -243,3 +243,95 @@ def test_fp32_larger_window_is_refused():
     with pytest.raises(_lib.HwgatError):
         ops.window_graph_attention(xn.to(torch.bfloat16).cuda(), w.float().cuda(), b.float().cuda(), dev_bits(32, 4, 0),
                                    2, window=8)
+
+
+# ------------------------------------------------------------------ attention dropout (self.attn_drop, HWGATE.py:112)
+def _revealing_inputs(W, d, h, B, F, seed=0):
+    """Inputs whose attention OUTPUT is the probability matrix: token j of a window carries a one-hot of its position
+    in the window (xn), the value projection copies that one-hot (v_j = e_j), so O[i, head, :N'] = P'[i, :N']."""
+    N = 2 * W
+    assert N <= 64 and d >= N
+    rng = np.random.default_rng(seed)
+    xn = torch.zeros(B, F, 64, d, dtype=torch.float64)
+    for fr in range(F):
+        for k in range(64):
+            xn[:, fr, k, (fr % 2) * W + k % W] = 1.0
+    xn[..., N:] = torch.from_numpy(rng.standard_normal((B, F, 64, d - N))) * 0.5      # makes the logits differ
+    w = torch.zeros(3 * d, d, dtype=torch.float64)
+    w[:2 * d, N:] = torch.from_numpy(rng.standard_normal((2 * d, d - N))) * 0.2        # q, k from the random part
+    for hh in range(h):
+        for e in range(N):
+            w[2 * d + hh * 64 + e, e] = 1.0                                            # v_j = one-hot(position of j)
+    b = torch.zeros(3 * d, dtype=torch.float64)
+    return xn, w, b
+
+
+@pytest.mark.parametrize("W", [16, 32])
+def test_attention_dropout_mask_rate_and_gradients(W):
+    """attn_drop > 0 (K2b / K3b): the dropped probabilities are exactly 0, the kept ones P / (1-p); the rate is p;
+    the mask is reproducible from the seed and differs between rows and heads; and the backward, checked against
+    oracle autograd with the recovered mask, regenerates the same mask."""
+    from sl_hwgat_b200 import ops
+    d, h, B, F, N, p_drop = 128, 2, 4, 8, 2 * W, 0.3
+    xn, w, b = _revealing_inputs(W, d, h, B, F)
+    bits = dev_bits(W, F, 0)
+    g = torch.from_numpy(np.random.default_rng(1).standard_normal((B, F, 64, d))).to(torch.bfloat16)
+
+    def run(p):
+        x_ = xn.to("cuda", torch.bfloat16).requires_grad_(True)
+        w_ = w.float().cuda().requires_grad_(True)
+        b_ = b.float().cuda().requires_grad_(True)
+        torch.manual_seed(7); torch.cuda.manual_seed(7)
+        y = ops.window_graph_attention(x_, w_, b_, bits, h, shift=0, threshold=None, window=W, attn_drop=p)
+        y.backward(g.cuda())
+        return y.detach().float().cpu(), x_.grad.float().cpu(), w_.grad.cpu()
+
+    y0, _, _ = run(0.0)
+    y1, dx1, dw1 = run(p_drop)
+    y1b, _, _ = run(p_drop)
+    assert torch.equal(y1, y1b)                                        # same seed, same mask
+    # O -> P: windows order, per head the first N channels
+    def probs(y):
+        yw = O.window_partition(y, W, 2)                               # (B_, N, d)
+        return torch.stack([yw[:, :, hh * 64: hh * 64 + N] for hh in range(h)], 1)     # (B_, h, N, N)
+    P0, P1 = probs(y0), probs(y1)
+    live = P0 > 1e-3
+    kept = P1 != 0
+    rate = 1.0 - (kept & live).sum().item() / live.sum().item()
+    assert abs(rate - p_drop) < 0.01, rate
+    scale = 1.0 / (1.0 - p_drop)
+    err = ((P1 - P0 * scale).abs()[kept & live] / (P0 * scale)[kept & live]).max().item()
+    assert err < 1.5e-2, err                                           # two bf16 roundings
+    assert not torch.equal(kept[:, 0], kept[:, 1]) and not torch.equal(kept[0], kept[1])
+    # backward against oracle autograd with the recovered mask
+    mask = O.combined_mask(adj_w(W), F, W, 2, 0)
+    drop = kept.double() * scale
+    x_, w_, b_ = (t.clone().requires_grad_(True) for t in rounded(xn, w, b, g.double())[:3])
+    yo = O.attention_core(x_, w_, b_, h, mask, W, 2, 0, None, bf16_points=True, drop_mask=drop)
+    (yo * g.double()).sum().backward()
+    assert rel_l2(y1, yo.detach()) < BF16_TOL
+    assert rel_l2(dx1, x_.grad) < BF16_TOL and rel_l2(dw1, w_.grad) < BF16_TOL
+
+
+def test_model_with_attention_dropout_trains():
+    """attn_drop_rate != 0 through the drop-in model (the reference passes it at model_params.py:256): runs on
+    K2b / K3b in train mode, is the identity in eval mode."""
+    from sl_hwgat_b200.models import HWGATE, model_params
+    p = model_params.HWGATEParams({"num_class": 10, "src_len": 16}, 2, "cuda")
+    p.drop_rate, p.attn_drop_rate = 0.0, 0.2
+    torch.manual_seed(0)
+    m = HWGATE.Model(*p.get_model_params()).cuda()
+    p.attn_drop_rate = 0.0
+    torch.manual_seed(0)
+    m0 = HWGATE.Model(*p.get_model_params()).cuda()
+    m0.load_state_dict(m.state_dict())
+    x = O.synthetic_keypoints(2, 16, 2, seed=3).cuda()
+    m.eval(); m0.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        assert torch.equal(m(x), m0(x))
+    m.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m(x)
+    out.float().sum().backward()
+    assert torch.isfinite(out).all()
+    assert all(torch.isfinite(q.grad).all() for q in m.parameters() if q.grad is not None)
