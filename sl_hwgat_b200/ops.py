@@ -67,6 +67,12 @@ def _require_binary(t: Optional[torch.Tensor], what: str) -> None:
 _CAST_CACHE: dict = {}
 
 
+def invalidate_cast_cache() -> None:
+    """Forget every cached low-precision parameter copy.  Needed after parameters were written through raw pointers,
+    which does not bump torch's `_version` counter: sl_hwgat_b200.optim.AdamW calls this after every step."""
+    _CAST_CACHE.clear()
+
+
 def cast_cached(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """Detached contiguous copy of a parameter in `dtype`, reused until the parameter is modified in place
     (`_version`) or re-allocated (`data_ptr`): inference re-casts nothing, training casts once per step

@@ -81,4 +81,8 @@ class AdamW(torch.optim.Optimizer):
                                                sizes, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                                                float(group["weight_decay"]), t, float(grad_scale),
                                                torch.cuda.current_stream().cuda_stream), "hwgat_adamw_step")
+        # the kernel wrote the parameters through raw pointers: torch's version counters did not move, so the cached
+        # bf16 copies the ops keep per parameter version (ops.cast_cached) must be dropped explicitly
+        from . import ops
+        ops.invalidate_cast_cache()
         return loss

@@ -335,3 +335,29 @@ def test_model_with_attention_dropout_trains():
     out.float().sum().backward()
     assert torch.isfinite(out).all()
     assert all(torch.isfinite(q.grad).all() for q in m.parameters() if q.grad is not None)
+
+
+@pytest.mark.parametrize("W", [16, 64])
+def test_tc2_128_keypoints(W):
+    """K = 128 keypoints: a temporal group spans two tiles (W = 16: 8 windows) or two whole-tile windows (W = 64)."""
+    from sl_hwgat_b200 import ops
+    d, h, B, F, K = 128, 2, 2, 8, 128
+    edges = [EDGES[0]] * (K // W)
+    adj = O.window_adjacency(edges, W, 2)
+    rng = np.random.default_rng(77 + W)
+    xn = torch.from_numpy(rng.standard_normal((B, F, K, d))).to(torch.bfloat16).double()
+    w = torch.from_numpy(rng.standard_normal((3 * d, d)) * 0.05).to(torch.bfloat16).double()
+    b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1).float().double()
+    g = torch.from_numpy(rng.standard_normal((B, F, K, d))).to(torch.bfloat16).double()
+    bits = ops.mask_build(torch.from_numpy(adj.astype(np.float32)).cuda(), F, 1, W, 2)
+    x_ = xn.to("cuda", torch.bfloat16).requires_grad_(True)
+    w_ = w.float().cuda().requires_grad_(True)
+    b_ = b.float().cuda().requires_grad_(True)
+    y = ops.window_graph_attention(x_, w_, b_, bits, h, shift=1, threshold=0.04, window=W, impl="tc2")
+    y.backward(g.to("cuda", torch.bfloat16))
+    mask = O.combined_mask(adj, F, W, 2, 1)
+    xo, wo, bo = (t.clone().requires_grad_(True) for t in (xn, w, b))
+    yo = O.attention_core(xo, wo, bo, h, mask, W, 2, 1, 0.04, bf16_points=True)
+    (yo * g).sum().backward()
+    assert rel_l2(y, yo.detach()) < BF16_TOL and rel_l2(x_.grad, xo.grad) < BF16_TOL
+    assert rel_l2(w_.grad, wo.grad) < BF16_TOL and rel_l2(b_.grad, bo.grad) < BF16_TOL
