@@ -434,10 +434,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--trace-allreduce", action="store_true", help="CUDA events around every gradient bucket")
+    ap.add_argument("--frames", type=int, default=0, help="override the config's sequence length T (sweeps)")
+    ap.add_argument("--window", type=int, default=0, help="override the config's window_size W: 16, 32, 64 (sweeps)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     mode, cfg_batch, what = set_config(args.config)
+    if args.frames or args.window:
+        global T_FRAMES, WINDOW
+        T_FRAMES, WINDOW = args.frames or T_FRAMES, args.window or WINDOW
+        what += f" [overridden for a sweep: T={T_FRAMES}, window_size={WINDOW}]"
     train = mode == "train"
 
     # stdout carries exactly one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG >= VERSION, so a
