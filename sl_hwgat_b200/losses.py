@@ -1,10 +1,9 @@
 """Label-smoothed cross entropy with the reference's class name and semantics
 (hwgat/losses/SmoothCrossEntropy.py:15-39, smooth_factor 0.01): the criterion
-the fwd+bwd metric is quoted with.  On CUDA tensors it is kernel K14
+the fwd+bwd metric is quoted with.  It is kernel K14
 (sl_hwgat_b200.ops.smooth_cross_entropy: one pass per row, deterministic mean,
-fused backward); CPU tensors - the reference evaluates its loss wherever its
-tensors live - take the same four-line formula in PyTorch."""
-import torch
+fused backward).  Like the rest of the package it has no CPU path: logits that
+are not on a CUDA device raise."""
 import torch.nn as nn
 
 from sl_hwgat_b200 import ops
@@ -16,9 +15,7 @@ class SmoothedCrossEntropyLoss(nn.Module):
         self.smooth_factor = smooth_factor
 
     def forward(self, input, target):
-        if input.is_cuda and input.dim() == 2:
-            return ops.smooth_cross_entropy(input, target, self.smooth_factor)
-        logp = torch.log_softmax(input.float(), dim=-1)
-        nll = -logp.gather(-1, target.unsqueeze(-1)).squeeze(-1)
-        uniform = -logp.mean(dim=-1)
-        return ((1.0 - self.smooth_factor) * nll + self.smooth_factor * uniform).mean()
+        # (rows, classes) logits, (rows,) class indices; anything else is flattened to that like log_softmax(dim=-1)
+        if input.dim() != 2:
+            input, target = input.reshape(-1, input.shape[-1]), target.reshape(-1)
+        return ops.smooth_cross_entropy(input, target, self.smooth_factor)

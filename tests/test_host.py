@@ -90,6 +90,9 @@ def test_product_path_fails_loudly_without_cuda():
     from sl_hwgat_b200 import ops
     with pytest.raises(_lib.HwgatError):
         ops.temporal_merge(torch.zeros(1, 4, 64, 128))
+    from sl_hwgat_b200.losses import SmoothedCrossEntropyLoss
+    with pytest.raises(_lib.HwgatError):
+        SmoothedCrossEntropyLoss()(torch.zeros(2, 5), torch.zeros(2, dtype=torch.long))
     if not torch.cuda.is_available():
         from sl_hwgat_b200.models import model_params
         with pytest.raises(RuntimeError):
@@ -213,3 +216,23 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_header_is_plain_c_and_links_from_a_c_host(tmp_path):
+    """include/hwgat_b200.h compiles as C99 and a C program linked against the library can call it (no GPU needed for
+    the housekeeping entry points): the boundary carries no C++ or torch types."""
+    import shutil
+    import subprocess
+    from sl_hwgat_b200 import _lib
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    _lib.load()
+    exe = str(tmp_path / "host_check")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_abi", "host_check.c"), "-o", exe, "-L", libdir, "-lhwgat_b200",
+           "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "c abi ok" in r.stdout, r.stdout + r.stderr
