@@ -361,3 +361,15 @@ def test_tc2_128_keypoints(W):
     (yo * g).sum().backward()
     assert rel_l2(y, yo.detach()) < BF16_TOL and rel_l2(x_.grad, xo.grad) < BF16_TOL
     assert rel_l2(w_.grad, wo.grad) < BF16_TOL and rel_l2(b_.grad, bo.grad) < BF16_TOL
+
+
+def test_tc2_empty_batch():
+    from sl_hwgat_b200 import ops
+    bits = dev_bits(32, 4, 0)
+    w = torch.zeros(384, 128, device="cuda", requires_grad=True)
+    b = torch.zeros(384, device="cuda", requires_grad=True)
+    x = torch.empty(0, 4, 64, 128, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y = ops.window_graph_attention(x, w, b, bits, 2, window=32)
+    assert y.shape == (0, 4, 64, 128)
+    y.sum().backward()
+    assert float(w.grad.abs().sum()) == 0.0 and float(b.grad.abs().sum()) == 0.0
