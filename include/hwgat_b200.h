@@ -137,8 +137,15 @@ int hwgat_attn2_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const
 int hwgat_attn2_bwd(const void* d_out, const void* xn, const void* w_qkv, const float* b_qkv, const void* qkv,
                     const uint32_t* bits, float threshold, void* d_xn, float* d_w, float* d_b, void* workspace,
                     size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int TP, int shift,
-                    int layout, float attn_p, unsigned long long seed, unsigned long long offset,
+                    int layout, int qk_perm, float attn_p, unsigned long long seed, unsigned long long offset,
                     hwgat_stream_t stream);
+/* Hybrid for the reference window: K2 (hwgat_attn_fwd, bf16) that also KEEPS the q (scaled), k, v rows it formed in
+ * `qkv` (n x 3d bf16; q and k with the columns of every head permuted like K3's dQKV, v plain), so that the backward
+ * can be hwgat_attn2_bwd(..., qkv, ..., qk_perm = 1, ...) - K3b's tcgen05 core without the QKV recompute of K3 and
+ * without a projection GEMM.  Workspace as hwgat_attn_fwd.                                                        */
+int hwgat_attn_fwd_keep(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, float threshold,
+                        void* out, void* qkv, void* workspace, size_t workspace_bytes, int B, int F, int K, int d,
+                        int heads, int W, int TP, int shift, int layout, hwgat_stream_t stream);
 
 /* ---- rest of the block, bf16 / autocast path --------------------------
  * Bandwidth-bound fusions of the PyTorch elementwise chains of PartAttentionBlock.forward

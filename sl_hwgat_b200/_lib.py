@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("HWGAT_B200_LIB") or os.path.join(HERE, "lib", "libhwg
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # name -> (restype, argtypes); must list every symbol of include/hwgat_b200.h
 SIGNATURES = {
@@ -33,8 +33,10 @@ SIGNATURES = {
     "hwgat_attn2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t]
                         + [c_int] * 9 + [c_float, c_ulonglong, c_ulonglong, c_void_p]),
     "hwgat_attn2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_size_t] + [c_int] * 9 + [c_float, c_ulonglong, c_ulonglong,
-                                                                               c_void_p]),
+                                c_void_p, c_void_p, c_size_t] + [c_int] * 10 + [c_float, c_ulonglong, c_ulonglong,
+                                                                                c_void_p]),
+    "hwgat_attn_fwd_keep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                    c_size_t] + [c_int] * 9 + [c_void_p]),
     "hwgat_ln_fwd": (c_int, [c_void_p] * 6 + [c_longlong, c_int, c_float, c_void_p]),
     "hwgat_ln_bwd": (c_int, [c_void_p] * 9 + [c_longlong, c_int, c_void_p]),
     "hwgat_bda_ln_fwd": (c_int, [c_void_p] * 9 + [c_longlong, c_int, c_float, c_float, c_ulonglong, c_ulonglong,

@@ -29,7 +29,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 11; }
+int hwgat_version(void) { return 12; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -94,6 +94,25 @@ int hwgat_attn_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const 
   a.xn = xn; a.w_qkv = w_qkv; a.b_qkv = b_qkv; a.bits = bits; a.threshold = threshold; a.out = out;
   a.workspace = workspace; a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
   return dtype == HWGAT_F32 ? attn_fwd_f32(a, (cudaStream_t)stream) : attn_fwd_bf16(a, (cudaStream_t)stream);
+}
+
+int hwgat_attn_fwd_keep(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, float threshold,
+                        void* out, void* qkv, void* workspace, size_t workspace_bytes, int B, int F, int K, int d,
+                        int heads, int W, int TP, int shift, int layout, hwgat_stream_t stream) {
+  int st = check_geometry(B, F, K, d, heads, W, TP, shift, layout, HWGAT_BF16);
+  if (st) return st;
+  if (B == 0) return HWGAT_OK;
+  if (!xn || !w_qkv || !b_qkv || !bits || !out || !qkv) return HWGAT_ERR_NULL;
+  if (misaligned(xn) || misaligned(w_qkv) || misaligned(out) || misaligned(b_qkv) || misaligned(workspace) ||
+      misaligned(qkv))
+    return HWGAT_ERR_ALIGN;
+  const size_t need = hwgat_attn_workspace_bytes(B, F, K, d, heads, HWGAT_BF16, 0);
+  if (!workspace || workspace_bytes < need) return HWGAT_ERR_WORKSPACE;
+  AttnArgs a{};
+  a.xn = xn; a.w_qkv = w_qkv; a.b_qkv = b_qkv; a.bits = bits; a.threshold = threshold; a.out = out;
+  a.qkv_out = qkv;
+  a.workspace = workspace; a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
+  return attn_fwd_bf16(a, (cudaStream_t)stream);
 }
 
 int hwgat_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits,
@@ -162,11 +181,12 @@ int hwgat_attn2_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const
 int hwgat_attn2_bwd(const void* d_out, const void* xn, const void* w_qkv, const float* b_qkv, const void* qkv,
                     const uint32_t* bits, float threshold, void* d_xn, float* d_w, float* d_b, void* workspace,
                     size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int TP, int shift,
-                    int layout, float attn_p, unsigned long long seed, unsigned long long offset,
+                    int layout, int qk_perm, float attn_p, unsigned long long seed, unsigned long long offset,
                     hwgat_stream_t stream) {
   int st = check_geometry2(B, F, K, d, heads, W, TP, shift, layout);
   if (st) return st;
   if (!(attn_p >= 0.f) || attn_p >= 1.f) return HWGAT_ERR_SHAPE;
+  if (qk_perm && !qkv) return HWGAT_ERR_NULL;      // only a kept qkv can be permuted (the re-projection is not)
   if (!d_w || !d_b) return HWGAT_ERR_NULL;
   if (B == 0) {
     cudaMemsetAsync(d_w, 0, sizeof(float) * 3 * d * d, (cudaStream_t)stream);
@@ -183,7 +203,7 @@ int hwgat_attn2_bwd(const void* d_out, const void* xn, const void* w_qkv, const 
   a.xn = xn; a.w_qkv = w_qkv; a.b_qkv = b_qkv; a.bits = bits; a.threshold = threshold; a.d_out = d_out;
   a.d_xn = d_xn; a.d_w = d_w; a.d_b = d_b; a.workspace = workspace;
   a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
-  a.attn_p = attn_p; a.seed = seed; a.offset = offset;
+  a.attn_p = attn_p; a.seed = seed; a.offset = offset; a.qk_perm = qk_perm;
   return attn2_bwd(a, W, (const __nv_bfloat16*)qkv, (cudaStream_t)stream);
 }
 

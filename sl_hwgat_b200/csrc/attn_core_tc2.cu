@@ -796,10 +796,13 @@ int attn2_bwd(const AttnArgs& a, int W, const bf16* qkv_saved, cudaStream_t s) {
   }
   if (st) return st;
   // d_xn[n, d] = dQKV[n, 3d] . Wqkv[3d, d]  (against Wqkv^T so that both operands are K-major)
-  if ((st = transpose_bf16((const bf16*)a.w_qkv, wt, d3, d, s, false))) return st;
+  // qk_perm (q, k kept by K2 with permuted columns): dQ follows k's column order and dK follows q's, so the first 2d
+  // columns of dQKV are permuted and the two weight-side GEMMs undo it as they do for K3; dV follows dO: plain
+  const bool perm = a.qk_perm != 0;
+  if ((st = transpose_bf16((const bf16*)a.w_qkv, wt, d3, d, s, perm, 2 * d))) return st;
   if ((st = gemm_tc_nt_epi_none(dqkv, wt, (bf16*)a.d_xn, n, d, d3, s))) return st;
   // d_w[3d, d] = dQKV^T . xn ; d_b = column sums of dQKV
-  return gemm_tc_tn(dqkv, (const bf16*)a.xn, a.d_w, a.d_b, d3, d, n, s, false);
+  return gemm_tc_tn(dqkv, (const bf16*)a.xn, a.d_w, a.d_b, d3, d, n, s, perm, 2 * d);
 }
 
 }  // namespace hwgat

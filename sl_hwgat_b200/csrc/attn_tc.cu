@@ -305,6 +305,7 @@ struct FwdTcArgs {
   const bf16* bias_tiles;  // (heads, 192 x 16) core-matrix tiles made by prep_qkv_kernel
   const uint32_t* bits;
   bf16* out;
+  bf16* qkv;               // optional [n, 3d]: q (scaled), k, v as the attention saw them, kept for K3b (hybrid backward)
   float threshold;
   int heads, tiles, w_stages;
   int pace;   // 1: one chunk of MMAs in flight at a time (tc_issuer)
@@ -378,6 +379,7 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   if ((st = make_tmap_2d(&tmW, wp, (uint64_t)3 * d, (uint64_t)d, 64))) return st;
   FwdTcArgs p;
   p.bias_tiles = bias_tiles; p.bits = a.bits; p.out = (bf16*)a.out; p.threshold = a.threshold;
+  p.qkv = (bf16*)a.qkv_out;
   p.heads = a.heads; p.tiles = a.tiles(); p.w_stages = stages; p.pace = d == 128;   // forward: see tc_issuer
   p.geo = make_geom(a.F, a.K, d, a.shift, a.layout);
   const int grid = p.tiles < 148 ? p.tiles : 148;
@@ -477,6 +479,36 @@ HW_DEV void store_rows_16x64_perm(const float (&c)[8][4], float mul, bf16* __res
   st_global32(p1 + 16 * t, r1);
 }
 
+// bf16 block registers of 16 rows x 64 columns (rows_to_blocks layout) -> global rows p0 (row g) and p1 (row g+8).
+// _perm: in the permuted column order of the dQKV workspace (one 32-byte store per row, no shuffles); the plain form
+// transposes inside the quad like store_rows_16x64.
+HW_DEV void store_blocks_16x64_perm(const uint32_t (&f)[4][4], bf16* __restrict__ p0, bf16* __restrict__ p1, int t) {
+  uint32_t r0[8], r1[8];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    r0[nt] = f[nt >> 1][(nt & 1) * 2];
+    r1[nt] = f[nt >> 1][(nt & 1) * 2 + 1];
+  }
+  st_global32(p0 + 16 * t, r0);
+  st_global32(p1 + 16 * t, r1);
+}
+HW_DEV void store_blocks_16x64(const uint32_t (&f)[4][4], bf16* __restrict__ p0, bf16* __restrict__ p1, int t) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r0[4], r1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nt = 4 * half + j;
+      r0[j] = f[nt >> 1][(nt & 1) * 2];
+      r1[j] = f[nt >> 1][(nt & 1) * 2 + 1];
+    }
+    quad_transpose4(r0, t);
+    quad_transpose4(r1, t);
+    *reinterpret_cast<int4*>(p0 + 32 * half + 8 * t) = make_int4((int)r0[0], (int)r0[1], (int)r0[2], (int)r0[3]);
+    *reinterpret_cast<int4*>(p1 + 32 * half + 8 * t) = make_int4((int)r1[0], (int)r1[1], (int)r1[2], (int)r1[3]);
+  }
+}
+
 // ===========================================================================
 // K2 kernel.  Attention warps: ONE warp per window (all 32 query rows); the two warp sets (warps 4-7,
 // 8-11) work on alternate heads, one TMEM accumulator each.  Every q / k / v row is converted from
@@ -564,9 +596,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
     const uint32_t tb = tmem + set * kAccStride + ((uint32_t)(32 * win) << 16);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-      size_t orow[4];
+      size_t orow[4], qrow[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) orow[r] = (size_t)p.geo.token_row(tile, 32 * win + 8 * r + g) * d;
+      for (int r = 0; r < 4; ++r) {
+        const size_t tr = (size_t)p.geo.token_row(tile, 32 * win + 8 * r + g);
+        orow[r] = tr * d;
+        qrow[r] = tr * 3 * d;
+      }
       const uint32_t* mw = p.bits + p.geo.mask_base(tile) + 32 * win;
       float mk0[2][8], mk1[2][8];
       build_row_masks(mw[g], mw[g + 8], t, mk0);
@@ -603,6 +639,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->acc_empty[set]);  // last TMEM read of this head
+        if (p.qkv) {
+          // keep q (scaled), k, v for the hybrid backward (K3b): q and k with the columns of the head permuted like
+          // dQKV (S = q k^T does not care, and the weight-side GEMMs undo it for free), v in the plain order because
+          // dP = dO v^T meets the un-permuted dO
+          bf16* q0 = p.qkv + qrow[0] + h * kHd;
+          bf16* q1 = p.qkv + qrow[1] + h * kHd;
+          bf16* q2 = p.qkv + qrow[2] + h * kHd;
+          bf16* q3 = p.qkv + qrow[3] + h * kHd;
+          store_blocks_16x64_perm(qa0, q0, q1, t);
+          store_blocks_16x64_perm(qa1, q2, q3, t);
+          store_blocks_16x64_perm(kb0, q0 + d, q1 + d, t);
+          store_blocks_16x64_perm(kb1, q2 + d, q3 + d, t);
+          store_blocks_16x64(vb0, q0 + 2 * d, q1 + 2 * d, t);
+          store_blocks_16x64(vb1, q2 + 2 * d, q3 + 2 * d, t);
+        }
         float s0[4][4], s1[4][4];
         zero4x4(s0);
         zero4x4(s1);

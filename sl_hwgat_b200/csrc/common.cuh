@@ -170,6 +170,8 @@ struct AttnArgs {
   const void* d_out;         // bwd
   void* d_xn; float* d_w; float* d_b;
   void* workspace;
+  void* qkv_out = nullptr;                  // K2 only: keep q, k, v for the hybrid backward (K3b)
+  int qk_perm = 0;                          // K3b only: the q and k thirds of the saved qkv are column-permuted (from K2)
   float attn_p = 0.f;                       // attention dropout (K2b / K3b only)
   unsigned long long seed = 0, offset = 0;
   int B, F, K, d, heads, shift, layout;
@@ -186,8 +188,9 @@ int attn2_bwd(const AttnArgs& a, int W, const __nv_bfloat16* qkv_saved, cudaStre
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t s);
 int attn_bwd_tc(const AttnArgs& a, __nv_bfloat16* dqkv, cudaStream_t s);
 int gemm_tc_tn(const __nv_bfloat16* A, const __nv_bfloat16* Bm, float* C, float* colsum, int M, int N, long long Kd,
-               cudaStream_t s, bool perm64 = false);
-int transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int R, int Cc, cudaStream_t s, bool perm64 = false);
+               cudaStream_t s, bool perm64 = false, int perm_limit = 0x7fffffff);   // perm64 applies to rows < perm_limit
+int transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int R, int Cc, cudaStream_t s, bool perm64 = false,
+                   int perm_limit = 0x7fffffff);
 bool gemm_pair_enabled();
 bool set_gemm_pair(bool on);
 int gemm_tc_nt_epi_none(const __nv_bfloat16* A, const __nv_bfloat16* Bt, __nv_bfloat16* C, long long M, int N, int K,

@@ -65,7 +65,8 @@ HW_DEV int perm64_inv(int r) {
   const int p = r & 63, t = p >> 4, nt = (p >> 1) & 7, b = p & 1;
   return (r & ~63) + 8 * nt + 2 * t + b;
 }
-__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R, int Cc, bool perm64) {
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R, int Cc, bool perm64,
+                                      int perm_limit) {
   __shared__ bf16 t[32][33];
   int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8)
@@ -73,12 +74,12 @@ __global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restr
   __syncthreads();
   int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += 8)
-    if (c0 + i < Cc && r < R) out[(size_t)(c0 + i) * R + (perm64 ? perm64_fwd(r) : r)] = t[threadIdx.x][i];
+    if (c0 + i < Cc && r < R) out[(size_t)(c0 + i) * R + (perm64 && r < perm_limit ? perm64_fwd(r) : r)] = t[threadIdx.x][i];
 }
 
-int transpose_bf16(const bf16* in, bf16* out, int R, int Cc, cudaStream_t s, bool perm64) {
+int transpose_bf16(const bf16* in, bf16* out, int R, int Cc, cudaStream_t s, bool perm64, int perm_limit) {
   if (perm64 && R % 64) return HWGAT_ERR_UNSUPPORTED;
-  transpose_bf16_kernel<<<dim3((Cc + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, s>>>(in, out, R, Cc, perm64);
+  transpose_bf16_kernel<<<dim3((Cc + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, s>>>(in, out, R, Cc, perm64, perm_limit);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
                                                             const __grid_constant__ CUtensorMap tmB,
                                                             float* __restrict__ C, float* __restrict__ colsum, int M,
                                                             int N, int k_blocks_total, int k_blocks_per_cta,
-                                                            bool perm64) {
+                                                            bool perm64, int perm_limit) {
   using Cfg = GemmTnCfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int arow = mb * 128 + q * 32 + lane;              // row of A^T = column of A
-    const int row = perm64 ? perm64_inv(arow) : arow;       // A's columns are K3's permuted dQKV columns: undo
+    const int row = perm64 && arow < perm_limit ? perm64_inv(arow) : arow;   // A's columns are K3's permuted dQKV columns: undo
     float* crow = C + (size_t)row * N + (size_t)nb * BN;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
 
 template <int BN>
 static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd,
-                     cudaStream_t s, bool perm64) {
+                     cudaStream_t s, bool perm64, int perm_limit) {
   using Cfg = GemmTnCfg<BN>;
   static PerDeviceOnce once;
   once.run([] { cudaFuncSetAttribute(gemm_tc_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem); });
@@ -254,7 +255,7 @@ static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int
   if (splits > kblocks) splits = kblocks;
   const int per = (kblocks + splits - 1) / splits;
   splits = (kblocks + per - 1) / per;
-  gemm_tc_tn_kernel<BN><<<dim3(tiles, splits), 192, Cfg::kSmem, s>>>(tmA, tmB, C, colsum, M, N, kblocks, per, perm64);
+  gemm_tc_tn_kernel<BN><<<dim3(tiles, splits), 192, Cfg::kSmem, s>>>(tmA, tmB, C, colsum, M, N, kblocks, per, perm64, perm_limit);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_pair_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  float* __restrict__ C, float* __restrict__ colsum, int M,
                                                                  int N, int k_blocks_total, int k_blocks_per_cta,
-                                                                 bool perm64) {
+                                                                 bool perm64, int perm_limit) {
   using Cfg = GemmTnPairCfg;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_pair_kernel(const __grid_co
     tc_fence_after();
     const int arow = (2 * mb + (int)rank) * 128 + q * 32 + lane;
     if (arow < M) {   // warp-uniform: M % 128 == 0
-      const int row = perm64 ? perm64_inv(arow) : arow;
+      const int row = perm64 && arow < perm_limit ? perm64_inv(arow) : arow;
       float* crow = C + (size_t)row * N + (size_t)nb * 256;
 #pragma unroll 1
       for (int c = 0; c < 256; c += 32) {
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_pair_kernel(const __grid_co
 }
 
 static int launch_tn_pair(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd,
-                          cudaStream_t s, bool perm64) {
+                          cudaStream_t s, bool perm64, int perm_limit) {
   using Cfg = GemmTnPairCfg;
   static PerDeviceOnce once;
   once.run([] { cudaFuncSetAttribute(gemm_tc_tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem); });
@@ -428,7 +429,7 @@ static int launch_tn_pair(const bf16* A, const bf16* Bm, float* C, float* colsum
   cfg.stream = s;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_tn_pair_kernel, tmA, tmB, C, colsum, M, N, kblocks, per, perm64);
+  cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_tn_pair_kernel, tmA, tmB, C, colsum, M, N, kblocks, per, perm64, perm_limit);
   count_launch();
   return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
 }
@@ -436,16 +437,16 @@ static int launch_tn_pair(const bf16* A, const bf16* Bm, float* C, float* colsum
 // C[M,N] = A[Kd,M]^T . B[Kd,N] (fp32 out), colsum[M] = column sums of A; M % 128 == 0, N % 128 == 0, Kd % 64 == 0
 // perm64: rows of C / entries of colsum are written through the inverse of K3's dQKV column permutation
 int gemm_tc_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd, cudaStream_t s,
-               bool perm64) {
+               bool perm64, int perm_limit) {
   if (M % 128 || N % 128 || Kd % 64) return HWGAT_ERR_UNSUPPORTED;
   if (N % 256 == 0) {
     // CTA pairs (256 x 256 tiles): +10-15 % once there are enough tiles to split the token range over 74 pairs evenly
     // (measured at M x N = 1536 x 512, 1024 x 512, 512 x 1024, 768 x 256; slower at two tiles)
     if (gemm_pair_enabled() && M >= 256 && ((M + 255) / 256) * (N / 256) >= 3)
-      return launch_tn_pair(A, Bm, C, colsum, M, N, Kd, s, perm64);
-    return launch_tn<256>(A, Bm, C, colsum, M, N, Kd, s, perm64);
+      return launch_tn_pair(A, Bm, C, colsum, M, N, Kd, s, perm64, perm_limit);
+    return launch_tn<256>(A, Bm, C, colsum, M, N, Kd, s, perm64, perm_limit);
   }
-  return launch_tn<128>(A, Bm, C, colsum, M, N, Kd, s, perm64);
+  return launch_tn<128>(A, Bm, C, colsum, M, N, Kd, s, perm64, perm_limit);
 }
 
 }  // namespace hwgat

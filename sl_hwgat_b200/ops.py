@@ -26,7 +26,10 @@ HEAD_DIM = 64
 #   "fused" : K2 / K3 (attn_tc.cu) - QKV projection inside the attention kernel, 32 x 32 windows on mma.sync
 #   "tc2"   : K2b / K3b (attn_core_tc2.cu) - projection GEMM + attention core with every product on tcgen05
 # W = 32 / 64 always take "tc2" (the only kernels built for them).  HWGAT_ATTN_IMPL overrides for A/B runs.
+#   "hybrid": K2 forward that also keeps its q, k, v rows + K3b backward on them (no recompute, no projection GEMM)
 ATTN_IMPL = os.environ.get("HWGAT_ATTN_IMPL", "fused")
+# with "fused": widths from which the hybrid is used (0 = never); HWGAT_HYBRID_MIN_D overrides for A/B runs
+HYBRID_MIN_D = int(os.environ.get("HWGAT_HYBRID_MIN_D", "0"))
 
 
 def _need_cuda(*tensors: torch.Tensor) -> None:
@@ -164,7 +167,7 @@ class _WindowGraphAttention(torch.autograd.Function):
     residual stream; forward saves only its inputs (K3 recomputes)."""
 
     @staticmethod
-    def forward(ctx, xn, w_qkv, b_qkv, bits, threshold, heads, shift, layout, frames, kps):
+    def forward(ctx, xn, w_qkv, b_qkv, bits, threshold, heads, shift, layout, frames, kps, hybrid=False):
         lib = _lib.load()
         _need_cuda(xn, w_qkv, b_qkv, bits)
         code = _dtype_code(xn)
@@ -179,23 +182,42 @@ class _WindowGraphAttention(torch.autograd.Function):
         out = torch.empty_like(xn_c)
         ws_bytes = lib.hwgat_attn_workspace_bytes(B, frames, kps, d, heads, code, 0)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xn_c.device) if ws_bytes else None
+        # hybrid (bf16, gradients wanted): K2 also keeps the q, k, v rows it formed, and the backward is K3b's
+        # tcgen05 core on them (no QKV recompute) followed by the same d_xn / d_w GEMMs
+        hybrid = bool(hybrid) and code == BF16 and any(ctx.needs_input_grad[:3]) and B > 0
+        qkv = torch.empty((n_tok, 3 * d), dtype=torch.bfloat16, device=xn_c.device) if hybrid else None
         with torch.cuda.device(xn_c.device):
-            check(lib.hwgat_attn_fwd(xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
-                                     float(threshold), out.data_ptr(), _ptr(ws), ws_bytes, B, frames, kps, d, heads,
-                                     WINDOW, TEMPORAL_PATCH, shift, layout, code, _stream()), "hwgat_attn_fwd")
-        ctx.save_for_backward(xn_c, w_c, b_c, bits)
+            if hybrid:
+                check(lib.hwgat_attn_fwd_keep(xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
+                                              float(threshold), out.data_ptr(), qkv.data_ptr(), _ptr(ws), ws_bytes, B,
+                                              frames, kps, d, heads, WINDOW, TEMPORAL_PATCH, shift, layout, _stream()),
+                      "hwgat_attn_fwd_keep")
+            else:
+                check(lib.hwgat_attn_fwd(xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
+                                         float(threshold), out.data_ptr(), _ptr(ws), ws_bytes, B, frames, kps, d, heads,
+                                         WINDOW, TEMPORAL_PATCH, shift, layout, code, _stream()), "hwgat_attn_fwd")
+        ctx.save_for_backward(xn_c, w_c, b_c, bits, qkv)
         ctx.meta = (float(threshold), heads, shift, layout, frames, kps, B, d, code, w_qkv.dtype, b_qkv.dtype)
         return out.view_as(xn)
 
     @staticmethod
     def backward(ctx, d_out):
         lib = _lib.load()
-        xn_c, w_c, b_c, bits = ctx.saved_tensors
+        xn_c, w_c, b_c, bits, qkv = ctx.saved_tensors
         threshold, heads, shift, layout, frames, kps, B, d, code, w_dtype, b_dtype = ctx.meta
         g = d_out.to(xn_c.dtype).contiguous()
         d_xn = torch.empty_like(xn_c)
         d_w = torch.empty((3 * d, d), dtype=torch.float32, device=xn_c.device)
         d_b = torch.empty((3 * d,), dtype=torch.float32, device=xn_c.device)
+        if qkv is not None:       # hybrid: K3b on the q, k, v kept by K2 (q, k column-permuted: qk_perm = 1)
+            ws_bytes = lib.hwgat_attn2_workspace_bytes(B, frames, kps, d, heads, 1, 1)
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xn_c.device)
+            with torch.cuda.device(xn_c.device):
+                check(lib.hwgat_attn2_bwd(g.data_ptr(), xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), qkv.data_ptr(),
+                                          bits.data_ptr(), threshold, d_xn.data_ptr(), d_w.data_ptr(), d_b.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), B, frames, kps, d, heads, WINDOW, TEMPORAL_PATCH,
+                                          shift, layout, 1, 0.0, 0, 0, _stream()), "hwgat_attn2_bwd")
+            return (d_xn.view_as(d_out), d_w.to(w_dtype), d_b.to(b_dtype)) + (None,) * 8
         ws_bytes = lib.hwgat_attn_workspace_bytes(B, frames, kps, d, heads, code, 1)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xn_c.device)
         with torch.cuda.device(xn_c.device):
@@ -203,7 +225,7 @@ class _WindowGraphAttention(torch.autograd.Function):
                                      threshold, d_xn.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), ws.data_ptr(),
                                      ws.numel(), B, frames, kps, d, heads, WINDOW, TEMPORAL_PATCH, shift, layout,
                                      code, _stream()), "hwgat_attn_bwd")
-        return (d_xn.view_as(d_out), d_w.to(w_dtype), d_b.to(b_dtype), None, None, None, None, None, None, None)
+        return (d_xn.view_as(d_out), d_w.to(w_dtype), d_b.to(b_dtype)) + (None,) * 8
 
 
 class _WindowGraphAttention2(torch.autograd.Function):
@@ -257,7 +279,7 @@ class _WindowGraphAttention2(torch.autograd.Function):
             check(lib.hwgat_attn2_bwd(g.data_ptr(), xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), _ptr(qkv),
                                       bits.data_ptr(), threshold, d_xn.data_ptr(), d_w.data_ptr(), d_b.data_ptr(),
                                       ws.data_ptr(), ws.numel(), B, frames, kps, d, heads, window, TEMPORAL_PATCH,
-                                      shift, layout, attn_p, seed, off, _stream()), "hwgat_attn2_bwd")
+                                      shift, layout, 0, attn_p, seed, off, _stream()), "hwgat_attn2_bwd")
         return (d_xn.view_as(d_out), d_w.to(w_dtype), d_b.to(b_dtype)) + (None,) * 10
 
 
@@ -287,7 +309,8 @@ def window_graph_attention(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.T
     if window != WINDOW or attn_drop > 0 or (impl == "tc2" and xn.dtype == torch.bfloat16):
         return _WindowGraphAttention2.apply(xn, w_qkv, b_qkv, bits, thr, heads, shift, layout, frames, kps, window,
                                             save_qkv, float(attn_drop))
-    return _WindowGraphAttention.apply(xn, w_qkv, b_qkv, bits, thr, heads, shift, layout, frames, kps)
+    hybrid = impl == "hybrid" or (impl == "fused" and HYBRID_MIN_D and xn.shape[-1] >= HYBRID_MIN_D)
+    return _WindowGraphAttention.apply(xn, w_qkv, b_qkv, bits, thr, heads, shift, layout, frames, kps, hybrid)
 
 
 # --------------------------------------------------------------------------

@@ -373,3 +373,33 @@ def test_tc2_empty_batch():
     assert y.shape == (0, 4, 64, 128)
     y.sum().backward()
     assert float(w.grad.abs().sum()) == 0.0 and float(b.grad.abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------ hybrid: K2 keeps q, k, v; backward on K3b
+@pytest.mark.parametrize("d,h", [(128, 2), (256, 4), (512, 8)])
+@pytest.mark.parametrize("shift", [0, 1])
+@pytest.mark.parametrize("thr", [None, 0.04])
+def test_hybrid_attention_vs_oracle_and_fused(d, h, shift, thr):
+    """impl="hybrid": the fused forward (K2) also stores the q, k, v rows it formed (q, k column-permuted inside each
+    head), and the backward is K3b's tcgen05 core on them.  Forward bit-identical to the fused kernels, gradients
+    within the bf16 tolerance of the oracle."""
+    B, F = 3, 8
+    xn, w, b, g = rounded(*seeded(d, shift, 16, B=B, F=F, std=0.05))
+    yh, dxh, dwh, dbh = run_tc2(xn, w, b, g, h, shift, thr, 16, impl="hybrid")
+    yf, dxf, dwf, dbf = run_tc2(xn, w, b, g, h, shift, thr, 16, impl="fused")
+    assert torch.equal(yh, yf)
+    by, bdx, bdw, bdb = oracle_points(xn, w, b, g, h, F, shift, thr, 16)
+    errs = dict(dx=rel_l2(dxh, bdx), dw=rel_l2(dwh, bdw), db=rel_l2(dbh, bdb))
+    assert all(e < BF16_TOL for e in errs.values()), errs
+    assert rel_l2(dxh, dxf) < 1e-2 and rel_l2(dwh, dwf) < 1e-2
+
+
+def test_hybrid_multi_tile_replication():
+    d, h, F = 512, 8, 16
+    xn, w, b, g = rounded(*seeded(d, 1, 16, B=1, F=F, std=0.05))
+    ys, dxs, dws, dbs = run_tc2(xn, w, b, g, h, 1, 0.05, 16, impl="hybrid")
+    for Bbig in (64, 37):
+        yb, dxb, dwb, dbb = run_tc2(xn.expand(Bbig, -1, -1, -1).contiguous(), w, b,
+                                    g.expand(Bbig, -1, -1, -1).contiguous(), h, 1, 0.05, 16, impl="hybrid")
+        assert torch.equal(yb, ys.expand(Bbig, -1, -1, -1)) and torch.equal(dxb, dxs.expand(Bbig, -1, -1, -1))
+        assert rel_l2(dwb, dws * Bbig) < 1e-3 and rel_l2(dbb, dbs * Bbig) < 1e-3
