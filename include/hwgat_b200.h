@@ -292,6 +292,12 @@ int hwgat_debug_set_gemm_pair(int on);
 /* Number of kernel launches issued through this library since load (all
  * streams, this process) - what bench.py reports as "gpu_launches". */
 unsigned long long hwgat_launch_count(void);
+/* Deterministic mode (process-wide; returns the previous setting).  Outputs and input gradients are always
+ * bit-reproducible; PARAMETER gradients are by default summed with fp32 atomics over a token split (order varies run
+ * to run, ~1e-6 relative).  on != 0: every token split of the weight-gradient GEMMs and every CTA of the bias /
+ * LayerNorm column sums writes its own partial and a finish kernel adds them in index order: bit-reproducible.
+ * In this mode (only) the library takes stream-ordered scratch from cudaMallocAsync / cudaFreeAsync.              */
+int hwgat_set_deterministic(int on);
 
 #ifdef __cplusplus
 }

@@ -14,13 +14,14 @@ LIB_PATH = os.environ.get("HWGAT_B200_LIB") or os.path.join(HERE, "lib", "libhwg
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # name -> (restype, argtypes); must list every symbol of include/hwgat_b200.h
 SIGNATURES = {
     "hwgat_version": (c_int, []),
     "hwgat_error_string": (c_char_p, [c_int]),
     "hwgat_launch_count": (c_ulonglong, []),
+    "hwgat_set_deterministic": (c_int, [c_int]),
     "hwgat_adjacency_build": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hwgat_mask_build": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hwgat_mask_pack": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
@@ -98,6 +99,8 @@ def load() -> ctypes.CDLL:
     got = lib.hwgat_version()
     if got != ABI_VERSION:
         raise HwgatError(f"libhwgat_b200 ABI {got}, binding expects {ABI_VERSION}: rebuild the library")
+    if os.environ.get("HWGAT_DETERMINISTIC", "0") not in ("", "0"):   # see ops.set_deterministic
+        lib.hwgat_set_deterministic(1)
     _lib = lib
     return lib
 

@@ -5,6 +5,7 @@
 
 namespace hwgat {
 unsigned long long g_launches = 0;
+int g_deterministic = 0;
 
 static bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
 
@@ -29,7 +30,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 12; }
+int hwgat_version(void) { return 13; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -46,6 +47,8 @@ const char* hwgat_error_string(int status) {
 }
 
 unsigned long long hwgat_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int hwgat_set_deterministic(int on) { return __atomic_exchange_n(&g_deterministic, on ? 1 : 0, __ATOMIC_RELAXED); }
 
 int hwgat_adjacency_build(const int32_t* edges, int n_edges, int nW, int W, int TP, float* adj,
                           hwgat_stream_t stream) {

@@ -83,13 +83,14 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 
 // column sums of a [rows][cols] matrix into a zeroed vector (d_b = sum_t dQKV[t,:])
 __global__ void colsum_f32_kernel(const float* __restrict__ X, float* __restrict__ out, long long rows, int cols,
-                                  long long rows_per_block) {
+                                  long long rows_per_block, float* __restrict__ part = nullptr) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   float s = 0.f;
   for (long long r = r0; r < r1; ++r) s += X[r * cols + c];
-  atomicAdd(&out[c], s);
+  if (part) part[(size_t)blockIdx.y * cols + c] = s;   // deterministic mode: fixed-order finish (det_finish)
+  else atomicAdd(&out[c], s);
 }
 
 // ---------------------------------------------------------------------------
@@ -354,6 +355,7 @@ int attn_bwd_f32(const AttnArgs& a, cudaStream_t s) {
   cudaMemsetAsync(a.d_b, 0, sizeof(float) * d3, s);
   int splits = (int)((n + 2047) / 2048);
   if (splits > 512) splits = 512;
+  if (deterministic()) splits = 1;
   int kps = (int)(((n + splits - 1) / splits + 15) / 16 * 16);
   dim3 g2((d + 63) / 64, (d3 + 63) / 64, (unsigned)((n + kps - 1) / kps));
   gemm_f32_kernel<true, false, true, false><<<g2, 256, 0, s>>>(dqkv, (const float*)a.xn, nullptr, a.d_w, d3, d, (int)n, kps);
@@ -361,8 +363,10 @@ int attn_bwd_f32(const AttnArgs& a, cudaStream_t s) {
   if ((st = check_last())) return st;
   long long rpb = 512;
   dim3 g3((d3 + 127) / 128, (unsigned)((n + rpb - 1) / rpb));
-  colsum_f32_kernel<<<g3, 128, 0, s>>>(dqkv, a.d_b, n, d3, rpb);
+  float* part = det_scratch(1, (int)g3.y, d3, s);
+  colsum_f32_kernel<<<g3, 128, 0, s>>>(dqkv, a.d_b, n, d3, rpb, part);
   count_launch();
+  det_finish(part, (int)g3.y, d3, a.d_b, nullptr, nullptr, s);
   return check_last();
 }
 
@@ -393,7 +397,7 @@ int linear_f32_bwd(const float* dy, const float* x, const float* w, float* dx, f
   if (dw) {
     // the contraction runs over the n rows: one split (deterministic plain stores) up to 4096 rows
     dim3 g((d_in + 63) / 64, (d_out + 63) / 64, 1);
-    if (n <= 4096) {
+    if (n <= 4096 || deterministic()) {
       gemm_f32_kernel<true, false, false, false><<<g, 256, 0, s>>>(dy, x, nullptr, dw, d_out, d_in, n, n);
     } else {
       cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d_out * d_in, s);

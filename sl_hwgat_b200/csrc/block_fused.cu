@@ -24,6 +24,33 @@ HW_DEV float warp_sum(float v) {
   return v;
 }
 
+// Deterministic mode: per-CTA partial column sums part[v][cta][col] -> out_v[col], CTAs added in index order.
+__global__ void col_finish_kernel(const float* __restrict__ part, int nblocks, int cols, float* __restrict__ o0,
+                                  float* __restrict__ o1, float* __restrict__ o2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float* outs[3] = {o0, o1, o2};
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    if (!outs[v]) continue;
+    float a = 0.f;
+    for (int b = 0; b < nblocks; ++b) a += part[((size_t)v * nblocks + b) * cols + c];
+    outs[v][c] = a;
+  }
+}
+float* det_scratch(int nvec, int grid, int cols, cudaStream_t s) {
+  if (!deterministic()) return nullptr;
+  void* p = nullptr;
+  if (cudaMallocAsync(&p, sizeof(float) * (size_t)nvec * grid * cols, s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return (float*)p;
+}
+void det_finish(float* part, int grid, int cols, float* o0, float* o1, float* o2, cudaStream_t s) {
+  if (!part) return;
+  col_finish_kernel<<<(cols + 127) / 128, 128, 0, s>>>(part, grid, cols, o0, o1, o2);
+  count_launch();
+  cudaFreeAsync(part, s);
+}
+
 // ---------------------------------------------------------------------------
 // K5 / K6 thread mapping.  A row of d = 128 / 256 / 512 columns is owned by kL = d/16 = 8 / 16 / 32 lanes, each
 // holding FOUR float4 (columns i*4*kL + 4*lc .. +3, i = 0..3), and a warp works on 32/kL rows at once.  Every
@@ -128,7 +155,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
                                                      const float* __restrict__ x, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                      float* __restrict__ dx, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, long long n, int uF2, int uK) {
+                                                     float* __restrict__ dbeta, long long n, int uF2, int uK,
+                                                     float* __restrict__ part) {
   constexpr int d = kL * 16, kRows = 32 / kL;
   __shared__ float red[2][8][d];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane / kL, lc = lane % kL;
@@ -195,8 +223,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
     float a = 0.f, b = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { a += red[0][w][c]; b += red[1][w][c]; }
-    atomicAdd(dgamma + c, a);
-    atomicAdd(dbeta + c, b);
+    if (part) {
+      part[((size_t)0 * gridDim.x + blockIdx.x) * d + c] = a;
+      part[((size_t)1 * gridDim.x + blockIdx.x) * d + c] = b;
+    } else {
+      atomicAdd(dgamma + c, a);
+      atomicAdd(dbeta + c, b);
+    }
   }
 }
 
@@ -288,7 +321,7 @@ __global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict
                                                          float* __restrict__ dbias, float* __restrict__ dgamma,
                                                          float* __restrict__ dbeta, long long n, float scale,
                                                          uint32_t thresh, unsigned long long seed,
-                                                         unsigned long long offset) {
+                                                         unsigned long long offset, float* __restrict__ part) {
   constexpr int d = kL * 16, kRows = 32 / kL;
   __shared__ float red[kLN ? 3 : 1][8][d];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane / kL, lc = lane % kL;
@@ -375,8 +408,16 @@ __global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict
       a += red[0][w][c];
       if (kLN) { b += red[1][w][c]; cc += red[2][w][c]; }
     }
-    if (dbias) atomicAdd(dbias + c, a);
-    if (kLN) { atomicAdd(dgamma + c, b); atomicAdd(dbeta + c, cc); }
+    if (part) {
+      part[((size_t)0 * gridDim.x + blockIdx.x) * d + c] = a;
+      if (kLN) {
+        part[((size_t)1 * gridDim.x + blockIdx.x) * d + c] = b;
+        part[((size_t)2 * gridDim.x + blockIdx.x) * d + c] = cc;
+      }
+    } else {
+      if (dbias) atomicAdd(dbias + c, a);
+      if (kLN) { atomicAdd(dgamma + c, b); atomicAdd(dbeta + c, cc); }
+    }
   }
 }
 
@@ -416,7 +457,8 @@ __global__ void __launch_bounds__(256) bias_gelu_dropout_bwd_kernel(const bf16* 
                                                                     const bf16* __restrict__ dg, bf16* __restrict__ du0,
                                                                     float* __restrict__ dbias, long long nvec, int cols,
                                                                     float scale, uint32_t thresh,
-                                                                    unsigned long long seed, unsigned long long offset) {
+                                                                    unsigned long long seed, unsigned long long offset,
+                                                                    float* __restrict__ part) {
   __shared__ float red[256][9];
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -451,7 +493,8 @@ __global__ void __launch_bounds__(256) bias_gelu_dropout_bwd_kernel(const bf16* 
     for (int i = 0; i < 8; ++i) {
       float sum = 0.f;
       for (int j = threadIdx.x; j < 256; j += G) sum += red[j][i];
-      atomicAdd(dbias + c0 + i, sum);
+      if (part) part[(size_t)blockIdx.x * cols + c0 + i] = sum;
+      else atomicAdd(dbias + c0 + i, sum);
     }
   }
 }
@@ -486,13 +529,15 @@ int launch_ln_bwd(const bf16* dy, const float* dres, const float* x, const float
   cudaMemsetAsync(dbeta, 0, sizeof(float) * d, s);
   long long want = (n + 7) / 8;
   const int grid = (int)(want < 148LL * 4 ? (want < 1 ? 1 : want) : 148LL * 4);
+  float* part = det_scratch(2, grid, d, s);
   switch (d) {
-    case 128: ln_bwd_kernel<8><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK); break;
-    case 256: ln_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK); break;
-    case 512: ln_bwd_kernel<32><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK); break;
+    case 128: ln_bwd_kernel<8><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK, part); break;
+    case 256: ln_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK, part); break;
+    case 512: ln_bwd_kernel<32><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK, part); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();
+  det_finish(part, grid, d, dgamma, dbeta, nullptr, s);
   return (int)cudaGetLastError();
 }
 
@@ -528,11 +573,11 @@ template <bool kLN>
 static int bda_bwd_dispatch(int grid, cudaStream_t s, const float* g_x1, const bf16* dy, const float* x1,
                             const float* mean, const float* rstd, const float* gamma, float* d_res, bf16* d_a0,
                             float* dbias, float* dgamma, float* dbeta, long long n, int d, float scale, uint32_t thresh,
-                            unsigned long long seed, unsigned long long offset) {
+                            unsigned long long seed, unsigned long long offset, float* part) {
   switch (d) {
-    case 128: bda_ln_bwd_kernel<8, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset); break;
-    case 256: bda_ln_bwd_kernel<16, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset); break;
-    case 512: bda_ln_bwd_kernel<32, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset); break;
+    case 128: bda_ln_bwd_kernel<8, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset, part); break;
+    case 256: bda_ln_bwd_kernel<16, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset, part); break;
+    case 512: bda_ln_bwd_kernel<32, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset, part); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   return 0;
@@ -550,10 +595,12 @@ int launch_bda_ln_bwd(const float* g_x1, const bf16* dy, const float* x1, const 
   }
   long long want = (n + 7) / 8;
   const int grid = (int)(want < 148LL * 4 ? (want < 1 ? 1 : want) : 148LL * 4);
-  int st = gamma ? bda_bwd_dispatch<true>(grid, s, g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, scale, thresh, seed, offset)
-                 : bda_bwd_dispatch<false>(grid, s, g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, scale, thresh, seed, offset);
+  float* part = det_scratch(3, grid, d, s);
+  int st = gamma ? bda_bwd_dispatch<true>(grid, s, g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, scale, thresh, seed, offset, part)
+                 : bda_bwd_dispatch<false>(grid, s, g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, scale, thresh, seed, offset, part);
   if (st) return st;
   count_launch();
+  det_finish(part, grid, d, dbias, gamma ? dgamma : nullptr, gamma ? dbeta : nullptr, s);
   return (int)cudaGetLastError();
 }
 
@@ -566,7 +613,10 @@ int launch_bias_gelu_dropout(const bf16* u0, const float* bias, const bf16* dg, 
   const int grid = ew_grid(nvec);
   if (backward) {
     if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * cols, s);
-    bias_gelu_dropout_bwd_kernel<<<grid, 256, 0, s>>>(u0, bias, dg, out, dbias, nvec, cols, scale, thresh, seed, offset);
+    float* part = dbias ? det_scratch(1, grid, cols, s) : nullptr;
+    bias_gelu_dropout_bwd_kernel<<<grid, 256, 0, s>>>(u0, bias, dg, out, dbias, nvec, cols, scale, thresh, seed, offset,
+                                                       part);
+    if (part) { count_launch(); det_finish(part, grid, cols, dbias, nullptr, nullptr, s); return (int)cudaGetLastError(); }
   } else {
     bias_gelu_dropout_fwd_kernel<<<grid, 256, 0, s>>>(u0, bias, out, nvec, cols, scale, thresh, seed, offset);
   }
@@ -709,7 +759,7 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(const float* __restric
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma, float* __restrict__ dx,
                                                           float* __restrict__ dgamma, int tokens, int slices,
-                                                          int kp_real, int kp_pad) {
+                                                          int kp_real, int kp_pad, float* __restrict__ part) {
   constexpr int d = kV * 128;
   __shared__ float red[8][d];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -755,7 +805,8 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(const float* __restric
     float a = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) a += red[w][c];
-    atomicAdd(dgamma + c, a);
+    if (part) part[(size_t)blockIdx.x * d + c] = a;
+    else atomicAdd(dgamma + c, a);
   }
 }
 
@@ -792,13 +843,15 @@ int launch_ln_pool_bwd(const float* g, const float* x, const float* mean, const 
                        float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s, int kp_real, int kp_pad) {
   cudaMemsetAsync(dgamma, 0, sizeof(float) * d, s);
   const int slices = pool_slices(B, tokens);
+  float* part = det_scratch(1, B * slices, d, s);
   switch (d) {
-    case 128: ln_pool_bwd_kernel<1><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad); break;
-    case 256: ln_pool_bwd_kernel<2><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad); break;
-    case 512: ln_pool_bwd_kernel<4><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad); break;
+    case 128: ln_pool_bwd_kernel<1><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad, part); break;
+    case 256: ln_pool_bwd_kernel<2><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad, part); break;
+    case 512: ln_pool_bwd_kernel<4><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad, part); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();
+  det_finish(part, B * slices, d, dgamma, nullptr, nullptr, s);
   return (int)cudaGetLastError();
 }
 

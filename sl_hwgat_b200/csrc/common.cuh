@@ -19,6 +19,17 @@ constexpr int kTok = 32;               // tokens per window (N = TP*W)
 constexpr int kHd = 64;                // head dim at every level
 constexpr int kTileTok = 128;          // tokens per tile = one temporal group = 4 windows x 32
 
+// Deterministic mode (hwgat_set_deterministic): parameter gradients are summed in a fixed order.  The token-split
+// weight-gradient GEMMs keep the split but every split writes its own partial, and the column reductions of the
+// bandwidth-bound backward kernels write per-CTA partials; a finish kernel adds the partials in index order.  The
+// partials live in stream-ordered scratch (cudaMallocAsync - the one place the library allocates, only in this mode).
+extern int g_deterministic;
+inline bool deterministic() { return __atomic_load_n(&g_deterministic, __ATOMIC_RELAXED) != 0; }
+// nullptr outside deterministic mode; else [nvec][grid][cols] floats on the stream (block_fused.cu)
+float* det_scratch(int nvec, int grid, int cols, cudaStream_t s);
+// o_v[c] = sum over grid, in index order, of part[v][.][c]; frees part on the stream; no-op for part == nullptr
+void det_finish(float* part, int grid, int cols, float* o0, float* o1, float* o2, cudaStream_t s);
+
 // Every launch made by the library is counted (hwgat_launch_count()).
 extern unsigned long long g_launches;
 inline void count_launch(int n = 1) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }

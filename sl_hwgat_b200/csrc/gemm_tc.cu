@@ -144,8 +144,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
                                                             const __grid_constant__ CUtensorMap tmB,
                                                             float* __restrict__ C, float* __restrict__ colsum, int M,
                                                             int N, int k_blocks_total, int k_blocks_per_cta,
-                                                            bool perm64, int perm_limit) {
+                                                            bool perm64, int perm_limit, int sum_mod,
+                                                            long long split_stride) {
   using Cfg = GemmTnCfg<BN>;
+  C += (size_t)blockIdx.y * split_stride;                 // deterministic mode: one partial per token split
+  if (colsum) colsum += (size_t)blockIdx.y * split_stride;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
@@ -162,7 +165,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
   // (Contiguous 1/n_blocks shares - the first version - made the CTAs that share an A tile run at different speeds in
   // different parts of the loop: they drifted ~90 us apart, further than a line stays in L2, and A was read from HBM
   // once per CTA - 3.70 GB instead of 2.15 GB for d_w at d = 512, ncu.)
-  const int sum_first = colsum ? kb0 + nb * kSumChunk : kb1;
+  // sum_mod == n_blocks; deterministic mode passes 1: the nb == 0 CTA alone sums every chunk (one adder per entry).
+  const int sum_first = colsum && nb < sum_mod ? kb0 + nb * kSumChunk : kb1;
   const bool do_sum = sum_first < kb1;
 
   for (int i = threadIdx.x; i < 8192 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + Cfg::kOnesOff)[i] = 0x3f803f80u;
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
       uint32_t ph = 0;
       for (int c0 = kb0, c = 0; c0 < kb1; c0 += kSumChunk, ++c) {
         const int c1 = c0 + kSumChunk < kb1 ? c0 + kSumChunk : kb1;
-        if (colsum && c % n_blocks == nb) tn_issue<BN, true>(smem, full, empty, tmem, c0, c1, kb0, sum_first, s, ph);
+        if (colsum && c % sum_mod == nb) tn_issue<BN, true>(smem, full, empty, tmem, c0, c1, kb0, sum_first, s, ph);
         else tn_issue<BN, false>(smem, full, empty, tmem, c0, c1, kb0, sum_first, s, ph);
       }
       if (elect_one_sync()) umma_commit(acc_full);
@@ -236,6 +240,36 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_kernel(const __grid_constan
   if (warp == 1) tmem_dealloc(tmem, Cfg::kTmemCols);
 }
 
+// Deterministic mode.  The token split stays (it is what fills the 148 SMs), but every split writes its own zeroed
+// partial [M*N | M] - its atomics then have one adder per element - and this kernel adds the partials in split order.
+__global__ void tn_finish_kernel(const float* __restrict__ part, int splits, long long mn, int M, float* __restrict__ C,
+                                 float* __restrict__ colsum) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = mn + M;
+  if (i >= (colsum ? stride : mn)) return;
+  float a = 0.f;
+  for (int sp = 0; sp < splits; ++sp) a += part[sp * stride + i];
+  if (i < mn) C[i] = a; else colsum[i - mn] = a;
+}
+struct TnDet {
+  float* part = nullptr;
+  long long stride = 0;
+  int begin(int splits, int M, int N, cudaStream_t s) {
+    if (!deterministic() || splits <= 1) return 0;
+    stride = (long long)M * N + M;
+    if (cudaMallocAsync((void**)&part, sizeof(float) * (size_t)stride * splits, s) != cudaSuccess) return (int)cudaGetLastError();
+    cudaMemsetAsync(part, 0, sizeof(float) * (size_t)stride * splits, s);
+    return 0;
+  }
+  void finish(int splits, int M, int N, float* C, float* colsum, cudaStream_t s) {
+    if (!part) return;
+    const long long total = colsum ? stride : (long long)M * N;
+    tn_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(part, splits, (long long)M * N, M, C, colsum);
+    count_launch();
+    cudaFreeAsync(part, s);
+  }
+};
+
 template <int BN>
 static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd,
                      cudaStream_t s, bool perm64, int perm_limit) {
@@ -246,8 +280,6 @@ static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int
   int st;
   if ((st = make_tmap_2d(&tmA, A, (uint64_t)Kd, (uint64_t)M, 64))) return st;
   if ((st = make_tmap_2d(&tmB, Bm, (uint64_t)Kd, (uint64_t)N, 64))) return st;
-  cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s);
-  if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * M, s);
   const int tiles = (M / 128) * (N / BN);
   const int kblocks = (int)(Kd / 64);
   int splits = 148 / tiles;  // one wave: tiles * splits <= 148 SMs (a 149th CTA would double the time)
@@ -255,8 +287,17 @@ static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int
   if (splits > kblocks) splits = kblocks;
   const int per = (kblocks + splits - 1) / splits;
   splits = (kblocks + per - 1) / per;
-  gemm_tc_tn_kernel<BN><<<dim3(tiles, splits), 192, Cfg::kSmem, s>>>(tmA, tmB, C, colsum, M, N, kblocks, per, perm64, perm_limit);
+  TnDet det;
+  if ((st = det.begin(splits, M, N, s))) return st;
+  if (!det.part) {
+    cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s);
+    if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * M, s);
+  }
+  gemm_tc_tn_kernel<BN><<<dim3(tiles, splits), 192, Cfg::kSmem, s>>>(
+      tmA, tmB, det.part ? det.part : C, !colsum ? nullptr : det.part ? det.part + (size_t)M * N : colsum, M, N, kblocks,
+      per, perm64, perm_limit, deterministic() ? 1 : N / BN, det.stride);
   count_launch();
+  det.finish(splits, M, N, C, colsum, s);
   return (int)cudaGetLastError();
 }
 
@@ -307,8 +348,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_pair_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  float* __restrict__ C, float* __restrict__ colsum, int M,
                                                                  int N, int k_blocks_total, int k_blocks_per_cta,
-                                                                 bool perm64, int perm_limit) {
+                                                                 bool perm64, int perm_limit, int sum_mod,
+                                                                 long long split_stride) {
   using Cfg = GemmTnPairCfg;
+  C += (size_t)blockIdx.y * split_stride;
+  if (colsum) colsum += (size_t)blockIdx.y * split_stride;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
@@ -322,7 +366,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_pair_kernel(const __grid_co
   const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
   const int kb0 = blockIdx.y * k_blocks_per_cta;
   const int kb1 = kb0 + k_blocks_per_cta < k_blocks_total ? kb0 + k_blocks_per_cta : k_blocks_total;
-  const int sum_first = colsum ? kb0 + nb * kSumChunk : kb1;   // column sums in interleaved chunks: see gemm_tc_tn_kernel
+  const int sum_first = colsum && nb < sum_mod ? kb0 + nb * kSumChunk : kb1;   // interleaved chunks: see gemm_tc_tn_kernel
   const bool do_sum = sum_first < kb1;
 
   for (int i = threadIdx.x; i < 8192 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + Cfg::kOnesOff)[i] = 0x3f803f80u;
@@ -365,7 +409,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_pair_kernel(const __grid_co
       uint32_t ph = 0;
       for (int c0 = kb0, c = 0; c0 < kb1; c0 += kSumChunk, ++c) {
         const int c1 = c0 + kSumChunk < kb1 ? c0 + kSumChunk : kb1;
-        if (colsum && c % n_blocks == nb) tn_pair_issue<true>(smem, full, empty, tmem, c0, c1, kb0, sum_first, s, ph);
+        if (colsum && c % sum_mod == nb) tn_pair_issue<true>(smem, full, empty, tmem, c0, c1, kb0, sum_first, s, ph);
         else tn_pair_issue<false>(smem, full, empty, tmem, c0, c1, kb0, sum_first, s, ph);
       }
       if (elect_one_sync()) umma_commit_pair(acc_full);
@@ -410,8 +454,6 @@ static int launch_tn_pair(const bf16* A, const bf16* Bm, float* C, float* colsum
   int st;
   if ((st = make_tmap_2d(&tmA, A, (uint64_t)Kd, (uint64_t)M, 64))) return st;
   if ((st = make_tmap_2d(&tmB, Bm, (uint64_t)Kd, (uint64_t)N, 64))) return st;
-  cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s);
-  if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * M, s);
   const int tiles = ((M + 255) / 256) * (N / 256);
   const int kblocks = (int)(Kd / 64);
   int splits = 74 / tiles;  // one wave of CTA pairs
@@ -419,6 +461,14 @@ static int launch_tn_pair(const bf16* A, const bf16* Bm, float* C, float* colsum
   if (splits > kblocks) splits = kblocks;
   const int per = (kblocks + splits - 1) / splits;
   splits = (kblocks + per - 1) / per;
+  TnDet det;
+  if ((st = det.begin(splits, M, N, s))) return st;
+  if (!det.part) {
+    cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s);
+    if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * M, s);
+  }
+  float* c_out = det.part ? det.part : C;
+  float* sum_out = !colsum ? nullptr : det.part ? det.part + (size_t)M * N : colsum;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -429,8 +479,10 @@ static int launch_tn_pair(const bf16* A, const bf16* Bm, float* C, float* colsum
   cfg.stream = s;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_tn_pair_kernel, tmA, tmB, C, colsum, M, N, kblocks, per, perm64, perm_limit);
+  cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_tn_pair_kernel, tmA, tmB, c_out, sum_out, M, N, kblocks, per, perm64, perm_limit,
+                                       deterministic() ? 1 : N / 256, det.stride);
   count_launch();
+  det.finish(splits, M, N, C, colsum, s);
   return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
 }
 

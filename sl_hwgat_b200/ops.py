@@ -70,6 +70,15 @@ def _require_binary(t: Optional[torch.Tensor], what: str) -> None:
 _CAST_CACHE: dict = {}
 
 
+def set_deterministic(on: bool = True) -> bool:
+    """Bit-reproducible PARAMETER gradients (outputs and input gradients always are): every token split of the
+    weight-gradient GEMMs and every CTA of the bias / LayerNorm column sums writes its own partial, added in index
+    order by a finish kernel (hwgat_set_deterministic, include/hwgat_b200.h; also env HWGAT_DETERMINISTIC=1).  The
+    default keeps the fp32-atomic sums, whose order varies run to run at the 1e-6 level.  Process-wide; returns the
+    previous setting.  The reference offers nothing comparable (its cuBLAS / eager backward is not run-to-run exact either)."""
+    return bool(_lib.load().hwgat_set_deterministic(1 if on else 0))
+
+
 def invalidate_cast_cache() -> None:
     """Forget every cached low-precision parameter copy.  Needed after parameters were written through raw pointers,
     which does not bump torch's `_version` counter: sl_hwgat_b200.optim.AdamW calls this after every step."""

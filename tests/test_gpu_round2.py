@@ -255,6 +255,56 @@ def test_run_twice_determinism():
     assert torch.equal(outs[0], outs[1])
 
 
+def test_deterministic_mode_makes_parameter_gradients_bit_reproducible():
+    """ops.set_deterministic(True): unsplit weight-gradient GEMMs + fixed-order column sums -> every gradient of a
+    whole train step (bf16 autocast, dropout on, threshold drop on) is bit-identical between two runs; and the
+    deterministic gradients agree with the default (atomic) ones to fp32 summation-order noise."""
+    import sl_hwgat_b200.ops as ops
+    from sl_hwgat_b200.losses import SmoothedCrossEntropyLoss
+
+    def step(m, x, y):
+        torch.manual_seed(5)
+        torch.cuda.manual_seed(5)
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = SmoothedCrossEntropyLoss(0.1)(m(x), y)
+        loss.backward()
+        return {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+
+    m, cfg, sd = build(32, 10, drop=0.1)
+    m.train()
+    x = O.synthetic_keypoints(64, 32, 2, seed=3).cuda()
+    y = torch.arange(64, device="cuda") % 10
+    base = step(m, x, y)
+    prev = ops.set_deterministic(True)
+    try:
+        a, b = step(m, x, y), step(m, x, y)
+    finally:
+        ops.set_deterministic(prev)
+    assert a.keys() == b.keys() == base.keys() and len(a) >= 100
+    for n in a:
+        assert torch.equal(a[n], b[n]), n
+        assert rel_l2(a[n].double(), base[n].double()) < 1e-4, n
+    # the fp32 path too
+    m32, _, _ = build(16, 10, drop=0.0)
+    m32.train()
+    x32 = O.synthetic_keypoints(8, 16, 2, seed=4).cuda()
+
+    def step32():
+        torch.manual_seed(7)
+        m32.zero_grad(set_to_none=True)
+        SmoothedCrossEntropyLoss(0.1)(m32(x32), y[:8]).backward()
+        return {n: p.grad.detach().clone() for n, p in m32.named_parameters() if p.grad is not None}
+
+    prev = ops.set_deterministic(True)
+    try:
+        a, b = step32(), step32()
+    finally:
+        ops.set_deterministic(prev)
+    for n in a:
+        assert torch.equal(a[n], b[n]), n
+
+
 # ------------------------------------------------------------------ drop-in replay (utils.py:55-59, 185-214)
 def test_dropin_replays_reference_load_model_and_checkpoint_filter(tmp_path):
     """Instantiate the model the way utils.load_model does - importlib on 'models.<model_type>' and
