@@ -291,6 +291,40 @@ int hwgat_debug_set_gemm_pair(int on);
 
 /* Number of kernel launches issued through this library since load (all
  * streams, this process) - what bench.py reports as "gpu_launches". */
+/* K9 with learned token weights: GATE's `weightedAvg` = Linear(F*K, 1) over the token axis (hwgat/models/GATE.py:185,
+ * 207) fused with the final LayerNorm (GATE.py:205).  pooled[b, c] = sum_t tok_w[t] * (xhat[b,t,c] gamma[c]) + beta[c];
+ * the caller passes beta * sum(tok_w) + the Linear's bias as `beta`.  tok_w f32 (tokens) indexes REAL tokens
+ * (frame * kp_real + keypoint).  Backward: dx, dgamma as hwgat_ln_pool_bwd; d_tok_w[t] = sum_b sum_c g[b,c] gamma[c]
+ * xhat[b,t,c], summed over the samples in a fixed order through dw_part (B * tokens floats of scratch); the caller
+ * adds the g.beta term.                                                                                              */
+int hwgat_ln_wpool_fwd(const float* x, const float* gamma, const float* beta, const float* tok_w, float* pooled,
+                       float* mean, float* rstd, void* scratch, size_t scratch_bytes, int B, int tokens, int d,
+                       float eps, int kp_real, int kp_pad, hwgat_stream_t stream);
+int hwgat_ln_wpool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* tok_w, float* dx, float* dgamma, float* d_tok_w, float* dw_part, int B, int tokens,
+                       int d, int kp_real, int kp_pad, hwgat_stream_t stream);
+
+/* ---- K15 / K16: frame-banded graph attention of the sibling models WGATE and GATE --------------------------------
+ * Replaces MSA.forward of hwgat/models/WGATE.py:87-108 (windows of W = 16 keypoints over ALL frames, additive
+ * -10000 mask, called from PartAttentionBlock.forward, WGATE.py:150-158) and of hwgat/models/GATE.py:49-69 (all 29
+ * keypoints x all frames, stored here as one window of W = 32 with three padded keypoints), up to the output
+ * projection.  The adjacency those models build (model_params.py:204-229, 59-74) is frame-banded - a token is linked to
+ * keypoints of its own and of the two adjacent frames - and after the softmax every non-edge weighs exactly 0 in fp32,
+ * so the kernels evaluate only the band: W queries x 3W keys per (sample, window, frame).
+ *   xn   bf16 (B, F, K, d)      LayerNorm-ed stream, K % W == 0, B*F*K % 128 == 0, d % 128 == 0, d/heads in {16,32,64}
+ *   bits u32  (K/W, W, 3)       bit j of word (w, i, r): keypoint i of window w attends keypoint j of frame f-1+r
+ *                               (r = 0 previous, 1 same, 2 next frame); a row without any bit yields a zero output row
+ *   out  bf16 (B, F, K, d)      head-merged context; qkv bf16 (B*F*K, 3d) is written and must be kept for the backward
+ *   lse  f32  (B*F*K, heads)    logsumexp of the scaled logits over the edges (NULL in inference)
+ * Backward: d_xn bf16, d_w f32 (3d, d), d_b f32 (3d); workspace from hwgat_band_attn_workspace_bytes(.., 1).
+ * No attention dropout (both models default to attn_drop_rate = 0; the host side refuses p > 0).                  */
+size_t hwgat_band_attn_workspace_bytes(int B, int F, int K, int d, int backward);
+int hwgat_band_attn_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, void* out,
+                        void* qkv, float* lse, int B, int F, int K, int d, int heads, int W, hwgat_stream_t stream);
+int hwgat_band_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const void* qkv, const void* ctx,
+                        const float* lse, const uint32_t* bits, void* d_xn, float* d_w, float* d_b, void* workspace,
+                        size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, hwgat_stream_t stream);
+
 unsigned long long hwgat_launch_count(void);
 /* Deterministic mode (process-wide; returns the previous setting).  Outputs and input gradients are always
  * bit-reproducible; PARAMETER gradients are by default summed with fp32 atomics over a token split (order varies run

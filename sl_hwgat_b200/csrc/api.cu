@@ -30,7 +30,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 13; }
+int hwgat_version(void) { return 15; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -154,6 +154,42 @@ static int check_geometry2(int B, int F, int K, int d, int heads, int W, int TP,
   if (layout == HWGAT_LAYOUT_WINDOWS && shift != 0) return HWGAT_ERR_SHAPE;
   if ((long long)B * F * K > 0x7fffffffLL / 4) return HWGAT_ERR_UNSUPPORTED;
   return HWGAT_OK;
+}
+
+// ---- K15 / K16: frame-banded graph attention (WGATE.py:68-108, GATE.py:30-69) ----
+size_t hwgat_band_attn_workspace_bytes(int B, int F, int K, int d, int backward) {
+  return band_attn_workspace_bytes((long long)B * F * K, d, backward);
+}
+
+int hwgat_band_attn_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, void* out,
+                        void* qkv, float* lse, int B, int F, int K, int d, int heads, int W, hwgat_stream_t stream) {
+  if (!band_attn_supported(B, F, K, d, heads, W)) return B < 0 || F < 1 || K < 1 ? HWGAT_ERR_SHAPE : HWGAT_ERR_UNSUPPORTED;
+  if (B == 0) return HWGAT_OK;
+  if (!xn || !w_qkv || !b_qkv || !bits || !out || !qkv) return HWGAT_ERR_NULL;
+  if (misaligned(xn) || misaligned(w_qkv) || misaligned(b_qkv) || misaligned(out) || misaligned(qkv) || misaligned(lse))
+    return HWGAT_ERR_ALIGN;
+  return band_attn_fwd((const __nv_bfloat16*)xn, (const __nv_bfloat16*)w_qkv, b_qkv, bits, (__nv_bfloat16*)out,
+                       (__nv_bfloat16*)qkv, lse, B, F, K, d, heads, W, (cudaStream_t)stream);
+}
+
+int hwgat_band_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const void* qkv, const void* ctx,
+                        const float* lse, const uint32_t* bits, void* d_xn, float* d_w, float* d_b, void* workspace,
+                        size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, hwgat_stream_t stream) {
+  if (!band_attn_supported(B, F, K, d, heads, W)) return B < 0 || F < 1 || K < 1 ? HWGAT_ERR_SHAPE : HWGAT_ERR_UNSUPPORTED;
+  if (!d_w || !d_b) return HWGAT_ERR_NULL;
+  if (B == 0) {
+    cudaMemsetAsync(d_w, 0, sizeof(float) * 3 * d * d, (cudaStream_t)stream);
+    cudaMemsetAsync(d_b, 0, sizeof(float) * 3 * d, (cudaStream_t)stream);
+    return (int)cudaGetLastError();
+  }
+  if (!d_out || !xn || !w_qkv || !qkv || !ctx || !lse || !bits || !d_xn) return HWGAT_ERR_NULL;
+  if (misaligned(d_out) || misaligned(xn) || misaligned(w_qkv) || misaligned(qkv) || misaligned(ctx) || misaligned(lse) ||
+      misaligned(d_xn) || misaligned(d_w) || misaligned(workspace))
+    return HWGAT_ERR_ALIGN;
+  if (!workspace || workspace_bytes < hwgat_band_attn_workspace_bytes(B, F, K, d, 1)) return HWGAT_ERR_WORKSPACE;
+  return band_attn_bwd((const __nv_bfloat16*)xn, (const __nv_bfloat16*)w_qkv, bits, (const __nv_bfloat16*)qkv,
+                       (const __nv_bfloat16*)ctx, lse, (const __nv_bfloat16*)d_out, (__nv_bfloat16*)d_xn, d_w, d_b,
+                       workspace, B, F, K, d, heads, W, (cudaStream_t)stream);
 }
 
 size_t hwgat_attn2_workspace_bytes(int B, int F, int K, int d, int heads, int backward, int have_qkv) {
@@ -453,6 +489,34 @@ int hwgat_ln_pool_bwd(const float* g, const float* x, const float* mean, const f
   if (B > 0 && (!g || !x || !mean || !rstd || !gamma || !dx)) return HWGAT_ERR_NULL;
   if (misaligned(g) || misaligned(x) || misaligned(gamma) || misaligned(dx)) return HWGAT_ERR_ALIGN;
   return launch_ln_pool_bwd(g, x, mean, rstd, gamma, dx, dgamma, B, tokens, d, (cudaStream_t)stream, kp_real, kp_pad);
+}
+
+// the weighted pool of GATE (GATE.py:207): pooled = sum_t tok_w[t] * LayerNorm(x)[t]  (+ the caller's folded bias in beta)
+int hwgat_ln_wpool_fwd(const float* x, const float* gamma, const float* beta, const float* tok_w, float* pooled,
+                       float* mean, float* rstd, void* scratch, size_t scratch_bytes, int B, int tokens, int d,
+                       float eps, int kp_real, int kp_pad, hwgat_stream_t stream) {
+  if (!tok_w) return HWGAT_ERR_NULL;
+  if (B < 0 || tokens <= 0 || bad_pad(tokens, kp_real, kp_pad)) return HWGAT_ERR_SHAPE;
+  if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
+  if (B == 0) return HWGAT_OK;
+  if (!x || !gamma || !beta || !pooled || !mean || !rstd) return HWGAT_ERR_NULL;
+  if (misaligned(x) || misaligned(gamma)) return HWGAT_ERR_ALIGN;
+  const size_t need = ln_pool_scratch_bytes(B, tokens, d);
+  if (need > 0 && (!scratch || scratch_bytes < need)) return HWGAT_ERR_WORKSPACE;
+  return launch_ln_pool_fwd(x, gamma, beta, pooled, mean, rstd, (float*)scratch, B, tokens, d, eps, (cudaStream_t)stream,
+                            kp_real, kp_pad, tok_w);
+}
+
+int hwgat_ln_wpool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* tok_w, float* dx, float* dgamma, float* d_tok_w, float* dw_part, int B, int tokens,
+                       int d, int kp_real, int kp_pad, hwgat_stream_t stream) {
+  if (B < 0 || tokens <= 0 || bad_pad(tokens, kp_real, kp_pad)) return HWGAT_ERR_SHAPE;
+  if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
+  if (!dgamma || !d_tok_w || !tok_w) return HWGAT_ERR_NULL;
+  if (B > 0 && (!g || !x || !mean || !rstd || !gamma || !dx || !dw_part)) return HWGAT_ERR_NULL;
+  if (misaligned(g) || misaligned(x) || misaligned(gamma) || misaligned(dx)) return HWGAT_ERR_ALIGN;
+  return launch_ln_pool_bwd(g, x, mean, rstd, gamma, dx, dgamma, B, tokens, d, (cudaStream_t)stream, kp_real, kp_pad,
+                            tok_w, dw_part, d_tok_w);
 }
 
 int hwgat_adamw_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,

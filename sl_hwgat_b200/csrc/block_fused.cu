@@ -690,7 +690,10 @@ __global__ void __launch_bounds__(256) ln_pool_fwd_kernel(const float* __restric
                                                           const float* __restrict__ beta, float* __restrict__ pooled,
                                                           float* __restrict__ mean, float* __restrict__ rstd,
                                                           float* __restrict__ scratch, int tokens, int slices,
-                                                          float eps, int kp_real, int kp_pad) {
+                                                          float eps, int kp_real, int kp_pad,
+                                                          const float* __restrict__ tok_w) {
+  // tok_w != nullptr (GATE's learned `weightedAvg`, GATE.py:207): pooled = sum_t tok_w[t] * LayerNorm(x)[t]; the
+  // caller folds beta * sum(tok_w) + the pool's bias into `beta`.  nullptr: the mean (weights 1, scaled once at the end).
   constexpr int d = kV * 128;
   __shared__ float red[8][d];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -723,15 +726,16 @@ __global__ void __launch_bounds__(256) ln_pool_fwd_kernel(const float* __restric
     }
     const float rs = rsqrtf(warp_sum(q) * (1.f / d) + eps);
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    const float rw = tok_w ? rs * tok_w[tk] : rs;
 #pragma unroll
     for (int i = 0; i < kV; ++i) {  // sum of xhat; gamma / beta / 1/tokens are applied once at the end
-      acc[i].x += v[i].x * rs; acc[i].y += v[i].y * rs; acc[i].z += v[i].z * rs; acc[i].w += v[i].w * rs;
+      acc[i].x += v[i].x * rw; acc[i].y += v[i].y * rw; acc[i].z += v[i].z * rw; acc[i].w += v[i].w * rw;
     }
   }
 #pragma unroll
   for (int i = 0; i < kV; ++i) *reinterpret_cast<float4*>(&red[wib][i * 128 + lane * 4]) = acc[i];
   __syncthreads();
-  const float inv = 1.f / tokens;
+  const float inv = tok_w ? 1.f : 1.f / tokens;
   for (int c = threadIdx.x; c < d; c += 256) {
     float a = 0.f;
 #pragma unroll
@@ -759,12 +763,15 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(const float* __restric
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma, float* __restrict__ dx,
                                                           float* __restrict__ dgamma, int tokens, int slices,
-                                                          int kp_real, int kp_pad, float* __restrict__ part) {
+                                                          int kp_real, int kp_pad, float* __restrict__ part,
+                                                          const float* __restrict__ tok_w, float* __restrict__ dw_part) {
+  // tok_w != nullptr: the weighted pool; dw_part[b][t] = sum_c g[b,c] gamma[c] xhat[b,t,c] (the caller adds g.beta and
+  // sums over the samples in a fixed order)
   constexpr int d = kV * 128;
   __shared__ float red[8][d];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int b = blockIdx.x / slices, sl = blockIdx.x - b * slices;
-  const float inv = 1.f / tokens;
+  const float inv = tok_w ? 1.f : 1.f / tokens;
   float4 gy[kV], gg[kV], dg[kV];
   float s1 = 0.f;
 #pragma unroll
@@ -789,14 +796,21 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(const float* __restric
       const float4 xv = *reinterpret_cast<const float4*>(x + row * d + i * 128 + lane * 4);
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       s2 += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
-      dg[i].x += gy[i].x * xh[i].x; dg[i].y += gy[i].y * xh[i].y; dg[i].z += gy[i].z * xh[i].z; dg[i].w += gy[i].w * xh[i].w;
     }
-    const float m2 = warp_sum(s2) * (1.f / d);
+    const float wt = tok_w ? tok_w[tk] : 1.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      dg[i].x += wt * gy[i].x * xh[i].x; dg[i].y += wt * gy[i].y * xh[i].y;
+      dg[i].z += wt * gy[i].z * xh[i].z; dg[i].w += wt * gy[i].w * xh[i].w;
+    }
+    const float s2w = warp_sum(s2);
+    if (dw_part && lane == 0) dw_part[(long long)b * tokens + tk] = s2w;
+    const float m2 = s2w * (1.f / d), rw = rs * wt;
 #pragma unroll
     for (int i = 0; i < kV; ++i)
       *reinterpret_cast<float4*>(dx + row * d + i * 128 + lane * 4) =
-          make_float4(rs * (gg[i].x - m1 - xh[i].x * m2), rs * (gg[i].y - m1 - xh[i].y * m2),
-                      rs * (gg[i].z - m1 - xh[i].z * m2), rs * (gg[i].w - m1 - xh[i].w * m2));
+          make_float4(rw * (gg[i].x - m1 - xh[i].x * m2), rw * (gg[i].y - m1 - xh[i].y * m2),
+                      rw * (gg[i].z - m1 - xh[i].z * m2), rw * (gg[i].w - m1 - xh[i].w * m2));
   }
 #pragma unroll
   for (int i = 0; i < kV; ++i) *reinterpret_cast<float4*>(&red[wib][i * 128 + lane * 4]) = dg[i];
@@ -823,35 +837,42 @@ size_t ln_pool_scratch_bytes(int B, int tokens, int d) {
 }
 
 int launch_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean, float* rstd,
-                       float* scratch, int B, int tokens, int d, float eps, cudaStream_t s, int kp_real, int kp_pad) {
+                       float* scratch, int B, int tokens, int d, float eps, cudaStream_t s, int kp_real, int kp_pad,
+                       const float* tok_w) {
   const int slices = pool_slices(B, tokens);
   switch (d) {
-    case 128: ln_pool_fwd_kernel<1><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps, kp_real, kp_pad); break;
-    case 256: ln_pool_fwd_kernel<2><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps, kp_real, kp_pad); break;
-    case 512: ln_pool_fwd_kernel<4><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps, kp_real, kp_pad); break;
+    case 128: ln_pool_fwd_kernel<1><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps, kp_real, kp_pad, tok_w); break;
+    case 256: ln_pool_fwd_kernel<2><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps, kp_real, kp_pad, tok_w); break;
+    case 512: ln_pool_fwd_kernel<4><<<B * slices, 256, 0, s>>>(x, gamma, beta, pooled, mean, rstd, scratch, tokens, slices, eps, kp_real, kp_pad, tok_w); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();
   if (slices > 1) {
-    ln_pool_finish_kernel<<<(B * d + 255) / 256, 256, 0, s>>>(scratch, gamma, beta, pooled, B, d, slices, 1.f / tokens);
+    ln_pool_finish_kernel<<<(B * d + 255) / 256, 256, 0, s>>>(scratch, gamma, beta, pooled, B, d, slices,
+                                                              tok_w ? 1.f : 1.f / tokens);
     count_launch();
   }
   return (int)cudaGetLastError();
 }
 
 int launch_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
-                       float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s, int kp_real, int kp_pad) {
+                       float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s, int kp_real, int kp_pad,
+                       const float* tok_w, float* dw_part, float* d_tok_w) {
   cudaMemsetAsync(dgamma, 0, sizeof(float) * d, s);
   const int slices = pool_slices(B, tokens);
   float* part = det_scratch(1, B * slices, d, s);
   switch (d) {
-    case 128: ln_pool_bwd_kernel<1><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad, part); break;
-    case 256: ln_pool_bwd_kernel<2><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad, part); break;
-    case 512: ln_pool_bwd_kernel<4><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad, part); break;
+    case 128: ln_pool_bwd_kernel<1><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad, part, tok_w, dw_part); break;
+    case 256: ln_pool_bwd_kernel<2><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad, part, tok_w, dw_part); break;
+    case 512: ln_pool_bwd_kernel<4><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad, part, tok_w, dw_part); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();
   det_finish(part, B * slices, d, dgamma, nullptr, nullptr, s);
+  if (dw_part && d_tok_w) {   // d_tok_w[t] = sum over the samples, in sample order (always deterministic)
+    col_finish_kernel<<<(tokens + 127) / 128, 128, 0, s>>>(dw_part, B, tokens, d_tok_w, nullptr, nullptr);
+    count_launch();
+  }
   return (int)cudaGetLastError();
 }
 

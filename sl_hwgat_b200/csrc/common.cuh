@@ -161,9 +161,10 @@ int launch_embed_fwd(const float* x, const float* Bm, const float* pe, float* ou
 size_t ln_pool_scratch_bytes(int B, int tokens, int d);
 int launch_ln_pool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean, float* rstd,
                        float* scratch, int B, int tokens, int d, float eps, cudaStream_t s, int kp_real = 0,
-                       int kp_pad = 0);
+                       int kp_pad = 0, const float* tok_w = nullptr);
 int launch_ln_pool_bwd(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
-                       float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s, int kp_real = 0, int kp_pad = 0);
+                       float* dx, float* dgamma, int B, int tokens, int d, cudaStream_t s, int kp_real = 0, int kp_pad = 0,
+                       const float* tok_w = nullptr, float* dw_part = nullptr, float* d_tok_w = nullptr);
 
 int linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, int n, int d_in, int d_out,
                    cudaStream_t s);
@@ -196,6 +197,15 @@ int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s);
 size_t attn2_workspace_bytes(long long n, int d, int backward, int have_qkv);
 int attn2_fwd(const AttnArgs& a, int W, __nv_bfloat16* qkv, cudaStream_t s);
 int attn2_bwd(const AttnArgs& a, int W, const __nv_bfloat16* qkv_saved, cudaStream_t s);
+// K15 / K16 (band_attn.cu): frame-banded graph attention of WGATE / GATE
+bool band_attn_supported(int B, int F, int K, int d, int heads, int W);
+size_t band_attn_workspace_bytes(long long n, int d, int backward);
+int band_attn_fwd(const __nv_bfloat16* xn, const __nv_bfloat16* w_qkv, const float* b_qkv, const uint32_t* bits,
+                  __nv_bfloat16* out, __nv_bfloat16* qkv, float* lse, int B, int F, int K, int d, int heads, int W,
+                  cudaStream_t s);
+int band_attn_bwd(const __nv_bfloat16* xn, const __nv_bfloat16* w_qkv, const uint32_t* bits, const __nv_bfloat16* qkv,
+                  const __nv_bfloat16* ctx, const float* lse, const __nv_bfloat16* d_out, __nv_bfloat16* d_xn,
+                  float* d_w, float* d_b, void* workspace, int B, int F, int K, int d, int heads, int W, cudaStream_t s);
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t s);
 int attn_bwd_tc(const AttnArgs& a, __nv_bfloat16* dqkv, cudaStream_t s);
 int gemm_tc_tn(const __nv_bfloat16* A, const __nv_bfloat16* Bm, float* C, float* colsum, int M, int N, long long Kd,

@@ -276,16 +276,21 @@ class PartAttentionBlock(nn.Module):
         x, xn = ops.layer_norm_residual(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         return self.forward_chain(x, xn, None)[0]
 
-    def forward_chain(self, x, xn, next_norm, merge=False):
+    def _context(self, x, xn, bits=None):
+        """the block's attention up to the head-merged context (before self.attn.proj)"""
+        attn = self.attn
+        return ops.window_graph_attention(xn, attn.qkv.weight, attn.qkv.bias, self._block_bits(x.device),
+                                          attn.num_heads, shift=self.shift_size, threshold=attn._draw_threshold(),
+                                          layout=LAYOUT_BFKD, window=self.window_size, attn_drop=attn._attn_p())
+
+    def forward_chain(self, x, xn, next_norm, merge=False, bits=None):
         """Fused bf16 path.  x: fp32 residual stream, xn = norm1(x) in bf16 (made by the previous kernel of the
         chain).  Returns (x_out, next_norm(x_out) in bf16 or None): the LayerNorm that consumes the block's output
         is computed by the same kernel that forms the output (K6).  merge=True (last block of a level, next_norm =
         the next level's first norm1): x_out is stored directly in TemporalMerging's layout (B, F/2, K, 2d) and
         next_norm runs over the merged 2d-wide rows - K4 and its adjoint are folded into K6 / K5'."""
         attn, ff = self.attn, self.ff
-        ctx = ops.window_graph_attention(xn, attn.qkv.weight, attn.qkv.bias, self._block_bits(x.device),
-                                         attn.num_heads, shift=self.shift_size, threshold=attn._draw_threshold(),
-                                         layout=LAYOUT_BFKD, window=self.window_size, attn_drop=attn._attn_p())
+        ctx = self._context(x, xn, bits)       # (the sibling models WGATE / GATE plug their banded attention in here)
         a0 = ops.output_projection(ctx, attn.proj.weight)          # K12; bias, dropout, shortcut and norm2: K6
         x, h = ops.bias_dropout_add_ln(x, a0, attn.proj.bias, self.norm2, attn.proj_drop.p, self.training)
         # K10: fc1 + bias + GELU + dropout + fc2's matmul on the tcgen05 GEMMs with fused epilogues

@@ -136,3 +136,91 @@ class HGATEParams():
         return (self.kp_dim, self.num_kps, self.temporal_dim, self.num_classes, self.embed_dim,
                 self.temporal_patch_size, self.pe, self.depths, self.num_heads, self.adj_mat, self.drop_rate,
                 self.attn_drop_rate, self.ff_ratio, self.norm_layer, self.device)
+
+
+def _frame_band(same, frames):
+    """(frames*k, frames*k) float32: `same` (k, k) on the diagonal frame blocks, the identity between adjacent frames,
+    zero further apart - the token order is frame * k + keypoint."""
+    k = same.shape[0]
+    eye_f = torch.eye(frames)
+    step = torch.diag(torch.ones(frames - 1), 1) + torch.diag(torch.ones(frames - 1), -1) if frames > 1 \
+        else torch.zeros(1, 1)
+    return torch.kron(eye_f, same) + torch.kron(step, torch.eye(k))
+
+
+class WGATEParams():
+    """Drop-in for the WGATEParams class of hwgat/models/model_params.py:80-240 (same constructor, attributes and
+    get_model_params() tuple).  adj_mat is (nW, F*W, F*W): the window's skeleton with self loops inside a frame, the
+    identity between adjacent frames (model_params.py:204-229).  Host set-up work, built with torch on the CPU like
+    the reference's numpy loops (it is F^2 blocks once per model, not on the step)."""
+
+    def __init__(self, dataset_params, input_dim, device=None) -> None:
+        self.kp_dim = input_dim
+        self.num_kps = 64
+        self.temporal_dim = dataset_params['src_len']
+        self.num_classes = dataset_params['num_class']
+        self.embed_dim = 128
+        self.pe = True
+        self.depths = 8
+        self.num_heads = 8
+        self.window_size = 16
+        self.drop_rate = 0.1
+        self.attn_drop_rate = 0.0
+        self.ff_ratio = 2.
+        self.norm_layer = nn.LayerNorm
+        self.kp_norm = True
+        self.device = device
+        self.edges = [_window_edges() for _ in range(self.num_kps // self.window_size)]
+        self.adj_mat = torch.as_tensor(self.get_adj_mat(), dtype=torch.float32)
+
+    def get_adj_mat(self):
+        return torch.stack([_frame_band(torch.as_tensor(self.get_adj(i), dtype=torch.float32), self.temporal_dim)
+                            for i in range(len(self.edges))]).numpy()
+
+    def get_adj(self, index):
+        """(W, W) skeleton adjacency of window `index` with self loops (model_params.py:233-239)."""
+        a = torch.eye(self.window_size)
+        for i, j in self.edges[index]:
+            a[i, j] = 1
+            a[j, i] = 1
+        return a.numpy()
+
+    def get_model_params(self):
+        return (self.kp_dim, self.num_kps, self.temporal_dim, self.num_classes, self.embed_dim, self.pe, self.depths,
+                self.num_heads, self.window_size, self.ff_ratio, self.adj_mat, self.drop_rate, self.attn_drop_rate,
+                self.norm_layer, self.device)
+
+
+class GATEParams():
+    """Drop-in for the GATEParams class of hwgat/models/model_params.py:5-77.  adj_mat is (F*29, F*29): the 34 body
+    and hand edges inside every frame (NO self loops) and a link between the same keypoint of adjacent frames
+    (model_params.py:59-74)."""
+
+    def __init__(self, dataset_params, input_dim, device=None) -> None:
+        self.kp_dim = input_dim
+        self.num_kps = 29
+        self.temporal_dim = dataset_params['src_len']
+        self.num_classes = dataset_params['num_class']
+        self.embed_dim = 128
+        self.pe = True
+        self.depths = 8
+        self.num_heads = 8
+        self.ff_ratio = 2.
+        self.drop_rate = 0.1
+        self.attn_drop_rate = 0.0
+        self.norm_layer = nn.LayerNorm
+        self.device = device
+        self.edges = _body_edges()
+        self.adj_mat = torch.as_tensor(self.get_adj(self.edges, self.temporal_dim, self.num_kps), dtype=torch.float32)
+
+    def get_adj(self, spatial_links, num_fr, num_kp):
+        same = torch.zeros(num_kp, num_kp)
+        for i, j in spatial_links:
+            same[i, j] = 1
+            same[j, i] = 1
+        return _frame_band(same, num_fr).numpy()
+
+    def get_model_params(self):
+        return (self.kp_dim, self.num_kps, self.temporal_dim, self.num_classes, self.embed_dim, self.pe, self.depths,
+                self.num_heads, self.ff_ratio, self.adj_mat, self.drop_rate, self.attn_drop_rate, self.norm_layer,
+                self.device)

@@ -323,6 +323,130 @@ def window_graph_attention(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.T
 
 
 # --------------------------------------------------------------------------
+# K15 / K16: frame-banded graph attention (the sibling models WGATE and GATE)
+# --------------------------------------------------------------------------
+
+BAND_WINDOWS = (16, 32)
+
+
+def band_mask_pack(adj_mask: torch.Tensor, frames: int, window: int) -> torch.Tensor:
+    """Pack the ADDITIVE mask of WGATE / GATE - 0 on graph edges, -10000 elsewhere (WGATE.py:190, GATE.py:142) - into
+    the (nW, window, 3) uint32 band words of K15 / K16, after proving that the band is all there is.
+
+    adj_mask: (nW, frames*kw, frames*kw) with the token order f*kw + k of WGATE's window_partition (WGATE.py:32-45),
+    kw <= window keypoints per window; keypoints kw .. window-1 of the packed words are padding (no bits: the stream
+    stores `window` keypoints per window).  GATE's (1, 1, F*29, F*29) buffer is the nW = 1, kw = 29 case.  Requirements, checked here once per mask (the result
+    is cached by the callers) and refused loudly otherwise - there is no dense-attention fallback:
+      * every entry is 0 or -10000;
+      * entries between tokens more than one frame apart are -10000 (frame-banded);
+      * the (f, f-1), (f, f) and (f, f+1) blocks do not depend on f (frame-invariant);
+      * every token has at least one edge (so the -10000 terms vanish in the reference's fp32 softmax and the banded
+        softmax equals it).
+    Integer / bit work only; runs as a handful of torch ops on the mask's device at model set-up, not on the step."""
+    m = adj_mask.detach()
+    if m.dim() in (2, 4):
+        m = m.reshape(-1, m.shape[-2], m.shape[-1])
+    nW, N, N2 = m.shape
+    if N != N2 or N % frames:
+        raise _lib.HwgatError(f"adjacency mask {tuple(adj_mask.shape)} does not cover {frames} frames")
+    kw = N // frames
+    if kw > window or window not in BAND_WINDOWS:
+        raise _lib.HwgatError(f"band attention: {kw} keypoints per window do not fit the kernels' window of {window}")
+    edge = m == 0
+    if not bool((edge | (m == -10000.0)).all()):
+        raise _lib.HwgatError("band attention: the additive mask must hold only 0 (edge) and -10000 (no edge)")
+    e = edge.reshape(nW, frames, kw, frames, kw).permute(0, 1, 3, 2, 4)          # (nW, fq, fk, i, j)
+    fq = torch.arange(frames, device=m.device)
+    far = (fq[:, None] - fq[None, :]).abs() > 1
+    if bool(e[:, far].any()):
+        raise _lib.HwgatError("band attention: the graph links tokens more than one frame apart; the sm_100a kernels "
+                              "evaluate the frame band only and there is no dense fallback")
+    blocks = []
+    for r in (-1, 0, 1):                                                        # key frame = query frame + r
+        q = fq[(fq + r >= 0) & (fq + r < frames)]
+        if q.numel() == 0:
+            blocks.append(torch.zeros(nW, kw, kw, dtype=torch.bool, device=m.device))
+            continue
+        blk = e[:, q, q + r]                                                    # (nW, n, i, j)
+        if not bool((blk == blk[:, :1]).all()):
+            raise _lib.HwgatError("band attention: the graph changes from frame to frame (not frame-invariant)")
+        blocks.append(blk[:, 0])
+    band = torch.stack(blocks, dim=2)                                           # (nW, i, 3, j)
+    if not bool(e.any(dim=-1).any(dim=2).all()):
+        raise _lib.HwgatError("band attention: a token without any edge (its softmax would spread over all tokens)")
+    weights = (1 << torch.arange(kw, device=m.device, dtype=torch.int64))
+    words = (band.to(torch.int64) * weights).sum(dim=-1)                        # (nW, kw, 3)
+    out = torch.zeros(nW, window, 3, dtype=torch.int64, device=m.device)
+    out[:, :kw] = words
+    # uint32 payload in an int32 tensor (bit 31 = keypoint 31)
+    out = torch.where(out >= 2 ** 31, out - 2 ** 32, out).to(torch.int32)
+    return out.contiguous()
+
+
+class _BandGraphAttention(torch.autograd.Function):
+    """QKV projection (tcgen05 GEMM) + frame-banded graph attention (K15) ; backward K16 + the three GEMMs."""
+
+    @staticmethod
+    def forward(ctx, xn, w_qkv, b_qkv, bits, heads, window):
+        lib = _lib.load()
+        _need_cuda(xn, w_qkv, b_qkv, bits)
+        if xn.dtype != torch.bfloat16 or xn.dim() != 4:
+            raise _lib.HwgatError("band attention takes the bf16 (B, F, K, d) stream (bf16 autocast only, no fallback)")
+        xn_c = xn.contiguous()
+        B, F, K, d = xn_c.shape
+        if bits.shape != (K // window, window, 3):
+            raise ValueError(f"band words {tuple(bits.shape)} do not match K = {K}, window = {window}")
+        w_c = cast_cached(w_qkv, torch.bfloat16)
+        b_c = cast_cached(b_qkv, torch.float32)
+        n_tok = B * F * K
+        out = torch.empty_like(xn_c)
+        qkv = torch.empty((n_tok, 3 * d), dtype=torch.bfloat16, device=xn_c.device)
+        need = any(ctx.needs_input_grad[:3])
+        lse = torch.empty((n_tok, heads), dtype=torch.float32, device=xn_c.device) if need else None
+        with torch.cuda.device(xn_c.device):
+            check(lib.hwgat_band_attn_fwd(xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
+                                          out.data_ptr(), qkv.data_ptr(), _ptr(lse), B, F, K, d, heads, window,
+                                          _stream()), "hwgat_band_attn_fwd")
+        if need:
+            ctx.save_for_backward(xn_c, w_c, bits, qkv, out, lse)
+        ctx.meta = (heads, window, w_qkv.dtype, b_qkv.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        xn_c, w_c, bits, qkv, out, lse = ctx.saved_tensors
+        heads, window, w_dtype, b_dtype = ctx.meta
+        B, F, K, d = xn_c.shape
+        g = d_out.to(torch.bfloat16).contiguous()
+        d_xn = torch.empty_like(xn_c)
+        d_w = torch.empty((3 * d, d), dtype=torch.float32, device=xn_c.device)
+        d_b = torch.empty((3 * d,), dtype=torch.float32, device=xn_c.device)
+        ws_bytes = lib.hwgat_band_attn_workspace_bytes(B, F, K, d, 1)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xn_c.device)
+        with torch.cuda.device(xn_c.device):
+            check(lib.hwgat_band_attn_bwd(g.data_ptr(), xn_c.data_ptr(), w_c.data_ptr(), qkv.data_ptr(), out.data_ptr(),
+                                          lse.data_ptr(), bits.data_ptr(), d_xn.data_ptr(), d_w.data_ptr(),
+                                          d_b.data_ptr(), ws.data_ptr(), ws.numel(), B, F, K, d, heads, window,
+                                          _stream()), "hwgat_band_attn_bwd")
+        return d_xn, d_w.to(w_dtype), d_b.to(b_dtype), None, None, None
+
+
+def band_attention_supported(B: int, F: int, K: int, d: int, heads: int, window: int) -> bool:
+    return (window in BAND_WINDOWS and K % window == 0 and d % 128 == 0 and d % heads == 0
+            and d // heads in (16, 32, 64) and (B * F * K) % 128 == 0)
+
+
+def band_graph_attention(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, bits: torch.Tensor, heads: int,
+                         window: int) -> torch.Tensor:
+    """window_partition + QKV + additive-masked attention over all frames + window_reverse of WGATE
+    (WGATE.py:150-158, 87-106) / the masked full attention of GATE (GATE.py:49-66), without the output projection, on
+    the (B, F, K, d) bf16 stream.  bits: band_mask_pack(...).  The attention evaluates the graph's frame band only
+    (see band_mask_pack for why that equals the reference's dense softmax)."""
+    return _BandGraphAttention.apply(xn, w_qkv, b_qkv, bits, heads, window)
+
+
+# --------------------------------------------------------------------------
 # K4: temporal merge
 # --------------------------------------------------------------------------
 
@@ -734,6 +858,68 @@ def fourier_embed(x: torch.Tensor, fourier_b: torch.Tensor, pe: torch.Tensor, p:
         check(lib.hwgat_embed_fwd(x_c.data_ptr(), b_c.data_ptr(), pe_c.data_ptr(), out.data_ptr(), Bsz * T * K, C, E, K,
                                   T, pp, seed, off, _stream()), "hwgat_embed_fwd")
     return out
+
+
+class _LayerNormWeightedPool(torch.autograd.Function):
+    """K9 with learned token weights (GATE.py:205-207)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, tok_w, tok_b, eps, kp_real):
+        lib = _lib.load()
+        _need_cuda(x, gamma, beta, tok_w)
+        if x.dtype != torch.float32 or x.dim() != 4:
+            raise _lib.HwgatError("layer_norm_weighted_pool takes the fp32 residual stream as (B, F, K, d)")
+        x_c = x.contiguous()
+        Bsz, F, kp_st, d = x_c.shape
+        kp_pad = kp_st if kp_real and kp_real != kp_st else 0
+        kp_r = kp_real if kp_pad else 0
+        tokens = F * (kp_real or kp_st)
+        w_c = tok_w.detach().float().reshape(-1).contiguous()
+        if w_c.numel() != tokens:
+            raise ValueError(f"token weights: {w_c.numel()} for {tokens} tokens")
+        g_c, b_c = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        wsum = w_c.sum()
+        beta_eff = b_c * wsum + (tok_b.detach().float().reshape(()) if tok_b is not None else 0.0)
+        pooled = torch.empty((Bsz, d), dtype=torch.float32, device=x_c.device)
+        mean = torch.empty(Bsz * F * kp_st, dtype=torch.float32, device=x_c.device)
+        rstd = torch.empty(Bsz * F * kp_st, dtype=torch.float32, device=x_c.device)
+        sc_bytes = lib.hwgat_ln_pool_scratch_bytes(Bsz, tokens, d)
+        scratch = torch.empty(sc_bytes, dtype=torch.uint8, device=x_c.device) if sc_bytes else None
+        with torch.cuda.device(x_c.device):
+            check(lib.hwgat_ln_wpool_fwd(x_c.data_ptr(), g_c.data_ptr(), beta_eff.data_ptr(), w_c.data_ptr(),
+                                         pooled.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(scratch), sc_bytes,
+                                         Bsz, tokens, d, float(eps), kp_r, kp_pad, _stream()), "hwgat_ln_wpool_fwd")
+        ctx.save_for_backward(x_c, g_c, b_c, w_c, mean, rstd)
+        ctx.meta = (Bsz, tokens, d, gamma.dtype, beta.dtype, kp_r, kp_pad, tok_w.shape, tok_w.dtype, wsum,
+                    None if tok_b is None else (tok_b.shape, tok_b.dtype))
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x_c, g_c, b_c, w_c, mean, rstd = ctx.saved_tensors
+        Bsz, tokens, d, gdt, bdt, kp_r, kp_pad, w_shape, w_dt, wsum, tb = ctx.meta
+        gg = g.float().contiguous()
+        dx = torch.zeros_like(x_c) if kp_pad else torch.empty_like(x_c)
+        dgamma = torch.empty(d, dtype=torch.float32, device=x_c.device)
+        d_w = torch.empty(tokens, dtype=torch.float32, device=x_c.device)
+        part = torch.empty(max(Bsz * tokens, 1), dtype=torch.float32, device=x_c.device)
+        with torch.cuda.device(x_c.device):
+            check(lib.hwgat_ln_wpool_bwd(gg.data_ptr(), x_c.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g_c.data_ptr(),
+                                         w_c.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), d_w.data_ptr(),
+                                         part.data_ptr(), Bsz, tokens, d, kp_r, kp_pad, _stream()), "hwgat_ln_wpool_bwd")
+        gsum = gg.sum(0)                                   # (d,) tiny
+        d_w = d_w + (gsum * b_c).sum()                     # + sum_b g[b] . beta, the same for every token
+        d_tb = None if tb is None else gsum.sum().reshape(tb[0]).to(tb[1])
+        return dx, dgamma.to(gdt), (gsum * wsum).to(bdt), d_w.reshape(w_shape).to(w_dt), d_tb, None, None
+
+
+def layer_norm_weighted_pool(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, tok_w: torch.Tensor,
+                             tok_b: Optional[torch.Tensor], eps: float = 1e-5, kp_real: int = 0) -> torch.Tensor:
+    """(B, F, K, d) -> (B, d): sum_t tok_w[t] * LayerNorm(x)[b, t] + tok_b - self.norm followed by GATE's learned
+    `weightedAvg` Linear(F*K, 1) over the token axis (GATE.py:205-207) in one pass over x.  kp_real as in
+    layer_norm_mean_pool (tok_w indexes the real tokens frame * kp_real + keypoint)."""
+    return _LayerNormWeightedPool.apply(x, gamma, beta, tok_w, tok_b, eps, kp_real)
 
 
 class _LayerNormPool(torch.autograd.Function):

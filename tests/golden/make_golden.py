@@ -286,10 +286,89 @@ def hgate_golden(mp, sce):
     np.savez_compressed(os.path.join(HERE, "hgate.npz"), **out)
 
 
+def wgate_gate_golden(mp, sce):
+    """Section 8: the sibling models WGATE (hwgat/models/WGATE.py, WGATEParams) and GATE (hwgat/models/GATE.py,
+    GATEParams): dense attention over all frames with the graph as an additive -10000 mask.  Unmodified reference,
+    fp64: the additive masks, MSA forward + backward, the full models with the loss and every parameter gradient."""
+    import importlib
+    from oracle import wgate_oracle as WG
+    wg = importlib.import_module("models.WGATE")
+    ga = importlib.import_module("models.GATE")
+    out = {}
+
+    class Parent:                      # MSA.forward reads the mask off `parent` by name (WGATE.py:102, GATE.py:60)
+        pass
+
+    for name, F in (("wgate", 8), ("gate", 6)):
+        if name == "wgate":
+            params = mp.WGATEParams({"num_class": 10, "src_len": F}, 2, "cpu")
+            K = 64
+        else:
+            params = mp.GATEParams({"num_class": 10, "src_len": F}, 2, "cpu")
+            K = 29
+        params.drop_rate = 0.0
+        adj = params.adj_mat
+        out[name + "_adj"] = adj.numpy().astype(np.uint8)
+        mask = adj.masked_fill(adj == 0, float(-10000)).masked_fill(adj == 1, float(0))     # WGATE.py:190 / GATE.py:142
+        parent = Parent()
+        parent.adj_mask = mask.double() if name == "wgate" else mask.double()[None, None]
+        for (d, h) in ((128, 8), (128, 2), (256, 8)):
+            B = 2
+            std = 0.2 if d == 128 else 0.1
+            rng = np.random.default_rng(6000 + d + h + (0 if name == "wgate" else 1))
+            xn = torch.from_numpy(rng.standard_normal((B, F, K, d)))
+            w = torch.from_numpy(rng.standard_normal((3 * d, d)) * std)
+            b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1)
+            g = torch.from_numpy(rng.standard_normal((B, F, K, d)))
+            msa = (wg if name == "wgate" else ga).MSA(h, d, adj_mask="adj_mask").double()
+            with torch.no_grad():
+                msa.qkv.weight.copy_(w); msa.qkv.bias.copy_(b)
+                msa.proj.weight.copy_(torch.eye(d, dtype=torch.float64)); msa.proj.bias.zero_()
+            xn_ = xn.clone().requires_grad_(True)
+            if name == "wgate":
+                y = wg.window_reverse(msa(wg.window_partition(xn_, 16), B, 4, parent), 16, F, K)    # WGATE.py:155-157
+            else:
+                y = msa(xn_.reshape(B, F * K, d), parent).reshape(B, F, K, d)                       # GATE.py:198, 106
+            (y * g).sum().backward()
+            key = f"{name}_d{d}_h{h}"
+            out[key + "_y"], out[key + "_ysum"] = sample(y, 53)
+            out[key + "_dx"], out[key + "_dxsum"] = sample(xn_.grad, 53)
+            out[key + "_dw"], out[key + "_dwsum"] = sample(msa.qkv.weight.grad, 251)
+            out[key + "_db"] = msa.qkv.bias.grad.numpy().copy()
+        # full model: T = 8 (WGATE) / 6 (GATE), depth cut to 3 blocks, fp64, loss and gradients
+        params.depths = 3
+        cfg = (WG.WGATEConfig if name == "wgate" else WG.GATEConfig)(temporal_dim=F, num_classes=10, depths=3)
+        sd = WG.make_state_dict(cfg, seed=1001, weight_std=0.05)
+        model = (wg if name == "wgate" else ga).Model(*params.get_model_params())
+        model.load_state_dict(sd, strict=True)
+        out[name + "_state_dict_names"] = np.array(list(model.state_dict().keys()))
+        out[name + "_state_dict_shapes"] = np.array([str(tuple(v.shape)) for v in model.state_dict().values()])
+        model = model.double()
+        x = WG.synthetic_keypoints(2, F, K, seed=1001).double()
+        y = torch.from_numpy(np.array([3, 7]))
+        model.train()                               # drop_rate 0: train == eval (neither model has a threshold path)
+        logits = model(x)
+        loss = sce.SmoothedCrossEntropyLoss()(logits, y)
+        loss.backward()
+        out[name + "_model_logits"] = logits.detach().numpy()
+        out[name + "_model_loss"] = np.array(loss.item())
+        names, norms, heads = [], [], []
+        for n, p in model.named_parameters():
+            if p.grad is None:
+                continue
+            first = np.zeros(4); first[:min(4, p.numel())] = p.grad.reshape(-1)[:4].numpy()     # (weightedAvg.bias has 1)
+            names.append(n); norms.append(p.grad.norm().item()); heads.append(first)
+        out[name + "_gnames"], out[name + "_gnorms"], out[name + "_gheads"] = np.array(names), np.array(norms), np.stack(heads)
+    np.savez_compressed(os.path.join(HERE, "wgate_gate.npz"), **out)
+
+
 def main():
     from oracle import hwgate_oracle as O
     hw, mp, sce = import_reference()
     torch.manual_seed(0)
+    if "--only-wgate" in sys.argv:
+        wgate_gate_golden(mp, sce)
+        return
     if "--only-hgate" in sys.argv:
         hgate_golden(mp, sce)
         return

@@ -326,3 +326,102 @@ def test_hgate_full_model_matches_reference(golden_dir):
         gr = sd64[str(name)].grad
         assert abs(gr.norm().item() - norm) <= 1e-8 * norm, name
         assert np.abs(gr.reshape(-1)[:4].numpy() - head).max() <= 1e-8 * max(np.abs(head).max(), 1e-12), name
+
+
+# ------------------------------------------------------------------ sibling models WGATE and GATE (section 8)
+def band_core_inputs(name, d, h, B=2):
+    """Same seeded inputs as tests/golden/make_golden.py section 8."""
+    F, K = (8, 64) if name == "wgate" else (6, 29)
+    std = 0.2 if d == 128 else 0.1
+    rng = np.random.default_rng(6000 + d + h + (0 if name == "wgate" else 1))
+    xn = torch.from_numpy(rng.standard_normal((B, F, K, d)))
+    w = torch.from_numpy(rng.standard_normal((3 * d, d)) * std)
+    b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1)
+    g = torch.from_numpy(rng.standard_normal((B, F, K, d)))
+    return xn, w, b, g
+
+
+def band_adjacency(name):
+    from oracle import wgate_oracle as WG
+    if name == "wgate":
+        return WG.wgate_adjacency(WG.WGATEConfig().edges, 8, 16)
+    return WG.gate_adjacency(WG.GATEConfig().edges, 6, 29)
+
+
+@pytest.mark.parametrize("name", ["wgate", "gate"])
+def test_wgate_gate_adjacency_matches_reference(golden_dir, name):
+    G = _load(golden_dir, "wgate_gate.npz")
+    adj = band_adjacency(name)
+    assert adj.shape == G[name + "_adj"].shape and np.array_equal(adj != 0, G[name + "_adj"] != 0)
+    assert set(np.unique(adj)) == {0.0, 1.0}
+
+
+@pytest.mark.parametrize("name", ["wgate", "gate"])
+@pytest.mark.parametrize("d,h", [(128, 8), (128, 2), (256, 8)])
+def test_wgate_gate_attention_core_matches_reference(golden_dir, name, d, h):
+    from oracle import wgate_oracle as WG
+    G = _load(golden_dir, "wgate_gate.npz")
+    key = f"{name}_d{d}_h{h}"
+    xn, w, b, g = band_core_inputs(name, d, h)
+    mask = WG.additive_mask(band_adjacency(name))
+    x_, w_, b_ = (t.clone().requires_grad_(True) for t in (xn, w, b))
+    if name == "wgate":
+        y = WG.wgate_attention_core(x_, w_, b_, h, mask, 16)
+    else:
+        y = WG.gate_attention_core(x_, w_, b_, h, mask)
+    (y * g).sum().backward()
+
+    def chk(t, nm, stride):
+        a = t.detach().reshape(-1).numpy()
+        ref = G[key + "_" + nm]
+        assert np.abs(a[::stride] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (key, nm)
+        s = G[key + "_" + nm + "sum"]
+        assert abs(a.sum() - s[0]) <= 1e-9 * s[1] and a.size == int(s[2])
+    chk(y, "y", 53)
+    chk(x_.grad, "dx", 53)
+    chk(w_.grad, "dw", 251)
+    assert np.abs(b_.grad.numpy() - G[key + "_db"]).max() <= 1e-9 * np.abs(G[key + "_db"]).max()
+
+
+@pytest.mark.parametrize("name", ["wgate", "gate"])
+def test_wgate_gate_full_model_matches_reference(golden_dir, name):
+    from oracle import wgate_oracle as WG
+    G = _load(golden_dir, "wgate_gate.npz")
+    F, K = (8, 64) if name == "wgate" else (6, 29)
+    cfg = (WG.WGATEConfig if name == "wgate" else WG.GATEConfig)(temporal_dim=F, num_classes=10, depths=3)
+    sd = WG.make_state_dict(cfg, seed=1001, weight_std=0.05)
+    assert sorted(sd.keys()) == sorted(G[name + "_state_dict_names"])
+    shapes = dict(zip(G[name + "_state_dict_names"], G[name + "_state_dict_shapes"]))
+    assert all(str(tuple(v.shape)) == shapes[k] for k, v in sd.items())
+    sd64 = {k: v.double().requires_grad_(k not in ("B", "pos_encoder.pe", "adj_mask")) for k, v in sd.items()}
+    x = WG.synthetic_keypoints(2, F, K, seed=1001).double()
+    logits = (WG.wgate_forward if name == "wgate" else WG.gate_forward)(x, sd64, cfg)
+    ref = G[name + "_model_logits"]
+    assert np.abs(logits.detach().numpy() - ref).max() <= 1e-9 * np.abs(ref).max()
+    loss = O.smoothed_cross_entropy(logits, torch.tensor([3, 7]))
+    assert abs(loss.item() - float(G[name + "_model_loss"])) < 1e-9
+    loss.backward()
+    for pname, norm, head in zip(G[name + "_gnames"], G[name + "_gnorms"], G[name + "_gheads"]):
+        gr = sd64[str(pname)].grad
+        assert abs(gr.norm().item() - norm) <= 1e-8 * norm, pname
+        got = np.zeros(4); got[:min(4, gr.numel())] = gr.reshape(-1)[:4].numpy()
+        assert np.abs(got - head).max() <= 1e-8 * max(np.abs(head).max(), 1e-12), pname
+
+
+@pytest.mark.parametrize("name", ["wgate", "gate"])
+def test_band_restriction_equals_dense_additive_softmax(name):
+    """The claim the product kernels rest on (band_attn.cu header): with the reference's graphs, softmax(logits +
+    additive mask) over all F*k tokens equals the softmax over the 3-frame band's edges alone - in fp32 the -10000
+    terms underflow to exactly 0 once the row maximum (an edge) is subtracted."""
+    from oracle import wgate_oracle as WG
+    adj = band_adjacency(name)
+    adj = adj[0] if name == "wgate" else adj
+    N = adj.shape[0]
+    rng = np.random.default_rng(7)
+    s = torch.from_numpy(rng.standard_normal((N, N)).astype(np.float32) * 8.0)            # logits up to ~ +-35
+    dense = torch.softmax(s + torch.from_numpy(WG.additive_mask(adj).astype(np.float32)), dim=-1)
+    edges = torch.from_numpy(adj != 0)
+    banded = torch.softmax(torch.where(edges, s, torch.full_like(s, float("-inf"))), dim=-1)
+    assert torch.equal(dense == 0, ~edges)                     # every non-edge weighs exactly zero
+    assert torch.allclose(dense, banded, rtol=1e-6, atol=0)
+    assert bool(edges.any(dim=-1).all())                       # no empty row (else the softmax would go dense)

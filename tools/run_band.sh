@@ -1,0 +1,5 @@
+#!/bin/bash
+# band attention (WGATE / GATE): parity tests
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_band.py -x -q -m gpu -s > gpurun_out/r02n_band_tests.log 2>&1
+tail -30 gpurun_out/r02n_band_tests.log
