@@ -56,6 +56,14 @@ CONFIGS = {
     "hgate_train512": ("train", 64, 262, 512, 32,
                        "sibling model HGATE (hwgat/models/HGATE.py): training fwd+bwd, T=64 frames x 29 keypoints x 2, "
                        "262 classes, depths [2,2,4], heads [2,4,8], TP=2, dropout 0.1"),
+    # the sibling models WGATE / GATE: one width, 8 blocks, attention over all frames with an
+    # additive graph mask - evaluated here as a 3-frame band (K15 / K16)
+    "wgate_train512": ("train", 64, 262, 512, 16,
+                       "sibling model WGATE (hwgat/models/WGATE.py): training fwd+bwd, T=64 frames x 64 keypoints x 2, "
+                       "262 classes, 8 blocks, d=128, 8 heads, windows of 16 keypoints x all frames, dropout 0.1"),
+    "gate_train512": ("train", 64, 262, 512, 32,
+                      "sibling model GATE (hwgat/models/GATE.py): training fwd+bwd, T=64 frames x 29 keypoints x 2, "
+                      "262 classes, 8 blocks, d=128, 8 heads, attention over all 1856 tokens, dropout 0.1"),
 }
 MODEL = "HWGATE"
 
@@ -63,8 +71,8 @@ MODEL = "HWGATE"
 def set_config(name):
     global T_FRAMES, CLASSES, WINDOW, METRIC, MODEL, KPS
     mode, T_FRAMES, CLASSES, batch, WINDOW, what = CONFIGS[name]
-    MODEL = "HGATE" if name.startswith("hgate") else "HWGATE"
-    KPS = 32 if MODEL == "HGATE" else 64          # stored keypoints per frame
+    MODEL = {"hgate": "HGATE", "wgate": "WGATE", "gate": "GATE"}.get(name.split("_")[0], "HWGATE")
+    KPS = 32 if MODEL in ("HGATE", "GATE") else 64          # stored keypoints per frame
     METRIC = "HWGAT sequences/sec fwd+bwd" if mode == "train" else "HWGAT sequences/sec inference forward"
     return mode, batch, what
 
@@ -149,7 +157,7 @@ class KernelTimer:
                      "hwgat_ln_bwd_unmerge", "hwgat_merge_fwd", "hwgat_merge_bwd", "hwgat_ln_fwd",
                      "hwgat_ln_bwd", "hwgat_bda_ln_fwd", "hwgat_bda_ln_bwd", "hwgat_bias_gelu_dropout_fwd",
                      "hwgat_bias_gelu_dropout_bwd", "hwgat_ffn_fwd", "hwgat_ffn_bwd", "hwgat_proj_fwd",
-                     "hwgat_proj_bwd"):
+                     "hwgat_proj_bwd", "hwgat_band_attn_fwd", "hwgat_band_attn_bwd"):
             fn = getattr(lib, name)
             self.orig[name] = fn
             setattr(lib, name, self._wrap(name, fn))
@@ -158,6 +166,8 @@ class KernelTimer:
     DIM_ARG = {
         "hwgat_attn_fwd": lambda a: (int(a[11]), 0), "hwgat_attn_bwd": lambda a: (int(a[14]), 0),
         "hwgat_attn2_fwd": lambda a: (int(a[12]), 0), "hwgat_attn2_bwd": lambda a: (int(a[15]), 0),
+        "hwgat_band_attn_fwd": lambda a: (int(a[10]), int(a[7]) * int(a[8]) * int(a[9]), int(a[12])),
+        "hwgat_band_attn_bwd": lambda a: (int(a[15]), int(a[12]) * int(a[13]) * int(a[14]), int(a[17])),   # (.., W, diag, stream)
         "hwgat_bda_merge_fwd": lambda a: (int(a[5]), int(a[4]), False),
         "hwgat_ln_bwd_unmerge": lambda a: (int(a[10]), int(a[9])),
         "hwgat_merge_fwd": lambda a: (int(a[5]), 0), "hwgat_merge_bwd": lambda a: (int(a[5]), 0),
@@ -204,6 +214,14 @@ class KernelTimer:
         for (name, key), (ms, cnt) in sorted(agg.items()):
             d = key[0]
             avg = ms / cnt
+            if "band_attn" in name:
+                # QKV projection + banded core (W queries x 3W keys per frame): 6 n d^2 + 4 n 3W d FLOP, backward twice
+                n_rows, W = key[1], key[2]
+                fl = (6.0 * n_rows * d * d + 12.0 * n_rows * W * d) * (2 if name.endswith("bwd") else 1)
+                out.append({"kernel": ("K16 " if name.endswith("bwd") else "K15 ") + f"{name} d={d}", "bound": "tensor",
+                            "calls_per_step": cnt / steps, "avg_ms": avg, "alg_flops": fl,
+                            "achieved": fl / (avg * 1e-3) / 1e12, "unit": "TFLOP/s", "total_ms": ms})
+                continue
             if "attn" in name:
                 level = {128: 0, 256: 1, 512: 2}[d]
                 fl = attn_flops(B, level, name.endswith("bwd"))
@@ -245,12 +263,13 @@ class KernelTimer:
 def build_model(device, drop=0.1):
     import torch
     from sl_hwgat_b200.models import HWGATE, model_params
-    if MODEL == "HGATE":
-        from sl_hwgat_b200.models import HGATE
-        p = model_params.HGATEParams({"num_class": CLASSES, "src_len": T_FRAMES}, 2, device)
+    if MODEL in ("HGATE", "WGATE", "GATE"):
+        import importlib
+        mod = importlib.import_module("sl_hwgat_b200.models." + MODEL)
+        p = getattr(model_params, MODEL + "Params")({"num_class": CLASSES, "src_len": T_FRAMES}, 2, device)
         p.drop_rate = drop
         torch.manual_seed(1001)
-        return HGATE.Model(*p.get_model_params()).to(device)
+        return mod.Model(*p.get_model_params()).to(device)
     p = model_params.HWGATEParams({"num_class": CLASSES, "src_len": T_FRAMES}, 2, device)
     p.drop_rate = drop
     if WINDOW != p.window_size:
@@ -268,7 +287,7 @@ def synthetic_batch(B):
     gather = np.array(head + larm + lh + head + rarm + rh + head + larm + rh + head + rarm + lh)
     rng = np.random.default_rng(1001)
     raw = rng.random((B, T_FRAMES, 29, 2), dtype=np.float32)
-    x = torch.from_numpy(np.ascontiguousarray(raw if MODEL == "HGATE" else raw[:, :, gather, :]))
+    x = torch.from_numpy(np.ascontiguousarray(raw if MODEL in ("HGATE", "GATE") else raw[:, :, gather, :]))
     y = torch.from_numpy(rng.integers(0, CLASSES, size=(B,), dtype=np.int64))
     return x, y
 
@@ -283,6 +302,13 @@ def _oracle_setup(batch, device=None):
         sd = H.make_state_dict(cfg, seed=1001)
         x = H.synthetic_keypoints(batch, T_FRAMES, seed=1001)
         fwd = lambda xx, s_, thr, drop: H.model_forward(xx, s_, cfg, drop=drop, training=thr is not None)
+    elif MODEL in ("WGATE", "GATE"):
+        from oracle import wgate_oracle as WG
+        cfg = (WG.WGATEConfig if MODEL == "WGATE" else WG.GATEConfig)(temporal_dim=T_FRAMES, num_classes=CLASSES)
+        sd = WG.make_state_dict(cfg, seed=1001)
+        x = WG.synthetic_keypoints(batch, T_FRAMES, cfg.num_kps, seed=1001)
+        model_fwd = WG.wgate_forward if MODEL == "WGATE" else WG.gate_forward
+        fwd = lambda xx, s_, thr, drop: model_fwd(xx, s_, cfg, drop=drop, training=thr is not None)
     else:
         cfg = O.HWGATEConfig(temporal_dim=T_FRAMES, num_classes=CLASSES, window_size=WINDOW,
                              edges=O.HWGATEConfig().edges[:64 // WINDOW])
@@ -293,7 +319,7 @@ def _oracle_setup(batch, device=None):
     if device is not None:
         sd = {k: v.to(device) for k, v in sd.items()}
         x, y = x.to(device), y.to(device)
-    return fwd, sd, x, y, sum(cfg.depths)
+    return fwd, sd, x, y, (sum(cfg.depths) if MODEL in ("HWGATE", "HGATE") else 0)
 
 
 def cpu_reference_arm(steps, warmup, batch=8, mode="train"):
@@ -304,7 +330,7 @@ def cpu_reference_arm(steps, warmup, batch=8, mode="train"):
     torch.set_num_threads(cores)
     fwd, sd, x, y, n_thr = _oracle_setup(batch)
     for k, v in sd.items():
-        if mode == "train" and k not in ("B", "pos_encoder.pe") and not k.endswith("attn_mask"):
+        if mode == "train" and k not in ("B", "pos_encoder.pe", "adj_mask") and not k.endswith("attn_mask"):
             v.requires_grad_(True)
     torch.manual_seed(1001)
     times = []
@@ -326,7 +352,7 @@ def cpu_reference_arm(steps, warmup, batch=8, mode="train"):
     return {"value": batch * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"oracle port of the reference {MODEL} (fp32, " +
                       ("train mode, dropout 0.1" if mode == "train" else "eval forward") +
-                      f"), batch {batch} x T={T_FRAMES} x {29 if MODEL == 'HGATE' else 64} kp x 2, {CLASSES} classes, "
+                      f"), batch {batch} x T={T_FRAMES} x {29 if MODEL in ('HGATE', 'GATE') else 64} kp x 2, {CLASSES} classes, "
                       f"window_size {WINDOW}, "
                       f"{len(times)} " + ("fwd+bwd" if mode == "train" else "forward") + f" steps after {warmup} warm-up",
             "ms_per_step": 1e3 * total / len(times), "batch": batch}
@@ -343,9 +369,11 @@ def gpu_eager_baseline(dev, mode, batch):
     train = mode == "train"
     fwd, sd, _, _, n_thr = _oracle_setup(8, dev)
     for k, v in sd.items():
-        if train and k not in ("B", "pos_encoder.pe") and not k.endswith("attn_mask"):
+        if train and k not in ("B", "pos_encoder.pe", "adj_mask") and not k.endswith("attn_mask"):
             v.requires_grad_(True)
     out = {}
+    if MODEL in ("WGATE", "GATE"):
+        batch = min(batch, 32)     # dense (F*k)^2 logits: 1 GiB per block per 32 sequences in fp32 at T = 64, kept for backward
     for name, autocast in (("fp32", False), ("bf16_autocast", True)):
         B = batch
         while B >= 8:

@@ -30,7 +30,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 15; }
+int hwgat_version(void) { return 16; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -162,19 +162,21 @@ size_t hwgat_band_attn_workspace_bytes(int B, int F, int K, int d, int backward)
 }
 
 int hwgat_band_attn_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, void* out,
-                        void* qkv, float* lse, int B, int F, int K, int d, int heads, int W, hwgat_stream_t stream) {
+                        void* qkv, float* lse, int B, int F, int K, int d, int heads, int W, int diag,
+                        hwgat_stream_t stream) {
   if (!band_attn_supported(B, F, K, d, heads, W)) return B < 0 || F < 1 || K < 1 ? HWGAT_ERR_SHAPE : HWGAT_ERR_UNSUPPORTED;
   if (B == 0) return HWGAT_OK;
   if (!xn || !w_qkv || !b_qkv || !bits || !out || !qkv) return HWGAT_ERR_NULL;
   if (misaligned(xn) || misaligned(w_qkv) || misaligned(b_qkv) || misaligned(out) || misaligned(qkv) || misaligned(lse))
     return HWGAT_ERR_ALIGN;
   return band_attn_fwd((const __nv_bfloat16*)xn, (const __nv_bfloat16*)w_qkv, b_qkv, bits, (__nv_bfloat16*)out,
-                       (__nv_bfloat16*)qkv, lse, B, F, K, d, heads, W, (cudaStream_t)stream);
+                       (__nv_bfloat16*)qkv, lse, B, F, K, d, heads, W, diag, (cudaStream_t)stream);
 }
 
 int hwgat_band_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const void* qkv, const void* ctx,
                         const float* lse, const uint32_t* bits, void* d_xn, float* d_w, float* d_b, void* workspace,
-                        size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, hwgat_stream_t stream) {
+                        size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int diag,
+                        hwgat_stream_t stream) {
   if (!band_attn_supported(B, F, K, d, heads, W)) return B < 0 || F < 1 || K < 1 ? HWGAT_ERR_SHAPE : HWGAT_ERR_UNSUPPORTED;
   if (!d_w || !d_b) return HWGAT_ERR_NULL;
   if (B == 0) {
@@ -189,7 +191,7 @@ int hwgat_band_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, co
   if (!workspace || workspace_bytes < hwgat_band_attn_workspace_bytes(B, F, K, d, 1)) return HWGAT_ERR_WORKSPACE;
   return band_attn_bwd((const __nv_bfloat16*)xn, (const __nv_bfloat16*)w_qkv, bits, (const __nv_bfloat16*)qkv,
                        (const __nv_bfloat16*)ctx, lse, (const __nv_bfloat16*)d_out, (__nv_bfloat16*)d_xn, d_w, d_b,
-                       workspace, B, F, K, d, heads, W, (cudaStream_t)stream);
+                       workspace, B, F, K, d, heads, W, diag, (cudaStream_t)stream);
 }
 
 size_t hwgat_attn2_workspace_bytes(int B, int F, int K, int d, int heads, int backward, int have_qkv) {

@@ -18,12 +18,19 @@
 // in TMEM) would only add latency to a kernel that waits for memory.
 //
 // One CTA (8 warps) owns FR consecutive frames of one (sample, window) and one 64-column slice of d (64 / HD heads):
-// it stages q, k, v (backward: + dO) of frames f0-1 .. f0+FR in shared memory with 16-byte coalesced copies (128-byte
-// rows, XOR-swizzled for ldmatrix), then every warp works on one (frame, 16-query tile) from fragments.
+// one thread issues a TMA box copy per tensor - (64 columns, W keypoints, FR+2 frames) of q, k, v (backward: + dO) with
+// the 128-byte hardware swizzle ldmatrix wants; frames -1 and F of the halo come back zero-filled - and then every warp
+// works on one (frame, 16-query tile) from fragments.  (The first version staged with cp.async from all threads: 17 %
+// of the forward's instructions, in a kernel that turned out to be bound by instruction issue: ncu r02o.)
+// kDiag: in the graphs the reference builds, the blocks between adjacent frames are the identity (a keypoint is linked
+// to itself in the previous and the next frame).  The host passes diag = 1 when every off-frame word is 1 << i or 0,
+// and the kernels then evaluate only the diagonal of those blocks (12 instead of 24 logits per thread per head at
+// W = 16); each CTA verifies the promise against the words it loads and traps if it is broken.  Any other band runs the
+// general path.
 // The backward needs no atomics and no cross-CTA traffic: with the forward's logsumexp saved and delta = rowsum(dO * O)
 // formed while dO is staged, a warp computes dQ of its 16 tokens as QUERIES (blocks (f, f-1..f+1)) and dK, dV of the same
 // 16 tokens as KEYS (blocks (f-1..f+1, f)); the off-diagonal blocks are computed twice, which costs nothing here.
-#include "common.cuh"
+#include "tc.cuh"
 
 namespace hwgat {
 
@@ -36,11 +43,9 @@ constexpr int kRowBytes = 128;          // 64 bf16 columns of one token per CTA
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct BandArgs {
-  const bf16* qkv;       // [n, 3d]  q | k | v (unscaled; the kernels apply hd^-1/2 to the fp32 logits)
   const uint32_t* bits;  // [nW][W][3] : bit j of word (w, i, r) = query keypoint i attends key keypoint j of frame f-1+r
   bf16* out;             // fwd: ctx [n, d]
-  float* lse;            // fwd (optional) / bwd: [n, heads] logsumexp of the scaled logits over the edges
-  const bf16* d_out;     // bwd: dO [n, d]
+  float* lse;            // fwd (optional) / bwd: [n, heads] BASE-2 logsumexp of the scaled logits over the edges
   const bf16* ctx;       // bwd: O  [n, d]
   bf16* dqkv;            // bwd: [n, 3d]
   int B, F, K, d, heads;
@@ -52,9 +57,11 @@ struct Cfg {
   static constexpr int MT = W / 16;          // 16-query tiles per frame
   static constexpr int FR = 8 / MT;          // frames per CTA (one warp per (frame, tile))
   static constexpr int NSLOT = FR + 2;       // + one halo frame on each side
-  static constexpr int kTensor = W * kRowBytes;
+  static constexpr int kTensor = W * kRowBytes;          // one frame of one tensor
+  static constexpr int kAll = NSLOT * kTensor;            // one tensor, all staged frames = one TMA box
 };
 
+// byte offset of 16-byte chunk `chunk` of staged row `row` (= slot * W + keypoint): CU_TENSOR_MAP_SWIZZLE_128B
 HW_DEV uint32_t swz(int row, int chunk) { return (uint32_t)(row * kRowBytes + ((chunk ^ (row & 7)) << 4)); }
 
 HW_DEV void ldsm4(uint32_t (&r)[4], uint32_t addr) {
@@ -65,13 +72,20 @@ HW_DEV void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-HW_DEV void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int bytes = valid ? 16 : 0;   // 0: nothing is read, the 16 bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(bytes));
+// one MUFU each (exp2f / log2f carry range fix-ups worth ~8 instructions per element; the first version spent 29 % of
+// its instructions there).  ex2(-inf) = 0: masked logits need no select after the exponential.
+HW_DEV float ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(x));
+  return r;
 }
-HW_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+HW_DEV float lg2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(x));
+  return r;
+}
 
-// A fragment (16 rows x 16 columns) of rows row0.. of a staged tensor, columns [chunk0*8, chunk0*8 + 16)
+// A fragment (16 rows x 16 columns) of staged rows row0.., columns [chunk0*8, chunk0*8 + 16)
 HW_DEV void load_a(uint32_t (&a)[4], uint32_t base, int row0, int chunk0, int lane) {
   ldsm4(a, base + swz(row0 + (lane & 7) + ((lane >> 3) & 1) * 8, chunk0 + (lane >> 4)));
 }
@@ -102,47 +116,73 @@ HW_DEV Item decode_item(const BandArgs& p) {
   return it;
 }
 
+// the words of window w into shared memory; kDiag: hold the host to its promise
+template <int W, bool kDiag>
+HW_DEV void load_bits(uint32_t* sbits, const BandArgs& p, int w, int tid) {
+  for (int i = tid; i < W * 3; i += kThreads) {
+    const uint32_t v = p.bits[w * W * 3 + i];
+    sbits[i] = v;
+    if (kDiag && i % 3 != 1 && (v & ~(1u << (i / 3))) != 0u) __trap();
+  }
+}
+
+// In the diagonal path the only live logit of row r of an off-frame block is column r.  In the accumulator layout of
+// the tile pair np == mt it belongs to lane quad position qd == (g >> 1): element (g & 1) of tile 0 for row g and element
+// 2 + (g & 1) of tile 1 for row g + 8.  Only that lane contributes; the quad reductions spread the result.
+HW_DEV float diag_row0(const float (&t0)[4], int g) { return g & 1 ? t0[1] : t0[0]; }
+HW_DEV float diag_row1(const float (&t1)[4], int g) { return g & 1 ? t1[3] : t1[2]; }
+HW_DEV void diag_frag(uint32_t (&a)[4], float v0, float v1, int g) {   // A fragment that is zero off the diagonal
+  a[0] = g & 1 ? pack_bf16(0.f, v0) : pack_bf16(v0, 0.f);
+  a[1] = 0u;
+  a[2] = 0u;
+  a[3] = g & 1 ? pack_bf16(0.f, v1) : pack_bf16(v1, 0.f);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // K15 forward
 // ---------------------------------------------------------------------------------------------------------------------
-template <int W, int HD>
-__global__ void __launch_bounds__(kThreads, 2) band_attn_fwd_kernel(const BandArgs p) {
+template <int W, int HD, bool kDiag>
+__global__ void __launch_bounds__(kThreads, kDiag ? 3 : 2)
+band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const BandArgs p) {
   using C = Cfg<W>;
   constexpr int KS = HD / 16, HPC = 64 / HD, CH = HD / 8, NTF = W / 8;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  uint32_t* sbits = reinterpret_cast<uint32_t*>(smem + C::NSLOT * 3 * C::kTensor);
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint32_t* sbits = reinterpret_cast<uint32_t*>(smem + 3 * C::kAll);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sbits + W * 3);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Item it = decode_item<W>(p);
-  const int d3 = 3 * p.d;
 
-  // stage q (own frames only), k, v of frames f0-1 .. f0+FR
-  for (int piece = tid; piece < C::NSLOT * 3 * W * 8; piece += kThreads) {
-    const int chunk = piece & 7, row = (piece >> 3) % W, t = (piece / (8 * W)) % 3, slot = piece / (8 * W * 3);
-    const int frame = it.f0 - 1 + slot;
-    const bool valid = frame >= 0 && frame < p.F && !(t == 0 && (slot == 0 || slot == C::NSLOT - 1));
-    const long long token = ((long long)it.b * p.F + (valid ? frame : 0)) * p.K + it.w * W + row;
-    cp_async16(sbase + (slot * 3 + t) * C::kTensor + swz(row, chunk),
-               p.qkv + token * d3 + (size_t)t * p.d + it.cc * 64 + chunk * 8, valid);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmQKV);
   }
-  for (int i = tid; i < W * 3; i += kThreads) sbits[i] = p.bits[it.w * W * 3 + i];
-  cp_async_wait_all();
+  load_bits<W, kDiag>(sbits, p, it.w, tid);
   __syncthreads();
+  if (tid == 0) {   // q, k, v of frames f0-1 .. f0+FR: three boxes of (64 columns, W keypoints, FR+2 frames)
+    mbar_expect_tx(bar, 3 * C::kAll);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) tma_load_4d(smem + t * C::kAll, &tmQKV, bar, t * p.d + it.cc * 64, it.w * W, it.f0 - 1, it.b);
+  }
+  mbar_wait(bar, 0);
 
   const int fi = warp / C::MT, mt = warp % C::MT;
   const int frame = it.f0 + fi;
   if (frame >= p.F) return;
   const int slot = fi + 1, g = lane >> 2, qd = lane & 3;
-  const uint32_t sq = sbase + (slot * 3 + 0) * C::kTensor;
+  const int qrow = slot * W + mt * 16;                       // first staged row of the warp's queries
+  const uint32_t sq = sbase, sk = sbase + C::kAll, sv = sbase + 2 * C::kAll;
+  const int r0 = mt * 16 + g, r1 = r0 + 8;                   // keypoints of the thread's two rows
   uint32_t mw[2][3];
 #pragma unroll
-  for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-    for (int kf = 0; kf < 3; ++kf) {
-      const int kfr = frame - 1 + kf;
-      mw[ri][kf] = kfr >= 0 && kfr < p.F ? sbits[(mt * 16 + g + ri * 8) * 3 + kf] : 0u;
-    }
+  for (int kf = 0; kf < 3; ++kf) {
+    const bool ok = (unsigned)(frame - 1 + kf) < (unsigned)p.F;
+    mw[0][kf] = ok ? sbits[r0 * 3 + kf] : 0u;
+    mw[1][kf] = ok ? sbits[r1 * 3 + kf] : 0u;
+  }
+  const bool own = qd == (g >> 1);
   const float sl2 = p.scale * kLog2e;
   const long long tok0 = ((long long)it.b * p.F + frame) * p.K + it.w * W + mt * 16;
 
@@ -150,52 +190,83 @@ __global__ void __launch_bounds__(kThreads, 2) band_attn_fwd_kernel(const BandAr
   for (int hh = 0; hh < HPC; ++hh) {
     uint32_t qa[KS][4];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) load_a(qa[ks], sq, mt * 16, hh * CH + ks * 2, lane);
-    float s[3][NTF][4];
+    for (int ks = 0; ks < KS; ++ks) load_a(qa[ks], sq, qrow, hh * CH + ks * 2, lane);
+    constexpr int NB = kDiag ? 1 : 3;          // blocks held as full tiles: the own frame, or all three
+    float s[NB][NTF][4];
+    float dg[2][2];                            // kDiag: the diagonal logits of the previous / next frame, rows g, g+8
 #pragma unroll
     for (int kf = 0; kf < 3; ++kf) {
+      const bool ok = (unsigned)(frame - 1 + kf) < (unsigned)p.F;
+      const int krow = (slot - 1 + kf) * W;
+      if (kDiag && kf != 1) {
+        float t2[2][4] = {};
+        if (ok) {
 #pragma unroll
-      for (int nt = 0; nt < NTF; ++nt) s[kf][nt][0] = s[kf][nt][1] = s[kf][nt][2] = s[kf][nt][3] = 0.f;
-      const int kfr = frame - 1 + kf;
-      if (kfr < 0 || kfr >= p.F) continue;
-      const uint32_t sk = sbase + ((slot - 1 + kf) * 3 + 1) * C::kTensor;
+          for (int ks = 0; ks < KS; ++ks) {
+            uint32_t kb[4];
+            load_b_nk(kb, sk, krow + mt * 16, hh * CH + ks * 2, lane);
+            mma16816(t2[0], qa[ks], kb[0], kb[1]);
+            mma16816(t2[1], qa[ks], kb[2], kb[3]);
+          }
+        }
+        dg[kf >> 1][0] = own && ((mw[0][kf] >> r0) & 1u) ? diag_row0(t2[0], g) : -INFINITY;
+        dg[kf >> 1][1] = own && ((mw[1][kf] >> r1) & 1u) ? diag_row1(t2[1], g) : -INFINITY;
+        continue;
+      }
+      float (&sb)[NTF][4] = s[kDiag ? 0 : kf];
+#pragma unroll
+      for (int nt = 0; nt < NTF; ++nt) sb[nt][0] = sb[nt][1] = sb[nt][2] = sb[nt][3] = 0.f;
+      if (!ok) continue;
 #pragma unroll
       for (int np = 0; np < NTF / 2; ++np)
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
           uint32_t kb[4];
-          load_b_nk(kb, sk, np * 16, hh * CH + ks * 2, lane);
-          mma16816(s[kf][2 * np], qa[ks], kb[0], kb[1]);
-          mma16816(s[kf][2 * np + 1], qa[ks], kb[2], kb[3]);
+          load_b_nk(kb, sk, krow + np * 16, hh * CH + ks * 2, lane);
+          mma16816(sb[2 * np], qa[ks], kb[0], kb[1]);
+          mma16816(sb[2 * np + 1], qa[ks], kb[2], kb[3]);
         }
     }
-    // masked softmax over the edges of each row (rows g and g + 8 of the tile)
+    // masked softmax over the edges of each row (rows g and g + 8 of the tile): non-edges become -inf once, so the
+    // exponentials need no second mask test
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-    for (int kf = 0; kf < 3; ++kf)
+    for (int b = 0; b < NB; ++b)
 #pragma unroll
       for (int nt = 0; nt < NTF; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int kp = nt * 8 + qd * 2 + (i & 1);
-          const bool live = (mw[i >> 1][kf] >> kp) & 1u;
-          if (live) { if (i < 2) m0 = fmaxf(m0, s[kf][nt][i]); else m1 = fmaxf(m1, s[kf][nt][i]); }
+          const float v = (mw[i >> 1][kDiag ? 1 : b] >> kp) & 1u ? s[b][nt][i] : -INFINITY;
+          s[b][nt][i] = v;
+          if (i < 2) m0 = fmaxf(m0, v); else m1 = fmaxf(m1, v);
         }
+    if (kDiag) {
+      m0 = fmaxf(m0, fmaxf(dg[0][0], dg[1][0]));
+      m1 = fmaxf(m1, fmaxf(dg[0][1], dg[1][1]));
+    }
     m0 = quad_max(m0); m1 = quad_max(m1);
-    const float mm0 = m0 == -INFINITY ? 0.f : m0, mm1 = m1 == -INFINITY ? 0.f : m1;
+    const float mm0 = m0 == -INFINITY ? 0.f : m0 * sl2, mm1 = m1 == -INFINITY ? 0.f : m1 * sl2;   // log2 units
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-    for (int kf = 0; kf < 3; ++kf)
+    for (int b = 0; b < NB; ++b)
 #pragma unroll
       for (int nt = 0; nt < NTF; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int kp = nt * 8 + qd * 2 + (i & 1);
-          const bool live = (mw[i >> 1][kf] >> kp) & 1u;
-          const float e = live ? exp2f((s[kf][nt][i] - (i < 2 ? mm0 : mm1)) * sl2) : 0.f;
-          s[kf][nt][i] = e;
+          const float e = ex2(fmaf(s[b][nt][i], sl2, -(i < 2 ? mm0 : mm1)));
+          s[b][nt][i] = e;
           if (i < 2) l0 += e; else l1 += e;
         }
+    if (kDiag) {
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        dg[x][0] = ex2(fmaf(dg[x][0], sl2, -mm0));
+        dg[x][1] = ex2(fmaf(dg[x][1], sl2, -mm1));
+        l0 += dg[x][0];
+        l1 += dg[x][1];
+      }
+    }
     l0 = quad_sum(l0); l1 = quad_sum(l1);
 
     float o[CH][4];
@@ -203,91 +274,120 @@ __global__ void __launch_bounds__(kThreads, 2) band_attn_fwd_kernel(const BandAr
     for (int c = 0; c < CH; ++c) o[c][0] = o[c][1] = o[c][2] = o[c][3] = 0.f;
 #pragma unroll
     for (int kf = 0; kf < 3; ++kf) {
-      const int kfr = frame - 1 + kf;
-      if (kfr < 0 || kfr >= p.F) continue;
-      const uint32_t sv = sbase + ((slot - 1 + kf) * 3 + 2) * C::kTensor;
-#pragma unroll
-      for (int np = 0; np < NTF / 2; ++np) {
+      if ((unsigned)(frame - 1 + kf) >= (unsigned)p.F) continue;
+      const int vrow = (slot - 1 + kf) * W;
+      if (kDiag && kf != 1) {
         uint32_t pa[4];
-        pa[0] = pack_bf16(s[kf][2 * np][0], s[kf][2 * np][1]);
-        pa[1] = pack_bf16(s[kf][2 * np][2], s[kf][2 * np][3]);
-        pa[2] = pack_bf16(s[kf][2 * np + 1][0], s[kf][2 * np + 1][1]);
-        pa[3] = pack_bf16(s[kf][2 * np + 1][2], s[kf][2 * np + 1][3]);
+        diag_frag(pa, dg[kf >> 1][0], dg[kf >> 1][1], g);
 #pragma unroll
         for (int hp = 0; hp < CH / 2; ++hp) {
           uint32_t vb[4];
-          load_b_kn(vb, sv, np * 16, hh * CH + hp * 2, lane);
+          load_b_kn(vb, sv, vrow + mt * 16, hh * CH + hp * 2, lane);
+          mma16816(o[2 * hp], pa, vb[0], vb[1]);
+          mma16816(o[2 * hp + 1], pa, vb[2], vb[3]);
+        }
+        continue;
+      }
+      const float (&sb)[NTF][4] = s[kDiag ? 0 : kf];
+#pragma unroll
+      for (int np = 0; np < NTF / 2; ++np) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16(sb[2 * np][0], sb[2 * np][1]);
+        pa[1] = pack_bf16(sb[2 * np][2], sb[2 * np][3]);
+        pa[2] = pack_bf16(sb[2 * np + 1][0], sb[2 * np + 1][1]);
+        pa[3] = pack_bf16(sb[2 * np + 1][2], sb[2 * np + 1][3]);
+#pragma unroll
+        for (int hp = 0; hp < CH / 2; ++hp) {
+          uint32_t vb[4];
+          load_b_kn(vb, sv, vrow + np * 16, hh * CH + hp * 2, lane);
           mma16816(o[2 * hp], pa, vb[0], vb[1]);
           mma16816(o[2 * hp + 1], pa, vb[2], vb[3]);
         }
       }
     }
-    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    const float i0 = l0 > 0.f ? __fdividef(1.f, l0) : 0.f, i1 = l1 > 0.f ? __fdividef(1.f, l1) : 0.f;
     __syncwarp();
     // the head's output replaces its (consumed) q columns in the warp's own rows
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      *reinterpret_cast<uint32_t*>(smem + (slot * 3) * C::kTensor + swz(mt * 16 + g, hh * CH + c) + qd * 4) =
-          pack_bf16(o[c][0] * i0, o[c][1] * i0);
-      *reinterpret_cast<uint32_t*>(smem + (slot * 3) * C::kTensor + swz(mt * 16 + g + 8, hh * CH + c) + qd * 4) =
-          pack_bf16(o[c][2] * i1, o[c][3] * i1);
+      *reinterpret_cast<uint32_t*>(smem + swz(qrow + g, hh * CH + c) + qd * 4) = pack_bf16(o[c][0] * i0, o[c][1] * i0);
+      *reinterpret_cast<uint32_t*>(smem + swz(qrow + g + 8, hh * CH + c) + qd * 4) = pack_bf16(o[c][2] * i1, o[c][3] * i1);
     }
     if (p.lse && qd == 0) {
-      const int head = it.cc * HPC + hh;
-      p.lse[(tok0 + g) * p.heads + head] = l0 > 0.f ? mm0 * p.scale + logf(l0) : 0.f;
-      p.lse[(tok0 + g + 8) * p.heads + head] = l1 > 0.f ? mm1 * p.scale + logf(l1) : 0.f;
+      float* lrow = p.lse + (tok0 + g) * p.heads + it.cc * HPC + hh;       // base-2 logsumexp of the scaled logits
+      lrow[0] = l0 > 0.f ? mm0 + lg2(l0) : 0.f;
+      lrow[8 * p.heads] = l1 > 0.f ? mm1 + lg2(l1) : 0.f;
     }
   }
   __syncwarp();
+  bf16* orow = p.out + tok0 * p.d + it.cc * 64;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int piece = lane + 32 * i, row = piece >> 3, chunk = piece & 7;
-    const int4 v = *reinterpret_cast<const int4*>(smem + (slot * 3) * C::kTensor + swz(mt * 16 + row, chunk));
-    *reinterpret_cast<int4*>(p.out + (tok0 + row) * p.d + it.cc * 64 + chunk * 8) = v;
+    const int4 v = *reinterpret_cast<const int4*>(smem + swz(qrow + row, chunk));
+    *reinterpret_cast<int4*>(orow + row * p.d + chunk * 8) = v;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K16 backward
 // ---------------------------------------------------------------------------------------------------------------------
-template <int W, int HD>
-__global__ void __launch_bounds__(kThreads, 2) band_attn_bwd_kernel(const BandArgs p) {
+template <int W, int HD, bool kDiag>
+__global__ void __launch_bounds__(kThreads, 2)
+band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const BandArgs p) {
   using C = Cfg<W>;
   constexpr int KS = HD / 16, HPC = 64 / HD, CH = HD / 8, NTF = W / 8;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  float* s_lse = reinterpret_cast<float*>(smem + C::NSLOT * 4 * C::kTensor);      // [NSLOT][W][HPC]
-  float* s_delta = s_lse + C::NSLOT * W * HPC;                                      // [NSLOT][W][HPC]
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* s_lse = reinterpret_cast<float*>(smem + 4 * C::kAll);                      // [NSLOT * W][HPC]
+  float* s_delta = s_lse + C::NSLOT * W * HPC;                                      // [NSLOT * W][HPC]
   uint32_t* sbits = reinterpret_cast<uint32_t*>(s_delta + C::NSLOT * W * HPC);     // [W][3]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sbits + W * 3);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Item it = decode_item<W>(p);
   const int d3 = 3 * p.d;
 
-  // stage q, k, v of frames f0-1 .. f0+FR
-  for (int piece = tid; piece < C::NSLOT * 3 * W * 8; piece += kThreads) {
-    const int chunk = piece & 7, row = (piece >> 3) % W, t = (piece / (8 * W)) % 3, slot = piece / (8 * W * 3);
-    const int frame = it.f0 - 1 + slot;
-    const bool valid = frame >= 0 && frame < p.F;
-    const long long token = ((long long)it.b * p.F + (valid ? frame : 0)) * p.K + it.w * W + row;
-    cp_async16(sbase + (slot * 4 + t) * C::kTensor + swz(row, chunk),
-               p.qkv + token * d3 + (size_t)t * p.d + it.cc * 64 + chunk * 8, valid);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
   }
-  // dO through registers: delta[row][head] = sum over the head's columns of dO * O, formed on the way
-  static_assert((Cfg<W>::NSLOT * W * 8) % kThreads == 0, "uniform trip count for the shuffles below");
-  for (int piece = tid; piece < C::NSLOT * W * 8; piece += kThreads) {
-    const int chunk = piece & 7, row = (piece >> 3) % W, slot = piece / (8 * W);
-    const int frame = it.f0 - 1 + slot;
-    const bool valid = frame >= 0 && frame < p.F;
-    const long long token = ((long long)it.b * p.F + (valid ? frame : 0)) * p.K + it.w * W + row;
-    int4 go = make_int4(0, 0, 0, 0), oo = make_int4(0, 0, 0, 0);
-    if (valid) {
-      go = ld_stream16(p.d_out + token * p.d + it.cc * 64 + chunk * 8);
-      oo = ld_stream16(p.ctx + token * p.d + it.cc * 64 + chunk * 8);
-    }
-    *reinterpret_cast<int4*>(smem + (slot * 4 + 3) * C::kTensor + swz(row, chunk)) = go;
+  load_bits<W, kDiag>(sbits, p, it.w, tid);
+  __syncthreads();
+  if (tid == 0) {   // q, k, v, dO of frames f0-1 .. f0+FR
+    mbar_expect_tx(bar, 4 * C::kAll);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) tma_load_4d(smem + t * C::kAll, &tmQKV, bar, t * p.d + it.cc * 64, it.w * W, it.f0 - 1, it.b);
+    tma_load_4d(smem + 3 * C::kAll, &tmDO, bar, it.cc * 64, it.w * W, it.f0 - 1, it.b);
+  }
+  // while the boxes fly: O through registers (delta = rowsum(dO * O) per head) and the saved logsumexp
+  constexpr int kPasses = C::NSLOT * W * 8 / kThreads;
+  static_assert(C::NSLOT * W * 8 % kThreads == 0, "uniform trip count for the shuffles below");
+  const long long tok_base = (long long)it.b * p.F * p.K + it.w * W;      // token (b, frame 0, first keypoint of w)
+  const bf16* oo_base = p.ctx + tok_base * p.d + it.cc * 64;
+  int4 oo[kPasses];
+#pragma unroll
+  for (int ps = 0; ps < kPasses; ++ps) {
+    const int srow = ps * 32 + (tid >> 3), chunk = tid & 7;                // staged row = slot * W + keypoint
+    const int frame = it.f0 - 1 + srow / W;
+    oo[ps] = (unsigned)frame < (unsigned)p.F ? ld_stream16(oo_base + (frame * p.K + srow % W) * p.d + chunk * 8)
+                                             : make_int4(0, 0, 0, 0);
+  }
+  for (int i = tid; i < C::NSLOT * W * HPC; i += kThreads) {
+    const int hh = i % HPC, srow = i / HPC;
+    const int frame = it.f0 - 1 + srow / W;
+    s_lse[i] = (unsigned)frame < (unsigned)p.F
+                   ? p.lse[(tok_base + (long long)frame * p.K + srow % W) * p.heads + it.cc * HPC + hh] : 0.f;
+  }
+  mbar_wait(bar, 0);
+#pragma unroll
+  for (int ps = 0; ps < kPasses; ++ps) {
+    const int srow = ps * 32 + (tid >> 3), chunk = tid & 7;
+    const int4 go = *reinterpret_cast<const int4*>(smem + 3 * C::kAll + swz(srow, chunk));
     const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&go);
-    const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&oo);
+    const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&oo[ps]);
     float dot = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -296,29 +396,21 @@ __global__ void __launch_bounds__(kThreads, 2) band_attn_bwd_kernel(const BandAr
     }
 #pragma unroll
     for (int o = 1; o < CH; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    if (chunk % CH == 0) s_delta[(slot * W + row) * HPC + chunk / CH] = dot;
+    if (chunk % CH == 0) s_delta[srow * HPC + chunk / CH] = dot;
   }
-  for (int i = tid; i < C::NSLOT * W * HPC; i += kThreads) {
-    const int hh = i % HPC, row = (i / HPC) % W, slot = i / (HPC * W);
-    const int frame = it.f0 - 1 + slot;
-    const bool valid = frame >= 0 && frame < p.F;
-    const long long token = ((long long)it.b * p.F + (valid ? frame : 0)) * p.K + it.w * W + row;
-    s_lse[i] = valid ? p.lse[token * p.heads + it.cc * HPC + hh] * kLog2e : 0.f;
-  }
-  for (int i = tid; i < W * 3; i += kThreads) sbits[i] = p.bits[it.w * W * 3 + i];
-  cp_async_wait_all();
   __syncthreads();
 
   const int fi = warp / C::MT, mt = warp % C::MT;
   const int frame = it.f0 + fi;
   const bool active = frame < p.F;
   const int slot = fi + 1, g = lane >> 2, qd = lane & 3;
+  const int own_row = slot * W + mt * 16;                     // first staged row of the warp's 16 tokens
   const float sl2 = p.scale * kLog2e;
+  const uint32_t sq = sbase, sk = sbase + C::kAll, sv = sbase + 2 * C::kAll, sdo = sbase + 3 * C::kAll;
+  const bool own = qd == (g >> 1);
   uint32_t outq[HPC][CH][2], outk[HPC][CH][2], outv[HPC][CH][2];
 
   if (active) {
-    const uint32_t sq = sbase + (slot * 4 + 0) * C::kTensor, sk = sbase + (slot * 4 + 1) * C::kTensor;
-    const uint32_t sv = sbase + (slot * 4 + 2) * C::kTensor, sdo = sbase + (slot * 4 + 3) * C::kTensor;
     const int r0 = mt * 16 + g, r1 = r0 + 8;   // keypoints of the thread's two rows
 #pragma unroll
     for (int hh = 0; hh < HPC; ++hh) {
@@ -327,50 +419,58 @@ __global__ void __launch_bounds__(kThreads, 2) band_attn_bwd_kernel(const BandAr
         uint32_t qa[KS][4], da[KS][4];
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          load_a(qa[ks], sq, mt * 16, hh * CH + ks * 2, lane);
-          load_a(da[ks], sdo, mt * 16, hh * CH + ks * 2, lane);
+          load_a(qa[ks], sq, own_row, hh * CH + ks * 2, lane);
+          load_a(da[ks], sdo, own_row, hh * CH + ks * 2, lane);
         }
-        const float lse0 = s_lse[(slot * W + r0) * HPC + hh], lse1 = s_lse[(slot * W + r1) * HPC + hh];
-        const float dl0 = s_delta[(slot * W + r0) * HPC + hh], dl1 = s_delta[(slot * W + r1) * HPC + hh];
+        const float lse0 = s_lse[(own_row + g) * HPC + hh], lse1 = s_lse[(own_row + g + 8) * HPC + hh];
+        const float dl0 = s_delta[(own_row + g) * HPC + hh], dl1 = s_delta[(own_row + g + 8) * HPC + hh];
         float dq[CH][4];
 #pragma unroll
         for (int c = 0; c < CH; ++c) dq[c][0] = dq[c][1] = dq[c][2] = dq[c][3] = 0.f;
 #pragma unroll
         for (int kf = 0; kf < 3; ++kf) {
-          const int kfr = frame - 1 + kf;
-          if (kfr < 0 || kfr >= p.F) continue;
-          const uint32_t skk = sbase + ((slot - 1 + kf) * 4 + 1) * C::kTensor;
-          const uint32_t svk = sbase + ((slot - 1 + kf) * 4 + 2) * C::kTensor;
+          if ((unsigned)(frame - 1 + kf) >= (unsigned)p.F) continue;
+          const int krow = (slot - 1 + kf) * W;
           const uint32_t w0 = sbits[r0 * 3 + kf], w1 = sbits[r1 * 3 + kf];
+          const bool diag = kDiag && kf != 1;
 #pragma unroll
           for (int np = 0; np < NTF / 2; ++np) {
+            if (diag && np != mt) continue;
             float s[2][4] = {}, dp[2][4] = {};
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
               uint32_t kb[4], vb[4];
-              load_b_nk(kb, skk, np * 16, hh * CH + ks * 2, lane);
-              load_b_nk(vb, svk, np * 16, hh * CH + ks * 2, lane);
+              load_b_nk(kb, sk, krow + np * 16, hh * CH + ks * 2, lane);
+              load_b_nk(vb, sv, krow + np * 16, hh * CH + ks * 2, lane);
               mma16816(s[0], qa[ks], kb[0], kb[1]);
               mma16816(s[1], qa[ks], kb[2], kb[3]);
               mma16816(dp[0], da[ks], vb[0], vb[1]);
               mma16816(dp[1], da[ks], vb[2], vb[3]);
             }
-            float ds[2][4];
+            uint32_t dsa[4];
+            if (diag) {
+              const bool lv0 = own && ((w0 >> r0) & 1u), lv1 = own && ((w1 >> r1) & 1u);
+              const float p0 = ex2(lv0 ? fmaf(diag_row0(s[0], g), sl2, -lse0) : -INFINITY);
+              const float p1 = ex2(lv1 ? fmaf(diag_row1(s[1], g), sl2, -lse1) : -INFINITY);
+              diag_frag(dsa, p0 * (diag_row0(dp[0], g) - dl0), p1 * (diag_row1(dp[1], g) - dl1), g);
+            } else {
+              float ds[2][4];
 #pragma unroll
-            for (int t = 0; t < 2; ++t)
+              for (int t = 0; t < 2; ++t)
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int kp = np * 16 + t * 8 + qd * 2 + (i & 1);
-                const bool live = ((i < 2 ? w0 : w1) >> kp) & 1u;
-                const float pr = live ? exp2f(s[t][i] * sl2 - (i < 2 ? lse0 : lse1)) : 0.f;
-                ds[t][i] = pr * (dp[t][i] - (i < 2 ? dl0 : dl1));
-              }
-            uint32_t dsa[4] = {pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]),
-                               pack_bf16(ds[1][0], ds[1][1]), pack_bf16(ds[1][2], ds[1][3])};
+                for (int i = 0; i < 4; ++i) {
+                  const int kp = np * 16 + t * 8 + qd * 2 + (i & 1);
+                  const bool live = ((i < 2 ? w0 : w1) >> kp) & 1u;
+                  const float pr = ex2(live ? fmaf(s[t][i], sl2, -(i < 2 ? lse0 : lse1)) : -INFINITY);
+                  ds[t][i] = pr * (dp[t][i] - (i < 2 ? dl0 : dl1));
+                }
+              dsa[0] = pack_bf16(ds[0][0], ds[0][1]); dsa[1] = pack_bf16(ds[0][2], ds[0][3]);
+              dsa[2] = pack_bf16(ds[1][0], ds[1][1]); dsa[3] = pack_bf16(ds[1][2], ds[1][3]);
+            }
 #pragma unroll
             for (int hp = 0; hp < CH / 2; ++hp) {
               uint32_t kb[4];
-              load_b_kn(kb, skk, np * 16, hh * CH + hp * 2, lane);
+              load_b_kn(kb, sk, krow + np * 16, hh * CH + hp * 2, lane);
               mma16816(dq[2 * hp], dsa, kb[0], kb[1]);
               mma16816(dq[2 * hp + 1], dsa, kb[2], kb[3]);
             }
@@ -387,8 +487,8 @@ __global__ void __launch_bounds__(kThreads, 2) band_attn_bwd_kernel(const BandAr
         uint32_t ka[KS][4], va[KS][4];
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          load_a(ka[ks], sk, mt * 16, hh * CH + ks * 2, lane);
-          load_a(va[ks], sv, mt * 16, hh * CH + ks * 2, lane);
+          load_a(ka[ks], sk, own_row, hh * CH + ks * 2, lane);
+          load_a(va[ks], sv, own_row, hh * CH + ks * 2, lane);
         }
         float dk[CH][4], dv[CH][4];
 #pragma unroll
@@ -398,44 +498,54 @@ __global__ void __launch_bounds__(kThreads, 2) band_attn_bwd_kernel(const BandAr
         }
 #pragma unroll
         for (int qo = 0; qo < 3; ++qo) {
-          const int qfr = frame - 1 + qo;
-          if (qfr < 0 || qfr >= p.F) continue;
-          const int qslot = slot - 1 + qo, kfrel = 2 - qo;   // this warp's frame seen from the query frame
-          const uint32_t sqq = sbase + (qslot * 4 + 0) * C::kTensor, sdq = sbase + (qslot * 4 + 3) * C::kTensor;
+          if ((unsigned)(frame - 1 + qo) >= (unsigned)p.F) continue;
+          const int qrow = (slot - 1 + qo) * W, kfrel = 2 - qo;   // this warp's frame seen from the query frame
+          const bool diag = kDiag && qo != 1;
 #pragma unroll
           for (int np = 0; np < NTF / 2; ++np) {
+            if (diag && np != mt) continue;
             float s[2][4] = {}, dp[2][4] = {};
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
               uint32_t qb[4], gb[4];
-              load_b_nk(qb, sqq, np * 16, hh * CH + ks * 2, lane);
-              load_b_nk(gb, sdq, np * 16, hh * CH + ks * 2, lane);
+              load_b_nk(qb, sq, qrow + np * 16, hh * CH + ks * 2, lane);
+              load_b_nk(gb, sdo, qrow + np * 16, hh * CH + ks * 2, lane);
               mma16816(s[0], ka[ks], qb[0], qb[1]);
               mma16816(s[1], ka[ks], qb[2], qb[3]);
               mma16816(dp[0], va[ks], gb[0], gb[1]);
               mma16816(dp[1], va[ks], gb[2], gb[3]);
             }
-            float pt[2][4], ds[2][4];
+            uint32_t pa[4], dsa[4];
+            if (diag) {   // query keypoint == key keypoint: the thread's own two rows
+              const bool lv0 = own && ((sbits[r0 * 3 + kfrel] >> r0) & 1u), lv1 = own && ((sbits[r1 * 3 + kfrel] >> r1) & 1u);
+              const float p0 = ex2(lv0 ? fmaf(diag_row0(s[0], g), sl2, -s_lse[(qrow + r0) * HPC + hh]) : -INFINITY);
+              const float p1 = ex2(lv1 ? fmaf(diag_row1(s[1], g), sl2, -s_lse[(qrow + r1) * HPC + hh]) : -INFINITY);
+              diag_frag(pa, p0, p1, g);
+              diag_frag(dsa, p0 * (diag_row0(dp[0], g) - s_delta[(qrow + r0) * HPC + hh]),
+                        p1 * (diag_row1(dp[1], g) - s_delta[(qrow + r1) * HPC + hh]), g);
+            } else {
+              float pt[2][4], ds[2][4];
 #pragma unroll
-            for (int t = 0; t < 2; ++t)
+              for (int t = 0; t < 2; ++t)
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int qc = np * 16 + t * 8 + qd * 2 + (i & 1);          // query keypoint (column)
-                const bool live = (sbits[qc * 3 + kfrel] >> (i < 2 ? r0 : r1)) & 1u;
-                const float lq = s_lse[(qslot * W + qc) * HPC + hh], dq_ = s_delta[(qslot * W + qc) * HPC + hh];
-                const float pr = live ? exp2f(s[t][i] * sl2 - lq) : 0.f;
-                pt[t][i] = pr;
-                ds[t][i] = pr * (dp[t][i] - dq_);
-              }
-            uint32_t pa[4] = {pack_bf16(pt[0][0], pt[0][1]), pack_bf16(pt[0][2], pt[0][3]),
-                              pack_bf16(pt[1][0], pt[1][1]), pack_bf16(pt[1][2], pt[1][3])};
-            uint32_t dsa[4] = {pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]),
-                               pack_bf16(ds[1][0], ds[1][1]), pack_bf16(ds[1][2], ds[1][3])};
+                for (int i = 0; i < 4; ++i) {
+                  const int qc = np * 16 + t * 8 + qd * 2 + (i & 1);          // query keypoint (column)
+                  const bool live = (sbits[qc * 3 + kfrel] >> (i < 2 ? r0 : r1)) & 1u;
+                  const float lq = s_lse[(qrow + qc) * HPC + hh], dq_ = s_delta[(qrow + qc) * HPC + hh];
+                  const float pr = ex2(live ? fmaf(s[t][i], sl2, -lq) : -INFINITY);
+                  pt[t][i] = pr;
+                  ds[t][i] = pr * (dp[t][i] - dq_);
+                }
+              pa[0] = pack_bf16(pt[0][0], pt[0][1]); pa[1] = pack_bf16(pt[0][2], pt[0][3]);
+              pa[2] = pack_bf16(pt[1][0], pt[1][1]); pa[3] = pack_bf16(pt[1][2], pt[1][3]);
+              dsa[0] = pack_bf16(ds[0][0], ds[0][1]); dsa[1] = pack_bf16(ds[0][2], ds[0][3]);
+              dsa[2] = pack_bf16(ds[1][0], ds[1][1]); dsa[3] = pack_bf16(ds[1][2], ds[1][3]);
+            }
 #pragma unroll
             for (int hp = 0; hp < CH / 2; ++hp) {
               uint32_t gb[4], qb[4];
-              load_b_kn(gb, sdq, np * 16, hh * CH + hp * 2, lane);
-              load_b_kn(qb, sqq, np * 16, hh * CH + hp * 2, lane);
+              load_b_kn(gb, sdo, qrow + np * 16, hh * CH + hp * 2, lane);
+              load_b_kn(qb, sq, qrow + np * 16, hh * CH + hp * 2, lane);
               mma16816(dv[2 * hp], pa, gb[0], gb[1]);
               mma16816(dv[2 * hp + 1], pa, gb[2], gb[3]);
               mma16816(dk[2 * hp], dsa, qb[0], qb[1]);
@@ -459,57 +569,67 @@ __global__ void __launch_bounds__(kThreads, 2) band_attn_bwd_kernel(const BandAr
   for (int hh = 0; hh < HPC; ++hh)
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      const uint32_t o0 = swz(mt * 16 + g, hh * CH + c) + qd * 4, o1 = swz(mt * 16 + g + 8, hh * CH + c) + qd * 4;
-      *reinterpret_cast<uint32_t*>(smem + (slot * 4 + 0) * C::kTensor + o0) = outq[hh][c][0];
-      *reinterpret_cast<uint32_t*>(smem + (slot * 4 + 0) * C::kTensor + o1) = outq[hh][c][1];
-      *reinterpret_cast<uint32_t*>(smem + (slot * 4 + 1) * C::kTensor + o0) = outk[hh][c][0];
-      *reinterpret_cast<uint32_t*>(smem + (slot * 4 + 1) * C::kTensor + o1) = outk[hh][c][1];
-      *reinterpret_cast<uint32_t*>(smem + (slot * 4 + 2) * C::kTensor + o0) = outv[hh][c][0];
-      *reinterpret_cast<uint32_t*>(smem + (slot * 4 + 2) * C::kTensor + o1) = outv[hh][c][1];
+      const uint32_t o0 = swz(own_row + g, hh * CH + c) + qd * 4, o1 = swz(own_row + g + 8, hh * CH + c) + qd * 4;
+      *reinterpret_cast<uint32_t*>(smem + o0) = outq[hh][c][0];
+      *reinterpret_cast<uint32_t*>(smem + o1) = outq[hh][c][1];
+      *reinterpret_cast<uint32_t*>(smem + C::kAll + o0) = outk[hh][c][0];
+      *reinterpret_cast<uint32_t*>(smem + C::kAll + o1) = outk[hh][c][1];
+      *reinterpret_cast<uint32_t*>(smem + 2 * C::kAll + o0) = outv[hh][c][0];
+      *reinterpret_cast<uint32_t*>(smem + 2 * C::kAll + o1) = outv[hh][c][1];
     }
   __syncwarp();
-  const long long tok0 = ((long long)it.b * p.F + frame) * p.K + it.w * W + mt * 16;
+  bf16* orow = p.dqkv + (((long long)it.b * p.F + frame) * p.K + it.w * W + mt * 16) * d3 + it.cc * 64;
 #pragma unroll
   for (int t = 0; t < 3; ++t)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int piece = lane + 32 * i, row = piece >> 3, chunk = piece & 7;
-      const int4 v = *reinterpret_cast<const int4*>(smem + (slot * 4 + t) * C::kTensor + swz(mt * 16 + row, chunk));
-      *reinterpret_cast<int4*>(p.dqkv + (tok0 + row) * d3 + (size_t)t * p.d + it.cc * 64 + chunk * 8) = v;
+      const int4 v = *reinterpret_cast<const int4*>(smem + t * C::kAll + swz(own_row + row, chunk));
+      *reinterpret_cast<int4*>(orow + row * d3 + t * p.d + chunk * 8) = v;
     }
 }
 
-template <int W, int HD>
-static int launch_fwd(const BandArgs& p, cudaStream_t s) {
+template <int W, int HD, bool kDiag>
+static int launch_fwd(const BandArgs& p, const bf16* qkv, cudaStream_t s) {
   using C = Cfg<W>;
-  constexpr int smem = C::NSLOT * 3 * C::kTensor + W * 3 * 4 + 128;
+  constexpr int smem = 3 * C::kAll + W * 3 * 4 + 16 + 1024;
   static PerDeviceOnce once;
-  once.run([] { cudaFuncSetAttribute(band_attn_fwd_kernel<W, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+  once.run([] { cudaFuncSetAttribute(band_attn_fwd_kernel<W, HD, kDiag>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
   const long long grid = (long long)p.B * (p.K / W) * (p.d / 64) * ((p.F + C::FR - 1) / C::FR);
   if (grid > 0x7fffffffLL) return HWGAT_ERR_UNSUPPORTED;
-  band_attn_fwd_kernel<W, HD><<<(unsigned)grid, kThreads, smem, s>>>(p);
+  CUtensorMap tm;
+  int st;
+  if ((st = make_tmap_4d(&tm, qkv, (uint64_t)3 * p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
+  band_attn_fwd_kernel<W, HD, kDiag><<<(unsigned)grid, kThreads, smem, s>>>(tm, p);
   count_launch();
   return (int)cudaGetLastError();
 }
-template <int W, int HD>
-static int launch_bwd(const BandArgs& p, cudaStream_t s) {
+template <int W, int HD, bool kDiag>
+static int launch_bwd(const BandArgs& p, const bf16* qkv, const bf16* d_out, cudaStream_t s) {
   using C = Cfg<W>;
   constexpr int HPC = 64 / HD;
-  constexpr int smem = C::NSLOT * 4 * C::kTensor + 2 * C::NSLOT * W * HPC * 4 + W * 3 * 4 + 128;
+  constexpr int smem = 4 * C::kAll + 2 * C::NSLOT * W * HPC * 4 + W * 3 * 4 + 16 + 1024;
   static PerDeviceOnce once;
-  once.run([] { cudaFuncSetAttribute(band_attn_bwd_kernel<W, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+  once.run([] { cudaFuncSetAttribute(band_attn_bwd_kernel<W, HD, kDiag>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
   const long long grid = (long long)p.B * (p.K / W) * (p.d / 64) * ((p.F + C::FR - 1) / C::FR);
   if (grid > 0x7fffffffLL) return HWGAT_ERR_UNSUPPORTED;
-  band_attn_bwd_kernel<W, HD><<<(unsigned)grid, kThreads, smem, s>>>(p);
+  CUtensorMap tm, tmdo;
+  int st;
+  if ((st = make_tmap_4d(&tm, qkv, (uint64_t)3 * p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
+  if ((st = make_tmap_4d(&tmdo, d_out, (uint64_t)p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
+  band_attn_bwd_kernel<W, HD, kDiag><<<(unsigned)grid, kThreads, smem, s>>>(tm, tmdo, p);
   count_launch();
   return (int)cudaGetLastError();
 }
 
 template <bool kBwd>
-static int dispatch(const BandArgs& p, int W, cudaStream_t s) {
+static int dispatch(const BandArgs& p, const bf16* qkv, const bf16* d_out, int W, bool diag, cudaStream_t s) {
   const int hd = p.d / p.heads;
-#define BAND_CASE(WW, HH) \
-  if (W == WW && hd == HH) return kBwd ? launch_bwd<WW, HH>(p, s) : launch_fwd<WW, HH>(p, s);
+#define BAND_CASE(WW, HH)                                                                                  \
+  if (W == WW && hd == HH) {                                                                               \
+    if (diag) return kBwd ? launch_bwd<WW, HH, true>(p, qkv, d_out, s) : launch_fwd<WW, HH, true>(p, qkv, s);   \
+    return kBwd ? launch_bwd<WW, HH, false>(p, qkv, d_out, s) : launch_fwd<WW, HH, false>(p, qkv, s);           \
+  }
   BAND_CASE(16, 16) BAND_CASE(16, 32) BAND_CASE(16, 64) BAND_CASE(32, 16) BAND_CASE(32, 32) BAND_CASE(32, 64)
 #undef BAND_CASE
   return HWGAT_ERR_UNSUPPORTED;
@@ -535,29 +655,29 @@ size_t band_attn_workspace_bytes(long long n, int d, int backward) {
 
 // forward: qkv (caller's buffer, kept for the backward) = xn . Wqkv^T + b ; out = banded attention ; lse optional
 int band_attn_fwd(const bf16* xn, const bf16* w_qkv, const float* b_qkv, const uint32_t* bits, bf16* out, bf16* qkv,
-                  float* lse, int B, int F, int K, int d, int heads, int W, cudaStream_t s) {
+                  float* lse, int B, int F, int K, int d, int heads, int W, int diag, cudaStream_t s) {
   const long long n = (long long)B * F * K;
   int st;
   if ((st = gemm_tc_nt_epi_bias(xn, w_qkv, b_qkv, qkv, n, 3 * d, d, s))) return st;
   band::BandArgs p{};
-  p.qkv = qkv; p.bits = bits; p.out = out; p.lse = lse;
+  p.bits = bits; p.out = out; p.lse = lse;
   p.B = B; p.F = F; p.K = K; p.d = d; p.heads = heads; p.scale = 1.0f / sqrtf((float)(d / heads));
-  return band::dispatch<false>(p, W, s);
+  return band::dispatch<false>(p, qkv, nullptr, W, diag != 0, s);
 }
 
 // backward: dqkv (workspace) from the core, then d_xn = dqkv . Wqkv, d_w = dqkv^T . xn, d_b = column sums of dqkv
 int band_attn_bwd(const bf16* xn, const bf16* w_qkv, const uint32_t* bits, const bf16* qkv, const bf16* ctx,
                   const float* lse, const bf16* d_out, bf16* d_xn, float* d_w, float* d_b, void* workspace, int B, int F,
-                  int K, int d, int heads, int W, cudaStream_t s) {
+                  int K, int d, int heads, int W, int diag, cudaStream_t s) {
   const long long n = (long long)B * F * K;
   const int d3 = 3 * d;
   bf16* dqkv = (bf16*)workspace;
   bf16* wt = dqkv + (size_t)n * d3;
   band::BandArgs p{};
-  p.qkv = qkv; p.bits = bits; p.lse = const_cast<float*>(lse); p.d_out = d_out; p.ctx = ctx; p.dqkv = dqkv;
+  p.bits = bits; p.lse = const_cast<float*>(lse); p.ctx = ctx; p.dqkv = dqkv;
   p.B = B; p.F = F; p.K = K; p.d = d; p.heads = heads; p.scale = 1.0f / sqrtf((float)(d / heads));
   int st;
-  if ((st = band::dispatch<true>(p, W, s))) return st;
+  if ((st = band::dispatch<true>(p, qkv, d_out, W, diag != 0, s))) return st;
   if ((st = transpose_bf16(w_qkv, wt, d3, d, s))) return st;
   if ((st = gemm_tc_nt_epi_none(dqkv, wt, d_xn, n, d, d3, s))) return st;
   return gemm_tc_tn(dqkv, xn, d_w, d_b, d3, d, n, s);

@@ -202,10 +202,11 @@ bool band_attn_supported(int B, int F, int K, int d, int heads, int W);
 size_t band_attn_workspace_bytes(long long n, int d, int backward);
 int band_attn_fwd(const __nv_bfloat16* xn, const __nv_bfloat16* w_qkv, const float* b_qkv, const uint32_t* bits,
                   __nv_bfloat16* out, __nv_bfloat16* qkv, float* lse, int B, int F, int K, int d, int heads, int W,
-                  cudaStream_t s);
+                  int diag, cudaStream_t s);
 int band_attn_bwd(const __nv_bfloat16* xn, const __nv_bfloat16* w_qkv, const uint32_t* bits, const __nv_bfloat16* qkv,
                   const __nv_bfloat16* ctx, const float* lse, const __nv_bfloat16* d_out, __nv_bfloat16* d_xn,
-                  float* d_w, float* d_b, void* workspace, int B, int F, int K, int d, int heads, int W, cudaStream_t s);
+                  float* d_w, float* d_b, void* workspace, int B, int F, int K, int d, int heads, int W, int diag,
+                  cudaStream_t s);
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t s);
 int attn_bwd_tc(const AttnArgs& a, __nv_bfloat16* dqkv, cudaStream_t s);
 int gemm_tc_tn(const __nv_bfloat16* A, const __nv_bfloat16* Bm, float* C, float* colsum, int M, int N, long long Kd,

@@ -379,15 +379,19 @@ def band_mask_pack(adj_mask: torch.Tensor, frames: int, window: int) -> torch.Te
     out = torch.zeros(nW, window, 3, dtype=torch.int64, device=m.device)
     out[:, :kw] = words
     # uint32 payload in an int32 tensor (bit 31 = keypoint 31)
-    out = torch.where(out >= 2 ** 31, out - 2 ** 32, out).to(torch.int32)
-    return out.contiguous()
+    out = torch.where(out >= 2 ** 31, out - 2 ** 32, out).to(torch.int32).contiguous()
+    # the blocks between adjacent frames are (a subset of) the identity in every graph the reference builds: K15 / K16
+    # then evaluate only their diagonal (`diag` of hwgat_band_attn_fwd); one host read at set-up, cached by the callers
+    row_bit = weights[None, :, None]
+    out.band_diag = bool(((words[:, :, (0, 2)] & ~row_bit) == 0).all().item())
+    return out
 
 
 class _BandGraphAttention(torch.autograd.Function):
     """QKV projection (tcgen05 GEMM) + frame-banded graph attention (K15) ; backward K16 + the three GEMMs."""
 
     @staticmethod
-    def forward(ctx, xn, w_qkv, b_qkv, bits, heads, window):
+    def forward(ctx, xn, w_qkv, b_qkv, bits, heads, window, diag):
         lib = _lib.load()
         _need_cuda(xn, w_qkv, b_qkv, bits)
         if xn.dtype != torch.bfloat16 or xn.dim() != 4:
@@ -406,17 +410,17 @@ class _BandGraphAttention(torch.autograd.Function):
         with torch.cuda.device(xn_c.device):
             check(lib.hwgat_band_attn_fwd(xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
                                           out.data_ptr(), qkv.data_ptr(), _ptr(lse), B, F, K, d, heads, window,
-                                          _stream()), "hwgat_band_attn_fwd")
+                                          int(diag), _stream()), "hwgat_band_attn_fwd")
         if need:
             ctx.save_for_backward(xn_c, w_c, bits, qkv, out, lse)
-        ctx.meta = (heads, window, w_qkv.dtype, b_qkv.dtype)
+        ctx.meta = (heads, window, w_qkv.dtype, b_qkv.dtype, int(diag))
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         lib = _lib.load()
         xn_c, w_c, bits, qkv, out, lse = ctx.saved_tensors
-        heads, window, w_dtype, b_dtype = ctx.meta
+        heads, window, w_dtype, b_dtype, diag = ctx.meta
         B, F, K, d = xn_c.shape
         g = d_out.to(torch.bfloat16).contiguous()
         d_xn = torch.empty_like(xn_c)
@@ -427,9 +431,9 @@ class _BandGraphAttention(torch.autograd.Function):
         with torch.cuda.device(xn_c.device):
             check(lib.hwgat_band_attn_bwd(g.data_ptr(), xn_c.data_ptr(), w_c.data_ptr(), qkv.data_ptr(), out.data_ptr(),
                                           lse.data_ptr(), bits.data_ptr(), d_xn.data_ptr(), d_w.data_ptr(),
-                                          d_b.data_ptr(), ws.data_ptr(), ws.numel(), B, F, K, d, heads, window,
+                                          d_b.data_ptr(), ws.data_ptr(), ws.numel(), B, F, K, d, heads, window, diag,
                                           _stream()), "hwgat_band_attn_bwd")
-        return d_xn, d_w.to(w_dtype), d_b.to(b_dtype), None, None, None
+        return d_xn, d_w.to(w_dtype), d_b.to(b_dtype), None, None, None, None
 
 
 def band_attention_supported(B: int, F: int, K: int, d: int, heads: int, window: int) -> bool:
@@ -438,12 +442,15 @@ def band_attention_supported(B: int, F: int, K: int, d: int, heads: int, window:
 
 
 def band_graph_attention(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, bits: torch.Tensor, heads: int,
-                         window: int) -> torch.Tensor:
+                         window: int, diag: Optional[bool] = None) -> torch.Tensor:
     """window_partition + QKV + additive-masked attention over all frames + window_reverse of WGATE
     (WGATE.py:150-158, 87-106) / the masked full attention of GATE (GATE.py:49-66), without the output projection, on
     the (B, F, K, d) bf16 stream.  bits: band_mask_pack(...).  The attention evaluates the graph's frame band only
-    (see band_mask_pack for why that equals the reference's dense softmax)."""
-    return _BandGraphAttention.apply(xn, w_qkv, b_qkv, bits, heads, window)
+    (see band_mask_pack for why that equals the reference's dense softmax).  diag: the off-frame blocks are the
+    identity (None: what band_mask_pack found; False forces the general path)."""
+    if diag is None:
+        diag = getattr(bits, "band_diag", False)
+    return _BandGraphAttention.apply(xn, w_qkv, b_qkv, bits, heads, window, bool(diag))
 
 
 # --------------------------------------------------------------------------

@@ -126,6 +126,89 @@ def test_band_attention_frame_edges_and_ragged_chunks(name, F, B):
     assert max(errs) < BF16_TOL, errs
 
 
+@pytest.mark.parametrize("W,K,hd", [(16, 64, 16), (32, 32, 16), (16, 32, 64), (32, 64, 32)])
+def test_band_attention_general_band_and_forced_general_path(W, K, hd):
+    """(1) An adjacency whose blocks between adjacent frames are NOT the identity (a shifted identity plus random
+    links) - the kernels' general path - against the dense additive-mask oracle.  (2) A graph with the identity
+    between frames: the diagonal fast path gives the same result as the general path forced on it."""
+    from sl_hwgat_b200 import ops
+    F, B, heads = 5, 4, 128 // hd
+    d = heads * hd
+    rng = np.random.default_rng(77 + W + hd)
+    same = np.eye(W)
+    for i, j in [(0, 1), (0, 2), (1, 5), (3, 4), (4, 9), (7, W - 1), (W - 2, W - 1)]:
+        same[i, j] = same[j, i] = 1
+    nxt = np.roll(np.eye(W), 1, axis=1) + (rng.random((W, W)) < 0.1)            # to the next frame: not the identity
+    prv = np.eye(W) * (np.arange(W) % 3 != 0)[:, None] + (rng.random((W, W)) < 0.1)
+    fr = np.arange(F)
+    dt = fr[None, :] - fr[:, None]                                               # key frame - query frame
+
+    def band(nx, pv):
+        blocks = (np.where((dt == 0)[:, None, :, None], same[None, :, None, :], 0) +
+                  np.where((dt == 1)[:, None, :, None], nx[None, :, None, :], 0) +
+                  np.where((dt == -1)[:, None, :, None], pv[None, :, None, :], 0))
+        return (blocks.reshape(F * W, F * W) != 0).astype(np.float64)
+    nW = K // W
+    mask = WG.additive_mask(np.stack([band(nxt, prv)] * nW))
+    bits = ops.band_mask_pack(torch.from_numpy(mask).float().cuda(), F, W)
+    assert bits.band_diag is False
+    xn = torch.from_numpy(rng.standard_normal((B, F, K, d)))
+    w = torch.from_numpy(rng.standard_normal((3 * d, d)) * 0.2)
+    b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1)
+    g = torch.from_numpy(rng.standard_normal((B, F, K, d)))
+
+    def run(bits_, diag=None):
+        x_ = xn.float().cuda().requires_grad_(True)
+        w_ = w.float().cuda().requires_grad_(True)
+        b_ = b.float().cuda().requires_grad_(True)
+        y = ops.band_graph_attention(x_.to(torch.bfloat16), w_, b_, bits_, heads, W, diag)
+        (y.float() * g.float().cuda()).sum().backward()
+        return [t.detach().double().cpu() for t in (y, x_.grad, w_.grad, b_.grad)]
+
+    got = run(bits)
+    rb = lambda t: t.float().bfloat16().double()
+    x_, w_, b_ = rb(xn).requires_grad_(True), rb(w).requires_grad_(True), b.float().double().requires_grad_(True)
+    ref = WG.wgate_attention_core(x_, w_, b_, heads, mask, W)
+    (ref * g.float().double()).sum().backward()
+    errs = [rel_l2(a, r) for a, r in zip(got, (ref.detach(), x_.grad, w_.grad, b_.grad))]
+    assert max(errs) < BF16_TOL, errs
+    # (2) identity between frames: fast path == general path (the same fp32 values on the live entries)
+    bits_i = ops.band_mask_pack(torch.from_numpy(WG.additive_mask(np.stack([band(np.eye(W), np.eye(W))] * nW))).float().cuda(), F, W)
+    assert bits_i.band_diag is True
+    fast, general = run(bits_i), run(bits_i, diag=False)
+    for a, c in zip(fast, general):
+        assert rel_l2(a, c) < 2e-3          # identical up to the summation order inside the MMAs / bf16 rounding
+
+
+def test_band_diag_promise_is_checked_on_the_device():
+    """diag = 1 with words that are not diagonal must not silently compute something else: the CTAs trap."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import torch, numpy as np, sys
+        sys.path.insert(0, %r)
+        from sl_hwgat_b200 import ops
+        from oracle import wgate_oracle as WG
+        F, W = 4, 16
+        adj = WG.wgate_adjacency(WG.WGATEConfig().edges, F, W)
+        for f in range(1, F):                     # keypoint 3 also sees keypoint 5 of the previous frame, in every frame
+            adj[:, f * W + 3, (f - 1) * W + 5] = 1
+        bits = ops.band_mask_pack(torch.from_numpy(WG.additive_mask(adj)).float().cuda(), F, W)
+        assert bits.band_diag is False
+        x = torch.randn(2, F, 64, 128, device="cuda", dtype=torch.bfloat16)
+        w = torch.randn(384, 128, device="cuda") * 0.1
+        b = torch.zeros(384, device="cuda")
+        try:
+            ops.band_graph_attention(x, w, b, bits, 8, W, diag=True)
+            torch.cuda.synchronize()
+        except Exception as e:
+            print("TRAPPED", type(e).__name__)
+            sys.exit(0)
+        print("NO TRAP")
+    """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "TRAPPED" in r.stdout, (r.stdout, r.stderr[-500:])
+
+
 @pytest.mark.parametrize("name", ["wgate", "gate"])
 def test_band_model_params_and_state_dict_match_reference(golden_dir, name):
     G = np.load(os.path.join(golden_dir, "wgate_gate.npz"))
