@@ -362,3 +362,22 @@ def test_weighted_pool_vs_torch_fp32():
     for a, b_ in zip(got, want):
         assert rel_l2(a.double(), b_) < 1e-5
     assert float(xr.grad[:, :, K:].abs().max()) == 0.0           # padded rows get no gradient
+
+
+@pytest.mark.parametrize("name", ["wgate", "gate"])
+def test_band_models_cuda_graph_inference(name):
+    """the per-sample evaluator (inference.py:88-95) through runtime.GraphedInference: replays equal the eager forward"""
+    from sl_hwgat_b200.runtime import GraphedInference
+    K = 64 if name == "wgate" else 29
+    m, cfg, sd, p = build(name, 16, classes=50, depths=2)
+    m.eval()
+    fast = GraphedInference(m)
+    for B in (4, 8):
+        x = WG.synthetic_keypoints(B, 16, K, seed=B).cuda()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            want = m(x)
+        assert torch.equal(fast(x), want)
+        x2 = WG.synthetic_keypoints(B, 16, K, seed=B + 100).cuda()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            want2 = m(x2)
+        assert torch.equal(fast(x2), want2) and not torch.equal(want, want2)
