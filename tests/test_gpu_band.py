@@ -381,3 +381,34 @@ def test_band_models_cuda_graph_inference(name):
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             want2 = m(x2)
         assert torch.equal(fast(x2), want2) and not torch.equal(want, want2)
+
+
+@pytest.mark.parametrize("name", ["wgate", "gate"])
+def test_band_attention_full_size_replication(name):
+    """The bench shape (B = 512, T = 64: 32768 CTAs per launch) through a size-independent property: every sample is the
+    same sequence, so every sample's output and input gradient must equal sample 0's bit for bit, sample 0 must match the
+    dense oracle, and the weight gradient must be 512 x the one-sample gradient."""
+    from sl_hwgat_b200 import ops
+    from sl_hwgat_b200.models.HGATE import _pad_kp
+    B, F, d, h = 512, 64, 128, 8
+    K, W = (64, 16) if name == "wgate" else (29, 32)
+    rng = np.random.default_rng(11)
+    x1 = torch.from_numpy(rng.standard_normal((1, F, K, d))).float()
+    g1 = torch.from_numpy(rng.standard_normal((1, F, K, d))).float()
+    w = torch.from_numpy(rng.standard_normal((3 * d, d)) * 0.2).float()
+    b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1).float()
+    mask = dense_mask(name, F)
+    bits = ops.band_mask_pack(torch.from_numpy(mask).float().cuda(), F, W)
+    xp = _pad_kp(x1, 2) if name == "gate" else x1
+    gp = _pad_kp(g1, 2) if name == "gate" else g1
+    x_ = xp.cuda().to(torch.bfloat16).expand(B, -1, -1, -1).contiguous().requires_grad_(True)
+    w_, b_ = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = ops.band_graph_attention(x_, w_, b_, bits, h, W)
+    y.backward(gp.cuda().to(torch.bfloat16).expand(B, -1, -1, -1).contiguous())
+    assert torch.equal(y, y[:1].expand_as(y)) and torch.equal(x_.grad, x_.grad[:1].expand_as(x_.grad))
+    rb = lambda t: t.bfloat16().double()
+    xr, wr, br = rb(x1).cuda().requires_grad_(True), rb(w).cuda().requires_grad_(True), b.double().cuda().requires_grad_(True)
+    ref = (WG.wgate_attention_core(xr, wr, br, h, mask, 16) if name == "wgate" else WG.gate_attention_core(xr, wr, br, h, mask))
+    (ref * rb(g1).cuda()).sum().backward()
+    assert rel_l2(y[0, :, :K], ref[0]) < BF16_TOL and rel_l2(x_.grad[0, :, :K], xr.grad[0]) < BF16_TOL
+    assert rel_l2(w_.grad / B, wr.grad) < BF16_TOL and rel_l2(b_.grad / B, br.grad) < BF16_TOL
