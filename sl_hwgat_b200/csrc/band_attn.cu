@@ -50,6 +50,7 @@ struct BandArgs {
   bf16* dqkv;            // bwd: [n, 3d]
   int B, F, K, d, heads;
   float scale;
+  int pf_dist;           // L2 prefetch distance in work items (0 = off): the items of the next wave of CTAs
 };
 
 template <int W>
@@ -104,10 +105,9 @@ struct Item {
   int b, w, f0, cc;
 };
 template <int W>
-HW_DEV Item decode_item(const BandArgs& p) {
+HW_DEV Item decode_item(const BandArgs& p, int i) {
   using C = Cfg<W>;
   const int nchunks = (p.F + C::FR - 1) / C::FR, ncc = p.d / 64, nW = p.K / W;
-  int i = blockIdx.x;
   Item it;
   it.f0 = (i % nchunks) * C::FR; i /= nchunks;
   it.cc = i % ncc; i /= ncc;
@@ -152,7 +152,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const BandArgs p
   uint64_t* bar = reinterpret_cast<uint64_t*>(sbits + W * 3);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const Item it = decode_item<W>(p);
+  const Item it = decode_item<W>(p, blockIdx.x);
 
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -165,6 +165,13 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const BandArgs p
     mbar_expect_tx(bar, 3 * C::kAll);
 #pragma unroll
     for (int t = 0; t < 3; ++t) tma_load_4d(smem + t * C::kAll, &tmQKV, bar, t * p.d + it.cc * 64, it.w * W, it.f0 - 1, it.b);
+    // Pull the boxes of the item a CTA of the NEXT wave will work on into L2: with 2 - 3 resident CTAs per SM the
+    // load phase that opens an item is exposed latency, and an L2 hit shortens it.
+    if (p.pf_dist > 0 && blockIdx.x + p.pf_dist < gridDim.x) {
+      const Item nx = decode_item<W>(p, blockIdx.x + p.pf_dist);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) tma_prefetch_4d(&tmQKV, t * p.d + nx.cc * 64, nx.w * W, nx.f0 - 1, nx.b);
+    }
   }
   mbar_wait(bar, 0);
 
@@ -334,7 +341,8 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const BandArgs p
 // ---------------------------------------------------------------------------------------------------------------------
 template <int W, int HD, bool kDiag>
 __global__ void __launch_bounds__(kThreads, 2)
-band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const BandArgs p) {
+band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                     const __grid_constant__ CUtensorMap tmO, const BandArgs p) {
   using C = Cfg<W>;
   constexpr int KS = HD / 16, HPC = 64 / HD, CH = HD / 8, NTF = W / 8;
   extern __shared__ unsigned char smem_raw[];
@@ -345,7 +353,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint64_t* bar = reinterpret_cast<uint64_t*>(sbits + W * 3);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const Item it = decode_item<W>(p);
+  const Item it = decode_item<W>(p, blockIdx.x);
   const int d3 = 3 * p.d;
 
   if (tid == 0) {
@@ -353,6 +361,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     mbar_fence_init();
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmO);
   }
   load_bits<W, kDiag>(sbits, p, it.w, tid);
   __syncthreads();
@@ -361,6 +370,13 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #pragma unroll
     for (int t = 0; t < 3; ++t) tma_load_4d(smem + t * C::kAll, &tmQKV, bar, t * p.d + it.cc * 64, it.w * W, it.f0 - 1, it.b);
     tma_load_4d(smem + 3 * C::kAll, &tmDO, bar, it.cc * 64, it.w * W, it.f0 - 1, it.b);
+    if (p.pf_dist > 0 && blockIdx.x + p.pf_dist < gridDim.x) {   // next wave's boxes -> L2 (see the forward)
+      const Item nx = decode_item<W>(p, blockIdx.x + p.pf_dist);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) tma_prefetch_4d(&tmQKV, t * p.d + nx.cc * 64, nx.w * W, nx.f0 - 1, nx.b);
+      tma_prefetch_4d(&tmDO, nx.cc * 64, nx.w * W, nx.f0 - 1, nx.b);
+      tma_prefetch_4d(&tmO, nx.cc * 64, nx.w * W, nx.f0 - 1, nx.b);     // O is read through registers below
+    }
   }
   // while the boxes fly: O through registers (delta = rowsum(dO * O) per head) and the saved logsumexp
   constexpr int kPasses = C::NSLOT * W * 8 / kThreads;
@@ -589,6 +605,17 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
 }
 
+// One wave of resident CTAs ahead (occupancy x SMs), per device and kernel; HWGAT_BAND_PREFETCH=0 switches it off
+static int prefetch_distance(const void* kernel, int smem) {
+  static const bool off = [] { const char* e = getenv("HWGAT_BAND_PREFETCH"); return e && e[0] == '0'; }();
+  if (off) return 0;
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return per_sm * sms;
+}
+
 template <int W, int HD, bool kDiag>
 static int launch_fwd(const BandArgs& p, const bf16* qkv, cudaStream_t s) {
   using C = Cfg<W>;
@@ -600,7 +627,9 @@ static int launch_fwd(const BandArgs& p, const bf16* qkv, cudaStream_t s) {
   CUtensorMap tm;
   int st;
   if ((st = make_tmap_4d(&tm, qkv, (uint64_t)3 * p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
-  band_attn_fwd_kernel<W, HD, kDiag><<<(unsigned)grid, kThreads, smem, s>>>(tm, p);
+  BandArgs q = p;
+  q.pf_dist = prefetch_distance((const void*)band_attn_fwd_kernel<W, HD, kDiag>, smem);
+  band_attn_fwd_kernel<W, HD, kDiag><<<(unsigned)grid, kThreads, smem, s>>>(tm, q);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -613,11 +642,14 @@ static int launch_bwd(const BandArgs& p, const bf16* qkv, const bf16* d_out, cud
   once.run([] { cudaFuncSetAttribute(band_attn_bwd_kernel<W, HD, kDiag>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
   const long long grid = (long long)p.B * (p.K / W) * (p.d / 64) * ((p.F + C::FR - 1) / C::FR);
   if (grid > 0x7fffffffLL) return HWGAT_ERR_UNSUPPORTED;
-  CUtensorMap tm, tmdo;
+  CUtensorMap tm, tmdo, tmo;
   int st;
   if ((st = make_tmap_4d(&tm, qkv, (uint64_t)3 * p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
   if ((st = make_tmap_4d(&tmdo, d_out, (uint64_t)p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
-  band_attn_bwd_kernel<W, HD, kDiag><<<(unsigned)grid, kThreads, smem, s>>>(tm, tmdo, p);
+  if ((st = make_tmap_4d(&tmo, p.ctx, (uint64_t)p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
+  BandArgs q = p;
+  q.pf_dist = prefetch_distance((const void*)band_attn_bwd_kernel<W, HD, kDiag>, smem);
+  band_attn_bwd_kernel<W, HD, kDiag><<<(unsigned)grid, kThreads, smem, s>>>(tm, tmdo, tmo, q);
   count_launch();
   return (int)cudaGetLastError();
 }
