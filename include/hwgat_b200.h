@@ -317,17 +317,20 @@ int hwgat_ln_wpool_bwd(const float* g, const float* x, const float* mean, const 
  *   out  bf16 (B, F, K, d)      head-merged context; qkv bf16 (B*F*K, 3d) is written and must be kept for the backward
  *   lse  f32  (B*F*K, heads)    base-2 logsumexp of the scaled logits over the edges, for the backward (NULL in inference)
  * Backward: d_xn bf16, d_w f32 (3d, d), d_b f32 (3d); workspace from hwgat_band_attn_workspace_bytes(.., 1).
+ * dtype HWGAT_F32: the 1e-5 parity mode - xn, w_qkv, out, qkv, ctx, d_out, d_xn float32, true fp32 FFMA, one thread per
+ * (token, head) walking the set bits of its band words, gather-only backward; no B*F*K % 128 / d % 128 constraint; the
+ * saved lse is a natural-log logsumexp; diag is ignored.  HWGAT_BF16: the timed kernels described above.
  * diag != 0: the caller promises that every previous- / next-frame word (r = 0, 2) of row i is 1 << i or 0 - the
  * identity the reference's graphs have between adjacent frames - and the kernels evaluate only the diagonal of those
  * blocks; every CTA checks the words it loads and traps if the promise is broken.  diag = 0: any band.
  * No attention dropout (both models default to attn_drop_rate = 0; the host side refuses p > 0).                  */
-size_t hwgat_band_attn_workspace_bytes(int B, int F, int K, int d, int backward);
-int hwgat_band_attn_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, void* out,
-                        void* qkv, float* lse, int B, int F, int K, int d, int heads, int W, int diag,
+size_t hwgat_band_attn_workspace_bytes(int dtype, int B, int F, int K, int d, int backward);
+int hwgat_band_attn_fwd(int dtype, const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits,
+                        void* out, void* qkv, float* lse, int B, int F, int K, int d, int heads, int W, int diag,
                         hwgat_stream_t stream);
-int hwgat_band_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const void* qkv, const void* ctx,
-                        const float* lse, const uint32_t* bits, void* d_xn, float* d_w, float* d_b, void* workspace,
-                        size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int diag,
+int hwgat_band_attn_bwd(int dtype, const void* d_out, const void* xn, const void* w_qkv, const void* qkv,
+                        const void* ctx, const float* lse, const uint32_t* bits, void* d_xn, float* d_w, float* d_b,
+                        void* workspace, size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int diag,
                         hwgat_stream_t stream);
 
 unsigned long long hwgat_launch_count(void);

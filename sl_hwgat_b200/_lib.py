@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("HWGAT_B200_LIB") or os.path.join(HERE, "lib", "libhwg
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 # name -> (restype, argtypes); must list every symbol of include/hwgat_b200.h
 SIGNATURES = {
@@ -22,9 +22,9 @@ SIGNATURES = {
     "hwgat_error_string": (c_char_p, [c_int]),
     "hwgat_ln_wpool_fwd": (c_int, [c_void_p] * 8 + [c_size_t, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "hwgat_ln_wpool_bwd": (c_int, [c_void_p] * 10 + [c_int] * 5 + [c_void_p]),
-    "hwgat_band_attn_workspace_bytes": (c_size_t, [c_int] * 5),
-    "hwgat_band_attn_fwd": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_void_p]),
-    "hwgat_band_attn_bwd": (c_int, [c_void_p] * 11 + [c_size_t] + [c_int] * 7 + [c_void_p]),
+    "hwgat_band_attn_workspace_bytes": (c_size_t, [c_int] * 6),
+    "hwgat_band_attn_fwd": (c_int, [c_int] + [c_void_p] * 7 + [c_int] * 7 + [c_void_p]),
+    "hwgat_band_attn_bwd": (c_int, [c_int] + [c_void_p] * 11 + [c_size_t] + [c_int] * 7 + [c_void_p]),
     "hwgat_launch_count": (c_ulonglong, []),
     "hwgat_set_deterministic": (c_int, [c_int]),
     "hwgat_adjacency_build": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -30,7 +30,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 16; }
+int hwgat_version(void) { return 17; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -157,27 +157,45 @@ static int check_geometry2(int B, int F, int K, int d, int heads, int W, int TP,
 }
 
 // ---- K15 / K16: frame-banded graph attention (WGATE.py:68-108, GATE.py:30-69) ----
-size_t hwgat_band_attn_workspace_bytes(int B, int F, int K, int d, int backward) {
-  return band_attn_workspace_bytes((long long)B * F * K, d, backward);
+// fp32 (parity mode): no 128-row GEMM tiles, so only the keypoint / head geometry is constrained
+static bool band_f32_supported(int B, int F, int K, int d, int heads, int W) {
+  if (B < 0 || F < 1 || K < 1 || d < 1 || heads < 1 || (W != 16 && W != 32) || K % W || d % heads) return false;
+  const int hd = d / heads;
+  return hd == 16 || hd == 32 || hd == 64;
+}
+static int band_check(int dtype, int B, int F, int K, int d, int heads, int W) {
+  if (dtype != HWGAT_F32 && dtype != HWGAT_BF16) return HWGAT_ERR_UNSUPPORTED;
+  if (B < 0 || F < 1 || K < 1 || d < 1 || heads < 1) return HWGAT_ERR_SHAPE;
+  const bool ok = dtype == HWGAT_F32 ? band_f32_supported(B, F, K, d, heads, W) : band_attn_supported(B, F, K, d, heads, W);
+  return ok ? HWGAT_OK : HWGAT_ERR_UNSUPPORTED;
 }
 
-int hwgat_band_attn_fwd(const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits, void* out,
-                        void* qkv, float* lse, int B, int F, int K, int d, int heads, int W, int diag,
+size_t hwgat_band_attn_workspace_bytes(int dtype, int B, int F, int K, int d, int backward) {
+  const long long n = (long long)B * F * K;
+  if (dtype == HWGAT_F32) return backward ? sizeof(float) * (size_t)n * 3 * d + 256 : 0;
+  return band_attn_workspace_bytes(n, d, backward);
+}
+
+int hwgat_band_attn_fwd(int dtype, const void* xn, const void* w_qkv, const float* b_qkv, const uint32_t* bits,
+                        void* out, void* qkv, float* lse, int B, int F, int K, int d, int heads, int W, int diag,
                         hwgat_stream_t stream) {
-  if (!band_attn_supported(B, F, K, d, heads, W)) return B < 0 || F < 1 || K < 1 ? HWGAT_ERR_SHAPE : HWGAT_ERR_UNSUPPORTED;
+  if (int st = band_check(dtype, B, F, K, d, heads, W)) return st;
   if (B == 0) return HWGAT_OK;
   if (!xn || !w_qkv || !b_qkv || !bits || !out || !qkv) return HWGAT_ERR_NULL;
   if (misaligned(xn) || misaligned(w_qkv) || misaligned(b_qkv) || misaligned(out) || misaligned(qkv) || misaligned(lse))
     return HWGAT_ERR_ALIGN;
+  if (dtype == HWGAT_F32)
+    return band_attn_fwd_f32((const float*)xn, (const float*)w_qkv, b_qkv, bits, (float*)out, (float*)qkv, lse, B, F, K,
+                             d, heads, W, (cudaStream_t)stream);
   return band_attn_fwd((const __nv_bfloat16*)xn, (const __nv_bfloat16*)w_qkv, b_qkv, bits, (__nv_bfloat16*)out,
                        (__nv_bfloat16*)qkv, lse, B, F, K, d, heads, W, diag, (cudaStream_t)stream);
 }
 
-int hwgat_band_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const void* qkv, const void* ctx,
-                        const float* lse, const uint32_t* bits, void* d_xn, float* d_w, float* d_b, void* workspace,
-                        size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int diag,
+int hwgat_band_attn_bwd(int dtype, const void* d_out, const void* xn, const void* w_qkv, const void* qkv,
+                        const void* ctx, const float* lse, const uint32_t* bits, void* d_xn, float* d_w, float* d_b,
+                        void* workspace, size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int diag,
                         hwgat_stream_t stream) {
-  if (!band_attn_supported(B, F, K, d, heads, W)) return B < 0 || F < 1 || K < 1 ? HWGAT_ERR_SHAPE : HWGAT_ERR_UNSUPPORTED;
+  if (int st = band_check(dtype, B, F, K, d, heads, W)) return st;
   if (!d_w || !d_b) return HWGAT_ERR_NULL;
   if (B == 0) {
     cudaMemsetAsync(d_w, 0, sizeof(float) * 3 * d * d, (cudaStream_t)stream);
@@ -188,7 +206,11 @@ int hwgat_band_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, co
   if (misaligned(d_out) || misaligned(xn) || misaligned(w_qkv) || misaligned(qkv) || misaligned(ctx) || misaligned(lse) ||
       misaligned(d_xn) || misaligned(d_w) || misaligned(workspace))
     return HWGAT_ERR_ALIGN;
-  if (!workspace || workspace_bytes < hwgat_band_attn_workspace_bytes(B, F, K, d, 1)) return HWGAT_ERR_WORKSPACE;
+  if (!workspace || workspace_bytes < hwgat_band_attn_workspace_bytes(dtype, B, F, K, d, 1)) return HWGAT_ERR_WORKSPACE;
+  if (dtype == HWGAT_F32)
+    return band_attn_bwd_f32((const float*)xn, (const float*)w_qkv, bits, (const float*)qkv, (const float*)ctx, lse,
+                             (const float*)d_out, (float*)d_xn, d_w, d_b, workspace, B, F, K, d, heads, W,
+                             (cudaStream_t)stream);
   return band_attn_bwd((const __nv_bfloat16*)xn, (const __nv_bfloat16*)w_qkv, bits, (const __nv_bfloat16*)qkv,
                        (const __nv_bfloat16*)ctx, lse, (const __nv_bfloat16*)d_out, (__nv_bfloat16*)d_xn, d_w, d_b,
                        workspace, B, F, K, d, heads, W, diag, (cudaStream_t)stream);

@@ -307,6 +307,38 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
 
 static int check_last() { return (int)cudaGetLastError(); }
 
+// the weight side of an fp32 attention backward: d_xn = dQKV . Wqkv, d_w = dQKV^T . xn, d_b = column sums of dQKV
+static int qkv_weight_grads_f32(const float* dqkv, const float* xn, const float* w_qkv, float* d_xn, float* d_w,
+                                float* d_b, long long n, int d, cudaStream_t s) {
+  const int d3 = 3 * d;
+  int st;
+  // d_xn = dQKV . Wqkv        [n, 3d] x [3d, d]
+  dim3 g1((d + 63) / 64, (unsigned)((n + 63) / 64), 1);
+  gemm_f32_kernel<false, false, false, false><<<g1, 256, 0, s>>>(dqkv, w_qkv, nullptr, d_xn, (int)n, d, d3, d3);
+  count_launch();
+  if ((st = check_last())) return st;
+  // d_w = dQKV^T . xn         [3d, n] x [n, d]   (split-K over tokens, atomics into zeroed d_w)
+  cudaMemsetAsync(d_w, 0, sizeof(float) * d3 * d, s);
+  cudaMemsetAsync(d_b, 0, sizeof(float) * d3, s);
+  int splits = (int)((n + 2047) / 2048);
+  if (splits > 512) splits = 512;
+  if (deterministic()) splits = 1;
+  int kps = (int)(((n + splits - 1) / splits + 15) / 16 * 16);
+  dim3 g2((d + 63) / 64, (d3 + 63) / 64, (unsigned)((n + kps - 1) / kps));
+  gemm_f32_kernel<true, false, true, false><<<g2, 256, 0, s>>>(dqkv, xn, nullptr, d_w, d3, d, (int)n, kps);
+  count_launch();
+  if ((st = check_last())) return st;
+  long long rpb = 512;
+  dim3 g3((d3 + 127) / 128, (unsigned)((n + rpb - 1) / rpb));
+  float* part;
+  if ((st = det_scratch(&part, 1, (int)g3.y, d3, s))) return st;
+  colsum_f32_kernel<<<g3, 128, 0, s>>>(dqkv, d_b, n, d3, rpb, part);
+  count_launch();
+  det_finish(part, (int)g3.y, d3, d_b, nullptr, nullptr, s);
+  return check_last();
+}
+
+
 int attn_fwd_f32(const AttnArgs& a, cudaStream_t s) {
   const long long n = (long long)a.B * a.F * a.K;
   const int d = a.d;
@@ -344,30 +376,201 @@ int attn_bwd_f32(const AttnArgs& a, cudaStream_t s) {
       qkv, (const float*)a.d_out, a.bits, a.threshold, dqkv, g);
   count_launch();
   if ((st = check_last())) return st;
-  // d_xn = dQKV . Wqkv        [n, 3d] x [3d, d]
-  dim3 g1((d + 63) / 64, (unsigned)((n + 63) / 64), 1);
-  gemm_f32_kernel<false, false, false, false><<<g1, 256, 0, s>>>(dqkv, (const float*)a.w_qkv, nullptr, (float*)a.d_xn,
-                                                                 (int)n, d, d3, d3);
+  return qkv_weight_grads_f32(dqkv, (const float*)a.xn, (const float*)a.w_qkv, (float*)a.d_xn, a.d_w, a.d_b, n, d, s);
+}
+
+// ---------------------------------------------------------------------------
+// fp32 parity mode of K15 / K16 (band_attn.cu): the frame-banded graph attention of WGATE / GATE in true fp32.
+// One thread per (token, head) walks the set bits of its three band words - the graph has a handful of edges per
+// token - so nothing is staged and nothing is tiled: a correctness mode (1e-5 against the reference's fp64 outputs),
+// not a timed one.  The backward is gather-only (no atomics): a thread forms dQ of its token as a query, then dK / dV
+// of the same token as a key by testing, for each keypoint of the three neighbouring frames, whether that query
+// attends it.
+// ---------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128) band_fwd_f32_kernel(const float* __restrict__ qkv, const uint32_t* __restrict__ bits,
+                                                           float* __restrict__ out, float* __restrict__ lse,
+                                                           long long n, int F, int K, int d, int heads, int W, float scale) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * heads) return;
+  const int h = (int)(idx % heads);
+  const long long tok = idx / heads;
+  const int k = (int)(tok % K), f = (int)((tok / K) % F), w = k / W, i = k - w * W;
+  const int d3 = 3 * d;
+  const float* qp = qkv + tok * d3 + h * HD;
+  float q[HD];
+#pragma unroll
+  for (int e = 0; e < HD; ++e) q[e] = qp[e] * scale;                       // q * scale first, as WGATE.py:96
+  const long long win0 = tok - i;                                          // first token of the window in this frame
+  float m = -INFINITY;
+  for (int r = 0; r < 3; ++r) {
+    const int fr = f - 1 + r;
+    if (fr < 0 || fr >= F) continue;
+    uint32_t word = bits[(w * W + i) * 3 + r];
+    while (word) {
+      const int j = __ffs(word) - 1;
+      word &= word - 1;
+      const float* kp = qkv + (win0 + (long long)(r - 1) * K + j) * d3 + d + h * HD;
+      float sdot = 0.f;
+#pragma unroll
+      for (int e = 0; e < HD; ++e) sdot = fmaf(q[e], kp[e], sdot);
+      m = fmaxf(m, sdot);
+    }
+  }
+  float l = 0.f, o[HD];
+#pragma unroll
+  for (int e = 0; e < HD; ++e) o[e] = 0.f;
+  for (int r = 0; r < 3; ++r) {
+    const int fr = f - 1 + r;
+    if (fr < 0 || fr >= F) continue;
+    uint32_t word = bits[(w * W + i) * 3 + r];
+    while (word) {
+      const int j = __ffs(word) - 1;
+      word &= word - 1;
+      const float* kp = qkv + (win0 + (long long)(r - 1) * K + j) * d3 + d + h * HD;
+      float sdot = 0.f;
+#pragma unroll
+      for (int e = 0; e < HD; ++e) sdot = fmaf(q[e], kp[e], sdot);
+      const float pr = expf(sdot - m);
+      l += pr;
+      const float* vp = kp + d;
+#pragma unroll
+      for (int e = 0; e < HD; ++e) o[e] = fmaf(pr, vp[e], o[e]);
+    }
+  }
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  float* op = out + tok * d + h * HD;
+#pragma unroll
+  for (int e = 0; e < HD; ++e) op[e] = o[e] * inv;
+  if (lse) lse[idx] = l > 0.f ? m + logf(l) : 0.f;                          // natural-log logsumexp (fp32 mode)
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) band_bwd_f32_kernel(const float* __restrict__ qkv, const uint32_t* __restrict__ bits,
+                                                           const float* __restrict__ out, const float* __restrict__ lse,
+                                                           const float* __restrict__ d_out, float* __restrict__ dqkv,
+                                                           long long n, int F, int K, int d, int heads, int W, float scale) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * heads) return;
+  const int h = (int)(idx % heads);
+  const long long tok = idx / heads;
+  const int k = (int)(tok % K), f = (int)((tok / K) % F), w = k / W, i = k - w * W;
+  const int d3 = 3 * d;
+  const long long win0 = tok - i;
+  // ---- as a query: dQ_i = scale * sum_j dS_ij k_j,  dS_ij = P_ij (dO_i . v_j - dO_i . O_i)
+  {
+    const float* qp = qkv + tok * d3 + h * HD;
+    const float* gp = d_out + tok * d + h * HD;
+    const float* op = out + tok * d + h * HD;
+    float q[HD], g[HD], dq[HD];
+    float delta = 0.f;
+#pragma unroll
+    for (int e = 0; e < HD; ++e) {
+      q[e] = qp[e] * scale;
+      g[e] = gp[e];
+      delta = fmaf(g[e], op[e], delta);
+      dq[e] = 0.f;
+    }
+    const float li = lse[idx];
+    for (int r = 0; r < 3; ++r) {
+      const int fr = f - 1 + r;
+      if (fr < 0 || fr >= F) continue;
+      uint32_t word = bits[(w * W + i) * 3 + r];
+      while (word) {
+        const int j = __ffs(word) - 1;
+        word &= word - 1;
+        const float* kp = qkv + (win0 + (long long)(r - 1) * K + j) * d3 + d + h * HD;
+        const float* vp = kp + d;
+        float sdot = 0.f, dp = 0.f;
+#pragma unroll
+        for (int e = 0; e < HD; ++e) { sdot = fmaf(q[e], kp[e], sdot); dp = fmaf(g[e], vp[e], dp); }
+        const float ds = expf(sdot - li) * (dp - delta);
+#pragma unroll
+        for (int e = 0; e < HD; ++e) dq[e] = fmaf(ds, kp[e], dq[e]);
+      }
+    }
+    float* dst = dqkv + tok * d3 + h * HD;
+#pragma unroll
+    for (int e = 0; e < HD; ++e) dst[e] = dq[e] * scale;
+  }
+  // ---- as a key: dK_j = scale * sum_i dS_ij q_i,  dV_j = sum_i P_ij dO_i  over the queries i that attend j
+  {
+    const float* kp = qkv + tok * d3 + d + h * HD;
+    const float* vp = kp + d;
+    float kk[HD], vv[HD], dk[HD], dv[HD];
+#pragma unroll
+    for (int e = 0; e < HD; ++e) { kk[e] = kp[e]; vv[e] = vp[e]; dk[e] = 0.f; dv[e] = 0.f; }
+    for (int r = 0; r < 3; ++r) {
+      const int fq = f + 1 - r;                       // the query frame that sees this frame as its frame fq - 1 + r
+      if (fq < 0 || fq >= F) continue;
+      for (int qi = 0; qi < W; ++qi) {
+        if (!((bits[(w * W + qi) * 3 + r] >> i) & 1u)) continue;
+        const long long qt = win0 + (long long)(1 - r) * K + qi;
+        const float* qp = qkv + qt * d3 + h * HD;
+        const float* gp = d_out + qt * d + h * HD;
+        const float* op = out + qt * d + h * HD;
+        float sdot = 0.f, dp = 0.f, delta = 0.f;
+#pragma unroll
+        for (int e = 0; e < HD; ++e) {
+          sdot = fmaf(qp[e] * scale, kk[e], sdot);
+          dp = fmaf(gp[e], vv[e], dp);
+          delta = fmaf(gp[e], op[e], delta);
+        }
+        const float pr = expf(sdot - lse[qt * heads + h]);
+        const float ds = pr * (dp - delta) * scale;
+#pragma unroll
+        for (int e = 0; e < HD; ++e) { dk[e] = fmaf(ds, qp[e], dk[e]); dv[e] = fmaf(pr, gp[e], dv[e]); }
+      }
+    }
+    float* dst = dqkv + tok * d3 + d + h * HD;
+#pragma unroll
+    for (int e = 0; e < HD; ++e) { dst[e] = dk[e]; dst[d + e] = dv[e]; }
+  }
+}
+
+// forward: qkv (caller's buffer, kept) = xn . Wqkv^T + b ; out, lse (optional)
+int band_attn_fwd_f32(const float* xn, const float* w_qkv, const float* b_qkv, const uint32_t* bits, float* out,
+                      float* qkv, float* lse, int B, int F, int K, int d, int heads, int W, cudaStream_t s) {
+  const long long n = (long long)B * F * K;
+  const int hd = d / heads;
+  if ((n + 63) / 64 > 65535) return HWGAT_ERR_UNSUPPORTED;          // gemm_f32_kernel puts the token tiles on grid.y
+  dim3 gg((3 * d + 63) / 64, (unsigned)((n + 63) / 64), 1);
+  gemm_f32_kernel<false, true, false, true><<<gg, 256, 0, s>>>(xn, w_qkv, b_qkv, qkv, (int)n, 3 * d, d, d);
   count_launch();
-  if ((st = check_last())) return st;
-  // d_w = dQKV^T . xn         [3d, n] x [n, d]   (split-K over tokens, atomics into zeroed d_w)
-  cudaMemsetAsync(a.d_w, 0, sizeof(float) * d3 * d, s);
-  cudaMemsetAsync(a.d_b, 0, sizeof(float) * d3, s);
-  int splits = (int)((n + 2047) / 2048);
-  if (splits > 512) splits = 512;
-  if (deterministic()) splits = 1;
-  int kps = (int)(((n + splits - 1) / splits + 15) / 16 * 16);
-  dim3 g2((d + 63) / 64, (d3 + 63) / 64, (unsigned)((n + kps - 1) / kps));
-  gemm_f32_kernel<true, false, true, false><<<g2, 256, 0, s>>>(dqkv, (const float*)a.xn, nullptr, a.d_w, d3, d, (int)n, kps);
+  int st = check_last();
+  if (st) return st;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const unsigned grid = (unsigned)((n * heads + 127) / 128);
+  switch (hd) {
+    case 16: band_fwd_f32_kernel<16><<<grid, 128, 0, s>>>(qkv, bits, out, lse, n, F, K, d, heads, W, scale); break;
+    case 32: band_fwd_f32_kernel<32><<<grid, 128, 0, s>>>(qkv, bits, out, lse, n, F, K, d, heads, W, scale); break;
+    case 64: band_fwd_f32_kernel<64><<<grid, 128, 0, s>>>(qkv, bits, out, lse, n, F, K, d, heads, W, scale); break;
+    default: return HWGAT_ERR_UNSUPPORTED;
+  }
   count_launch();
-  if ((st = check_last())) return st;
-  long long rpb = 512;
-  dim3 g3((d3 + 127) / 128, (unsigned)((n + rpb - 1) / rpb));
-  float* part = det_scratch(1, (int)g3.y, d3, s);
-  colsum_f32_kernel<<<g3, 128, 0, s>>>(dqkv, a.d_b, n, d3, rpb, part);
-  count_launch();
-  det_finish(part, (int)g3.y, d3, a.d_b, nullptr, nullptr, s);
   return check_last();
+}
+
+// backward workspace: dqkv [n, 3d] fp32
+int band_attn_bwd_f32(const float* xn, const float* w_qkv, const uint32_t* bits, const float* qkv, const float* ctx,
+                      const float* lse, const float* d_out, float* d_xn, float* d_w, float* d_b, void* workspace, int B,
+                      int F, int K, int d, int heads, int W, cudaStream_t s) {
+  const long long n = (long long)B * F * K;
+  const int hd = d / heads, d3 = 3 * d;
+  if ((n + 63) / 64 > 65535) return HWGAT_ERR_UNSUPPORTED;
+  float* dqkv = (float*)workspace;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const unsigned grid = (unsigned)((n * heads + 127) / 128);
+  switch (hd) {
+    case 16: band_bwd_f32_kernel<16><<<grid, 128, 0, s>>>(qkv, bits, ctx, lse, d_out, dqkv, n, F, K, d, heads, W, scale); break;
+    case 32: band_bwd_f32_kernel<32><<<grid, 128, 0, s>>>(qkv, bits, ctx, lse, d_out, dqkv, n, F, K, d, heads, W, scale); break;
+    case 64: band_bwd_f32_kernel<64><<<grid, 128, 0, s>>>(qkv, bits, ctx, lse, d_out, dqkv, n, F, K, d, heads, W, scale); break;
+    default: return HWGAT_ERR_UNSUPPORTED;
+  }
+  count_launch();
+  int st = check_last();
+  if (st) return st;
+  return qkv_weight_grads_f32(dqkv, xn, w_qkv, d_xn, d_w, d_b, n, d, s);
 }
 
 // ---------------------------------------------------------------------------

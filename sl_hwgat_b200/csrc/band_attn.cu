@@ -616,6 +616,19 @@ static int prefetch_distance(const void* kernel, int smem) {
   return per_sm * sms;
 }
 
+constexpr int kMaxDevices = 64;
+static int cached_prefetch_distance(int* cache, const void* kernel, int smem) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return prefetch_distance(kernel, smem);
+  int v = __atomic_load_n(&cache[dev], __ATOMIC_RELAXED);
+  if (v == 0) {
+    v = prefetch_distance(kernel, smem) + 1;     // stored + 1 so that "prefetch off" (0) is cached too
+    __atomic_store_n(&cache[dev], v, __ATOMIC_RELAXED);
+  }
+  return v - 1;
+}
+
 template <int W, int HD, bool kDiag>
 static int launch_fwd(const BandArgs& p, const bf16* qkv, cudaStream_t s) {
   using C = Cfg<W>;
@@ -628,7 +641,8 @@ static int launch_fwd(const BandArgs& p, const bf16* qkv, cudaStream_t s) {
   int st;
   if ((st = make_tmap_4d(&tm, qkv, (uint64_t)3 * p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
   BandArgs q = p;
-  q.pf_dist = prefetch_distance((const void*)band_attn_fwd_kernel<W, HD, kDiag>, smem);
+  static int pf_cache[kMaxDevices];          // occupancy x SMs of this instantiation, per device (0 = not asked yet)
+  q.pf_dist = cached_prefetch_distance(pf_cache, (const void*)band_attn_fwd_kernel<W, HD, kDiag>, smem);
   band_attn_fwd_kernel<W, HD, kDiag><<<(unsigned)grid, kThreads, smem, s>>>(tm, q);
   count_launch();
   return (int)cudaGetLastError();
@@ -648,7 +662,8 @@ static int launch_bwd(const BandArgs& p, const bf16* qkv, const bf16* d_out, cud
   if ((st = make_tmap_4d(&tmdo, d_out, (uint64_t)p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
   if ((st = make_tmap_4d(&tmo, p.ctx, (uint64_t)p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
   BandArgs q = p;
-  q.pf_dist = prefetch_distance((const void*)band_attn_bwd_kernel<W, HD, kDiag>, smem);
+  static int pf_cache[kMaxDevices];
+  q.pf_dist = cached_prefetch_distance(pf_cache, (const void*)band_attn_bwd_kernel<W, HD, kDiag>, smem);
   band_attn_bwd_kernel<W, HD, kDiag><<<(unsigned)grid, kThreads, smem, s>>>(tm, tmdo, tmo, q);
   count_launch();
   return (int)cudaGetLastError();

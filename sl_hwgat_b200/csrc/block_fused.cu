@@ -38,11 +38,16 @@ __global__ void col_finish_kernel(const float* __restrict__ part, int nblocks, i
     outs[v][c] = a;
   }
 }
-float* det_scratch(int nvec, int grid, int cols, cudaStream_t s) {
-  if (!deterministic()) return nullptr;
+int det_scratch(float** part, int nvec, int grid, int cols, cudaStream_t s) {
+  *part = nullptr;
+  if (!deterministic()) return 0;
   void* p = nullptr;
-  if (cudaMallocAsync(&p, sizeof(float) * (size_t)nvec * grid * cols, s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  return (float*)p;
+  if (cudaMallocAsync(&p, sizeof(float) * (size_t)nvec * grid * cols, s) != cudaSuccess) {
+    cudaGetLastError();
+    return HWGAT_ERR_WORKSPACE;   // never fall back to the atomic sums silently: the caller asked for reproducibility
+  }
+  *part = (float*)p;
+  return 0;
 }
 void det_finish(float* part, int grid, int cols, float* o0, float* o1, float* o2, cudaStream_t s) {
   if (!part) return;
@@ -529,7 +534,8 @@ int launch_ln_bwd(const bf16* dy, const float* dres, const float* x, const float
   cudaMemsetAsync(dbeta, 0, sizeof(float) * d, s);
   long long want = (n + 7) / 8;
   const int grid = (int)(want < 148LL * 4 ? (want < 1 ? 1 : want) : 148LL * 4);
-  float* part = det_scratch(2, grid, d, s);
+  float* part;
+  if (int st = det_scratch(&part, 2, grid, d, s)) return st;
   switch (d) {
     case 128: ln_bwd_kernel<8><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK, part); break;
     case 256: ln_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK, part); break;
@@ -595,7 +601,8 @@ int launch_bda_ln_bwd(const float* g_x1, const bf16* dy, const float* x1, const 
   }
   long long want = (n + 7) / 8;
   const int grid = (int)(want < 148LL * 4 ? (want < 1 ? 1 : want) : 148LL * 4);
-  float* part = det_scratch(3, grid, d, s);
+  float* part;
+  if (int st = det_scratch(&part, 3, grid, d, s)) return st;
   int st = gamma ? bda_bwd_dispatch<true>(grid, s, g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, scale, thresh, seed, offset, part)
                  : bda_bwd_dispatch<false>(grid, s, g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, scale, thresh, seed, offset, part);
   if (st) return st;
@@ -613,7 +620,8 @@ int launch_bias_gelu_dropout(const bf16* u0, const float* bias, const bf16* dg, 
   const int grid = ew_grid(nvec);
   if (backward) {
     if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * cols, s);
-    float* part = dbias ? det_scratch(1, grid, cols, s) : nullptr;
+    float* part = nullptr;
+    if (dbias) { if (int st = det_scratch(&part, 1, grid, cols, s)) return st; }
     bias_gelu_dropout_bwd_kernel<<<grid, 256, 0, s>>>(u0, bias, dg, out, dbias, nvec, cols, scale, thresh, seed, offset,
                                                        part);
     if (part) { count_launch(); det_finish(part, grid, cols, dbias, nullptr, nullptr, s); return (int)cudaGetLastError(); }
@@ -860,7 +868,8 @@ int launch_ln_pool_bwd(const float* g, const float* x, const float* mean, const 
                        const float* tok_w, float* dw_part, float* d_tok_w) {
   cudaMemsetAsync(dgamma, 0, sizeof(float) * d, s);
   const int slices = pool_slices(B, tokens);
-  float* part = det_scratch(1, B * slices, d, s);
+  float* part;
+  if (int st = det_scratch(&part, 1, B * slices, d, s)) return st;
   switch (d) {
     case 128: ln_pool_bwd_kernel<1><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad, part, tok_w, dw_part); break;
     case 256: ln_pool_bwd_kernel<2><<<B * slices, 256, 0, s>>>(g, x, mean, rstd, gamma, dx, dgamma, tokens, slices, kp_real, kp_pad, part, tok_w, dw_part); break;

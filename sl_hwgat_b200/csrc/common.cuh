@@ -25,8 +25,9 @@ constexpr int kTileTok = 128;          // tokens per tile = one temporal group =
 // partials live in stream-ordered scratch (cudaMallocAsync - the one place the library allocates, only in this mode).
 extern int g_deterministic;
 inline bool deterministic() { return __atomic_load_n(&g_deterministic, __ATOMIC_RELAXED) != 0; }
-// nullptr outside deterministic mode; else [nvec][grid][cols] floats on the stream (block_fused.cu)
-float* det_scratch(int nvec, int grid, int cols, cudaStream_t s);
+// *part = nullptr outside deterministic mode; else [nvec][grid][cols] floats on the stream (block_fused.cu).  A failed
+// allocation is an error (HWGAT_ERR_WORKSPACE), not a silent return to the atomic sums.
+int det_scratch(float** part, int nvec, int grid, int cols, cudaStream_t s);
 // o_v[c] = sum over grid, in index order, of part[v][.][c]; frees part on the stream; no-op for part == nullptr
 void det_finish(float* part, int grid, int cols, float* o0, float* o1, float* o2, cudaStream_t s);
 
@@ -207,6 +208,11 @@ int band_attn_bwd(const __nv_bfloat16* xn, const __nv_bfloat16* w_qkv, const uin
                   const __nv_bfloat16* ctx, const float* lse, const __nv_bfloat16* d_out, __nv_bfloat16* d_xn,
                   float* d_w, float* d_b, void* workspace, int B, int F, int K, int d, int heads, int W, int diag,
                   cudaStream_t s);
+int band_attn_fwd_f32(const float* xn, const float* w_qkv, const float* b_qkv, const uint32_t* bits, float* out,
+                      float* qkv, float* lse, int B, int F, int K, int d, int heads, int W, cudaStream_t s);
+int band_attn_bwd_f32(const float* xn, const float* w_qkv, const uint32_t* bits, const float* qkv, const float* ctx,
+                      const float* lse, const float* d_out, float* d_xn, float* d_w, float* d_b, void* workspace, int B,
+                      int F, int K, int d, int heads, int W, cudaStream_t s);
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t s);
 int attn_bwd_tc(const AttnArgs& a, __nv_bfloat16* dqkv, cudaStream_t s);
 int gemm_tc_tn(const __nv_bfloat16* A, const __nv_bfloat16* Bm, float* C, float* colsum, int M, int N, long long Kd,

@@ -257,7 +257,11 @@ struct TnDet {
   int begin(int splits, int M, int N, cudaStream_t s) {
     if (!deterministic() || splits <= 1) return 0;
     stride = (long long)M * N + M;
-    if (cudaMallocAsync((void**)&part, sizeof(float) * (size_t)stride * splits, s) != cudaSuccess) return (int)cudaGetLastError();
+    if (cudaMallocAsync((void**)&part, sizeof(float) * (size_t)stride * splits, s) != cudaSuccess) {
+      cudaGetLastError();
+      part = nullptr;
+      return HWGAT_ERR_WORKSPACE;
+    }
     cudaMemsetAsync(part, 0, sizeof(float) * (size_t)stride * splits, s);
     return 0;
   }

@@ -11,7 +11,8 @@ is stored padded to 32 and K15 / K16 (ops.band_graph_attention, one "window" of 
 the (B, F, 32, d) stream; the three padded keypoints have no edges (zero context, never a key), are skipped by the
 weighted pool and carry no gradient.  Everything else runs on the HWGATE kernels (K5, K6, K10, K12; K8 embedding, K9
 with token weights, K13 head).  ops.band_mask_pack proves the band property of whatever `adj_mask` holds and refuses
-anything else: there is no dense fallback.  bf16 / autocast only.
+anything else: there is no dense fallback.  Precision as WGATE: bf16 autocast = the fused chain; no autocast = the
+true-fp32 band kernels (1e-5) between PyTorch LayerNorm / Linear / GELU.
 """
 import torch
 import torch.nn as nn
@@ -42,7 +43,8 @@ class MSA(nn.Module):
     def context(self, xn, bits, window=KP_PAD):
         if self.training and self.attn_drop.p > 0:
             raise _lib.HwgatError("band attention has no attention dropout (the reference's default is 0; no fallback)")
-        return ops.band_graph_attention(xn, self.qkv.weight, self.qkv.bias, bits, self.num_heads, window)
+        return ops.band_graph_attention(xn.to(_hw._attn_dtype(xn)), self.qkv.weight, self.qkv.bias, bits,
+                                        self.num_heads, window)
 
     # -- reference signature: x is (B, F*K, d), normalised
     def forward(self, x, parent):
@@ -51,7 +53,7 @@ class MSA(nn.Module):
             raise _lib.HwgatError("GATE without a graph is dense attention over all tokens: not built (no fallback)")
         K, F = parent.num_kps, F_K // parent.num_kps
         bits = parent._bits.get(getattr(parent, self.adj_mask), F, KP_PAD, x.device)
-        xb = _pad_kp(x.reshape(B, F, K, d), 2).to(torch.bfloat16)
+        xb = _pad_kp(x.reshape(B, F, K, d), 2)
         ctx = self.context(xb, bits)[:, :, :K].reshape(B, F_K, d)
         return self.proj_drop(self.proj(ctx))
 
@@ -92,14 +94,25 @@ class AttentionBlock(nn.Module):
         return (K == KP_PAD and self._fusable(x)
                 and ops.band_attention_supported(B, F, K, d, self.attn.num_heads, KP_PAD))
 
+    def forward_generic(self, x, bits):
+        """the block on the padded (B, F, 32, d) stream with PyTorch LayerNorm / Linear / GELU around the band
+        attention: the fp32 mode (GATE.py:111-116)"""
+        a = self.attn
+        x = x + a.proj_drop(a.proj(a.context(self.norm1(x), bits)))
+        return x + self.ff(self.norm2(x))
+
     def forward(self, x, parent):
         B, F_K, d = x.shape
         K = parent.num_kps
-        xp = _pad_kp(x.reshape(B, F_K // K, K, d), 2)
-        if not (x.is_cuda and self.supported(xp)):
+        if not x.is_cuda:
             raise _lib.HwgatError(_NEED_BF16.format("GATE"))
-        xp, xn = ops.layer_norm_residual(xp, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        y = self.forward_chain(xp, xn, None, bits=self.band_bits(xp, parent))[0]
+        xp = _pad_kp(x.reshape(B, F_K // K, K, d), 2)
+        bits = self.band_bits(xp, parent)
+        if self.supported(xp):
+            xp, xn = ops.layer_norm_residual(xp, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            y = self.forward_chain(xp, xn, None, bits=bits)[0]
+        else:
+            y = self.forward_generic(xp, bits)
         return y[:, :, :K].reshape(B, F_K, d)
 
 
@@ -143,25 +156,35 @@ class Model(nn.Module):
     _init_weights = _hw.Model._init_weights
 
     def forward_features(self, x):
-        if not (x.is_cuda and x.dtype == torch.float32 and _hw._attn_dtype(x) == torch.bfloat16 and self.pe
-                and not x.requires_grad and type(self.norm) is nn.LayerNorm and self.embed_dim in (128, 256, 512)
-                and x.shape[2] == self.num_kps <= KP_PAD):
+        if not (x.is_cuda and x.shape[2] == self.num_kps <= KP_PAD):
             raise _lib.HwgatError(_NEED_BF16.format("GATE"))
-        # K8 on the padded keypoint axis: the padded keypoints embed to finite values, have no edges and are never pooled
-        x = ops.fourier_embed(_pad_kp(x, 2), self.B, self.pos_encoder.pe, self.pos_encoder.dropout.p, self.training)
         blocks = list(self.layers)
-        if blocks:
-            if not blocks[0].supported(x):
-                raise _lib.HwgatError(_NEED_BF16.format("GATE") + f"; shape {tuple(x.shape)} is not supported")
-            bits = blocks[0].band_bits(x, self)
+        fast = (x.dtype == torch.float32 and _hw._attn_dtype(x) == torch.bfloat16 and self.pe and not x.requires_grad
+                and type(self.norm) is nn.LayerNorm and self.embed_dim in (128, 256, 512))
+        # the keypoint axis is padded to 32: the padded keypoints embed to finite values, have no edges, are never
+        # pooled and carry no gradient
+        if fast:
+            x = ops.fourier_embed(_pad_kp(x, 2), self.B, self.pos_encoder.pe, self.pos_encoder.dropout.p, self.training)
+        else:
+            x = _hw.embed_generic(self, _pad_kp(x, 2))
+        bits = blocks[0].band_bits(x, self) if blocks else None
+        if fast and blocks and blocks[0].supported(x):
             first = blocks[0].norm1
             x, xn = ops.layer_norm_residual(x, first.weight, first.bias, first.eps)                        # K5
             for i, blk in enumerate(blocks):
                 nxt = blocks[i + 1].norm1 if i + 1 < len(blocks) else None
                 x, xn = blk.forward_chain(x, xn, nxt, bits=bits)
-        # K9 with token weights: final LayerNorm + weightedAvg over the F*29 real tokens (GATE.py:205-207)
-        return ops.layer_norm_weighted_pool(x, self.norm.weight, self.norm.bias, self.weightedAvg.weight,
-                                            self.weightedAvg.bias, self.norm.eps, kp_real=self.num_kps)
+        else:
+            for blk in blocks:
+                x = blk.forward_generic(x, bits)
+        if fast:
+            # K9 with token weights: final LayerNorm + weightedAvg over the F*29 real tokens (GATE.py:205-207)
+            return ops.layer_norm_weighted_pool(x, self.norm.weight, self.norm.bias, self.weightedAvg.weight,
+                                                self.weightedAvg.bias, self.norm.eps, kp_real=self.num_kps)
+        B, F, _, d = x.shape
+        K = self.num_kps
+        x = self.norm(x[:, :, :K]).reshape(B, F * K, d)
+        return self.weightedAvg(x.transpose(1, 2)).squeeze(-1)
 
     def forward(self, x):
         if _hw.AUTOCAST == "bf16" and x.is_cuda and not torch.is_autocast_enabled():

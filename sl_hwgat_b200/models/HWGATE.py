@@ -46,6 +46,18 @@ def _attn_dtype(x):
     return torch.float32
 
 
+def embed_generic(model, x):
+    """Fourier embedding + positional encoding with PyTorch ops (HWGATE.py:343-347): the fp32 mode, and inputs that
+    need a gradient.  The embedding stays fp32 even under autocast (bf16 would round the argument 2*pi*x.B, values up
+    to ~300, by up to 2 rad)."""
+    with torch.autocast(device_type=x.device.type, enabled=False):
+        proj = (2. * math.pi * x.float()) @ model.B.float().t()
+        x = torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1)
+    if model.pe:
+        x = model.pos_encoder(x)
+    return x
+
+
 class PositionalEncoding(nn.Module):
     """Sinusoid over the frame axis + dropout (HWGATE.py:8-28); buffer `pe` is (1, max_len, 1, d)."""
 
@@ -426,12 +438,7 @@ class Model(nn.Module):
         if fused and self.pe and not self.B.requires_grad and not x.requires_grad:
             x = self._embed_fused(x)
         else:
-            # the embedding stays fp32 even under autocast (see _embed_fused)
-            with torch.autocast(device_type=x.device.type, enabled=False):
-                proj = (2. * math.pi * x.float()) @ self.B.float().t()
-                x = torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1)
-            if self.pe:
-                x = self.pos_encoder(x)
+            x = embed_generic(self, x)
         layers = list(self.layers)
         if fused and all(isinstance(l, PartAttentionLayer) and l.fusable(x) for l in layers[:1]):
             # levels chained on the fused kernels: each level's last residual add stores TemporalMerging's layout and

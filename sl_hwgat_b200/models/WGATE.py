@@ -11,7 +11,11 @@ adjacent frames (model_params.py:204-229), so the dense (F*16)^2 softmax the ref
 over a 3-frame band; K15 / K16 (ops.band_graph_attention) evaluate only that band on the (B, F, K, d) stream - the
 partition / reverse copies disappear into index arithmetic - and every other stage of the block runs on the HWGATE
 kernels (K5, K6, K10, K12; K8 embedding, K9 pool, K13 head).  ops.band_mask_pack proves the band property of whatever
-`adj_mask` holds and refuses a mask that is not banded: there is no dense fallback.  bf16 / autocast only.
+`adj_mask` holds and refuses a mask that is not banded: there is no dense fallback.
+
+Precision: inside `torch.autocast("cuda", dtype=torch.bfloat16)` the fused bf16 chain runs (the timed path).  Without
+autocast (the reference's unmodified loop, utils.py:102) the attention runs the true-fp32 band kernels (1e-5 against
+the reference's fp64 outputs) between PyTorch LayerNorm / Linear / GELU: correct, not fast.
 """
 import torch
 import torch.nn as nn
@@ -20,8 +24,8 @@ from sl_hwgat_b200 import _lib, ops
 from sl_hwgat_b200.models import HWGATE as _hw
 from sl_hwgat_b200.models.HWGATE import FeedForward, PositionalEncoding  # noqa: F401 (reference names)
 
-_NEED_BF16 = ("{} runs on the bf16 kernels only: call it on an fp32 CUDA tensor under "
-              "torch.autocast('cuda', dtype=torch.bfloat16) (no fp32 / CPU fallback)")
+_NEED_BF16 = ("{} runs on the sm_100a kernels only: call it on an fp32 CUDA tensor, under "
+              "torch.autocast('cuda', dtype=torch.bfloat16) for the fast path (no CPU fallback)")
 
 
 def window_partition(x, window_size=16):
@@ -75,7 +79,8 @@ class MSA(nn.Module):
 
     def context(self, xn, bits, window):
         self._check_drop()
-        return ops.band_graph_attention(xn, self.qkv.weight, self.qkv.bias, bits, self.num_heads, window)
+        return ops.band_graph_attention(xn.to(_hw._attn_dtype(xn)), self.qkv.weight, self.qkv.bias, bits,
+                                        self.num_heads, window)
 
     # -- reference signature: x is (B*nW, F*W, d), already partitioned and normalised
     def forward(self, x, B, nW, parent):
@@ -86,7 +91,7 @@ class MSA(nn.Module):
         W = parent.window_size
         F = F_W // W
         bits = parent._bits.get(mask, F, W, x.device)
-        xb = window_reverse(x, W, F, nW * W).to(torch.bfloat16)
+        xb = window_reverse(x, W, F, nW * W)
         ctx = window_partition(self.context(xb, bits, W), W)
         return self.proj_drop(self.proj(ctx))
 
@@ -125,11 +130,20 @@ class PartAttentionBlock(nn.Module):
         B, F, K, d = x.shape
         return self._fusable(x) and ops.band_attention_supported(B, F, K, d, self.num_heads, self.window_size)
 
+    def forward_generic(self, x, bits):
+        """the block with PyTorch LayerNorm / Linear / GELU around the band attention: the fp32 mode (WGATE.py:150-160)"""
+        a = self.attn
+        x = x + a.proj_drop(a.proj(a.context(self.norm1(x), bits, self.window_size)))
+        return x + self.ff(self.norm2(x))
+
     def forward(self, x, parent):
-        if not (x.is_cuda and self.supported(x)):
+        if not x.is_cuda:
             raise _lib.HwgatError(_NEED_BF16.format("WGATE"))
+        bits = self.band_bits(x, parent)
+        if not self.supported(x):
+            return self.forward_generic(x, bits)
         x, xn = ops.layer_norm_residual(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        return self.forward_chain(x, xn, None, bits=self.band_bits(x, parent))[0]
+        return self.forward_chain(x, xn, None, bits=bits)[0]
 
 
 class Model(nn.Module):
@@ -174,22 +188,31 @@ class Model(nn.Module):
     _init_weights = _hw.Model._init_weights
 
     def forward_features(self, x):
-        if not (x.is_cuda and x.dtype == torch.float32 and _hw._attn_dtype(x) == torch.bfloat16 and self.pe
-                and not x.requires_grad and type(self.norm) is nn.LayerNorm and self.embed_dim in (128, 256, 512)):
+        if not x.is_cuda:
             raise _lib.HwgatError(_NEED_BF16.format("WGATE"))
-        x = ops.fourier_embed(x, self.B, self.pos_encoder.pe, self.pos_encoder.dropout.p, self.training)   # K8
         blocks = list(self.layers)
-        if blocks:
-            if not blocks[0].supported(x):
-                raise _lib.HwgatError(_NEED_BF16.format("WGATE") + f"; shape {tuple(x.shape)} is not supported")
-            bits = blocks[0].band_bits(x, self)
+        fast = (x.dtype == torch.float32 and _hw._attn_dtype(x) == torch.bfloat16 and self.pe and not x.requires_grad
+                and type(self.norm) is nn.LayerNorm and self.embed_dim in (128, 256, 512))
+        if fast:
+            x = ops.fourier_embed(x, self.B, self.pos_encoder.pe, self.pos_encoder.dropout.p, self.training)   # K8
+        else:
+            x = _hw.embed_generic(self, x)
+        bits = blocks[0].band_bits(x, self) if blocks else None
+        if fast and blocks and blocks[0].supported(x):
             first = blocks[0].norm1
             x, xn = ops.layer_norm_residual(x, first.weight, first.bias, first.eps)                        # K5
             for i, blk in enumerate(blocks):
                 nxt = blocks[i + 1].norm1 if i + 1 < len(blocks) else None
                 x, xn = blk.forward_chain(x, xn, nxt, bits=bits)
-        # K9: final LayerNorm + mean over all F*K tokens (self.avgpool, WGATE.py:256)
-        return ops.layer_norm_mean_pool(x, self.norm.weight, self.norm.bias, self.norm.eps)
+        else:
+            # no autocast (fp32): the true-fp32 band kernels between PyTorch LayerNorm / Linear / GELU
+            for blk in blocks:
+                x = blk.forward_generic(x, bits)
+        if fast:
+            # K9: final LayerNorm + mean over all F*K tokens (self.avgpool, WGATE.py:256)
+            return ops.layer_norm_mean_pool(x, self.norm.weight, self.norm.bias, self.norm.eps)
+        B, F, K, d = x.shape
+        return self.norm(x).reshape(B, F * K, d).mean(dim=1)
 
     def forward(self, x):
         if _hw.AUTOCAST == "bf16" and x.is_cuda and not torch.is_autocast_enabled():

@@ -388,51 +388,53 @@ def band_mask_pack(adj_mask: torch.Tensor, frames: int, window: int) -> torch.Te
 
 
 class _BandGraphAttention(torch.autograd.Function):
-    """QKV projection (tcgen05 GEMM) + frame-banded graph attention (K15) ; backward K16 + the three GEMMs."""
+    """QKV projection + frame-banded graph attention (K15) ; backward K16 + the three weight-side GEMMs.  bf16: the
+    tcgen05 / TMA / HMMA kernels; fp32: the true-fp32 parity kernels (attn_f32.cu)."""
 
     @staticmethod
     def forward(ctx, xn, w_qkv, b_qkv, bits, heads, window, diag):
         lib = _lib.load()
         _need_cuda(xn, w_qkv, b_qkv, bits)
-        if xn.dtype != torch.bfloat16 or xn.dim() != 4:
-            raise _lib.HwgatError("band attention takes the bf16 (B, F, K, d) stream (bf16 autocast only, no fallback)")
+        if xn.dim() != 4:
+            raise _lib.HwgatError("band attention takes the (B, F, K, d) stream")
+        code = _dtype_code(xn)
         xn_c = xn.contiguous()
         B, F, K, d = xn_c.shape
         if bits.shape != (K // window, window, 3):
             raise ValueError(f"band words {tuple(bits.shape)} do not match K = {K}, window = {window}")
-        w_c = cast_cached(w_qkv, torch.bfloat16)
+        w_c = cast_cached(w_qkv, xn_c.dtype)
         b_c = cast_cached(b_qkv, torch.float32)
         n_tok = B * F * K
         out = torch.empty_like(xn_c)
-        qkv = torch.empty((n_tok, 3 * d), dtype=torch.bfloat16, device=xn_c.device)
+        qkv = torch.empty((n_tok, 3 * d), dtype=xn_c.dtype, device=xn_c.device)
         need = any(ctx.needs_input_grad[:3])
         lse = torch.empty((n_tok, heads), dtype=torch.float32, device=xn_c.device) if need else None
         with torch.cuda.device(xn_c.device):
-            check(lib.hwgat_band_attn_fwd(xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
+            check(lib.hwgat_band_attn_fwd(code, xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
                                           out.data_ptr(), qkv.data_ptr(), _ptr(lse), B, F, K, d, heads, window,
                                           int(diag), _stream()), "hwgat_band_attn_fwd")
         if need:
             ctx.save_for_backward(xn_c, w_c, bits, qkv, out, lse)
-        ctx.meta = (heads, window, w_qkv.dtype, b_qkv.dtype, int(diag))
+        ctx.meta = (heads, window, w_qkv.dtype, b_qkv.dtype, int(diag), code)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         lib = _lib.load()
         xn_c, w_c, bits, qkv, out, lse = ctx.saved_tensors
-        heads, window, w_dtype, b_dtype, diag = ctx.meta
+        heads, window, w_dtype, b_dtype, diag, code = ctx.meta
         B, F, K, d = xn_c.shape
-        g = d_out.to(torch.bfloat16).contiguous()
+        g = d_out.to(xn_c.dtype).contiguous()
         d_xn = torch.empty_like(xn_c)
         d_w = torch.empty((3 * d, d), dtype=torch.float32, device=xn_c.device)
         d_b = torch.empty((3 * d,), dtype=torch.float32, device=xn_c.device)
-        ws_bytes = lib.hwgat_band_attn_workspace_bytes(B, F, K, d, 1)
+        ws_bytes = lib.hwgat_band_attn_workspace_bytes(code, B, F, K, d, 1)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xn_c.device)
         with torch.cuda.device(xn_c.device):
-            check(lib.hwgat_band_attn_bwd(g.data_ptr(), xn_c.data_ptr(), w_c.data_ptr(), qkv.data_ptr(), out.data_ptr(),
-                                          lse.data_ptr(), bits.data_ptr(), d_xn.data_ptr(), d_w.data_ptr(),
-                                          d_b.data_ptr(), ws.data_ptr(), ws.numel(), B, F, K, d, heads, window, diag,
-                                          _stream()), "hwgat_band_attn_bwd")
+            check(lib.hwgat_band_attn_bwd(code, g.data_ptr(), xn_c.data_ptr(), w_c.data_ptr(), qkv.data_ptr(),
+                                          out.data_ptr(), lse.data_ptr(), bits.data_ptr(), d_xn.data_ptr(),
+                                          d_w.data_ptr(), d_b.data_ptr(), ws.data_ptr(), ws.numel(), B, F, K, d, heads,
+                                          window, diag, _stream()), "hwgat_band_attn_bwd")
         return d_xn, d_w.to(w_dtype), d_b.to(b_dtype), None, None, None, None
 
 
@@ -445,7 +447,7 @@ def band_graph_attention(xn: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Ten
                          window: int, diag: Optional[bool] = None) -> torch.Tensor:
     """window_partition + QKV + additive-masked attention over all frames + window_reverse of WGATE
     (WGATE.py:150-158, 87-106) / the masked full attention of GATE (GATE.py:49-66), without the output projection, on
-    the (B, F, K, d) bf16 stream.  bits: band_mask_pack(...).  The attention evaluates the graph's frame band only
+    the (B, F, K, d) stream: bf16 = the timed kernels, fp32 = the 1e-5 parity kernels.  bits: band_mask_pack(...).  The attention evaluates the graph's frame band only
     (see band_mask_pack for why that equals the reference's dense softmax).  diag: the off-frame blocks are the
     identity (None: what band_mask_pack found; False forces the general path)."""
     if diag is None:

@@ -10,7 +10,7 @@ import torch
 
 from oracle import hwgate_oracle as O
 from oracle import wgate_oracle as WG
-from tests._util import rel_l2
+from tests._util import rel_inf, rel_l2
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 2e-2
@@ -325,13 +325,13 @@ def test_band_mask_pack_refuses_what_the_kernels_cannot_do():
         ops.band_mask_pack(empty, F, 16)
 
 
-def test_band_models_refuse_fp32_and_attention_dropout():
+def test_band_models_refuse_cpu_and_attention_dropout():
     from sl_hwgat_b200 import _lib
     m, cfg, sd, p = build("wgate", 8)
     m.eval()
     with pytest.raises(_lib.HwgatError):
-        m(WG.synthetic_keypoints(2, 8, 64, seed=1).cuda())          # no autocast: no fp32 band kernels
-    m.train()
+        m.cpu()(WG.synthetic_keypoints(2, 8, 64, seed=1))            # no CPU path
+    m.cuda().train()
     for blk in m.layers:
         blk.attn.attn_drop.p = 0.1
     with pytest.raises(_lib.HwgatError, match="attention dropout"), torch.autocast("cuda", dtype=torch.bfloat16):
@@ -412,3 +412,68 @@ def test_band_attention_full_size_replication(name):
     (ref * rb(g1).cuda()).sum().backward()
     assert rel_l2(y[0, :, :K], ref[0]) < BF16_TOL and rel_l2(x_.grad[0, :, :K], xr.grad[0]) < BF16_TOL
     assert rel_l2(w_.grad / B, wr.grad) < BF16_TOL and rel_l2(b_.grad / B, br.grad) < BF16_TOL
+
+
+# ------------------------------------------------------------------ fp32 parity mode (no autocast)
+FP32_TOL = 1e-5
+
+
+@pytest.mark.parametrize("name", ["wgate", "gate"])
+@pytest.mark.parametrize("d,h", [(128, 8), (128, 2), (256, 8)])
+def test_band_attention_fp32_vs_reference_golden(golden_dir, name, d, h):
+    """the true-fp32 band kernels against the reference's fp64 outputs (dense attention, additive mask): 1e-5"""
+    from sl_hwgat_b200 import ops
+    from sl_hwgat_b200.models.HGATE import _pad_kp
+    G = np.load(os.path.join(golden_dir, "wgate_gate.npz"))
+    key = f"{name}_d{d}_h{h}"
+    xn, w, b, g = core_inputs(name, d, h)
+    B, F, K, _ = xn.shape
+    W = 16 if name == "wgate" else 32
+    bits = ops.band_mask_pack(torch.from_numpy(dense_mask(name, F)).float().cuda(), F, W)
+    x_ = xn.float().cuda().requires_grad_(True)
+    w_ = w.float().cuda().requires_grad_(True)
+    b_ = b.float().cuda().requires_grad_(True)
+    xp = _pad_kp(x_, 2) if name == "gate" else x_
+    y = ops.band_graph_attention(xp, w_, b_, bits, h, W)[:, :, :K]
+    assert y.dtype == torch.float32
+    (y * g.float().cuda()).sum().backward()
+
+    def chk(t, nm, stride):
+        a = t.detach().double().cpu().reshape(-1).numpy()[::stride]
+        ref = G[key + "_" + nm]
+        return float(np.abs(a - ref).max() / np.abs(ref).max())
+    errs = (chk(y, "y", 53), chk(x_.grad, "dx", 53), chk(w_.grad, "dw", 251), chk(b_.grad, "db", 1))
+    print(key, "fp32 max-rel y/dx/dw/db:", errs)
+    assert max(errs) < FP32_TOL, errs
+
+
+@pytest.mark.parametrize("name", ["wgate", "gate"])
+def test_band_model_fp32_vs_reference_golden(golden_dir, name):
+    """the drop-in model called without autocast (utils.py:102): logits, loss and every parameter gradient against the
+    reference's fp64 run"""
+    G = np.load(os.path.join(golden_dir, "wgate_gate.npz"))
+    F, K = (8, 64) if name == "wgate" else (6, 29)
+    m, cfg, sd, p = build(name, F)
+    m.train()                                    # drop 0
+    x = WG.synthetic_keypoints(2, F, K, seed=1001).cuda()
+    y = torch.tensor([3, 7]).cuda()
+    logits = m(x)
+    loss = O.smoothed_cross_entropy(logits, y)
+    loss.backward()
+    assert logits.dtype == torch.float32
+    assert rel_inf(logits, torch.from_numpy(G[name + "_model_logits"])) < FP32_TOL
+    assert abs(loss.item() - float(G[name + "_model_loss"])) < 1e-5 * abs(float(G[name + "_model_loss"]))
+    grads = dict(m.named_parameters())
+    worst = 0.0
+    for pname, norm, head in zip(G[name + "_gnames"], G[name + "_gnorms"], G[name + "_gheads"]):
+        gr = grads[str(pname)].grad.double().cpu()
+        worst = max(worst, abs(gr.norm().item() - norm) / norm)
+        got = np.zeros(4); got[:min(4, gr.numel())] = gr.reshape(-1)[:4].numpy()
+        assert np.abs(got - head).max() <= 1e-4 * max(np.abs(head).max(), 1e-12) + 1e-9, pname
+    assert worst < 1e-4, worst
+    # and the whole gradients against oracle autograd in fp64
+    sd64 = {k: v.double().requires_grad_(k not in ("B", "pos_encoder.pe", "adj_mask")) for k, v in sd.items()}
+    ref = (WG.wgate_forward if name == "wgate" else WG.gate_forward)(x.cpu().double(), sd64, cfg)
+    O.smoothed_cross_entropy(ref, y.cpu()).backward()
+    errs = {n: rel_l2(q.grad.cpu(), sd64[n].grad) for n, q in m.named_parameters() if q.grad is not None}
+    assert max(errs.values()) < 1e-4, sorted(errs.items(), key=lambda kv: -kv[1])[:3]
