@@ -11,11 +11,13 @@
 // of size N^2 ever exists.  The host side (ops.band_mask_pack) verifies that the adjacency really is frame-banded,
 // frame-invariant, 0/1-valued and without empty rows, and refuses anything else: there is no dense fallback.
 //
-// Bound: HBM.  Per token the forward reads q, k, v (3 d bf16) and writes ctx (d bf16) [+ 4 B * heads of logsumexp in
-// training]; the backward reads q, k, v, dO, ctx (5 d) and writes dQ, dK, dV (3 d).  The tensor work (mma.sync
-// m16n8k16, 12 - 36 instructions per 16 queries per head) is two orders of magnitude under the pipe's rate, so legacy
-// HMMA on register fragments is the right tool: a tcgen05 tile (M = 128, operands through smem descriptors, accumulator
-// in TMEM) would only add latency to a kernel that waits for memory.
+// Roofline: HBM.  Per token the forward reads q, k, v (3 d bf16) and writes ctx (d bf16) [+ 4 B * heads of logsumexp in
+// training]; the backward reads q, k, v, dO, ctx (5 d) and writes dQ, dK, dV (3 d).  Measured alone on the WGATE step
+// shape (ncu, profiles/r02o_band_wgate.md): DRAM traffic = those bytes; forward 65 %, backward 47 % of the HBM rate, the
+// backward limited by instruction issue (735 warp instructions per 16 tokens per head), not by memory.
+// The tensor work (mma.sync m16n8k16, 12 - 42 instructions per 16 tokens per head) is two orders of magnitude under the
+// pipe's rate, so legacy HMMA on register fragments is the right tool: a tcgen05 tile (M = 128, operands through smem
+// descriptors, accumulator in TMEM) would add latency and synchronisation to blocks of 16 x 48 logits.
 //
 // One CTA (8 warps) owns FR consecutive frames of one (sample, window) and one 64-column slice of d (64 / HD heads):
 // one thread issues a TMA box copy per tensor - (64 columns, W keypoints, FR+2 frames) of q, k, v (backward: + dO) with
@@ -29,7 +31,8 @@
 // general path.
 // The backward needs no atomics and no cross-CTA traffic: with the forward's logsumexp saved and delta = rowsum(dO * O)
 // formed while dO is staged, a warp computes dQ of its 16 tokens as QUERIES (blocks (f, f-1..f+1)) and dK, dV of the same
-// 16 tokens as KEYS (blocks (f-1..f+1, f)); the off-diagonal blocks are computed twice, which costs nothing here.
+// 16 tokens as KEYS (blocks (f-1..f+1, f)); every block is therefore evaluated twice (once per side), the price of having
+// no exchange between warps.
 #include "tc.cuh"
 
 namespace hwgat {
