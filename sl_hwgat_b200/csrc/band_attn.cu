@@ -89,6 +89,20 @@ HW_DEV float lg2(float x) {
   return r;
 }
 
+// transpose of an 8 x 8 b16 block held in the fragment layout (one 32-bit register per thread)
+HW_DEV uint32_t movm(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;\n" : "=r"(d) : "r"(a));
+  return d;
+}
+// A fragment of X^T from the A fragment of a 16 x 16 block X: the four 8 x 8 blocks transposed, the off-diagonal two swapped
+HW_DEV void transpose_frag(uint32_t (&t)[4], const uint32_t (&a)[4]) {
+  t[0] = movm(a[0]);
+  t[1] = movm(a[2]);
+  t[2] = movm(a[1]);
+  t[3] = movm(a[3]);
+}
+
 // A fragment (16 rows x 16 columns) of staged rows row0.., columns [chunk0*8, chunk0*8 + 16)
 HW_DEV void load_a(uint32_t (&a)[4], uint32_t base, int row0, int chunk0, int lane) {
   ldsm4(a, base + swz(row0 + (lane & 7) + ((lane >> 3) & 1) * 8, chunk0 + (lane >> 4)));
@@ -433,6 +447,9 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const int r0 = mt * 16 + g, r1 = r0 + 8;   // keypoints of the thread's two rows
 #pragma unroll
     for (int hh = 0; hh < HPC; ++hh) {
+      // P and dS of the block (own 16 queries x own 16 keys), kept as A fragments: the key side below needs exactly
+      // their transposes and gets them with eight movmatrix instead of evaluating the block a second time
+      uint32_t p_own[4] = {0u, 0u, 0u, 0u}, ds_own[4] = {0u, 0u, 0u, 0u};
       // ---- the warp's tokens as QUERIES: dQ = scale * sum over key frames dS . K
       {
         uint32_t qa[KS][4], da[KS][4];
@@ -473,7 +490,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
               const float p1 = ex2(lv1 ? fmaf(diag_row1(s[1], g), sl2, -lse1) : -INFINITY);
               diag_frag(dsa, p0 * (diag_row0(dp[0], g) - dl0), p1 * (diag_row1(dp[1], g) - dl1), g);
             } else {
-              float ds[2][4];
+              float pt[2][4], ds[2][4];
 #pragma unroll
               for (int t = 0; t < 2; ++t)
 #pragma unroll
@@ -481,10 +498,17 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                   const int kp = np * 16 + t * 8 + qd * 2 + (i & 1);
                   const bool live = ((i < 2 ? w0 : w1) >> kp) & 1u;
                   const float pr = ex2(live ? fmaf(s[t][i], sl2, -(i < 2 ? lse0 : lse1)) : -INFINITY);
+                  pt[t][i] = pr;
                   ds[t][i] = pr * (dp[t][i] - (i < 2 ? dl0 : dl1));
                 }
               dsa[0] = pack_bf16(ds[0][0], ds[0][1]); dsa[1] = pack_bf16(ds[0][2], ds[0][3]);
               dsa[2] = pack_bf16(ds[1][0], ds[1][1]); dsa[3] = pack_bf16(ds[1][2], ds[1][3]);
+              if (W == 16 && kf == 1 && np == mt) {
+                p_own[0] = pack_bf16(pt[0][0], pt[0][1]); p_own[1] = pack_bf16(pt[0][2], pt[0][3]);
+                p_own[2] = pack_bf16(pt[1][0], pt[1][1]); p_own[3] = pack_bf16(pt[1][2], pt[1][3]);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) ds_own[x] = dsa[x];
+              }
             }
 #pragma unroll
             for (int hp = 0; hp < CH / 2; ++hp) {
@@ -523,19 +547,27 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #pragma unroll
           for (int np = 0; np < NTF / 2; ++np) {
             if (diag && np != mt) continue;
+            // (own queries x own keys): transposes of the query side's block.  W = 16 only: at W = 32 it covers one of the
+            // two in-frame pairs and the eight extra live registers cost more than it saves (measured: +1.5 %)
+            const bool reuse = W == 16 && qo == 1 && np == mt;
             float s[2][4] = {}, dp[2][4] = {};
+            if (!reuse) {
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-              uint32_t qb[4], gb[4];
-              load_b_nk(qb, sq, qrow + np * 16, hh * CH + ks * 2, lane);
-              load_b_nk(gb, sdo, qrow + np * 16, hh * CH + ks * 2, lane);
-              mma16816(s[0], ka[ks], qb[0], qb[1]);
-              mma16816(s[1], ka[ks], qb[2], qb[3]);
-              mma16816(dp[0], va[ks], gb[0], gb[1]);
-              mma16816(dp[1], va[ks], gb[2], gb[3]);
+              for (int ks = 0; ks < KS; ++ks) {
+                uint32_t qb[4], gb[4];
+                load_b_nk(qb, sq, qrow + np * 16, hh * CH + ks * 2, lane);
+                load_b_nk(gb, sdo, qrow + np * 16, hh * CH + ks * 2, lane);
+                mma16816(s[0], ka[ks], qb[0], qb[1]);
+                mma16816(s[1], ka[ks], qb[2], qb[3]);
+                mma16816(dp[0], va[ks], gb[0], gb[1]);
+                mma16816(dp[1], va[ks], gb[2], gb[3]);
+              }
             }
             uint32_t pa[4], dsa[4];
-            if (diag) {   // query keypoint == key keypoint: the thread's own two rows
+            if (reuse) {
+              transpose_frag(pa, p_own);
+              transpose_frag(dsa, ds_own);
+            } else if (diag) {   // query keypoint == key keypoint: the thread's own two rows
               const bool lv0 = own && ((sbits[r0 * 3 + kfrel] >> r0) & 1u), lv1 = own && ((sbits[r1 * 3 + kfrel] >> r1) & 1u);
               const float p0 = ex2(lv0 ? fmaf(diag_row0(s[0], g), sl2, -s_lse[(qrow + r0) * HPC + hh]) : -INFINITY);
               const float p1 = ex2(lv1 ? fmaf(diag_row1(s[1], g), sl2, -s_lse[(qrow + r1) * HPC + hh]) : -INFINITY);
