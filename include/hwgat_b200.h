@@ -291,6 +291,20 @@ int hwgat_debug_set_gemm_pair(int on);
 
 /* Number of kernel launches issued through this library since load (all
  * streams, this process) - what bench.py reports as "gpu_launches". */
+/* fp32 parity mode of hwgat_attn2_fwd / hwgat_attn2_bwd: window_size 32 / 64 (N = 64 / 128 tokens) and HGATE's blocks in
+ * true fp32 (FFMA, one thread per token of a window; the 1e-5 mode of the north_star - a correctness mode, not timed).
+ * Every tensor float32; same semantics as hwgat_attn_fwd(HWGAT_F32, ...) (threshold drop, packed mask, -10000 fill);
+ * no attention dropout; no 128-token tile constraint (any B, even F, K % W == 0).  qkv (B*F*K, 3d) is written by the
+ * forward and read by the backward; backward workspace from hwgat_attn2_f32_workspace_bytes(.., 1).                */
+size_t hwgat_attn2_f32_workspace_bytes(int B, int F, int K, int d, int backward);
+int hwgat_attn2_fwd_f32(const float* xn, const float* w_qkv, const float* b_qkv, const uint32_t* bits, float threshold,
+                        float* out, float* qkv, int B, int F, int K, int d, int heads, int W, int TP, int shift,
+                        int layout, hwgat_stream_t stream);
+int hwgat_attn2_bwd_f32(const float* d_out, const float* xn, const float* w_qkv, const float* qkv, const uint32_t* bits,
+                        float threshold, float* d_xn, float* d_w, float* d_b, void* workspace, size_t workspace_bytes,
+                        int B, int F, int K, int d, int heads, int W, int TP, int shift, int layout,
+                        hwgat_stream_t stream);
+
 /* K9 with learned token weights: GATE's `weightedAvg` = Linear(F*K, 1) over the token axis (hwgat/models/GATE.py:185,
  * 207) fused with the final LayerNorm (GATE.py:205).  pooled[b, c] = sum_t tok_w[t] * (xhat[b,t,c] gamma[c]) + beta[c];
  * the caller passes beta * sum(tok_w) + the Linear's bias as `beta`.  tok_w f32 (tokens) indexes REAL tokens

@@ -14,12 +14,15 @@ LIB_PATH = os.environ.get("HWGAT_B200_LIB") or os.path.join(HERE, "lib", "libhwg
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 # name -> (restype, argtypes); must list every symbol of include/hwgat_b200.h
 SIGNATURES = {
     "hwgat_version": (c_int, []),
     "hwgat_error_string": (c_char_p, [c_int]),
+    "hwgat_attn2_f32_workspace_bytes": (c_size_t, [c_int] * 5),
+    "hwgat_attn2_fwd_f32": (c_int, [c_void_p] * 4 + [c_float] + [c_void_p] * 2 + [c_int] * 9 + [c_void_p]),
+    "hwgat_attn2_bwd_f32": (c_int, [c_void_p] * 5 + [c_float] + [c_void_p] * 4 + [c_size_t] + [c_int] * 9 + [c_void_p]),
     "hwgat_ln_wpool_fwd": (c_int, [c_void_p] * 8 + [c_size_t, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "hwgat_ln_wpool_bwd": (c_int, [c_void_p] * 10 + [c_int] * 5 + [c_void_p]),
     "hwgat_band_attn_workspace_bytes": (c_size_t, [c_int] * 6),

@@ -30,7 +30,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 17; }
+int hwgat_version(void) { return 18; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -268,6 +268,61 @@ int hwgat_attn2_bwd(const void* d_out, const void* xn, const void* w_qkv, const 
   a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
   a.attn_p = attn_p; a.seed = seed; a.offset = offset; a.qk_perm = qk_perm;
   return attn2_bwd(a, W, (const __nv_bfloat16*)qkv, (cudaStream_t)stream);
+}
+
+// ---- fp32 parity mode of the general-window attention (attn_win_f32.cu): window_size 32 / 64, HGATE's blocks ----
+static int check_geometry2_f32(int B, int F, int K, int d, int heads, int W, int TP, int shift, int layout) {
+  if (B < 0 || F <= 0 || K <= 0 || d <= 0 || heads <= 0) return HWGAT_ERR_SHAPE;
+  if (layout != HWGAT_LAYOUT_BFKD && layout != HWGAT_LAYOUT_WINDOWS) return HWGAT_ERR_UNSUPPORTED;
+  if ((W != 32 && W != 64) || TP != kTP) return HWGAT_ERR_UNSUPPORTED;     // W = 16: hwgat_attn_fwd(HWGAT_F32, ...)
+  if (d != heads * kHd || d % 4 != 0) return HWGAT_ERR_UNSUPPORTED;
+  if (F % TP != 0 || K % W != 0) return HWGAT_ERR_UNSUPPORTED;
+  if (shift < 0 || shift >= TP) return HWGAT_ERR_SHAPE;
+  if (layout == HWGAT_LAYOUT_WINDOWS && shift != 0) return HWGAT_ERR_SHAPE;
+  if ((long long)B * F * K > 64LL * 65535) return HWGAT_ERR_UNSUPPORTED;   // the FFMA GEMMs put the token tiles on grid.y
+  return HWGAT_OK;
+}
+
+size_t hwgat_attn2_f32_workspace_bytes(int B, int F, int K, int d, int backward) {
+  return attn2_workspace_bytes_f32((long long)B * F * K, d, backward);
+}
+
+int hwgat_attn2_fwd_f32(const float* xn, const float* w_qkv, const float* b_qkv, const uint32_t* bits, float threshold,
+                        float* out, float* qkv, int B, int F, int K, int d, int heads, int W, int TP, int shift,
+                        int layout, hwgat_stream_t stream) {
+  int st = check_geometry2_f32(B, F, K, d, heads, W, TP, shift, layout);
+  if (st) return st;
+  if (B == 0) return HWGAT_OK;
+  if (!xn || !w_qkv || !b_qkv || !bits || !out || !qkv) return HWGAT_ERR_NULL;
+  if (misaligned(xn) || misaligned(w_qkv) || misaligned(out) || misaligned(b_qkv) || misaligned(qkv)) return HWGAT_ERR_ALIGN;
+  AttnArgs a{};
+  a.xn = xn; a.w_qkv = w_qkv; a.b_qkv = b_qkv; a.bits = bits; a.threshold = threshold; a.out = out;
+  a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
+  return attn2_fwd_f32(a, W, qkv, (cudaStream_t)stream);
+}
+
+int hwgat_attn2_bwd_f32(const float* d_out, const float* xn, const float* w_qkv, const float* qkv, const uint32_t* bits,
+                        float threshold, float* d_xn, float* d_w, float* d_b, void* workspace, size_t workspace_bytes,
+                        int B, int F, int K, int d, int heads, int W, int TP, int shift, int layout,
+                        hwgat_stream_t stream) {
+  int st = check_geometry2_f32(B, F, K, d, heads, W, TP, shift, layout);
+  if (st) return st;
+  if (!d_w || !d_b) return HWGAT_ERR_NULL;
+  if (B == 0) {
+    cudaMemsetAsync(d_w, 0, sizeof(float) * 3 * d * d, (cudaStream_t)stream);
+    cudaMemsetAsync(d_b, 0, sizeof(float) * 3 * d, (cudaStream_t)stream);
+    return (int)cudaGetLastError();
+  }
+  if (!d_out || !xn || !w_qkv || !qkv || !bits || !d_xn) return HWGAT_ERR_NULL;
+  if (misaligned(d_out) || misaligned(xn) || misaligned(w_qkv) || misaligned(qkv) || misaligned(d_xn) || misaligned(d_w) ||
+      misaligned(workspace))
+    return HWGAT_ERR_ALIGN;
+  if (!workspace || workspace_bytes < hwgat_attn2_f32_workspace_bytes(B, F, K, d, 1)) return HWGAT_ERR_WORKSPACE;
+  AttnArgs a{};
+  a.xn = xn; a.w_qkv = w_qkv; a.bits = bits; a.threshold = threshold; a.d_out = d_out;
+  a.d_xn = d_xn; a.d_w = d_w; a.d_b = d_b; a.workspace = workspace;
+  a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
+  return attn2_bwd_f32(a, W, qkv, (cudaStream_t)stream);
 }
 
 int hwgat_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,

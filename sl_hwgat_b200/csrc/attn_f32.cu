@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
 static int check_last() { return (int)cudaGetLastError(); }
 
 // the weight side of an fp32 attention backward: d_xn = dQKV . Wqkv, d_w = dQKV^T . xn, d_b = column sums of dQKV
-static int qkv_weight_grads_f32(const float* dqkv, const float* xn, const float* w_qkv, float* d_xn, float* d_w,
+int qkv_weight_grads_f32(const float* dqkv, const float* xn, const float* w_qkv, float* d_xn, float* d_w,
                                 float* d_b, long long n, int d, cudaStream_t s) {
   const int d3 = 3 * d;
   int st;
@@ -556,7 +556,7 @@ int band_attn_bwd_f32(const float* xn, const float* w_qkv, const uint32_t* bits,
                       const float* lse, const float* d_out, float* d_xn, float* d_w, float* d_b, void* workspace, int B,
                       int F, int K, int d, int heads, int W, cudaStream_t s) {
   const long long n = (long long)B * F * K;
-  const int hd = d / heads, d3 = 3 * d;
+  const int hd = d / heads;
   if ((n + 63) / 64 > 65535) return HWGAT_ERR_UNSUPPORTED;
   float* dqkv = (float*)workspace;
   const float scale = 1.0f / sqrtf((float)hd);

@@ -196,6 +196,12 @@ int attn_bwd_f32(const AttnArgs& a, cudaStream_t s);
 int attn_fwd_bf16(const AttnArgs& a, cudaStream_t s);
 int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s);
 size_t attn2_workspace_bytes(long long n, int d, int backward, int have_qkv);
+// fp32 parity mode of K2b / K3b (attn_win_f32.cu): windows of N = 64 / 128 tokens
+size_t attn2_workspace_bytes_f32(long long n, int d, int backward);
+int attn2_fwd_f32(const AttnArgs& a, int W, float* qkv, cudaStream_t s);
+int attn2_bwd_f32(const AttnArgs& a, int W, const float* qkv, cudaStream_t s);
+int qkv_weight_grads_f32(const float* dqkv, const float* xn, const float* w_qkv, float* d_xn, float* d_w, float* d_b,
+                         long long n, int d, cudaStream_t s);
 int attn2_fwd(const AttnArgs& a, int W, __nv_bfloat16* qkv, cudaStream_t s);
 int attn2_bwd(const AttnArgs& a, int W, const __nv_bfloat16* qkv_saved, cudaStream_t s);
 // K15 / K16 (band_attn.cu): frame-banded graph attention of WGATE / GATE

@@ -9,8 +9,12 @@ How it runs here: the keypoint axis is stored padded to 32, so a block is one wi
 general-window tcgen05 attention (ops.window_graph_attention, window = 32: K2b / K3b) with the six padded tokens of
 every block masked out as keys; every other kernel of the HWGATE block (K5, K6, K10, K12, the folded temporal merge)
 runs unchanged on the padded rows, and the final LayerNorm + mean pool (K9) skips them.  Padded rows never reach the
-loss, so they get zero gradient and contribute nothing to any parameter gradient.  bf16 / autocast only: the fp32
-parity kernels are built for HWGATE's 32-token windows, so an fp32 call raises (no fallback).
+loss, so they get zero gradient and contribute nothing to any parameter gradient.
+
+Precision: inside `torch.autocast("cuda", dtype=torch.bfloat16)` the fused bf16 chain runs (the timed path).  Without
+autocast (the reference's unmodified loop, utils.py:102) the attention runs the true-fp32 general-window kernels
+(attn_win_f32.cu, 1e-5 against the reference's fp64 outputs) between PyTorch LayerNorm / Linear / GELU, the keypoint
+axis padded around every layer: correct, not fast.
 """
 import torch
 import torch.nn as nn
@@ -67,8 +71,8 @@ class MSA(_hw.MSA):
         K = TP_K // TP
         if B_f != B * f or K * TP != TP_K or K > KP_PAD:
             raise ValueError("x must be (B*f, 2*num_kps, d) with num_kps <= 32")
-        if (B * f) % 2:
-            raise _lib.HwgatError("the padded block layout needs an even number of blocks (B*f)")
+        if (B * f) % 2 and _hw._attn_dtype(x) == torch.bfloat16:
+            raise _lib.HwgatError("the padded block layout needs an even number of blocks (B*f) on the bf16 kernels")
         adj = self.adj_mat
         key = (None if attn_mask is None else (attn_mask.data_ptr(), attn_mask._version),
                None if adj is None else (adj.data_ptr(), adj._version), f, x.device)
@@ -81,7 +85,7 @@ class MSA(_hw.MSA):
             bits = ops.mask_pack(a, m, f, TP * KP_PAD, dev)
             self._bits[key] = bits
         xp = _pad_kp(x.reshape(B_f, TP, K, d), 2).reshape(B_f, TP * KP_PAD, d)
-        ctx = ops.window_graph_attention(xp.to(torch.bfloat16), self.qkv.weight, self.qkv.bias, bits, self.num_heads,
+        ctx = ops.window_graph_attention(xp.to(_hw._attn_dtype(x)), self.qkv.weight, self.qkv.bias, bits, self.num_heads,
                                          shift=0, threshold=None, layout=LAYOUT_WINDOWS, frames=f * TP, kps=KP_PAD,
                                          window=KP_PAD, attn_drop=self._attn_p())
         ctx = ctx.reshape(B_f, TP, KP_PAD, d)[:, :, :K].reshape(B_f, TP_K, d)
@@ -131,11 +135,10 @@ class GraphAttentionBlock(_hw.PartAttentionBlock):
 
     def forward(self, x):
         self._check_shape(x)
-        if not self._fusable(_pad_kp(x, 2) if x.shape[2] != KP_PAD else x):
-            raise _lib.HwgatError("HGATE runs on the bf16 kernels only: call it on an fp32 CUDA tensor under "
-                                  "torch.autocast('cuda', dtype=torch.bfloat16) (no fp32 / CPU fallback)")
+        if not x.is_cuda:
+            raise _lib.HwgatError("HGATE runs on the sm_100a kernels only (no CPU fallback)")
         K = x.shape[2]
-        y = super().forward(_pad_kp(x, 2))
+        y = super().forward(_pad_kp(x, 2))       # fused bf16 chain under autocast, the fp32 parity kernels without
         return y[:, :, :K] if K != KP_PAD else y
 
 
@@ -160,11 +163,10 @@ class BlockAttentionLayer(_hw.PartAttentionLayer):
         self.downsample = downsample(dim, temporal_patch_size) if downsample is not None else None
 
     def forward(self, x):
+        if not x.is_cuda:
+            raise _lib.HwgatError("HGATE runs on the sm_100a kernels only (no CPU fallback)")
         K = x.shape[2]
-        xp = _pad_kp(x, 2)
-        if not self.fusable(xp):
-            raise _lib.HwgatError("HGATE runs on the bf16 kernels only (fp32 CUDA tensor under bf16 autocast)")
-        y = self.forward_fused(xp)[0]
+        y = super().forward(_pad_kp(x, 2))       # fused when the shapes / autocast allow it, block by block otherwise
         return y[:, :, :K] if K != KP_PAD else y
 
 
@@ -209,8 +211,6 @@ class Model(_hw.Model):
         return super()._embed_fused(_pad_kp(x, 2))
 
     def forward_features(self, x):
-        if not (x.is_cuda and x.dtype == torch.float32 and _hw._attn_dtype(x) == torch.bfloat16 and self.pe
-                and not x.requires_grad):
-            raise _lib.HwgatError("HGATE runs on the bf16 kernels only: call it on an fp32 CUDA tensor under "
-                                  "torch.autocast('cuda', dtype=torch.bfloat16) (no fp32 / CPU fallback)")
+        if not x.is_cuda:
+            raise _lib.HwgatError("HGATE runs on the sm_100a kernels only (no CPU fallback)")
         return super().forward_features(x)

@@ -246,9 +246,11 @@ class _WindowGraphAttention2(torch.autograd.Function):
     def forward(ctx, xn, w_qkv, b_qkv, bits, threshold, heads, shift, layout, frames, kps, window, save_qkv, attn_p):
         lib = _lib.load()
         _need_cuda(xn, w_qkv, b_qkv, bits)
+        if xn.dtype == torch.float32:
+            return _WindowGraphAttention2._forward_f32(ctx, lib, xn, w_qkv, b_qkv, bits, threshold, heads, shift, layout,
+                                                       frames, kps, window, attn_p)
         if xn.dtype != torch.bfloat16:
-            raise _lib.HwgatError("the general-window attention kernels (K2b / K3b) are bf16 only; the fp32 parity "
-                                  "kernels are built for window_size 16")
+            raise _lib.HwgatError(f"unsupported dtype {xn.dtype}: the kernels take float32 or bfloat16")
         xn_c = xn.contiguous()
         d = xn_c.shape[-1]
         n_tok = xn_c.numel() // d
@@ -274,10 +276,47 @@ class _WindowGraphAttention2(torch.autograd.Function):
         return out.view_as(xn)
 
     @staticmethod
+    def _forward_f32(ctx, lib, xn, w_qkv, b_qkv, bits, threshold, heads, shift, layout, frames, kps, window, attn_p):
+        """the fp32 parity mode (attn_win_f32.cu): window_size 32 / 64, true fp32, qkv always kept"""
+        if attn_p > 0:
+            raise _lib.HwgatError("attention dropout is built into the bf16 kernels only (K2b / K3b)")
+        xn_c = xn.contiguous()
+        d = xn_c.shape[-1]
+        n_tok = xn_c.numel() // d
+        if frames * kps == 0 or n_tok % (frames * kps) != 0:
+            raise ValueError(f"token count {n_tok} is not a multiple of frames*keypoints = {frames * kps}")
+        B = n_tok // (frames * kps)
+        w_c = cast_cached(w_qkv, torch.float32)
+        b_c = cast_cached(b_qkv, torch.float32)
+        out = torch.empty_like(xn_c)
+        qkv = torch.empty((n_tok, 3 * d), dtype=torch.float32, device=xn_c.device)
+        with torch.cuda.device(xn_c.device):
+            check(lib.hwgat_attn2_fwd_f32(xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
+                                          float(threshold), out.data_ptr(), qkv.data_ptr(), B, frames, kps, d, heads,
+                                          window, TEMPORAL_PATCH, shift, layout, _stream()), "hwgat_attn2_fwd_f32")
+        ctx.save_for_backward(xn_c, w_c, b_c, bits, qkv if any(ctx.needs_input_grad[:3]) else None)
+        ctx.meta = (float(threshold), heads, shift, layout, frames, kps, B, d, window, w_qkv.dtype, b_qkv.dtype,
+                    0.0, 0, 0)
+        return out.view_as(xn)
+
+    @staticmethod
     def backward(ctx, d_out):
         lib = _lib.load()
         xn_c, w_c, b_c, bits, qkv = ctx.saved_tensors
         threshold, heads, shift, layout, frames, kps, B, d, window, w_dtype, b_dtype, attn_p, seed, off = ctx.meta
+        if xn_c.dtype == torch.float32:
+            g = d_out.float().contiguous()
+            d_xn = torch.empty_like(xn_c)
+            d_w = torch.empty((3 * d, d), dtype=torch.float32, device=xn_c.device)
+            d_b = torch.empty((3 * d,), dtype=torch.float32, device=xn_c.device)
+            ws_bytes = lib.hwgat_attn2_f32_workspace_bytes(B, frames, kps, d, 1)
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xn_c.device)
+            with torch.cuda.device(xn_c.device):
+                check(lib.hwgat_attn2_bwd_f32(g.data_ptr(), xn_c.data_ptr(), w_c.data_ptr(), qkv.data_ptr(),
+                                              bits.data_ptr(), threshold, d_xn.data_ptr(), d_w.data_ptr(),
+                                              d_b.data_ptr(), ws.data_ptr(), ws.numel(), B, frames, kps, d, heads,
+                                              window, TEMPORAL_PATCH, shift, layout, _stream()), "hwgat_attn2_bwd_f32")
+            return (d_xn.view_as(d_out), d_w.to(w_dtype), d_b.to(b_dtype)) + (None,) * 10
         g = d_out.to(torch.bfloat16).contiguous()
         d_xn = torch.empty_like(xn_c)
         d_w = torch.empty((3 * d, d), dtype=torch.float32, device=xn_c.device)

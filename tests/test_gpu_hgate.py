@@ -111,9 +111,69 @@ def test_hgate_model_vs_reference_golden_and_oracle_gradients(golden_dir):
     assert rel_l2(out, ref1) < BF16_TOL
 
 
-def test_hgate_fp32_is_refused():
+@pytest.mark.parametrize("d,h", [(128, 2), (256, 4)])
+@pytest.mark.parametrize("shift", [0, 1])
+def test_hgate_fp32_msa_vs_reference_golden(golden_dir, d, h, shift):
+    """MSA.forward without autocast: the true-fp32 general-window kernels (attn_win_f32.cu) on HGATE's 58-token blocks
+    stored as 64, against the reference's fp64 outputs: 1e-5"""
+    from sl_hwgat_b200.models import HGATE
+    G = np.load(os.path.join(golden_dir, "hgate.npz"))
+    key = f"d{d}_s{shift}"
+    B, F = 2, 4
+    std = 0.2 if d == 128 else 0.1
+    rng = np.random.default_rng(5000 + d + 10 * shift)
+    xn = torch.from_numpy(rng.standard_normal((B, F, 29, d)))
+    w = torch.from_numpy(rng.standard_normal((3 * d, d)) * std)
+    b = torch.from_numpy(rng.standard_normal((3 * d,)) * 0.1)
+    g = torch.from_numpy(rng.standard_normal((B, F, 29, d)))
+    adj = torch.from_numpy(G["adj"].astype(np.float32)).cuda()
+    blk = HGATE.GraphAttentionBlock(dim=d, num_kps=29, num_heads=h, temporal_patch_size=2, temporal_dim=F,
+                                    shift_size=shift, adj_mat=adj, drop=0.0).cuda()
+    msa = blk.attn
+    with torch.no_grad():
+        msa.qkv.weight.copy_(w); msa.qkv.bias.copy_(b)
+        msa.proj.weight.copy_(torch.eye(d)); msa.proj.bias.zero_()
+    x_ = xn.float().cuda().requires_grad_(True)
+    xs = torch.roll(x_, shifts=-shift, dims=1) if shift else x_
+    yb = msa(HGATE.block_partition(xs, 2), B, F // 2, attn_mask=blk.attn_mask)
+    y = HGATE.block_reverse(yb, 2, F, 29)
+    y = torch.roll(y, shifts=shift, dims=1) if shift else y
+    assert y.dtype == torch.float32
+    (y * g.float().cuda()).sum().backward()
+
+    def chk(t, name, stride):
+        a = t.detach().double().cpu().reshape(-1).numpy()[::stride]
+        ref = G[key + "_" + name]
+        return float(np.abs(a - ref).max() / np.abs(ref).max())
+    errs = (chk(y, "y", 53), chk(x_.grad, "dx", 53), chk(msa.qkv.weight.grad, "dw", 251), chk(msa.qkv.bias.grad, "db", 1))
+    print(key, "HGATE fp32 max-rel y/dx/dw/db:", errs)
+    assert max(errs) < 1e-5, errs
+
+
+def test_hgate_fp32_model_vs_reference_golden(golden_dir):
+    """the drop-in model called without autocast (utils.py:102): logits, loss and every gradient against the
+    reference's fp64 run"""
+    G = np.load(os.path.join(golden_dir, "hgate.npz"))
+    m, cfg, sd, p = build()
+    m.train()                                    # drop 0
+    x = H.synthetic_keypoints(2, 16, seed=1001).cuda()
+    y = torch.tensor([3, 7]).cuda()
+    logits = m(x)
+    assert logits.dtype == torch.float32
+    loss = O.smoothed_cross_entropy(logits, y)
+    loss.backward()
+    assert rel_inf(logits, torch.from_numpy(G["model_logits"])) < 1e-5
+    assert abs(loss.item() - float(G["model_loss"])) < 1e-5 * abs(float(G["model_loss"]))
+    grads = dict(m.named_parameters())
+    for name, norm, head in zip(G["gnames"], G["gnorms"], G["gheads"]):
+        gr = grads[str(name)].grad.double().cpu()
+        assert abs(gr.norm().item() - norm) <= 1e-4 * norm, name
+        assert np.abs(gr.reshape(-1)[:4].numpy() - head).max() <= 1e-4 * max(np.abs(head).max(), 1e-12) + 1e-9, name
+
+
+def test_hgate_cpu_is_refused():
     from sl_hwgat_b200 import _lib
     m, cfg, sd, p = build()
     m.eval()
     with pytest.raises(_lib.HwgatError):
-        m(H.synthetic_keypoints(2, 16, seed=1).cuda())          # no autocast: fp32 -> no kernels for 64-token blocks
+        m.cpu()(H.synthetic_keypoints(2, 16, seed=1))

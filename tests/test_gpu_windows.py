@@ -234,15 +234,94 @@ def test_model_larger_windows_gradients_vs_oracle(W):
     assert worst[0][1] < 8e-2, worst
 
 
-def test_fp32_larger_window_is_refused():
-    """the fp32 parity kernels are built for W = 16 only: other windows raise instead of falling back"""
+def test_unsupported_window_is_refused():
+    """windows other than 16 / 32 / 64 raise instead of falling back"""
     from sl_hwgat_b200 import _lib, ops
     xn, w, b, g = seeded(128, 0, 32)
     with pytest.raises(_lib.HwgatError):
-        ops.window_graph_attention(xn.float().cuda(), w.float().cuda(), b.float().cuda(), dev_bits(32, 4, 0), 2, window=32)
-    with pytest.raises(_lib.HwgatError):
         ops.window_graph_attention(xn.to(torch.bfloat16).cuda(), w.float().cuda(), b.float().cuda(), dev_bits(32, 4, 0),
                                    2, window=8)
+
+
+# ------------------------------------------------------------------ fp32 parity mode for window_size 32 / 64
+def run_f32(xn, w, b, g, heads, shift, thr, W, layout=0):
+    from sl_hwgat_b200 import ops
+    F = xn.shape[1]
+    bits = dev_bits(W, F, shift)
+    x_ = xn.float().cuda().requires_grad_(True)
+    w_ = w.float().cuda().requires_grad_(True)
+    b_ = b.float().cuda().requires_grad_(True)
+    y = ops.window_graph_attention(x_, w_, b_, bits, heads, shift=shift, threshold=thr, layout=layout, window=W)
+    assert y.dtype == torch.float32
+    y.backward(g.float().cuda())
+    return y.detach(), x_.grad, w_.grad, b_.grad
+
+
+@pytest.mark.parametrize("W", [32, 64])
+@pytest.mark.parametrize("d,h", [(128, 2), (256, 4)])
+@pytest.mark.parametrize("shift", [0, 1])
+@pytest.mark.parametrize("thr", [None, 0.04])
+def test_f32_larger_window_attention_vs_reference_golden(golden_dir, W, d, h, shift, thr):
+    """attn_win_f32.cu against the unmodified reference (fp64) run with window_size W, eval and train (threshold drop):
+    1e-5, the north_star's fp32 tolerance"""
+    G = np.load(os.path.join(golden_dir, "larger_windows.npz"))
+    key = f"W{W}_d{d}_s{shift}_thr{thr}"
+    xn, w, b, g = seeded(d, shift, W)
+    y, dx, dw, db = run_f32(xn, w, b, g, h, shift, thr, W)
+
+    def chk(t, name, stride):
+        a = t.detach().double().cpu().reshape(-1).numpy()[::stride]
+        ref = G[key + "_" + name]
+        return float(np.abs(a - ref).max() / np.abs(ref).max())
+    errs = (chk(y, "y", 61), chk(dx, "dx", 61), chk(dw, "dw", 251), chk(db, "db", 1))
+    print(key, "fp32 max-rel y/dx/dw/db:", errs)
+    assert max(errs) < 1e-5, errs
+
+
+@pytest.mark.parametrize("W", [32, 64])
+def test_f32_larger_window_fully_masked_rows_and_windows_layout(W):
+    """a threshold below 1/N drops every logit (uniform rows); LAYOUT_WINDOWS equals LAYOUT_BFKD on the partitioned
+    tensor"""
+    from sl_hwgat_b200 import ops
+    xn, w, b, g = seeded(128, 0, W, std=0.02)
+    y, dx, dw, db = run_f32(xn, w, b, g, 2, 0, 0.001, W)
+    by, bdx, bdw, bdb = oracle_points(xn, w, b, g, 2, 4, 0, 0.001, W, bf16_points=False)
+    # dead rows: no logit gradient (dQ = dK = 0); the value path (uniform P) still carries one
+    assert rel_inf(y, by) < 1e-5 and rel_inf(dx, bdx) < 1e-5 and rel_inf(dw, bdw) < 1e-5
+    xn, w, b, g = seeded(128, 0, W, B=2)
+    y0, dx0, dw0, db0 = run_f32(xn, w, b, g, 2, 0, 0.04, W)
+    xw, gw = O.window_partition(xn, W, 2), O.window_partition(g, W, 2)
+    F = xn.shape[1]
+    bits = dev_bits(W, F, 0)
+    x_ = xw.float().cuda().requires_grad_(True)
+    yw = ops.window_graph_attention(x_, w.float().cuda(), b.float().cuda(), bits, 2, threshold=0.04,
+                                    layout=ops.LAYOUT_WINDOWS, frames=F, kps=64, window=W)
+    yw.backward(gw.float().cuda())
+    assert torch.equal(O.window_partition(y0.cpu().double(), W, 2).float(), yw.detach().cpu())
+    assert torch.equal(O.window_partition(dx0.cpu().double(), W, 2).float(), x_.grad.cpu())
+
+
+@pytest.mark.parametrize("W", [32, 64])
+def test_f32_model_larger_windows_vs_reference_golden(golden_dir, W):
+    """the drop-in model with window_size W called without autocast: the fp32 parity kernels end to end"""
+    G = np.load(os.path.join(golden_dir, "larger_windows.npz"))
+    m, cfg, sd = build_w(W)
+    x = O.synthetic_keypoints(2, 16, 2, seed=1001).cuda()
+    m.eval()
+    with torch.no_grad():
+        ev = m(x)
+    assert ev.dtype == torch.float32
+    assert rel_inf(ev, torch.from_numpy(G[f"model_W{W}_eval_logits"])) < 1e-5
+    m.train()
+    thr = [0.03, 0.05, 0.031, 0.2, 0.033, 0.04, 0.0312, 0.1]
+    it = iter(thr)
+    real = torch.rand
+    torch.rand = lambda *a, **k: torch.tensor([next(it)])
+    try:
+        tr = m(x)
+    finally:
+        torch.rand = real
+    assert rel_inf(tr, torch.from_numpy(G[f"model_W{W}_train_logits"])) < 1e-5
 
 
 # ------------------------------------------------------------------ attention dropout (self.attn_drop, HWGATE.py:112)
