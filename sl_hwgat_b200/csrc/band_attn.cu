@@ -41,7 +41,6 @@ typedef __nv_bfloat16 bf16;
 
 namespace band {
 
-constexpr int kThreads = 256;
 constexpr int kRowBytes = 128;          // 64 bf16 columns of one token per CTA
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -56,10 +55,14 @@ struct BandArgs {
   int pf_dist;           // L2 prefetch distance in work items (0 = off): the items of the next wave of CTAs
 };
 
-template <int W>
+// FRAMES = frames per CTA, one warp per (frame, 16-query tile).  Forward: 8 warps.  Backward at W = 16: 6 frames / 6
+// warps - 69 KB of shared memory and <= 113 registers let a THIRD CTA share the SM (8 frames: 86 KB, two CTAs), and
+// three CTAs overlap the load -> compute -> store phases of an item better than two.
+template <int W, int FRAMES = 8 / (W / 16)>
 struct Cfg {
   static constexpr int MT = W / 16;          // 16-query tiles per frame
-  static constexpr int FR = 8 / MT;          // frames per CTA (one warp per (frame, tile))
+  static constexpr int FR = FRAMES;          // frames per CTA
+  static constexpr int kThreads = 32 * FR * MT;
   static constexpr int NSLOT = FR + 2;       // + one halo frame on each side
   static constexpr int kTensor = W * kRowBytes;          // one frame of one tensor
   static constexpr int kAll = NSLOT * kTensor;            // one tensor, all staged frames = one TMA box
@@ -121,9 +124,8 @@ HW_DEV void load_b_kn(uint32_t (&r)[4], uint32_t base, int row0, int chunk0, int
 struct Item {
   int b, w, f0, cc;
 };
-template <int W>
+template <int W, typename C>
 HW_DEV Item decode_item(const BandArgs& p, int i) {
-  using C = Cfg<W>;
   const int nchunks = (p.F + C::FR - 1) / C::FR, ncc = p.d / 64, nW = p.K / W;
   Item it;
   it.f0 = (i % nchunks) * C::FR; i /= nchunks;
@@ -134,7 +136,7 @@ HW_DEV Item decode_item(const BandArgs& p, int i) {
 }
 
 // the words of window w into shared memory; kDiag: hold the host to its promise
-template <int W, bool kDiag>
+template <int W, bool kDiag, int kThreads>
 HW_DEV void load_bits(uint32_t* sbits, const BandArgs& p, int w, int tid) {
   for (int i = tid; i < W * 3; i += kThreads) {
     const uint32_t v = p.bits[w * W * 3 + i];
@@ -159,9 +161,10 @@ HW_DEV void diag_frag(uint32_t (&a)[4], float v0, float v1, int g) {   // A frag
 // K15 forward
 // ---------------------------------------------------------------------------------------------------------------------
 template <int W, int HD, bool kDiag>
-__global__ void __launch_bounds__(kThreads, kDiag ? 3 : 2)
+__global__ void __launch_bounds__(Cfg<W>::kThreads, kDiag ? 3 : 2)
 band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const BandArgs p) {
   using C = Cfg<W>;
+  constexpr int kThreads = C::kThreads;
   constexpr int KS = HD / 16, HPC = 64 / HD, CH = HD / 8, NTF = W / 8;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -169,14 +172,14 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const BandArgs p
   uint64_t* bar = reinterpret_cast<uint64_t*>(sbits + W * 3);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const Item it = decode_item<W>(p, blockIdx.x);
+  const Item it = decode_item<W, C>(p, blockIdx.x);
 
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmQKV);
   }
-  load_bits<W, kDiag>(sbits, p, it.w, tid);
+  load_bits<W, kDiag, kThreads>(sbits, p, it.w, tid);
   __syncthreads();
   if (tid == 0) {   // q, k, v of frames f0-1 .. f0+FR: three boxes of (64 columns, W keypoints, FR+2 frames)
     mbar_expect_tx(bar, 3 * C::kAll);
@@ -185,7 +188,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const BandArgs p
     // Pull the boxes of the item a CTA of the NEXT wave will work on into L2: with 2 - 3 resident CTAs per SM the
     // load phase that opens an item is exposed latency, and an L2 hit shortens it.
     if (p.pf_dist > 0 && blockIdx.x + p.pf_dist < gridDim.x) {
-      const Item nx = decode_item<W>(p, blockIdx.x + p.pf_dist);
+      const Item nx = decode_item<W, C>(p, blockIdx.x + p.pf_dist);
 #pragma unroll
       for (int t = 0; t < 3; ++t) tma_prefetch_4d(&tmQKV, t * p.d + nx.cc * 64, nx.w * W, nx.f0 - 1, nx.b);
     }
@@ -356,11 +359,17 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const BandArgs p
 // ---------------------------------------------------------------------------------------------------------------------
 // K16 backward
 // ---------------------------------------------------------------------------------------------------------------------
+template <int W>
+struct BwdCfg : Cfg<W, W == 16 ? 6 : 4> {
+  static constexpr int kCtasPerSm = W == 16 ? 3 : 2;
+};
+
 template <int W, int HD, bool kDiag>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(BwdCfg<W>::kThreads, BwdCfg<W>::kCtasPerSm)
 band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                      const __grid_constant__ CUtensorMap tmO, const BandArgs p) {
-  using C = Cfg<W>;
+  using C = BwdCfg<W>;
+  constexpr int kThreads = C::kThreads;
   constexpr int KS = HD / 16, HPC = 64 / HD, CH = HD / 8, NTF = W / 8;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -370,7 +379,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint64_t* bar = reinterpret_cast<uint64_t*>(sbits + W * 3);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const Item it = decode_item<W>(p, blockIdx.x);
+  const Item it = decode_item<W, C>(p, blockIdx.x);
   const int d3 = 3 * p.d;
 
   if (tid == 0) {
@@ -380,7 +389,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmO);
   }
-  load_bits<W, kDiag>(sbits, p, it.w, tid);
+  load_bits<W, kDiag, kThreads>(sbits, p, it.w, tid);
   __syncthreads();
   if (tid == 0) {   // q, k, v, dO of frames f0-1 .. f0+FR
     mbar_expect_tx(bar, 4 * C::kAll);
@@ -388,7 +397,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     for (int t = 0; t < 3; ++t) tma_load_4d(smem + t * C::kAll, &tmQKV, bar, t * p.d + it.cc * 64, it.w * W, it.f0 - 1, it.b);
     tma_load_4d(smem + 3 * C::kAll, &tmDO, bar, it.cc * 64, it.w * W, it.f0 - 1, it.b);
     if (p.pf_dist > 0 && blockIdx.x + p.pf_dist < gridDim.x) {   // next wave's boxes -> L2 (see the forward)
-      const Item nx = decode_item<W>(p, blockIdx.x + p.pf_dist);
+      const Item nx = decode_item<W, C>(p, blockIdx.x + p.pf_dist);
 #pragma unroll
       for (int t = 0; t < 3; ++t) tma_prefetch_4d(&tmQKV, t * p.d + nx.cc * 64, nx.w * W, nx.f0 - 1, nx.b);
       tma_prefetch_4d(&tmDO, nx.cc * 64, nx.w * W, nx.f0 - 1, nx.b);
@@ -396,17 +405,19 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
   }
   // while the boxes fly: O through registers (delta = rowsum(dO * O) per head) and the saved logsumexp
-  constexpr int kPasses = C::NSLOT * W * 8 / kThreads;
-  static_assert(C::NSLOT * W * 8 % kThreads == 0, "uniform trip count for the shuffles below");
+  // staged rows per pass = kThreads / 8; the last pass may be partial: whole warps drop out (4 rows per warp, row
+  // count a multiple of 4), so the shuffles below stay warp-uniform
+  constexpr int kRows = C::NSLOT * W, kPasses = (kRows * 8 + kThreads - 1) / kThreads;
+  static_assert(kRows % 4 == 0 && kThreads % 32 == 0, "warp-uniform tail");
   const long long tok_base = (long long)it.b * p.F * p.K + it.w * W;      // token (b, frame 0, first keypoint of w)
   const bf16* oo_base = p.ctx + tok_base * p.d + it.cc * 64;
   int4 oo[kPasses];
 #pragma unroll
   for (int ps = 0; ps < kPasses; ++ps) {
-    const int srow = ps * 32 + (tid >> 3), chunk = tid & 7;                // staged row = slot * W + keypoint
+    const int srow = ps * (kThreads / 8) + (tid >> 3), chunk = tid & 7;    // staged row = slot * W + keypoint
     const int frame = it.f0 - 1 + srow / W;
-    oo[ps] = (unsigned)frame < (unsigned)p.F ? ld_stream16(oo_base + (frame * p.K + srow % W) * p.d + chunk * 8)
-                                             : make_int4(0, 0, 0, 0);
+    oo[ps] = srow < kRows && (unsigned)frame < (unsigned)p.F
+                 ? ld_stream16(oo_base + (frame * p.K + srow % W) * p.d + chunk * 8) : make_int4(0, 0, 0, 0);
   }
   for (int i = tid; i < C::NSLOT * W * HPC; i += kThreads) {
     const int hh = i % HPC, srow = i / HPC;
@@ -417,7 +428,8 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   mbar_wait(bar, 0);
 #pragma unroll
   for (int ps = 0; ps < kPasses; ++ps) {
-    const int srow = ps * 32 + (tid >> 3), chunk = tid & 7;
+    const int srow = ps * (kThreads / 8) + (tid >> 3), chunk = tid & 7;
+    if (srow >= kRows) break;                                               // warp-uniform
     const int4 go = *reinterpret_cast<const int4*>(smem + 3 * C::kAll + swz(srow, chunk));
     const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&go);
     const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&oo[ps]);
@@ -641,24 +653,24 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 }
 
 // One wave of resident CTAs ahead (occupancy x SMs), per device and kernel; HWGAT_BAND_PREFETCH=0 switches it off
-static int prefetch_distance(const void* kernel, int smem) {
+static int prefetch_distance(const void* kernel, int threads, int smem) {
   static const bool off = [] { const char* e = getenv("HWGAT_BAND_PREFETCH"); return e && e[0] == '0'; }();
   if (off) return 0;
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
   return per_sm * sms;
 }
 
 constexpr int kMaxDevices = 64;
-static int cached_prefetch_distance(int* cache, const void* kernel, int smem) {
+static int cached_prefetch_distance(int* cache, const void* kernel, int threads, int smem) {
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= kMaxDevices) return prefetch_distance(kernel, smem);
+  if (dev < 0 || dev >= kMaxDevices) return prefetch_distance(kernel, threads, smem);
   int v = __atomic_load_n(&cache[dev], __ATOMIC_RELAXED);
   if (v == 0) {
-    v = prefetch_distance(kernel, smem) + 1;     // stored + 1 so that "prefetch off" (0) is cached too
+    v = prefetch_distance(kernel, threads, smem) + 1;     // stored + 1 so that "prefetch off" (0) is cached too
     __atomic_store_n(&cache[dev], v, __ATOMIC_RELAXED);
   }
   return v - 1;
@@ -677,14 +689,14 @@ static int launch_fwd(const BandArgs& p, const bf16* qkv, cudaStream_t s) {
   if ((st = make_tmap_4d(&tm, qkv, (uint64_t)3 * p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
   BandArgs q = p;
   static int pf_cache[kMaxDevices];          // occupancy x SMs of this instantiation, per device (0 = not asked yet)
-  q.pf_dist = cached_prefetch_distance(pf_cache, (const void*)band_attn_fwd_kernel<W, HD, kDiag>, smem);
-  band_attn_fwd_kernel<W, HD, kDiag><<<(unsigned)grid, kThreads, smem, s>>>(tm, q);
+  q.pf_dist = cached_prefetch_distance(pf_cache, (const void*)band_attn_fwd_kernel<W, HD, kDiag>, C::kThreads, smem);
+  band_attn_fwd_kernel<W, HD, kDiag><<<(unsigned)grid, C::kThreads, smem, s>>>(tm, q);
   count_launch();
   return (int)cudaGetLastError();
 }
 template <int W, int HD, bool kDiag>
 static int launch_bwd(const BandArgs& p, const bf16* qkv, const bf16* d_out, cudaStream_t s) {
-  using C = Cfg<W>;
+  using C = BwdCfg<W>;
   constexpr int HPC = 64 / HD;
   constexpr int smem = 4 * C::kAll + 2 * C::NSLOT * W * HPC * 4 + W * 3 * 4 + 16 + 1024;
   static PerDeviceOnce once;
@@ -698,8 +710,8 @@ static int launch_bwd(const BandArgs& p, const bf16* qkv, const bf16* d_out, cud
   if ((st = make_tmap_4d(&tmo, p.ctx, (uint64_t)p.d, (uint64_t)p.K, (uint64_t)p.F, (uint64_t)p.B, W, C::NSLOT))) return st;
   BandArgs q = p;
   static int pf_cache[kMaxDevices];
-  q.pf_dist = cached_prefetch_distance(pf_cache, (const void*)band_attn_bwd_kernel<W, HD, kDiag>, smem);
-  band_attn_bwd_kernel<W, HD, kDiag><<<(unsigned)grid, kThreads, smem, s>>>(tm, tmdo, tmo, q);
+  q.pf_dist = cached_prefetch_distance(pf_cache, (const void*)band_attn_bwd_kernel<W, HD, kDiag>, C::kThreads, smem);
+  band_attn_bwd_kernel<W, HD, kDiag><<<(unsigned)grid, C::kThreads, smem, s>>>(tm, tmdo, tmo, q);
   count_launch();
   return (int)cudaGetLastError();
 }
