@@ -13,8 +13,8 @@
 //
 // Roofline: HBM.  Per token the forward reads q, k, v (3 d bf16) and writes ctx (d bf16) [+ 4 B * heads of logsumexp in
 // training]; the backward reads q, k, v, dO, ctx (5 d) and writes dQ, dK, dV (3 d).  Measured alone on the WGATE step
-// shape (ncu, profiles/r02o_band_wgate.md): DRAM traffic = those bytes; forward 65 %, backward 47 % of the HBM rate, the
-// backward limited by instruction issue (735 warp instructions per 16 tokens per head), not by memory.
+// shape (ncu, profiles/r02o_band_wgate.md): DRAM traffic = those bytes; forward 67 %, backward 56 % of the HBM rate, the
+// backward limited by instruction issue (~700 warp instructions per 16 tokens per head), not by memory.
 // The tensor work (mma.sync m16n8k16, 12 - 42 instructions per 16 tokens per head) is two orders of magnitude under the
 // pipe's rate, so legacy HMMA on register fragments is the right tool: a tcgen05 tile (M = 128, operands through smem
 // descriptors, accumulator in TMEM) would add latency and synchronisation to blocks of 16 x 48 logits.
