@@ -64,13 +64,24 @@ CONFIGS = {
     "gate_train512": ("train", 64, 262, 512, 32,
                       "sibling model GATE (hwgat/models/GATE.py): training fwd+bwd, T=64 frames x 29 keypoints x 2, "
                       "262 classes, 8 blocks, d=128, 8 heads, attention over all 1856 tokens, dropout 0.1"),
+    # The reference's own loop (utils.py:102, 128): fp32, NO autocast.  The drop-in then runs its fp32 path, whose GEMMs
+    # are six bf16 tcgen05 products of hi / mid / lo planes (the "x3" mode, csrc/gemm_x3.cu; HWGAT_FP32=ffma selects
+    # the true-fp32 FFMA kernels instead).  The incumbent beside it is gpu_eager_baseline.fp32.
+    "train128_fp32": ("train", 64, 262, 128, 16,
+                      "the reference's unmodified fp32 loop (no autocast): HWGATE training fwd+bwd, T=64, 262 classes, "
+                      "128 sequences per GPU, train mode (threshold drop + dropout 0.1), fp32 tensors end to end"),
+    "infer256_fp32": ("infer", 64, 262, 256, 16,
+                      "the reference's unmodified fp32 evaluation (no autocast): HWGATE eval forward, T=64, 262 classes, "
+                      "256 sequences per GPU, fp32 tensors end to end"),
 }
 MODEL = "HWGATE"
+AMP = True          # bf16 autocast around the forward (every config but the *_fp32 ones)
 
 
 def set_config(name):
-    global T_FRAMES, CLASSES, WINDOW, METRIC, MODEL, KPS
+    global T_FRAMES, CLASSES, WINDOW, METRIC, MODEL, KPS, AMP
     mode, T_FRAMES, CLASSES, batch, WINDOW, what = CONFIGS[name]
+    AMP = not name.endswith("_fp32")
     MODEL = {"hgate": "HGATE", "wgate": "WGATE", "gate": "GATE"}.get(name.split("_")[0], "HWGATE")
     KPS = 32 if MODEL in ("HGATE", "GATE") else 64          # stored keypoints per frame
     METRIC = "HWGAT sequences/sec fwd+bwd" if mode == "train" else "HWGAT sequences/sec inference forward"
@@ -439,6 +450,14 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _fp32_mode():
+    try:
+        from sl_hwgat_b200 import ops
+        return ops.fp32_mode()
+    except Exception:      # the CPU reference arm runs without the library
+        return "n/a"
+
+
 def workload_config(n_gpus, per_gpu_batch, what, mode, strong):
     par = "single GPU"
     if n_gpus > 1:
@@ -447,6 +466,7 @@ def workload_config(n_gpus, per_gpu_batch, what, mode, strong):
     return {"workload": what, "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * n_gpus,
             "frames": T_FRAMES, "window_size": WINDOW, "tokens_per_window": 2 * WINDOW, "parallelism": par,
             "scaling_mode": "strong (fixed global batch)" if strong else "weak (fixed per-GPU batch)",
+            "precision": "bf16 autocast" if AMP else "fp32, no autocast (fp32 mode %s)" % _fp32_mode(),
             "l2": "activations per block (>= 0.5 GB) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -509,13 +529,13 @@ def main():
 
     def step(xd, yd):
         if not train:
-            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=AMP):
                 return model(xd)
         if sync is not None:
             sync.zero_grad()
         else:
             model.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=AMP):
             logits = model(xd)
         loss = criterion(logits, yd)
         loss.backward()
@@ -556,7 +576,7 @@ def main():
         t_end = torch.cuda.Event(enable_timing=True)
         sync.zero_grad()
         t0.record()
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=AMP):
             logits = model(x_dev)
         loss = criterion(logits, y_dev)
         loss.backward()
@@ -618,7 +638,8 @@ def main():
         line = {"metric": METRIC, "value": B * world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
-                "dtype": "bf16", "data": "synthetic", "config": workload_config(world, B, what, mode, args.strong),
+                "dtype": "bf16" if AMP else "f32", "data": "synthetic",
+                "config": workload_config(world, B, what, mode, args.strong),
                 "e2e": {"value": B * world * args.steps / (ms2 * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if train else B * 8,
                         "ms_per_step": ms2 / args.steps, "last_loss" if train else "last_pred": last},
@@ -636,8 +657,10 @@ def main():
             try:
                 line["gpu_eager_baseline"] = gpu_eager_baseline(dev, mode, min(B, 128))
                 eb = line["gpu_eager_baseline"].get("bf16_autocast") or line["gpu_eager_baseline"].get("fp32")
-                if eb:
+                if eb and AMP:
                     line["speedup_vs_gpu_eager_bf16"] = line["value"] / eb["value"]
+                if not AMP and line["gpu_eager_baseline"].get("fp32"):
+                    line["speedup_vs_gpu_eager_fp32"] = line["value"] / line["gpu_eager_baseline"]["fp32"]["value"]
             except Exception as exc:      # a reported baseline must not take the bench line down with it
                 line["gpu_eager_baseline"] = {"error": repr(exc)[:300]}
         if world == 1 and not args.no_cpu_baseline:

@@ -352,8 +352,22 @@ unsigned long long hwgat_launch_count(void);
  * bit-reproducible; PARAMETER gradients are by default summed with fp32 atomics over a token split (order varies run
  * to run, ~1e-6 relative).  on != 0: every token split of the weight-gradient GEMMs and every CTA of the bias /
  * LayerNorm column sums writes its own partial and a finish kernel adds them in index order: bit-reproducible.
- * In this mode (only) the library takes stream-ordered scratch from cudaMallocAsync / cudaFreeAsync.              */
+ * In this mode (only) the library takes stream-ordered scratch from cudaMallocAsync / cudaFreeAsync.  on < 0 only
+ * queries.                                                                                                       */
 int hwgat_set_deterministic(int on);
+
+/* How the fp32 path (dtype HWGAT_F32, hwgat_linear_f32_*, the *_f32 attention entries) multiplies matrices
+ * (process-wide; returns the previous mode; any other value only queries).  The reference's own loop runs the model in
+ * fp32 without autocast (utils.py:102, 128; inference.py:95), so this is the mode a drop-in lands on.
+ *   HWGAT_FP32_FFMA  true-fp32 FFMA GEMMs: the 1e-5 parity mode (default of the library).
+ *   HWGAT_FP32_X3    every fp32 GEMM with n % 128 == 0, d_in % 128 == 0, d_out % 128 == 0 runs on tcgen05: the operands
+ *                    are split into three bf16 planes (hi + mid + lo = 24 mantissa bits) and the six partial products of
+ *                    weight >= 2^-16 are accumulated in fp32 in TMEM, the leading product in an accumulator of its own
+ *                    (gemm_x3.cu).  ~2e-7 relative against fp64, the level of an fp32 GEMM.  Takes stream-ordered
+ *                    scratch for the planes (cudaMallocAsync).  Other shapes, and deterministic mode, use FFMA.     */
+#define HWGAT_FP32_FFMA 0
+#define HWGAT_FP32_X3 1
+int hwgat_set_fp32_mode(int mode);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,9 @@ LIB_PATH = os.environ.get("HWGAT_B200_LIB") or os.path.join(HERE, "lib", "libhwg
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 18
+ABI_VERSION = 19
+FP32_MODES = {"ffma": 0, "x3": 1}      # HWGAT_FP32_FFMA / HWGAT_FP32_X3 (include/hwgat_b200.h)
+FP32_DEFAULT = "x3"        # the package default; the C library itself starts in FFMA mode
 
 # name -> (restype, argtypes); must list every symbol of include/hwgat_b200.h
 SIGNATURES = {
@@ -30,6 +32,7 @@ SIGNATURES = {
     "hwgat_band_attn_bwd": (c_int, [c_int] + [c_void_p] * 11 + [c_size_t] + [c_int] * 7 + [c_void_p]),
     "hwgat_launch_count": (c_ulonglong, []),
     "hwgat_set_deterministic": (c_int, [c_int]),
+    "hwgat_set_fp32_mode": (c_int, [c_int]),
     "hwgat_adjacency_build": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hwgat_mask_build": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hwgat_mask_pack": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
@@ -109,6 +112,10 @@ def load() -> ctypes.CDLL:
         raise HwgatError(f"libhwgat_b200 ABI {got}, binding expects {ABI_VERSION}: rebuild the library")
     if os.environ.get("HWGAT_DETERMINISTIC", "0") not in ("", "0"):   # see ops.set_deterministic
         lib.hwgat_set_deterministic(1)
+    mode = os.environ.get("HWGAT_FP32", FP32_DEFAULT).lower()          # see ops.set_fp32_mode
+    if mode not in FP32_MODES:
+        raise HwgatError(f"HWGAT_FP32={mode!r}: expected one of {sorted(FP32_MODES)}")
+    lib.hwgat_set_fp32_mode(FP32_MODES[mode])
     _lib = lib
     return lib
 

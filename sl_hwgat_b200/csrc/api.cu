@@ -30,7 +30,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 18; }
+int hwgat_version(void) { return 19; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -48,7 +48,14 @@ const char* hwgat_error_string(int status) {
 
 unsigned long long hwgat_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
-int hwgat_set_deterministic(int on) { return __atomic_exchange_n(&g_deterministic, on ? 1 : 0, __ATOMIC_RELAXED); }
+int hwgat_set_fp32_mode(int mode) {
+  if (mode != HWGAT_FP32_FFMA && mode != HWGAT_FP32_X3) return __atomic_load_n(&g_fp32_mode, __ATOMIC_RELAXED);
+  return __atomic_exchange_n(&g_fp32_mode, mode, __ATOMIC_RELAXED);
+}
+int hwgat_set_deterministic(int on) {
+  if (on < 0) return __atomic_load_n(&g_deterministic, __ATOMIC_RELAXED);   // query
+  return __atomic_exchange_n(&g_deterministic, on ? 1 : 0, __ATOMIC_RELAXED);
+}
 
 int hwgat_adjacency_build(const int32_t* edges, int n_edges, int nW, int W, int TP, float* adj,
                           hwgat_stream_t stream) {

@@ -312,6 +312,7 @@ int qkv_weight_grads_f32(const float* dqkv, const float* xn, const float* w_qkv,
                                 float* d_b, long long n, int d, cudaStream_t s) {
   const int d3 = 3 * d;
   int st;
+  if (x3_enabled() && x3_supported(n, d, d3)) return linear_f32_bwd(dqkv, xn, w_qkv, d_xn, d_w, d_b, (int)n, d, d3, s);
   // d_xn = dQKV . Wqkv        [n, 3d] x [3d, d]
   dim3 g1((d + 63) / 64, (unsigned)((n + 63) / 64), 1);
   gemm_f32_kernel<false, false, false, false><<<g1, 256, 0, s>>>(dqkv, w_qkv, nullptr, d_xn, (int)n, d, d3, d3);
@@ -343,11 +344,7 @@ int attn_fwd_f32(const AttnArgs& a, cudaStream_t s) {
   const long long n = (long long)a.B * a.F * a.K;
   const int d = a.d;
   float* qkv = (float*)a.workspace;
-  dim3 gg((3 * d + 63) / 64, (unsigned)((n + 63) / 64), 1);
-  gemm_f32_kernel<false, true, false, true><<<gg, 256, 0, s>>>((const float*)a.xn, (const float*)a.w_qkv, a.b_qkv, qkv,
-                                                               (int)n, 3 * d, d, d);
-  count_launch();
-  int st = check_last();
+  int st = linear_f32_fwd((const float*)a.xn, (const float*)a.w_qkv, a.b_qkv, qkv, (int)n, d, 3 * d, s);
   if (st) return st;
   TileGeom g = make_geom(a.F, a.K, d, a.shift, a.layout);
   size_t smem = 4 * sizeof(CoreSmemF32);
@@ -363,11 +360,7 @@ int attn_bwd_f32(const AttnArgs& a, cudaStream_t s) {
   float* qkv = (float*)a.workspace;
   float* dqkv = qkv + n * d3;
   int st;
-  dim3 gg((d3 + 63) / 64, (unsigned)((n + 63) / 64), 1);
-  gemm_f32_kernel<false, true, false, true><<<gg, 256, 0, s>>>((const float*)a.xn, (const float*)a.w_qkv, a.b_qkv, qkv,
-                                                               (int)n, d3, d, d);
-  count_launch();
-  if ((st = check_last())) return st;
+  if ((st = linear_f32_fwd((const float*)a.xn, (const float*)a.w_qkv, a.b_qkv, qkv, (int)n, d, d3, s))) return st;
   TileGeom g = make_geom(a.F, a.K, d, a.shift, a.layout);
   constexpr int kWarps = 4;
   size_t smem = kWarps * sizeof(CoreSmemF32Bwd);
@@ -534,10 +527,7 @@ int band_attn_fwd_f32(const float* xn, const float* w_qkv, const float* b_qkv, c
   const long long n = (long long)B * F * K;
   const int hd = d / heads;
   if ((n + 63) / 64 > 65535) return HWGAT_ERR_UNSUPPORTED;          // gemm_f32_kernel puts the token tiles on grid.y
-  dim3 gg((3 * d + 63) / 64, (unsigned)((n + 63) / 64), 1);
-  gemm_f32_kernel<false, true, false, true><<<gg, 256, 0, s>>>(xn, w_qkv, b_qkv, qkv, (int)n, 3 * d, d, d);
-  count_launch();
-  int st = check_last();
+  int st = linear_f32_fwd(xn, w_qkv, b_qkv, qkv, (int)n, d, 3 * d, s);
   if (st) return st;
   const float scale = 1.0f / sqrtf((float)hd);
   const unsigned grid = (unsigned)((n * heads + 127) / 128);
@@ -578,6 +568,7 @@ int band_attn_bwd_f32(const float* xn, const float* w_qkv, const uint32_t* bits,
 // ---------------------------------------------------------------------------
 int linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, int n, int d_in, int d_out,
                    cudaStream_t s) {
+  if (x3_enabled() && x3_supported(n, d_in, d_out)) return linear_x3_fwd(x, w, bias, y, n, d_in, d_out, s);
   dim3 g((d_out + 63) / 64, (unsigned)((n + 63) / 64), 1);
   if (bias)
     gemm_f32_kernel<false, true, false, true><<<g, 256, 0, s>>>(x, w, bias, y, n, d_out, d_in, d_in);
@@ -591,6 +582,11 @@ int linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, 
 int linear_f32_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int n, int d_in,
                    int d_out, cudaStream_t s) {
   int st;
+  if (x3_enabled() && x3_supported(n, d_in, d_out) && (dx || dw)) {
+    if ((st = linear_x3_bwd(dy, x, w, dx, dw, n, d_in, d_out, s))) return st;
+    dx = nullptr;
+    dw = nullptr;      // the column sums below stay fp32
+  }
   if (dx) {
     dim3 g((d_in + 63) / 64, (unsigned)((n + 63) / 64), 1);
     gemm_f32_kernel<false, false, false, false><<<g, 256, 0, s>>>(dy, w, nullptr, dx, n, d_in, d_out, d_out);
@@ -613,9 +609,19 @@ int linear_f32_bwd(const float* dy, const float* x, const float* w, float* dx, f
   }
   if (db) {
     cudaMemsetAsync(db, 0, sizeof(float) * d_out, s);
-    dim3 g((d_out + 127) / 128, 1);
-    colsum_f32_kernel<<<g, 128, 0, s>>>(dy, db, n, d_out, n);
-    count_launch();
+    if (n <= 4096) {          // the classifier head: one block per 128 columns, plain order
+      dim3 g((d_out + 127) / 128, 1);
+      colsum_f32_kernel<<<g, 128, 0, s>>>(dy, db, n, d_out, n);
+      count_launch();
+    } else {                  // token-sized inputs (the blocks' Linears in the fp32 modes): 512-row partial sums
+      const long long rpb = 512;
+      dim3 g((d_out + 127) / 128, (unsigned)((n + rpb - 1) / rpb));
+      float* part;
+      if ((st = det_scratch(&part, 1, (int)g.y, d_out, s))) return st;
+      colsum_f32_kernel<<<g, 128, 0, s>>>(dy, db, n, d_out, rpb, part);
+      count_launch();
+      det_finish(part, (int)g.y, d_out, db, nullptr, nullptr, s);
+    }
     if ((st = check_last())) return st;
   }
   return 0;

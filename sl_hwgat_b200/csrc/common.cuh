@@ -171,6 +171,14 @@ int linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, 
                    cudaStream_t s);
 int linear_f32_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int n, int d_in,
                    int d_out, cudaStream_t s);
+// x3 mode of the fp32 path (gemm_x3.cu): fp32 GEMMs as six bf16 tcgen05 products of hi / mid / lo planes
+extern int g_fp32_mode;
+bool x3_enabled();
+bool x3_supported(long long n, int d_in, int d_out);
+int linear_x3_fwd(const float* x, const float* w, const float* bias, float* y, long long n, int d_in, int d_out,
+                  cudaStream_t s);
+int linear_x3_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, long long n, int d_in,
+                  int d_out, cudaStream_t s);
 int smooth_ce_fwd(const float* logits, const long long* target, float* lse, float* row_loss, float* loss, int rows,
                   int classes, float smooth, cudaStream_t s);
 int smooth_ce_bwd(const float* logits, const long long* target, const float* lse, const float* g, float* dlogits,

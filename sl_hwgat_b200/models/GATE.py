@@ -55,7 +55,7 @@ class MSA(nn.Module):
         bits = parent._bits.get(getattr(parent, self.adj_mask), F, KP_PAD, x.device)
         xb = _pad_kp(x.reshape(B, F, K, d), 2)
         ctx = self.context(xb, bits)[:, :, :K].reshape(B, F_K, d)
-        return self.proj_drop(self.proj(ctx))
+        return self.proj_drop(_hw.linear(self.proj, ctx))
 
 
 class AttentionBlock(nn.Module):
@@ -98,7 +98,7 @@ class AttentionBlock(nn.Module):
         """the block on the padded (B, F, 32, d) stream with PyTorch LayerNorm / Linear / GELU around the band
         attention: the fp32 mode (GATE.py:111-116)"""
         a = self.attn
-        x = x + a.proj_drop(a.proj(a.context(self.norm1(x), bits)))
+        x = x + a.proj_drop(_hw.linear(a.proj, a.context(self.norm1(x), bits)))
         return x + self.ff(self.norm2(x))
 
     def forward(self, x, parent):

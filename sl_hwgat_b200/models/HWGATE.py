@@ -46,6 +46,17 @@ def _attn_dtype(x):
     return torch.float32
 
 
+def linear(mod, x):
+    """`mod(x)` for an nn.Linear of a block.  On the fp32 path (no autocast: the reference's own loop) in x3 mode
+    (ops.set_fp32_mode / HWGAT_FP32) it runs on the library's tcgen05 fp32 GEMM (gemm_x3.cu) instead of cuBLAS' FFMA
+    sgemm; bf16 autocast never comes here (K10 / K12)."""
+    if (type(mod) is nn.Linear and x.is_cuda and x.dtype == torch.float32 and mod.weight.dtype == torch.float32
+            and not torch.is_autocast_enabled()
+            and ops.linear_x3_active(x.numel() // x.shape[-1], x.shape[-1], mod.weight.shape[0])):
+        return ops.linear_f32(x, mod.weight, mod.bias)
+    return mod(x)
+
+
 def embed_generic(model, x):
     """Fourier embedding + positional encoding with PyTorch ops (HWGATE.py:343-347): the fp32 mode, and inputs that
     need a gradient.  The embedding stays fp32 even under autocast (bf16 would round the argument 2*pi*x.B, values up
@@ -142,7 +153,7 @@ class MSA(nn.Module):
         return torch.rand(1).item()
 
     def _project(self, ctx):
-        return self.proj_drop(self.proj(ctx))
+        return self.proj_drop(linear(self.proj, ctx))
 
     # -- fast path used by PartAttentionBlock: x is the un-partitioned (B,F,K,d) tensor
     def _attn_p(self):
@@ -192,7 +203,7 @@ class FeedForward(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        return self.drop(linear(self.fc2, self.drop(self.act(linear(self.fc1, x)))))
 
 
 class PartAttentionBlock(nn.Module):

@@ -93,7 +93,7 @@ class MSA(nn.Module):
         bits = parent._bits.get(mask, F, W, x.device)
         xb = window_reverse(x, W, F, nW * W)
         ctx = window_partition(self.context(xb, bits, W), W)
-        return self.proj_drop(self.proj(ctx))
+        return self.proj_drop(_hw.linear(self.proj, ctx))
 
 
 class PartAttentionBlock(nn.Module):
@@ -133,7 +133,7 @@ class PartAttentionBlock(nn.Module):
     def forward_generic(self, x, bits):
         """the block with PyTorch LayerNorm / Linear / GELU around the band attention: the fp32 mode (WGATE.py:150-160)"""
         a = self.attn
-        x = x + a.proj_drop(a.proj(a.context(self.norm1(x), bits, self.window_size)))
+        x = x + a.proj_drop(_hw.linear(a.proj, a.context(self.norm1(x), bits, self.window_size)))
         return x + self.ff(self.norm2(x))
 
     def forward(self, x, parent):

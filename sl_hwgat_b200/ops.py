@@ -79,6 +79,30 @@ def set_deterministic(on: bool = True) -> bool:
     return bool(_lib.load().hwgat_set_deterministic(1 if on else 0))
 
 
+def set_fp32_mode(mode: str) -> str:
+    """How fp32 tensors (no autocast: the reference's own loop, utils.py:102) are multiplied.  "ffma": true-fp32 FFMA
+    GEMMs, the 1e-5 parity mode.  "x3": every Linear of the blocks and the QKV projection of the attention run on
+    tcgen05 as six bf16 products of hi / mid / lo planes with fp32 accumulation (gemm_x3.cu; ~2e-7 against fp64,
+    several times faster).  Process-wide (hwgat_set_fp32_mode; also env HWGAT_FP32); returns the previous mode."""
+    if mode not in _lib.FP32_MODES:
+        raise ValueError(f"fp32 mode {mode!r}: expected one of {sorted(_lib.FP32_MODES)}")
+    prev = _lib.load().hwgat_set_fp32_mode(_lib.FP32_MODES[mode])
+    return {v: k for k, v in _lib.FP32_MODES.items()}[prev]
+
+
+def linear_x3_active(n: int, d_in: int, d_out: int) -> bool:
+    """True when linear_f32 of this shape runs on the tcgen05 x3 GEMM (mode "x3", n, d_in, d_out multiples of 128,
+    not in deterministic mode); mirrors x3_supported in csrc/gemm_x3.cu."""
+    lib = _lib.load()
+    return (lib.hwgat_set_fp32_mode(-1) == _lib.FP32_MODES["x3"] and n >= 128 and n % 128 == 0 and 3 * n < 2 ** 31
+            and d_in % 128 == 0 and d_out % 128 == 0 and d_in <= 4096 and d_out <= 2048
+            and not lib.hwgat_set_deterministic(-1))
+
+
+def fp32_mode() -> str:
+    return {v: k for k, v in _lib.FP32_MODES.items()}[_lib.load().hwgat_set_fp32_mode(-1)]
+
+
 def invalidate_cast_cache() -> None:
     """Forget every cached low-precision parameter copy.  Needed after parameters were written through raw pointers,
     which does not bump torch's `_version` counter: sl_hwgat_b200.optim.AdamW calls this after every step."""
