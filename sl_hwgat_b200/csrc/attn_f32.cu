@@ -101,11 +101,11 @@ struct CoreSmemF32 {
   float k[kTok][kHd];
   float v[kTok][kHd];
 };
+// 24.8 KB per warp: k, v while the lanes are queries, then q, d_out in the same two tiles while they are keys
+// (with all four resident, 41 KB per warp, one 4-warp CTA filled an SM: latency-bound at 4 warps per SM)
 struct CoreSmemF32Bwd {
-  float k[kTok][kHd];
-  float v[kTok][kHd];
-  float q[kTok][kHd];
-  float g[kTok][kHd];       // d_out rows of this window/head
+  float a[kTok][kHd];       // k rows, then q rows (scaled)
+  float b[kTok][kHd];       // v rows, then d_out rows of this window/head
   float p[kTok][kTok + 1];
   float ds[kTok][kTok + 1];
 };
@@ -215,13 +215,8 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
   for (int j = 0; j < kTok; ++j) {
     const long long r = g.token_row(tile, w * kTok + j);
     const float* src = qkv + r * d3 + h * kHd;
-    float2 qq = *reinterpret_cast<const float2*>(src + lane * 2);
-    qq.x *= scale; qq.y *= scale;
-    *reinterpret_cast<float2*>(&sm.q[j][lane * 2]) = qq;
-    *reinterpret_cast<float2*>(&sm.k[j][lane * 2]) = *reinterpret_cast<const float2*>(src + d + lane * 2);
-    *reinterpret_cast<float2*>(&sm.v[j][lane * 2]) = *reinterpret_cast<const float2*>(src + 2 * d + lane * 2);
-    *reinterpret_cast<float2*>(&sm.g[j][lane * 2]) =
-        *reinterpret_cast<const float2*>(d_out + r * d + h * kHd + lane * 2);
+    *reinterpret_cast<float2*>(&sm.a[j][lane * 2]) = *reinterpret_cast<const float2*>(src + d + lane * 2);
+    *reinterpret_cast<float2*>(&sm.b[j][lane * 2]) = *reinterpret_cast<const float2*>(src + 2 * d + lane * 2);
   }
   __syncwarp();
   const long long my_row = g.token_row(tile, w * kTok + lane);
@@ -238,7 +233,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
       qr[4 * e] = t.x * scale; qr[4 * e + 1] = t.y * scale; qr[4 * e + 2] = t.z * scale; qr[4 * e + 3] = t.w * scale;
     }
 #pragma unroll
-    for (int j = 0; j < kTok; ++j) s[j] = dot64(qr, sm.k[j]);
+    for (int j = 0; j < kTok; ++j) s[j] = dot64(qr, sm.a[j]);
   }
   const uint32_t mword = bits[g.mask_base(tile) + w * kTok + lane];
   const uint32_t live = row_softmax_f32(s, mword, threshold);  // s[] now holds P
@@ -253,7 +248,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
     }
 #pragma unroll
     for (int j = 0; j < kTok; ++j) {
-      float a = dot64(gr, sm.v[j]);
+      float a = dot64(gr, sm.b[j]);
       dp[j] = a;
       dsum = fmaf(s[j], a, dsum);
     }
@@ -272,14 +267,22 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
 #pragma unroll
     for (int j = 0; j < kTok; ++j)
 #pragma unroll
-      for (int e = 0; e < kHd; ++e) dq[e] = fmaf(dp[j], sm.k[j][e], dq[e]);
+      for (int e = 0; e < kHd; ++e) dq[e] = fmaf(dp[j], sm.a[j][e], dq[e]);
     float4* dst = reinterpret_cast<float4*>(dqkv + my_row * d3 + h * kHd);
 #pragma unroll
     for (int e = 0; e < kHd / 4; ++e)
       dst[e] = make_float4(dq[4 * e] * scale, dq[4 * e + 1] * scale, dq[4 * e + 2] * scale, dq[4 * e + 3] * scale);
   }
   __syncwarp();
-  // ---- lane = key j: dK row = sum_i dS[i][j] q_i ; dV row = sum_i P[i][j] g_i
+  // ---- lane = key j: dK row = sum_i dS[i][j] q_i ; dV row = sum_i P[i][j] g_i   (q, d_out rows replace k, v)
+  for (int j = 0; j < kTok; ++j) {
+    const long long r = g.token_row(tile, w * kTok + j);
+    float2 qq = *reinterpret_cast<const float2*>(qkv + r * d3 + h * kHd + lane * 2);
+    qq.x *= scale; qq.y *= scale;
+    *reinterpret_cast<float2*>(&sm.a[j][lane * 2]) = qq;
+    *reinterpret_cast<float2*>(&sm.b[j][lane * 2]) = *reinterpret_cast<const float2*>(d_out + r * d + h * kHd + lane * 2);
+  }
+  __syncwarp();
   {
     float acc[kHd];
 #pragma unroll
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
     for (int i = 0; i < kTok; ++i) {
       float c = sm.ds[i][lane];
 #pragma unroll
-      for (int e = 0; e < kHd; ++e) acc[e] = fmaf(c, sm.q[i][e], acc[e]);
+      for (int e = 0; e < kHd; ++e) acc[e] = fmaf(c, sm.a[i][e], acc[e]);
     }
     float4* dst = reinterpret_cast<float4*>(dqkv + my_row * d3 + d + h * kHd);
 #pragma unroll
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
     for (int i = 0; i < kTok; ++i) {
       float c = sm.p[i][lane];
 #pragma unroll
-      for (int e = 0; e < kHd; ++e) acc[e] = fmaf(c, sm.g[i][e], acc[e]);
+      for (int e = 0; e < kHd; ++e) acc[e] = fmaf(c, sm.b[i][e], acc[e]);
     }
     dst = reinterpret_cast<float4*>(dqkv + my_row * d3 + 2 * d + h * kHd);
 #pragma unroll

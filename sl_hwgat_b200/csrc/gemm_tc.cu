@@ -276,7 +276,7 @@ struct TnDet {
 
 template <int BN>
 static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd,
-                     cudaStream_t s, bool perm64, int perm_limit, bool accumulate = false, int max_per = 0) {
+                     cudaStream_t s, bool perm64, int perm_limit) {
   using Cfg = GemmTnCfg<BN>;
   static PerDeviceOnce once;
   once.run([] { cudaFuncSetAttribute(gemm_tc_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem); });
@@ -289,12 +289,11 @@ static int launch_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int
   int splits = 148 / tiles;  // one wave: tiles * splits <= 148 SMs (a 149th CTA would double the time)
   if (splits < 1) splits = 1;
   if (splits > kblocks) splits = kblocks;
-  int per = (kblocks + splits - 1) / splits;
-  if (max_per > 0 && per > max_per) per = max_per;   // x3 mode: bounded accumulation chains, several waves
+  const int per = (kblocks + splits - 1) / splits;
   splits = (kblocks + per - 1) / per;
   TnDet det;
-  if (!accumulate && (st = det.begin(splits, M, N, s))) return st;
-  if (!det.part && !accumulate) {
+  if ((st = det.begin(splits, M, N, s))) return st;
+  if (!det.part) {
     cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s);
     if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * M, s);
   }
@@ -451,7 +450,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_tn_pair_kernel(const __grid_co
 }
 
 static int launch_tn_pair(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, int N, long long Kd,
-                          cudaStream_t s, bool perm64, int perm_limit, bool accumulate = false, int max_per = 0) {
+                          cudaStream_t s, bool perm64, int perm_limit) {
   using Cfg = GemmTnPairCfg;
   static PerDeviceOnce once;
   once.run([] { cudaFuncSetAttribute(gemm_tc_tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem); });
@@ -464,12 +463,11 @@ static int launch_tn_pair(const bf16* A, const bf16* Bm, float* C, float* colsum
   int splits = 74 / tiles;  // one wave of CTA pairs
   if (splits < 1) splits = 1;
   if (splits > kblocks) splits = kblocks;
-  int per = (kblocks + splits - 1) / splits;
-  if (max_per > 0 && per > max_per) per = max_per;
+  const int per = (kblocks + splits - 1) / splits;
   splits = (kblocks + per - 1) / per;
   TnDet det;
-  if (!accumulate && (st = det.begin(splits, M, N, s))) return st;
-  if (!det.part && !accumulate) {
+  if ((st = det.begin(splits, M, N, s))) return st;
+  if (!det.part) {
     cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s);
     if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * M, s);
   }
@@ -505,20 +503,6 @@ int gemm_tc_tn(const bf16* A, const bf16* Bm, float* C, float* colsum, int M, in
     return launch_tn<256>(A, Bm, C, colsum, M, N, Kd, s, perm64, perm_limit);
   }
   return launch_tn<128>(A, Bm, C, colsum, M, N, Kd, s, perm64, perm_limit);
-}
-
-// The x3 fp32 mode (gemm_x3.cu): C (+)= A^T . B without column sums; accumulate = add to what C holds (no memset);
-// max_kblocks_per_cta > 0 bounds the token range one CTA accumulates in TMEM before it adds to C (the tensor core adds
-// into its accumulator with truncation; the split then runs over several waves).  Not for deterministic mode.
-int gemm_tc_tn_ex(const bf16* A, const bf16* Bm, float* C, int M, int N, long long Kd, cudaStream_t s, bool accumulate,
-                  int max_kblocks_per_cta) {
-  if (M % 128 || N % 128 || Kd % 64 || deterministic()) return HWGAT_ERR_UNSUPPORTED;
-  if (N % 256 == 0) {
-    if (gemm_pair_enabled() && M >= 256 && ((M + 255) / 256) * (N / 256) >= 3)
-      return launch_tn_pair(A, Bm, C, nullptr, M, N, Kd, s, false, 0, accumulate, max_kblocks_per_cta);
-    return launch_tn<256>(A, Bm, C, nullptr, M, N, Kd, s, false, 0, accumulate, max_kblocks_per_cta);
-  }
-  return launch_tn<128>(A, Bm, C, nullptr, M, N, Kd, s, false, 0, accumulate, max_kblocks_per_cta);
 }
 
 }  // namespace hwgat

@@ -20,7 +20,7 @@
 //
 //   y  = x . W^T + b        gemm_nt_x3_kernel: TMA -> 6 planes per stage -> 24 tcgen05.mma per 64-wide k block -> TMEM
 //   dx = dy . W             the same kernel against the split of W^T
-//   dW = dy^T . x           six calls of gemm_tc_tn (gemm_tc.cu: MN-major operands straight from the row-major planes)
+//   dW = dy^T . x           gemm_tn_x3_kernel: MN-major operands straight from the row-major planes, token split
 //   db = column sums of dy  colsum_f32 (fp32)
 #include "tc.cuh"
 
@@ -241,13 +241,140 @@ static int launch_nt_x3(const bf16* A3, const bf16* B3, float* C, const float* b
   return (int)cudaGetLastError();
 }
 
-// ---- the three GEMMs of a Linear layer ------------------------------------------------------------------------------
-constexpr int kMainKBlocks = 16;   // 1024 tokens: longest chain of the leading accumulator of a weight-gradient GEMM
+// ---- TN GEMM over split planes (weight gradients) -------------------------------------------------------------------
+// C[M,N] (fp32) += sum over the six plane pairs of A_p[Kd,M]^T . B_q[Kd,N]: A3 = [3][Kd][M], B3 = [3][Kd][N] bf16, both
+// MN-major UMMA operands straight from the row-major planes (as gemm_tc_tn, gemm_tc.cu).  The contraction runs over
+// the tokens: grid = (128 x 128 tiles, token splits of kMainKBlocks k blocks), every CTA adds its partial to the zeroed
+// output with red.global.add - the leading accumulator never sees more than kMainKBlocks * 4 truncating steps.
+struct X3TnCfg {
+  static constexpr int kStages = 2;
+  static constexpr int kPlane = 64 * 128 * 2;             // [64 k][128 mn]: two 8 KB boxes
+  static constexpr int kStage = 6 * kPlane;
+  static constexpr int kBarOff = kStages * kStage;
+  static constexpr int kSmem = kBarOff + 256 + 1024;
+  static constexpr int kTmemCols = 256;                   // 128 leading + 128 corrections
+};
+constexpr int kMainKBlocks = 16;   // 1024 tokens
 
+__global__ void __launch_bounds__(192, 1) gemm_tn_x3_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmB,
+                                                            float* __restrict__ C, int N, int kd_rows, int k_blocks_total) {
+  using Cfg = X3TnCfg;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* acc_full = empty + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = N / 128;
+  const int mb = blockIdx.x / n_blocks, nb = blockIdx.x - mb * n_blocks;
+  const int kb0 = blockIdx.y * kMainKBlocks;
+  const int kb1 = kb0 + kMainKBlocks < k_blocks_total ? kb0 + kMainKBlocks : k_blocks_total;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one_sync()) {
+        unsigned char* st = smem + s * Cfg::kStage;
+        mbar_expect_tx(&full[s], Cfg::kStage);
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            tma_load_2d(st + p * Cfg::kPlane + j * 8192, &tmA, &full[s], mb * 128 + j * 64, p * kd_rows + kb * 64);
+            tma_load_2d(st + (3 + p) * Cfg::kPlane + j * 8192, &tmB, &full[s], nb * 128 + j * 64, p * kd_rows + kb * 64);
+          }
+      }
+      __syncwarp();
+      if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128, true, true);
+    constexpr int kPa[5] = {2, 0, 1, 1, 0};
+    constexpr int kPb[5] = {0, 2, 1, 0, 1};
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + 3 * Cfg::kPlane;
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)   // 16 tokens per step = two 8-row atoms = 2 KB
+            umma_bf16(tmem + 128, umma_desc_mn_sw128(sa + kPa[c] * Cfg::kPlane + ks * 2048, 8192, 1024),
+                      umma_desc_mn_sw128(sb + kPb[c] * Cfg::kPlane + ks * 2048, 8192, 1024), idesc, (kb > kb0) | (ks | c));
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem, umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024), umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024),
+                    idesc, (kb > kb0) | ks);
+        umma_commit(&empty[s]);
+      }
+      __syncwarp();
+      if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+    }
+    if (elect_one_sync()) umma_commit(acc_full);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float* crow = C + (size_t)(mb * 128 + q * 32 + lane) * N + (size_t)nb * 128;
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      uint32_t r[32], r2[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, r);
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + c, r2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(crow + c + i, __uint_as_float(r[i]) + __uint_as_float(r2[i]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, Cfg::kTmemCols);
+}
+
+static int launch_tn_x3(const bf16* A3, const bf16* B3, float* C, int M, int N, long long Kd, cudaStream_t s) {
+  using Cfg = X3TnCfg;
+  static PerDeviceOnce once;
+  once.run([] { cudaFuncSetAttribute(gemm_tn_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem); });
+  CUtensorMap tmA, tmB;
+  int st;
+  if ((st = make_tmap_2d(&tmA, A3, (uint64_t)(3 * Kd), (uint64_t)M, 64))) return st;
+  if ((st = make_tmap_2d(&tmB, B3, (uint64_t)(3 * Kd), (uint64_t)N, 64))) return st;
+  const int tiles = (M / 128) * (N / 128);
+  const int kblocks = (int)(Kd / 64);
+  const int splits = (kblocks + kMainKBlocks - 1) / kMainKBlocks;
+  if (splits > 65535) return HWGAT_ERR_UNSUPPORTED;
+  cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s);
+  gemm_tn_x3_kernel<<<dim3(tiles, splits), 192, Cfg::kSmem, s>>>(tmA, tmB, C, N, (int)Kd, kblocks);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ---- the three GEMMs of a Linear layer ------------------------------------------------------------------------------
 bool x3_enabled() { return __atomic_load_n(&g_fp32_mode, __ATOMIC_RELAXED) == 1 && !deterministic(); }
 bool x3_supported(long long n, int d_in, int d_out) {
-  return n >= 128 && n % 128 == 0 && n * 3 < 0x7fffffffLL && d_in % 128 == 0 && d_out % 128 == 0 && d_in <= 4096 &&
-         d_out <= X3Cfg::kMaxBiasN;
+  return n >= 128 && n % 128 == 0 && n * 3 < 0x7fffffffLL && n / 64 / kMainKBlocks < 65535 && d_in % 128 == 0 &&
+         d_out % 128 == 0 && d_in <= 4096 && d_out <= X3Cfg::kMaxBiasN;
 }
 
 struct Scratch {     // stream-ordered scratch for the bf16 planes
@@ -274,9 +401,6 @@ struct Scratch {     // stream-ordered scratch for the bf16 planes
   }
   ~Scratch() { if (p) cudaFreeAsync(p, s); }
 };
-
-int gemm_tc_tn_ex(const bf16* A, const bf16* Bm, float* C, int M, int N, long long Kd, cudaStream_t s, bool accumulate,
-                  int max_kblocks_per_cta);   // gemm_tc.cu
 
 int linear_x3_fwd(const float* x, const float* w, const float* bias, float* y, long long n, int d_in, int d_out,
                   cudaStream_t s) {
@@ -308,12 +432,7 @@ int linear_x3_bwd(const float* dy, const float* x, const float* w, float* dx, fl
   }
   if (dw) {
     if ((st = split_rows(x, x3, (long long)xe, s))) return st;
-    // smallest products first; the leading one last, flushed every kMainKBlocks k blocks
-    constexpr int kPa[6] = {2, 0, 1, 1, 0, 0};
-    constexpr int kPb[6] = {0, 2, 1, 0, 1, 0};
-    for (int c = 0; c < 6; ++c)
-      if ((st = gemm_tc_tn_ex(y3 + kPa[c] * ye, x3 + kPb[c] * xe, dw, d_out, d_in, n, s, c != 0, c == 5 ? kMainKBlocks : 0)))
-        return st;
+    if ((st = launch_tn_x3(y3, x3, dw, d_out, d_in, n, s))) return st;
   }
   return 0;
 }
