@@ -23,7 +23,8 @@ namespace hwgat {
 
 typedef __nv_bfloat16 bf16;
 
-enum { kEpiNone = 0, kEpiGelu = 1, kEpiMul = 2, kEpiBias = 3 };   // kEpiBias: C = acc + bias (fp32 add, then bf16)
+enum { kEpiNone = 0, kEpiGelu = 1, kEpiMul = 2, kEpiBias = 3, kEpiGeluEval = 4 };   // kEpiBias: C = acc + bias (fp32 add, then bf16)
+// kEpiGeluEval: C = gelu(acc + bias) only - inference (no dropout mask, no local derivative): half the instructions of kEpiGelu
 
 struct EpiArgs {
   bf16* C;            // [M, N] output
@@ -39,7 +40,7 @@ constexpr int kFM = 128, kFK = 64;
 // epilogue warps: 8 for the memory-bound epilogues, 16 for the ALU-bound GELU one (4 per SM sub-partition:
 // with 2 the issue slots were ~2/3 used and the fc1 GEMM ran at the speed of the standalone K7 kernel)
 template <int EPI>
-struct EpiWarps { static constexpr int kWarps = EPI == 1 ? 16 : 8; static constexpr int kThreads = 32 * (2 + kWarps); };
+struct EpiWarps { static constexpr int kWarps = (EPI == 1 || EPI == 4) ? 16 : 8; static constexpr int kThreads = 32 * (2 + kWarps); };
 
 constexpr int kMaxBiasN = 2048;  // widest bias the GELU epilogue stages in shared memory (hidden <= 2048)
 
@@ -85,6 +86,20 @@ HW_DEV void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& e, size_t ele
         const float4 b = lds_f4(sbias + col + 16 * g + 4 * q4);
         p[2 * q4] = pack_bf16(__uint_as_float(r[16 * g + 4 * q4]) + b.x, __uint_as_float(r[16 * g + 4 * q4 + 1]) + b.y);
         p[2 * q4 + 1] = pack_bf16(__uint_as_float(r[16 * g + 4 * q4 + 2]) + b.z, __uint_as_float(r[16 * g + 4 * q4 + 3]) + b.w);
+      }
+      st_global32(e.C + elem + 16 * g, p);
+    }
+  } else if (EPI == kEpiGeluEval) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint32_t p[8];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 b = lds_f4(sbias + col + 16 * g + 4 * q4);
+        p[2 * q4] = pack_bf16(gelu_exact(__uint_as_float(r[16 * g + 4 * q4]) + b.x),
+                              gelu_exact(__uint_as_float(r[16 * g + 4 * q4 + 1]) + b.y));
+        p[2 * q4 + 1] = pack_bf16(gelu_exact(__uint_as_float(r[16 * g + 4 * q4 + 2]) + b.z),
+                                  gelu_exact(__uint_as_float(r[16 * g + 4 * q4 + 3]) + b.w));
       }
       st_global32(e.C + elem + 16 * g, p);
     }
@@ -199,7 +214,7 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_kernel
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blocks = N / BN, m_blocks = M / kFM, tiles = n_blocks * m_blocks, nk = K / kFK;
-  if (EPI == kEpiGelu || EPI == kEpiBias)
+  if (EPI == kEpiGelu || EPI == kEpiBias || EPI == kEpiGeluEval)
     for (int i = threadIdx.x; i < N; i += blockDim.x) sbias[i] = e.bias ? e.bias[i] : 0.f;
 
   if (threadIdx.x == 0) {
@@ -338,7 +353,7 @@ __global__ void __launch_bounds__(EpiWarps<EPI>::kThreads, 1) gemm_nt_epi_pair_k
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int n_blocks = N / BN, m_blocks = (M + 2 * kFM - 1) / (2 * kFM), tiles = n_blocks * m_blocks, nk = K / kFK;
-  if (EPI == kEpiGelu || EPI == kEpiBias)
+  if (EPI == kEpiGelu || EPI == kEpiBias || EPI == kEpiGeluEval)
     for (int i = threadIdx.x; i < N; i += blockDim.x) sbias[i] = e.bias ? e.bias[i] : 0.f;
 
   if (threadIdx.x == 0) {
@@ -515,7 +530,9 @@ int ffn_fwd(const bf16* h, const bf16* w1, const float* b1, const bf16* w2, bf16
   e.C = act; e.C2 = gp; e.bias = b1; e.thresh = drop_threshold16(p); e.scale = drop_scale16(e.thresh);
   e.seed = seed; e.offset = offset;
   if (hidden > kMaxBiasN) return HWGAT_ERR_UNSUPPORTED;
-  int st = gemm_nt_epi<kEpiGelu>(h, w1, e, n, hidden, d, s);          // act, gp  [n, hidden]
+  // inference (no local derivative wanted, no dropout): the GELU-only epilogue
+  int st = (!gp && e.thresh == 0) ? gemm_nt_epi<kEpiGeluEval>(h, w1, e, n, hidden, d, s)
+                                  : gemm_nt_epi<kEpiGelu>(h, w1, e, n, hidden, d, s);          // act, gp  [n, hidden]
   if (st) return st;
   EpiArgs e2{};
   e2.C = v0;

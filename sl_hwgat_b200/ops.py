@@ -799,7 +799,7 @@ class _FeedForwardCore(torch.autograd.Function):
     epilogue).  Saves h, the hidden activation and its local derivative (mask folded in); nothing is recomputed."""
 
     @staticmethod
-    def forward(ctx, h, w1, b1, w2, p):
+    def forward(ctx, h, w1, b1, w2, p, grad_mode=True):
         lib = _lib.load()
         _need_cuda(h, w1, b1, w2)
         h_c = h.to(torch.bfloat16).contiguous()
@@ -811,7 +811,10 @@ class _FeedForwardCore(torch.autograd.Function):
         w1_c = cast_cached(w1, torch.bfloat16)
         w2_c = cast_cached(w2, torch.bfloat16)
         b1_c = cast_cached(b1, torch.float32) if b1 is not None else None
-        need_grad = any(ctx.needs_input_grad[:4])
+        # needs_input_grad is also set under torch.no_grad() (parameters still require grad) and grad mode is always
+        # off inside forward: the caller passes the grad mode it saw.  Inference then takes the GELU-only epilogue and
+        # writes no local derivative (1.6 GB per call at batch 256, T = 192)
+        need_grad = bool(grad_mode) and any(ctx.needs_input_grad[:4])
         seed, off = _philox_stream(h_c.device) if p > 0 else (0, 0)
         act = torch.empty((n, hidden), dtype=torch.bfloat16, device=h_c.device)
         gp = torch.empty_like(act) if need_grad else None
@@ -842,7 +845,7 @@ class _FeedForwardCore(torch.autograd.Function):
             check(lib.hwgat_ffn_bwd(dv.data_ptr(), h_c.data_ptr(), act.data_ptr(), gp.data_ptr(), w1_c.data_ptr(),
                                     w2_c.data_ptr(), dh.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(),
                                     ws.data_ptr(), ws.numel(), n, d, hidden, _stream()), "hwgat_ffn_bwd")
-        return (dh.to(hdt), dw1.to(w1dt), None if b1dt is None else db1.to(b1dt), dw2.to(w2dt), None)
+        return (dh.to(hdt), dw1.to(w1dt), None if b1dt is None else db1.to(b1dt), dw2.to(w2dt), None, None)
 
 
 def feed_forward_core(h: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor, p: float,
@@ -850,7 +853,7 @@ def feed_forward_core(h: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tens
     """dropout(gelu(h @ w1.T + b1)) @ w2.T as bf16: ff.fc1, ff.act, ff.drop and ff.fc2's matmul (HWGATE.py:130-134);
     fc2's bias, the second dropout and the residual add are K6's (bias_dropout_add_ln).
     h: (..., d) with prod(...) % 128 == 0, d % 128 == 0, hidden % 128 == 0, hidden <= 2048."""
-    return _FeedForwardCore.apply(h, w1, b1, w2, p if training else 0.0)
+    return _FeedForwardCore.apply(h, w1, b1, w2, p if training else 0.0, torch.is_grad_enabled())
 
 
 def ffn_supported(n_tokens: int, d: int, hidden: int) -> bool:

@@ -500,6 +500,35 @@ def test_feed_forward_core_no_dropout(d, hidden, n):
     assert rel_l2(b1.grad, b164.grad) < 8e-3
 
 
+@pytest.mark.parametrize("d", [128, 256, 512])
+def test_feed_forward_core_inference_epilogue(d):
+    """Under no_grad K10's fc1 GEMM takes the GELU-only epilogue (no dropout stream, no local derivative): same bits
+    as the training epilogue at p = 0, and within the bf16 band of the fp64 value."""
+    from sl_hwgat_b200 import ops
+    g = torch.Generator().manual_seed(d)
+    n, hidden = 128 * 301, 2 * d                     # 301 tiles: more than one per CTA, odd count
+    h = torch.randn(n, d, generator=g).to(torch.bfloat16).cuda()
+    w1 = (torch.randn(hidden, d, generator=g) / d ** 0.5).to(torch.bfloat16).float().cuda()
+    b1 = (0.3 * torch.randn(hidden, generator=g)).cuda()
+    w2 = (torch.randn(d, hidden, generator=g) / hidden ** 0.5).to(torch.bfloat16).float().cuda()
+    with torch.no_grad():
+        v_eval = ops.feed_forward_core(h, w1, b1, w2, 0.1, False)
+    w1.requires_grad_(True)
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():                        # parameters that require grad, as in model.eval() under no_grad
+        v_eval2 = ops.feed_forward_core(h, w1, b1, w2, 0.1, False)
+    torch.cuda.synchronize()
+    peak = torch.cuda.max_memory_allocated() - base
+    assert peak < (n * hidden + n * d) * 2 * 1.25          # act + v0, no local-derivative tensor
+    assert torch.equal(v_eval, v_eval2)
+    v_train = ops.feed_forward_core(h, w1, b1, w2, 0.0, True)      # wants gp: training epilogue
+    assert torch.equal(v_eval, v_train.detach())
+    ref = torch.nn.functional.gelu(h.double() @ w1.detach().double().t() + b1.double()) @ w2.double().t()
+    assert rel_l2(v_eval.float(), ref) < 6e-3
+
+
 @pytest.mark.parametrize("p", [0.1, 0.5])
 def test_feed_forward_core_dropout(p):
     """K10 with dropout: with W2 = I the output is the hidden activation itself, so the mask, its rate, the
