@@ -215,7 +215,11 @@ int hwgat_bias_gelu_dropout_bwd(const void* u0, const float* bias, const void* d
  *   gp (bf16, (n, hidden)) = d act / d (h . W1^T + b1)         dropout mask and 1/(1-p) folded in; NULL = do not save
  *   v0 (bf16, (n, d))      = act . W2^T
  * Replaces ff.fc1 + ff.act + ff.drop + ff.fc2's matmul (HWGATE.py:130-134).  h: (n, d) bf16, W1: (hidden, d) bf16,
- * b1: (hidden) fp32 or NULL, W2: (d, hidden) bf16.  n % 128 == 0, d % 128 == 0, hidden % 128 == 0, hidden <= 2048. */
+ * b1: (hidden) fp32 or NULL, W2: (d, hidden) bf16.  n % 128 == 0, d % 128 == 0, hidden % 128 == 0, hidden <= 2048.
+ * Inference: gp == NULL and p == 0 take a GELU-only epilogue; with act == NULL as well (activation not wanted) and
+ * hwgat_ffn_fused_supported(n, d, hidden) != 0 (d = 128 / 256, hidden = 2 d) the whole FeedForward is ONE kernel
+ * whose activation tile stays in shared memory (K10f): h is read once, v0 written once.                          */
+int hwgat_ffn_fused_supported(long long n, int d, int hidden);
 int hwgat_ffn_fwd(const void* h, const void* w1, const float* b1, const void* w2, void* act, void* gp, void* v0,
                   long long n, int d, int hidden, float p, unsigned long long seed, unsigned long long offset,
                   hwgat_stream_t stream);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("HWGAT_B200_LIB") or os.path.join(HERE, "lib", "libhwg
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 19
+ABI_VERSION = 20
 FP32_MODES = {"ffma": 0, "x3": 1}      # HWGAT_FP32_FFMA / HWGAT_FP32_X3 (include/hwgat_b200.h)
 FP32_DEFAULT = "x3"        # the package default; the C library itself starts in FFMA mode
 
@@ -70,6 +70,7 @@ SIGNATURES = {
     "hwgat_ln_pool_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "hwgat_ln_pool_fwd": (c_int, [c_void_p] * 7 + [c_size_t, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "hwgat_ln_pool_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "hwgat_ffn_fused_supported": (c_int, [c_longlong, c_int, c_int]),
     "hwgat_ffn_fwd": (c_int, [c_void_p] * 7 + [c_longlong, c_int, c_int, c_float, c_ulonglong, c_ulonglong,
                                c_void_p]),
     "hwgat_ffn_bwd_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "lib", "libhwgat_b200.so")
-SOURCES = ["api.cu", "mask_merge.cu", "attn_f32.cu", "gemm_tc.cu", "attn_tc.cu", "block_fused.cu", "ffn_tc.cu", "optim.cu", "head_loss.cu", "attn_core_tc2.cu", "band_attn.cu", "attn_win_f32.cu", "gemm_x3.cu"]
+SOURCES = ["api.cu", "mask_merge.cu", "attn_f32.cu", "gemm_tc.cu", "attn_tc.cu", "block_fused.cu", "ffn_tc.cu", "optim.cu", "head_loss.cu", "attn_core_tc2.cu", "band_attn.cu", "attn_win_f32.cu", "gemm_x3.cu", "ffn_fused.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc.cuh"), os.path.join(CSRC, "ew.cuh"), os.path.join(HERE, "..", "include", "hwgat_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -30,7 +30,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 19; }
+int hwgat_version(void) { return 20; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -490,6 +490,10 @@ static int check_ffn(long long n, int d, int hidden) {
   return HWGAT_OK;
 }
 
+int hwgat_ffn_fused_supported(long long n, int d, int hidden) {
+  return check_ffn(n, d, hidden) == 0 && ffn_eval_fused_supported(n, d, hidden) ? 1 : 0;
+}
+
 int hwgat_ffn_fwd(const void* h, const void* w1, const float* b1, const void* w2, void* act, void* gp, void* v0,
                   long long n, int d, int hidden, float p, unsigned long long seed, unsigned long long offset,
                   hwgat_stream_t stream) {
@@ -497,10 +501,16 @@ int hwgat_ffn_fwd(const void* h, const void* w1, const float* b1, const void* w2
   if (st) return st;
   if (bad_p(p)) return HWGAT_ERR_SHAPE;
   if (n == 0) return HWGAT_OK;
-  if (!h || !w1 || !w2 || !act || !v0) return HWGAT_ERR_NULL;
+  if (!h || !w1 || !w2 || !v0) return HWGAT_ERR_NULL;
   if (misaligned(h) || misaligned(w1) || misaligned(b1) || misaligned(w2) || misaligned(act) || misaligned(gp) ||
       misaligned(v0))
     return HWGAT_ERR_ALIGN;
+  if (!act) {   // inference, activation not wanted: the one-kernel form (ffn_fused.cu), where its shape allows
+    if (gp || p != 0.f) return HWGAT_ERR_NULL;
+    if (!ffn_eval_fused_supported(n, d, hidden)) return HWGAT_ERR_UNSUPPORTED;
+    return ffn_eval_fused((const __nv_bfloat16*)h, (const __nv_bfloat16*)w1, b1, (const __nv_bfloat16*)w2,
+                          (__nv_bfloat16*)v0, n, d, hidden, (cudaStream_t)stream);
+  }
   return ffn_fwd((const __nv_bfloat16*)h, (const __nv_bfloat16*)w1, b1, (const __nv_bfloat16*)w2, (__nv_bfloat16*)act,
                  (__nv_bfloat16*)gp, (__nv_bfloat16*)v0, n, d, hidden, p, seed, offset, (cudaStream_t)stream);
 }

@@ -240,6 +240,10 @@ int gemm_tc_nt_epi_none(const __nv_bfloat16* A, const __nv_bfloat16* Bt, __nv_bf
 int ffn_fwd(const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1, const __nv_bfloat16* w2,
             __nv_bfloat16* act, __nv_bfloat16* gp, __nv_bfloat16* v0, long long n, int d, int hidden, float p,
             unsigned long long seed, unsigned long long offset, cudaStream_t s);
+// K10f (ffn_fused.cu): inference FeedForward in one kernel, d = 128 / 256, hidden = 2 d
+bool ffn_eval_fused_supported(long long n, int d, int hidden);
+int ffn_eval_fused(const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1, const __nv_bfloat16* w2,
+                   __nv_bfloat16* v0, long long n, int d, int hidden, cudaStream_t s);
 int adamw_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                float* const* exp_avg_sq, const long long* sizes, double lr, double beta1, double beta2, double eps,
                double weight_decay, long long step, float grad_scale, cudaStream_t s);

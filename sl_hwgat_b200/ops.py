@@ -794,6 +794,9 @@ def bias_gelu_dropout(u0: torch.Tensor, bias: Optional[torch.Tensor], p: float, 
     return _BiasGeluDropout.apply(u0, bias, p if training else 0.0)
 
 
+FFN_FUSED = os.environ.get("HWGAT_FFN_FUSED", "1") != "0"     # A/B switch of the one-kernel inference FeedForward (K10f)
+
+
 class _FeedForwardCore(torch.autograd.Function):
     """v0 = dropout(gelu(h W1^T + b1)) W2^T on the tcgen05 GEMMs of K10 (bias, GELU and dropout in the first GEMM's
     epilogue).  Saves h, the hidden activation and its local derivative (mask folded in); nothing is recomputed."""
@@ -816,11 +819,13 @@ class _FeedForwardCore(torch.autograd.Function):
         # writes no local derivative (1.6 GB per call at batch 256, T = 192)
         need_grad = bool(grad_mode) and any(ctx.needs_input_grad[:4])
         seed, off = _philox_stream(h_c.device) if p > 0 else (0, 0)
-        act = torch.empty((n, hidden), dtype=torch.bfloat16, device=h_c.device)
+        # inference: one kernel, the activation tile never leaves the SM (K10f), where the shape allows
+        fused = (not need_grad and p == 0 and FFN_FUSED and bool(lib.hwgat_ffn_fused_supported(n, d, hidden)))
+        act = None if fused else torch.empty((n, hidden), dtype=torch.bfloat16, device=h_c.device)
         gp = torch.empty_like(act) if need_grad else None
         v0 = torch.empty(h_c.shape, dtype=torch.bfloat16, device=h_c.device)
         with torch.cuda.device(h_c.device):
-            check(lib.hwgat_ffn_fwd(h_c.data_ptr(), w1_c.data_ptr(), _ptr(b1_c), w2_c.data_ptr(), act.data_ptr(),
+            check(lib.hwgat_ffn_fwd(h_c.data_ptr(), w1_c.data_ptr(), _ptr(b1_c), w2_c.data_ptr(), _ptr(act),
                                     _ptr(gp), v0.data_ptr(), n, d, hidden, float(p), seed, off, _stream()),
                   "hwgat_ffn_fwd")
         if need_grad:

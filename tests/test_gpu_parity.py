@@ -500,31 +500,42 @@ def test_feed_forward_core_no_dropout(d, hidden, n):
     assert rel_l2(b1.grad, b164.grad) < 8e-3
 
 
+@pytest.mark.parametrize("n", [128 * 301, 128 * 3])
 @pytest.mark.parametrize("d", [128, 256, 512])
-def test_feed_forward_core_inference_epilogue(d):
-    """Under no_grad K10's fc1 GEMM takes the GELU-only epilogue (no dropout stream, no local derivative): same bits
-    as the training epilogue at p = 0, and within the bf16 band of the fp64 value."""
+def test_feed_forward_core_inference(d, n):
+    """Under no_grad K10 runs as ONE kernel for d = 128 / 256 (K10f: the activation tile stays in shared memory) and
+    with a GELU-only fc1 epilogue otherwise (no dropout stream, no local derivative).  Both give the bits of the
+    training form at p = 0 and sit within the bf16 band of the fp64 value; no (n, hidden) tensor is allocated by the
+    one-kernel form.  301 tiles: more than one per CTA, an odd count; 3 tiles: fewer tiles than SMs."""
     from sl_hwgat_b200 import ops
     g = torch.Generator().manual_seed(d)
-    n, hidden = 128 * 301, 2 * d                     # 301 tiles: more than one per CTA, odd count
+    hidden = 2 * d
     h = torch.randn(n, d, generator=g).to(torch.bfloat16).cuda()
-    w1 = (torch.randn(hidden, d, generator=g) / d ** 0.5).to(torch.bfloat16).float().cuda()
+    w1 = (torch.randn(hidden, d, generator=g) / d ** 0.5).to(torch.bfloat16).float().cuda().requires_grad_(True)
     b1 = (0.3 * torch.randn(hidden, generator=g)).cuda()
     w2 = (torch.randn(d, hidden, generator=g) / hidden ** 0.5).to(torch.bfloat16).float().cuda()
-    with torch.no_grad():
-        v_eval = ops.feed_forward_core(h, w1, b1, w2, 0.1, False)
-    w1.requires_grad_(True)
+    lib = ops._lib.load()
+    assert bool(lib.hwgat_ffn_fused_supported(n, d, hidden)) == (d in (128, 256))
     torch.cuda.synchronize()
     torch.cuda.reset_peak_memory_stats()
     base = torch.cuda.memory_allocated()
     with torch.no_grad():                        # parameters that require grad, as in model.eval() under no_grad
-        v_eval2 = ops.feed_forward_core(h, w1, b1, w2, 0.1, False)
+        v_eval = ops.feed_forward_core(h, w1, b1, w2, 0.1, False)
     torch.cuda.synchronize()
     peak = torch.cuda.max_memory_allocated() - base
-    assert peak < (n * hidden + n * d) * 2 * 1.25          # act + v0, no local-derivative tensor
-    assert torch.equal(v_eval, v_eval2)
-    v_train = ops.feed_forward_core(h, w1, b1, w2, 0.0, True)      # wants gp: training epilogue
-    assert torch.equal(v_eval, v_train.detach())
+    if d in (128, 256):
+        assert peak < n * d * 2 * 1.5 + (1 << 20)             # v0 only (+ cached bf16 weights)
+    else:
+        assert peak < (n * hidden + n * d) * 2 * 1.25 + (4 << 20)     # act + v0, no local-derivative tensor
+    prev, ops.FFN_FUSED = ops.FFN_FUSED, False
+    try:
+        with torch.no_grad():
+            v_two = ops.feed_forward_core(h, w1, b1, w2, 0.1, False)      # two GEMMs, GELU-only epilogue
+    finally:
+        ops.FFN_FUSED = prev
+    v_train = ops.feed_forward_core(h, w1, b1, w2, 0.0, True)      # wants the local derivative: training epilogue
+    assert torch.equal(v_two, v_train.detach())
+    assert torch.equal(v_eval, v_two)
     ref = torch.nn.functional.gelu(h.double() @ w1.detach().double().t() + b1.double()) @ w2.double().t()
     assert rel_l2(v_eval.float(), ref) < 6e-3
 
