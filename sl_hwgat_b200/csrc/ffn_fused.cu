@@ -212,11 +212,14 @@ __global__ void __launch_bounds__(FusedCfg<D>::kThreads, 1) ffn_eval_fused_kerne
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc1_empty[b]);          // the accumulator is free for fc1 of chunk g + 2
         uint32_t pk[16];
-        const float* bp = sbias + c * 128 + slice * 32;
+        const uint32_t bp = smem_u32(sbias + c * 128 + slice * 32);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pk[i] = pack_bf16(gelu_exact(__uint_as_float(r[2 * i]) + bp[2 * i]),
-                            gelu_exact(__uint_as_float(r[2 * i + 1]) + bp[2 * i + 1]));
+        for (int i = 0; i < 8; ++i) {                        // 16-byte broadcast loads of the bias
+          float4 bv;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(bv.x), "=f"(bv.y), "=f"(bv.z), "=f"(bv.w) : "r"(bp + 16 * i));
+          pk[2 * i] = pack_bf16(gelu_exact(__uint_as_float(r[4 * i]) + bv.x), gelu_exact(__uint_as_float(r[4 * i + 1]) + bv.y));
+          pk[2 * i + 1] = pack_bf16(gelu_exact(__uint_as_float(r[4 * i + 2]) + bv.z), gelu_exact(__uint_as_float(r[4 * i + 3]) + bv.w));
+        }
         mbar_wait(&act_empty[b], ((g >> 1) & 1) ^ 1);        // fc2 of chunk g - 2 has read this buffer
         {
           const int col0 = slice * 32;                        // column inside the [128 x 128] activation buffer
