@@ -438,6 +438,7 @@ def run_reference(args):
     mode, _, what = set_config(args.config)
     r = cpu_reference_arm(args.steps, args.warmup, mode=mode)
     cfg = workload_config(1, r["batch"], what, mode, False)
+    cfg["precision"] = "fp32 on the host cores (oracle port)"
     cfg["note"] = ("a bounded CPU sample of the same workload: batch %d per step on the host cores (the GPU arm runs "
                    "its own per-GPU batch); sequences/s normalises it" % r["batch"])
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
