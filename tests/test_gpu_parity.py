@@ -540,6 +540,33 @@ def test_feed_forward_core_inference(d, n):
     assert rel_l2(v_eval.float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("d", [128, 256])
+def test_feed_forward_fused_guard_rows(d):
+    """K10f straight through the C ABI (act = gp = NULL): nothing is written behind the last output row, and an
+    input with huge rows behind its end (which a wrong TMA box would pull in) leaves the result unchanged."""
+    from sl_hwgat_b200 import _lib
+    lib = _lib.load()
+    n, hidden = 128 * 7, 2 * d
+    g = torch.Generator().manual_seed(d + 1)
+    h_all = torch.randn(n + 128, d, generator=g).to(torch.bfloat16).cuda()
+    h_all[n:] = 1e30
+    w1 = (torch.randn(hidden, d, generator=g) / d ** 0.5).to(torch.bfloat16).cuda()
+    b1 = (0.3 * torch.randn(hidden, generator=g)).cuda()
+    w2 = (torch.randn(d, hidden, generator=g) / hidden ** 0.5).to(torch.bfloat16).cuda()
+    v0 = torch.full((n + 128, d), float("nan"), dtype=torch.bfloat16, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.hwgat_ffn_fused_supported(n, d, hidden) == 1
+    _lib.check(lib.hwgat_ffn_fwd(h_all.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), None, None, v0.data_ptr(),
+                                 n, d, hidden, 0.0, 0, 0, st), "hwgat_ffn_fwd")
+    torch.cuda.synchronize()
+    assert torch.isnan(v0[n:]).all() and torch.isfinite(v0[:n]).all()
+    act = torch.nn.functional.gelu(h_all[:n].double() @ w1.double().t() + b1.double()).to(torch.bfloat16).double()
+    assert rel_l2(v0[:n].float(), act @ w2.double().t()) < 4e-3
+    # act == NULL with a dropout probability or a derivative buffer is an argument error, not a silent path
+    assert lib.hwgat_ffn_fwd(h_all.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), None, None, v0.data_ptr(),
+                             n, d, hidden, 0.1, 0, 0, st) != 0
+
+
 @pytest.mark.parametrize("p", [0.1, 0.5])
 def test_feed_forward_core_dropout(p):
     """K10 with dropout: with W2 = I the output is the hidden activation itself, so the mask, its rate, the

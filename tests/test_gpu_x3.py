@@ -55,3 +55,30 @@ def test_x3_off_in_deterministic_mode_and_for_other_shapes(x3_mode):
         assert rel_l2(y, x.detach().double() @ w.detach().double().t()) < 1e-6
     finally:
         ops.set_deterministic(prev)
+
+
+def test_linear_x3_writes_nothing_outside_its_outputs(x3_mode):
+    """straight through the C ABI with NaN guard rows behind every output (the pool has no compute-sanitizer)"""
+    from sl_hwgat_b200 import _lib, ops
+    lib = _lib.load()
+    n, d_in, d_out = 128 * 5, 256, 384
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, d_in, generator=g).cuda()
+    w = (torch.randn(d_out, d_in, generator=g) / 16).cuda()
+    b = torch.randn(d_out, generator=g).cuda()
+    dy = torch.randn(n, d_out, generator=g).cuda()
+    nan = float("nan")
+    y = torch.full((n + 128, d_out), nan, device="cuda")
+    dx = torch.full((n + 128, d_in), nan, device="cuda")
+    dw = torch.full((d_out + 8, d_in), nan, device="cuda")
+    db = torch.full((d_out + 8,), nan, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.hwgat_linear_f32_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), n, d_in, d_out, st), "fwd")
+    _lib.check(lib.hwgat_linear_f32_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+                                        db.data_ptr(), n, d_in, d_out, st), "bwd")
+    torch.cuda.synchronize()
+    assert torch.isnan(y[n:]).all() and torch.isnan(dx[n:]).all() and torch.isnan(dw[d_out:]).all() and torch.isnan(db[d_out:]).all()
+    assert rel_l2(y[:n], x.double() @ w.double().t() + b.double()) < 2e-6
+    assert rel_l2(dx[:n], dy.double() @ w.double()) < 2e-6
+    assert rel_l2(dw[:d_out], dy.double().t() @ x.double()) < 2e-6
+    assert rel_l2(db[:d_out], dy.double().sum(0)) < 2e-6
