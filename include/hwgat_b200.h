@@ -186,6 +186,34 @@ int hwgat_bda_merge_fwd(const float* res, const void* a0, const float* bias, flo
 int hwgat_ln_bwd_unmerge(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
                          const float* gamma, float* dx, float* dgamma, float* dbeta, long long n_merged, int d_merged,
                          int F_merged, int K, hwgat_stream_t stream);
+
+/* The fp32 path's forms of K5 - K7 (the reference's unmodified loop runs without autocast): identical arithmetic and
+ * arguments, but every ACTIVATION tensor that is bf16 above - y, dy, a0, d_a0, u0, g, dg, du0 - is float32 here, so
+ * that the chain LayerNorm -> Linear (x3 tcgen05 GEMM, hwgat_linear_f32_*) -> bias / dropout / residual / LayerNorm
+ * stays in fp32 end to end (HWGATE.py:203-219, 130-134 as written, no autocast).                                   */
+int hwgat_ln_fwd_f32(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                 long long n, int d, float eps, hwgat_stream_t stream);
+int hwgat_ln_bwd_f32(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                 const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d,
+                 hwgat_stream_t stream);
+int hwgat_ln_bwd_unmerge_f32(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                         const float* gamma, float* dx, float* dgamma, float* dbeta, long long n_merged, int d_merged,
+                         int F_merged, int K, hwgat_stream_t stream);
+int hwgat_bda_merge_fwd_f32(const float* res, const void* a0, const float* bias, float* x_merged, long long n, int d, int F,
+                        int K, float p, unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
+int hwgat_bda_ln_fwd_f32(const float* res, const void* a0, const float* bias, const float* gamma, const float* beta,
+                     float* x1, void* y, float* mean, float* rstd, long long n, int d, float eps, float p,
+                     unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
+int hwgat_bda_ln_bwd_f32(const float* g_x1, const void* dy, const float* x1, const float* mean, const float* rstd,
+                     const float* gamma, float* d_res, void* d_a0, float* dbias, float* dgamma, float* dbeta,
+                     long long n, int d, float p, unsigned long long seed, unsigned long long offset,
+                     hwgat_stream_t stream);
+int hwgat_bias_gelu_dropout_fwd_f32(const void* u0, const float* bias, void* g, long long n, int cols, float p,
+                                unsigned long long seed, unsigned long long offset, hwgat_stream_t stream);
+int hwgat_bias_gelu_dropout_bwd_f32(const void* u0, const float* bias, const void* dg, void* du0, float* dbias,
+                                long long n, int cols, float p, unsigned long long seed, unsigned long long offset,
+                                hwgat_stream_t stream);
+
 /* K13: y(fp32) = x(fp32) . w^T + bias: the classifier head self.head (HWGATE.py:359) on the fp32 FFMA GEMM
  * (0.1 - 1 GFLOP; its output feeds a log-softmax, so it stays fp32 also under autocast).  bias may be NULL.       */
 int hwgat_linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, int n, int d_in, int d_out,

@@ -30,7 +30,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 20; }
+int hwgat_version(void) { return 21; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -332,45 +332,72 @@ int hwgat_attn2_bwd_f32(const float* d_out, const float* xn, const float* w_qkv,
   return attn2_bwd_f32(a, W, qkv, (cudaStream_t)stream);
 }
 
-int hwgat_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                 long long n, int d, float eps, hwgat_stream_t stream) {
+static int ln_fwd_impl(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                 long long n, int d, float eps, hwgat_stream_t stream, bool f32) {
   if (n < 0) return HWGAT_ERR_SHAPE;
   if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
   if (n == 0) return HWGAT_OK;
   if (!x || !gamma || !beta || !y || !mean || !rstd) return HWGAT_ERR_NULL;
   if (misaligned(x) || misaligned(gamma) || misaligned(beta) || misaligned(y)) return HWGAT_ERR_ALIGN;
-  return launch_ln_fwd(x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, n, d, eps, (cudaStream_t)stream);
+  return launch_ln_fwd(x, gamma, beta, y, mean, rstd, n, d, eps, (cudaStream_t)stream, f32);
+}
+int hwgat_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                 long long n, int d, float eps, hwgat_stream_t stream) {
+  return ln_fwd_impl(x, gamma, beta, y, mean, rstd, n, d, eps, stream, false);
+}
+int hwgat_ln_fwd_f32(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                 long long n, int d, float eps, hwgat_stream_t stream) {
+  return ln_fwd_impl(x, gamma, beta, y, mean, rstd, n, d, eps, stream, true);
 }
 
-int hwgat_ln_bwd(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+static int ln_bwd_impl(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
                  const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d,
-                 hwgat_stream_t stream) {
+                 hwgat_stream_t stream, bool f32) {
   if (n < 0) return HWGAT_ERR_SHAPE;
   if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
   if (!dgamma || !dbeta) return HWGAT_ERR_NULL;
   if (n > 0 && (!dy || !x || !mean || !rstd || !gamma || !dx)) return HWGAT_ERR_NULL;
   if (misaligned(dy) || misaligned(dres) || misaligned(x) || misaligned(gamma) || misaligned(dx)) return HWGAT_ERR_ALIGN;
-  return launch_ln_bwd((const __nv_bfloat16*)dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, d,
-                       (cudaStream_t)stream);
+  return launch_ln_bwd(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, d, (cudaStream_t)stream, 0, 0, f32);
+}
+int hwgat_ln_bwd(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                 const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d,
+                 hwgat_stream_t stream) {
+  return ln_bwd_impl(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, d, stream, false);
+}
+int hwgat_ln_bwd_f32(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                 const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d,
+                 hwgat_stream_t stream) {
+  return ln_bwd_impl(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, d, stream, true);
 }
 
 static bool bad_p(float p) { return !(p >= 0.f) || p >= 1.f; }
 
-int hwgat_ln_bwd_unmerge(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+static int ln_bwd_unmerge_impl(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
                          const float* gamma, float* dx, float* dgamma, float* dbeta, long long n_merged, int d_merged,
-                         int F_merged, int K, hwgat_stream_t stream) {
+                         int F_merged, int K, hwgat_stream_t stream, bool f32) {
   if (n_merged < 0 || F_merged <= 0 || K <= 0) return HWGAT_ERR_SHAPE;
   if (d_merged != 256 && d_merged != 512) return HWGAT_ERR_UNSUPPORTED;
   if (n_merged % ((long long)F_merged * K) != 0) return HWGAT_ERR_SHAPE;
   if (!dgamma || !dbeta) return HWGAT_ERR_NULL;
   if (n_merged > 0 && (!dy || !x || !mean || !rstd || !gamma || !dx)) return HWGAT_ERR_NULL;
   if (misaligned(dy) || misaligned(dres) || misaligned(x) || misaligned(gamma) || misaligned(dx)) return HWGAT_ERR_ALIGN;
-  return launch_ln_bwd((const __nv_bfloat16*)dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n_merged, d_merged,
-                       (cudaStream_t)stream, F_merged, K);
+  return launch_ln_bwd(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n_merged, d_merged, (cudaStream_t)stream,
+                       F_merged, K, f32);
+}
+int hwgat_ln_bwd_unmerge(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                         const float* gamma, float* dx, float* dgamma, float* dbeta, long long n_merged, int d_merged,
+                         int F_merged, int K, hwgat_stream_t stream) {
+  return ln_bwd_unmerge_impl(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n_merged, d_merged, F_merged, K, stream, false);
+}
+int hwgat_ln_bwd_unmerge_f32(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                         const float* gamma, float* dx, float* dgamma, float* dbeta, long long n_merged, int d_merged,
+                         int F_merged, int K, hwgat_stream_t stream) {
+  return ln_bwd_unmerge_impl(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n_merged, d_merged, F_merged, K, stream, true);
 }
 
-int hwgat_bda_merge_fwd(const float* res, const void* a0, const float* bias, float* x_merged, long long n, int d, int F,
-                        int K, float p, unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+static int bda_merge_fwd_impl(const float* res, const void* a0, const float* bias, float* x_merged, long long n, int d, int F,
+                        int K, float p, unsigned long long seed, unsigned long long offset, hwgat_stream_t stream, bool f32) {
   if (n < 0 || bad_p(p) || F <= 0 || K <= 0) return HWGAT_ERR_SHAPE;
   if (d != 128 && d != 256) return HWGAT_ERR_UNSUPPORTED;
   if (F % 2 != 0) return HWGAT_ERR_UNSUPPORTED;
@@ -378,8 +405,16 @@ int hwgat_bda_merge_fwd(const float* res, const void* a0, const float* bias, flo
   if (n == 0) return HWGAT_OK;
   if (!res || !a0 || !x_merged) return HWGAT_ERR_NULL;
   if (misaligned(res) || misaligned(a0) || misaligned(bias) || misaligned(x_merged)) return HWGAT_ERR_ALIGN;
-  return launch_bda_ln_fwd(res, (const __nv_bfloat16*)a0, bias, nullptr, nullptr, x_merged, nullptr, nullptr, nullptr, n,
-                           d, 0.f, p, seed, offset, (cudaStream_t)stream, F, K);
+  return launch_bda_ln_fwd(res, a0, bias, nullptr, nullptr, x_merged, nullptr, nullptr, nullptr, n, d, 0.f, p, seed,
+                           offset, (cudaStream_t)stream, F, K, f32);
+}
+int hwgat_bda_merge_fwd(const float* res, const void* a0, const float* bias, float* x_merged, long long n, int d, int F,
+                        int K, float p, unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  return bda_merge_fwd_impl(res, a0, bias, x_merged, n, d, F, K, p, seed, offset, stream, false);
+}
+int hwgat_bda_merge_fwd_f32(const float* res, const void* a0, const float* bias, float* x_merged, long long n, int d, int F,
+                        int K, float p, unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  return bda_merge_fwd_impl(res, a0, bias, x_merged, n, d, F, K, p, seed, offset, stream, true);
 }
 
 int hwgat_linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, int n, int d_in, int d_out,
@@ -419,9 +454,9 @@ int hwgat_smooth_ce_bwd(const float* logits, const long long* target, const floa
   return smooth_ce_bwd(logits, target, lse, g, dlogits, rows, classes, smooth, (cudaStream_t)stream);
 }
 
-int hwgat_bda_ln_fwd(const float* res, const void* a0, const float* bias, const float* gamma, const float* beta,
+static int bda_ln_fwd_impl(const float* res, const void* a0, const float* bias, const float* gamma, const float* beta,
                      float* x1, void* y, float* mean, float* rstd, long long n, int d, float eps, float p,
-                     unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+                     unsigned long long seed, unsigned long long offset, hwgat_stream_t stream, bool f32) {
   if (n < 0 || bad_p(p)) return HWGAT_ERR_SHAPE;
   if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
   if (n == 0) return HWGAT_OK;
@@ -430,14 +465,24 @@ int hwgat_bda_ln_fwd(const float* res, const void* a0, const float* bias, const 
   if (misaligned(res) || misaligned(a0) || misaligned(bias) || misaligned(gamma) || misaligned(beta) ||
       misaligned(x1) || misaligned(y))
     return HWGAT_ERR_ALIGN;
-  return launch_bda_ln_fwd(res, (const __nv_bfloat16*)a0, bias, gamma, beta, x1, (__nv_bfloat16*)y, mean, rstd, n, d,
-                           eps, p, seed, offset, (cudaStream_t)stream);
+  return launch_bda_ln_fwd(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, d, eps, p, seed, offset,
+                           (cudaStream_t)stream, 0, 0, f32);
+}
+int hwgat_bda_ln_fwd(const float* res, const void* a0, const float* bias, const float* gamma, const float* beta,
+                     float* x1, void* y, float* mean, float* rstd, long long n, int d, float eps, float p,
+                     unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  return bda_ln_fwd_impl(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, d, eps, p, seed, offset, stream, false);
+}
+int hwgat_bda_ln_fwd_f32(const float* res, const void* a0, const float* bias, const float* gamma, const float* beta,
+                     float* x1, void* y, float* mean, float* rstd, long long n, int d, float eps, float p,
+                     unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  return bda_ln_fwd_impl(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, d, eps, p, seed, offset, stream, true);
 }
 
-int hwgat_bda_ln_bwd(const float* g_x1, const void* dy, const float* x1, const float* mean, const float* rstd,
+static int bda_ln_bwd_impl(const float* g_x1, const void* dy, const float* x1, const float* mean, const float* rstd,
                      const float* gamma, float* d_res, void* d_a0, float* dbias, float* dgamma, float* dbeta,
                      long long n, int d, float p, unsigned long long seed, unsigned long long offset,
-                     hwgat_stream_t stream) {
+                     hwgat_stream_t stream, bool f32) {
   if (n < 0 || bad_p(p)) return HWGAT_ERR_SHAPE;
   if (d != 128 && d != 256 && d != 512) return HWGAT_ERR_UNSUPPORTED;
   if (gamma && (!dgamma || !dbeta)) return HWGAT_ERR_NULL;
@@ -448,8 +493,20 @@ int hwgat_bda_ln_bwd(const float* g_x1, const void* dy, const float* x1, const f
   if (misaligned(g_x1) || misaligned(dy) || misaligned(x1) || misaligned(gamma) || misaligned(d_res) ||
       misaligned(d_a0))
     return HWGAT_ERR_ALIGN;
-  return launch_bda_ln_bwd(g_x1, (const __nv_bfloat16*)dy, x1, mean, rstd, gamma, d_res, (__nv_bfloat16*)d_a0, dbias,
-                           dgamma, dbeta, n, d, p, seed, offset, (cudaStream_t)stream);
+  return launch_bda_ln_bwd(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, p, seed, offset,
+                           (cudaStream_t)stream, f32);
+}
+int hwgat_bda_ln_bwd(const float* g_x1, const void* dy, const float* x1, const float* mean, const float* rstd,
+                     const float* gamma, float* d_res, void* d_a0, float* dbias, float* dgamma, float* dbeta,
+                     long long n, int d, float p, unsigned long long seed, unsigned long long offset,
+                     hwgat_stream_t stream) {
+  return bda_ln_bwd_impl(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, p, seed, offset, stream, false);
+}
+int hwgat_bda_ln_bwd_f32(const float* g_x1, const void* dy, const float* x1, const float* mean, const float* rstd,
+                     const float* gamma, float* d_res, void* d_a0, float* dbias, float* dgamma, float* dbeta,
+                     long long n, int d, float p, unsigned long long seed, unsigned long long offset,
+                     hwgat_stream_t stream) {
+  return bda_ln_bwd_impl(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, p, seed, offset, stream, true);
 }
 
 static int check_gelu(long long n, int cols, float p) {
@@ -458,20 +515,28 @@ static int check_gelu(long long n, int cols, float p) {
   return HWGAT_OK;
 }
 
-int hwgat_bias_gelu_dropout_fwd(const void* u0, const float* bias, void* g, long long n, int cols, float p,
-                                unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+static int bias_gelu_dropout_fwd_impl(const void* u0, const float* bias, void* g, long long n, int cols, float p,
+                                unsigned long long seed, unsigned long long offset, hwgat_stream_t stream, bool f32) {
   int st = check_gelu(n, cols, p);
   if (st) return st;
   if (n == 0) return HWGAT_OK;
   if (!u0 || !g) return HWGAT_ERR_NULL;
   if (misaligned(u0) || misaligned(g)) return HWGAT_ERR_ALIGN;
-  return launch_bias_gelu_dropout((const __nv_bfloat16*)u0, bias, nullptr, (__nv_bfloat16*)g, nullptr, n, cols, p,
-                                  seed, offset, false, (cudaStream_t)stream);
+  return launch_bias_gelu_dropout(u0, bias, nullptr, g, nullptr, n, cols, p, seed, offset, false, (cudaStream_t)stream,
+                                  f32);
+}
+int hwgat_bias_gelu_dropout_fwd(const void* u0, const float* bias, void* g, long long n, int cols, float p,
+                                unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  return bias_gelu_dropout_fwd_impl(u0, bias, g, n, cols, p, seed, offset, stream, false);
+}
+int hwgat_bias_gelu_dropout_fwd_f32(const void* u0, const float* bias, void* g, long long n, int cols, float p,
+                                unsigned long long seed, unsigned long long offset, hwgat_stream_t stream) {
+  return bias_gelu_dropout_fwd_impl(u0, bias, g, n, cols, p, seed, offset, stream, true);
 }
 
-int hwgat_bias_gelu_dropout_bwd(const void* u0, const float* bias, const void* dg, void* du0, float* dbias,
+static int bias_gelu_dropout_bwd_impl(const void* u0, const float* bias, const void* dg, void* du0, float* dbias,
                                 long long n, int cols, float p, unsigned long long seed, unsigned long long offset,
-                                hwgat_stream_t stream) {
+                                hwgat_stream_t stream, bool f32) {
   int st = check_gelu(n, cols, p);
   if (st) return st;
   if (n == 0) {
@@ -480,8 +545,17 @@ int hwgat_bias_gelu_dropout_bwd(const void* u0, const float* bias, const void* d
   }
   if (!u0 || !dg || !du0) return HWGAT_ERR_NULL;
   if (misaligned(u0) || misaligned(dg) || misaligned(du0)) return HWGAT_ERR_ALIGN;
-  return launch_bias_gelu_dropout((const __nv_bfloat16*)u0, bias, (const __nv_bfloat16*)dg, (__nv_bfloat16*)du0, dbias,
-                                  n, cols, p, seed, offset, true, (cudaStream_t)stream);
+  return launch_bias_gelu_dropout(u0, bias, dg, du0, dbias, n, cols, p, seed, offset, true, (cudaStream_t)stream, f32);
+}
+int hwgat_bias_gelu_dropout_bwd(const void* u0, const float* bias, const void* dg, void* du0, float* dbias,
+                                long long n, int cols, float p, unsigned long long seed, unsigned long long offset,
+                                hwgat_stream_t stream) {
+  return bias_gelu_dropout_bwd_impl(u0, bias, dg, du0, dbias, n, cols, p, seed, offset, stream, false);
+}
+int hwgat_bias_gelu_dropout_bwd_f32(const void* u0, const float* bias, const void* dg, void* du0, float* dbias,
+                                long long n, int cols, float p, unsigned long long seed, unsigned long long offset,
+                                hwgat_stream_t stream) {
+  return bias_gelu_dropout_bwd_impl(u0, bias, dg, du0, dbias, n, cols, p, seed, offset, stream, true);
 }
 
 static int check_ffn(long long n, int d, int hidden) {

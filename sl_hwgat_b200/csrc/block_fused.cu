@@ -83,6 +83,24 @@ HW_DEV void fold_groups(float4 (&a)[4]) {
     }
 }
 
+
+// Activation I/O of K5 - K7 in two element types: bf16 (the autocast path: GEMM operands / outputs) and float (the fp32
+// path, whose GEMMs are the x3 tcgen05 kernels of gemm_x3.cu).  Four consecutive elements per access.
+template <class T> HW_DEV float4 ld4(const T* p);
+template <> HW_DEV float4 ld4<bf16>(const bf16* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+}
+template <> HW_DEV float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <class T> HW_DEV void st4(T* p, const float4& v);
+template <> HW_DEV void st4<bf16>(bf16* p, const float4& v) {
+  uint2 o;
+  o.x = pack_bf16(v.x, v.y);
+  o.y = pack_bf16(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+template <> HW_DEV void st4<float>(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
 // ---------------------------------------------------------------------------
 // TemporalMerging (HWGATE.py:55-63) folded into its neighbours.  The merged tensor (B, F/2, K, 2d) is, in units of
 // d-wide rows, (B, F/2, K, 2, d): merging is a ROW permutation of the (B, F, K, d) tensor,
@@ -106,9 +124,9 @@ HW_DEV long long unmerged_row0(long long R, int F2, int K) {
   return (long long)((b * (uint32_t)(2 * F2) + 2u * fi) * (uint32_t)K + k);
 }
 
-template <int kL>
+template <int kL, class T>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, bf16* __restrict__ y,
+                                                     const float* __restrict__ beta, T* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd,
                                                      long long n, float eps) {
   constexpr int d = kL * 16, kRows = 32 / kL;
@@ -140,14 +158,11 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     const float rs = rsqrtf(group_sum<kL>(q) * (1.f / d) + eps);
     if (!ok) continue;
     if (lc == 0) { mean[row] = mu; rstd[row] = rs; }
-    bf16* yr = y + row * d;
+    T* yr = y + row * d;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint2 o;
-      o.x = pack_bf16(v[i].x * rs * gm[i].x + bt[i].x, v[i].y * rs * gm[i].y + bt[i].y);
-      o.y = pack_bf16(v[i].z * rs * gm[i].z + bt[i].z, v[i].w * rs * gm[i].w + bt[i].w);
-      *reinterpret_cast<uint2*>(yr + i * 4 * kL + lc * 4) = o;
-    }
+    for (int i = 0; i < 4; ++i)
+      st4<T>(yr + i * 4 * kL + lc * 4, make_float4(v[i].x * rs * gm[i].x + bt[i].x, v[i].y * rs * gm[i].y + bt[i].y,
+                                                    v[i].z * rs * gm[i].z + bt[i].z, v[i].w * rs * gm[i].w + bt[i].w));
   }
 }
 
@@ -155,8 +170,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 // K5': dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 //      dgamma += sum_rows dy * xhat, dbeta += sum_rows dy   (per-lane partials, smem reduce, one atomic per column per CTA)
 // ---------------------------------------------------------------------------
-template <int kL>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dres,
+template <int kL, class T>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ dres,
                                                      const float* __restrict__ x, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                      float* __restrict__ dx, float* __restrict__ dgamma,
@@ -182,9 +197,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 xv = *reinterpret_cast<const float4*>(x + row * d + i * 4 * kL + lc * 4);
-      uint2 dv = *reinterpret_cast<const uint2*>(dy + row * d + i * 4 * kL + lc * 4);
-      if (!ok) dv = make_uint2(0u, 0u);
-      const float4 dyv = make_float4(bf16_lo(dv.x), bf16_hi(dv.x), bf16_lo(dv.y), bf16_hi(dv.y));
+      float4 dyv = ld4<T>(dy + row * d + i * 4 * kL + lc * 4);
+      if (!ok) dyv = make_float4(0.f, 0.f, 0.f, 0.f);
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       g[i] = make_float4(dyv.x * gm[i].x, dyv.y * gm[i].y, dyv.z * gm[i].z, dyv.w * gm[i].w);
       s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
@@ -243,11 +257,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
 // Thread mapping as K5.  Dropout flags of an 8-element granule (two of the lane's float4) come from one Philox call
 // keyed by (row, pair, lane column), identically in forward and backward.
 // ---------------------------------------------------------------------------
-template <int kL, bool kLN>
-__global__ void __launch_bounds__(256) bda_ln_fwd_kernel(const float* __restrict__ res, const bf16* __restrict__ a0,
+template <int kL, bool kLN, class T>
+__global__ void __launch_bounds__(256) bda_ln_fwd_kernel(const float* __restrict__ res, const T* __restrict__ a0,
                                                          const float* __restrict__ bias, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ x1,
-                                                         bf16* __restrict__ y, float* __restrict__ mean,
+                                                         T* __restrict__ y, float* __restrict__ mean,
                                                          float* __restrict__ rstd, long long n, float eps, float scale,
                                                          uint32_t thresh, unsigned long long seed,
                                                          unsigned long long offset, int mF, int mK) {
@@ -267,13 +281,12 @@ __global__ void __launch_bounds__(256) bda_ln_fwd_kernel(const float* __restrict
     const bool ok = base + sub < n;
     const long long row = ok ? base + sub : 0;   // rows past the end read row 0 and store nothing
     // all loads first (a non-uniform `if (ok)` around load + store made four dependent load -> store rounds)
-    float4 v[4];
-    uint2 av[4];
+    float4 v[4], av[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long long e = row * d + i * 4 * kL + lc * 4;
       v[i] = *reinterpret_cast<const float4*>(res + e);
-      av[i] = *reinterpret_cast<const uint2*>(a0 + e);
+      av[i] = ld4<T>(a0 + e);
     }
     float s = 0.f;
     // one Philox call covers 8 elements: the lane's float4 pair (i, i+1); granule id = (row, pair, lane column)
@@ -284,10 +297,10 @@ __global__ void __launch_bounds__(256) bda_ln_fwd_kernel(const float* __restrict
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint32_t keep = keep2[i >> 1] >> (4 * (i & 1));
-      v[i].x += (keep & 1u) ? (bf16_lo(av[i].x) + bs[i].x) * scale : 0.f;
-      v[i].y += (keep & 2u) ? (bf16_hi(av[i].x) + bs[i].y) * scale : 0.f;
-      v[i].z += (keep & 4u) ? (bf16_lo(av[i].y) + bs[i].z) * scale : 0.f;
-      v[i].w += (keep & 8u) ? (bf16_hi(av[i].y) + bs[i].w) * scale : 0.f;
+      v[i].x += (keep & 1u) ? (av[i].x + bs[i].x) * scale : 0.f;
+      v[i].y += (keep & 2u) ? (av[i].y + bs[i].y) * scale : 0.f;
+      v[i].z += (keep & 4u) ? (av[i].z + bs[i].z) * scale : 0.f;
+      v[i].w += (keep & 8u) ? (av[i].w + bs[i].w) * scale : 0.f;
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
     if (ok) {
@@ -307,22 +320,19 @@ __global__ void __launch_bounds__(256) bda_ln_fwd_kernel(const float* __restrict
     if (!ok) continue;
     if (lc == 0) { mean[row] = mu; rstd[row] = rs; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint2 o;
-      o.x = pack_bf16(v[i].x * rs * gm[i].x + bt[i].x, v[i].y * rs * gm[i].y + bt[i].y);
-      o.y = pack_bf16(v[i].z * rs * gm[i].z + bt[i].z, v[i].w * rs * gm[i].w + bt[i].w);
-      *reinterpret_cast<uint2*>(y + row * d + i * 4 * kL + lc * 4) = o;
-    }
+    for (int i = 0; i < 4; ++i)
+      st4<T>(y + row * d + i * 4 * kL + lc * 4, make_float4(v[i].x * rs * gm[i].x + bt[i].x, v[i].y * rs * gm[i].y + bt[i].y,
+                                                             v[i].z * rs * gm[i].z + bt[i].z, v[i].w * rs * gm[i].w + bt[i].w));
   }
 }
 
 // K6': dx = g_x1 + LN'(dy)  [kLN]  or  dx = g_x1  [!kLN];   d_res = dx (written only if kLN),
 //      d_a0 = mask * scale * dx (bf16),  dbias += colsum(mask * scale * dx),  dgamma / dbeta as K5'.
-template <int kL, bool kLN>
-__global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict__ g_x1, const bf16* __restrict__ dy,
+template <int kL, bool kLN, class T>
+__global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict__ g_x1, const T* __restrict__ dy,
                                                          const float* __restrict__ x1, const float* __restrict__ mean,
                                                          const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                         float* __restrict__ d_res, bf16* __restrict__ d_a0,
+                                                         float* __restrict__ d_res, T* __restrict__ d_a0,
                                                          float* __restrict__ dbias, float* __restrict__ dgamma,
                                                          float* __restrict__ dbeta, long long n, float scale,
                                                          uint32_t thresh, unsigned long long seed,
@@ -349,9 +359,8 @@ __global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict
       for (int i = 0; i < 4; ++i) {
         const long long e = row * d + i * 4 * kL + lc * 4;
         const float4 xv = *reinterpret_cast<const float4*>(x1 + e);
-        uint2 dv = *reinterpret_cast<const uint2*>(dy + e);
-        if (!ok) dv = make_uint2(0u, 0u);
-        const float4 dyv = make_float4(bf16_lo(dv.x), bf16_hi(dv.x), bf16_lo(dv.y), bf16_hi(dv.y));
+        float4 dyv = ld4<T>(dy + e);
+        if (!ok) dyv = make_float4(0.f, 0.f, 0.f, 0.f);
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
         g[i] = make_float4(dyv.x * gm[i].x, dyv.y * gm[i].y, dyv.z * gm[i].z, dyv.w * gm[i].w);
         s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
@@ -386,10 +395,7 @@ __global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict
       const uint32_t keep = keep2[i >> 1] >> (4 * (i & 1));
       const float4 da = make_float4((keep & 1u) ? o[i].x * scale : 0.f, (keep & 2u) ? o[i].y * scale : 0.f,
                                     (keep & 4u) ? o[i].z * scale : 0.f, (keep & 8u) ? o[i].w * scale : 0.f);
-      uint2 pk;
-      pk.x = pack_bf16(da.x, da.y);
-      pk.y = pack_bf16(da.z, da.w);
-      *reinterpret_cast<uint2*>(d_a0 + e) = pk;
+      st4<T>(d_a0 + e, da);
       dbs[i].x += da.x; dbs[i].y += da.y; dbs[i].z += da.z; dbs[i].w += da.w;
     }
   }
@@ -431,9 +437,33 @@ __global__ void __launch_bounds__(256) bda_ln_bwd_kernel(const float* __restrict
 // multiple of the row length, so a thread always sees the same 8 columns (bias in registers, and
 // dbias = colsum(du0) accumulates in registers in the backward).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bias_gelu_dropout_fwd_kernel(const bf16* __restrict__ u0,
+// eight consecutive activation elements (streaming access: touched once)
+template <class T> HW_DEV void ld8(const T* p, float (&o)[8]);
+template <> HW_DEV void ld8<bf16>(const bf16* p, float (&o)[8]) {
+  const int4 v = ld_stream16(p);
+  const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { o[2 * i] = bf16_lo(w[i]); o[2 * i + 1] = bf16_hi(w[i]); }
+}
+template <> HW_DEV void ld8<float>(const float* p, float (&o)[8]) {
+  const int4 a = ld_stream16(p), b = ld_stream16(p + 4);
+  o[0] = __int_as_float(a.x); o[1] = __int_as_float(a.y); o[2] = __int_as_float(a.z); o[3] = __int_as_float(a.w);
+  o[4] = __int_as_float(b.x); o[5] = __int_as_float(b.y); o[6] = __int_as_float(b.z); o[7] = __int_as_float(b.w);
+}
+template <class T> HW_DEV void st8(T* p, const float (&o)[8]);
+template <> HW_DEV void st8<bf16>(bf16* p, const float (&o)[8]) {
+  st_stream16(p, make_int4((int)pack_bf16(o[0], o[1]), (int)pack_bf16(o[2], o[3]), (int)pack_bf16(o[4], o[5]),
+                           (int)pack_bf16(o[6], o[7])));
+}
+template <> HW_DEV void st8<float>(float* p, const float (&o)[8]) {
+  st_stream16(p, make_int4(__float_as_int(o[0]), __float_as_int(o[1]), __float_as_int(o[2]), __float_as_int(o[3])));
+  st_stream16(p + 4, make_int4(__float_as_int(o[4]), __float_as_int(o[5]), __float_as_int(o[6]), __float_as_int(o[7])));
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) bias_gelu_dropout_fwd_kernel(const T* __restrict__ u0,
                                                                     const float* __restrict__ bias,
-                                                                    bf16* __restrict__ g, long long nvec, int cols,
+                                                                    T* __restrict__ g, long long nvec, int cols,
                                                                     float scale, uint32_t thresh,
                                                                     unsigned long long seed, unsigned long long offset) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -445,21 +475,19 @@ __global__ void __launch_bounds__(256) bias_gelu_dropout_fwd_kernel(const bf16* 
     for (int i = 0; i < 8; ++i) bs[i] = bias ? bias[c + i] : 0.f;
   }
   for (long long v = v0; v < nvec; v += stride) {
-    const int4 uv = ld_stream16(u0 + v * 8);
+    float u[8], o[8];
+    ld8<T>(u0 + v * 8, u);
     const uint32_t keep = thresh ? keep8((unsigned long long)v, offset, seed, thresh) : 0xFFu;
-    const uint32_t w[4] = {(uint32_t)uv.x, (uint32_t)uv.y, (uint32_t)uv.z, (uint32_t)uv.w};
-    uint32_t o[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      o[i] = pack_bf16(((keep >> (2 * i)) & 1u) ? gelu_exact(bf16_lo(w[i]) + bs[2 * i]) * scale : 0.f,
-                       ((keep >> (2 * i + 1)) & 1u) ? gelu_exact(bf16_hi(w[i]) + bs[2 * i + 1]) * scale : 0.f);
-    st_stream16(g + v * 8, make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]));
+    for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? gelu_exact(u[i] + bs[i]) * scale : 0.f;
+    st8<T>(g + v * 8, o);
   }
 }
 
-__global__ void __launch_bounds__(256) bias_gelu_dropout_bwd_kernel(const bf16* __restrict__ u0,
+template <class T>
+__global__ void __launch_bounds__(256) bias_gelu_dropout_bwd_kernel(const T* __restrict__ u0,
                                                                     const float* __restrict__ bias,
-                                                                    const bf16* __restrict__ dg, bf16* __restrict__ du0,
+                                                                    const T* __restrict__ dg, T* __restrict__ du0,
                                                                     float* __restrict__ dbias, long long nvec, int cols,
                                                                     float scale, uint32_t thresh,
                                                                     unsigned long long seed, unsigned long long offset,
@@ -472,20 +500,16 @@ __global__ void __launch_bounds__(256) bias_gelu_dropout_bwd_kernel(const bf16* 
 #pragma unroll
   for (int i = 0; i < 8; ++i) { bs[i] = bias ? bias[c0 + i] : 0.f; acc[i] = 0.f; }
   for (long long v = v0; v < nvec; v += stride) {
-    const int4 uv = ld_stream16(u0 + v * 8), gv = ld_stream16(dg + v * 8);
+    float u[8], q[8], o[8];
+    ld8<T>(u0 + v * 8, u);
+    ld8<T>(dg + v * 8, q);
     const uint32_t keep = thresh ? keep8((unsigned long long)v, offset, seed, thresh) : 0xFFu;
-    const uint32_t w[4] = {(uint32_t)uv.x, (uint32_t)uv.y, (uint32_t)uv.z, (uint32_t)uv.w};
-    const uint32_t q[4] = {(uint32_t)gv.x, (uint32_t)gv.y, (uint32_t)gv.z, (uint32_t)gv.w};
-    uint32_t o[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float a = ((keep >> (2 * i)) & 1u) ? bf16_lo(q[i]) * scale * gelu_grad(bf16_lo(w[i]) + bs[2 * i]) : 0.f;
-      const float b = ((keep >> (2 * i + 1)) & 1u) ? bf16_hi(q[i]) * scale * gelu_grad(bf16_hi(w[i]) + bs[2 * i + 1]) : 0.f;
-      o[i] = pack_bf16(a, b);
-      acc[2 * i] += a;
-      acc[2 * i + 1] += b;
+    for (int i = 0; i < 8; ++i) {
+      o[i] = ((keep >> i) & 1u) ? q[i] * scale * gelu_grad(u[i] + bs[i]) : 0.f;
+      acc[i] += o[i];
     }
-    st_stream16(du0 + v * 8, make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]));
+    st8<T>(du0 + v * 8, o);
   }
   if (!dbias) return;
   // threads t, t + G, t + 2G, ... (G = cols/8 column groups, 256 % G == 0) own the same 8 columns
@@ -505,7 +529,7 @@ __global__ void __launch_bounds__(256) bias_gelu_dropout_bwd_kernel(const bf16* 
 }
 
 // ---------------------------------------------------------------------------
-// launchers
+// launchers (f32: the activation tensors y / dy / a0 / d_a0 / u0 / g are float instead of bf16)
 // ---------------------------------------------------------------------------
 static int ew_grid(long long work_items) {
   long long want = (work_items + 255) / 256;
@@ -513,23 +537,29 @@ static int ew_grid(long long work_items) {
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
-int launch_ln_fwd(const float* x, const float* gamma, const float* beta, bf16* y, float* mean, float* rstd,
-                  long long n, int d, float eps, cudaStream_t s) {
+template <class T>
+static int ln_fwd_t(const float* x, const float* gamma, const float* beta, T* y, float* mean, float* rstd, long long n,
+                    int d, float eps, cudaStream_t s) {
   const int grid = ew_grid(n * 32);
   switch (d) {
-    case 128: ln_fwd_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
-    case 256: ln_fwd_kernel<16><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
-    case 512: ln_fwd_kernel<32><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
+    case 128: ln_fwd_kernel<8, T><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
+    case 256: ln_fwd_kernel<16, T><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
+    case 512: ln_fwd_kernel<32, T><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, n, eps); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();
   return (int)cudaGetLastError();
 }
+int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                  long long n, int d, float eps, cudaStream_t s, bool f32) {
+  return f32 ? ln_fwd_t<float>(x, gamma, beta, (float*)y, mean, rstd, n, d, eps, s)
+             : ln_fwd_t<bf16>(x, gamma, beta, (bf16*)y, mean, rstd, n, d, eps, s);
+}
 
-int launch_ln_bwd(const bf16* dy, const float* dres, const float* x, const float* mean, const float* rstd,
-                  const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d, cudaStream_t s,
-                  int unmerge_F2, int unmerge_K) {
-  const int uF2 = unmerge_F2, uK = unmerge_K;
+template <class T>
+static int ln_bwd_t(const T* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                    const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d, cudaStream_t s,
+                    int uF2, int uK) {
   cudaMemsetAsync(dgamma, 0, sizeof(float) * d, s);
   cudaMemsetAsync(dbeta, 0, sizeof(float) * d, s);
   long long want = (n + 7) / 8;
@@ -537,61 +567,72 @@ int launch_ln_bwd(const bf16* dy, const float* dres, const float* x, const float
   float* part;
   if (int st = det_scratch(&part, 2, grid, d, s)) return st;
   switch (d) {
-    case 128: ln_bwd_kernel<8><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK, part); break;
-    case 256: ln_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK, part); break;
-    case 512: ln_bwd_kernel<32><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK, part); break;
+    case 128: ln_bwd_kernel<8, T><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK, part); break;
+    case 256: ln_bwd_kernel<16, T><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK, part); break;
+    case 512: ln_bwd_kernel<32, T><<<grid, 256, 0, s>>>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, uF2, uK, part); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   count_launch();
   det_finish(part, grid, d, dgamma, dbeta, nullptr, s);
   return (int)cudaGetLastError();
 }
+int launch_ln_bwd(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+                  const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d, cudaStream_t s,
+                  int unmerge_F2, int unmerge_K, bool f32) {
+  return f32 ? ln_bwd_t<float>((const float*)dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, d, s, unmerge_F2, unmerge_K)
+             : ln_bwd_t<bf16>((const bf16*)dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, n, d, s, unmerge_F2, unmerge_K);
+}
 
-template <bool kLN>
-static int bda_fwd_dispatch(int grid, cudaStream_t s, const float* res, const bf16* a0, const float* bias,
-                            const float* gamma, const float* beta, float* x1, bf16* y, float* mean, float* rstd,
+template <bool kLN, class T>
+static int bda_fwd_dispatch(int grid, cudaStream_t s, const float* res, const T* a0, const float* bias,
+                            const float* gamma, const float* beta, float* x1, T* y, float* mean, float* rstd,
                             long long n, int d, float eps, float scale, uint32_t thresh, unsigned long long seed,
                             unsigned long long offset, int mF, int mK) {
   switch (d) {
-    case 128: bda_ln_fwd_kernel<8, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset, mF, mK); break;
-    case 256: bda_ln_fwd_kernel<16, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset, mF, mK); break;
-    case 512: bda_ln_fwd_kernel<32, kLN><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset, mF, mK); break;
+    case 128: bda_ln_fwd_kernel<8, kLN, T><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset, mF, mK); break;
+    case 256: bda_ln_fwd_kernel<16, kLN, T><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset, mF, mK); break;
+    case 512: bda_ln_fwd_kernel<32, kLN, T><<<grid, 256, 0, s>>>(res, a0, bias, gamma, beta, x1, y, mean, rstd, n, eps, scale, thresh, seed, offset, mF, mK); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   return 0;
 }
-
-int launch_bda_ln_fwd(const float* res, const bf16* a0, const float* bias, const float* gamma, const float* beta,
-                      float* x1, bf16* y, float* mean, float* rstd, long long n, int d, float eps, float p,
-                      unsigned long long seed, unsigned long long offset, cudaStream_t s, int merge_F, int merge_K) {
-  const int mF = merge_F, mK = merge_K;
+template <class T>
+static int bda_ln_fwd_t(const float* res, const T* a0, const float* bias, const float* gamma, const float* beta, float* x1,
+                        T* y, float* mean, float* rstd, long long n, int d, float eps, float p, unsigned long long seed,
+                        unsigned long long offset, cudaStream_t s, int mF, int mK) {
   const uint32_t thresh = drop_threshold16(p);
   const float scale = thresh ? 65536.f / (65536.f - (float)thresh) : 1.f;
   const int grid = ew_grid(n * 32);
-  int st = gamma ? bda_fwd_dispatch<true>(grid, s, res, a0, bias, gamma, beta, x1, y, mean, rstd, n, d, eps, scale, thresh, seed, offset, mF, mK)
-                 : bda_fwd_dispatch<false>(grid, s, res, a0, bias, gamma, beta, x1, y, mean, rstd, n, d, eps, scale, thresh, seed, offset, mF, mK);
+  int st = gamma ? bda_fwd_dispatch<true, T>(grid, s, res, a0, bias, gamma, beta, x1, y, mean, rstd, n, d, eps, scale, thresh, seed, offset, mF, mK)
+                 : bda_fwd_dispatch<false, T>(grid, s, res, a0, bias, gamma, beta, x1, y, mean, rstd, n, d, eps, scale, thresh, seed, offset, mF, mK);
   if (st) return st;
   count_launch();
   return (int)cudaGetLastError();
 }
+int launch_bda_ln_fwd(const float* res, const void* a0, const float* bias, const float* gamma, const float* beta,
+                      float* x1, void* y, float* mean, float* rstd, long long n, int d, float eps, float p,
+                      unsigned long long seed, unsigned long long offset, cudaStream_t s, int merge_F, int merge_K, bool f32) {
+  return f32 ? bda_ln_fwd_t<float>(res, (const float*)a0, bias, gamma, beta, x1, (float*)y, mean, rstd, n, d, eps, p, seed, offset, s, merge_F, merge_K)
+             : bda_ln_fwd_t<bf16>(res, (const bf16*)a0, bias, gamma, beta, x1, (bf16*)y, mean, rstd, n, d, eps, p, seed, offset, s, merge_F, merge_K);
+}
 
-template <bool kLN>
-static int bda_bwd_dispatch(int grid, cudaStream_t s, const float* g_x1, const bf16* dy, const float* x1,
-                            const float* mean, const float* rstd, const float* gamma, float* d_res, bf16* d_a0,
+template <bool kLN, class T>
+static int bda_bwd_dispatch(int grid, cudaStream_t s, const float* g_x1, const T* dy, const float* x1,
+                            const float* mean, const float* rstd, const float* gamma, float* d_res, T* d_a0,
                             float* dbias, float* dgamma, float* dbeta, long long n, int d, float scale, uint32_t thresh,
                             unsigned long long seed, unsigned long long offset, float* part) {
   switch (d) {
-    case 128: bda_ln_bwd_kernel<8, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset, part); break;
-    case 256: bda_ln_bwd_kernel<16, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset, part); break;
-    case 512: bda_ln_bwd_kernel<32, kLN><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset, part); break;
+    case 128: bda_ln_bwd_kernel<8, kLN, T><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset, part); break;
+    case 256: bda_ln_bwd_kernel<16, kLN, T><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset, part); break;
+    case 512: bda_ln_bwd_kernel<32, kLN, T><<<grid, 256, 0, s>>>(g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, scale, thresh, seed, offset, part); break;
     default: return HWGAT_ERR_UNSUPPORTED;
   }
   return 0;
 }
-
-int launch_bda_ln_bwd(const float* g_x1, const bf16* dy, const float* x1, const float* mean, const float* rstd,
-                      const float* gamma, float* d_res, bf16* d_a0, float* dbias, float* dgamma, float* dbeta,
-                      long long n, int d, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s) {
+template <class T>
+static int bda_ln_bwd_t(const float* g_x1, const T* dy, const float* x1, const float* mean, const float* rstd,
+                        const float* gamma, float* d_res, T* d_a0, float* dbias, float* dgamma, float* dbeta, long long n,
+                        int d, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s) {
   const uint32_t thresh = drop_threshold16(p);
   const float scale = thresh ? 65536.f / (65536.f - (float)thresh) : 1.f;
   if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * d, s);
@@ -603,17 +644,24 @@ int launch_bda_ln_bwd(const float* g_x1, const bf16* dy, const float* x1, const 
   const int grid = (int)(want < 148LL * 4 ? (want < 1 ? 1 : want) : 148LL * 4);
   float* part;
   if (int st = det_scratch(&part, 3, grid, d, s)) return st;
-  int st = gamma ? bda_bwd_dispatch<true>(grid, s, g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, scale, thresh, seed, offset, part)
-                 : bda_bwd_dispatch<false>(grid, s, g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, scale, thresh, seed, offset, part);
+  int st = gamma ? bda_bwd_dispatch<true, T>(grid, s, g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, scale, thresh, seed, offset, part)
+                 : bda_bwd_dispatch<false, T>(grid, s, g_x1, dy, x1, mean, rstd, gamma, d_res, d_a0, dbias, dgamma, dbeta, n, d, scale, thresh, seed, offset, part);
   if (st) return st;
   count_launch();
   det_finish(part, grid, d, dbias, gamma ? dgamma : nullptr, gamma ? dbeta : nullptr, s);
   return (int)cudaGetLastError();
 }
+int launch_bda_ln_bwd(const float* g_x1, const void* dy, const float* x1, const float* mean, const float* rstd,
+                      const float* gamma, float* d_res, void* d_a0, float* dbias, float* dgamma, float* dbeta,
+                      long long n, int d, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s,
+                      bool f32) {
+  return f32 ? bda_ln_bwd_t<float>(g_x1, (const float*)dy, x1, mean, rstd, gamma, d_res, (float*)d_a0, dbias, dgamma, dbeta, n, d, p, seed, offset, s)
+             : bda_ln_bwd_t<bf16>(g_x1, (const bf16*)dy, x1, mean, rstd, gamma, d_res, (bf16*)d_a0, dbias, dgamma, dbeta, n, d, p, seed, offset, s);
+}
 
-int launch_bias_gelu_dropout(const bf16* u0, const float* bias, const bf16* dg, bf16* out, float* dbias, long long n,
-                             int cols, float p, unsigned long long seed, unsigned long long offset, bool backward,
-                             cudaStream_t s) {
+template <class T>
+static int bias_gelu_dropout_t(const T* u0, const float* bias, const T* dg, T* out, float* dbias, long long n, int cols,
+                               float p, unsigned long long seed, unsigned long long offset, bool backward, cudaStream_t s) {
   const long long nvec = n * cols / 8;
   const uint32_t thresh = drop_threshold16(p);
   const float scale = thresh ? 65536.f / (65536.f - (float)thresh) : 1.f;
@@ -622,14 +670,20 @@ int launch_bias_gelu_dropout(const bf16* u0, const float* bias, const bf16* dg, 
     if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * cols, s);
     float* part = nullptr;
     if (dbias) { if (int st = det_scratch(&part, 1, grid, cols, s)) return st; }
-    bias_gelu_dropout_bwd_kernel<<<grid, 256, 0, s>>>(u0, bias, dg, out, dbias, nvec, cols, scale, thresh, seed, offset,
-                                                       part);
+    bias_gelu_dropout_bwd_kernel<T><<<grid, 256, 0, s>>>(u0, bias, dg, out, dbias, nvec, cols, scale, thresh, seed, offset,
+                                                          part);
     if (part) { count_launch(); det_finish(part, grid, cols, dbias, nullptr, nullptr, s); return (int)cudaGetLastError(); }
   } else {
-    bias_gelu_dropout_fwd_kernel<<<grid, 256, 0, s>>>(u0, bias, out, nvec, cols, scale, thresh, seed, offset);
+    bias_gelu_dropout_fwd_kernel<T><<<grid, 256, 0, s>>>(u0, bias, out, nvec, cols, scale, thresh, seed, offset);
   }
   count_launch();
   return (int)cudaGetLastError();
+}
+int launch_bias_gelu_dropout(const void* u0, const float* bias, const void* dg, void* out, float* dbias, long long n,
+                             int cols, float p, unsigned long long seed, unsigned long long offset, bool backward,
+                             cudaStream_t s, bool f32) {
+  return f32 ? bias_gelu_dropout_t<float>((const float*)u0, bias, (const float*)dg, (float*)out, dbias, n, cols, p, seed, offset, backward, s)
+             : bias_gelu_dropout_t<bf16>((const bf16*)u0, bias, (const bf16*)dg, (bf16*)out, dbias, n, cols, p, seed, offset, backward, s);
 }
 
 }  // namespace hwgat

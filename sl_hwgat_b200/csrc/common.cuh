@@ -141,21 +141,23 @@ int launch_mask_pack(const float* adj, int adj_windows, const float* mask, int n
                      cudaStream_t s);
 int launch_merge(const void* src, void* dst, int B, int F, int K, int d, int elem_bytes, bool backward, cudaStream_t s);
 
-int launch_ln_fwd(const float* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* mean, float* rstd,
-                  long long n, int d, float eps, cudaStream_t s);
-int launch_ln_bwd(const __nv_bfloat16* dy, const float* dres, const float* x, const float* mean, const float* rstd,
+// K5 - K7; f32: the activation tensors (y, dy, a0, d_a0, u0, g, dg, du0) are float instead of bf16 (the fp32 path)
+int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                  long long n, int d, float eps, cudaStream_t s, bool f32 = false);
+int launch_ln_bwd(const void* dy, const float* dres, const float* x, const float* mean, const float* rstd,
                   const float* gamma, float* dx, float* dgamma, float* dbeta, long long n, int d, cudaStream_t s,
-                  int unmerge_F2 = 0, int unmerge_K = 0);
-int launch_bda_ln_fwd(const float* res, const __nv_bfloat16* a0, const float* bias, const float* gamma,
-                      const float* beta, float* x1, __nv_bfloat16* y, float* mean, float* rstd, long long n, int d,
-                      float eps, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s,
-                      int merge_F = 0, int merge_K = 0);
-int launch_bda_ln_bwd(const float* g_x1, const __nv_bfloat16* dy, const float* x1, const float* mean, const float* rstd,
-                      const float* gamma, float* d_res, __nv_bfloat16* d_a0, float* dbias, float* dgamma, float* dbeta,
-                      long long n, int d, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s);
-int launch_bias_gelu_dropout(const __nv_bfloat16* u0, const float* bias, const __nv_bfloat16* dg, __nv_bfloat16* out,
-                             float* dbias, long long n, int cols, float p, unsigned long long seed,
-                             unsigned long long offset, bool backward, cudaStream_t s);
+                  int unmerge_F2 = 0, int unmerge_K = 0, bool f32 = false);
+int launch_bda_ln_fwd(const float* res, const void* a0, const float* bias, const float* gamma, const float* beta,
+                      float* x1, void* y, float* mean, float* rstd, long long n, int d, float eps, float p,
+                      unsigned long long seed, unsigned long long offset, cudaStream_t s, int merge_F = 0, int merge_K = 0,
+                      bool f32 = false);
+int launch_bda_ln_bwd(const float* g_x1, const void* dy, const float* x1, const float* mean, const float* rstd,
+                      const float* gamma, float* d_res, void* d_a0, float* dbias, float* dgamma, float* dbeta,
+                      long long n, int d, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s,
+                      bool f32 = false);
+int launch_bias_gelu_dropout(const void* u0, const float* bias, const void* dg, void* out, float* dbias, long long n,
+                             int cols, float p, unsigned long long seed, unsigned long long offset, bool backward,
+                             cudaStream_t s, bool f32 = false);
 
 int launch_embed_fwd(const float* x, const float* Bm, const float* pe, float* out, long long n, int C, int E, int K,
                      int T, float p, unsigned long long seed, unsigned long long offset, cudaStream_t s);

@@ -62,6 +62,7 @@ class AttentionBlock(nn.Module):
     """x + MSA(LN x) over all tokens, then x + FFN(LN x) (GATE.py:88-116).  The fused chain works on the padded
     (B, F, 32, d) stream; the reference's (B, F*K, d) input is accepted, padded and cut back."""
 
+    _chain_io = _hw.PartAttentionBlock._chain_io          # bf16 chain only (the fp32 chain is HWGATE's)
     _fusable = _hw.PartAttentionBlock._fusable
     forward_chain = _hw.PartAttentionBlock.forward_chain
 

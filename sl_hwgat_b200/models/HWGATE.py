@@ -277,14 +277,31 @@ class PartAttentionBlock(nn.Module):
             self._bits_key = key
         return self._bits
 
+    def _chain_io(self, x):
+        """dtype of the activations between the kernels of the fused chain, or None when the block runs module by
+        module.  bf16 under bf16 autocast.  float32 without autocast in the x3 mode of the fp32 path (HWGATE's own
+        blocks): the same kernels K5 - K7 with fp32 activations around the x3 tcgen05 GEMMs (gemm_x3.cu), so the
+        reference's unmodified fp32 loop runs no PyTorch elementwise op inside the blocks either."""
+        if x.dtype != torch.float32 or not x.is_cuda or self.dim not in (128, 256, 512):
+            return None
+        if not (type(self.norm1) is nn.LayerNorm and type(self.norm2) is nn.LayerNorm and isinstance(self.ff.act, nn.GELU)
+                and getattr(self.ff.act, "approximate", "none") == "none"):
+            return None
+        n, hidden = x.numel() // self.dim, self.ff.fc1.weight.shape[0]
+        if _attn_dtype(x) == torch.bfloat16:
+            ok = ops.proj_supported(n, self.dim, self.dim) and ops.ffn_supported(n, self.dim, hidden)
+            return torch.bfloat16 if ok else None
+        if (type(self) is PartAttentionBlock and not torch.is_autocast_enabled() and hidden in (256, 512, 1024)
+                and all(type(m) is nn.Linear and m.weight.dtype == torch.float32
+                        for m in (self.attn.proj, self.ff.fc1, self.ff.fc2))
+                and ops.linear_x3_active(n, self.dim, self.dim) and ops.linear_x3_active(n, self.dim, hidden)
+                and ops.linear_x3_active(n, hidden, self.dim)):
+            return torch.float32
+        return None
+
     def _fusable(self, x):
-        """bf16 autocast on the fp32 residual stream with the stock sub-modules: the elementwise chains
-        around the GEMMs run as the fused kernels K5-K7 instead of PyTorch ops."""
-        return (x.dtype == torch.float32 and _attn_dtype(x) == torch.bfloat16 and self.dim in (128, 256, 512)
-                and type(self.norm1) is nn.LayerNorm and type(self.norm2) is nn.LayerNorm
-                and isinstance(self.ff.act, nn.GELU) and getattr(self.ff.act, "approximate", "none") == "none"
-                and ops.proj_supported(x.numel() // self.dim, self.dim, self.dim)
-                and ops.ffn_supported(x.numel() // self.dim, self.dim, self.ff.fc1.weight.shape[0]))
+        """the elementwise chains around the GEMMs run as the fused kernels K5-K7 instead of PyTorch ops"""
+        return self._chain_io(x) is not None
 
     def _check_shape(self, x):
         B, F, K, d = x.shape
@@ -296,7 +313,7 @@ class PartAttentionBlock(nn.Module):
         if not self._fusable(x):
             x = x + self.attn.attend(self.norm1(x), self.shift_size, self._block_bits(x.device))
             return x + self.ff(self.norm2(x))
-        x, xn = ops.layer_norm_residual(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        x, xn = ops.layer_norm_residual(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, io=self._chain_io(x))
         return self.forward_chain(x, xn, None)[0]
 
     def _context(self, x, xn, bits=None):
@@ -313,15 +330,25 @@ class PartAttentionBlock(nn.Module):
         the next level's first norm1): x_out is stored directly in TemporalMerging's layout (B, F/2, K, 2d) and
         next_norm runs over the merged 2d-wide rows - K4 and its adjoint are folded into K6 / K5'."""
         attn, ff = self.attn, self.ff
+        io = xn.dtype                           # bf16 (autocast) or float32 (the fp32 path in x3 mode)
         ctx = self._context(x, xn, bits)       # (the sibling models WGATE / GATE plug their banded attention in here)
-        a0 = ops.output_projection(ctx, attn.proj.weight)          # K12; bias, dropout, shortcut and norm2: K6
-        x, h = ops.bias_dropout_add_ln(x, a0, attn.proj.bias, self.norm2, attn.proj_drop.p, self.training)
-        # K10: fc1 + bias + GELU + dropout + fc2's matmul on the tcgen05 GEMMs with fused epilogues
-        v0 = ops.feed_forward_core(h, ff.fc1.weight, ff.fc1.bias, ff.fc2.weight, ff.drop.p, self.training)
+        if io == torch.float32:
+            # the same chain with fp32 activations: the three Linears on the x3 tcgen05 GEMM (their biases stay with
+            # K6 / K7, as in the bf16 chain), fc1's bias + GELU + dropout as K7
+            a0 = ops.linear_f32(ctx, attn.proj.weight, None)
+            x, h = ops.bias_dropout_add_ln(x, a0, attn.proj.bias, self.norm2, attn.proj_drop.p, self.training, io=io)
+            act = ops.bias_gelu_dropout(ops.linear_f32(h, ff.fc1.weight, None), ff.fc1.bias, ff.drop.p, self.training,
+                                        io=io)
+            v0 = ops.linear_f32(act, ff.fc2.weight, None)
+        else:
+            a0 = ops.output_projection(ctx, attn.proj.weight)          # K12; bias, dropout, shortcut and norm2: K6
+            x, h = ops.bias_dropout_add_ln(x, a0, attn.proj.bias, self.norm2, attn.proj_drop.p, self.training)
+            # K10: fc1 + bias + GELU + dropout + fc2's matmul on the tcgen05 GEMMs with fused epilogues
+            v0 = ops.feed_forward_core(h, ff.fc1.weight, ff.fc1.bias, ff.fc2.weight, ff.drop.p, self.training)
         # fc2's bias, dropout, residual (and the next norm1): K6
         if merge:
-            return ops.bias_dropout_add_merge_ln(x, v0, ff.fc2.bias, next_norm, ff.drop.p, self.training)
-        return ops.bias_dropout_add_ln(x, v0, ff.fc2.bias, next_norm, ff.drop.p, self.training)
+            return ops.bias_dropout_add_merge_ln(x, v0, ff.fc2.bias, next_norm, ff.drop.p, self.training, io=io)
+        return ops.bias_dropout_add_ln(x, v0, ff.fc2.bias, next_norm, ff.drop.p, self.training, io=io)
 
 
 class PartAttentionLayer(nn.Module):
@@ -358,7 +385,8 @@ class PartAttentionLayer(nn.Module):
         blocks = list(self.blocks)
         if xn is None:
             first = blocks[0]
-            x, xn = ops.layer_norm_residual(x, first.norm1.weight, first.norm1.bias, first.norm1.eps)
+            x, xn = ops.layer_norm_residual(x, first.norm1.weight, first.norm1.bias, first.norm1.eps,
+                                            io=first._chain_io(x))
         fold = (next_level_norm is not None and type(self.downsample) is TemporalMerging
                 and self.downsample.temporal_patch_size == ops.TEMPORAL_PATCH and type(next_level_norm) is nn.LayerNorm
                 and ops.merge_fold_supported(self.dim, x.shape[1]))
@@ -445,7 +473,9 @@ class Model(nn.Module):
         return ops.fourier_embed(x, self.B, self.pos_encoder.pe, self.pos_encoder.dropout.p, self.training)
 
     def forward_features(self, x):
-        fused = x.is_cuda and _attn_dtype(x) == torch.bfloat16 and x.dtype == torch.float32
+        # the fused chain: bf16 autocast, or fp32 without autocast in the x3 mode (PartAttentionBlock._chain_io)
+        fused = x.is_cuda and x.dtype == torch.float32 and (
+            _attn_dtype(x) == torch.bfloat16 or (not torch.is_autocast_enabled() and ops.fp32_mode() == "x3"))
         if fused and self.pe and not self.B.requires_grad and not x.requires_grad:
             x = self._embed_fused(x)
         else:

@@ -99,6 +99,7 @@ class MSA(nn.Module):
 class PartAttentionBlock(nn.Module):
     """x + MSA(LN x) inside keypoint windows over all frames, then x + FFN(LN x) (WGATE.py:126-160)."""
 
+    _chain_io = _hw.PartAttentionBlock._chain_io          # bf16 chain only (the fp32 chain is HWGATE's)
     _fusable = _hw.PartAttentionBlock._fusable
     forward_chain = _hw.PartAttentionBlock.forward_chain
 

@@ -570,12 +570,21 @@ def _philox_stream(device) -> tuple:
     return seed & 0xFFFFFFFFFFFFFFFF, off
 
 
+def _ew(lib, name: str, io: torch.dtype):
+    """K5 - K7 entry point for activations of dtype `io`: bf16 (autocast path) or float32 (fp32 path, `_f32` forms)"""
+    if io == torch.float32:
+        return getattr(lib, name + "_f32")
+    if io != torch.bfloat16:
+        raise _lib.HwgatError(f"activation dtype {io}: the elementwise kernels take bfloat16 or float32")
+    return getattr(lib, name)
+
+
 class _LayerNormResidual(torch.autograd.Function):
     """(x) -> (x, LayerNorm(x) as bf16).  The first output is x itself: routing the residual branch
     through it lets backward add the residual gradient inside the LayerNorm-backward pass (K5')."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps):
+    def forward(ctx, x, gamma, beta, eps, io=torch.bfloat16):
         lib = _lib.load()
         _need_cuda(x, gamma, beta)
         if x.dtype != torch.float32:
@@ -584,49 +593,51 @@ class _LayerNormResidual(torch.autograd.Function):
         d = x_c.shape[-1]
         n = x_c.numel() // d
         g_c, b_c = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        y = torch.empty(x_c.shape, dtype=torch.bfloat16, device=x_c.device)
+        y = torch.empty(x_c.shape, dtype=io, device=x_c.device)
         mean = torch.empty(n, dtype=torch.float32, device=x_c.device)
         rstd = torch.empty(n, dtype=torch.float32, device=x_c.device)
         with torch.cuda.device(x_c.device):
-            check(lib.hwgat_ln_fwd(x_c.data_ptr(), g_c.data_ptr(), b_c.data_ptr(), y.data_ptr(), mean.data_ptr(),
-                                   rstd.data_ptr(), n, d, float(eps), _stream()), "hwgat_ln_fwd")
+            check(_ew(lib, "hwgat_ln_fwd", io)(x_c.data_ptr(), g_c.data_ptr(), b_c.data_ptr(), y.data_ptr(),
+                                               mean.data_ptr(), rstd.data_ptr(), n, d, float(eps), _stream()),
+                  "hwgat_ln_fwd")
         ctx.save_for_backward(x_c, g_c, mean, rstd)
-        ctx.meta = (n, d, gamma.dtype, beta.dtype)
+        ctx.meta = (n, d, gamma.dtype, beta.dtype, io)
         return x_c.detach(), y
 
     @staticmethod
     def backward(ctx, g_res, g_y):
         lib = _lib.load()
         x_c, g_c, mean, rstd = ctx.saved_tensors
-        n, d, gdt, bdt = ctx.meta
+        n, d, gdt, bdt, io = ctx.meta
         if g_y is None:
-            return g_res, None, None, None
-        dy = g_y.to(torch.bfloat16).contiguous()
+            return g_res, None, None, None, None
+        dy = g_y.to(io).contiguous()
         dres = g_res.float().contiguous() if g_res is not None else None
         dx = torch.empty_like(x_c)
         dgamma = torch.empty(d, dtype=torch.float32, device=x_c.device)
         dbeta = torch.empty(d, dtype=torch.float32, device=x_c.device)
         with torch.cuda.device(x_c.device):
-            check(lib.hwgat_ln_bwd(dy.data_ptr(), _ptr(dres), x_c.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                   g_c.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), n, d,
-                                   _stream()), "hwgat_ln_bwd")
-        return dx, dgamma.to(gdt), dbeta.to(bdt), None
+            check(_ew(lib, "hwgat_ln_bwd", io)(dy.data_ptr(), _ptr(dres), x_c.data_ptr(), mean.data_ptr(),
+                                               rstd.data_ptr(), g_c.data_ptr(), dx.data_ptr(), dgamma.data_ptr(),
+                                               dbeta.data_ptr(), n, d, _stream()), "hwgat_ln_bwd")
+        return dx, dgamma.to(gdt), dbeta.to(bdt), None, None
 
 
-def layer_norm_residual(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5):
-    """Returns (x, y): y = LayerNorm(x) in bf16 (norm1 / norm2 of the block + the autocast cast);
-    use the returned x for the residual add."""
-    return _LayerNormResidual.apply(x, gamma, beta, eps)
+def layer_norm_residual(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+                        io: torch.dtype = torch.bfloat16):
+    """Returns (x, y): y = LayerNorm(x) in bf16 (norm1 / norm2 of the block + the autocast cast; io = torch.float32:
+    in fp32, the fp32 path); use the returned x for the residual add."""
+    return _LayerNormResidual.apply(x, gamma, beta, eps, io)
 
 
 class _BiasDropoutAddLN(torch.autograd.Function):
     """x1 = res + dropout(a0 + bias); optionally y = LayerNorm(x1) as bf16 in the same pass (K6 / K6')."""
 
     @staticmethod
-    def forward(ctx, res, a0, bias, gamma, beta, eps, p):
+    def forward(ctx, res, a0, bias, gamma, beta, eps, p, io=torch.bfloat16):
         lib = _lib.load()
         _need_cuda(res, a0, bias, gamma, beta)
-        res_c, a_c = res.contiguous(), a0.to(torch.bfloat16).contiguous()
+        res_c, a_c = res.contiguous(), a0.to(io).contiguous()
         if res_c.dtype != torch.float32 or res_c.shape != a_c.shape:
             raise _lib.HwgatError("bias_dropout_add_ln takes an fp32 residual and a same-shape branch")
         d = res_c.shape[-1]
@@ -638,18 +649,18 @@ class _BiasDropoutAddLN(torch.autograd.Function):
         bt_c = beta.detach().float().contiguous() if has_ln else None
         seed, off = _philox_stream(dev) if p > 0 else (0, 0)
         x1 = torch.empty_like(res_c)
-        y = torch.empty(res_c.shape, dtype=torch.bfloat16, device=dev) if has_ln else None
+        y = torch.empty(res_c.shape, dtype=io, device=dev) if has_ln else None
         mean = torch.empty(n, dtype=torch.float32, device=dev) if has_ln else None
         rstd = torch.empty(n, dtype=torch.float32, device=dev) if has_ln else None
         with torch.cuda.device(dev):
-            check(lib.hwgat_bda_ln_fwd(res_c.data_ptr(), a_c.data_ptr(), _ptr(b_c), _ptr(g_c), _ptr(bt_c),
-                                       x1.data_ptr(), _ptr(y), _ptr(mean), _ptr(rstd), n, d, float(eps), float(p),
-                                       seed, off, _stream()), "hwgat_bda_ln_fwd")
+            check(_ew(lib, "hwgat_bda_ln_fwd", io)(res_c.data_ptr(), a_c.data_ptr(), _ptr(b_c), _ptr(g_c), _ptr(bt_c),
+                                                   x1.data_ptr(), _ptr(y), _ptr(mean), _ptr(rstd), n, d, float(eps),
+                                                   float(p), seed, off, _stream()), "hwgat_bda_ln_fwd")
         if has_ln:
             ctx.save_for_backward(x1, g_c, mean, rstd)
         ctx.meta = (n, d, float(p), seed, off, has_ln, a0.dtype,
                     None if bias is None else bias.dtype, None if gamma is None else gamma.dtype,
-                    None if beta is None else beta.dtype)
+                    None if beta is None else beta.dtype, io)
         if has_ln:
             return x1, y
         return x1, None
@@ -657,38 +668,39 @@ class _BiasDropoutAddLN(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_x1, g_y):
         lib = _lib.load()
-        n, d, p, seed, off, has_ln, adt, bdt, gdt, btdt = ctx.meta
+        n, d, p, seed, off, has_ln, adt, bdt, gdt, btdt, io = ctx.meta
         dev = (g_x1 if g_x1 is not None else g_y).device
         gx = g_x1.float().contiguous() if g_x1 is not None else None
-        d_a0 = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
+        d_a0 = torch.empty((n, d), dtype=io, device=dev)
+        bda_bwd = _ew(lib, "hwgat_bda_ln_bwd", io)
         dbias = torch.empty(d, dtype=torch.float32, device=dev) if bdt is not None else None
         if has_ln:
             x1, g_c, mean, rstd = ctx.saved_tensors
-            dy = (g_y if g_y is not None else torch.zeros_like(x1, dtype=torch.bfloat16)).to(torch.bfloat16).contiguous()
+            dy = (g_y if g_y is not None else torch.zeros_like(x1, dtype=io)).to(io).contiguous()
             d_res = torch.empty_like(x1)
             dgamma = torch.empty(d, dtype=torch.float32, device=dev)
             dbeta = torch.empty(d, dtype=torch.float32, device=dev)
             with torch.cuda.device(dev):
-                check(lib.hwgat_bda_ln_bwd(_ptr(gx), dy.data_ptr(), x1.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                           g_c.data_ptr(), d_res.data_ptr(), d_a0.data_ptr(), _ptr(dbias),
-                                           dgamma.data_ptr(), dbeta.data_ptr(), n, d, p, seed, off, _stream()),
+                check(bda_bwd(_ptr(gx), dy.data_ptr(), x1.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                              g_c.data_ptr(), d_res.data_ptr(), d_a0.data_ptr(), _ptr(dbias),
+                              dgamma.data_ptr(), dbeta.data_ptr(), n, d, p, seed, off, _stream()),
                       "hwgat_bda_ln_bwd")
             shape = x1.shape
             return (d_res, d_a0.view(shape).to(adt), None if dbias is None else dbias.to(bdt), dgamma.to(gdt),
-                    dbeta.to(btdt), None, None)
+                    dbeta.to(btdt), None, None, None)
         with torch.cuda.device(dev):
-            check(lib.hwgat_bda_ln_bwd(gx.data_ptr(), 0, 0, 0, 0, 0, 0, d_a0.data_ptr(), _ptr(dbias), 0, 0, n, d, p,
-                                       seed, off, _stream()), "hwgat_bda_ln_bwd")
-        return gx, d_a0.view(gx.shape).to(adt), None if dbias is None else dbias.to(bdt), None, None, None, None
+            check(bda_bwd(gx.data_ptr(), 0, 0, 0, 0, 0, 0, d_a0.data_ptr(), _ptr(dbias), 0, 0, n, d, p,
+                          seed, off, _stream()), "hwgat_bda_ln_bwd")
+        return gx, d_a0.view(gx.shape).to(adt), None if dbias is None else dbias.to(bdt), None, None, None, None, None
 
 
 def bias_dropout_add_ln(res: torch.Tensor, a0: torch.Tensor, bias: Optional[torch.Tensor], norm, p: float,
-                        training: bool):
+                        training: bool, io: torch.dtype = torch.bfloat16):
     """x1 = res + dropout(a0 + bias) [Linear bias + proj_drop / ff.drop + shortcut, HWGATE.py:115-116, 134-135,
     217, 219] and, if `norm` (an nn.LayerNorm) is given, y = norm(x1) as bf16 in the same pass.  Returns (x1, y)."""
     if norm is None:
-        return _BiasDropoutAddLN.apply(res, a0, bias, None, None, 0.0, p if training else 0.0)
-    return _BiasDropoutAddLN.apply(res, a0, bias, norm.weight, norm.bias, norm.eps, p if training else 0.0)
+        return _BiasDropoutAddLN.apply(res, a0, bias, None, None, 0.0, p if training else 0.0, io)
+    return _BiasDropoutAddLN.apply(res, a0, bias, norm.weight, norm.bias, norm.eps, p if training else 0.0, io)
 
 
 class _BdaMergeLN(torch.autograd.Function):
@@ -698,10 +710,10 @@ class _BdaMergeLN(torch.autograd.Function):
     Replaces K6 + K4 + K5 and K5' + K4' + K6' (HWGATE.py:134-135, 219, 55-63, 203)."""
 
     @staticmethod
-    def forward(ctx, res, a0, bias, gamma, beta, eps, p):
+    def forward(ctx, res, a0, bias, gamma, beta, eps, p, io=torch.bfloat16):
         lib = _lib.load()
         _need_cuda(res, a0, bias, gamma, beta)
-        res_c, a_c = res.contiguous(), a0.to(torch.bfloat16).contiguous()
+        res_c, a_c = res.contiguous(), a0.to(io).contiguous()
         if res_c.dtype != torch.float32 or res_c.shape != a_c.shape or res_c.dim() != 4:
             raise _lib.HwgatError("bias_dropout_add_merge_ln takes an fp32 (B,F,K,d) residual and a same-shape branch")
         B, F, K, d = res_c.shape
@@ -710,47 +722,49 @@ class _BdaMergeLN(torch.autograd.Function):
         g_c, bt_c = cast_cached(gamma, torch.float32), cast_cached(beta, torch.float32)
         seed, off = _philox_stream(dev) if p > 0 else (0, 0)
         xm = torch.empty((B, F // 2, K, 2 * d), dtype=torch.float32, device=dev)
-        y = torch.empty((B, F // 2, K, 2 * d), dtype=torch.bfloat16, device=dev)
+        y = torch.empty((B, F // 2, K, 2 * d), dtype=io, device=dev)
         mean = torch.empty(n // 2, dtype=torch.float32, device=dev)
         rstd = torch.empty(n // 2, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(lib.hwgat_bda_merge_fwd(res_c.data_ptr(), a_c.data_ptr(), _ptr(b_c), xm.data_ptr(), n, d, F, K,
-                                          float(p), seed, off, _stream()), "hwgat_bda_merge_fwd")
-            check(lib.hwgat_ln_fwd(xm.data_ptr(), g_c.data_ptr(), bt_c.data_ptr(), y.data_ptr(), mean.data_ptr(),
-                                   rstd.data_ptr(), n // 2, 2 * d, float(eps), _stream()), "hwgat_ln_fwd")
+            check(_ew(lib, "hwgat_bda_merge_fwd", io)(res_c.data_ptr(), a_c.data_ptr(), _ptr(b_c), xm.data_ptr(), n, d, F,
+                                                      K, float(p), seed, off, _stream()), "hwgat_bda_merge_fwd")
+            check(_ew(lib, "hwgat_ln_fwd", io)(xm.data_ptr(), g_c.data_ptr(), bt_c.data_ptr(), y.data_ptr(),
+                                               mean.data_ptr(), rstd.data_ptr(), n // 2, 2 * d, float(eps), _stream()),
+                  "hwgat_ln_fwd")
         ctx.save_for_backward(xm, g_c, mean, rstd)
         ctx.meta = (B, F, K, d, float(p), seed, off, a0.dtype, None if bias is None else bias.dtype, gamma.dtype,
-                    beta.dtype)
+                    beta.dtype, io)
         return xm, y
 
     @staticmethod
     def backward(ctx, g_xm, g_y):
         lib = _lib.load()
         xm, g_c, mean, rstd = ctx.saved_tensors
-        B, F, K, d, p, seed, off, adt, bdt, gdt, btdt = ctx.meta
+        B, F, K, d, p, seed, off, adt, bdt, gdt, btdt, io = ctx.meta
         n, dev = B * F * K, xm.device
-        dy = (g_y if g_y is not None else torch.zeros_like(xm, dtype=torch.bfloat16)).to(torch.bfloat16).contiguous()
+        dy = (g_y if g_y is not None else torch.zeros_like(xm, dtype=io)).to(io).contiguous()
         gx = g_xm.float().contiguous() if g_xm is not None else None
         d_x1 = torch.empty((B, F, K, d), dtype=torch.float32, device=dev)
         dgamma = torch.empty(2 * d, dtype=torch.float32, device=dev)
         dbeta = torch.empty(2 * d, dtype=torch.float32, device=dev)
-        d_a0 = torch.empty((B, F, K, d), dtype=torch.bfloat16, device=dev)
+        d_a0 = torch.empty((B, F, K, d), dtype=io, device=dev)
         dbias = torch.empty(d, dtype=torch.float32, device=dev) if bdt is not None else None
         with torch.cuda.device(dev):
-            check(lib.hwgat_ln_bwd_unmerge(dy.data_ptr(), _ptr(gx), xm.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                           g_c.data_ptr(), d_x1.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                                           n // 2, 2 * d, F // 2, K, _stream()), "hwgat_ln_bwd_unmerge")
-            check(lib.hwgat_bda_ln_bwd(d_x1.data_ptr(), 0, 0, 0, 0, 0, 0, d_a0.data_ptr(), _ptr(dbias), 0, 0, n, d, p,
-                                       seed, off, _stream()), "hwgat_bda_ln_bwd")
+            check(_ew(lib, "hwgat_ln_bwd_unmerge", io)(dy.data_ptr(), _ptr(gx), xm.data_ptr(), mean.data_ptr(),
+                                                       rstd.data_ptr(), g_c.data_ptr(), d_x1.data_ptr(),
+                                                       dgamma.data_ptr(), dbeta.data_ptr(), n // 2, 2 * d, F // 2, K,
+                                                       _stream()), "hwgat_ln_bwd_unmerge")
+            check(_ew(lib, "hwgat_bda_ln_bwd", io)(d_x1.data_ptr(), 0, 0, 0, 0, 0, 0, d_a0.data_ptr(), _ptr(dbias), 0, 0,
+                                                   n, d, p, seed, off, _stream()), "hwgat_bda_ln_bwd")
         return (d_x1, d_a0.to(adt), None if dbias is None else dbias.to(bdt), dgamma.to(gdt), dbeta.to(btdt), None,
-                None)
+                None, None)
 
 
 def bias_dropout_add_merge_ln(res: torch.Tensor, a0: torch.Tensor, bias: Optional[torch.Tensor], next_norm, p: float,
-                              training: bool):
+                              training: bool, io: torch.dtype = torch.bfloat16):
     """The last residual add of a level, TemporalMerging and the next level's first LayerNorm:
     returns (x_merged fp32 (B,F/2,K,2d), next_norm(x_merged) as bf16)."""
-    return _BdaMergeLN.apply(res, a0, bias, next_norm.weight, next_norm.bias, next_norm.eps, p if training else 0.0)
+    return _BdaMergeLN.apply(res, a0, bias, next_norm.weight, next_norm.bias, next_norm.eps, p if training else 0.0, io)
 
 
 def merge_fold_supported(d: int, frames: int) -> bool:
@@ -759,39 +773,41 @@ def merge_fold_supported(d: int, frames: int) -> bool:
 
 class _BiasGeluDropout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, u0, bias, p):
+    def forward(ctx, u0, bias, p, io=torch.bfloat16):
         lib = _lib.load()
         _need_cuda(u0, bias)
-        u_c = u0.to(torch.bfloat16).contiguous()
+        u_c = u0.to(io).contiguous()
         cols = u_c.shape[-1]
         n = u_c.numel() // cols
         b_c = bias.detach().float().contiguous() if bias is not None else None
         seed, off = _philox_stream(u_c.device) if p > 0 else (0, 0)
         g = torch.empty_like(u_c)
         with torch.cuda.device(u_c.device):
-            check(lib.hwgat_bias_gelu_dropout_fwd(u_c.data_ptr(), _ptr(b_c), g.data_ptr(), n, cols, float(p), seed, off,
-                                                  _stream()), "hwgat_bias_gelu_dropout_fwd")
+            check(_ew(lib, "hwgat_bias_gelu_dropout_fwd", io)(u_c.data_ptr(), _ptr(b_c), g.data_ptr(), n, cols, float(p),
+                                                              seed, off, _stream()), "hwgat_bias_gelu_dropout_fwd")
         ctx.save_for_backward(u_c, b_c)
-        ctx.meta = (n, cols, float(p), seed, off, u0.dtype, None if bias is None else bias.dtype)
+        ctx.meta = (n, cols, float(p), seed, off, u0.dtype, None if bias is None else bias.dtype, io)
         return g
 
     @staticmethod
     def backward(ctx, dg):
         lib = _lib.load()
         u_c, b_c = ctx.saved_tensors
-        n, cols, p, seed, off, udt, bdt = ctx.meta
-        dg_c = dg.to(torch.bfloat16).contiguous()
+        n, cols, p, seed, off, udt, bdt, io = ctx.meta
+        dg_c = dg.to(io).contiguous()
         du = torch.empty_like(u_c)
         dbias = torch.empty(cols, dtype=torch.float32, device=u_c.device) if bdt is not None else None
         with torch.cuda.device(u_c.device):
-            check(lib.hwgat_bias_gelu_dropout_bwd(u_c.data_ptr(), _ptr(b_c), dg_c.data_ptr(), du.data_ptr(), _ptr(dbias),
-                                                  n, cols, p, seed, off, _stream()), "hwgat_bias_gelu_dropout_bwd")
-        return du.to(udt), None if dbias is None else dbias.to(bdt), None
+            check(_ew(lib, "hwgat_bias_gelu_dropout_bwd", io)(u_c.data_ptr(), _ptr(b_c), dg_c.data_ptr(), du.data_ptr(),
+                                                              _ptr(dbias), n, cols, p, seed, off, _stream()),
+                  "hwgat_bias_gelu_dropout_bwd")
+        return du.to(udt), None if dbias is None else dbias.to(bdt), None, None
 
 
-def bias_gelu_dropout(u0: torch.Tensor, bias: Optional[torch.Tensor], p: float, training: bool) -> torch.Tensor:
+def bias_gelu_dropout(u0: torch.Tensor, bias: Optional[torch.Tensor], p: float, training: bool,
+                      io: torch.dtype = torch.bfloat16) -> torch.Tensor:
     """dropout(gelu(u0 + bias)), exact erf GELU: fc1 bias + ff.act + ff.drop (HWGATE.py:131-133)."""
-    return _BiasGeluDropout.apply(u0, bias, p if training else 0.0)
+    return _BiasGeluDropout.apply(u0, bias, p if training else 0.0, io)
 
 
 FFN_FUSED = os.environ.get("HWGAT_FFN_FUSED", "1") != "0"     # A/B switch of the one-kernel inference FeedForward (K10f)
