@@ -152,6 +152,24 @@ HW_DEV uint32_t row_softmax_f32(float (&s)[kTok], uint32_t mask_word, float thre
   return live;
 }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS): the k / v / q / dO rows of a window go to shared memory
+// without passing through registers, all 32 copies of a tile in flight at once
+HW_DEV void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+HW_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// rows [0, 32) of one window / head: src_col = first of the 64 columns inside a row of `stride` floats
+HW_DEV void copy_window_rows(float (*dst)[kHd], const float* __restrict__ src, int stride, int src_col, const TileGeom& g,
+                             int tile, int w, int lane) {
+  const int half = lane >> 4, chunk = lane & 15;     // two rows per instruction, 16 lanes x 16 bytes per row
+#pragma unroll 4
+  for (int it = 0; it < kTok / 2; ++it) {
+    const int j = 2 * it + half;
+    cp_async16(&dst[j][chunk * 4], src + g.token_row(tile, w * kTok + j) * stride + src_col + chunk * 4);
+  }
+}
+
 __global__ void __launch_bounds__(128) attn_core_fwd_f32_kernel(const float* __restrict__ qkv,
                                                                 const uint32_t* __restrict__ bits, float threshold,
                                                                 float* __restrict__ out, TileGeom g) {
@@ -162,14 +180,9 @@ __global__ void __launch_bounds__(128) attn_core_fwd_f32_kernel(const float* __r
   const int d = g.d, d3 = 3 * d;
   const float scale = 0.125f;  // head_dim^-0.5, head_dim = 64
 
-  // k, v rows of the window -> smem (each row: 64 floats, 2 per lane, coalesced)
-  for (int j = 0; j < kTok; ++j) {
-    const float* src = qkv + g.token_row(tile, w * kTok + j) * d3 + h * kHd;
-    float2 kk = *reinterpret_cast<const float2*>(src + d + lane * 2);
-    float2 vv = *reinterpret_cast<const float2*>(src + 2 * d + lane * 2);
-    *reinterpret_cast<float2*>(&sm.k[j][lane * 2]) = kk;
-    *reinterpret_cast<float2*>(&sm.v[j][lane * 2]) = vv;
-  }
+  // k, v rows of the window -> smem, asynchronously (the own q row is fetched meanwhile)
+  copy_window_rows(sm.k, qkv, d3, d + h * kHd, g, tile, w, lane);
+  copy_window_rows(sm.v, qkv, d3, 2 * d + h * kHd, g, tile, w, lane);
   const long long my_row = g.token_row(tile, w * kTok + lane);
   float q[kHd];
   {
@@ -180,6 +193,7 @@ __global__ void __launch_bounds__(128) attn_core_fwd_f32_kernel(const float* __r
       q[4 * e] = t.x * scale; q[4 * e + 1] = t.y * scale; q[4 * e + 2] = t.z * scale; q[4 * e + 3] = t.w * scale;
     }
   }
+  cp_async_wait_all();
   __syncwarp();
   float s[kTok];
 #pragma unroll
@@ -212,13 +226,8 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
   const int d = g.d, d3 = 3 * d;
   const float scale = 0.125f;
 
-  for (int j = 0; j < kTok; ++j) {
-    const long long r = g.token_row(tile, w * kTok + j);
-    const float* src = qkv + r * d3 + h * kHd;
-    *reinterpret_cast<float2*>(&sm.a[j][lane * 2]) = *reinterpret_cast<const float2*>(src + d + lane * 2);
-    *reinterpret_cast<float2*>(&sm.b[j][lane * 2]) = *reinterpret_cast<const float2*>(src + 2 * d + lane * 2);
-  }
-  __syncwarp();
+  copy_window_rows(sm.a, qkv, d3, d + h * kHd, g, tile, w, lane);          // k rows
+  copy_window_rows(sm.b, qkv, d3, 2 * d + h * kHd, g, tile, w, lane);      // v rows
   const long long my_row = g.token_row(tile, w * kTok + lane);
   // ---- lane = query i: P row, dP row, dS row, dQ row
   // (own q / d_out rows come from global into registers: reading smem row `lane`
@@ -232,6 +241,8 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
       float4 t = src[e];
       qr[4 * e] = t.x * scale; qr[4 * e + 1] = t.y * scale; qr[4 * e + 2] = t.z * scale; qr[4 * e + 3] = t.w * scale;
     }
+    cp_async_wait_all();
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < kTok; ++j) s[j] = dot64(qr, sm.a[j]);
   }
@@ -253,6 +264,9 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
       dsum = fmaf(s[j], a, dsum);
     }
   }
+  // v is no longer needed: the d_out rows of the window replace it while dS and dQ are formed
+  __syncwarp();
+  copy_window_rows(sm.b, d_out, d, h * kHd, g, tile, w, lane);
 #pragma unroll
   for (int j = 0; j < kTok; ++j) {
     float dsv = ((live >> j) & 1u) ? s[j] * (dp[j] - dsum) : 0.f;
@@ -273,15 +287,10 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
     for (int e = 0; e < kHd / 4; ++e)
       dst[e] = make_float4(dq[4 * e] * scale, dq[4 * e + 1] * scale, dq[4 * e + 2] * scale, dq[4 * e + 3] * scale);
   }
+  // ---- lane = key j: dK row = scale * sum_i dS[i][j] q_i ; dV row = sum_i P[i][j] g_i   (q rows replace k)
   __syncwarp();
-  // ---- lane = key j: dK row = sum_i dS[i][j] q_i ; dV row = sum_i P[i][j] g_i   (q, d_out rows replace k, v)
-  for (int j = 0; j < kTok; ++j) {
-    const long long r = g.token_row(tile, w * kTok + j);
-    float2 qq = *reinterpret_cast<const float2*>(qkv + r * d3 + h * kHd + lane * 2);
-    qq.x *= scale; qq.y *= scale;
-    *reinterpret_cast<float2*>(&sm.a[j][lane * 2]) = qq;
-    *reinterpret_cast<float2*>(&sm.b[j][lane * 2]) = *reinterpret_cast<const float2*>(d_out + r * d + h * kHd + lane * 2);
-  }
+  copy_window_rows(sm.a, qkv, d3, h * kHd, g, tile, w, lane);
+  cp_async_wait_all();
   __syncwarp();
   {
     float acc[kHd];
@@ -294,7 +303,8 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
     }
     float4* dst = reinterpret_cast<float4*>(dqkv + my_row * d3 + d + h * kHd);
 #pragma unroll
-    for (int e = 0; e < kHd / 4; ++e) dst[e] = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+    for (int e = 0; e < kHd / 4; ++e)
+      dst[e] = make_float4(acc[4 * e] * scale, acc[4 * e + 1] * scale, acc[4 * e + 2] * scale, acc[4 * e + 3] * scale);
 #pragma unroll
     for (int e = 0; e < kHd; ++e) acc[e] = 0.f;
     for (int i = 0; i < kTok; ++i) {
