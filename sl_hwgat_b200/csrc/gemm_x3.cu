@@ -252,29 +252,31 @@ struct X3TnCfg {
   static constexpr int kStage = 6 * kPlane;
   static constexpr int kBarOff = kStages * kStage;
   static constexpr int kSmem = kBarOff + 256 + 1024;
-  static constexpr int kTmemCols = 256;                   // 128 leading + 128 corrections
+  static constexpr int kTmemCols = 512;                   // two sets of (128 leading + 128 corrections)
 };
 constexpr int kMainKBlocks = 16;   // 1024 tokens
 
+// Persistent: a work item = (128 x 128 tile, token chain); the CTAs walk the items with a grid stride, two accumulator
+// sets in TMEM so that the red.global.add epilogue of one chain runs under the MMAs of the next (one CTA per chain - the
+// first version - spent a third of its time in set-up, pipeline fill and the epilogue: tensor pipe 48 % busy).
 __global__ void __launch_bounds__(192, 1) gemm_tn_x3_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB,
-                                                            float* __restrict__ C, int N, int kd_rows, int k_blocks_total) {
+                                                            float* __restrict__ C, int N, int kd_rows, int k_blocks_total,
+                                                            int tiles, int items) {
   using Cfg = X3TnCfg;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
   uint64_t* empty = full + Cfg::kStages;
   uint64_t* acc_full = empty + Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blocks = N / 128;
-  const int mb = blockIdx.x / n_blocks, nb = blockIdx.x - mb * n_blocks;
-  const int kb0 = blockIdx.y * kMainKBlocks;
-  const int kb1 = kb0 + kMainKBlocks < k_blocks_total ? kb0 + kMainKBlocks : k_blocks_total;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -285,66 +287,94 @@ __global__ void __launch_bounds__(192, 1) gemm_tn_x3_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // item -> (tile, chain): consecutive items are the tiles of ONE token chain, so the CTAs running at the same time
+  // read the same token rows of the planes (L2 hits across tiles)
   if (warp == 0) {
     int s = 0;
     uint32_t ph = 0;
-    for (int kb = kb0; kb < kb1; ++kb) {
-      mbar_wait(&empty[s], ph ^ 1);
-      if (elect_one_sync()) {
-        unsigned char* st = smem + s * Cfg::kStage;
-        mbar_expect_tx(&full[s], Cfg::kStage);
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int chain = item / tiles, tile = item - chain * tiles;
+      const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
+      const int kb0 = chain * kMainKBlocks;
+      const int kb1 = kb0 + kMainKBlocks < k_blocks_total ? kb0 + kMainKBlocks : k_blocks_total;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one_sync()) {
+          unsigned char* st = smem + s * Cfg::kStage;
+          mbar_expect_tx(&full[s], Cfg::kStage);
 #pragma unroll
-        for (int p = 0; p < 3; ++p)
+          for (int p = 0; p < 3; ++p)
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            tma_load_2d(st + p * Cfg::kPlane + j * 8192, &tmA, &full[s], mb * 128 + j * 64, p * kd_rows + kb * 64);
-            tma_load_2d(st + (3 + p) * Cfg::kPlane + j * 8192, &tmB, &full[s], nb * 128 + j * 64, p * kd_rows + kb * 64);
-          }
+            for (int j = 0; j < 2; ++j) {
+              tma_load_2d(st + p * Cfg::kPlane + j * 8192, &tmA, &full[s], mb * 128 + j * 64, p * kd_rows + kb * 64);
+              tma_load_2d(st + (3 + p) * Cfg::kPlane + j * 8192, &tmB, &full[s], nb * 128 + j * 64, p * kd_rows + kb * 64);
+            }
+        }
+        __syncwarp();
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = umma_idesc_bf16(128, 128, true, true);
     constexpr int kPa[5] = {2, 0, 1, 1, 0};
     constexpr int kPb[5] = {0, 2, 1, 0, 1};
-    int s = 0;
+    int s = 0, it = 0;
     uint32_t ph = 0;
-    for (int kb = kb0; kb < kb1; ++kb) {
-      mbar_wait(&full[s], ph);
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int chain = item / tiles;
+      const int kb0 = chain * kMainKBlocks;
+      const int kb1 = kb0 + kMainKBlocks < k_blocks_total ? kb0 + kMainKBlocks : k_blocks_total;
+      const int buf = it & 1;
+      const uint32_t t_main = tmem + buf * 256, t_corr = t_main + 128;
+      mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      if (elect_one_sync()) {
-        const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + 3 * Cfg::kPlane;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStage), sb = sa + 3 * Cfg::kPlane;
 #pragma unroll
-        for (int c = 0; c < 5; ++c)
+          for (int c = 0; c < 5; ++c)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)   // 16 tokens per step = two 8-row atoms = 2 KB
-            umma_bf16(tmem + 128, umma_desc_mn_sw128(sa + kPa[c] * Cfg::kPlane + ks * 2048, 8192, 1024),
-                      umma_desc_mn_sw128(sb + kPb[c] * Cfg::kPlane + ks * 2048, 8192, 1024), idesc, (kb > kb0) | (ks | c));
+            for (int ks = 0; ks < 4; ++ks)   // 16 tokens per step = two 8-row atoms = 2 KB
+              umma_bf16(t_corr, umma_desc_mn_sw128(sa + kPa[c] * Cfg::kPlane + ks * 2048, 8192, 1024),
+                        umma_desc_mn_sw128(sb + kPb[c] * Cfg::kPlane + ks * 2048, 8192, 1024), idesc, (kb > kb0) | (ks | c));
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tmem, umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024), umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024),
-                    idesc, (kb > kb0) | ks);
-        umma_commit(&empty[s]);
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(t_main, umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024), umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024),
+                      idesc, (kb > kb0) | ks);
+          umma_commit(&empty[s]);
+          if (kb == kb1 - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
     }
-    if (elect_one_sync()) umma_commit(acc_full);
-    __syncwarp();
   } else {
     const int q = warp & 3;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    float* crow = C + (size_t)(mb * 128 + q * 32 + lane) * N + (size_t)nb * 128;
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int chain = item / tiles, tile = item - chain * tiles;
+      const int mb = tile / n_blocks, nb = tile - mb * n_blocks;
+      const int buf = it & 1;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      float* crow = C + (size_t)(mb * 128 + q * 32 + lane) * N + (size_t)nb * 128;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * 256;
 #pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {
-      uint32_t r[32], r2[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, r);
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + c, r2);
-      tmem_ld_wait();
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t r[32], r2[32];
+        tmem_ld32(taddr + c, r);
+        tmem_ld32(taddr + 128 + c, r2);
+        tmem_ld_wait();
+        if (c == 96) {                       // last read of this accumulator set: hand it back before the atomics
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
 #pragma unroll
-      for (int i = 0; i < 32; ++i) atomicAdd(crow + c + i, __uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        for (int i = 0; i < 32; ++i) atomicAdd(crow + c + i, __uint_as_float(r[i]) + __uint_as_float(r2[i]));
+      }
     }
   }
   tc_fence_before();
@@ -362,10 +392,12 @@ static int launch_tn_x3(const bf16* A3, const bf16* B3, float* C, int M, int N, 
   if ((st = make_tmap_2d(&tmB, B3, (uint64_t)(3 * Kd), (uint64_t)N, 64))) return st;
   const int tiles = (M / 128) * (N / 128);
   const int kblocks = (int)(Kd / 64);
-  const int splits = (kblocks + kMainKBlocks - 1) / kMainKBlocks;
-  if (splits > 65535) return HWGAT_ERR_UNSUPPORTED;
+  const long long chains = (kblocks + kMainKBlocks - 1) / kMainKBlocks;
+  const long long items = chains * tiles;
+  if (items > 0x7fffffffLL) return HWGAT_ERR_UNSUPPORTED;
   cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, s);
-  gemm_tn_x3_kernel<<<dim3(tiles, splits), 192, Cfg::kSmem, s>>>(tmA, tmB, C, N, (int)Kd, kblocks);
+  const int grid = items < 148 ? (int)items : 148;
+  gemm_tn_x3_kernel<<<grid, 192, Cfg::kSmem, s>>>(tmA, tmB, C, N, (int)Kd, kblocks, tiles, (int)items);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -373,7 +405,7 @@ static int launch_tn_x3(const bf16* A3, const bf16* B3, float* C, int M, int N, 
 // ---- the three GEMMs of a Linear layer ------------------------------------------------------------------------------
 bool x3_enabled() { return __atomic_load_n(&g_fp32_mode, __ATOMIC_RELAXED) == 1 && !deterministic(); }
 bool x3_supported(long long n, int d_in, int d_out) {
-  return n >= 128 && n % 128 == 0 && n * 3 < 0x7fffffffLL && n / 64 / kMainKBlocks < 65535 && d_in % 128 == 0 &&
+  return n >= 128 && n % 128 == 0 && n * 3 < 0x7fffffffLL && d_in % 128 == 0 &&
          d_out % 128 == 0 && d_in <= 4096 && d_out <= X3Cfg::kMaxBiasN;
 }
 
