@@ -113,6 +113,15 @@ int hwgat_attn_bwd(const void* d_out, const void* xn, const void* w_qkv, const f
                    int B, int F, int K, int d, int heads, int W, int TP, int shift, int layout,
                    int dtype, hwgat_stream_t stream);
 
+
+/* fp32 only: the backward of hwgat_attn_fwd(..., HWGAT_F32, ...) when the caller KEPT the forward's workspace, which
+ * holds the projected rows qkv (n, 3d) fp32: no re-projection (one x3 GEMM and its splits less per block), and the
+ * workspace here holds dqkv only: hwgat_attn_workspace_bytes(B, F, K, d, heads, HWGAT_F32, 0) bytes.               */
+int hwgat_attn_bwd_f32_kept(const float* d_out, const float* xn, const float* w_qkv, const float* qkv,
+                            const uint32_t* bits, float threshold, float* d_xn, float* d_w, float* d_b, void* workspace,
+                            size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int TP, int shift,
+                            int layout, hwgat_stream_t stream);
+
 /* K4 - stage transition.  Replaces TemporalMerging.forward (HWGATE.py:55-63):
  * out[b,fi,k,tp*d+e] = x[b,fi*TP+tp,k,e];  x: (B,F,K,d) -> out: (B,F/TP,K,TP*d). */
 int hwgat_merge_fwd(const void* x, void* out, int B, int F, int K, int d, int TP,

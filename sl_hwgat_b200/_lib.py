@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("HWGAT_B200_LIB") or os.path.join(HERE, "lib", "libhwg
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 21
+ABI_VERSION = 22
 FP32_MODES = {"ffma": 0, "x3": 1}      # HWGAT_FP32_FFMA / HWGAT_FP32_X3 (include/hwgat_b200.h)
 FP32_DEFAULT = "x3"        # the package default; the C library itself starts in FFMA mode
 
@@ -39,6 +39,7 @@ SIGNATURES = {
     "hwgat_attn_workspace_bytes": (c_size_t, [c_int] * 7),
     "hwgat_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t]
                        + [c_int] * 10 + [c_void_p]),
+    "hwgat_attn_bwd_f32_kept": (c_int, [c_void_p] * 5 + [c_float] + [c_void_p] * 4 + [c_size_t] + [c_int] * 9 + [c_void_p]),
     "hwgat_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_size_t] + [c_int] * 10 + [c_void_p]),
     "hwgat_attn2_workspace_bytes": (c_size_t, [c_int] * 7),

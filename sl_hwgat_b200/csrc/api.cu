@@ -30,7 +30,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 21; }
+int hwgat_version(void) { return 22; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -776,6 +776,31 @@ static int merge_common(const void* src, void* dst, int B, int F, int K, int d, 
   if (!src || !dst) return HWGAT_ERR_NULL;
   if (misaligned(src) || misaligned(dst)) return HWGAT_ERR_ALIGN;
   return launch_merge(src, dst, B, F, K, d, eb, backward, (cudaStream_t)stream);
+}
+
+int hwgat_attn_bwd_f32_kept(const float* d_out, const float* xn, const float* w_qkv, const float* qkv,
+                            const uint32_t* bits, float threshold, float* d_xn, float* d_w, float* d_b, void* workspace,
+                            size_t workspace_bytes, int B, int F, int K, int d, int heads, int W, int TP, int shift,
+                            int layout, hwgat_stream_t stream) {
+  int st = check_geometry(B, F, K, d, heads, W, TP, shift, layout, HWGAT_F32);
+  if (st) return st;
+  if (!d_w || !d_b) return HWGAT_ERR_NULL;
+  if (B == 0) {
+    cudaMemsetAsync(d_w, 0, sizeof(float) * 3 * d * d, (cudaStream_t)stream);
+    cudaMemsetAsync(d_b, 0, sizeof(float) * 3 * d, (cudaStream_t)stream);
+    return (int)cudaGetLastError();
+  }
+  if (!d_out || !xn || !w_qkv || !qkv || !bits || !d_xn) return HWGAT_ERR_NULL;
+  if (misaligned(d_out) || misaligned(xn) || misaligned(w_qkv) || misaligned(qkv) || misaligned(d_xn) ||
+      misaligned(d_w) || misaligned(workspace))
+    return HWGAT_ERR_ALIGN;
+  const size_t need = hwgat_attn_workspace_bytes(B, F, K, d, heads, HWGAT_F32, 0);     // dqkv: as large as qkv
+  if (!workspace || workspace_bytes < need) return HWGAT_ERR_WORKSPACE;
+  AttnArgs a{};
+  a.xn = xn; a.w_qkv = w_qkv; a.b_qkv = nullptr; a.bits = bits; a.threshold = threshold; a.d_out = d_out;
+  a.d_xn = d_xn; a.d_w = d_w; a.d_b = d_b; a.workspace = workspace;
+  a.B = B; a.F = F; a.K = K; a.d = d; a.heads = heads; a.shift = shift; a.layout = layout;
+  return attn_bwd_f32(a, (cudaStream_t)stream, qkv);
 }
 
 int hwgat_merge_fwd(const void* x, void* out, int B, int F, int K, int d, int TP, int dtype, hwgat_stream_t stream) {

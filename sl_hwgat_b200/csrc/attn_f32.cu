@@ -367,13 +367,20 @@ int attn_fwd_f32(const AttnArgs& a, cudaStream_t s) {
   return check_last();
 }
 
-int attn_bwd_f32(const AttnArgs& a, cudaStream_t s) {
+// kept_qkv: the projected rows the forward left in ITS workspace (the caller kept that buffer): no re-projection, and
+// the backward workspace holds dqkv only.  NULL: re-project into the first half of the backward workspace.
+int attn_bwd_f32(const AttnArgs& a, cudaStream_t s, const float* kept_qkv) {
   const long long n = (long long)a.B * a.F * a.K;
   const int d = a.d, d3 = 3 * d;
-  float* qkv = (float*)a.workspace;
-  float* dqkv = qkv + n * d3;
   int st;
-  if ((st = linear_f32_fwd((const float*)a.xn, (const float*)a.w_qkv, a.b_qkv, qkv, (int)n, d, d3, s))) return st;
+  const float* qkv = kept_qkv;
+  float* dqkv = (float*)a.workspace;
+  if (!kept_qkv) {
+    float* q = (float*)a.workspace;
+    dqkv = q + n * d3;
+    if ((st = linear_f32_fwd((const float*)a.xn, (const float*)a.w_qkv, a.b_qkv, q, (int)n, d, d3, s))) return st;
+    qkv = q;
+  }
   TileGeom g = make_geom(a.F, a.K, d, a.shift, a.layout);
   constexpr int kWarps = 4;
   size_t smem = kWarps * sizeof(CoreSmemF32Bwd);

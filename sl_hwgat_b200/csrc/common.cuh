@@ -202,7 +202,7 @@ struct AttnArgs {
   int tiles() const { return B * (F / 2) * (K / 64); }
 };
 int attn_fwd_f32(const AttnArgs& a, cudaStream_t s);
-int attn_bwd_f32(const AttnArgs& a, cudaStream_t s);
+int attn_bwd_f32(const AttnArgs& a, cudaStream_t s, const float* kept_qkv = nullptr);
 int attn_fwd_bf16(const AttnArgs& a, cudaStream_t s);
 int attn_bwd_bf16(const AttnArgs& a, cudaStream_t s);
 size_t attn2_workspace_bytes(long long n, int d, int backward, int have_qkv);

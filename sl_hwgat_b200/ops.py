@@ -229,19 +229,31 @@ class _WindowGraphAttention(torch.autograd.Function):
                 check(lib.hwgat_attn_fwd(xn_c.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), bits.data_ptr(),
                                          float(threshold), out.data_ptr(), _ptr(ws), ws_bytes, B, frames, kps, d, heads,
                                          WINDOW, TEMPORAL_PATCH, shift, layout, code, _stream()), "hwgat_attn_fwd")
-        ctx.save_for_backward(xn_c, w_c, b_c, bits, qkv)
+        # fp32: the forward's workspace IS the projected qkv (n, 3d): kept for the backward instead of re-projecting
+        # (12 d bytes per token; one x3 GEMM and its splits less per block)
+        keep_ws = ws if (code == F32 and B > 0 and any(ctx.needs_input_grad[:3])) else None
+        ctx.save_for_backward(xn_c, w_c, b_c, bits, qkv, keep_ws)
         ctx.meta = (float(threshold), heads, shift, layout, frames, kps, B, d, code, w_qkv.dtype, b_qkv.dtype)
         return out.view_as(xn)
 
     @staticmethod
     def backward(ctx, d_out):
         lib = _lib.load()
-        xn_c, w_c, b_c, bits, qkv = ctx.saved_tensors
+        xn_c, w_c, b_c, bits, qkv, kept = ctx.saved_tensors
         threshold, heads, shift, layout, frames, kps, B, d, code, w_dtype, b_dtype = ctx.meta
         g = d_out.to(xn_c.dtype).contiguous()
         d_xn = torch.empty_like(xn_c)
         d_w = torch.empty((3 * d, d), dtype=torch.float32, device=xn_c.device)
         d_b = torch.empty((3 * d,), dtype=torch.float32, device=xn_c.device)
+        if kept is not None:      # fp32 with the forward's qkv kept
+            ws = torch.empty(kept.numel(), dtype=torch.uint8, device=xn_c.device)
+            with torch.cuda.device(xn_c.device):
+                check(lib.hwgat_attn_bwd_f32_kept(g.data_ptr(), xn_c.data_ptr(), w_c.data_ptr(), kept.data_ptr(),
+                                                  bits.data_ptr(), threshold, d_xn.data_ptr(), d_w.data_ptr(),
+                                                  d_b.data_ptr(), ws.data_ptr(), ws.numel(), B, frames, kps, d, heads,
+                                                  WINDOW, TEMPORAL_PATCH, shift, layout, _stream()),
+                      "hwgat_attn_bwd_f32_kept")
+            return (d_xn.view_as(d_out), d_w.to(w_dtype), d_b.to(b_dtype)) + (None,) * 8
         if qkv is not None:       # hybrid: K3b on the q, k, v kept by K2 (q, k column-permuted: qk_perm = 1)
             ws_bytes = lib.hwgat_attn2_workspace_bytes(B, frames, kps, d, heads, 1, 1)
             ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xn_c.device)
