@@ -230,6 +230,16 @@ int hwgat_linear_f32_fwd(const float* x, const float* w, const float* bias, floa
 /* K13': dx = dy . w, dw = dy^T . x, db = column sums of dy; each output may be NULL (skipped).                    */
 int hwgat_linear_f32_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int n,
                          int d_in, int d_out, hwgat_stream_t stream);
+
+/* The x3 form of the two entries above with the split of x kept between them: hwgat_linear_x3_fwd also writes the three
+ * bf16 planes of x (hi, mid, lo: [3][n][d_in], caller-owned) and hwgat_linear_x3_bwd takes them instead of x - the
+ * weight gradient contracts the same planes, so x is neither split twice nor kept in fp32.  Shapes for which
+ * hwgat_linear_x3_supported() is 0 return HWGAT_ERR_UNSUPPORTED (use hwgat_linear_f32_*).  dx, dw, db may be NULL.  */
+int hwgat_linear_x3_supported(long long n, int d_in, int d_out);
+int hwgat_linear_x3_fwd(const float* x, const float* w, const float* bias, float* y, void* x_planes, long long n, int d_in,
+                        int d_out, hwgat_stream_t stream);
+int hwgat_linear_x3_bwd(const float* dy, const void* x_planes, const float* w, float* dx, float* dw, float* db,
+                        long long n, int d_in, int d_out, hwgat_stream_t stream);
 /* K14: label-smoothed cross entropy, SmoothedCrossEntropyLoss.forward (losses/SmoothCrossEntropy.py:35-39):
  * loss = mean_b [(1-smooth) * (-logp[b, target_b]) + smooth * (-mean_c logp[b, c])]; logits (rows, classes) fp32,
  * target int64; lse and row_loss (rows) are saved / scratch; the mean is a fixed-order sum (deterministic).        */

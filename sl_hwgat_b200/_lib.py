@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("HWGAT_B200_LIB") or os.path.join(HERE, "lib", "libhwg
 
 F32, BF16 = 0, 1
 LAYOUT_BFKD, LAYOUT_WINDOWS = 0, 1
-ABI_VERSION = 22
+ABI_VERSION = 23
 FP32_MODES = {"ffma": 0, "x3": 1}      # HWGAT_FP32_FFMA / HWGAT_FP32_X3 (include/hwgat_b200.h)
 FP32_DEFAULT = "x3"        # the package default; the C library itself starts in FFMA mode
 
@@ -66,6 +66,9 @@ SIGNATURES = {
                                                       c_void_p]),
     "hwgat_ln_bwd_unmerge": (c_int, [c_void_p] * 9 + [c_longlong, c_int, c_int, c_int, c_void_p]),
     "hwgat_ln_bwd_unmerge_f32": (c_int, [c_void_p] * 9 + [c_longlong, c_int, c_int, c_int, c_void_p]),
+    "hwgat_linear_x3_supported": (c_int, [c_longlong, c_int, c_int]),
+    "hwgat_linear_x3_fwd": (c_int, [c_void_p] * 5 + [c_longlong, c_int, c_int, c_void_p]),
+    "hwgat_linear_x3_bwd": (c_int, [c_void_p] * 6 + [c_longlong, c_int, c_int, c_void_p]),
     "hwgat_linear_f32_fwd": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_void_p]),
     "hwgat_linear_f32_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p]),
     "hwgat_smooth_ce_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_float, c_void_p]),

@@ -30,7 +30,7 @@ using namespace hwgat;
 
 extern "C" {
 
-int hwgat_version(void) { return 22; }
+int hwgat_version(void) { return 23; }
 
 const char* hwgat_error_string(int status) {
   switch (status) {
@@ -438,6 +438,31 @@ int hwgat_linear_f32_bwd(const float* dy, const float* x, const float* w, float*
   if (!dy || (dx && !w) || (dw && !x)) return HWGAT_ERR_NULL;
   if ((n + 63) / 64 > 65535) return HWGAT_ERR_UNSUPPORTED;
   return linear_f32_bwd(dy, x, w, dx, dw, db, n, d_in, d_out, s);
+}
+
+/* x3 Linear with the split of x kept by the caller (see hwgat_b200.h) */
+int hwgat_linear_x3_supported(long long n, int d_in, int d_out) { return x3_supported(n, d_in, d_out) ? 1 : 0; }
+
+int hwgat_linear_x3_fwd(const float* x, const float* w, const float* bias, float* y, void* x_planes, long long n, int d_in,
+                        int d_out, hwgat_stream_t stream) {
+  if (n <= 0 || d_in <= 0 || d_out <= 0) return HWGAT_ERR_SHAPE;
+  if (!x3_supported(n, d_in, d_out)) return HWGAT_ERR_UNSUPPORTED;
+  if (!x || !w || !y) return HWGAT_ERR_NULL;
+  if (misaligned(x) || misaligned(w) || misaligned(y) || misaligned(x_planes)) return HWGAT_ERR_ALIGN;
+  return linear_x3_fwd(x, w, bias, y, n, d_in, d_out, (cudaStream_t)stream, (__nv_bfloat16*)x_planes);
+}
+
+int hwgat_linear_x3_bwd(const float* dy, const void* x_planes, const float* w, float* dx, float* dw, float* db,
+                        long long n, int d_in, int d_out, hwgat_stream_t stream) {
+  if (n <= 0 || d_in <= 0 || d_out <= 0) return HWGAT_ERR_SHAPE;
+  if (!x3_supported(n, d_in, d_out)) return HWGAT_ERR_UNSUPPORTED;
+  if (!dy || (dx && !w) || (dw && !x_planes)) return HWGAT_ERR_NULL;
+  if (misaligned(dy) || misaligned(x_planes) || misaligned(w) || misaligned(dx) || misaligned(dw)) return HWGAT_ERR_ALIGN;
+  cudaStream_t s = (cudaStream_t)stream;
+  int st;
+  if ((dx || dw) && (st = linear_x3_bwd(dy, nullptr, w, dx, dw, n, d_in, d_out, s, (const __nv_bfloat16*)x_planes))) return st;
+  if (db && (st = colsum_f32(dy, db, n, d_out, s))) return st;
+  return 0;
 }
 
 int hwgat_smooth_ce_fwd(const float* logits, const long long* target, float* lse, float* row_loss, float* loss,

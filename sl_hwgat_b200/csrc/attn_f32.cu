@@ -627,24 +627,28 @@ int linear_f32_bwd(const float* dy, const float* x, const float* w, float* dx, f
     count_launch();
     if ((st = check_last())) return st;
   }
-  if (db) {
-    cudaMemsetAsync(db, 0, sizeof(float) * d_out, s);
-    if (n <= 4096) {          // the classifier head: one block per 128 columns, plain order
-      dim3 g((d_out + 127) / 128, 1);
-      colsum_f32_kernel<<<g, 128, 0, s>>>(dy, db, n, d_out, n);
-      count_launch();
-    } else {                  // token-sized inputs (the blocks' Linears in the fp32 modes): 512-row partial sums
-      const long long rpb = 512;
-      dim3 g((d_out + 127) / 128, (unsigned)((n + rpb - 1) / rpb));
-      float* part;
-      if ((st = det_scratch(&part, 1, (int)g.y, d_out, s))) return st;
-      colsum_f32_kernel<<<g, 128, 0, s>>>(dy, db, n, d_out, rpb, part);
-      count_launch();
-      det_finish(part, (int)g.y, d_out, db, nullptr, nullptr, s);
-    }
-    if ((st = check_last())) return st;
-  }
+  if (db && (st = colsum_f32(dy, db, n, d_out, s))) return st;
   return 0;
+}
+
+// out[c] = sum over the n rows of x[:, c]
+int colsum_f32(const float* x, float* out, long long n, int cols, cudaStream_t s) {
+  int st;
+  cudaMemsetAsync(out, 0, sizeof(float) * cols, s);
+  if (n <= 4096) {          // the classifier head: one block per 128 columns, plain order
+    dim3 g((cols + 127) / 128, 1);
+    colsum_f32_kernel<<<g, 128, 0, s>>>(x, out, n, cols, n);
+    count_launch();
+  } else {                  // token-sized inputs (the blocks' Linears in the fp32 modes): 512-row partial sums
+    const long long rpb = 512;
+    dim3 g((cols + 127) / 128, (unsigned)((n + rpb - 1) / rpb));
+    float* part;
+    if ((st = det_scratch(&part, 1, (int)g.y, cols, s))) return st;
+    colsum_f32_kernel<<<g, 128, 0, s>>>(x, out, n, cols, rpb, part);
+    count_launch();
+    det_finish(part, (int)g.y, cols, out, nullptr, nullptr, s);
+  }
+  return check_last();
 }
 
 }  // namespace hwgat

@@ -178,9 +178,10 @@ extern int g_fp32_mode;
 bool x3_enabled();
 bool x3_supported(long long n, int d_in, int d_out);
 int linear_x3_fwd(const float* x, const float* w, const float* bias, float* y, long long n, int d_in, int d_out,
-                  cudaStream_t s);
+                  cudaStream_t s, __nv_bfloat16* x_planes_out = nullptr);
 int linear_x3_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, long long n, int d_in,
-                  int d_out, cudaStream_t s);
+                  int d_out, cudaStream_t s, const __nv_bfloat16* x_planes = nullptr);
+int colsum_f32(const float* x, float* out, long long n, int cols, cudaStream_t s);
 int smooth_ce_fwd(const float* logits, const long long* target, float* lse, float* row_loss, float* loss, int rows,
                   int classes, float smooth, cudaStream_t s);
 int smooth_ce_bwd(const float* logits, const long long* target, const float* lse, const float* g, float* dlogits,

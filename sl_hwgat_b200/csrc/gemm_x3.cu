@@ -434,25 +434,28 @@ struct Scratch {     // stream-ordered scratch for the bf16 planes
   ~Scratch() { if (p) cudaFreeAsync(p, s); }
 };
 
+// x_planes_out (optional): caller-owned [3][n][d_in] bf16 that receives the split of x, to be handed to linear_x3_bwd
+// (the weight gradient needs the same planes: no second split, and the fp32 x need not be kept)
 int linear_x3_fwd(const float* x, const float* w, const float* bias, float* y, long long n, int d_in, int d_out,
-                  cudaStream_t s) {
+                  cudaStream_t s, bf16* x_planes_out) {
   Scratch sc(s);
   int st;
   const size_t xe = (size_t)n * d_in, we = (size_t)d_out * d_in;
-  if ((st = sc.get((3 * xe + 3 * we) * sizeof(bf16)))) return st;
-  bf16* x3 = (bf16*)sc.p;
-  bf16* w3 = x3 + 3 * xe;
+  if ((st = sc.get(((x_planes_out ? 0 : 3 * xe) + 3 * we) * sizeof(bf16)))) return st;
+  bf16* w3 = (bf16*)sc.p;
+  bf16* x3 = x_planes_out ? x_planes_out : w3 + 3 * we;
   if ((st = split_rows(x, x3, (long long)xe, s))) return st;
   if ((st = split_rows(w, w3, (long long)we, s))) return st;
   return launch_nt_x3(x3, w3, y, bias, n, d_out, d_in, s);
 }
 
-// dx[n, d_in] = dy . W ; dw[d_out, d_in] = dy^T . x ; either may be NULL (db: the caller's fp32 column sums)
+// dx[n, d_in] = dy . W ; dw[d_out, d_in] = dy^T . x ; either may be NULL (db: the caller's fp32 column sums).
+// x_planes (optional): the split of x kept from linear_x3_fwd; then x itself is not read.
 int linear_x3_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, long long n, int d_in, int d_out,
-                  cudaStream_t s) {
+                  cudaStream_t s, const bf16* x_planes) {
   Scratch sc(s);
   int st;
-  const size_t ye = (size_t)n * d_out, xe = dw ? (size_t)n * d_in : 0, we = dx ? (size_t)d_out * d_in : 0;
+  const size_t ye = (size_t)n * d_out, xe = (dw && !x_planes) ? (size_t)n * d_in : 0, we = dx ? (size_t)d_out * d_in : 0;
   if ((st = sc.get((3 * ye + 3 * xe + 3 * we) * sizeof(bf16)))) return st;
   bf16* y3 = (bf16*)sc.p;
   bf16* x3 = y3 + 3 * ye;
@@ -463,8 +466,8 @@ int linear_x3_bwd(const float* dy, const float* x, const float* w, float* dx, fl
     if ((st = launch_nt_x3(y3, wt3, dx, nullptr, n, d_in, d_out, s))) return st;
   }
   if (dw) {
-    if ((st = split_rows(x, x3, (long long)xe, s))) return st;
-    if ((st = launch_tn_x3(y3, x3, dw, d_out, d_in, n, s))) return st;
+    if (!x_planes && (st = split_rows(x, x3, (long long)xe, s))) return st;
+    if ((st = launch_tn_x3(y3, x_planes ? x_planes : x3, dw, d_out, d_in, n, s))) return st;
   }
   return 0;
 }

@@ -1103,27 +1103,40 @@ class _LinearF32(torch.autograd.Function):
             raise ValueError(f"head weight {tuple(w.shape)} does not match (n, {d_in}) input")
         n = x_c.numel() // d_in
         y = torch.empty(x_c.shape[:-1] + (d_out,), dtype=torch.float32, device=x_c.device)
+        # x3 mode with a weight gradient to come: keep the bf16 planes of x (6 bytes per element) instead of x (4):
+        # the weight-gradient GEMM contracts the same planes, so the backward does not split x again
+        planes = None
+        if ctx.needs_input_grad[1] and n > 0 and linear_x3_active(n, d_in, d_out):
+            planes = torch.empty((3, n, d_in), dtype=torch.bfloat16, device=x_c.device)
         with torch.cuda.device(x_c.device):
-            check(lib.hwgat_linear_f32_fwd(x_c.data_ptr(), w_c.data_ptr(), _ptr(b_c), y.data_ptr(), n, d_in, d_out,
-                                           _stream()), "hwgat_linear_f32_fwd")
-        ctx.save_for_backward(x_c, w_c)
-        ctx.meta = (n, d_in, d_out, x.dtype, w.dtype, None if b is None else b.dtype)
+            if planes is not None:
+                check(lib.hwgat_linear_x3_fwd(x_c.data_ptr(), w_c.data_ptr(), _ptr(b_c), y.data_ptr(), planes.data_ptr(), n,
+                                              d_in, d_out, _stream()), "hwgat_linear_x3_fwd")
+            else:
+                check(lib.hwgat_linear_f32_fwd(x_c.data_ptr(), w_c.data_ptr(), _ptr(b_c), y.data_ptr(), n, d_in, d_out,
+                                               _stream()), "hwgat_linear_f32_fwd")
+        ctx.save_for_backward(x_c if planes is None else None, w_c, planes)
+        ctx.meta = (n, d_in, d_out, x.dtype, w.dtype, None if b is None else b.dtype, tuple(x_c.shape))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         lib = _lib.load()
-        x_c, w_c = ctx.saved_tensors
-        n, d_in, d_out, xdt, wdt, bdt = ctx.meta
+        x_c, w_c, planes = ctx.saved_tensors
+        n, d_in, d_out, xdt, wdt, bdt, xshape = ctx.meta
         dy_c = dy.float().contiguous()
-        dev = x_c.device
+        dev = w_c.device
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], bdt is not None and ctx.needs_input_grad[2]
-        dx = torch.empty_like(x_c) if need_x else None
+        dx = torch.empty(xshape, dtype=torch.float32, device=dev) if need_x else None
         dw = torch.empty((d_out, d_in), dtype=torch.float32, device=dev) if need_w else None
         db = torch.empty((d_out,), dtype=torch.float32, device=dev) if need_b else None
         with torch.cuda.device(dev):
-            check(lib.hwgat_linear_f32_bwd(dy_c.data_ptr(), x_c.data_ptr(), w_c.data_ptr(), _ptr(dx), _ptr(dw), _ptr(db),
-                                           n, d_in, d_out, _stream()), "hwgat_linear_f32_bwd")
+            if planes is not None:
+                check(lib.hwgat_linear_x3_bwd(dy_c.data_ptr(), planes.data_ptr(), w_c.data_ptr(), _ptr(dx), _ptr(dw),
+                                              _ptr(db), n, d_in, d_out, _stream()), "hwgat_linear_x3_bwd")
+            else:
+                check(lib.hwgat_linear_f32_bwd(dy_c.data_ptr(), x_c.data_ptr(), w_c.data_ptr(), _ptr(dx), _ptr(dw),
+                                               _ptr(db), n, d_in, d_out, _stream()), "hwgat_linear_f32_bwd")
         return (None if dx is None else dx.to(xdt), None if dw is None else dw.to(wdt),
                 None if db is None else db.to(bdt))
 

@@ -33,7 +33,7 @@ def test_linear_x3_against_fp64(n, d_in, d_out, x3_mode):
     y = ops.linear_f32(x, w, b)
     y.backward(dy)
     torch.cuda.synchronize()
-    assert ops._lib.launch_count() - before >= 3 + 6            # splits + GEMMs + column sums: the x3 path ran (FFMA: 4)
+    assert ops._lib.launch_count() - before >= 3 + 5            # splits + GEMMs + column sums: the x3 path ran (FFMA: 4)
     xd, wd, bd, dyd = x.detach().double(), w.detach().double(), b.detach().double(), dy.double()
     errs = {"y": rel_l2(y, xd @ wd.t() + bd), "dx": rel_l2(x.grad, dyd @ wd), "dw": rel_l2(w.grad, dyd.t() @ xd),
             "db": rel_l2(b.grad, dyd.sum(0)), "y_inf": rel_inf(y, xd @ wd.t() + bd)}
