@@ -91,12 +91,11 @@ def set_fp32_mode(mode: str) -> str:
 
 
 def linear_x3_active(n: int, d_in: int, d_out: int) -> bool:
-    """True when linear_f32 of this shape runs on the tcgen05 x3 GEMM (mode "x3", n, d_in, d_out multiples of 128,
-    not in deterministic mode); mirrors x3_supported in csrc/gemm_x3.cu."""
+    """True when linear_f32 of this shape runs on the tcgen05 x3 GEMM: mode "x3", not in deterministic mode, and a shape
+    gemm_x3.cu takes (n, d_in, d_out multiples of 128: hwgat_linear_x3_supported)."""
     lib = _lib.load()
-    return (lib.hwgat_set_fp32_mode(-1) == _lib.FP32_MODES["x3"] and n >= 128 and n % 128 == 0 and 3 * n < 2 ** 31
-            and d_in % 128 == 0 and d_out % 128 == 0 and d_in <= 4096 and d_out <= 2048
-            and not lib.hwgat_set_deterministic(-1))
+    return (lib.hwgat_set_fp32_mode(-1) == _lib.FP32_MODES["x3"] and not lib.hwgat_set_deterministic(-1)
+            and bool(lib.hwgat_linear_x3_supported(n, d_in, d_out)))
 
 
 def fp32_mode() -> str:
