@@ -279,8 +279,8 @@ class PartAttentionBlock(nn.Module):
 
     def _chain_io(self, x):
         """dtype of the activations between the kernels of the fused chain, or None when the block runs module by
-        module.  bf16 under bf16 autocast.  float32 without autocast in the x3 mode of the fp32 path (HWGATE's own
-        blocks): the same kernels K5 - K7 with fp32 activations around the x3 tcgen05 GEMMs (gemm_x3.cu), so the
+        module.  bf16 under bf16 autocast.  float32 without autocast in the x3 mode of the fp32 path (HWGATE's and
+        HGATE's blocks; WGATE / GATE keep PyTorch's elementwise ops there): the same kernels K5 - K7 with fp32 activations around the x3 tcgen05 GEMMs (gemm_x3.cu), so the
         reference's unmodified fp32 loop runs no PyTorch elementwise op inside the blocks either."""
         if x.dtype != torch.float32 or not x.is_cuda or self.dim not in (128, 256, 512):
             return None
@@ -291,7 +291,7 @@ class PartAttentionBlock(nn.Module):
         if _attn_dtype(x) == torch.bfloat16:
             ok = ops.proj_supported(n, self.dim, self.dim) and ops.ffn_supported(n, self.dim, hidden)
             return torch.bfloat16 if ok else None
-        if (type(self) is PartAttentionBlock and not torch.is_autocast_enabled() and hidden in (256, 512, 1024)
+        if (isinstance(self, PartAttentionBlock) and not torch.is_autocast_enabled() and hidden in (256, 512, 1024)
                 and all(type(m) is nn.Linear and m.weight.dtype == torch.float32
                         for m in (self.attn.proj, self.ff.fc1, self.ff.fc2))
                 and ops.linear_x3_active(n, self.dim, self.dim) and ops.linear_x3_active(n, self.dim, hidden)
