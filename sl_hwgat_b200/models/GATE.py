@@ -62,7 +62,7 @@ class AttentionBlock(nn.Module):
     """x + MSA(LN x) over all tokens, then x + FFN(LN x) (GATE.py:88-116).  The fused chain works on the padded
     (B, F, 32, d) stream; the reference's (B, F*K, d) input is accepted, padded and cut back."""
 
-    _chain_io = _hw.PartAttentionBlock._chain_io          # bf16 chain only (the fp32 chain is HWGATE's)
+    _chain_io = _hw.PartAttentionBlock._chain_io          # bf16 under autocast, float32 in the x3 fp32 mode
     _fusable = _hw.PartAttentionBlock._fusable
     forward_chain = _hw.PartAttentionBlock.forward_chain
 
@@ -110,7 +110,7 @@ class AttentionBlock(nn.Module):
         xp = _pad_kp(x.reshape(B, F_K // K, K, d), 2)
         bits = self.band_bits(xp, parent)
         if self.supported(xp):
-            xp, xn = ops.layer_norm_residual(xp, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            xp, xn = ops.layer_norm_residual(xp, self.norm1.weight, self.norm1.bias, self.norm1.eps, io=self._chain_io(xp))
             y = self.forward_chain(xp, xn, None, bits=bits)[0]
         else:
             y = self.forward_generic(xp, bits)
@@ -160,7 +160,7 @@ class Model(nn.Module):
         if not (x.is_cuda and x.shape[2] == self.num_kps <= KP_PAD):
             raise _lib.HwgatError(_NEED_BF16.format("GATE"))
         blocks = list(self.layers)
-        fast = (x.dtype == torch.float32 and _hw._attn_dtype(x) == torch.bfloat16 and self.pe and not x.requires_grad
+        fast = (_hw.chain_enabled(x) and self.pe and not x.requires_grad
                 and type(self.norm) is nn.LayerNorm and self.embed_dim in (128, 256, 512))
         # the keypoint axis is padded to 32: the padded keypoints embed to finite values, have no edges, are never
         # pooled and carry no gradient
@@ -171,7 +171,7 @@ class Model(nn.Module):
         bits = blocks[0].band_bits(x, self) if blocks else None
         if fast and blocks and blocks[0].supported(x):
             first = blocks[0].norm1
-            x, xn = ops.layer_norm_residual(x, first.weight, first.bias, first.eps)                        # K5
+            x, xn = ops.layer_norm_residual(x, first.weight, first.bias, first.eps, io=blocks[0]._chain_io(x))    # K5
             for i, blk in enumerate(blocks):
                 nxt = blocks[i + 1].norm1 if i + 1 < len(blocks) else None
                 x, xn = blk.forward_chain(x, xn, nxt, bits=bits)

@@ -46,6 +46,12 @@ def _attn_dtype(x):
     return torch.float32
 
 
+def chain_enabled(x):
+    """the fused chain can run on x: fp32 CUDA tensor under bf16 autocast, or without autocast in the x3 fp32 mode"""
+    return x.is_cuda and x.dtype == torch.float32 and (
+        _attn_dtype(x) == torch.bfloat16 or (not torch.is_autocast_enabled() and ops.fp32_mode() == "x3"))
+
+
 def linear(mod, x):
     """`mod(x)` for an nn.Linear of a block.  On the fp32 path (no autocast: the reference's own loop) in x3 mode
     (ops.set_fp32_mode / HWGAT_FP32) it runs on the library's tcgen05 fp32 GEMM (gemm_x3.cu) instead of cuBLAS' FFMA
@@ -279,8 +285,7 @@ class PartAttentionBlock(nn.Module):
 
     def _chain_io(self, x):
         """dtype of the activations between the kernels of the fused chain, or None when the block runs module by
-        module.  bf16 under bf16 autocast.  float32 without autocast in the x3 mode of the fp32 path (HWGATE's and
-        HGATE's blocks; WGATE / GATE keep PyTorch's elementwise ops there): the same kernels K5 - K7 with fp32 activations around the x3 tcgen05 GEMMs (gemm_x3.cu), so the
+        module.  bf16 under bf16 autocast.  float32 without autocast in the x3 mode of the fp32 path: the same kernels K5 - K7 with fp32 activations around the x3 tcgen05 GEMMs (gemm_x3.cu), so the
         reference's unmodified fp32 loop runs no PyTorch elementwise op inside the blocks either."""
         if x.dtype != torch.float32 or not x.is_cuda or self.dim not in (128, 256, 512):
             return None
@@ -291,7 +296,7 @@ class PartAttentionBlock(nn.Module):
         if _attn_dtype(x) == torch.bfloat16:
             ok = ops.proj_supported(n, self.dim, self.dim) and ops.ffn_supported(n, self.dim, hidden)
             return torch.bfloat16 if ok else None
-        if (isinstance(self, PartAttentionBlock) and not torch.is_autocast_enabled() and hidden in (256, 512, 1024)
+        if (not torch.is_autocast_enabled() and hidden in (256, 512, 1024)
                 and all(type(m) is nn.Linear and m.weight.dtype == torch.float32
                         for m in (self.attn.proj, self.ff.fc1, self.ff.fc2))
                 and ops.linear_x3_active(n, self.dim, self.dim) and ops.linear_x3_active(n, self.dim, hidden)
@@ -474,8 +479,7 @@ class Model(nn.Module):
 
     def forward_features(self, x):
         # the fused chain: bf16 autocast, or fp32 without autocast in the x3 mode (PartAttentionBlock._chain_io)
-        fused = x.is_cuda and x.dtype == torch.float32 and (
-            _attn_dtype(x) == torch.bfloat16 or (not torch.is_autocast_enabled() and ops.fp32_mode() == "x3"))
+        fused = chain_enabled(x)
         if fused and self.pe and not self.B.requires_grad and not x.requires_grad:
             x = self._embed_fused(x)
         else:

@@ -99,7 +99,7 @@ class MSA(nn.Module):
 class PartAttentionBlock(nn.Module):
     """x + MSA(LN x) inside keypoint windows over all frames, then x + FFN(LN x) (WGATE.py:126-160)."""
 
-    _chain_io = _hw.PartAttentionBlock._chain_io          # bf16 chain only (the fp32 chain is HWGATE's)
+    _chain_io = _hw.PartAttentionBlock._chain_io          # bf16 under autocast, float32 in the x3 fp32 mode
     _fusable = _hw.PartAttentionBlock._fusable
     forward_chain = _hw.PartAttentionBlock.forward_chain
 
@@ -143,7 +143,7 @@ class PartAttentionBlock(nn.Module):
         bits = self.band_bits(x, parent)
         if not self.supported(x):
             return self.forward_generic(x, bits)
-        x, xn = ops.layer_norm_residual(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        x, xn = ops.layer_norm_residual(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, io=self._chain_io(x))
         return self.forward_chain(x, xn, None, bits=bits)[0]
 
 
@@ -192,7 +192,7 @@ class Model(nn.Module):
         if not x.is_cuda:
             raise _lib.HwgatError(_NEED_BF16.format("WGATE"))
         blocks = list(self.layers)
-        fast = (x.dtype == torch.float32 and _hw._attn_dtype(x) == torch.bfloat16 and self.pe and not x.requires_grad
+        fast = (_hw.chain_enabled(x) and self.pe and not x.requires_grad
                 and type(self.norm) is nn.LayerNorm and self.embed_dim in (128, 256, 512))
         if fast:
             x = ops.fourier_embed(x, self.B, self.pos_encoder.pe, self.pos_encoder.dropout.p, self.training)   # K8
@@ -201,12 +201,12 @@ class Model(nn.Module):
         bits = blocks[0].band_bits(x, self) if blocks else None
         if fast and blocks and blocks[0].supported(x):
             first = blocks[0].norm1
-            x, xn = ops.layer_norm_residual(x, first.weight, first.bias, first.eps)                        # K5
+            x, xn = ops.layer_norm_residual(x, first.weight, first.bias, first.eps, io=blocks[0]._chain_io(x))    # K5
             for i, blk in enumerate(blocks):
                 nxt = blocks[i + 1].norm1 if i + 1 < len(blocks) else None
                 x, xn = blk.forward_chain(x, xn, nxt, bits=bits)
         else:
-            # no autocast (fp32): the true-fp32 band kernels between PyTorch LayerNorm / Linear / GELU
+            # shapes the chain does not take (or the FFMA fp32 mode): the band kernels between PyTorch LayerNorm / Linear / GELU
             for blk in blocks:
                 x = blk.forward_generic(x, bits)
         if fast:
