@@ -110,6 +110,31 @@ class HwgatError(RuntimeError):
     pass
 
 
+# Entry points that take stream-ordered scratch inside the library (the bf16 planes of the x3 fp32 GEMMs): the pool
+# cannot grow while PyTorch's caching allocator sits on the free memory, so a HWGAT_ERR_WORKSPACE from them is retried
+# once after the cache has been released (every such call fails before it has written anything, or is idempotent).
+_SCRATCH_CALLS = ("hwgat_attn_fwd", "hwgat_attn_bwd", "hwgat_attn_bwd_f32_kept", "hwgat_attn2_fwd_f32", "hwgat_attn2_bwd_f32",
+                  "hwgat_band_attn_fwd", "hwgat_band_attn_bwd", "hwgat_linear_f32_fwd", "hwgat_linear_f32_bwd",
+                  "hwgat_linear_x3_fwd", "hwgat_linear_x3_bwd")
+ERR_WORKSPACE = 1003
+
+
+def _with_scratch_retry(fn):
+    def call(*args):
+        status = fn(*args)
+        if status == ERR_WORKSPACE:
+            try:
+                import torch
+                torch.cuda.synchronize()
+                torch.cuda.empty_cache()
+            except Exception:      # noqa: BLE001 - no torch / no device: report the original status
+                return status
+            status = fn(*args)
+        return status
+    call.__name__ = getattr(fn, "__name__", "hwgat_call")
+    return call
+
+
 def load() -> ctypes.CDLL:
     """Load the library once.  Raises if it has not been built."""
     global _lib
@@ -129,6 +154,8 @@ def load() -> ctypes.CDLL:
         raise HwgatError(f"libhwgat_b200 ABI {got}, binding expects {ABI_VERSION}: rebuild the library")
     if os.environ.get("HWGAT_DETERMINISTIC", "0") not in ("", "0"):   # see ops.set_deterministic
         lib.hwgat_set_deterministic(1)
+    for name in _SCRATCH_CALLS:
+        setattr(lib, name, _with_scratch_retry(getattr(lib, name)))
     mode = os.environ.get("HWGAT_FP32", FP32_DEFAULT).lower()          # see ops.set_fp32_mode
     if mode not in FP32_MODES:
         raise HwgatError(f"HWGAT_FP32={mode!r}: expected one of {sorted(FP32_MODES)}")

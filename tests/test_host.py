@@ -236,3 +236,27 @@ def test_header_is_plain_c_and_links_from_a_c_host(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "c abi ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_scratch_failure_is_retried_once_after_releasing_the_torch_cache(monkeypatch):
+    """entry points that take stream-ordered scratch (the x3 planes) retry a HWGAT_ERR_WORKSPACE once, after
+    torch.cuda.empty_cache(): the pool cannot grow while the caching allocator holds the free memory"""
+    import torch
+    from sl_hwgat_b200 import _lib
+    calls, released = [], []
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: released.append(1))
+
+    def fake(*args):
+        calls.append(args)
+        return _lib.ERR_WORKSPACE if len(calls) == 1 else 0
+
+    wrapped = _lib._with_scratch_retry(fake)
+    assert wrapped(1, 2) == 0 and len(calls) == 2 and released == [1]
+    calls.clear(), released.clear()
+    always = _lib._with_scratch_retry(lambda *a: _lib.ERR_WORKSPACE)
+    assert always() == _lib.ERR_WORKSPACE and released == [1]            # one retry, then the error is reported
+    ok = _lib._with_scratch_retry(lambda *a: 0)
+    assert ok() == 0 and released == [1]
+    lib = _lib.load()
+    assert all(callable(getattr(lib, n)) for n in _lib._SCRATCH_CALLS)
