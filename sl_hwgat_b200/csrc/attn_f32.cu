@@ -160,13 +160,16 @@ HW_DEV void cp_async16(void* smem, const void* gmem) {
 HW_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // rows [0, 32) of one window / head: src_col = first of the 64 columns inside a row of `stride` floats
-HW_DEV void copy_window_rows(float (*dst)[kHd], const float* __restrict__ src, int stride, int src_col, const TileGeom& g,
-                             int tile, int w, int lane) {
+// (r0, r1: TileGeom::window_base - the token rows of the window's two frames)
+HW_DEV void copy_window_rows(float (*dst)[kHd], const float* __restrict__ src, int stride, int src_col, long long r0,
+                             long long r1, int lane) {
   const int half = lane >> 4, chunk = lane & 15;     // two rows per instruction, 16 lanes x 16 bytes per row
-#pragma unroll 4
-  for (int it = 0; it < kTok / 2; ++it) {
-    const int j = 2 * it + half;
-    cp_async16(&dst[j][chunk * 4], src + g.token_row(tile, w * kTok + j) * stride + src_col + chunk * 4);
+  const float* s0 = src + (r0 + half) * stride + src_col + chunk * 4;      // rows half, half + 2, ... of frame 0
+  const float* s1 = src + (r1 + half) * stride + src_col + chunk * 4;
+#pragma unroll
+  for (int it = 0; it < kWin / 2; ++it) {
+    cp_async16(&dst[2 * it + half][chunk * 4], s0 + (long long)(2 * it) * stride);
+    cp_async16(&dst[kWin + 2 * it + half][chunk * 4], s1 + (long long)(2 * it) * stride);
   }
 }
 
@@ -181,9 +184,11 @@ __global__ void __launch_bounds__(128) attn_core_fwd_f32_kernel(const float* __r
   const float scale = 0.125f;  // head_dim^-0.5, head_dim = 64
 
   // k, v rows of the window -> smem, asynchronously (the own q row is fetched meanwhile)
-  copy_window_rows(sm.k, qkv, d3, d + h * kHd, g, tile, w, lane);
-  copy_window_rows(sm.v, qkv, d3, 2 * d + h * kHd, g, tile, w, lane);
-  const long long my_row = g.token_row(tile, w * kTok + lane);
+  long long r0, r1;
+  g.window_base(tile, w, r0, r1);
+  copy_window_rows(sm.k, qkv, d3, d + h * kHd, r0, r1, lane);
+  copy_window_rows(sm.v, qkv, d3, 2 * d + h * kHd, r0, r1, lane);
+  const long long my_row = lane < kWin ? r0 + lane : r1 + lane - kWin;
   float q[kHd];
   {
     const float4* src = reinterpret_cast<const float4*>(qkv + my_row * d3 + h * kHd);
@@ -226,9 +231,11 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
   const int d = g.d, d3 = 3 * d;
   const float scale = 0.125f;
 
-  copy_window_rows(sm.a, qkv, d3, d + h * kHd, g, tile, w, lane);          // k rows
-  copy_window_rows(sm.b, qkv, d3, 2 * d + h * kHd, g, tile, w, lane);      // v rows
-  const long long my_row = g.token_row(tile, w * kTok + lane);
+  long long r0, r1;
+  g.window_base(tile, w, r0, r1);
+  copy_window_rows(sm.a, qkv, d3, d + h * kHd, r0, r1, lane);          // k rows
+  copy_window_rows(sm.b, qkv, d3, 2 * d + h * kHd, r0, r1, lane);      // v rows
+  const long long my_row = lane < kWin ? r0 + lane : r1 + lane - kWin;
   // ---- lane = query i: P row, dP row, dS row, dQ row
   // (own q / d_out rows come from global into registers: reading smem row `lane`
   //  from every lane would be a 32-way bank conflict)
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
   }
   // v is no longer needed: the d_out rows of the window replace it while dS and dQ are formed
   __syncwarp();
-  copy_window_rows(sm.b, d_out, d, h * kHd, g, tile, w, lane);
+  copy_window_rows(sm.b, d_out, d, h * kHd, r0, r1, lane);
 #pragma unroll
   for (int j = 0; j < kTok; ++j) {
     float dsv = ((live >> j) & 1u) ? s[j] * (dp[j] - dsum) : 0.f;
@@ -289,7 +296,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_core_bwd_f32_kernel(const fl
   }
   // ---- lane = key j: dK row = scale * sum_i dS[i][j] q_i ; dV row = sum_i P[i][j] g_i   (q rows replace k)
   __syncwarp();
-  copy_window_rows(sm.a, qkv, d3, h * kHd, g, tile, w, lane);
+  copy_window_rows(sm.a, qkv, d3, h * kHd, r0, r1, lane);
   cp_async_wait_all();
   __syncwarp();
   {

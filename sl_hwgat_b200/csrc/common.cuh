@@ -80,6 +80,24 @@ struct TileGeom {
     fr = fr >= F ? fr - F : fr;
     return ((long long)(b * F + fr) * K + kg * 64 + w * kWin + k);
   }
+  // token rows of window w of a tile: rows [0, 16) of the window are tokens r0 .. r0 + 15 (frame tp = 0), rows
+  // [16, 32) are r1 .. r1 + 15 (tp = 1) - the divisions of token_row once per window instead of once per row
+  HW_DEV void window_base(int tile, int w, long long& r0, long long& r1) const {
+    if (layout == HWGAT_LAYOUT_WINDOWS) {
+      r0 = (long long)tile * kTileTok + w * kTok;
+      r1 = r0 + kWin;
+      return;
+    }
+    const int b = tile / (f * kgroups);
+    const int r = tile - b * (f * kgroups);
+    const int fi = r / kgroups, kg = r - fi * kgroups;
+    int fr0 = 2 * fi + shift, fr1 = 2 * fi + 1 + shift;
+    fr0 = fr0 >= F ? fr0 - F : fr0;
+    fr1 = fr1 >= F ? fr1 - F : fr1;
+    const long long col = kg * 64 + w * kWin;
+    r0 = (long long)(b * F + fr0) * K + col;
+    r1 = (long long)(b * F + fr1) * K + col;
+  }
 };
 inline TileGeom make_geom(int F, int K, int d, int shift, int layout) {
   TileGeom g;
