@@ -253,3 +253,20 @@ def test_graphed_inference_matches_eager_and_is_batch1_safe():
     n0 = _lib.launch_count()
     fast(torch.rand(1, T, 64, 2, device="cuda"))
     assert _lib.launch_count() == n0                # replay: no host-side launches through the library
+
+
+def test_graphed_inference_fp32_path():
+    """the reference's per-sample evaluator runs without autocast (inference.py:95): the fp32 path (x3 GEMMs, whose
+    plane scratch is stream-ordered and becomes allocation nodes of the graph) captured and replayed"""
+    from sl_hwgat_b200.runtime import GraphedInference
+    T, classes = 16, 11
+    model, _, _ = build(T, classes)
+    model.eval()
+    fast = GraphedInference(model, autocast_dtype=None)
+    for B in (1, 2, 1):
+        x = torch.rand(B, T, 64, 2, device="cuda")
+        with torch.no_grad():
+            want = model(x)
+        got = fast(x)
+        assert got.dtype == torch.float32 and got.shape == (B, classes)
+        assert torch.equal(got, want)
